@@ -1,0 +1,195 @@
+/*
+ * b200r.h -- C-ABI of libb200robust.so: the B200 (sm_100a) implementation of RobustART's
+ * noise-injection + classification-eval hot path.
+ *
+ * Nothing like this exists in the reference (it is 100 % Python); each entry point names the
+ * reference Python function it replaces (path:line relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative B200R_E* code; b200r_last_error() gives
+ *     a thread-local human-readable message. Nothing throws, nothing owns caller memory.
+ *   - all pointers are DEVICE pointers unless the parameter name ends in _host.
+ *   - every launch takes an explicit CUDA stream (a CUstream / cudaStream_t handle passed as
+ *     void*; NULL = legacy default stream). No function synchronises unless documented.
+ *   - images are uint8 NHWC [n,h,w,3] (RobustART/noise/utils/add_noise_utils.py:27-31) or
+ *     float32 NCHW [n,3,h,w] in [0,1] (prototype/prototype/solver/benchmark_eval_adv.py:229-232).
+ */
+#ifndef B200R_H_
+#define B200R_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200R_OK 0
+#define B200R_EINVAL (-1)   /* bad argument (shape, id, severity, null pointer) */
+#define B200R_ECUDA (-2)    /* CUDA runtime / driver error, see b200r_last_error() */
+#define B200R_ENOSPC (-3)   /* workspace too small */
+#define B200R_ENOTSUP (-4)  /* valid request the library does not implement */
+
+typedef void* b200r_stream_t;
+
+const char* b200r_last_error(void);
+int b200r_version(void);
+/* number of SMs of the current device (148 on B200); grids are sized from it. */
+int b200r_sm_count(int* sms);
+
+/* ------------------------------------------------------------------------------------------
+ * ImageNet-C corruptions.  ids follow corruption_tuple
+ * (RobustART/noise/utils/imagenet_c/__init__.py:5-8).
+ * ------------------------------------------------------------------------------------------ */
+enum b200r_corruption {
+  B200R_GAUSSIAN_NOISE = 0,    /* corruptions.py:122-126 */
+  B200R_SHOT_NOISE = 1,        /* corruptions.py:129-133 */
+  B200R_IMPULSE_NOISE = 2,     /* corruptions.py:136-140 */
+  B200R_DEFOCUS_BLUR = 3,      /* corruptions.py:187-198 */
+  B200R_GLASS_BLUR = 4,        /* corruptions.py:169-184 */
+  B200R_MOTION_BLUR = 5,       /* corruptions.py:201-216 */
+  B200R_ZOOM_BLUR = 6,         /* corruptions.py:219-232 */
+  B200R_SNOW = 7,              /* corruptions.py:265-290 */
+  B200R_FROST = 8,             /* corruptions.py:244-262 */
+  B200R_FOG = 9,               /* corruptions.py:235-241 */
+  B200R_BRIGHTNESS = 10,       /* corruptions.py:353-361 */
+  B200R_CONTRAST = 11,         /* corruptions.py:345-350 */
+  B200R_ELASTIC_TRANSFORM = 12,/* corruptions.py:395-424 */
+  B200R_PIXELATE = 13,         /* corruptions.py:385-391 */
+  B200R_JPEG_COMPRESSION = 14, /* corruptions.py:375-382 */
+  B200R_SPECKLE_NOISE = 15,    /* corruptions.py:143-147 */
+  B200R_GAUSSIAN_BLUR = 16,    /* corruptions.py:162-166 */
+  B200R_SPATTER = 17,          /* corruptions.py:293-342 */
+  B200R_SATURATE = 18,         /* corruptions.py:364-372 */
+  B200R_NUM_CORRUPTIONS = 19
+};
+
+/* Scratch bytes b200r_corrupt_u8 needs for (id, severity, n, h, w). May be 0. */
+int b200r_corrupt_workspace_bytes(int corruption_id, int severity, int n, int h, int w,
+                                  size_t* bytes);
+
+/* Number of float32 values of externally supplied randomness (`ext_noise`) the corruption
+ * consumes for a batch of n images, 0 if the corruption is deterministic.  The layout per
+ * corruption is documented in DESIGN.md ("shared-draw parity mode"). */
+int b200r_corrupt_ext_noise_count(int corruption_id, int severity, int n, int h, int w,
+                                  size_t* count);
+
+/* corrupt(x, severity, corruption_number=id) for a whole batch
+ * (replaces the per-image loop add_noise_utils.py:27-31 + imagenet_c/__init__.py:13-35,
+ * including the final np.uint8 truncation).  in/out: uint8 NHWC; out may alias in.
+ * RNG: counter-based Philox4x32-10 keyed by `seed`; image i of this call uses stream
+ * `image_offset + i`, so results do not depend on batch split or world size.
+ * ext_noise: NULL (device RNG) or b200r_corrupt_ext_noise_count() floats of caller-drawn
+ * randomness, used instead of the device RNG (parity against the CPU oracle). */
+int b200r_corrupt_u8(int corruption_id, int severity, const uint8_t* in, uint8_t* out, int n, int h,
+                     int w, uint64_t seed, uint64_t image_offset, const float* ext_noise,
+                     void* workspace, size_t workspace_bytes, b200r_stream_t stream);
+
+/* Optional assets: frost textures (corruptions.py:250-260 reads frost{1..6}.{png,jpg}; the files
+ * are not in the reference repo).  rgb: device uint8 [th,tw,3]; slot in [0,6). */
+int b200r_set_frost_texture(int slot, const uint8_t* rgb, int th, int tw);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / normalisation (ToTensor+Normalize, imagenet_dataloader.py:74-80;
+ * normalize(x)/normalize(x,"inv"), benchmark_eval_adv.py:33-46).
+ * mean/std: host float[3].
+ * ------------------------------------------------------------------------------------------ */
+int b200r_u8nhwc_to_f32nchw(const uint8_t* in, float* out, int n, int h, int w,
+                            const float* mean_host, const float* std_host, b200r_stream_t stream);
+/* out = (x - mean)/std (inverse = 0), x*std + mean (inverse = 1), or x/std (inverse = 2: the
+ * input-gradient of normalisation), NCHW float32 */
+int b200r_normalize_f32nchw(const float* in, float* out, int n, int h, int w,
+                            const float* mean_host, const float* std_host, int inverse,
+                            b200r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Gradient-attack inner steps on float32 NCHW [n, chw] in [0,1].
+ * foolbox 3.3.1 gradient_descent_base.py (third-party, pinned requirements.txt:13) via
+ * RobustART/noise/utils/adv/attack.py:20-33; in-repo restatement
+ * prototype/prototype/solver/adv_cls_solver_train_pgd_new.py:84-103.
+ * ------------------------------------------------------------------------------------------ */
+/* x = x0 + U(-eps,eps), clipped to [0,1] when clip01 != 0 (foolbox clips, imfgsm_attack.py:73-74
+ * does not); u: optional caller-drawn uniforms in [0,1) [n*chw] */
+int b200r_random_start_linf(const float* x0, float* x, size_t n, size_t chw, float eps,
+                            uint64_t seed, uint64_t image_offset, const float* u, int clip01,
+                            b200r_stream_t stream);
+/* x = clip01(x0 + clip(x + alpha*sign(g) - x0, -eps, eps)); x updated in place. */
+int b200r_pgd_step_linf(float* x, const float* g, const float* x0, size_t n, size_t chw,
+                        float alpha, float eps, b200r_stream_t stream);
+/* x = x + alpha*g/max(||g||_2,1e-12); d = x - x0; x = clip01(x0 + d*min(1, eps/||d||_2)) per
+ * sample.  workspace: 2*n floats. */
+int b200r_pgd_step_l2(float* x, const float* g, const float* x0, size_t n, size_t chw, float alpha,
+                      float eps, float* workspace, b200r_stream_t stream);
+/* MI-FGSM step (Attacks/imfgsm_attack.py:85-90): m = decay*m + g/mean|g| (per sample);
+ * x = clip01(x0 + clip(x + step*sign(m) - x0, -eps, eps)).  workspace: n floats. */
+int b200r_mim_step_linf(float* x, float* momentum, const float* g, const float* x0, size_t n,
+                        size_t chw, float step, float eps, float decay, float* workspace,
+                        b200r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Loss / metrics on logits [n, classes] float32.
+ * ------------------------------------------------------------------------------------------ */
+/* softmax cross-entropy: loss[i] (nullable), dlogits = (softmax - onehot)*grad_scale (nullable)
+ * (F.cross_entropy; foolbox sums, MIM means -> grad_scale = 1 or 1/n) */
+int b200r_ce_loss_grad(const float* logits, const int64_t* labels, float* loss, float* dlogits,
+                       int n, int classes, float grad_scale, b200r_stream_t stream);
+/* scores = softmax(logits) (cls_solver.py:420) */
+int b200r_softmax(const float* logits, float* scores, int n, int classes, b200r_stream_t stream);
+/* counters[0] += #top1 hits, [1] += #top5 hits, [2] += n ; pred (nullable) = argmax
+ * (misc.py:441-455 accuracy(); imagenet_evaluator.py:49-67).  Tie-break: lowest index wins. */
+int b200r_topk_count(const float* logits, const int64_t* labels, int n, int classes,
+                     int64_t* counters, int64_t* pred, b200r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense contractions on the tcgen05 tensor cores ("split-bf16" activations: every fp32 tensor
+ * is stored as two bf16 planes hi = bf16(v), lo = bf16(v - hi); a product uses hi*hi + hi*lo +
+ * lo*hi with fp32 accumulation in TMEM).
+ * ------------------------------------------------------------------------------------------ */
+enum b200r_act { B200R_ACT_NONE = 0, B200R_ACT_RELU = 1, B200R_ACT_RELU6 = 2,
+                 B200R_ACT_GELU_TANH = 3, B200R_ACT_GELU_ERF = 4, B200R_ACT_SWISH = 5,
+                 B200R_ACT_TANH = 6 };
+
+/* split a float32 tensor into hi/lo bf16 planes: planes[0:count] = hi, planes[count:2count] = lo */
+int b200r_split_f32(const float* in, uint16_t* planes, size_t count, b200r_stream_t stream);
+int b200r_merge_f32(const uint16_t* planes, float* out, size_t count, b200r_stream_t stream);
+
+/* Implicit-GEMM convolution, NHWC, replaces nn.Conv2d(bias=False)+BatchNorm2d(eval)+act(+residual)
+ * (resnet_official.py:71-140,330-346).
+ *   x      : split planes of [n, h, w, cin]           (cin % 64 == 0)
+ *   wgt    : split planes of [cout, kh, kw, cin]      (cout % 64 == 0)
+ *   scale, bias : float32 [cout] (folded BN; nullable = 1 / 0)
+ *   res    : split planes of [n, ho, wo, cout] added before the activation (nullable)
+ *   y      : split planes of [n, ho, wo, cout] (nullable if y_f32 given)
+ *   y_f32  : float32 [n, ho, wo, cout] (nullable)
+ *   passes : 3 = hi*hi+hi*lo+lo*hi (fp32-faithful), 1 = hi*hi only (plain bf16)
+ */
+int b200r_conv2d_nhwc(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias,
+                      const uint16_t* res, uint16_t* y, float* y_f32, int n, int h, int w, int cin,
+                      int cout, int kh, int kw, int stride, int pad, int act, int passes,
+                      b200r_stream_t stream);
+
+/* y[m, nout] = act(x[m,k] . wgt[nout,k]^T * scale + bias (+res)) -- nn.Linear (fc heads, ViT/Mixer
+ * MLPs).  k % 64 == 0; nout arbitrary (tiles are masked). */
+int b200r_linear(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias,
+                 const uint16_t* res, uint16_t* y, float* y_f32, int m, int k, int nout, int act,
+                 int passes, b200r_stream_t stream);
+
+/* 7x7/s2 stem patches (resnet_official.py:221-224): u8 NHWC image -> normalised, im2col'd split
+ * planes [n*ho*wo, kpad] with kpad = 192 (7*7*3 = 147 zero-padded), column = (ky*7+kx)*3+c. */
+int b200r_stem_im2col_u8(const uint8_t* img, uint16_t* planes, int n, int h, int w,
+                         const float* mean_host, const float* std_host, b200r_stream_t stream);
+/* same from float32 NCHW in [0,1] (the attack path) */
+int b200r_stem_im2col_f32(const float* img, uint16_t* planes, int n, int h, int w,
+                          const float* mean_host, const float* std_host, b200r_stream_t stream);
+
+/* MaxPool2d(3, 2, 1) on split planes NHWC (resnet_official.py:227) */
+int b200r_maxpool3x3s2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int c,
+                            b200r_stream_t stream);
+/* AdaptiveAvgPool2d(1) on split planes NHWC -> split planes [n, c] (resnet_official.py:238) */
+int b200r_global_avgpool_nhwc(const uint16_t* x, uint16_t* y, int n, int hw, int c,
+                              b200r_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200R_H_ */

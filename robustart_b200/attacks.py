@@ -1,0 +1,148 @@
+"""Gradient attacks of RobustART.noise on B200: same call signatures as
+RobustART/noise/utils/adv/attack.py:20-42, same update rules as foolbox 3.3.1 (third-party, pinned in
+the reference's requirements.txt:13) and the vendored MI-FGSM (Attacks/imfgsm_attack.py:62-93).
+
+The model is whatever the caller passes (the reference hands in arbitrary nn.Modules); its forward
+and input-gradient run through torch.autograd.  Everything around it -- random start, softmax-CE
+gradient, sign/normalise/step/project/clip, (de)normalisation -- is one fused sm_100a kernel each
+(robustart_b200/csrc/attack_steps.cu, loss_metrics.cu).  Unlike eagerpy's loss.backward() only the
+input gradient is requested, so no weight gradients are computed.
+"""
+from __future__ import annotations
+
+import itertools
+from typing import Optional
+
+import torch
+
+from . import ops
+
+_call_counter = itertools.count()
+
+
+class _NormalizeFn(torch.autograd.Function):
+    """(x - mean)/std with both directions on our kernels (b200r_normalize_f32nchw)."""
+
+    @staticmethod
+    def forward(ctx, x, mean, std):
+        ctx.ms = (mean, std)
+        return ops.normalize(x.contiguous(), "normal", mean, std)
+
+    @staticmethod
+    def backward(ctx, g):
+        mean, std = ctx.ms
+        return ops.normalize(g.contiguous(), "grad", mean, std), None, None
+
+
+class PyTorchModel:
+    """Minimal stand-in for foolbox.PyTorchModel as the solvers build it
+    (benchmark_eval_adv.py:198-207): inputs in `bounds`, `preprocessing` = dict(mean, std, axis=-3).
+    A real foolbox model object works too: the attacks only need `model(x) -> logits` and `.bounds`."""
+
+    def __init__(self, model, bounds=(0, 1), device=None, preprocessing=None):
+        self.model = model
+        self.bounds = tuple(bounds)
+        self.device = device
+        self.preprocessing = preprocessing
+        if preprocessing is not None:
+            assert preprocessing.get("axis", -3) == -3, "only channel-first preprocessing is supported"
+            self._mean = tuple(float(v) for v in preprocessing["mean"])
+            self._std = tuple(float(v) for v in preprocessing["std"])
+
+    def __call__(self, x):
+        if self.preprocessing is not None:
+            x = _NormalizeFn.apply(x, self._mean, self._std)
+        return self.model(x)
+
+
+def _bounds01(f_model):
+    b = getattr(f_model, "bounds", (0, 1))
+    lo, hi = float(b[0]), float(b[1])
+    if (lo, hi) != (0.0, 1.0):
+        raise NotImplementedError("only model bounds (0, 1) are supported, got %r" % (b,))
+
+
+def _input_grad(f_model, x, label, grad_scale=1.0):
+    """d/dx sum_i CE(f(x)_i, y_i) * grad_scale, using our CE kernel for dL/dlogits."""
+    x = x.detach().requires_grad_(True)
+    with torch.enable_grad():
+        logits = f_model(x)
+    if hasattr(logits, "raw"):  # eagerpy tensor from a real foolbox model
+        logits = logits.raw
+    _, dlogits = ops.ce_loss_grad(logits.detach().float().contiguous(), label, grad_scale)
+    (g,) = torch.autograd.grad(logits, x, grad_outputs=dlogits.to(logits.dtype))
+    return g.contiguous()
+
+
+def _prep(input, label):
+    if not input.is_cuda:
+        raise TypeError("adversarial noise needs CUDA tensors (the reference is GPU-only here too)")
+    x0 = input.detach().to(torch.float32).contiguous()
+    y = label.detach().to(torch.int64).view(-1).contiguous()
+    return x0, y
+
+
+def pgd_linf(input, label, f_model, eps, rel_stepsize, steps, *, random_start=True, seed: Optional[int] = None,
+             start_uniform: Optional[torch.Tensor] = None):
+    """foolbox LinfProjectedGradientDescentAttack(rel_stepsize, steps)(f_model, input, label, epsilons=eps)[0]
+    (attack.py:20-23): raw adversarials."""
+    _bounds01(f_model)
+    x0, y = _prep(input, label)
+    alpha = float(rel_stepsize) * float(eps)
+    if random_start:
+        s = next(_call_counter) if seed is None else seed
+        x = ops.random_start_linf(x0, float(eps), seed=s, u=start_uniform, clip01=True)
+    else:
+        x = x0.clone()
+    for _ in range(int(steps)):
+        g = _input_grad(f_model, x, y)
+        ops.pgd_step_linf_(x, g, x0, alpha, float(eps))
+    return x
+
+
+def fgsm(input, label, f_model, eps):
+    """foolbox LinfFastGradientAttack(): one step of size eps, no random start (attack.py:30-33)."""
+    return pgd_linf(input, label, f_model, eps, rel_stepsize=1.0, steps=1, random_start=False)
+
+
+def pgd_l2(input, label, f_model, eps, rel_stepsize, steps, *, random_start=True, seed: Optional[int] = None,
+           start_direction: Optional[torch.Tensor] = None):
+    """foolbox L2ProjectedGradientDescentAttack (attack.py:25-28).  Random start: a uniform draw from
+    the eps-ball (foolbox uniform_n_balls: the first n coordinates of a uniform point on the
+    (n+1)-sphere); the n+1 normals come from torch's generator (plumbing, once per call)."""
+    _bounds01(f_model)
+    x0, y = _prep(input, label)
+    alpha = float(rel_stepsize) * float(eps)
+    n = x0.shape[0]
+    if random_start:
+        if start_direction is None:
+            gen = None
+            if seed is not None:
+                gen = torch.Generator(device=x0.device)
+                gen.manual_seed(seed)
+            z = torch.randn(n, x0[0].numel() + 1, device=x0.device, generator=gen)
+            start_direction = (z / z.norm(dim=1, keepdim=True))[:, :-1].reshape(x0.shape)
+        x = (x0 + float(eps) * start_direction).clamp_(0, 1).contiguous()
+    else:
+        x = x0.clone()
+    for _ in range(int(steps)):
+        g = _input_grad(f_model, x, y)
+        ops.pgd_step_l2_(x, g, x0, alpha, float(eps))
+    return x
+
+
+def mim_linf(input, label, model, eps, num_steps, step_size, decay_factor, *, seed: Optional[int] = None,
+             start_uniform: Optional[torch.Tensor] = None):
+    """_mim_whitebox (imfgsm_attack.py:62-93): `model` takes NORMALISED input; CE *mean* loss; the random
+    start is not clipped to [0,1]; the two diagnostic forwards (err, err_pgd) are not needed for the
+    result and are skipped."""
+    x0, y = _prep(input, label)
+    n = x0.shape[0]
+    s = next(_call_counter) if seed is None else seed
+    x = ops.random_start_linf(x0, float(eps), seed=s, u=start_uniform, clip01=False)
+    momentum = torch.zeros_like(x0)
+    f_model = PyTorchModel(model, preprocessing=dict(mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, axis=-3))
+    for _ in range(int(num_steps)):
+        g = _input_grad(f_model, x, y, grad_scale=1.0 / n)
+        ops.mim_step_linf_(x, momentum, g, x0, float(step_size), float(eps), float(decay_factor))
+    return x

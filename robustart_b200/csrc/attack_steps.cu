@@ -1,0 +1,321 @@
+// Fused elementwise kernels of the gradient attacks + layout/normalisation (all HBM-bound).
+//   foolbox 3.3.1 gradient_descent_base.py run(): x += a*normalize(g); x = project(x,x0,eps);
+//   x = clip(x, 0, 1)   (called from RobustART/noise/utils/adv/attack.py:20-33)
+//   MI-FGSM: RobustART/noise/utils/adv/Attacks/imfgsm_attack.py:85-90
+//   normalize(): prototype/prototype/solver/benchmark_eval_adv.py:33-46
+// Algorithmic traffic per image per step (fp32, 3x224x224): Linf read x,g,x0 + write x =
+// 4 * 602 112 B; L2 / MIM add one extra read of g for the per-sample norm.
+#include "common.cuh"
+#include "corrupt.cuh"
+
+namespace {
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float sgn(float g) { return (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f); }
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// ---- u8 NHWC -> float NCHW, (x/255 - mean)/std -----------------------------------------------
+struct Norm3 { float mean[3], inv_std[3], std[3]; };
+
+__global__ void __launch_bounds__(kThreads) u8nhwc_to_f32nchw_kernel(const uint4* __restrict__ in,
+                                                                      float* __restrict__ out,
+                                                                      uint32_t groups_per_image,
+                                                                      uint32_t hw, Norm3 nm) {
+  const uint32_t img = blockIdx.y;
+  const uint32_t gi = blockIdx.x * kThreads + threadIdx.x;
+  if (gi >= groups_per_image) return;
+  const uint4* p = in + ((size_t)img * groups_per_image + gi) * 3;
+  uint4 a = ld_stream_u4(p), b = ld_stream_u4(p + 1), c = ld_stream_u4(p + 2);
+  uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+  float v[3][16];
+#pragma unroll
+  for (int byte = 0; byte < 48; ++byte) {
+    const int ch = byte % 3, px = byte / 3;
+    float x = (float)((w[byte >> 2] >> (8 * (byte & 3))) & 0xFFu);
+    // torchvision ToTensor: x/255 (true division), Normalize: (t - mean)/std
+    v[ch][px] = (__fdiv_rn(x, 255.0f) - nm.mean[ch]) / nm.std[ch];
+  }
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float* o = out + ((size_t)img * 3 + ch) * hw + (size_t)gi * 16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      st_stream_f4(o + 4 * q, make_float4(v[ch][4 * q], v[ch][4 * q + 1], v[ch][4 * q + 2], v[ch][4 * q + 3]));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) normalize_kernel(const float4* __restrict__ in,
+                                                              float4* __restrict__ out, uint32_t hw4,
+                                                              Norm3 nm, int inverse) {
+  const uint32_t plane = blockIdx.y;  // n*3 + c
+  const int ch = plane % 3;
+  const float m = nm.mean[ch], s = nm.std[ch];
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < hw4; i += gridDim.x * kThreads) {
+    float4 v = ld_stream_f4(in + (size_t)plane * hw4 + i);
+    if (inverse == 2) {
+      v.x = v.x / s; v.y = v.y / s; v.z = v.z / s; v.w = v.w / s;
+    } else if (inverse) {  // x * std + mean  (no fma contraction: match torch's two roundings)
+      v.x = __fadd_rn(__fmul_rn(v.x, s), m); v.y = __fadd_rn(__fmul_rn(v.y, s), m);
+      v.z = __fadd_rn(__fmul_rn(v.z, s), m); v.w = __fadd_rn(__fmul_rn(v.w, s), m);
+    } else {
+      v.x = (v.x - m) / s; v.y = (v.y - m) / s; v.z = (v.z - m) / s; v.w = (v.w - m) / s;
+    }
+    st_stream_f4(out + (size_t)plane * hw4 + i, v);
+  }
+}
+
+// ---- Linf ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) random_start_linf_kernel(const float4* __restrict__ x0,
+                                                                      float4* __restrict__ x,
+                                                                      const float4* __restrict__ u,
+                                                                      size_t chw4, float eps, uint32_t k0,
+                                                                      uint32_t k1, uint64_t image_offset,
+                                                                      int clip01) {
+  const size_t img = blockIdx.y;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < chw4; i += (size_t)gridDim.x * kThreads) {
+    float4 a = ld_stream_f4(x0 + img * chw4 + i), r;
+    if (u) {
+      r = ld_stream_f4(u + img * chw4 + i);
+    } else {
+      uint4 p = philox4x32_10(rng_counter((uint32_t)i, RNG_PGD, 0, image_offset + img), k0, k1);
+      r = make_float4(u32_to_unit(p.x), u32_to_unit(p.y), u32_to_unit(p.z), u32_to_unit(p.w));
+    }
+    const float two_eps = 2.f * eps;
+    // uniform(-eps, eps) = (hi - lo)*u + lo ; then x0 + that ; then clip to [0,1]
+    a.x = __fadd_rn(a.x, __fadd_rn(__fmul_rn(two_eps, r.x), -eps));
+    a.y = __fadd_rn(a.y, __fadd_rn(__fmul_rn(two_eps, r.y), -eps));
+    a.z = __fadd_rn(a.z, __fadd_rn(__fmul_rn(two_eps, r.z), -eps));
+    a.w = __fadd_rn(a.w, __fadd_rn(__fmul_rn(two_eps, r.w), -eps));
+    if (clip01) {
+      a.x = clampf(a.x, 0.f, 1.f); a.y = clampf(a.y, 0.f, 1.f);
+      a.z = clampf(a.z, 0.f, 1.f); a.w = clampf(a.w, 0.f, 1.f);
+    }
+    st_stream_f4(x + img * chw4 + i, a);
+  }
+}
+
+__device__ __forceinline__ float linf_update(float x, float s_alpha, float x0, float eps) {
+  float t = __fadd_rn(x, s_alpha);                   // x + alpha*sign(g)
+  float d = clampf(__fsub_rn(t, x0), -eps, eps);     // clip(x - x0, -eps, eps)
+  return clampf(__fadd_rn(x0, d), 0.f, 1.f);         // clip(x0 + d, 0, 1)
+}
+
+__global__ void __launch_bounds__(kThreads) pgd_step_linf_kernel(float4* __restrict__ x,
+                                                                  const float4* __restrict__ g,
+                                                                  const float4* __restrict__ x0,
+                                                                  size_t total4, float alpha, float eps) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total4; i += (size_t)gridDim.x * kThreads) {
+    float4 xv = x[i];
+    float4 gv = ld_stream_f4(g + i), ov = ld_stream_f4(x0 + i);
+    xv.x = linf_update(xv.x, alpha * sgn(gv.x), ov.x, eps);
+    xv.y = linf_update(xv.y, alpha * sgn(gv.y), ov.y, eps);
+    xv.z = linf_update(xv.z, alpha * sgn(gv.z), ov.z, eps);
+    xv.w = linf_update(xv.w, alpha * sgn(gv.w), ov.w, eps);
+    x[i] = xv;
+  }
+}
+
+// ---- per-sample reductions -------------------------------------------------------------------
+// mode 0: sum g^2 ; mode 1: sum |g|.  grid (slices, n); atomicAdd into acc[n] (pre-zeroed)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) sample_reduce_kernel(const float4* __restrict__ g,
+                                                                  float* __restrict__ acc, size_t chw4) {
+  const size_t img = blockIdx.y;
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < chw4; i += (size_t)gridDim.x * kThreads) {
+    float4 v = __ldg(g + img * chw4 + i);
+    if (MODE == 0) s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    else s += fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w);
+  }
+  s = warp_sum(s);
+  __shared__ float sb[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) t += sb[i];
+    atomicAdd(&acc[img], t);
+  }
+}
+
+// L2 phase 2: x = x + alpha * g / max(||g||,1e-12); accumulate ||x - x0||^2
+__global__ void __launch_bounds__(kThreads) l2_ascent_kernel(float4* __restrict__ x,
+                                                              const float4* __restrict__ g,
+                                                              const float4* __restrict__ x0,
+                                                              const float* __restrict__ gnorm2,
+                                                              float* __restrict__ dnorm2, size_t chw4,
+                                                              float alpha) {
+  const size_t img = blockIdx.y;
+  const float f = alpha * (1.0f / fmaxf(sqrtf(gnorm2[img]), 1e-12f));
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < chw4; i += (size_t)gridDim.x * kThreads) {
+    const size_t k = img * chw4 + i;
+    float4 xv = x[k], gv = ld_stream_f4(g + k), ov = __ldg(x0 + k);
+    xv.x = __fadd_rn(xv.x, __fmul_rn(f, gv.x)); xv.y = __fadd_rn(xv.y, __fmul_rn(f, gv.y));
+    xv.z = __fadd_rn(xv.z, __fmul_rn(f, gv.z)); xv.w = __fadd_rn(xv.w, __fmul_rn(f, gv.w));
+    float dx = xv.x - ov.x, dy = xv.y - ov.y, dz = xv.z - ov.z, dw = xv.w - ov.w;
+    s += dx * dx + dy * dy + dz * dz + dw * dw;
+    x[k] = xv;
+  }
+  s = warp_sum(s);
+  __shared__ float sb[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) t += sb[i];
+    atomicAdd(&dnorm2[img], t);
+  }
+}
+
+// L2 phase 3: x = clip01(x0 + (x - x0) * min(1, eps / max(||d||,1e-12)))
+__global__ void __launch_bounds__(kThreads) l2_project_kernel(float4* __restrict__ x,
+                                                               const float4* __restrict__ x0,
+                                                               const float* __restrict__ dnorm2,
+                                                               size_t chw4, float eps) {
+  const size_t img = blockIdx.y;
+  const float f = fminf(1.0f, eps / fmaxf(sqrtf(dnorm2[img]), 1e-12f));
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < chw4; i += (size_t)gridDim.x * kThreads) {
+    const size_t k = img * chw4 + i;
+    float4 xv = x[k], ov = ld_stream_f4(x0 + k);
+    xv.x = clampf(__fadd_rn(ov.x, __fmul_rn(__fsub_rn(xv.x, ov.x), f)), 0.f, 1.f);
+    xv.y = clampf(__fadd_rn(ov.y, __fmul_rn(__fsub_rn(xv.y, ov.y), f)), 0.f, 1.f);
+    xv.z = clampf(__fadd_rn(ov.z, __fmul_rn(__fsub_rn(xv.z, ov.z), f)), 0.f, 1.f);
+    xv.w = clampf(__fadd_rn(ov.w, __fmul_rn(__fsub_rn(xv.w, ov.w), f)), 0.f, 1.f);
+    x[k] = xv;
+  }
+}
+
+// MIM phase 2: m = decay*m + g/mean|g| ; x = linf_update(x, step*sign(m), x0, eps)
+__global__ void __launch_bounds__(kThreads) mim_apply_kernel(float4* __restrict__ x,
+                                                              float4* __restrict__ mom,
+                                                              const float4* __restrict__ g,
+                                                              const float4* __restrict__ x0,
+                                                              const float* __restrict__ abs_sum,
+                                                              size_t chw4, float step, float eps,
+                                                              float decay) {
+  const size_t img = blockIdx.y;
+  const float mean_abs = abs_sum[img] / (float)(chw4 * 4);
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < chw4; i += (size_t)gridDim.x * kThreads) {
+    const size_t k = img * chw4 + i;
+    float4 xv = x[k], mv = mom[k], gv = ld_stream_f4(g + k), ov = ld_stream_f4(x0 + k);
+    mv.x = __fadd_rn(__fmul_rn(decay, mv.x), gv.x / mean_abs);
+    mv.y = __fadd_rn(__fmul_rn(decay, mv.y), gv.y / mean_abs);
+    mv.z = __fadd_rn(__fmul_rn(decay, mv.z), gv.z / mean_abs);
+    mv.w = __fadd_rn(__fmul_rn(decay, mv.w), gv.w / mean_abs);
+    xv.x = linf_update(xv.x, step * sgn(mv.x), ov.x, eps);
+    xv.y = linf_update(xv.y, step * sgn(mv.y), ov.y, eps);
+    xv.z = linf_update(xv.z, step * sgn(mv.z), ov.z, eps);
+    xv.w = linf_update(xv.w, step * sgn(mv.w), ov.w, eps);
+    mom[k] = mv;
+    x[k] = xv;
+  }
+}
+
+Norm3 make_norm(const float* mean, const float* std) {
+  Norm3 n;
+  for (int i = 0; i < 3; ++i) { n.mean[i] = mean[i]; n.std[i] = std[i]; n.inv_std[i] = 1.f / std[i]; }
+  return n;
+}
+
+inline unsigned slices_for(size_t chw4, size_t n) {
+  // enough CTAs to fill 148 SMs x 8 resident CTAs even for small n, capped by the work
+  size_t per = (chw4 + kThreads - 1) / kThreads;
+  size_t want = (size_t)b200r_num_sms() * 8 / (n ? n : 1) + 1;
+  return (unsigned)(per < want ? per : want);
+}
+}  // namespace
+
+extern "C" {
+
+int b200r_u8nhwc_to_f32nchw(const uint8_t* in, float* out, int n, int h, int w, const float* mean_host,
+                            const float* std_host, b200r_stream_t stream) {
+  B200R_CHECK_ARG(in && out && mean_host && std_host, "null pointer");
+  B200R_CHECK_ARG(n >= 0 && h > 0 && w > 0 && (h * w) % 16 == 0, "h*w must be a multiple of 16");
+  if (n == 0) return B200R_OK;
+  const uint32_t g48 = (uint32_t)(h * w) / 16;
+  dim3 grid((g48 + kThreads - 1) / kThreads, n);
+  u8nhwc_to_f32nchw_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(in), out, g48, (uint32_t)(h * w), make_norm(mean_host, std_host));
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_normalize_f32nchw(const float* in, float* out, int n, int h, int w, const float* mean_host,
+                            const float* std_host, int inverse, b200r_stream_t stream) {
+  B200R_CHECK_ARG(in && out && mean_host && std_host, "null pointer");
+  B200R_CHECK_ARG(n >= 0 && h > 0 && w > 0 && (h * w) % 4 == 0, "h*w must be a multiple of 4");
+  if (n == 0) return B200R_OK;
+  const uint32_t hw4 = (uint32_t)(h * w) / 4;
+  dim3 grid(min((hw4 + kThreads - 1) / kThreads, 64u), n * 3);
+  normalize_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(in),
+                                                             reinterpret_cast<float4*>(out), hw4,
+                                                             make_norm(mean_host, std_host), inverse);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_random_start_linf(const float* x0, float* x, size_t n, size_t chw, float eps, uint64_t seed,
+                            uint64_t image_offset, const float* u, int clip01, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x0 && x, "null pointer");
+  B200R_CHECK_ARG(chw % 4 == 0 && n < 65536, "chw must be a multiple of 4 and n < 65536");
+  if (n == 0) return B200R_OK;
+  dim3 grid(slices_for(chw / 4, n), (unsigned)n);
+  random_start_linf_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(x0), reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(u),
+      chw / 4, eps, (uint32_t)seed, (uint32_t)(seed >> 32), image_offset, clip01);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_pgd_step_linf(float* x, const float* g, const float* x0, size_t n, size_t chw, float alpha,
+                        float eps, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && g && x0, "null pointer");
+  B200R_CHECK_ARG((n * chw) % 4 == 0, "n*chw must be a multiple of 4");
+  if (n == 0) return B200R_OK;
+  const size_t total4 = n * chw / 4;
+  size_t blocks = (total4 + kThreads - 1) / kThreads;
+  size_t cap = (size_t)b200r_num_sms() * 16;
+  pgd_step_linf_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(x0),
+      total4, alpha, eps);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_pgd_step_l2(float* x, const float* g, const float* x0, size_t n, size_t chw, float alpha,
+                      float eps, float* workspace, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && g && x0 && workspace, "null pointer");
+  B200R_CHECK_ARG(chw % 4 == 0 && n < 65536, "chw must be a multiple of 4 and n < 65536");
+  if (n == 0) return B200R_OK;
+  cudaStream_t s = as_stream(stream);
+  B200R_CUDA(cudaMemsetAsync(workspace, 0, 2 * n * sizeof(float), s));
+  dim3 grid(slices_for(chw / 4, n), (unsigned)n);
+  sample_reduce_kernel<0><<<grid, kThreads, 0, s>>>(reinterpret_cast<const float4*>(g), workspace, chw / 4);
+  l2_ascent_kernel<<<grid, kThreads, 0, s>>>(reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(g),
+                                             reinterpret_cast<const float4*>(x0), workspace, workspace + n,
+                                             chw / 4, alpha);
+  l2_project_kernel<<<grid, kThreads, 0, s>>>(reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(x0),
+                                              workspace + n, chw / 4, eps);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_mim_step_linf(float* x, float* momentum, const float* g, const float* x0, size_t n, size_t chw,
+                        float step, float eps, float decay, float* workspace, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && momentum && g && x0 && workspace, "null pointer");
+  B200R_CHECK_ARG(chw % 4 == 0 && n < 65536, "chw must be a multiple of 4 and n < 65536");
+  if (n == 0) return B200R_OK;
+  cudaStream_t s = as_stream(stream);
+  B200R_CUDA(cudaMemsetAsync(workspace, 0, n * sizeof(float), s));
+  dim3 grid(slices_for(chw / 4, n), (unsigned)n);
+  sample_reduce_kernel<1><<<grid, kThreads, 0, s>>>(reinterpret_cast<const float4*>(g), workspace, chw / 4);
+  mim_apply_kernel<<<grid, kThreads, 0, s>>>(reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(momentum),
+                                             reinterpret_cast<const float4*>(g),
+                                             reinterpret_cast<const float4*>(x0), workspace, chw / 4, step, eps,
+                                             decay);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+}  // extern "C"

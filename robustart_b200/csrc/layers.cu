@@ -1,0 +1,219 @@
+// Memory-bound layers around the tensor-core contractions, all on "split-bf16" activations
+// (planes[0:count] = hi = bf16(v), planes[count:2*count] = lo = bf16(v - hi)), NHWC.
+//   split / merge                       : format conversion
+//   stem im2col                         : 7x7/s2/p3 patches of the input image (resnet_official.py:221-224)
+//   maxpool 3x3 s2 p1                   : resnet_official.py:227
+//   global average pool                 : resnet_official.py:238
+#include "common.cuh"
+
+namespace {
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint32_t pack_bf16x2(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }
+
+__global__ void __launch_bounds__(kThreads) split_kernel(const float4* __restrict__ in, uint2* __restrict__ hi,
+                                                          uint2* __restrict__ lo, size_t count4) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < count4; i += (size_t)gridDim.x * kThreads) {
+    float4 v = ld_stream_f4(in + i);
+    uint16_t h[4], l[4];
+    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
+    split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+    hi[i] = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+    lo[i] = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) merge_kernel(const uint2* __restrict__ hi, const uint2* __restrict__ lo,
+                                                          float4* __restrict__ out, size_t count4) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < count4; i += (size_t)gridDim.x * kThreads) {
+    uint2 h = hi[i], l = lo[i];
+    float4 v;
+    v.x = bf16_bits_to_f32(h.x & 0xFFFF) + bf16_bits_to_f32(l.x & 0xFFFF);
+    v.y = bf16_bits_to_f32(h.x >> 16) + bf16_bits_to_f32(l.x >> 16);
+    v.z = bf16_bits_to_f32(h.y & 0xFFFF) + bf16_bits_to_f32(l.y & 0xFFFF);
+    v.w = bf16_bits_to_f32(h.y >> 16) + bf16_bits_to_f32(l.y >> 16);
+    out[i] = v;
+  }
+}
+
+// ---- stem im2col ------------------------------------------------------------------------------
+// one thread per (output pixel, 8-column chunk): kpad = 192 columns = 24 chunks; column = (ky*7+kx)*3+c
+constexpr int kStemK = 192;
+struct Norm3 { float mean[3], std[3]; };
+
+template <bool U8>
+__global__ void __launch_bounds__(kThreads) stem_im2col_kernel(const void* __restrict__ img,
+                                                                uint4* __restrict__ hi, uint4* __restrict__ lo,
+                                                                int n, int h, int w, int ho, int wo, Norm3 nm) {
+  const size_t total = (size_t)n * ho * wo * (kStemK / 8);
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int chunk = (int)(t % (kStemK / 8));
+    const size_t pix = t / (kStemK / 8);
+    const int ox = (int)(pix % wo);
+    const int oy = (int)((pix / wo) % ho);
+    const int im = (int)(pix / ((size_t)wo * ho));
+    uint16_t hh[8], ll[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = chunk * 8 + j;
+      float v = 0.f;
+      if (col < 147) {
+        const int tap = col / 3, c = col - tap * 3;
+        const int ky = tap / 7, kx = tap - ky * 7;
+        const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+          float x;
+          if (U8) x = __fdiv_rn((float)static_cast<const uint8_t*>(img)[(((size_t)im * h + iy) * w + ix) * 3 + c], 255.0f);
+          else x = static_cast<const float*>(img)[(((size_t)im * 3 + c) * h + iy) * w + ix];
+          v = (x - nm.mean[c]) / nm.std[c];
+        }
+      }
+      split_bf16(v, hh[j], ll[j]);
+    }
+    hi[t] = make_uint4(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]), pack_bf16x2(hh[4], hh[5]), pack_bf16x2(hh[6], hh[7]));
+    lo[t] = make_uint4(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]), pack_bf16x2(ll[4], ll[5]), pack_bf16x2(ll[6], ll[7]));
+  }
+}
+
+// ---- maxpool 3x3 s2 p1, 8 channels per thread ---------------------------------------------------
+__global__ void __launch_bounds__(kThreads) maxpool_kernel(const uint4* __restrict__ xhi, const uint4* __restrict__ xlo,
+                                                            uint4* __restrict__ yhi, uint4* __restrict__ ylo,
+                                                            int n, int h, int w, int c8, int ho, int wo) {
+  const size_t total = (size_t)n * ho * wo * c8;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int cc = (int)(t % c8);
+    const size_t pix = t / c8;
+    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), im = (int)(pix / ((size_t)wo * ho));
+    float best[8];
+    uint32_t bh[8], bl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bh[j] = 0xFF80u; bl[j] = 0; }
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= h) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= w) continue;
+        const size_t idx = (((size_t)im * h + iy) * w + ix) * c8 + cc;
+        uint4 a = __ldg(xhi + idx), b = __ldg(xlo + idx);
+        uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t hb = (aw[j >> 1] >> (16 * (j & 1))) & 0xFFFF, lb = (bw[j >> 1] >> (16 * (j & 1))) & 0xFFFF;
+          float v = bf16_bits_to_f32((uint16_t)hb) + bf16_bits_to_f32((uint16_t)lb);
+          if (v > best[j]) { best[j] = v; bh[j] = hb; bl[j] = lb; }
+        }
+      }
+    }
+    yhi[t] = make_uint4(bh[0] | (bh[1] << 16), bh[2] | (bh[3] << 16), bh[4] | (bh[5] << 16), bh[6] | (bh[7] << 16));
+    ylo[t] = make_uint4(bl[0] | (bl[1] << 16), bl[2] | (bl[3] << 16), bl[4] | (bl[5] << 16), bl[6] | (bl[7] << 16));
+  }
+}
+
+// ---- global average pool: one warp per (image, 8-channel chunk) -----------------------------------
+__global__ void __launch_bounds__(kThreads) avgpool_kernel(const uint4* __restrict__ xhi, const uint4* __restrict__ xlo,
+                                                            uint4* __restrict__ yhi, uint4* __restrict__ ylo,
+                                                            int n, int hw, int c8) {
+  const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n * c8) return;
+  const int im = warp / c8, cc = warp - im * c8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = lane; p < hw; p += 32) {
+    const size_t idx = ((size_t)im * hw + p) * c8 + cc;
+    uint4 a = __ldg(xhi + idx), b = __ldg(xlo + idx);
+    uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      s[j] += bf16_bits_to_f32((uint16_t)(aw[j >> 1] >> (16 * (j & 1)))) + bf16_bits_to_f32((uint16_t)(bw[j >> 1] >> (16 * (j & 1))));
+  }
+  uint16_t hh[8], ll[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = warp_sum(s[j]) / (float)hw;
+    split_bf16(v, hh[j], ll[j]);
+  }
+  if (lane == 0) {
+    yhi[warp] = make_uint4(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]), pack_bf16x2(hh[4], hh[5]), pack_bf16x2(hh[6], hh[7]));
+    ylo[warp] = make_uint4(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]), pack_bf16x2(ll[4], ll[5]), pack_bf16x2(ll[6], ll[7]));
+  }
+}
+
+inline unsigned grid_for(size_t items) {
+  size_t b = (items + kThreads - 1) / kThreads;
+  size_t cap = (size_t)b200r_num_sms() * 16;
+  return (unsigned)(b < cap ? (b ? b : 1) : cap);
+}
+}  // namespace
+
+extern "C" {
+
+int b200r_split_f32(const float* in, uint16_t* planes, size_t count, b200r_stream_t stream) {
+  B200R_CHECK_ARG(in && planes, "null pointer");
+  B200R_CHECK_ARG(count % 4 == 0, "count must be a multiple of 4");
+  if (!count) return B200R_OK;
+  split_kernel<<<grid_for(count / 4), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(planes), reinterpret_cast<uint2*>(planes + count), count / 4);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_merge_f32(const uint16_t* planes, float* out, size_t count, b200r_stream_t stream) {
+  B200R_CHECK_ARG(out && planes, "null pointer");
+  B200R_CHECK_ARG(count % 4 == 0, "count must be a multiple of 4");
+  if (!count) return B200R_OK;
+  merge_kernel<<<grid_for(count / 4), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint2*>(planes), reinterpret_cast<const uint2*>(planes + count), reinterpret_cast<float4*>(out), count / 4);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+static int stem_common(const void* img, uint16_t* planes, int n, int h, int w, const float* mean, const float* std,
+                       bool u8, cudaStream_t s) {
+  B200R_CHECK_ARG(img && planes && mean && std, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "bad shape");
+  const int ho = h / 2, wo = w / 2;
+  const size_t rows = (size_t)n * ho * wo;
+  Norm3 nm;
+  for (int i = 0; i < 3; ++i) { nm.mean[i] = mean[i]; nm.std[i] = std[i]; }
+  uint4* hi = reinterpret_cast<uint4*>(planes);
+  uint4* lo = reinterpret_cast<uint4*>(planes + rows * kStemK);
+  if (u8) stem_im2col_kernel<true><<<grid_for(rows * (kStemK / 8)), kThreads, 0, s>>>(img, hi, lo, n, h, w, ho, wo, nm);
+  else stem_im2col_kernel<false><<<grid_for(rows * (kStemK / 8)), kThreads, 0, s>>>(img, hi, lo, n, h, w, ho, wo, nm);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_stem_im2col_u8(const uint8_t* img, uint16_t* planes, int n, int h, int w, const float* mean_host,
+                         const float* std_host, b200r_stream_t stream) {
+  return stem_common(img, planes, n, h, w, mean_host, std_host, true, as_stream(stream));
+}
+int b200r_stem_im2col_f32(const float* img, uint16_t* planes, int n, int h, int w, const float* mean_host,
+                          const float* std_host, b200r_stream_t stream) {
+  return stem_common(img, planes, n, h, w, mean_host, std_host, false, as_stream(stream));
+}
+
+int b200r_maxpool3x3s2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int c, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && y, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c % 8 == 0, "c must be a multiple of 8");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const size_t cin = (size_t)n * h * w * c, cout = (size_t)n * ho * wo * c;
+  maxpool_kernel<<<grid_for(cout / 8), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + cin), reinterpret_cast<uint4*>(y),
+      reinterpret_cast<uint4*>(y + cout), n, h, w, c / 8, ho, wo);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_global_avgpool_nhwc(const uint16_t* x, uint16_t* y, int n, int hw, int c, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && y, "null pointer");
+  B200R_CHECK_ARG(n > 0 && hw > 0 && c % 8 == 0, "c must be a multiple of 8");
+  const size_t cin = (size_t)n * hw * c, cout = (size_t)n * c;
+  const int warps = n * (c / 8);
+  avgpool_kernel<<<(warps * 32 + kThreads - 1) / kThreads, kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + cin), reinterpret_cast<uint4*>(y),
+      reinterpret_cast<uint4*>(y + cout), n, hw, c / 8);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,313 @@
+"""torch-tensor front end of the C-ABI: device memory and streams come from PyTorch, every
+computation is a hand-written sm_100a kernel in libb200robust.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+
+CORRUPTION_NAMES = (
+    "gaussian_noise", "shot_noise", "impulse_noise", "defocus_blur", "glass_blur", "motion_blur",
+    "zoom_blur", "snow", "frost", "fog", "brightness", "contrast", "elastic_transform", "pixelate",
+    "jpeg_compression", "speckle_noise", "gaussian_blur", "spatter", "saturate",
+)  # order of corruption_tuple, RobustART/noise/utils/imagenet_c/__init__.py:5-8
+CORRUPTION_IDS = {n: i for i, n in enumerate(CORRUPTION_NAMES)}
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # benchmark_eval_adv.py:33-38
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+_workspaces = {}
+_frost_loaded = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(t: torch.Tensor, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise TypeError("%s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    key = torch.device(device).index
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def corruption_id(corruption: Union[int, str]) -> int:
+    if isinstance(corruption, str):
+        if corruption not in CORRUPTION_IDS:
+            raise KeyError(corruption)
+        return CORRUPTION_IDS[corruption]
+    cid = int(corruption)
+    if not 0 <= cid < len(CORRUPTION_NAMES):
+        raise IndexError("corruption_number %d not in [0, 18]" % cid)
+    return cid
+
+
+def ext_noise_count(corruption, severity: int, n: int, h: int, w: int) -> int:
+    lib = _lib.load()
+    out = C.c_size_t(0)
+    _lib.check(lib.b200r_corrupt_ext_noise_count(corruption_id(corruption), severity, n, h, w, C.byref(out)))
+    return out.value
+
+
+def ensure_frost_textures(device):
+    """Upload the frost textures once per device (procedural stand-ins unless the user supplied the
+    reference's frost1..6 files via robustart_b200.assets.set_frost_dir)."""
+    key = torch.device(device).index
+    if key in _frost_loaded:
+        return
+    from .assets import frost_textures
+    lib = _lib.load()
+    keep = []
+    with torch.cuda.device(device):
+        for slot, tex in enumerate(frost_textures()):
+            t = torch.from_numpy(np.ascontiguousarray(tex)).to(device)
+            _lib.check(lib.b200r_set_frost_texture(slot, t.data_ptr(), t.shape[0], t.shape[1]))
+            keep.append(t)
+    _frost_loaded[key] = keep  # the library borrows the device memory: keep it alive
+
+
+def corrupt_u8(images: torch.Tensor, corruption: Union[int, str], severity: int = 1, *, seed: int = 0,
+               image_offset: int = 0, ext_noise: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ImageNet-C corruption of a uint8 NHWC CUDA batch (b200r_corrupt_u8)."""
+    _need_cuda(images, torch.uint8, "images")
+    if images.dim() != 4 or images.shape[-1] != 3:
+        raise ValueError("images must be [n,h,w,3] uint8")
+    n, h, w, _ = images.shape
+    cid = corruption_id(corruption)
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty_like(images)
+    else:
+        _need_cuda(out, torch.uint8, "out")
+    if cid == CORRUPTION_IDS["frost"]:
+        ensure_frost_textures(images.device)
+    if ext_noise is not None:
+        _need_cuda(ext_noise, torch.float32, "ext_noise")
+        need = ext_noise_count(cid, severity, n, h, w)
+        if ext_noise.numel() != need:
+            raise ValueError("ext_noise has %d values, corruption needs %d" % (ext_noise.numel(), need))
+    with torch.cuda.device(images.device):
+        nbytes = C.c_size_t(0)
+        _lib.check(lib.b200r_corrupt_workspace_bytes(cid, severity, n, h, w, C.byref(nbytes)))
+        ws = workspace(nbytes.value, images.device) if nbytes.value else None
+        _lib.check(lib.b200r_corrupt_u8(cid, severity, images.data_ptr(), out.data_ptr(), n, h, w,
+                                        seed & (2 ** 64 - 1), image_offset, _ptr(ext_noise), _ptr(ws),
+                                        nbytes.value, _stream()))
+    return out
+
+
+def u8nhwc_to_f32nchw(images: torch.Tensor, mean=IMAGENET_MEAN, std=IMAGENET_STD,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(images, torch.uint8, "images")
+    n, h, w, _ = images.shape
+    if out is None:
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=images.device)
+    with torch.cuda.device(images.device):
+        _lib.check(_lib.load().b200r_u8nhwc_to_f32nchw(images.data_ptr(), out.data_ptr(), n, h, w,
+                                                       _lib.f3(mean), _lib.f3(std), _stream()))
+    return out
+
+
+def normalize(x: torch.Tensor, mode: str = "normal", mean=IMAGENET_MEAN, std=IMAGENET_STD,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """normalize(x) / normalize(x, 'inv') of benchmark_eval_adv.py:33-46 on float32 NCHW."""
+    _need_cuda(x, torch.float32, "x")
+    n, c, h, w = x.shape
+    assert c == 3
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_normalize_f32nchw(x.data_ptr(), out.data_ptr(), n, h, w, _lib.f3(mean),
+                                                       _lib.f3(std), {"normal": 0, "inv": 1, "grad": 2}[mode], _stream()))
+    return out
+
+
+def random_start_linf(x0: torch.Tensor, eps: float, *, seed: int = 0, image_offset: int = 0,
+                      u: Optional[torch.Tensor] = None, clip01: bool = True) -> torch.Tensor:
+    _need_cuda(x0, torch.float32, "x0")
+    x = torch.empty_like(x0)
+    n = x0.shape[0]
+    chw = x0[0].numel()
+    if u is not None:
+        _need_cuda(u, torch.float32, "u")
+    with torch.cuda.device(x0.device):
+        _lib.check(_lib.load().b200r_random_start_linf(x0.data_ptr(), x.data_ptr(), n, chw, eps, seed,
+                                                       image_offset, _ptr(u), 1 if clip01 else 0, _stream()))
+    return x
+
+
+def pgd_step_linf_(x: torch.Tensor, g: torch.Tensor, x0: torch.Tensor, alpha: float, eps: float):
+    for t, nm in ((x, "x"), (g, "g"), (x0, "x0")):
+        _need_cuda(t, torch.float32, nm)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_pgd_step_linf(x.data_ptr(), g.data_ptr(), x0.data_ptr(), x.shape[0],
+                                                   x[0].numel(), alpha, eps, _stream()))
+    return x
+
+
+def pgd_step_l2_(x: torch.Tensor, g: torch.Tensor, x0: torch.Tensor, alpha: float, eps: float):
+    for t, nm in ((x, "x"), (g, "g"), (x0, "x0")):
+        _need_cuda(t, torch.float32, nm)
+    n = x.shape[0]
+    ws = workspace(8 * n, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_pgd_step_l2(x.data_ptr(), g.data_ptr(), x0.data_ptr(), n, x[0].numel(),
+                                                 alpha, eps, ws.data_ptr(), _stream()))
+    return x
+
+
+def mim_step_linf_(x, momentum, g, x0, step: float, eps: float, decay: float):
+    for t, nm in ((x, "x"), (momentum, "momentum"), (g, "g"), (x0, "x0")):
+        _need_cuda(t, torch.float32, nm)
+    n = x.shape[0]
+    ws = workspace(4 * n, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_mim_step_linf(x.data_ptr(), momentum.data_ptr(), g.data_ptr(),
+                                                   x0.data_ptr(), n, x[0].numel(), step, eps, decay,
+                                                   ws.data_ptr(), _stream()))
+    return x
+
+
+def ce_loss_grad(logits: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0, want_grad=True):
+    _need_cuda(logits, torch.float32, "logits")
+    _need_cuda(labels, torch.int64, "labels")
+    n, k = logits.shape
+    loss = torch.empty(n, dtype=torch.float32, device=logits.device)
+    d = torch.empty_like(logits) if want_grad else None
+    with torch.cuda.device(logits.device):
+        _lib.check(_lib.load().b200r_ce_loss_grad(logits.data_ptr(), labels.data_ptr(), loss.data_ptr(),
+                                                  _ptr(d), n, k, grad_scale, _stream()))
+    return loss, d
+
+
+def softmax(logits: torch.Tensor) -> torch.Tensor:
+    _need_cuda(logits, torch.float32, "logits")
+    out = torch.empty_like(logits)
+    with torch.cuda.device(logits.device):
+        _lib.check(_lib.load().b200r_softmax(logits.data_ptr(), out.data_ptr(), logits.shape[0],
+                                             logits.shape[1], _stream()))
+    return out
+
+
+def topk_count_(counters: torch.Tensor, logits: torch.Tensor, labels: torch.Tensor,
+                pred: Optional[torch.Tensor] = None):
+    """counters (int64[3], CUDA) += [top1 hits, top5 hits, n]."""
+    _need_cuda(logits, torch.float32, "logits")
+    _need_cuda(labels, torch.int64, "labels")
+    _need_cuda(counters, torch.int64, "counters")
+    with torch.cuda.device(logits.device):
+        _lib.check(_lib.load().b200r_topk_count(logits.data_ptr(), labels.data_ptr(), logits.shape[0],
+                                                logits.shape[1], counters.data_ptr(), _ptr(pred), _stream()))
+    return counters
+
+
+# ------------------------------------------------------------------------------------------------
+# split-bf16 tensors + tensor-core contractions
+# ------------------------------------------------------------------------------------------------
+ACT = {None: 0, "none": 0, "relu": 1, "relu6": 2, "gelu_tanh": 3, "gelu_erf": 4, "swish": 5, "tanh": 6}
+
+
+def split_f32(x: torch.Tensor) -> torch.Tensor:
+    """float32 tensor of shape S -> int16 tensor [2, *S] holding the (hi, lo) bf16 planes."""
+    _need_cuda(x, torch.float32, "x")
+    planes = torch.empty((2,) + tuple(x.shape), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_split_f32(x.data_ptr(), planes.data_ptr(), x.numel(), _stream()))
+    return planes
+
+
+def merge_f32(planes: torch.Tensor) -> torch.Tensor:
+    _need_cuda(planes, torch.int16, "planes")
+    out = torch.empty(tuple(planes.shape[1:]), dtype=torch.float32, device=planes.device)
+    with torch.cuda.device(planes.device):
+        _lib.check(_lib.load().b200r_merge_f32(planes.data_ptr(), out.data_ptr(), out.numel(), _stream()))
+    return out
+
+
+def conv2d_nhwc(x, wgt, scale=None, bias=None, res=None, *, stride=1, pad=0, act=None, passes=3, out=None,
+                out_f32=None, want_planes=True):
+    """x: planes [2,n,h,w,cin]; wgt: planes [2,cout,kh,kw,cin]; returns planes [2,n,ho,wo,cout]."""
+    _need_cuda(x, torch.int16, "x")
+    _need_cuda(wgt, torch.int16, "wgt")
+    _, n, h, w, cin = x.shape
+    _, cout, kh, kw, cin2 = wgt.shape
+    assert cin == cin2
+    ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    if out is None and want_planes:
+        out = torch.empty((2, n, ho, wo, cout), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_conv2d_nhwc(x.data_ptr(), wgt.data_ptr(), _ptr(scale), _ptr(bias), _ptr(res),
+                                                 _ptr(out), _ptr(out_f32), n, h, w, cin, cout, kh, kw, stride, pad,
+                                                 ACT[act], passes, _stream()))
+    return out if out is not None else out_f32
+
+
+def linear(x, wgt, scale=None, bias=None, res=None, *, act=None, passes=3, out=None, out_f32=None, want_planes=True):
+    """x: planes [2,m,k]; wgt: planes [2,nout,k]."""
+    _need_cuda(x, torch.int16, "x")
+    _need_cuda(wgt, torch.int16, "wgt")
+    m, k = x.shape[1], x.shape[-1]
+    m = x[0].numel() // k
+    nout = wgt.shape[1]
+    if out is None and want_planes:
+        out = torch.empty((2, m, nout), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_linear(x.data_ptr(), wgt.data_ptr(), _ptr(scale), _ptr(bias), _ptr(res), _ptr(out),
+                                            _ptr(out_f32), m, k, nout, ACT[act], passes, _stream()))
+    return out if out is not None else out_f32
+
+
+def stem_im2col(img, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
+    """uint8 NHWC or float32 NCHW image batch -> planes [2, n*ho*wo, 192] of normalised 7x7/s2 patches."""
+    if img.dtype == torch.uint8:
+        n, h, w, _ = img.shape
+        fn = _lib.load().b200r_stem_im2col_u8
+    else:
+        _need_cuda(img, torch.float32, "img")
+        n, _, h, w = img.shape
+        fn = _lib.load().b200r_stem_im2col_f32
+    rows = n * (h // 2) * (w // 2)
+    if out is None:
+        out = torch.empty((2, rows, 192), dtype=torch.int16, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(fn(img.data_ptr(), out.data_ptr(), n, h, w, _lib.f3(mean), _lib.f3(std), _stream()))
+    return out
+
+
+def maxpool3x3s2(x, out=None):
+    _, n, h, w, c = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((2, n, ho, wo, c), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_maxpool3x3s2_nhwc(x.data_ptr(), out.data_ptr(), n, h, w, c, _stream()))
+    return out
+
+
+def global_avgpool(x, out=None):
+    _, n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((2, n, c), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_global_avgpool_nhwc(x.data_ptr(), out.data_ptr(), n, h * w, c, _stream()))
+    return out

@@ -1,0 +1,152 @@
+"""Fused attack-step kernels and attack loops vs the torch fp32 restatement (oracle/attacks.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MEAN, STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def _data(cuda, n=6, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x0 = torch.rand(n, 3, 224, 224, generator=g).to(cuda)
+    grad = torch.randn(n, 3, 224, 224, generator=g).to(cuda)
+    grad[0, 0, :4, :4] = 0.0   # sign(0) = 0 must be honoured
+    y = torch.randint(0, 10, (n,), generator=g).to(cuda)
+    return x0, grad, y
+
+
+def test_linf_step_bit_exact(cuda):
+    from robustart_b200 import ops
+    x0, g, _ = _data(cuda)
+    eps, alpha = 4 / 255, 3 / 40 * 4 / 255
+    u = torch.rand_like(x0)
+    x = ops.random_start_linf(x0, eps, u=u)
+    ref = (x0 + ((eps - (-eps)) * u + (-eps))).clamp(0, 1)
+    assert torch.equal(x, ref)
+    for _ in range(3):
+        ref = ref + alpha * g.sign()
+        ref = (x0 + (ref - x0).clamp(-eps, eps)).clamp(0, 1)
+        ops.pgd_step_linf_(x, g, x0, alpha, eps)
+    assert torch.equal(x, ref)
+    assert (x - x0).abs().max().item() <= eps + 1e-7
+    assert x.min().item() >= 0 and x.max().item() <= 1
+
+
+def test_random_start_device_rng(cuda):
+    from robustart_b200 import ops
+    x0 = torch.full((4, 3, 224, 224), 0.5, device=cuda)
+    eps = 8 / 255
+    a = ops.random_start_linf(x0, eps, seed=1)
+    b = ops.random_start_linf(x0, eps, seed=1)
+    c = ops.random_start_linf(x0, eps, seed=2)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    d = (a - x0)
+    assert d.abs().max().item() <= eps + 1e-7
+    assert abs(d.mean().item()) < 1e-4 and abs(d.std().item() - eps / 3 ** 0.5) < 1e-4
+
+
+def test_l2_step(cuda):
+    from robustart_b200 import ops
+    from oracle import attacks as OA
+    x0, g, _ = _data(cuda)
+    eps, alpha = 3.0, 3 / 40 * 3.0
+    x = x0.clone()
+    ref = x0.clone()
+    for _ in range(3):
+        ops.pgd_step_l2_(x, g, x0, alpha, eps)
+        gn = g * (1.0 / OA._l2(g).clamp_min(1e-12))
+        ref = ref + alpha * gn
+        d = ref - x0
+        d = d * torch.minimum(torch.ones_like(OA._l2(d)), eps / OA._l2(d).clamp_min(1e-12))
+        ref = (x0 + d).clamp(0, 1)
+    assert (x - ref).abs().max().item() < 2e-6
+    assert OA._l2(x - x0).max().item() <= eps * (1 + 1e-5)
+
+
+def test_mim_step(cuda):
+    from robustart_b200 import ops
+    x0, g, _ = _data(cuda)
+    eps, step, decay = 8 / 255, 0.002, 1.0
+    x, m = x0.clone(), torch.zeros_like(x0)
+    rx, rm = x0.clone(), torch.zeros_like(x0)
+    for it in range(3):
+        gi = g * (it + 1)
+        ops.mim_step_linf_(x, m, gi, x0, step, eps, decay)
+        grad = gi / gi.abs().mean(dim=[1, 2, 3], keepdim=True)
+        rm = decay * rm + grad
+        rx = rx + step * rm.sign()
+        rx = (x0 + (rx - x0).clamp(-eps, eps)).clamp(0, 1)
+    assert (m - rm).abs().max().item() < 1e-4 * rm.abs().max().item()
+    mism = (x != rx).float().mean().item()
+    assert mism < 1e-4, mism
+
+
+def _mlp(cuda, seed=0):
+    torch.manual_seed(seed)
+    net = torch.nn.Sequential(torch.nn.AdaptiveAvgPool2d(8), torch.nn.Flatten(), torch.nn.Linear(192, 64),
+                              torch.nn.Tanh(), torch.nn.Linear(64, 10)).to(cuda).eval()
+    return net
+
+
+@pytest.mark.parametrize("attack", ["pgd_linf", "fgsm", "pgd_l2", "mim_linf"])
+def test_attack_loops_match_restatement(cuda, attack):
+    from robustart_b200 import attacks as A
+    from oracle import attacks as OA
+    net = _mlp(cuda)
+    x0, _, y = _data(cuda, n=8, seed=3)
+    m = torch.tensor(MEAN, device=cuda).view(1, 3, 1, 1)
+    s = torch.tensor(STD, device=cuda).view(1, 3, 1, 1)
+    fmodel = A.PyTorchModel(net, bounds=(0, 1), preprocessing=dict(mean=MEAN, std=STD, axis=-3))
+    ref_fn = lambda x: net((x - m) / s)
+    u = torch.rand_like(x0)
+    if attack == "pgd_linf":
+        eps = 4 / 255
+        got = A.pgd_linf(x0, y, fmodel, eps, 3 / 40, 10, start_uniform=u)
+        want = OA.pgd_linf(ref_fn, x0, y, eps, 3 / 40, 10, start_u=u)
+        tol_frac, bound = 5e-3, eps
+    elif attack == "fgsm":
+        eps = 8 / 255
+        got = A.fgsm(x0, y, fmodel, eps)
+        want = OA.fgsm(ref_fn, x0, y, eps)
+        tol_frac, bound = 1e-3, eps
+    elif attack == "pgd_l2":
+        eps = 2.0
+        z = torch.randn(8, 3 * 224 * 224 + 1, device=cuda)
+        dirn = (z / z.norm(dim=1, keepdim=True))[:, :-1].reshape(x0.shape)
+        got = A.pgd_l2(x0, y, fmodel, eps, 3 / 40, 10, start_direction=dirn)
+        want = OA.pgd_l2(ref_fn, x0, y, eps, 3 / 40, 10, start_direction=dirn)
+        assert (got - want).abs().max().item() < 1e-4
+        assert OA._l2(got - x0).max().item() <= eps * (1 + 1e-5)
+        return
+    else:
+        eps = 8 / 255
+        got = A.mim_linf(x0, y, net, eps, 10, 0.002, 1.0, start_uniform=u)
+        want = OA.mim_linf(net, x0, y, eps, 10, 0.002, 1.0, start_u=u)
+        tol_frac, bound = 5e-3, eps
+    assert (got - x0).abs().max().item() <= bound + 1e-6
+    assert got.min().item() >= 0 and got.max().item() <= 1
+    # a sign flip of a ~0 gradient moves a coordinate by 2*alpha: allow a tiny fraction of those
+    mism = ((got - want).abs() > 1e-6).float().mean().item()
+    assert mism < tol_frac, mism
+    # attack quality agrees: same predictions on the adversarials
+    assert torch.equal(ref_fn(got).argmax(1), ref_fn(want).argmax(1))
+
+
+def test_addnoise_adv_surface(cuda):
+    """The plugin call the solvers make (benchmark_eval_adv.py:198-209,231)."""
+    from RobustART.noise import AddNoise
+    from robustart_b200.attacks import PyTorchModel
+    net = _mlp(cuda)
+    x0, _, y = _data(cuda, n=4, seed=5)
+    fmodel = PyTorchModel(net, bounds=(0, 1), preprocessing=dict(mean=MEAN, std=STD, axis=-3))
+    gen = AddNoise("pgd_linf")
+    gen.set_config(f_model=fmodel, eps=4 / 255, steps=5)
+    adv = gen.add_noise(x0, y)
+    assert adv.shape == x0.shape and adv.is_cuda and adv.dtype == torch.float32
+    assert (adv - x0).abs().max().item() <= 4 / 255 + 1e-6
+    with pytest.raises(AssertionError):
+        gen.set_config(bogus=1)
+    # defaults are not shared between instances (the reference aliases the module-level dict)
+    assert AddNoise("pgd_linf").config["steps"] == 20

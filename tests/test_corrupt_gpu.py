@@ -1,0 +1,120 @@
+"""GPU parity of the ImageNet-C kernels against the CPU oracle (shared-draw mode) -- through the C-ABI.
+
+Tolerance (stated, per BASELINE north_star "stated fp tolerance for corrupted pixels"): the kernels
+compute in fp32, the reference in fp64, then both truncate to uint8, so a value landing within 1e-5 of
+an integer may fall on the other side: |gpu - oracle| <= 1 LSB everywhere, and on at most MISMATCH_FRAC
+of the pixels.  Integer pipelines (shot with shared draws, impulse, pixelate) are bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import synth_images, oracle_batch
+
+pytestmark = pytest.mark.gpu
+
+EXACT = {"shot_noise", "impulse_noise"}
+# fraction of pixels allowed to differ by exactly 1 LSB
+MISMATCH_FRAC = {"default": 0.02, "brightness": 0.10, "saturate": 0.10, "fog": 0.05, "frost": 0.05}
+PIXEL_FAMILY = ["gaussian_noise", "shot_noise", "impulse_noise", "speckle_noise", "brightness", "saturate",
+                "contrast", "frost", "fog"]
+
+
+def _run(cuda, name, sev, images, ext):
+    from robustart_b200 import ops
+    d = torch.from_numpy(images).to(cuda)
+    e = torch.from_numpy(ext).to(cuda) if ext.size else None
+    out = ops.corrupt_u8(d, name, sev, ext_noise=e)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _compare(name, got, want):
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    if name in EXACT:
+        assert diff.max() == 0, f"{name}: {np.count_nonzero(diff)} mismatching bytes, max {diff.max()}"
+        return
+    frac = np.count_nonzero(diff) / diff.size
+    assert diff.max() <= 1, f"{name}: max abs diff {diff.max()} (frac>1: {(diff > 1).mean():.2e})"
+    lim = MISMATCH_FRAC.get(name, MISMATCH_FRAC["default"])
+    assert frac <= lim, f"{name}: {frac:.4f} of pixels differ by 1 LSB (limit {lim})"
+
+
+@pytest.mark.parametrize("name", PIXEL_FAMILY)
+@pytest.mark.parametrize("sev", [1, 2, 3, 4, 5])
+def test_pixel_family_matches_oracle(cuda, name, sev):
+    images = synth_images(4, seed=sev)
+    kw = {}
+    if name == "frost":
+        from robustart_b200.assets import frost_textures
+        kw["textures"] = frost_textures()
+    want, ext = oracle_batch(images, name, sev, **kw)
+    got = _run(cuda, name, sev, images, ext)
+    _compare(name, got, want)
+
+
+@pytest.mark.parametrize("name", ["gaussian_noise", "speckle_noise", "shot_noise", "impulse_noise"])
+def test_device_rng_distribution(cuda, name):
+    """Device Philox mode: the corruption's first two moments per input level match the oracle's."""
+    from robustart_b200 import ops
+    sev = 3
+    n = 8
+    images = np.empty((n, 224, 224, 3), np.uint8)
+    levels = [0, 32, 64, 96, 128, 160, 200, 255]
+    for i, lv in enumerate(levels):
+        images[i] = lv
+    want, _ = oracle_batch(images, name, sev, seed0=7)
+    got = ops.corrupt_u8(torch.from_numpy(images).to(cuda), name, sev, seed=1234).cpu().numpy()
+    for i, lv in enumerate(levels):
+        a, b = got[i].astype(np.float64), want[i].astype(np.float64)
+        se = b.std() / np.sqrt(b.size) + 1e-9
+        assert abs(a.mean() - b.mean()) < 6 * se + 0.35, (name, lv, a.mean(), b.mean())
+        assert abs(a.std() - b.std()) < 0.02 * b.std() + 0.35, (name, lv, a.std(), b.std())
+
+
+def test_device_rng_is_counter_based(cuda):
+    """Same seed + image_offset => same bytes, independent of batch split."""
+    from robustart_b200 import ops
+    images = torch.from_numpy(synth_images(6, seed=3)).to(cuda)
+    whole = ops.corrupt_u8(images, "gaussian_noise", 2, seed=99, image_offset=10)
+    a = ops.corrupt_u8(images[:2].contiguous(), "gaussian_noise", 2, seed=99, image_offset=10)
+    b = ops.corrupt_u8(images[2:].contiguous(), "gaussian_noise", 2, seed=99, image_offset=12)
+    assert torch.equal(whole, torch.cat([a, b]))
+    other = ops.corrupt_u8(images, "gaussian_noise", 2, seed=100, image_offset=10)
+    assert not torch.equal(whole, other)
+
+
+def test_full_batch_properties(cuda):
+    """BASELINE config 2 size (N=256): deterministic kernels are idempotent under re-run, in-place ==
+    out-of-place, and severity is monotone in distortion for gaussian noise."""
+    from robustart_b200 import ops
+    rs = np.random.RandomState(0)
+    images = torch.from_numpy(rs.randint(0, 256, size=(256, 224, 224, 3), dtype=np.uint8)).to(cuda)
+    for name in ["brightness", "contrast", "saturate"]:
+        o1 = ops.corrupt_u8(images, name, 3)
+        o2 = ops.corrupt_u8(images, name, 3)
+        assert torch.equal(o1, o2)
+        tmp = images.clone()
+        ops.corrupt_u8(tmp, name, 3, out=tmp)
+        assert torch.equal(tmp, o1)
+    prev = 0.0
+    for sev in range(1, 6):
+        o = ops.corrupt_u8(images, "gaussian_noise", sev, seed=5)
+        err = (o.float() - images.float()).abs().mean().item()
+        assert err > prev
+        prev = err
+
+
+def test_argument_errors(cuda):
+    from robustart_b200 import ops
+    images = torch.zeros((1, 224, 224, 3), dtype=torch.uint8, device=cuda)
+    with pytest.raises(ValueError):
+        ops.corrupt_u8(images, "gaussian_noise", 0)     # reference silently treats 0 as severity 5
+    with pytest.raises(ValueError):
+        ops.corrupt_u8(images, "gaussian_noise", 6)
+    with pytest.raises(KeyError):
+        ops.corrupt_u8(images, "no_such_noise", 1)
+    with pytest.raises(TypeError):
+        ops.corrupt_u8(images.cpu(), "gaussian_noise", 1)  # no CPU fallback
+    empty = torch.zeros((0, 224, 224, 3), dtype=torch.uint8, device=cuda)
+    assert ops.corrupt_u8(empty, "gaussian_noise", 1).shape[0] == 0

@@ -1,0 +1,116 @@
+"""tcgen05 implicit-GEMM kernel vs torch (float64 reference).  Tolerance: split-bf16 with 3 passes keeps
+~16 mantissa bits per operand => relative error of a length-K dot product ~ 2^-16; we assert
+|err| <= 3e-5 * sqrt(K) * rms(a)*rms(b) style bounds via a normalised max error."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_err(got, ref):
+    return ((got.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+def test_split_merge_roundtrip(cuda):
+    from robustart_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(1024, 256, device=cuda) * 37.0
+    p = ops.split_f32(x)
+    y = ops.merge_f32(p)
+    assert ((y - x).abs() <= x.abs() * 2 ** -15).all()
+    hi = p[0].view(torch.bfloat16).float()
+    assert torch.equal(hi, x.bfloat16().float())
+
+
+@pytest.mark.parametrize("m,k,n", [(128, 64, 64), (256, 128, 128), (1000, 192, 64), (4096, 512, 1000), (300, 2048, 1000)])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_linear_matches_fp64(cuda, m, k, n, passes):
+    from robustart_b200 import ops
+    torch.manual_seed(m + k + n)
+    x = torch.randn(m, k, device=cuda)
+    w = torch.randn(n, k, device=cuda) / k ** 0.5
+    b = torch.randn(n, device=cuda)
+    s = torch.rand(n, device=cuda) + 0.5
+    ref = (x.double() @ w.double().t()) * s.double() + b.double()
+    out = torch.empty(m, n, device=cuda)
+    ops.linear(ops.split_f32(x), ops.split_f32(w), s, b, passes=passes, out_f32=out, want_planes=False)
+    torch.cuda.synchronize()
+    err = _rel_err(out, ref)
+    assert err < (2e-5 if passes == 3 else 2e-2), err
+    # planes output + residual + relu
+    r = torch.randn(m, n, device=cuda)
+    y = ops.linear(ops.split_f32(x), ops.split_f32(w), s, b, res=ops.split_f32(r), act="relu", passes=passes)
+    got = ops.merge_f32(y)
+    ref2 = torch.relu(ref + r.double())
+    assert _rel_err(got, ref2) < (4e-5 if passes == 3 else 2e-2)
+
+
+CONVS = [
+    # n, h, w, cin, cout, k, stride, pad
+    (2, 56, 56, 64, 64, 3, 1, 1),
+    (3, 28, 28, 128, 128, 3, 1, 1),
+    (5, 14, 14, 256, 256, 3, 1, 1),
+    (5, 7, 7, 512, 512, 3, 1, 1),
+    (2, 56, 56, 64, 256, 1, 1, 0),
+    (2, 56, 56, 128, 128, 3, 2, 1),
+    (3, 28, 28, 256, 256, 3, 2, 1),
+    (2, 56, 56, 256, 512, 1, 2, 0),
+    (3, 14, 14, 1024, 2048, 1, 2, 0),
+    (2, 14, 14, 512, 512, 3, 2, 1),
+    (2, 16, 16, 64, 64, 5, 1, 2),
+]
+
+
+@pytest.mark.parametrize("cfg", CONVS)
+def test_conv_matches_torch(cuda, cfg):
+    from robustart_b200 import ops
+    n, h, w, cin, cout, k, stride, pad = cfg
+    torch.manual_seed(sum(cfg))
+    x = torch.randn(n, cin, h, w, device=cuda)
+    wt = torch.randn(cout, cin, k, k, device=cuda) / (cin * k * k) ** 0.5
+    s = torch.rand(cout, device=cuda) + 0.5
+    b = torch.randn(cout, device=cuda)
+    ref = torch.nn.functional.conv2d(x.double(), wt.double(), stride=stride, padding=pad)
+    ref = ref * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1)
+    ho, wo = ref.shape[2:]
+    res = torch.randn(n, cout, ho, wo, device=cuda)
+    ref = torch.relu(ref + res.double())
+    xp = ops.split_f32(x.permute(0, 2, 3, 1).contiguous())
+    wp = ops.split_f32(wt.permute(0, 2, 3, 1).contiguous())
+    rp = ops.split_f32(res.permute(0, 2, 3, 1).contiguous())
+    y = ops.conv2d_nhwc(xp, wp, s, b, rp, stride=stride, pad=pad, act="relu")
+    torch.cuda.synchronize()
+    got = ops.merge_f32(y).permute(0, 3, 1, 2)
+    err = _rel_err(got, ref)
+    assert err < 4e-5, (cfg, err)
+
+
+def test_pool_layers(cuda):
+    from robustart_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(3, 64, 112, 112, device=cuda)
+    xp = ops.split_f32(x.permute(0, 2, 3, 1).contiguous())
+    xm = ops.merge_f32(xp).permute(0, 3, 1, 2)   # what the planes actually hold
+    mp = ops.merge_f32(ops.maxpool3x3s2(xp)).permute(0, 3, 1, 2)
+    assert torch.equal(mp, torch.nn.functional.max_pool2d(xm, 3, 2, 1))
+    ap = ops.merge_f32(ops.global_avgpool(xp))
+    assert (ap - xm.mean(dim=(2, 3))).abs().max().item() < 1e-5
+
+
+def test_stem_im2col(cuda):
+    from robustart_b200 import ops
+    torch.manual_seed(0)
+    img = torch.randint(0, 256, (2, 224, 224, 3), dtype=torch.uint8, device=cuda)
+    p = ops.stem_im2col(img)
+    cols = ops.merge_f32(p).view(2, 112, 112, 192)
+    xn = ops.u8nhwc_to_f32nchw(img)
+    ref = torch.nn.functional.unfold(xn, 7, padding=3, stride=2)         # [n, 3*49, L] ordered (c, ky, kx)
+    ref = ref.view(2, 3, 49, 112, 112).permute(0, 3, 4, 2, 1).reshape(2, 112, 112, 147)  # (tap, c)
+    assert (cols[..., :147] - ref).abs().max().item() < 1e-4
+    assert cols[..., 147:].abs().max().item() == 0
+    # float path
+    x01 = torch.rand(2, 3, 224, 224, device=cuda)
+    p2 = ops.merge_f32(ops.stem_im2col(x01)).view(2, 112, 112, 192)
+    ref2 = torch.nn.functional.unfold(ops.normalize(x01), 7, padding=3, stride=2)
+    ref2 = ref2.view(2, 3, 49, 112, 112).permute(0, 3, 4, 2, 1).reshape(2, 112, 112, 147)
+    assert (p2[..., :147] - ref2).abs().max().item() < 1e-4

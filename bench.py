@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Headline benchmark: BASELINE.json configs[1] -- ResNet-50 + ImageNet-C gaussian_noise severity 1-5,
+batch 256 per GPU.  One "step" = one pass of the hot path over one batch of 256 synthetic 224x224x3 uint8
+images: AddNoise gaussian_noise (severity cycles 1..5) -> normalise -> ResNet-50 forward -> top-1/top-5
+counters.  metric = corrupted-images/sec (whole job, all GPUs).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (sm_100a kernels)
+  python bench.py --impl reference ...                           the reference's CPU path on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...              N > 1: one rank per GPU, weak scaling
+
+Prints ONE JSON line (contract in the task statement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 256
+H = W = 224
+R_INPUTS = 8      # rotating input batches: 8 x 38.5 MB = 308 MB > 126 MB L2
+METRIC = "corrupted-images/sec"
+WORKLOAD = "configs[1]: ResNet-50 + ImageNet-C gaussian_noise severity 1-5 (cycled per step), batch 256/GPU"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, str(gpu_index)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", self.gpu], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's CPU path restated in oracle/ (numpy AddNoise loop +
+# torch fp32 ResNet-50 on the host cores).  This is the only place bench.py executes oracle/.
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pass(n_images, threads, seed=0):
+    import numpy as np
+    import torch
+    from oracle import imagenet_c as O
+    from oracle import models as OM
+    from oracle import metrics as OMet
+    from robustart_b200 import nets
+    torch.set_num_threads(threads)
+    if not hasattr(cpu_reference_pass, "_model"):
+        cpu_reference_pass._model = OM.build("resnet50", nets.random_state_dict(nets.resnet_spec("resnet50"), 0))
+    model = cpu_reference_pass._model
+    rs = np.random.RandomState(seed)
+    images = rs.randint(0, 256, size=(n_images, H, W, 3), dtype=np.uint8)
+    labels = torch.from_numpy(rs.randint(0, 1000, size=(n_images,)))
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    t0 = time.perf_counter()
+    O.add_noise_for_imagenet_c(images, severity=1 + seed % 5, corruption_name="gaussian_noise", draws=O.NumpyDraws(seed))
+    t1 = time.perf_counter()
+    with torch.no_grad():
+        x = (torch.from_numpy(images).permute(0, 3, 1, 2).float().div(255) - mean) / std
+        logits = model(x)
+    hits = OMet.topk_hits(logits, labels)
+    t2 = time.perf_counter()
+    return {"total_s": t2 - t0, "noise_s": t1 - t0, "model_s": t2 - t1, "hits": hits}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = 32
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_pass(per_step, threads)
+    t = 0.0
+    for i in range(args.steps):
+        t += cpu_reference_pass(per_step, threads, seed=i)["total_s"]
+    value = per_step * args.steps / t
+    sample = "%d steps x %d images of the same workload (numpy gaussian_noise loop + torch fp32 ResNet-50)" % (args.steps, per_step)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "reference_batch_per_step": per_step,
+                       "note": "reference CPU path = oracle port (the reference package itself cannot be imported: skimage/wand/easydict absent)"},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def gemm_roofline(model, pipe, pk):
+    """Live per-launch timing of the dominant kernel (tcgen05 implicit GEMM) with CUDA events on the
+    launching stream: the forward is re-run eagerly with an event pair around every conv / linear."""
+    import torch
+    from robustart_b200 import ops
+    recs = []
+    orig_conv, orig_lin = ops.conv2d_nhwc, ops.linear
+
+    def conv(x, wgt, *a, **k):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        y = orig_conv(x, wgt, *a, **k)
+        e.record()
+        _, n, h, w, cin = x.shape
+        _, cout, kh, kw, _ = wgt.shape
+        st, pd = k.get("stride", 1), k.get("pad", 0)
+        ho, wo = (h + 2 * pd - kh) // st + 1, (w + 2 * pd - kw) // st + 1
+        recs.append((s, e, 2.0 * n * ho * wo * cout * kh * kw * cin))
+        return y
+
+    def lin(x, wgt, *a, **k):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        y = orig_lin(x, wgt, *a, **k)
+        e.record()
+        kk = x.shape[-1]
+        recs.append((s, e, 2.0 * (x[0].numel() // kk) * kk * wgt.shape[1]))
+        return y
+
+    ops.conv2d_nhwc, ops.linear = conv, lin
+    try:
+        for _ in range(2):
+            recs.clear()
+            model.forward(pipe.static_in)
+            torch.cuda.synchronize()
+    finally:
+        ops.conv2d_nhwc, ops.linear = orig_conv, orig_lin
+    ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+    flops = sum(f for _, _, f in recs)
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    return {"bound": "tensor", "kernel": "gemm_kernel<BN> (tcgen05 implicit GEMM, all %d launches of one forward)" % len(recs),
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": pk["_source"] + ", sustained bf16 (kernel timed inside a long step)",
+            "gemm_ms_per_step": ms, "algorithmic_gflop_per_step": flops / 1e9,
+            "note": "algorithmic FLOPs = 2*M*N*K of the fp32 convolution; the split-bf16 scheme issues 3 bf16 MMAs per "
+                    "product, so tensor-pipe FLOP/s are 3x achieved"}
+
+
+def corruption_roofline(pipe, inputs, pk):
+    import torch
+    from robustart_b200 import ops
+    outs = [torch.empty_like(inputs[0]) for _ in range(len(inputs))]
+    for i in range(3):
+        ops.corrupt_u8(inputs[i % len(inputs)], "gaussian_noise", 1 + i % 5, seed=i, out=outs[i % len(outs)])
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 40
+    s.record()
+    for i in range(iters):
+        ops.corrupt_u8(inputs[i % len(inputs)], "gaussian_noise", 1 + i % 5, seed=i, out=outs[i % len(outs)])
+    e.record()
+    torch.cuda.synchronize()
+    t = s.elapsed_time(e) * 1e-3 / iters
+    alg = 2.0 * BATCH * H * W * 3
+    return {"bound": "hbm", "kernel": "normal_noise_kernel (gaussian_noise, u8 NHWC -> u8 NHWC)", "achieved": alg / t / 1e9,
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg / t / 1e9 / pk["hbm_gbs"], "traffic": None,
+            "us_per_launch": t * 1e6, "algorithmic_bytes_per_launch": alg, "images_per_s_kernel_only": BATCH / t}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from robustart_b200 import nets, _lib
+    from robustart_b200.evalpipe import CorruptEvalPipeline
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+
+    model = nets.build_model("resnet50", device=dev, seed=0)
+    pipe = CorruptEvalPipeline(model, BATCH, H, W, seed=1234 + rank)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    inputs = [torch.randint(0, 256, (BATCH, H, W, 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(R_INPUTS)]
+    labels = torch.randint(0, 1000, (BATCH,), device=dev, generator=g)
+    h_inputs = [t.cpu().pin_memory() for t in inputs[:4]]
+    h_labels = labels.cpu().pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------
+    for i in range(args.warmup):
+        pipe.step_device(inputs[i % R_INPUTS], labels, "gaussian_noise", 1 + i % 5)
+    pipe.reset()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(args.steps):
+        pipe.step_device(inputs[i % R_INPUTS], labels, "gaussian_noise", 1 + i % 5)
+    e.record()
+    barrier()
+    dev_ms = s.elapsed_time(e)
+    clocks = sampler.stop() if rank == 0 else None
+    pipe.allreduce_counters()                      # the one collective of the evaluation
+    counts = pipe.counters.tolist()
+
+    # ---- end-to-end through host buffers ("e2e") ----------------------------------------------
+    for i in range(max(3, args.warmup // 2)):
+        pipe.step_host(h_inputs[i % len(h_inputs)], h_labels, "gaussian_noise", 1 + i % 5)
+    barrier()
+    t0 = time.perf_counter()
+    s.record()
+    for i in range(args.steps):
+        pipe.step_host(h_inputs[i % len(h_inputs)], h_labels, "gaussian_noise", 1 + i % 5)
+    e.record()
+    barrier()
+    e2e_ms = max(s.elapsed_time(e), 0.0)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        value = world * BATCH * args.steps / (dev_ms * 1e-3)
+        e2e_v = world * BATCH * args.steps / (e2e_ms * 1e-3)
+        roof = gemm_roofline(model, pipe, pk)
+        roof_c = corruption_roofline(pipe, inputs, pk)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cpu_reference_pass(16, threads)
+            r = [cpu_reference_pass(32, threads, seed=i) for i in range(3)]
+            tot = sum(x["total_s"] for x in r)
+            cpu = {"value": 96 / tot, "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": "3 x 32 images of the same workload: oracle numpy gaussian_noise loop (%.0f img/s alone) + torch fp32 "
+                             "ResNet-50 forward (%.0f img/s alone)" % (96 / sum(x["noise_s"] for x in r), 96 / sum(x["model_s"] for x in r))}
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate: fp32-faithful)", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "image": "224x224x3 uint8 NHWC",
+                           "weights": "synthetic (nets.random_state_dict seed 0)", "parallelism": "dp%d" % world,
+                           "l2": "inputs rotate over %d batches = %d MB > 126 MB L2" % (R_INPUTS, R_INPUTS * BATCH * H * W * 3 // 2 ** 20),
+                           "forward": "CUDA graph replay", "counters": [int(c) for c in counts]},
+                "clocks": clocks,
+                "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": BATCH * H * W * 3 + BATCH * 8,
+                        "d2h_bytes_per_step": 24, "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall_ms / args.steps,
+                        "api": "CorruptEvalPipeline.step_host (pinned host uint8 batch -> counters on host)"},
+                "gpu_launches": pipe.launches_per_step * args.steps,
+                "gpu_launches_per_step": pipe.launches_per_step,
+                "roofline": roof, "roofline_corruption": roof_c}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

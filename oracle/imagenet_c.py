@@ -326,9 +326,11 @@ def glass_blur(x, severity, draws):  # corruptions.py:169-184
                 dx, dy = d[j]
                 j += 1
                 hp, wp = h + dy, w + dx
-                tmp = x[h, w].copy()
+                # `x[h, w], x[hp, wp] = x[hp, wp], x[h, w]` (corruptions.py:182) on a 3-channel array
+                # swaps VIEWS: the first assignment already overwrote x[h, w] when the second one
+                # reads it, so the net effect is a copy x[h, w] <- x[hp, wp]; x[hp, wp] keeps its value.
+                # (Verified against the reference's own code by tests/golden/make_golden.py.)
                 x[h, w] = x[hp, wp]
-                x[hp, wp] = tmp
     return np.clip(sk_gaussian(x / 255., sigma=c[0], multichannel=True), 0, 1) * 255
 
 

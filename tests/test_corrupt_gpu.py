@@ -15,7 +15,10 @@ pytestmark = pytest.mark.gpu
 
 EXACT = {"shot_noise", "impulse_noise"}
 # fraction of pixels allowed to differ by exactly 1 LSB
-MISMATCH_FRAC = {"default": 0.02, "brightness": 0.10, "saturate": 0.10, "fog": 0.05, "frost": 0.05}
+# brightness / saturate: the HSV round trip often lands EXACTLY on an integer in real arithmetic
+# (e.g. saturate c=2: p*255 = 2*min - max), so fp64 rounding noise alone decides k vs k-1 in the
+# reference; fp32 decides differently on a large share of such pixels.  Still <= 1 LSB.
+MISMATCH_FRAC = {"default": 0.02, "brightness": 0.5, "saturate": 0.5, "fog": 0.05, "frost": 0.05}
 PIXEL_FAMILY = ["gaussian_noise", "shot_noise", "impulse_noise", "speckle_noise", "brightness", "saturate",
                 "contrast", "frost", "fog"]
 

@@ -1,0 +1,72 @@
+"""The oracle is pinned against vectors produced by the REFERENCE's own corruptions.py
+(tests/golden/make_golden.py, run in the build container where /root/reference exists)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from util import synth_images
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "imagenet_c_reference.json")))
+
+
+def _cases():
+    names = sorted({k.split("/")[0] for k in GOLD["cases"]})
+    return names
+
+
+@pytest.mark.parametrize("name", _cases())
+def test_oracle_reproduces_reference_bytes(name):
+    from oracle import imagenet_c as O
+    from robustart_b200.assets import frost_textures
+    images = synth_images(2, seed=42)
+    kw = {"textures": frost_textures()} if name == "frost" else {}
+    for sev in range(1, 6):
+        for i in range(2):
+            seed = 1000 + 10 * i + sev
+            out = O.corrupt(images[i].copy(), sev, name, draws=O.NumpyDraws(seed), **kw)
+            sha = hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest()
+            assert sha == GOLD["cases"]["%s/%d/%d" % (name, sev, i)]["sha256"], (name, sev, i)
+
+
+def test_unpinned_list_is_what_we_document():
+    assert sorted(GOLD["skipped_unpinned"]) == ["motion_blur", "snow"]
+    assert len(GOLD["cases"]) == 17 * 5 * 2
+
+
+def test_corrupt_dispatch_and_errors():
+    from oracle import imagenet_c as O
+    img = synth_images(1, seed=1)[0]
+    a = O.corrupt(img, 2, corruption_name="contrast")
+    b = O.corrupt(img, 2, corruption_number=11)
+    assert np.array_equal(a, b) and a.dtype == np.uint8
+    with pytest.raises(ValueError):
+        O.corrupt(img, 1)
+    assert O.CORRUPTION_NAMES[15:] == ("speckle_noise", "gaussian_blur", "spatter", "saturate")
+
+
+def test_replay_draws_roundtrip():
+    from oracle import imagenet_c as O
+    img = synth_images(1, seed=2)[0]
+    d = O.NumpyDraws(5)
+    a = O.corrupt(img, 3, "fog", draws=d)
+    b = O.corrupt(img, 3, "fog", draws=O.ReplayDraws(d.log))
+    assert np.array_equal(a, b)
+    assert sum(np.size(x) for _, x in d.log) == 65535
+
+
+def test_metrics_oracle():
+    import torch
+    from oracle import metrics as OM
+    z = torch.tensor([[0.1, 0.9, 0.0, 0.2, 0.3, 0.4, 0.5], [0.9, 0.1, 0.0, 0.2, 0.3, 0.4, 0.5]])
+    y = torch.tensor([1, 2])
+    assert OM.topk_hits(z, y) == [1, 1]
+    a1, a5 = OM.accuracy(z, y, (1, 5))
+    assert a1.item() == 50.0 and a5.item() == 50.0
+    # sampler: contiguous slices of one permutation, last rank takes the remainder, no duplication
+    n, w = 50001, 8
+    parts = [OM.sampler_indices(n, w, r) for r in range(w)]
+    assert sorted(sum(parts, [])) == list(range(n))
+    assert [len(p) for p in parts] == [6251] * 7 + [50001 - 7 * 6251]

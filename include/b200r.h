@@ -182,6 +182,15 @@ int b200r_stem_im2col_u8(const uint8_t* img, uint16_t* planes, int n, int h, int
 int b200r_stem_im2col_f32(const float* img, uint16_t* planes, int n, int h, int w,
                           const float* mean_host, const float* std_host, b200r_stream_t stream);
 
+/* Fused stem: conv1 7x7/s2/p3 (3 -> 64) + BN + act straight from the raw uint8 NHWC image
+ * (resnet_official.py:221-226,331-333 after ToTensor+Normalize, imagenet_dataloader.py:78-79): the patch
+ * gather, x/255, (x-mean)/std and the bf16 split happen while the operand tile is written to shared
+ * memory; nothing but the image is read from HBM.  wgt: split planes [64, 192] (column = (ky*7+kx)*3+c,
+ * 147 real + 45 zero columns); y: split planes [n, h/2, w/2, 64]. */
+int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* scale, const float* bias,
+                          uint16_t* y, int n, int h, int w, const float* mean_host,
+                          const float* std_host, int act, int passes, b200r_stream_t stream);
+
 /* MaxPool2d(3, 2, 1) on split planes NHWC (resnet_official.py:227) */
 int b200r_maxpool3x3s2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int c,
                             b200r_stream_t stream);

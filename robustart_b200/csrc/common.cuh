@@ -78,12 +78,22 @@ __device__ __forceinline__ float u32_to_unit(uint32_t r) { return (float)(r >> 8
 __device__ __forceinline__ float u16_to_unit_open0(uint32_t r16) { return (float)(r16 + 1u) * (1.0f / 65536.0f); }
 
 // Box-Muller on two 16-bit uniforms -> two N(0,1) (MUFU lg2/sqrt/sin/cos; 2 MUFU per normal)
-__device__ __forceinline__ void box_muller16(uint32_t r, float& z0, float& z1) {
-  float u1 = u16_to_unit_open0(r & 0xFFFFu);
-  float u2 = (float)(r >> 16) * (1.0f / 65536.0f);
-  float rad = sqrtf(-2.0f * __logf(u1));
+// u1 = (k+1)/65536 in (0,1], u2 = k/65536 in [0,1): built with bit tricks (mantissa injection) so the
+// only XU-pipe work is the four MUFUs (lg2, sqrt, sin, cos).  `scale` multiplies both normals.
+__device__ __forceinline__ void box_muller16(uint32_t r, float& z0, float& z1, float scale = 1.0f) {
+  // [1,2) floats with the 16 random bits in the top of the mantissa
+  const float a = __uint_as_float(0x3F800000u | ((r & 0xFFFFu) << 7));        // 1 + k1/65536
+  const float b = __uint_as_float(0x3F800000u | ((r >> 16) << 7));            // 1 + k2/65536
+  const float u1 = 2.0f - a;                                                  // 1 - k1/65536 in (0,1]
+  float lg;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
+  float rad;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(lg * -1.3862943611198906f));  // sqrt(-2 ln u1)
+  rad *= scale;
+  const float ang = fmaf(b, 6.283185307179586f, -6.283185307179586f);         // 2*pi*u2
   float s, c;
-  __sincosf(6.283185307179586f * u2, &s, &c);
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
   z0 = rad * c;
   z1 = rad * s;
 }

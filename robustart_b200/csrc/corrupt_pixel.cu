@@ -49,17 +49,17 @@ __global__ void __launch_bounds__(kThreads) normal_noise_kernel(const uint4* __r
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float4 t = ld_stream_f4(e + q);
-      z[4 * q] = t.x; z[4 * q + 1] = t.y; z[4 * q + 2] = t.z; z[4 * q + 3] = t.w;
+      z[4 * q] = t.x * c; z[4 * q + 1] = t.y * c; z[4 * q + 2] = t.z * c; z[4 * q + 3] = t.w * c;
     }
   } else {
     const uint64_t gimg = image_offset + img;
 #pragma unroll
     for (int call = 0; call < 2; ++call) {
       uint4 r = philox4x32_10(rng_counter(gi, SPECKLE ? RNG_SPECKLE : RNG_GAUSS, call, gimg), k0, k1);
-      box_muller16(r.x, z[8 * call + 0], z[8 * call + 1]);
-      box_muller16(r.y, z[8 * call + 2], z[8 * call + 3]);
-      box_muller16(r.z, z[8 * call + 4], z[8 * call + 5]);
-      box_muller16(r.w, z[8 * call + 6], z[8 * call + 7]);
+      box_muller16(r.x, z[8 * call + 0], z[8 * call + 1], c);   // normals pre-scaled by sigma
+      box_muller16(r.y, z[8 * call + 2], z[8 * call + 3], c);
+      box_muller16(r.z, z[8 * call + 4], z[8 * call + 5], c);
+      box_muller16(r.w, z[8 * call + 6], z[8 * call + 7], c);
     }
   }
   uint32_t wi[4] = {v.x, v.y, v.z, v.w}, wo[4];
@@ -68,9 +68,10 @@ __global__ void __launch_bounds__(kThreads) normal_noise_kernel(const uint4* __r
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float x = byte_f(wi[q], k) * kInv255;
-      float zz = z[4 * q + k] * c;
-      float r = SPECKLE ? fmaf(x, zz, x) : (x + zz);
+      const float bf = byte_f(wi[q], k);
+      const float zz = z[4 * q + k];
+      // gaussian: x + c*z ; speckle: x + x*c*z  (x = b/255)
+      const float r = SPECKLE ? fmaf(bf * kInv255, zz, bf * kInv255) : fmaf(bf, kInv255, zz);
       o[k] = f01_to_u8bits(__saturatef(r));
     }
     wo[q] = pack4(o[0], o[1], o[2], o[3]);

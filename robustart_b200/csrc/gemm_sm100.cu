@@ -8,7 +8,7 @@
 // product, which is what holds the 1e-3 logit tolerance against the fp32 reference.  passes = 1 is
 // plain bf16.
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor (5-D map over [plane, N, H, W, C] for activations --
 //               the tap shift is a coordinate offset, padding is TMA out-of-bounds zero fill, stride is
 //               the map's elementStrides -- and a 3-D map over [plane, Cout, K] for weights) into a
@@ -16,12 +16,13 @@
 //   warp 1      TMEM allocation + single-thread tcgen05.mma issue (UMMA 128 x BN x 16, kind::f16,
 //               bf16 inputs, fp32 accumulate), tcgen05.commit onto the ring's "empty" barriers and the
 //               accumulator's "full" barrier.
-//   warps 2-5   epilogue: tcgen05.ld the 128 x BN fp32 accumulator (double-buffered in TMEM so the next
+//   warps 2-9   epilogue: tcgen05.ld the 128 x BN fp32 accumulator (double-buffered in TMEM so the next
 //               tile's MMAs overlap), folded-BN scale/bias, residual, activation, re-split to bf16
 //               planes (and/or fp32), masked stores.
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <string.h>
 
 namespace {
 
@@ -29,7 +30,7 @@ constexpr int BM = 128;       // UMMA_M (cta_group::1)
 constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 3;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
 
 // ---------------------------------------------------------------------------------------------
@@ -122,6 +123,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// two fp32 -> packed bf16x2 (round to nearest even): `hi` lands in the upper half, `lo` in the lower
+__device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzled operand tile (rows of 64 bf16 at a 128 B pitch, 8-row atoms 1024 B apart)
@@ -151,7 +158,14 @@ struct GemmParams {
   uint16_t* y_hi;
   uint16_t* y_lo;
   float* y_f32;
+  // STEM variant only: the A operand is gathered from the raw uint8 NHWC image by producer warps
+  const uint8_t* img;       // [N, H_in, W_in, 3]
+  const uint32_t* lut;      // [3][256]: normalised value of byte b in channel c as (hi | lo << 16) bf16 pair
+  int H_in, W_in, stem_Ho, stem_Wo;
+  long long M_total;        // N * Ho * Wo
 };
+
+constexpr int kStemProducerWarps = 4;   // one thread per A-tile row
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -168,8 +182,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, bool STEM>
+__global__ void __launch_bounds__(kThreads + (STEM ? kStemProducerWarps * 32 : 0), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
@@ -193,8 +207,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    // STEM: the A tile is written by 128 producer threads (one arrival each) next to the TMA thread's
+    // arrive.expect_tx for the weight tile
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), STEM ? 1 + kStemProducerWarps * 32 : 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -210,7 +226,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const int total_tiles = m_tiles * p.tiles_n;
   const int kblocks = p.KH * p.KW * p.cin_blocks;
   const uint32_t a_bytes = (uint32_t)p.rows_box * BK * 2;
-  const uint32_t tx_bytes = (p.passes == 3 ? 2u : 1u) * (a_bytes + (uint32_t)B_TILE_BYTES);
+  const uint32_t tx_bytes = (p.passes == 3 ? 2u : 1u) * ((STEM ? 0u : a_bytes) + (uint32_t)B_TILE_BYTES);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -228,10 +244,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               const uint32_t sa = smem_base + stage * STAGE_BYTES;
               mbar_expect_tx(full_bar(stage), tx_bytes);
               const int kcol = ((kh * p.KW + kw) * p.cin_blocks + cb) * BK;
-              tma_load_5d(sa, &map_a, full_bar(stage), cb * BK, w_in0 + kw, h_in0 + kh, n0, 0);
+              if (!STEM) tma_load_5d(sa, &map_a, full_bar(stage), cb * BK, w_in0 + kw, h_in0 + kh, n0, 0);
               tma_load_3d(sa + 2 * A_TILE_BYTES, &map_b, full_bar(stage), kcol, nt * BN, 0);
               if (p.passes == 3) {
-                tma_load_5d(sa + A_TILE_BYTES, &map_a, full_bar(stage), cb * BK, w_in0 + kw, h_in0 + kh, n0, 1);
+                if (!STEM) tma_load_5d(sa + A_TILE_BYTES, &map_a, full_bar(stage), cb * BK, w_in0 + kw, h_in0 + kh, n0, 1);
                 tma_load_3d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b, full_bar(stage), kcol, nt * BN, 1);
               }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -274,9 +290,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
       }
     }
-  } else {
-    // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
+  } else if (warp < 10) {
+    // ===================== epilogue (8 warps) =====================
+    // TMEM lane quarter = warp % 4 (hardware restriction); the two warps of a quarter split the columns.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const int box_hw = p.bh * p.bw;
     const int nl = r / box_hw, rem = r - nl * box_hw, hl = rem / p.bw, wl = rem - hl * p.bw;
@@ -292,7 +310,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), v);
         tmem_ld_wait();
@@ -301,58 +319,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           const size_t off = out_row * p.Cout + col0;
           const bool full = (col0 + 32 <= p.Cout);
           float f[32];
+          if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = min(col0 + j, p.Cout - 1);
-            float s = p.scale ? __ldg(p.scale + col) : 1.f;
-            float b = p.bias ? __ldg(p.bias + col) : 0.f;
-            f[j] = fmaf(__uint_as_float(v[j]), s, b);
-          }
-          if (p.res_hi) {
-            if (full) {
+            for (int q = 0; q < 8; ++q) {
+              const float4 s4 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + col0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+              const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+              f[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), s4.x, b4.x);
+              f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, b4.y);
+              f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, b4.z);
+              f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, b4.w);
+            }
+            if (p.res_hi) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                uint4 h = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off) + q);
-                uint4 l = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off) + q);
-                uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+                const uint4 h = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off) + q);
+                const uint4 l = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off) + q);
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  f[8 * q + j] += bf16_bits_to_f32((uint16_t)(hw[j >> 1] >> (16 * (j & 1)))) +
-                                  bf16_bits_to_f32((uint16_t)(lw[j >> 1] >> (16 * (j & 1))));
+                for (int j = 0; j < 4; ++j) {
+                  f[8 * q + 2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                  f[8 * q + 2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+                }
               }
-            } else {
-              for (int j = 0; j < 32 && col0 + j < p.Cout; ++j)
-                f[j] += bf16_bits_to_f32(p.res_hi[off + j]) + bf16_bits_to_f32(p.res_lo[off + j]);
             }
-          }
+            if (p.act == B200R_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-          if (p.y_f32) {
-            if (full) {
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            } else if (p.act != B200R_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+            }
+            if (p.y_f32) {
 #pragma unroll
               for (int q = 0; q < 8; ++q)
                 reinterpret_cast<float4*>(p.y_f32 + off)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-            } else {
-              for (int j = 0; j < 32 && col0 + j < p.Cout; ++j) p.y_f32[off + j] = f[j];
             }
-          }
-          if (p.y_hi) {
-            uint16_t hh[32], ll[32];
+            if (p.y_hi) {
+              uint32_t ph[16], pl[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) split_bf16(f[j], hh[j], ll[j]);
-            if (full) {
+              for (int j = 0; j < 16; ++j) {
+                ph[j] = cvt_bf16x2(f[2 * j + 1], f[2 * j]);
+                const float h0 = __uint_as_float(ph[j] << 16), h1 = __uint_as_float(ph[j] & 0xFFFF0000u);
+                pl[j] = cvt_bf16x2(f[2 * j + 1] - h1, f[2 * j] - h0);
+              }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                uint4 h, l;
-                h.x = hh[8 * q] | ((uint32_t)hh[8 * q + 1] << 16); h.y = hh[8 * q + 2] | ((uint32_t)hh[8 * q + 3] << 16);
-                h.z = hh[8 * q + 4] | ((uint32_t)hh[8 * q + 5] << 16); h.w = hh[8 * q + 6] | ((uint32_t)hh[8 * q + 7] << 16);
-                l.x = ll[8 * q] | ((uint32_t)ll[8 * q + 1] << 16); l.y = ll[8 * q + 2] | ((uint32_t)ll[8 * q + 3] << 16);
-                l.z = ll[8 * q + 4] | ((uint32_t)ll[8 * q + 5] << 16); l.w = ll[8 * q + 6] | ((uint32_t)ll[8 * q + 7] << 16);
-                reinterpret_cast<uint4*>(p.y_hi + off)[q] = h;
-                reinterpret_cast<uint4*>(p.y_lo + off)[q] = l;
+                reinterpret_cast<uint4*>(p.y_hi + off)[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+                reinterpret_cast<uint4*>(p.y_lo + off)[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
               }
-            } else {
-              for (int j = 0; j < 32 && col0 + j < p.Cout; ++j) { p.y_hi[off + j] = hh[j]; p.y_lo[off + j] = ll[j]; }
+            }
+          } else {
+            // ragged last column chunk (e.g. fc: 1000 = 31*32 + 8): scalar path
+            for (int j = 0; j < 32 && col0 + j < p.Cout; ++j) {
+              const int col = col0 + j;
+              float x = fmaf(__uint_as_float(v[j]), p.scale ? __ldg(p.scale + col) : 1.f, p.bias ? __ldg(p.bias + col) : 0.f);
+              if (p.res_hi) x += bf16_bits_to_f32(p.res_hi[off + j]) + bf16_bits_to_f32(p.res_lo[off + j]);
+              x = apply_act(x, p.act);
+              if (p.y_f32) p.y_f32[off + j] = x;
+              if (p.y_hi) { uint16_t hh, ll; split_bf16(x, hh, ll); p.y_hi[off + j] = hh; p.y_lo[off + j] = ll; }
             }
           }
         }
@@ -360,6 +384,62 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  } else if (STEM) {
+    // ===================== stem A producer (4 warps, one thread per tile row) =====================
+    // 7x7 / stride 2 / pad 3 patches of the uint8 NHWC image, K ordered (ky, kx, c) = 7 runs of 21
+    // consecutive image bytes; ToTensor + Normalize + bf16 split come from a 3x256 LUT; the 64-element
+    // k-block row is stored as 8 16-byte chunks at the 128B-swizzled position (chunk ^ (row & 7)).
+    const int r = (warp - 10) * 32 + lane;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mt = t / p.tiles_n;
+      const long long m = (long long)mt * BM + r;
+      const bool live = m < p.M_total;
+      const int ox = live ? (int)(m % p.stem_Wo) : 0;
+      const int oy = live ? (int)((m / p.stem_Wo) % p.stem_Ho) : 0;
+      const int n_img = live ? (int)(m / ((long long)p.stem_Wo * p.stem_Ho)) : 0;
+      const int iy0 = oy * 2 - 3, ix0 = ox * 2 - 3;
+      uint32_t rowok = 0, colok = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        rowok |= (uint32_t)(live && iy0 + k >= 0 && iy0 + k < p.H_in) << k;
+        colok |= (uint32_t)(ix0 + k >= 0 && ix0 + k < p.W_in) << k;
+      }
+      const uint8_t* base = p.img + (((long long)n_img * p.H_in + iy0) * p.W_in + ix0) * 3;
+      const long long row_pitch = (long long)p.W_in * 3;
+#pragma unroll
+      for (int kb = 0; kb < 3; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        uint8_t* a_hi = smem + stage * STAGE_BYTES + r * 128;
+        uint8_t* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint32_t e[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = kb * 64 + q * 8 + j;   // compile-time after unrolling
+            uint32_t val = 0;
+            if (col < 147) {
+              const int ky = col / 21, rem = col % 21, kx = rem / 3, c = rem % 3;
+              if (((rowok >> ky) & 1u) && ((colok >> kx) & 1u)) val = __ldg(p.lut + c * 256 + base[ky * row_pitch + rem]);
+            }
+            e[j] = val;
+          }
+          uint4 h, l;
+          h.x = __byte_perm(e[0], e[1], 0x5410); h.y = __byte_perm(e[2], e[3], 0x5410);
+          h.z = __byte_perm(e[4], e[5], 0x5410); h.w = __byte_perm(e[6], e[7], 0x5410);
+          l.x = __byte_perm(e[0], e[1], 0x7632); l.y = __byte_perm(e[2], e[3], 0x7632);
+          l.z = __byte_perm(e[4], e[5], 0x7632); l.w = __byte_perm(e[6], e[7], 0x7632);
+          const int chunk = (q ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(a_hi + chunk) = h;
+          if (p.passes == 3) *reinterpret_cast<uint4*>(a_lo + chunk) = l;
+        }
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(full_bar(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
     }
   }
 
@@ -391,18 +471,18 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <int BN>
+template <int BN, bool STEM>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * BN * BK * 2;
   const int smem = kStages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static bool configured = false;
   if (!configured) {
-    B200R_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200R_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_img * p.tiles_n;
   const int grid = total < b200r_num_sms() ? total : b200r_num_sms();
-  gemm_kernel<BN><<<grid, kThreads, smem, s>>>(ma, mb, p);
+  gemm_kernel<BN, STEM><<<grid, kThreads + (STEM ? kStemProducerWarps * 32 : 0), smem, s>>>(ma, mb, p);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
@@ -477,12 +557,90 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(B) failed: %d (Cout=%d K=%llu)", (int)r, Cout, (unsigned long long)K); return B200R_ECUDA; }
   }
-  return BN == 64 ? launch<64>(ma, mb, p, s) : launch<128>(ma, mb, p, s);
+  return BN == 64 ? launch<64, false>(ma, mb, p, s) : launch<128, false>(ma, mb, p, s);
+}
+
+// ---- fused stem ---------------------------------------------------------------------------------
+struct StemLut { uint32_t* d = nullptr; float key[6] = {0, 0, 0, 0, 0, 0}; };
+StemLut g_stem_lut[8];
+std::mutex g_stem_mu;
+
+uint16_t host_bf16(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+float host_bf16_to_f32(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+int get_stem_lut(const float* mean, const float* stdv, const uint32_t** out) {
+  int dev = 0;
+  B200R_CUDA(cudaGetDevice(&dev));
+  B200R_CHECK_ARG(dev >= 0 && dev < 8, "device index out of range");
+  std::lock_guard<std::mutex> lk(g_stem_mu);
+  StemLut& L = g_stem_lut[dev];
+  bool same = L.d != nullptr;
+  for (int i = 0; i < 3 && same; ++i) same = (L.key[i] == mean[i]) && (L.key[3 + i] == stdv[i]);
+  if (!same) {  // first use per device (or new constants): host table + blocking copy (not capturable)
+    uint32_t h[768];
+    for (int c = 0; c < 3; ++c)
+      for (int b = 0; b < 256; ++b) {
+        const float v = ((float)b / 255.0f - mean[c]) / stdv[c];   // ToTensor + Normalize in fp32
+        const uint16_t hi = host_bf16(v), lo = host_bf16(v - host_bf16_to_f32(hi));
+        h[c * 256 + b] = (uint32_t)hi | ((uint32_t)lo << 16);
+      }
+    if (!L.d) B200R_CUDA(cudaMalloc(&L.d, sizeof(h)));
+    B200R_CUDA(cudaMemcpy(L.d, h, sizeof(h), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 3; ++i) { L.key[i] = mean[i]; L.key[3 + i] = stdv[i]; }
+  }
+  *out = L.d;
+  return B200R_OK;
 }
 
 }  // namespace
 
 extern "C" {
+
+int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* scale, const float* bias, uint16_t* y,
+                          int n, int h, int w, const float* mean_host, const float* std_host, int act, int passes,
+                          b200r_stream_t stream) {
+  B200R_CHECK_ARG(img && wgt && y && mean_host && std_host, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "bad shape");
+  B200R_CHECK_ARG(passes == 1 || passes == 3, "passes must be 1 or 3");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { b200r_set_error("cuTensorMapEncodeTiled not available from the driver"); return B200R_ECUDA; }
+  const uint32_t* lut = nullptr;
+  int rc = get_stem_lut(mean_host, std_host, &lut);
+  if (rc) return rc;
+  const int Ho = h / 2, Wo = w / 2, Cout = 64, K = 192;
+  GemmParams p{};
+  p.bn = 1; p.bh = 1; p.bw = 128; p.rows_box = 128;
+  p.M_total = (long long)n * Ho * Wo;
+  p.tiles_w = (int)((p.M_total + 127) / 128); p.tiles_h = 1; p.tiles_img = 1; p.tiles_n = 1;
+  p.N = 1; p.Ho = 1; p.Wo = (int)p.M_total; p.Cout = Cout;          // epilogue sees a flat [M, 64] output
+  p.KH = 1; p.KW = 1; p.stride = 1; p.pad = 0; p.cin_blocks = K / 64;
+  p.passes = passes; p.act = act; p.scale = scale; p.bias = bias;
+  p.y_hi = y; p.y_lo = y + (size_t)p.M_total * Cout;
+  p.img = img; p.lut = lut; p.H_in = h; p.W_in = w;
+  CUtensorMap mb;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)Cout * K * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, 64, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(stem B) failed: %d", (int)r); return B200R_ECUDA; }
+  }
+  p.stem_Ho = Ho; p.stem_Wo = Wo;   // the producer decodes (n, oy, ox) from the real output geometry
+  return launch<64, true>(mb, mb, p, as_stream(stream));
+}
 
 int b200r_conv2d_nhwc(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias, const uint16_t* res,
                       uint16_t* y, float* y_f32, int n, int h, int w, int cin, int cout, int kh, int kw, int stride,

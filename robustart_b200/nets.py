@@ -171,9 +171,13 @@ class ResNet:
         n = images.shape[0]
         h, w = (images.shape[1], images.shape[2]) if images.dtype == torch.uint8 else (images.shape[2], images.shape[3])
         P = self.passes
-        cols = ops.stem_im2col(images)
-        x = ops.linear(cols, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P)
-        x = x.view(2, n, h // 2, w // 2, 64)
+        if images.dtype == torch.uint8:
+            # raw pixels: gather + ToTensor + Normalize + split fused into the stem GEMM's operand producer
+            x = ops.stem_conv7x7_u8(images, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P)
+        else:
+            cols = ops.stem_im2col(images)
+            x = ops.linear(cols, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P)
+            x = x.view(2, n, h // 2, w // 2, 64)
         x = ops.maxpool3x3s2(x)
         for blk in self.blocks:
             idn = blk["down"](x, passes=P) if "down" in blk else x
@@ -220,7 +224,7 @@ class ResNet:
         return run
 
     def launches_per_forward(self) -> int:
-        n = 2 + 1 + 1 + 1  # im2col, stem gemm, maxpool, avgpool, fc
+        n = 1 + 1 + 1 + 1  # fused stem, maxpool, avgpool, fc
         for blk in self.blocks:
             n += (3 if blk["kind"] == "bottleneck" else 2) + (1 if "down" in blk else 0)
         return n

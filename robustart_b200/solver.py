@@ -1,0 +1,228 @@
+"""Evaluation solvers of the hot path: the reference's `cls_solver --evaluate` (clean / ImageNet-C) and
+`*_benchmark_eval_adv` (adversarial) command lines, re-hosted on the B200 pipeline.
+
+Kept from the reference (prototype/prototype/solver/cls_solver.py:352-457,460-481;
+benchmark_eval_adv.py:191-299): CLI flags, YAML schema (model / model_src / model_tgt, data.*, saver.pretrain.*),
+`--eps` as a Python expression, env-var rank discovery (dist.py:21-54, linklink/__init__.py:21-34), the
+DistributedSampler(round_up=False) sharding rule (sampler.py:8-52), checkpoint key handling.
+Replaced: the per-image JSON dump + file merge + re-parse (imagenet_dataset.py:250-277, base_dataset.py:116-133,
+imagenet_evaluator.py:49-67) by device counters and ONE all-reduce; the CPU DataLoader by device-resident
+synthetic batches (`data.read_from: fake|synthetic`) -- JPEG decode / DALI / memcached readers are outside
+the hot path and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from typing import Dict, Optional
+
+import torch
+import yaml
+
+from . import nets, ops
+
+
+class AttrDict(dict):
+    """Tiny EasyDict stand-in (the reference depends on `easydict`, misc.py:15)."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            self[k] = v
+
+    def __setitem__(self, k, v):
+        if isinstance(v, dict) and not isinstance(v, AttrDict):
+            v = AttrDict(v)
+        elif isinstance(v, list):
+            v = [AttrDict(x) if isinstance(x, dict) else x for x in v]
+        super().__setitem__(k, v)
+
+    __setattr__ = __setitem__
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
+def parse_config(config_file: str) -> AttrDict:  # misc.py:67-72
+    with open(config_file) as f:
+        return AttrDict(yaml.load(f, Loader=yaml.FullLoader))
+
+
+# name -> model config, the subset of prototype/prototype/utils/model_config.py:3-288 with a B200 kernel path
+model_name_dict = {
+    "resnet18": {"type": "resnet18_official", "kwargs": {"bn": {"use_sync_bn": False, "kwargs": {}}}},
+    "resnet34": {"type": "resnet34_official", "kwargs": {"bn": {"use_sync_bn": False, "kwargs": {}}}},
+    "resnet50": {"type": "resnet50_official", "kwargs": {"bn": {"use_sync_bn": False, "kwargs": {}}}},
+    "resnet101": {"type": "resnet101_official", "kwargs": {"bn": {"use_sync_bn": False, "kwargs": {}}}},
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# distributed bring-up (dist.py:21-54): one process per GPU, NCCL; SKIP_DIST=1 -> single process
+# ------------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self, rank=0, world_size=1, local_rank=0, initialized=False):
+        self.rank, self.world_size, self.local_rank, self.initialized = rank, world_size, local_rank, initialized
+
+
+def dist_init(backend: Optional[str] = None) -> Dist:
+    import torch.distributed as dist
+    if os.environ.get("SKIP_DIST", "0") == "1":
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        return Dist()
+    if "SLURM_PROCID" in os.environ and "RANK" not in os.environ:
+        rank, world = int(os.environ["SLURM_PROCID"]), int(os.environ["SLURM_NTASKS"])
+    else:
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank % max(torch.cuda.device_count(), 1))))
+    if world == 1:
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+        return Dist(rank, world, local)
+    backend = backend or os.environ.get("B200R_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() else "gloo")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    return Dist(rank, world, local, True)
+
+
+def shard_indices(n_items: int, world_size: int, rank: int, epoch: int = 0):
+    """DistributedSampler(round_up=False).__iter__ (sampler.py:36-46): one seeded permutation, rank r takes
+    [r*ceil(N/W), (r+1)*ceil(N/W)), the last rank the remainder; nothing is padded or duplicated."""
+    num_samples = int(math.ceil(n_items * 1.0 / world_size))
+    g = torch.Generator()
+    g.manual_seed(epoch)
+    indices = torch.randperm(n_items, generator=g)
+    return indices[num_samples * rank: num_samples * rank + num_samples]
+
+
+def reduce_counters(counters: torch.Tensor, d: Dist) -> torch.Tensor:
+    """The single collective of an evaluation: int64 [.., 3] hit counters summed over ranks."""
+    if d.initialized and d.world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+    return counters
+
+
+# ------------------------------------------------------------------------------------------------
+class SyntheticImageNet:
+    """Device-resident stand-in for the validation set (`read_from: fake` reuses one decoded file for
+    every sample in the reference, base_dataset.py:73-80; here every index gets its own seeded image).
+    Items are generated on the fly from their global index, so any sharding sees the same data."""
+
+    def __init__(self, n_items: int, input_size: int, device, seed: int = 0):
+        self.n, self.size, self.device, self.seed = n_items, input_size, device, seed
+
+    def batch(self, indices: torch.Tensor):
+        n = len(indices)
+        imgs = torch.empty((n, self.size, self.size, 3), dtype=torch.uint8, device=self.device)
+        labels = torch.empty(n, dtype=torch.int64, device=self.device)
+        g = torch.Generator(device=self.device)
+        for j, idx in enumerate(indices.tolist()):
+            g.manual_seed(self.seed * 1000003 + idx)
+            imgs[j] = torch.randint(0, 256, (self.size, self.size, 3), dtype=torch.uint8, device=self.device, generator=g)
+            labels[j] = idx % 1000
+        return imgs, labels
+
+
+def load_checkpoint(path: Optional[str]) -> Optional[Dict[str, torch.Tensor]]:
+    if not path or not os.path.exists(path):
+        return None
+    return torch.load(path, map_location="cpu")
+
+
+def build_b200_model(model_cfg, ckpt_path, device):
+    """model_entry (model/__init__.py:292-332) for the families with a kernel path."""
+    mtype = model_cfg["type"]
+    sd = load_checkpoint(ckpt_path)
+    return nets.build_model(mtype, sd, device=device)
+
+
+def build_torch_model(model_cfg, ckpt_path, device):
+    """An autograd-capable module for the SOURCE model of an attack (input gradients); the forward/backward of
+    arbitrary source models stays on PyTorch until the dgrad kernels land."""
+    from . import torch_models
+    arch = nets.ARCH_ALIASES.get(model_cfg["type"], model_cfg["type"])
+    sd = load_checkpoint(ckpt_path)
+    if sd is None:
+        sd = nets.random_state_dict(nets.resnet_spec(arch), 0)
+    return torch_models.build(arch, nets._strip_prefix(sd)).to(device).eval()
+
+
+# ------------------------------------------------------------------------------------------------
+class EvalSolver:
+    def __init__(self, config: AttrDict, prefix: str = "", dist_info: Optional[Dist] = None):
+        self.config = config
+        self.dist = dist_info or dist_init()
+        if not torch.cuda.is_available():
+            raise RuntimeError("the evaluation solvers need a CUDA device (as the reference does, cls_solver.py:108)")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        data = config.data
+        if data.get("read_from", "fake") not in ("fake", "synthetic"):
+            raise NotImplementedError("data.read_from=%r: file/JPEG readers are outside the B200 hot path; "
+                                      "use read_from: fake (synthetic tensors)" % data.get("read_from"))
+        self.batch_size = int(data.get("batch_size", 64))
+        self.input_size = int(data.get("input_size", 224))
+        n_items = int(data.get("test", {}).get("limit_samples", data.get("num_samples", 50000)))
+        self.dataset = SyntheticImageNet(n_items, self.input_size, self.device)
+        self.indices = shard_indices(n_items, self.dist.world_size, self.dist.rank)
+        self.result_path = os.path.join(config.get("save_path", "."), prefix, "results")
+        if self.dist.rank == 0:
+            os.makedirs(self.result_path, exist_ok=True)
+
+    def _batches(self):
+        for i in range(0, len(self.indices), self.batch_size):
+            yield self.dataset.batch(self.indices[i:i + self.batch_size])
+
+    def _finish(self, counters, tag="results"):
+        reduce_counters(counters, self.dist)
+        c = counters.tolist()
+        metric = {"top1": 100.0 * c[0] / max(c[2], 1), "top5": 100.0 * c[1] / max(c[2], 1), "count": c[2]}
+        if self.dist.rank == 0:
+            with open(os.path.join(self.result_path, tag + ".metrics.json"), "w") as f:
+                json.dump(metric, f, indent=2)
+            print(json.dumps(metric, indent=2))
+        return metric
+
+    # cls_solver.py:352-457
+    def evaluate(self, model, corruption=None, severity=1):
+        from RobustART.noise.utils import add_noise_utils as anu
+        counters = torch.zeros(3, dtype=torch.int64, device=self.device)
+        done = 0
+        for imgs, labels in self._batches():
+            if corruption is not None:
+                ops.corrupt_u8(imgs, corruption, severity, seed=anu._seed(), image_offset=int(self.indices[done]), out=imgs)
+            logits = model(imgs)
+            ops.topk_count_(counters, logits, labels)
+            done += imgs.shape[0]
+        tag = "results" if corruption is None else "noise-%s-%d-results" % (corruption, severity)
+        return self._finish(counters, tag)
+
+    # benchmark_eval_adv.py:191-254
+    def evaluate_adv(self, model_src, model_tgt, attack="none", eps=0.0):
+        from RobustART.noise import AddNoise
+        from .attacks import PyTorchModel
+        counters = torch.zeros(3, dtype=torch.int64, device=self.device)
+        gen = None
+        if attack in ("autoattack_linf", "mim_linf", "pgd_l1"):
+            gen = AddNoise(attack)
+            gen.set_config(model=model_src, eps=eps)
+        elif attack != "none":
+            f_model = PyTorchModel(model_src, bounds=(0, 1), preprocessing=dict(mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, axis=-3))
+            gen = AddNoise(attack)
+            gen.set_config(f_model=f_model, eps=eps)
+        for imgs, labels in self._batches():
+            x01 = ops.normalize(ops.u8nhwc_to_f32nchw(imgs), "inv")   # the loader normalises, the solver undoes it (:229)
+            if gen is not None:
+                x01 = gen.add_noise(x01, labels).contiguous()
+            logits = model_tgt(x01)                                   # normalisation fused into the stem gather
+            ops.topk_count_(counters, logits, labels)
+        return self._finish(counters, "results")

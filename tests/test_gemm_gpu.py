@@ -114,3 +114,28 @@ def test_stem_im2col(cuda):
     ref2 = torch.nn.functional.unfold(ops.normalize(x01), 7, padding=3, stride=2)
     ref2 = ref2.view(2, 3, 49, 112, 112).permute(0, 3, 4, 2, 1).reshape(2, 112, 112, 147)
     assert (p2[..., :147] - ref2).abs().max().item() < 1e-4
+
+
+def test_fused_stem_matches_im2col_path(cuda):
+    """The fused uint8 stem (LUT normalisation, producer-warp gather) equals conv2d on the normalised image."""
+    from robustart_b200 import ops
+    torch.manual_seed(0)
+    img = torch.randint(0, 256, (5, 224, 224, 3), dtype=torch.uint8, device=cuda)
+    w = torch.randn(64, 3, 7, 7, device=cuda) * 0.1
+    s = torch.rand(64, device=cuda) + 0.5
+    b = torch.randn(64, device=cuda)
+    wp = torch.zeros(64, 192, device=cuda)
+    wp[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)
+    y = ops.stem_conv7x7_u8(img, ops.split_f32(wp), s, b, act="relu")
+    torch.cuda.synchronize()
+    got = ops.merge_f32(y).permute(0, 3, 1, 2)
+    xn = ops.u8nhwc_to_f32nchw(img)
+    ref = torch.nn.functional.conv2d(xn.double(), w.double(), stride=2, padding=3)
+    ref = torch.relu(ref * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1))
+    assert _rel_err(got, ref) < 4e-5
+    # batch that is not a multiple of the 128-row tile and odd geometry
+    img2 = torch.randint(0, 256, (1, 32, 48, 3), dtype=torch.uint8, device=cuda)
+    y2 = ops.merge_f32(ops.stem_conv7x7_u8(img2, ops.split_f32(wp), s, b, act="relu")).permute(0, 3, 1, 2)
+    ref2 = torch.relu(torch.nn.functional.conv2d(ops.u8nhwc_to_f32nchw(img2).double(), w.double(), stride=2, padding=3)
+                      * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1))
+    assert _rel_err(y2, ref2) < 4e-5

@@ -61,8 +61,10 @@ def test_layout_and_normalize(cuda):
     out = ops.u8nhwc_to_f32nchw(img)
     m = torch.tensor(ops.IMAGENET_MEAN, device=cuda).view(1, 3, 1, 1)
     s = torch.tensor(ops.IMAGENET_STD, device=cuda).view(1, 3, 1, 1)
-    ref = ((img.permute(0, 3, 1, 2).float() / 255) - m) / s
-    assert torch.equal(out, ref)
+    # ToTensor + Normalize run on the CPU in the reference's loader (true division by 255; torch's CUDA
+    # kernel multiplies by the reciprocal instead), so the bit-exact reference is the CPU computation.
+    ref = ((img.cpu().permute(0, 3, 1, 2).float() / 255) - m.cpu()) / s.cpu()
+    assert torch.equal(out.cpu(), ref)
     inv = ops.normalize(out, "inv")
     assert torch.equal(inv, out * s + m)
     assert torch.equal(ops.normalize(inv, "normal"), (inv - m) / s)

@@ -1,0 +1,54 @@
+"""The evaluation command lines end to end on one GPU (SKIP_DIST=1, synthetic data)."""
+import json
+import os
+
+import pytest
+import torch
+import yaml
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cfg(tmp_path, arch="resnet18_official", n=96, bs=32):
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "exprs", "b200", "resnet50_eval.yaml")))
+    cfg["model"]["type"] = arch
+    cfg["data"]["batch_size"] = bs
+    cfg["data"]["test"]["limit_samples"] = n
+    cfg["save_path"] = str(tmp_path)
+    p = tmp_path / "config.yaml"
+    p.write_text(yaml.safe_dump(cfg))
+    return str(p)
+
+
+def test_cls_solver_clean_and_imagenet_c(cuda, tmp_path, monkeypatch):
+    monkeypatch.setenv("SKIP_DIST", "1")
+    import prototype.prototype.solver.cls_solver as cls
+    from RobustART.noise.utils import add_noise_utils as anu
+    anu.reseed(7)
+    cfg = _cfg(tmp_path)
+    m0 = cls.main(["--config", cfg, "--evaluate"])
+    assert m0["count"] == 96 and 0 <= m0["top1"] <= m0["top5"] <= 100
+    m1 = cls.main(["--config", cfg, "--evaluate", "--corruption", "gaussian_noise", "--severity", "5"])
+    assert m1["count"] == 96
+    assert json.load(open(tmp_path / "results" / "noise-gaussian_noise-5-results.metrics.json")) == m1
+    # same counters as doing it by hand through the kernel ops
+    from robustart_b200 import nets, ops, solver as S
+    model = nets.build_model("resnet18", device=cuda)
+    ds = S.SyntheticImageNet(96, 224, cuda)
+    idx = S.shard_indices(96, 1, 0)
+    c = torch.zeros(3, dtype=torch.int64, device=cuda)
+    for i in range(0, 96, 32):
+        x, y = ds.batch(idx[i:i + 32])
+        ops.topk_count_(c, model(x), y)
+    assert abs(100.0 * c[0].item() / 96 - m0["top1"]) < 1e-9
+
+
+@pytest.mark.parametrize("attack,eps", [("pgd_linf", "4/255"), ("fgsm", "8/255"), ("mim_linf", "8/255"), ("none", "0")])
+def test_benchmark_eval_adv_cli(cuda, tmp_path, monkeypatch, attack, eps):
+    monkeypatch.setenv("SKIP_DIST", "1")
+    import prototype.prototype.solver.base_benchmark_eval_adv as adv
+    cfg = _cfg(tmp_path, n=32, bs=16)
+    m = adv.main(["--config", cfg, "--src_name", "resnet18", "--src_path", "", "--tgt_name", "resnet18", "--tgt_path", "",
+                  "--attack", attack, "--eps", eps])
+    assert m["count"] == 32 and 0 <= m["top1"] <= 100

@@ -1,7 +1,7 @@
 // Stencil / resampling ImageNet-C corruptions: shared-memory staged, ALU/smem-bound.
 //   gaussian_blur (corruptions.py:162-166)  glass_blur (:169-184)  defocus_blur (:187-198, disk :26-38)
 //   zoom_blur (:219-232, clipped_zoom :104-114)  motion_blur (:201-216)  snow (:265-290)
-// elastic_transform (:395-424) and spatter (:293-342) are not implemented yet (B200R_ENOTSUP).
+//   elastic_transform (:395-424).  spatter (:293-342) is not implemented yet (B200R_ENOTSUP).
 //
 // Third-party arithmetic restated here (same restatement as oracle/imagenet_c.py):
 //   skimage.filters.gaussian -> scipy.ndimage.gaussian_filter(sigma=[s,s,0], mode='nearest', truncate=4)
@@ -478,6 +478,185 @@ __global__ void __launch_bounds__(kMotionThreads, 1) snow_kernel(const uint8_t* 
   }
 }
 
+// =============================================================================================
+// elastic_transform (corruptions.py:395-424)
+//   1. random affine: pts2 = pts1 + U(-c2,c2) (float32), cv2.getAffineTransform, cv2.warpAffine(INTER_LINEAR,
+//      BORDER_REFLECT_101).  OpenCV's classic path is restated exactly: M inverted in double, coordinates in
+//      1/1024 fixed point (cvRound), sub-pixel position quantised to 1/32, float weight table (1-fy)(1-fx)...
+//      (checked against cv2 4.13: max |diff| = 0).
+//   2. displacement fields: gaussian_filter(U(-1,1), sigma=c1, mode='reflect', truncate=3) * c0.  sigma reaches
+//      170 px (radius 512 > image), so the reflect-folded 1-D filter is a dense symmetric 224x224 matrix T
+//      (built on the host in double): field = T * F * T, two small dense products per field.
+//   3. scipy.ndimage.map_coordinates(order=1, mode='reflect') at (y+dy, x+dx).
+// ext layout: [n][6 + 2*H*W] uniforms (affine points, then the dx field, then the dy field).
+// =============================================================================================
+struct ElasticT { float* d = nullptr; int size = 0; };
+ElasticT g_elastic[8][5];
+std::mutex g_elastic_mu;
+static const double kElastic[5][3] = {{244 * 2, 244 * 0.7, 244 * 0.1}, {244 * 2, 244 * 0.08, 244 * 0.2}, {244 * 0.05, 244 * 0.01, 244 * 0.02},
+                                      {244 * 0.07, 244 * 0.01, 244 * 0.02}, {244 * 0.12, 244 * 0.01, 244 * 0.02}};
+
+std::vector<float> make_reflect_gauss_matrix(int n, double sigma, double truncate) {
+  const int r = (int)(truncate * sigma + 0.5);
+  std::vector<double> w(2 * r + 1);
+  double sum = 0;
+  for (int i = -r; i <= r; ++i) { w[i + r] = exp(-0.5 / (sigma * sigma) * (double)i * i); sum += w[i + r]; }
+  std::vector<double> T((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int k = -r; k <= r; ++k) {
+      long v = i + k;                       // scipy 'reflect': d c b a | a b c d | d c b a
+      const long p = 2L * n;
+      v %= p; if (v < 0) v += p;
+      if (v >= n) v = p - 1 - v;
+      T[(size_t)i * n + v] += w[k + r] / sum;
+    }
+  std::vector<float> out(T.size());
+  for (size_t i = 0; i < T.size(); ++i) out[i] = (float)T[i];
+  return out;
+}
+
+constexpr int kElThreads = 256;
+
+__global__ void __launch_bounds__(kElThreads) elastic_warp_kernel(const uint8_t* __restrict__ in, float* __restrict__ warped, int h, int w,
+                                                                   double c2, const float* __restrict__ ext, size_t ext_stride,
+                                                                   uint32_t k0, uint32_t k1, uint64_t image_offset) {
+  __shared__ double sA[6];
+  const int img = blockIdx.y;
+  if (threadIdx.x == 0) {
+    float u[6];
+    if (ext) { for (int i = 0; i < 6; ++i) u[i] = ext[(size_t)img * ext_stride + i]; }
+    else {
+      uint4 a = philox4x32_10(rng_counter(0, RNG_ELASTIC, 0, image_offset + img), k0, k1);
+      uint4 b = philox4x32_10(rng_counter(1, RNG_ELASTIC, 0, image_offset + img), k0, k1);
+      u[0] = u32_to_unit(a.x); u[1] = u32_to_unit(a.y); u[2] = u32_to_unit(a.z); u[3] = u32_to_unit(a.w);
+      u[4] = u32_to_unit(b.x); u[5] = u32_to_unit(b.y);
+    }
+    // pts1 (x,y): (c+s, c+s), (c+s, c-s), (c-s, c-s) with c = size//2, s = min(size)//3, all float32
+    const float cx = (float)(h / 2), cy = (float)(w / 2), s = (float)(min(h, w) / 3);
+    const float p1[3][2] = {{cx + s, cy + s}, {cx + s, cy - s}, {cx - s, cy - s}};
+    double q[3][2];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 2; ++j) q[i][j] = (double)(p1[i][j] + (float)(-c2 + (2.0 * c2) * (double)u[2 * i + j]));
+    // solve dst = M [x y 1]^T through the three correspondences
+    const double dx01 = p1[0][0] - p1[1][0], dy01 = p1[0][1] - p1[1][1], dx12 = p1[1][0] - p1[2][0], dy12 = p1[1][1] - p1[2][1];
+    const double det = dx01 * dy12 - dx12 * dy01;
+    double M[6];
+    for (int r = 0; r < 2; ++r) {
+      const double a = q[0][r] - q[1][r], b = q[1][r] - q[2][r];
+      M[3 * r + 0] = (a * dy12 - b * dy01) / det;
+      M[3 * r + 1] = (dx01 * b - dx12 * a) / det;
+      M[3 * r + 2] = q[2][r] - M[3 * r] * p1[2][0] - M[3 * r + 1] * p1[2][1];
+    }
+    // cv::warpAffine inverts M (imgwarp.cpp)
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    const double A11 = M[4] * D, A22 = M[0] * D;
+    M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+    const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+    M[2] = b1; M[5] = b2;
+    for (int i = 0; i < 6; ++i) sA[i] = M[i];
+  }
+  __syncthreads();
+  const uint8_t* src = in + (size_t)img * h * w * 3;
+  float* dst = warped + (size_t)img * h * w * 3;
+  for (int pix = blockIdx.x * kElThreads + threadIdx.x; pix < h * w; pix += gridDim.x * kElThreads) {
+    const int y = pix / w, x = pix - y * w;
+    const long long X0 = llrint((sA[1] * y + sA[2]) * 1024.0) + 16, Y0 = llrint((sA[4] * y + sA[5]) * 1024.0) + 16;
+    const long long X = (X0 + llrint(sA[0] * x * 1024.0)) >> 5, Y = (Y0 + llrint(sA[3] * x * 1024.0)) >> 5;
+    const int ix = (int)(X >> 5), iy = (int)(Y >> 5);
+    const float fx = (float)(X & 31) * (1.f / 32.f), fy = (float)(Y & 31) * (1.f / 32.f);
+    const int x0 = reflect101(ix, w), x1 = reflect101(ix + 1, w), y0 = reflect101(iy, h), y1 = reflect101(iy + 1, h);
+    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float a = __fdiv_rn((float)src[(y0 * w + x0) * 3 + c], 255.f), b = __fdiv_rn((float)src[(y0 * w + x1) * 3 + c], 255.f);
+      const float cc = __fdiv_rn((float)src[(y1 * w + x0) * 3 + c], 255.f), d = __fdiv_rn((float)src[(y1 * w + x1) * 3 + c], 255.f);
+      dst[pix * 3 + c] = a * w00 + b * w01 + cc * w10 + d * w11;
+    }
+  }
+}
+
+// uniform fields U(-1,1): F [n][2][h*w]
+__global__ void __launch_bounds__(kElThreads) elastic_field_kernel(float* __restrict__ F, int hw, const float* __restrict__ ext,
+                                                                    size_t ext_stride, uint32_t k0, uint32_t k1, uint64_t image_offset) {
+  const int img = blockIdx.y;
+  for (int i = blockIdx.x * kElThreads + threadIdx.x; i < 2 * hw; i += gridDim.x * kElThreads) {
+    float u;
+    if (ext) u = ext[(size_t)img * ext_stride + 6 + i];
+    else {
+      uint4 r = philox4x32_10(rng_counter((uint32_t)(i >> 2), RNG_ELASTIC, 1, image_offset + img), k0, k1);
+      u = u32_to_unit((i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w);
+    }
+    F[(size_t)img * 2 * hw + i] = -1.f + 2.f * u;
+  }
+}
+
+// C[b] = left ? T * B[b] : B[b] * T   (T symmetric n x n, n % 32 == 0), 32x32 tile per CTA, 8x32 threads x 4 rows
+__global__ void __launch_bounds__(256) elastic_matmul_kernel(const float* __restrict__ T, const float* __restrict__ B, float* __restrict__ C,
+                                                              int n, int left, float scale) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const float* Bb = B + (size_t)blockIdx.z * n * n;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < n; k0 += 32) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = ty * 4 + j;
+      // A operand rows by..by+31 (T if left else B), B operand cols bx..bx+31 (B if left else T)
+      sa[r][tx] = left ? T[(size_t)(by + r) * n + k0 + tx] : Bb[(size_t)(by + r) * n + k0 + tx];
+      sb[r][tx] = left ? Bb[(size_t)(k0 + r) * n + bx + tx] : T[(size_t)(k0 + r) * n + bx + tx];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float bv = sb[k][tx];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(sa[ty * 4 + j][k], bv, acc[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) C[(size_t)blockIdx.z * n * n + (size_t)(by + ty * 4 + j) * n + bx + tx] = acc[j] * scale;
+}
+
+__device__ __forceinline__ float scipy_reflect_coord(float in, int len) {  // ni_interpolation.c map_coordinate, NI_EXTEND_REFLECT
+  const float flen = (float)len;
+  if (in < 0.f) {
+    const float sz2 = 2.f * flen;
+    if (in < -sz2) in = sz2 * (float)(int)(-in / sz2) + in;
+    in = in < -flen ? in + sz2 : -in - 1.f;
+  } else if (in > flen - 1.f) {
+    const float sz2 = 2.f * flen;
+    in -= sz2 * (float)(int)(in / sz2);
+    if (in >= flen) in = sz2 - in - 1.f;
+  }
+  return in;
+}
+__device__ __forceinline__ int scipy_reflect_idx(int i, int n) { return i < 0 ? -i - 1 : (i >= n ? 2 * n - i - 1 : i); }
+
+__global__ void __launch_bounds__(kElThreads) elastic_gather_kernel(const float* __restrict__ warped, const float* __restrict__ disp,
+                                                                     uint8_t* __restrict__ out, int h, int w) {
+  const int img = blockIdx.y, hw = h * w;
+  const float* W = warped + (size_t)img * hw * 3;
+  const float* dxp = disp + (size_t)img * 2 * hw;
+  const float* dyp = dxp + hw;
+  uint8_t* dst = out + (size_t)img * hw * 3;
+  for (int pix = blockIdx.x * kElThreads + threadIdx.x; pix < hw; pix += gridDim.x * kElThreads) {
+    const int y = pix / w, x = pix - y * w;
+    const float cy = scipy_reflect_coord((float)y + dyp[pix], h), cx = scipy_reflect_coord((float)x + dxp[pix], w);
+    const int iy = (int)floorf(cy), ix = (int)floorf(cx);
+    const float ty = cy - (float)iy, tx = cx - (float)ix;
+    const int y0 = scipy_reflect_idx(iy, h), y1 = scipy_reflect_idx(iy + 1, h), x0 = scipy_reflect_idx(ix, w), x1 = scipy_reflect_idx(ix + 1, w);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = (1.f - ty) * ((1.f - tx) * W[(y0 * w + x0) * 3 + c] + tx * W[(y0 * w + x1) * 3 + c]) +
+                      ty * ((1.f - tx) * W[(y1 * w + x0) * 3 + c] + tx * W[(y1 * w + x1) * 3 + c]);
+      dst[pix * 3 + c] = (uint8_t)f01_to_u8(__saturatef(v));
+    }
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -490,7 +669,9 @@ size_t corrupt_stencil_ws(int id, int sev, int n, int h, int w) {
   (void)sev;
   // a scratch image: glass_blur's intermediate, and the detour for in-place calls (none of these
   // kernels can overwrite its own input)
-  if (id == B200R_SPATTER || id == B200R_ELASTIC_TRANSFORM) return 0;
+  if (id == B200R_SPATTER) return 0;
+  // elastic: warped fp32 image + two ping-pong buffers of the (dx, dy) fields
+  if (id == B200R_ELASTIC_TRANSFORM) return (size_t)n * h * w * (3 + 2 + 2) * sizeof(float);
   return (size_t)n * h * w * 3;
 }
 
@@ -507,6 +688,7 @@ size_t corrupt_ext_count(int id, int sev, int n, int h, int w) {
     }
     case B200R_MOTION_BLUR: return (size_t)n;
     case B200R_SNOW: return (size_t)n * ((size_t)h * w + 1);
+    case B200R_ELASTIC_TRANSFORM: return (size_t)n * (6 + 2 * (size_t)h * w);
     default: return 0;
   }
 }
@@ -516,6 +698,7 @@ static int stencil_dispatch(const CorruptArgs& a);
 int corrupt_stencil_family(const CorruptArgs& a0) {
   CorruptArgs a = a0;
   const size_t bytes = (size_t)a.n * a.h * a.w * 3;
+  if (a.id == B200R_ELASTIC_TRANSFORM) return stencil_dispatch(a);   // reads `in` fully before writing `out`
   const bool inplace = (a.in == a.out) && a.id != B200R_SNOW;
   if (inplace || a.id == B200R_GLASS_BLUR) {
     B200R_CHECK_ARG(a.ws && a.ws_bytes >= bytes, "this corruption needs %zu workspace bytes", bytes);
@@ -612,8 +795,43 @@ static int stencil_dispatch(const CorruptArgs& a) {
       B200R_LAUNCH_CHECK();
       return B200R_OK;
     }
+    case B200R_ELASTIC_TRANSFORM: {
+      B200R_CHECK_ARG(a.h == a.w && a.h % 32 == 0, "elastic_transform expects square images with size %% 32 == 0");
+      const size_t hw = (size_t)a.h * a.w;
+      const size_t need = corrupt_stencil_ws(a.id, a.severity, a.n, a.h, a.w);
+      B200R_CHECK_ARG(a.ws && a.ws_bytes >= need, "elastic_transform needs %zu workspace bytes", need);
+      int dev = 0;
+      B200R_CUDA(cudaGetDevice(&dev));
+      B200R_CHECK_ARG(dev >= 0 && dev < 8, "device index out of range");
+      const float* dT = nullptr;
+      {
+        std::lock_guard<std::mutex> lk(g_elastic_mu);
+        ElasticT& t = g_elastic[dev][s];
+        if (!t.d || t.size != a.h) {  // first use: host build + blocking copy (not capturable)
+          std::vector<float> T = make_reflect_gauss_matrix(a.h, kElastic[s][1], 3.0);
+          if (t.d) cudaFree(t.d);
+          B200R_CUDA(cudaMalloc(&t.d, T.size() * sizeof(float)));
+          B200R_CUDA(cudaMemcpy(t.d, T.data(), T.size() * sizeof(float), cudaMemcpyHostToDevice));
+          t.size = a.h;
+        }
+        dT = t.d;
+      }
+      float* warped = static_cast<float*>(a.ws);
+      float* f0 = warped + (size_t)a.n * hw * 3;
+      float* f1 = f0 + (size_t)a.n * hw * 2;
+      const size_t ext_stride = 6 + 2 * hw;
+      dim3 gp(32, a.n);
+      elastic_warp_kernel<<<gp, kElThreads, 0, a.stream>>>(a.in, warped, a.h, a.w, kElastic[s][2], a.ext, ext_stride, k0, k1, a.image_offset);
+      elastic_field_kernel<<<gp, kElThreads, 0, a.stream>>>(f0, (int)hw, a.ext, ext_stride, k0, k1, a.image_offset);
+      dim3 gm(a.w / 32, a.h / 32, 2 * a.n);
+      elastic_matmul_kernel<<<gm, 256, 0, a.stream>>>(dT, f0, f1, a.h, 1, 1.0f);                       // T * F
+      elastic_matmul_kernel<<<gm, 256, 0, a.stream>>>(dT, f1, f0, a.h, 0, (float)kElastic[s][0]);      // (T F) * T * c0
+      elastic_gather_kernel<<<gp, kElThreads, 0, a.stream>>>(warped, f0, a.out, a.h, a.w);
+      B200R_LAUNCH_CHECK();
+      return B200R_OK;
+    }
     default:
-      b200r_set_error("%s is not implemented on the GPU yet", a.id == B200R_SPATTER ? "spatter" : "elastic_transform");
+      b200r_set_error("spatter is not implemented on the GPU yet");
       return B200R_ENOTSUP;
   }
 }

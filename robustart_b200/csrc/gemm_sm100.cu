@@ -129,6 +129,17 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+// 256-bit global accesses (sm_100, PTX 8.8): one full 32-byte sector per thread per instruction
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t* v) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzled operand tile (rows of 64 bf16 at a 128 B pitch, 8-row atoms 1024 B apart)
@@ -317,7 +328,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const int col0 = nt * BN + c0;
         if (row_ok && col0 < p.Cout) {
           const size_t off = out_row * p.Cout + col0;
-          const bool full = (col0 + 32 <= p.Cout);
+          const bool full = (col0 + 32 <= p.Cout) && (p.Cout % 16 == 0);
           float f[32];
           if (full) {
 #pragma unroll
@@ -331,14 +342,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
             if (p.res_hi) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 h = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off) + q);
-                const uint4 l = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off) + q);
-                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+              for (int q = 0; q < 2; ++q) {
+                uint32_t hw[8], lw[8];
+                ld_global_v8(p.res_hi + off + 16 * q, hw);
+                ld_global_v8(p.res_lo + off + 16 * q, lw);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  f[8 * q + 2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-                  f[8 * q + 2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+                for (int j = 0; j < 8; ++j) {
+                  f[16 * q + 2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                  f[16 * q + 2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
                 }
               }
             }
@@ -362,11 +373,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 const float h0 = __uint_as_float(ph[j] << 16), h1 = __uint_as_float(ph[j] & 0xFFFF0000u);
                 pl[j] = cvt_bf16x2(f[2 * j + 1] - h1, f[2 * j] - h0);
               }
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                reinterpret_cast<uint4*>(p.y_hi + off)[q] = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-                reinterpret_cast<uint4*>(p.y_lo + off)[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
-              }
+              st_global_v8(p.y_hi + off, ph);
+              st_global_v8(p.y_hi + off + 16, ph + 8);
+              st_global_v8(p.y_lo + off, pl);
+              st_global_v8(p.y_lo + off + 16, pl + 8);
             }
           } else {
             // ragged last column chunk (e.g. fc: 1000 = 31*32 + 8): scalar path
@@ -386,60 +396,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   } else if (STEM) {
-    // ===================== stem A producer (4 warps, one thread per tile row) =====================
-    // 7x7 / stride 2 / pad 3 patches of the uint8 NHWC image, K ordered (ky, kx, c) = 7 runs of 21
-    // consecutive image bytes; ToTensor + Normalize + bf16 split come from a 3x256 LUT; the 64-element
-    // k-block row is stored as 8 16-byte chunks at the 128B-swizzled position (chunk ^ (row & 7)).
-    const int r = (warp - 10) * 32 + lane;
+    // ===================== stem A producer (4 warps) =====================
+    // 7x7 / stride 2 / pad 3 patches of the uint8 NHWC image.  A tile = ONE output row of one image
+    // (Wo <= 128 pixels).  Per tile the 7 input rows it touches are staged once in shared memory, already
+    // mapped through the 3x256 LUT (ToTensor + Normalize + bf16 split -> hi | lo<<16) and padded with zero
+    // columns/rows, so the per-pixel gather needs no bounds checks: K is ordered (ky, kx, c), i.e. 7 runs of
+    // 21 consecutive staged words starting at word 6*ox.  The 64-element k-block row goes out as 8 16-byte
+    // chunks at the 128B-swizzled position (chunk ^ (row & 7)).
+    const int ptid = threadIdx.x - 10 * 32;                    // 0..127
+    const int r = ptid;                                         // tile row = output column ox
+    const int row_bytes = p.W_in * 3;
+    const int pitch = 9 + row_bytes + 15;                       // staged words per input row (zero padded)
+    uint32_t* s_conv = reinterpret_cast<uint32_t*>(smem + kStages * STAGE_BYTES + 512);
+    uint32_t* s_lut = s_conv + 7 * pitch;
+    for (int i = ptid; i < 768; i += kStemProducerWarps * 32) s_lut[i] = __ldg(p.lut + i);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mt = t / p.tiles_n;
-      const long long m = (long long)mt * BM + r;
-      const bool live = m < p.M_total;
-      const int ox = live ? (int)(m % p.stem_Wo) : 0;
-      const int oy = live ? (int)((m / p.stem_Wo) % p.stem_Ho) : 0;
-      const int n_img = live ? (int)(m / ((long long)p.stem_Wo * p.stem_Ho)) : 0;
-      const int iy0 = oy * 2 - 3, ix0 = ox * 2 - 3;
-      uint32_t rowok = 0, colok = 0;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        rowok |= (uint32_t)(live && iy0 + k >= 0 && iy0 + k < p.H_in) << k;
-        colok |= (uint32_t)(ix0 + k >= 0 && ix0 + k < p.W_in) << k;
+      const int oy = mt % p.tiles_h, n_img = mt / p.tiles_h;
+      const uint8_t* img_base = p.img + (long long)n_img * p.H_in * row_bytes;
+      for (int i = ptid; i < 7 * pitch; i += kStemProducerWarps * 32) {
+        const int ky = i / pitch, col = i - ky * pitch, bi = col - 9, iy = oy * 2 - 3 + ky;
+        uint32_t val = 0;
+        if (iy >= 0 && iy < p.H_in && bi >= 0 && bi < row_bytes) val = s_lut[(bi % 3) * 256 + img_base[(long long)iy * row_bytes + bi]];
+        s_conv[i] = val;
       }
-      const uint8_t* base = p.img + (((long long)n_img * p.H_in + iy0) * p.W_in + ix0) * 3;
-      const long long row_pitch = (long long)p.W_in * 3;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t* my = s_conv + 6 * r;                      // (2*ox - 3)*3 + 9 = 6*ox
 #pragma unroll
       for (int kb = 0; kb < 3; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         uint8_t* a_hi = smem + stage * STAGE_BYTES + r * 128;
         uint8_t* a_lo = a_hi + A_TILE_BYTES;
+        if (r < p.rows_box) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint32_t e[8];
+          for (int q = 0; q < 8; ++q) {
+            uint32_t e[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = kb * 64 + q * 8 + j;   // compile-time after unrolling
-            uint32_t val = 0;
-            if (col < 147) {
-              const int ky = col / 21, rem = col % 21, kx = rem / 3, c = rem % 3;
-              if (((rowok >> ky) & 1u) && ((colok >> kx) & 1u)) val = __ldg(p.lut + c * 256 + base[ky * row_pitch + rem]);
+            for (int j = 0; j < 8; ++j) {
+              const int col = kb * 64 + q * 8 + j;               // compile-time after unrolling
+              e[j] = (col < 147) ? my[(col / 21) * pitch + (col % 21)] : 0u;
             }
-            e[j] = val;
+            uint4 h, l;
+            h.x = __byte_perm(e[0], e[1], 0x5410); h.y = __byte_perm(e[2], e[3], 0x5410);
+            h.z = __byte_perm(e[4], e[5], 0x5410); h.w = __byte_perm(e[6], e[7], 0x5410);
+            l.x = __byte_perm(e[0], e[1], 0x7632); l.y = __byte_perm(e[2], e[3], 0x7632);
+            l.z = __byte_perm(e[4], e[5], 0x7632); l.w = __byte_perm(e[6], e[7], 0x7632);
+            const int chunk = (q ^ (r & 7)) << 4;
+            *reinterpret_cast<uint4*>(a_hi + chunk) = h;
+            if (p.passes == 3) *reinterpret_cast<uint4*>(a_lo + chunk) = l;
           }
-          uint4 h, l;
-          h.x = __byte_perm(e[0], e[1], 0x5410); h.y = __byte_perm(e[2], e[3], 0x5410);
-          h.z = __byte_perm(e[4], e[5], 0x5410); h.w = __byte_perm(e[6], e[7], 0x5410);
-          l.x = __byte_perm(e[0], e[1], 0x7632); l.y = __byte_perm(e[2], e[3], 0x7632);
-          l.z = __byte_perm(e[4], e[5], 0x7632); l.w = __byte_perm(e[6], e[7], 0x7632);
-          const int chunk = (q ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(a_hi + chunk) = h;
-          if (p.passes == 3) *reinterpret_cast<uint4*>(a_lo + chunk) = l;
         }
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
         mbar_arrive(full_bar(stage));
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");            // everyone done reading s_conv before restaging
     }
   }
 
@@ -474,11 +488,12 @@ EncodeTiledFn get_encode() {
 template <int BN, bool STEM>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * BN * BK * 2;
-  const int smem = kStages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static bool configured = false;
-  if (!configured) {
+  // STEM adds the staged input rows (7 x (W_in*3 + 24) words) and the 3 KB LUT behind the barriers
+  const int smem = kStages * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + (STEM ? 7 * (p.W_in * 3 + 24) * 4 + 768 * 4 : 0);
+  static int configured = 0;
+  if (configured < smem) {
     B200R_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured = smem;
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_img * p.tiles_n;
   const int grid = total < b200r_num_sms() ? total : b200r_num_sms();
@@ -619,10 +634,11 @@ int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* 
   if (rc) return rc;
   const int Ho = h / 2, Wo = w / 2, Cout = 64, K = 192;
   GemmParams p{};
-  p.bn = 1; p.bh = 1; p.bw = 128; p.rows_box = 128;
+  B200R_CHECK_ARG(Wo <= 128, "fused stem supports input widths up to 256");
+  p.bn = 1; p.bh = 1; p.bw = Wo; p.rows_box = Wo;                    // one tile = one output row of one image
   p.M_total = (long long)n * Ho * Wo;
-  p.tiles_w = (int)((p.M_total + 127) / 128); p.tiles_h = 1; p.tiles_img = 1; p.tiles_n = 1;
-  p.N = 1; p.Ho = 1; p.Wo = (int)p.M_total; p.Cout = Cout;          // epilogue sees a flat [M, 64] output
+  p.tiles_w = 1; p.tiles_h = Ho; p.tiles_img = n; p.tiles_n = 1;
+  p.N = n; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
   p.KH = 1; p.KW = 1; p.stride = 1; p.pad = 0; p.cin_blocks = K / 64;
   p.passes = passes; p.act = act; p.scale = scale; p.bias = bias;
   p.y_hi = y; p.y_lo = y + (size_t)p.M_total * Cout;

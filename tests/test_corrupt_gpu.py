@@ -56,10 +56,12 @@ def test_pixel_family_matches_oracle(cuda, name, sev):
     _compare(name, got, want)
 
 
-STENCIL_FAMILY = ["gaussian_blur", "glass_blur", "defocus_blur", "zoom_blur", "motion_blur", "snow"]
-# kernels with a hard threshold / rounding step inside (snow: layer < c3 -> 0; motion: Q16 round half up):
+STENCIL_FAMILY = ["gaussian_blur", "glass_blur", "defocus_blur", "zoom_blur", "motion_blur", "snow", "elastic_transform"]
+# kernels with a hard threshold / rounding step inside (snow: layer < c3 -> 0; motion: Q16 round half up;
+# elastic: OpenCV's 1/32-pixel coordinate quantisation and a displacement field scaled by up to 488 px):
 # an fp32-vs-fp64 tie flips a whole quantisation step at isolated pixels, bounded by OUTLIER_FRAC.
-OUTLIER_FRAC = {"snow": 2e-3, "motion_blur": 1e-3, "glass_blur": 2e-3}
+OUTLIER_FRAC = {"snow": 2e-3, "motion_blur": 1e-3, "glass_blur": 2e-3, "elastic_transform": 5e-3}
+STENCIL_MISMATCH = {"elastic_transform": 0.25}
 
 
 @pytest.mark.parametrize("name", STENCIL_FAMILY)
@@ -72,7 +74,7 @@ def test_stencil_family_matches_oracle(cuda, name, sev):
     outl = (diff > 1).mean()
     assert outl <= OUTLIER_FRAC.get(name, 0.0), f"{name} s{sev}: {outl:.2e} of pixels differ by more than 1 LSB (max {diff.max()})"
     frac = np.count_nonzero(diff) / diff.size
-    assert frac <= 0.03, f"{name} s{sev}: {frac:.4f} of pixels differ"
+    assert frac <= STENCIL_MISMATCH.get(name, 0.03), f"{name} s{sev}: {frac:.4f} of pixels differ"
     # in-place call gives the same bytes
     from robustart_b200 import ops
     d = torch.from_numpy(images).to(cuda)
@@ -90,7 +92,21 @@ def test_pixelate_bit_exact(cuda, sev):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("name", ["elastic_transform", "spatter", "jpeg_compression"])
+@pytest.mark.parametrize("sev", [1, 2, 3, 4, 5])
+def test_jpeg_bit_exact(cuda, sev):
+    """libjpeg's integer pipeline (colour, 4:2:0, islow DCT, quantiser, fancy upsampling) restated exactly:
+    the GPU bytes equal PIL's save(JPEG)+open."""
+    images = synth_images(4, seed=30 + sev)
+    want, _ = oracle_batch(images, "jpeg_compression", sev)
+    got = _run(cuda, "jpeg_compression", sev, images, np.zeros(0, np.float32))
+    assert np.array_equal(got, want)
+    from robustart_b200 import ops
+    d = torch.from_numpy(images).to(cuda)
+    ops.corrupt_u8(d, "jpeg_compression", sev, out=d)           # in place
+    assert np.array_equal(d.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("name", ["spatter"])
 def test_unimplemented_corruptions_fail_loudly(cuda, name):
     from robustart_b200 import ops
     images = torch.zeros((1, 224, 224, 3), dtype=torch.uint8, device=cuda)

@@ -70,3 +70,16 @@ def test_metrics_oracle():
     parts = [OM.sampler_indices(n, w, r) for r in range(w)]
     assert sorted(sum(parts, [])) == list(range(n))
     assert [len(p) for p in parts] == [6251] * 7 + [50001 - 7 * 6251]
+
+
+def test_jpeg_restatement_equals_pil():
+    """oracle/jpeg_restatement.py (the algorithm the CUDA kernel follows) == PIL's libjpeg round trip."""
+    import io
+    from PIL import Image
+    from oracle.jpeg_restatement import jpeg_roundtrip
+    imgs = synth_images(2, seed=3)
+    for q in (25, 18, 15, 10, 7):
+        for i in range(2):
+            o = io.BytesIO()
+            Image.fromarray(imgs[i]).save(o, "JPEG", quality=q)
+            assert np.array_equal(jpeg_roundtrip(imgs[i], q), np.array(Image.open(o)))

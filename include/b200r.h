@@ -198,6 +198,31 @@ int b200r_maxpool3x3s2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w,
 int b200r_global_avgpool_nhwc(const uint16_t* x, uint16_t* y, int n, int hw, int c,
                               b200r_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Token models (ViT-B/16: prototype/prototype/model/vision_transformer.py:44-349; MLP-Mixer-B/16:
+ * prototype/prototype/model/vit/mlp_mixer.py:7-159), split planes [rows, c].
+ * ------------------------------------------------------------------------------------------ */
+/* nn.LayerNorm over the last dimension (biased variance) */
+int b200r_layernorm(const uint16_t* x, uint16_t* y, const float* gamma, const float* beta, int rows,
+                    int c, float eps, b200r_stream_t stream);
+/* patch embedding operand: [n*(h/p)*(w/p), 3*p*p], column = c*p*p + ky*p + kx (== conv weight
+ * .reshape(D, -1)), ToTensor+Normalize fused (u8) / Normalize fused (float NCHW in [0,1]) */
+int b200r_patch_gather_u8(const uint8_t* img, uint16_t* y, int n, int h, int w, int patch,
+                          const float* mean_host, const float* std_host, b200r_stream_t stream);
+int b200r_patch_gather_f32(const float* img, uint16_t* y, int n, int h, int w, int patch,
+                           const float* mean_host, const float* std_host, b200r_stream_t stream);
+/* y[n, 1+np, c] = cat(cls, x[n, np, c]) + pos[1+np, c]   (cls, pos: float32) */
+int b200r_assemble_tokens(const uint16_t* x, const float* cls, const float* pos, uint16_t* y, int n,
+                          int num_patches, int c, b200r_stream_t stream);
+/* out[n*t, h*d] = softmax(q k^T * scale) v with qkv[n*t, 3*h*d] packed "(qkv h d)" */
+int b200r_attention(const uint16_t* qkv, uint16_t* out, int n, int tokens, int heads, int head_dim,
+                    float scale, b200r_stream_t stream);
+/* Mixer token mixing: y[b, c, t_pad] = x[b, t, c] (zero padded), and out[b,t,c] = res[b,t,c] + y[b,c,t] */
+int b200r_tokens_to_channels(const uint16_t* x, uint16_t* y, int b, int t, int c, int t_pad,
+                             b200r_stream_t stream);
+int b200r_channels_to_tokens_add(const uint16_t* y, const uint16_t* res, uint16_t* out, int b, int t,
+                                 int c, int t_pad, b200r_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,3 +100,13 @@ def check(rc: int):
 
 def f3(vals):
     return (C.c_float * 3)(*[float(v) for v in vals])
+
+SIGNATURES.update({
+    "b200r_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, c_stream]),
+    "b200r_patch_gather_u8": (C.c_int, [c_u8p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_host_f3, c_host_f3, c_stream]),
+    "b200r_patch_gather_f32": (C.c_int, [c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_host_f3, c_host_f3, c_stream]),
+    "b200r_assemble_tokens": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_stream]),
+    "b200r_tokens_to_channels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_channels_to_tokens_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+})

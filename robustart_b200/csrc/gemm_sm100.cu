@@ -410,6 +410,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     uint32_t* s_conv = reinterpret_cast<uint32_t*>(smem + kStages * STAGE_BYTES + 512);
     uint32_t* s_lut = s_conv + 7 * pitch;
     for (int i = ptid; i < 768; i += kStemProducerWarps * 32) s_lut[i] = __ldg(p.lut + i);
+    for (int i = ptid; i < 7 * pitch; i += kStemProducerWarps * 32) s_conv[i] = 0u;   // pads stay zero for the whole kernel
     asm volatile("bar.sync 1, 128;" ::: "memory");
     int stage = 0;
     uint32_t phase = 0;
@@ -417,11 +418,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int mt = t / p.tiles_n;
       const int oy = mt % p.tiles_h, n_img = mt / p.tiles_h;
       const uint8_t* img_base = p.img + (long long)n_img * p.H_in * row_bytes;
-      for (int i = ptid; i < 7 * pitch; i += kStemProducerWarps * 32) {
-        const int ky = i / pitch, col = i - ky * pitch, bi = col - 9, iy = oy * 2 - 3 + ky;
-        uint32_t val = 0;
-        if (iy >= 0 && iy < p.H_in && bi >= 0 && bi < row_bytes) val = s_lut[(bi % 3) * 256 + img_base[(long long)iy * row_bytes + bi]];
-        s_conv[i] = val;
+      // stage the 7 input rows: 16-byte loads (all issued before first use), bytes -> LUT words
+      {
+        const int q_per_row = row_bytes / 16;                   // 42 for W = 224
+        constexpr int kMaxIt = 4;                               // ceil(7*q_per_row / 128) for W <= 256 (requires row_bytes % 16 == 0)
+        uint4 v[kMaxIt];
+        int dstw[kMaxIt];
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+          const int idx = ptid + it * (kStemProducerWarps * 32);
+          dstw[it] = -1;
+          v[it] = make_uint4(0, 0, 0, 0);
+          if (idx < 7 * q_per_row) {
+            const int ky = idx / q_per_row, q = idx - ky * q_per_row, iy = oy * 2 - 3 + ky;
+            dstw[it] = ky * pitch + 9 + q * 16;
+            if (iy >= 0 && iy < p.H_in) v[it] = __ldg(reinterpret_cast<const uint4*>(img_base + (long long)iy * row_bytes) + q);
+            else dstw[it] = -(ky * pitch + 9 + q * 16) - 2;     // out-of-image row: store zeros
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+          if (dstw[it] == -1) continue;
+          const bool zero = dstw[it] < 0;
+          const int d0 = zero ? -(dstw[it] + 2) : dstw[it];
+          const uint32_t w4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+          const int c0 = (d0 - 9 - (d0 / pitch) * pitch) % 3;   // channel of the first byte of this 16-byte group
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t b = (w4[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            const int c = (c0 + j) % 3;
+            s_conv[d0 + j] = zero ? 0u : s_lut[c * 256 + b];
+          }
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t* my = s_conv + 6 * r;                      // (2*ox - 3)*3 + 9 = 6*ox
@@ -634,7 +662,7 @@ int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* 
   if (rc) return rc;
   const int Ho = h / 2, Wo = w / 2, Cout = 64, K = 192;
   GemmParams p{};
-  B200R_CHECK_ARG(Wo <= 128, "fused stem supports input widths up to 256");
+  B200R_CHECK_ARG(Wo <= 128 && w % 16 == 0, "fused stem supports input widths up to 256, multiples of 16");
   p.bn = 1; p.bh = 1; p.bw = Wo; p.rows_box = Wo;                    // one tile = one output row of one image
   p.M_total = (long long)n * Ho * Wo;
   p.tiles_w = 1; p.tiles_h = Ho; p.tiles_img = n; p.tiles_n = 1;

@@ -237,3 +237,199 @@ def build_model(arch: str, state_dict=None, device="cuda", passes: int = 3, seed
     if state_dict is None:
         state_dict = random_state_dict(resnet_spec(arch), seed)
     return ResNet(arch, state_dict, device, passes)
+
+
+# ================================================================================================
+# Token models: ViT-B/16 (prototype/prototype/model/vision_transformer.py:198-349,420-436; config
+# model_config.py:216-225 -> representation_size 768) and MLP-Mixer-B/16 (vit/mlp_mixer.py:7-159).
+# ================================================================================================
+def vit_spec(depth=12, dim=768, mlp=3072, patch=16, img=224, classes=1000, rep=768):
+    np_ = (img // patch) ** 2
+    spec = [("pos_embedding", (1, np_ + 1, dim)), ("cls_token", (1, 1, dim)),
+            ("embedding.weight", (dim, 3, patch, patch)), ("embedding.bias", (dim,))]
+    for d in range(depth):
+        p = "transformer.encoders.encoder_%d." % d
+        spec += [(p + "norm1.weight", (dim,)), (p + "norm1.bias", (dim,)),
+                 (p + "attention.to_qkv.weight", (3 * dim, dim)), (p + "attention.to_qkv.bias", (3 * dim,)),
+                 (p + "attention.to_out.weight", (dim, dim)), (p + "attention.to_out.bias", (dim,)),
+                 (p + "norm2.weight", (dim,)), (p + "norm2.bias", (dim,)),
+                 (p + "feedforward.mlp1.weight", (mlp, dim)), (p + "feedforward.mlp1.bias", (mlp,)),
+                 (p + "feedforward.mlp2.weight", (dim, mlp)), (p + "feedforward.mlp2.bias", (dim,))]
+    spec += [("transformer.encoder_norm.weight", (dim,)), ("transformer.encoder_norm.bias", (dim,))]
+    if rep:
+        spec += [("pre_logits.weight", (rep, dim)), ("pre_logits.bias", (rep,))]
+    spec += [("head.weight", (classes, rep or dim)), ("head.bias", (classes,))]
+    return spec
+
+
+def mixer_spec(depth=12, dim=768, patch=16, img=224, classes=1000, token_ratio=0.5, channel_ratio=4.0):
+    np_ = (img // patch) ** 2
+    tok, ch = round(dim * token_ratio), round(dim * channel_ratio)
+    spec = [("patch_embed.proj.weight", (dim, 3, patch, patch)), ("patch_embed.proj.bias", (dim,))]
+    for d in range(depth):
+        p = "blocks.%d." % d
+        spec += [(p + "norm1.weight", (dim,)), (p + "norm1.bias", (dim,)), (p + "norm2.weight", (dim,)), (p + "norm2.bias", (dim,)),
+                 (p + "token_mix.fc1.weight", (tok, np_)), (p + "token_mix.fc1.bias", (tok,)),
+                 (p + "token_mix.fc2.weight", (np_, tok)), (p + "token_mix.fc2.bias", (np_,)),
+                 (p + "channel_mix.fc1.weight", (ch, dim)), (p + "channel_mix.fc1.bias", (ch,)),
+                 (p + "channel_mix.fc2.weight", (dim, ch)), (p + "channel_mix.fc2.bias", (dim,))]
+    spec += [("norm.weight", (dim,)), ("norm.bias", (dim,)), ("head.weight", (classes, dim)), ("head.bias", (classes,))]
+    return spec
+
+
+def random_token_state_dict(spec, seed=0):
+    """Synthetic weights for the token models: Linear ~ N(0, 1/fan_in) so activations keep O(1) scale through 12
+    blocks, LayerNorm affine and biases non-trivial, embeddings N(0, 0.02)."""
+    import zlib
+    out = {}
+    for key, shape in spec:
+        g = torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * seed) & 0x7FFFFFFF)
+        if key in ("pos_embedding", "cls_token"):
+            t = torch.randn(shape, generator=g) * 0.02
+        elif len(shape) == 4:
+            t = torch.randn(shape, generator=g) * (1.0 / (shape[1] * shape[2] * shape[3])) ** 0.5
+        elif len(shape) == 2:
+            t = torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
+        elif "norm" in key and key.endswith("weight"):
+            t = torch.rand(shape, generator=g) * 0.5 + 0.75
+        else:
+            t = torch.randn(shape, generator=g) * 0.05
+        out[key] = t
+    return out
+
+
+class _Lin:
+    def __init__(self, sd, name, device, k_pad=None, n_pad=None):
+        w, b = sd[name + ".weight"].float(), sd[name + ".bias"].float()
+        if k_pad or n_pad:
+            wp = torch.zeros(n_pad or w.shape[0], k_pad or w.shape[1])
+            wp[:w.shape[0], :w.shape[1]] = w
+            bp = torch.zeros(n_pad or w.shape[0])
+            bp[:b.shape[0]] = b
+            w, b = wp, bp
+        self.w = ops.split_f32(w.contiguous().to(device))
+        self.b = b.contiguous().to(device)
+
+    def __call__(self, x, act=None, res=None, passes=3, out_f32=None):
+        if out_f32 is not None:
+            return ops.linear(x, self.w, None, self.b, res, act=act, passes=passes, out_f32=out_f32, want_planes=False)
+        return ops.linear(x, self.w, None, self.b, res, act=act, passes=passes)
+
+
+class _TokenModel:
+    def __init__(self, device, passes):
+        self.device, self.passes = torch.device(device), passes
+        self._graphs = {}
+
+    graphed = ResNet.graphed
+    __call__ = lambda self, images, logits=None: self.forward(images, logits)
+
+
+class ViT(_TokenModel):
+    def __init__(self, state_dict, device, passes=3, depth=12, dim=768, heads=12, patch=16):
+        super().__init__(device, passes)
+        sd = _strip_prefix(state_dict)
+        dev = self.device
+        self.arch, self.depth, self.dim, self.heads, self.patch = "vit_b16_224", depth, dim, heads, patch
+        self.embed = _Lin({"e.weight": sd["embedding.weight"].reshape(dim, -1), "e.bias": sd["embedding.bias"]}, "e", dev)
+        self.cls = sd["cls_token"].float().reshape(-1).contiguous().to(dev)
+        self.pos = sd["pos_embedding"].float().reshape(-1, dim).contiguous().to(dev)
+        self.blocks = []
+        for d in range(depth):
+            p = "transformer.encoders.encoder_%d." % d
+            self.blocks.append(dict(
+                n1=(sd[p + "norm1.weight"].float().to(dev), sd[p + "norm1.bias"].float().to(dev)),
+                n2=(sd[p + "norm2.weight"].float().to(dev), sd[p + "norm2.bias"].float().to(dev)),
+                qkv=_Lin(sd, p + "attention.to_qkv", dev), out=_Lin(sd, p + "attention.to_out", dev),
+                m1=_Lin(sd, p + "feedforward.mlp1", dev), m2=_Lin(sd, p + "feedforward.mlp2", dev)))
+        self.norm = (sd["transformer.encoder_norm.weight"].float().to(dev), sd["transformer.encoder_norm.bias"].float().to(dev))
+        self.pre = _Lin(sd, "pre_logits", dev) if "pre_logits.weight" in sd else None
+        self.head = _Lin(sd, "head", dev)
+        self.num_classes = sd["head.weight"].shape[0]
+
+    def forward(self, images, logits=None):
+        n = images.shape[0]
+        P = self.passes
+        x = self.embed(ops.patch_gather(images, self.patch), passes=P)              # [n*196, 768]
+        npatch = x.shape[1] // n
+        x = ops.assemble_tokens(x, self.cls, self.pos, n, npatch)                   # [n*197, 768]
+        T = npatch + 1
+        scale = (self.dim // self.heads) ** -0.5
+        for b in self.blocks:
+            y = ops.layernorm(x, *b["n1"], eps=1e-5)
+            y = ops.attention(b["qkv"](y, passes=P), n, T, self.heads, self.dim // self.heads, scale)
+            x = b["out"](y, res=x, passes=P)                                        # x = attn(norm1(x)) + x
+            y = ops.layernorm(x, *b["n2"], eps=1e-5)
+            y = b["m1"](y, act="gelu_tanh", passes=P)                               # tanh-approx GELU (:19-37)
+            x = b["m2"](y, res=x, passes=P)
+        x = ops.layernorm(x, *self.norm, eps=1e-5)
+        cls = x.view(2, n, T, self.dim)[:, :, 0].contiguous()                       # x[:, 0]
+        if self.pre is not None:
+            cls = self.pre(cls, act="tanh", passes=P)
+        if logits is None:
+            logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
+        self.head(cls, passes=P, out_f32=logits)
+        return logits
+
+    def launches_per_forward(self):
+        return 2 + 1 + self.depth * 7 + 1 + 1 + (1 if self.pre else 0) + 1
+
+
+class Mixer(_TokenModel):
+    T_PAD = 256   # token dimension padded so that the [b*c, t] rows are 16-byte aligned and K is a multiple of 64
+
+    def __init__(self, state_dict, device, passes=3, depth=12, dim=768, patch=16):
+        super().__init__(device, passes)
+        sd = _strip_prefix(state_dict)
+        dev = self.device
+        self.arch, self.depth, self.dim, self.patch = "mixer_b16_224", depth, dim, patch
+        self.embed = _Lin({"e.weight": sd["patch_embed.proj.weight"].reshape(dim, -1), "e.bias": sd["patch_embed.proj.bias"]}, "e", dev)
+        self.blocks = []
+        for d in range(depth):
+            p = "blocks.%d." % d
+            tok = sd[p + "token_mix.fc1.weight"].shape[0]
+            self.blocks.append(dict(
+                n1=(sd[p + "norm1.weight"].float().to(dev), sd[p + "norm1.bias"].float().to(dev)),
+                n2=(sd[p + "norm2.weight"].float().to(dev), sd[p + "norm2.bias"].float().to(dev)),
+                t1=_Lin(sd, p + "token_mix.fc1", dev, k_pad=self.T_PAD), t2=_Lin(sd, p + "token_mix.fc2", dev, n_pad=self.T_PAD),
+                c1=_Lin(sd, p + "channel_mix.fc1", dev), c2=_Lin(sd, p + "channel_mix.fc2", dev), tok=tok))
+        self.norm = (sd["norm.weight"].float().to(dev), sd["norm.bias"].float().to(dev))
+        self.head = _Lin(sd, "head", dev)
+        self.num_classes = sd["head.weight"].shape[0]
+
+    def forward(self, images, logits=None):
+        n = images.shape[0]
+        P = self.passes
+        x = self.embed(ops.patch_gather(images, self.patch), passes=P)              # [n*196, 768]
+        T = x.shape[1] // n
+        for b in self.blocks:
+            y = ops.layernorm(x, *b["n1"], eps=1e-6)                                # vit_base.py:159
+            y = ops.tokens_to_channels(y, n, T, self.dim, self.T_PAD)               # [n*768, 256] (zero padded)
+            y = b["t1"](y, act="gelu_erf", passes=P)                                # nn.GELU (erf)
+            y = b["t2"](y, passes=P)                                                # [n*768, 256], columns >= 196 are 0
+            x = ops.channels_to_tokens_add(y, x, n, T, self.dim, self.T_PAD)        # x + token_mix(...)^T
+            y = ops.layernorm(x, *b["n2"], eps=1e-6)
+            y = b["c1"](y, act="gelu_erf", passes=P)
+            x = b["c2"](y, res=x, passes=P)
+        x = ops.layernorm(x, *self.norm, eps=1e-6)
+        pooled = ops.global_avgpool(x.view(2, n, T, 1, self.dim))                   # x.mean(dim=1)
+        if logits is None:
+            logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
+        self.head(pooled, passes=P, out_f32=logits)
+        return logits
+
+    def launches_per_forward(self):
+        return 2 + self.depth * 8 + 1 + 1 + 1
+
+
+_TOKEN_ARCHS = {"vit_b16_224": (ViT, vit_spec), "vit_base_patch16_224": (ViT, vit_spec), "mixer_b16_224": (Mixer, mixer_spec)}
+_build_resnet = build_model
+
+
+def build_model(arch: str, state_dict=None, device="cuda", passes: int = 3, seed: int = 0):  # noqa: F811
+    if arch in _TOKEN_ARCHS:
+        cls, spec = _TOKEN_ARCHS[arch]
+        if state_dict is None:
+            state_dict = random_token_state_dict(spec(), seed)
+        return cls(state_dict, device, passes)
+    return _build_resnet(arch, state_dict, device, passes, seed)

@@ -323,3 +323,62 @@ def global_avgpool(x, out=None):
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().b200r_global_avgpool_nhwc(x.data_ptr(), out.data_ptr(), n, h * w, c, _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# token-model layers (ViT / MLP-Mixer)
+# ------------------------------------------------------------------------------------------------
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    """x: planes [2, rows, c]."""
+    _need_cuda(x, torch.int16, "x")
+    c = x.shape[-1]
+    rows = x[0].numel() // c
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_layernorm(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, c, eps, _stream()))
+    return out
+
+
+def patch_gather(img, patch=16, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """uint8 NHWC or float32 NCHW batch -> planes [2, n*(h/p)*(w/p), 3*p*p]."""
+    if img.dtype == torch.uint8:
+        n, h, w, _ = img.shape
+        fn = _lib.load().b200r_patch_gather_u8
+    else:
+        _need_cuda(img, torch.float32, "img")
+        n, _, h, w = img.shape
+        fn = _lib.load().b200r_patch_gather_f32
+    out = torch.empty((2, n * (h // patch) * (w // patch), 3 * patch * patch), dtype=torch.int16, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(fn(img.data_ptr(), out.data_ptr(), n, h, w, patch, _lib.f3(mean), _lib.f3(std), _stream()))
+    return out
+
+
+def assemble_tokens(x, cls, pos, n, num_patches):
+    c = x.shape[-1]
+    out = torch.empty((2, n * (num_patches + 1), c), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_assemble_tokens(x.data_ptr(), cls.data_ptr(), pos.data_ptr(), out.data_ptr(), n, num_patches, c, _stream()))
+    return out
+
+
+def attention(qkv, n, tokens, heads, head_dim, scale):
+    out = torch.empty((2, n * tokens, heads * head_dim), dtype=torch.int16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.load().b200r_attention(qkv.data_ptr(), out.data_ptr(), n, tokens, heads, head_dim, scale, _stream()))
+    return out
+
+
+def tokens_to_channels(x, b, t, c, t_pad):
+    out = torch.empty((2, b * c, t_pad), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_tokens_to_channels(x.data_ptr(), out.data_ptr(), b, t, c, t_pad, _stream()))
+    return out
+
+
+def channels_to_tokens_add(y, res, b, t, c, t_pad):
+    out = torch.empty((2, b * t, c), dtype=torch.int16, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.load().b200r_channels_to_tokens_add(y.data_ptr(), res.data_ptr(), out.data_ptr(), b, t, c, t_pad, _stream()))
+    return out

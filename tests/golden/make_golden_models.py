@@ -93,3 +93,36 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def token_models():
+    """ViT-B/16 (representation_size 768, model_config.py:216-225) and MLP-Mixer-B/16 golden logits."""
+    from util import synth_images
+    from robustart_b200 import nets
+    shim()
+    sys.path.insert(0, REF)
+    for k in [k for k in sys.modules if k == "prototype" or k.startswith("prototype.")]:
+        del sys.modules[k]
+    import prototype.prototype.model.vision_transformer as V
+    import prototype.prototype.model.vit.mlp_mixer as MX
+    assert V.__file__.startswith(REF) and MX.__file__.startswith(REF)
+    images = synth_images(2, seed=9)
+    x = torch.from_numpy(images).permute(0, 3, 1, 2).float().div(255)
+    xn = (x - torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)) / torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    out = {}
+    for name, model, spec in (("vit_b16_224", V.vit_b16_224(drop_path=0.0, dropout=0.0, attention_dropout=0.0, qkv_bias=True,
+                                                            representation_size=768), nets.vit_spec()),
+                              ("mixer_b16_224", MX.mixer_b16_224(), nets.mixer_spec())):
+        ref_sd = model.state_dict()
+        assert [(k, tuple(v.shape)) for k, v in ref_sd.items()] == [(k, tuple(s)) for k, s in spec], name
+        model.load_state_dict(nets.random_token_state_dict(spec, 0), strict=True)
+        model.eval()
+        with torch.no_grad():
+            lg = model(xn)
+        out[name] = lg.numpy()
+        print(name, "logits abs max %.3f std %.3f" % (lg.abs().max(), lg.std()), lg.argmax(1).tolist())
+    np.savez(os.path.join(HERE, "token_logits.npz"), **out)
+
+
+if __name__ == "__main__" and "--tokens" in sys.argv:
+    token_models()

@@ -1,0 +1,61 @@
+"""ViT-B/16 and MLP-Mixer-B/16 on the B200 kernels: layer checks vs torch and golden logits from the
+REFERENCE's own classes (tests/golden/make_golden_models.py --tokens).  Tolerance 1e-3 on logits."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import synth_images
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "token_logits.npz"))
+
+
+def test_layernorm_and_attention_layers(cuda):
+    from robustart_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(3 * 197, 768, device=cuda) * 2 + 0.3
+    g, b = torch.rand(768, device=cuda) + 0.5, torch.randn(768, device=cuda)
+    for eps in (1e-5, 1e-6):
+        y = ops.merge_f32(ops.layernorm(ops.split_f32(x), g, b, eps=eps))
+        xs = ops.merge_f32(ops.split_f32(x))
+        ref = torch.nn.functional.layer_norm(xs.double(), (768,), g.double(), b.double(), eps)
+        assert (y.double() - ref).abs().max().item() < 2e-4
+    qkv = torch.randn(3 * 197, 3 * 768, device=cuda)
+    out = ops.merge_f32(ops.attention(ops.split_f32(qkv), 3, 197, 12, 64, 64 ** -0.5))
+    q, k, v = ops.merge_f32(ops.split_f32(qkv)).double().view(3, 197, 3, 12, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 64 ** -0.5, -1) @ v).permute(0, 2, 1, 3).reshape(3 * 197, 768)
+    assert (out.double() - ref).abs().max().item() < 2e-4
+
+
+def test_token_transposes_and_patches(cuda):
+    from robustart_b200 import ops
+    torch.manual_seed(1)
+    x = torch.randn(2, 196, 768, device=cuda)
+    xp = ops.split_f32(x.view(2 * 196, 768))
+    y = ops.merge_f32(ops.tokens_to_channels(xp, 2, 196, 768, 256)).view(2, 768, 256)
+    xm = ops.merge_f32(xp).view(2, 196, 768)
+    assert torch.equal(y[:, :, :196], xm.transpose(1, 2)) and y[:, :, 196:].abs().max().item() == 0
+    back = ops.merge_f32(ops.channels_to_tokens_add(ops.split_f32(y.reshape(2 * 768, 256)), xp, 2, 196, 768, 256)).view(2, 196, 768)
+    assert (back - 2 * xm).abs().max().item() < 1e-5
+    img = torch.randint(0, 256, (2, 224, 224, 3), dtype=torch.uint8, device=cuda)
+    cols = ops.merge_f32(ops.patch_gather(img, 16)).view(2, 196, 768)
+    ref = torch.nn.functional.unfold(ops.u8nhwc_to_f32nchw(img), 16, stride=16).transpose(1, 2)   # (c, ky, kx) columns
+    assert (cols - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("arch", ["vit_b16_224", "mixer_b16_224"])
+def test_token_model_logits_match_reference(cuda, arch):
+    from robustart_b200 import nets
+    model = nets.build_model(arch, device=cuda, seed=0)
+    images = torch.from_numpy(synth_images(2, seed=9)).to(cuda)
+    got = model(images).cpu().numpy()
+    want = GOLD[arch]
+    err = np.abs(got - want).max()
+    assert err < 1e-3, (arch, err)
+    assert (got.argmax(1) == want.argmax(1)).all()
+    for g, w in zip(got, want):
+        assert set(np.argsort(-g)[:5]) == set(np.argsort(-w)[:5])
+    x01 = images.permute(0, 3, 1, 2).float().div(255).contiguous()
+    assert np.abs(model(x01).cpu().numpy() - got).max() < 1e-4

@@ -147,7 +147,7 @@ int b200r_topk_count(const float* logits, const int64_t* labels, int n, int clas
  * ------------------------------------------------------------------------------------------ */
 enum b200r_act { B200R_ACT_NONE = 0, B200R_ACT_RELU = 1, B200R_ACT_RELU6 = 2,
                  B200R_ACT_GELU_TANH = 3, B200R_ACT_GELU_ERF = 4, B200R_ACT_SWISH = 5,
-                 B200R_ACT_TANH = 6 };
+                 B200R_ACT_TANH = 6, B200R_ACT_SIGMOID = 7 };
 
 /* split a float32 tensor into hi/lo bf16 planes: planes[0:count] = hi, planes[count:2count] = lo */
 int b200r_split_f32(const float* in, uint16_t* planes, size_t count, b200r_stream_t stream);
@@ -155,8 +155,8 @@ int b200r_merge_f32(const uint16_t* planes, float* out, size_t count, b200r_stre
 
 /* Implicit-GEMM convolution, NHWC, replaces nn.Conv2d(bias=False)+BatchNorm2d(eval)+act(+residual)
  * (resnet_official.py:71-140,330-346).
- *   x      : split planes of [n, h, w, cin]           (cin % 64 == 0)
- *   wgt    : split planes of [cout, kh, kw, cin]      (cout % 64 == 0)
+ *   x      : split planes of [n, h, w, cin]           (cin % 8 == 0; K tails are zero-filled by TMA)
+ *   wgt    : split planes of [cout, kh, kw, cin]      (any cout; cout % 16 == 0 takes the vector epilogue)
  *   scale, bias : float32 [cout] (folded BN; nullable = 1 / 0)
  *   res    : split planes of [n, ho, wo, cout] added before the activation (nullable)
  *   y      : split planes of [n, ho, wo, cout] (nullable if y_f32 given)
@@ -169,7 +169,7 @@ int b200r_conv2d_nhwc(const uint16_t* x, const uint16_t* wgt, const float* scale
                       b200r_stream_t stream);
 
 /* y[m, nout] = act(x[m,k] . wgt[nout,k]^T * scale + bias (+res)) -- nn.Linear (fc heads, ViT/Mixer
- * MLPs).  k % 64 == 0; nout arbitrary (tiles are masked). */
+ * MLPs).  k % 8 == 0; nout arbitrary (tiles are masked). */
 int b200r_linear(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias,
                  const uint16_t* res, uint16_t* y, float* y_f32, int m, int k, int nout, int act,
                  int passes, b200r_stream_t stream);
@@ -197,6 +197,26 @@ int b200r_maxpool3x3s2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w,
 /* AdaptiveAvgPool2d(1) on split planes NHWC -> split planes [n, c] (resnet_official.py:238) */
 int b200r_global_avgpool_nhwc(const uint16_t* x, uint16_t* y, int n, int hw, int c,
                               b200r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Mobile families (MobileNetV2: prototype/prototype/model/mobilenet_v2.py:31-202; EfficientNet-B0:
+ * prototype/prototype/model/efficientnet.py:289-495): the layers that are not dense contractions.
+ * ------------------------------------------------------------------------------------------ */
+/* depthwise k x k conv + folded BN + act on split planes NHWC.  wgt: float32 [k*k][c] (tap major) */
+int b200r_dwconv_nhwc(const uint16_t* x, const float* wgt, const float* scale, const float* bias,
+                      uint16_t* y, int n, int h, int w, int c, int k, int stride, int pad, int act,
+                      b200r_stream_t stream);
+/* squeeze-excite scaling: y[n, p, c] = x[n, p, c] * s[n, c]  (s: split planes [n, s_stride]) */
+int b200r_channel_scale(const uint16_t* x, const uint16_t* s, uint16_t* y, int n, int hw, int c,
+                        int s_stride, b200r_stream_t stream);
+/* k x k patches of the 3-channel input image as a GEMM operand: planes [n*ho*wo, kpad],
+ * column = (ky*k + kx)*3 + c, zero padded to kpad; ToTensor+Normalize fused */
+int b200r_image_im2col_u8(const uint8_t* img, uint16_t* planes, int n, int h, int w, int k, int stride,
+                          int pad, int kpad, const float* mean_host, const float* std_host,
+                          b200r_stream_t stream);
+int b200r_image_im2col_f32(const float* img, uint16_t* planes, int n, int h, int w, int k, int stride,
+                           int pad, int kpad, const float* mean_host, const float* std_host,
+                           b200r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Token models (ViT-B/16: prototype/prototype/model/vision_transformer.py:44-349; MLP-Mixer-B/16:

@@ -110,3 +110,13 @@ SIGNATURES.update({
     "b200r_tokens_to_channels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_channels_to_tokens_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
 })
+
+SIGNATURES.update({
+    "b200r_dwconv_nhwc": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_channel_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_image_im2col_u8": (C.c_int, [c_u8p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_host_f3,
+                                        c_host_f3, c_stream]),
+    "b200r_image_im2col_f32": (C.c_int, [c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_host_f3,
+                                         c_host_f3, c_stream]),
+})

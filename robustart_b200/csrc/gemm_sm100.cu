@@ -160,7 +160,7 @@ struct GemmParams {
   int tiles_w, tiles_h, tiles_img;    // M tiling
   int tiles_n;                        // N tiling
   int N, Ho, Wo, Cout;
-  int KH, KW, stride, pad, cin_blocks;  // cin_blocks = Cin / 64
+  int KH, KW, stride, pad, cin_blocks, cin;  // cin_blocks = ceil(Cin / 64)
   int passes, act;
   const float* scale;
   const float* bias;
@@ -189,8 +189,63 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case B200R_ACT_GELU_ERF: return 0.5f * v * (1.f + erff(v * 0.7071067811865476f));
     case B200R_ACT_SWISH: return v / (1.f + expf(-v));
     case B200R_ACT_TANH: return tanhf(v);
+    case B200R_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
     default: return v;
   }
+}
+
+// vector epilogue for NC (32 or 16) consecutive output channels of one pixel
+template <int NC>
+__device__ __forceinline__ void epi_vec(const GemmParams& p, const uint32_t* v, size_t off, int col0) {
+  float f[NC];
+#pragma unroll
+            for (int q = 0; q < NC / 4; ++q) {
+              const float4 s4 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + col0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+              const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+              f[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), s4.x, b4.x);
+              f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, b4.y);
+              f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, b4.z);
+              f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, b4.w);
+            }
+            if (p.res_hi) {
+#pragma unroll
+              for (int q = 0; q < NC / 16; ++q) {
+                uint32_t hw[8], lw[8];
+                ld_global_v8(p.res_hi + off + 16 * q, hw);
+                ld_global_v8(p.res_lo + off + 16 * q, lw);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  f[16 * q + 2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                  f[16 * q + 2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+                }
+              }
+            }
+            if (p.act == B200R_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.f);
+            } else if (p.act != B200R_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < NC; ++j) f[j] = apply_act(f[j], p.act);
+            }
+            if (p.y_f32) {
+#pragma unroll
+              for (int q = 0; q < NC / 4; ++q)
+                reinterpret_cast<float4*>(p.y_f32 + off)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            }
+            if (p.y_hi) {
+              uint32_t ph[NC / 2], pl[NC / 2];
+#pragma unroll
+              for (int j = 0; j < NC / 2; ++j) {
+                ph[j] = cvt_bf16x2(f[2 * j + 1], f[2 * j]);
+                const float h0 = __uint_as_float(ph[j] << 16), h1 = __uint_as_float(ph[j] & 0xFFFF0000u);
+                pl[j] = cvt_bf16x2(f[2 * j + 1] - h1, f[2 * j] - h0);
+              }
+#pragma unroll
+              for (int q = 0; q < NC / 16; ++q) {
+                st_global_v8(p.y_hi + off + 16 * q, ph + 8 * q);
+                st_global_v8(p.y_lo + off + 16 * q, pl + 8 * q);
+              }
+            }
 }
 
 template <int BN, bool STEM>
@@ -254,7 +309,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               mbar_wait(empty_bar(stage), phase ^ 1);
               const uint32_t sa = smem_base + stage * STAGE_BYTES;
               mbar_expect_tx(full_bar(stage), tx_bytes);
-              const int kcol = ((kh * p.KW + kw) * p.cin_blocks + cb) * BK;
+              const int kcol = (kh * p.KW + kw) * p.cin + cb * BK;
               if (!STEM) tma_load_5d(sa, &map_a, full_bar(stage), cb * BK, w_in0 + kw, h_in0 + kh, n0, 0);
               tma_load_3d(sa + 2 * A_TILE_BYTES, &map_b, full_bar(stage), kcol, nt * BN, 0);
               if (p.passes == 3) {
@@ -329,55 +384,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (row_ok && col0 < p.Cout) {
           const size_t off = out_row * p.Cout + col0;
           const bool full = (col0 + 32 <= p.Cout) && (p.Cout % 16 == 0);
-          float f[32];
           if (full) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 s4 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + col0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
-              const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-              f[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), s4.x, b4.x);
-              f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, b4.y);
-              f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, b4.z);
-              f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, b4.w);
-            }
-            if (p.res_hi) {
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                uint32_t hw[8], lw[8];
-                ld_global_v8(p.res_hi + off + 16 * q, hw);
-                ld_global_v8(p.res_lo + off + 16 * q, lw);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  f[16 * q + 2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-                  f[16 * q + 2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
-                }
-              }
-            }
-            if (p.act == B200R_ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            } else if (p.act != B200R_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-            }
-            if (p.y_f32) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                reinterpret_cast<float4*>(p.y_f32 + off)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-            }
-            if (p.y_hi) {
-              uint32_t ph[16], pl[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                ph[j] = cvt_bf16x2(f[2 * j + 1], f[2 * j]);
-                const float h0 = __uint_as_float(ph[j] << 16), h1 = __uint_as_float(ph[j] & 0xFFFF0000u);
-                pl[j] = cvt_bf16x2(f[2 * j + 1] - h1, f[2 * j] - h0);
-              }
-              st_global_v8(p.y_hi + off, ph);
-              st_global_v8(p.y_hi + off + 16, ph + 8);
-              st_global_v8(p.y_lo + off, pl);
-              st_global_v8(p.y_lo + off + 16, pl + 8);
-            }
+            epi_vec<32>(p, v, off, col0);
+          } else if (p.Cout % 16 == 0 && col0 + 16 <= p.Cout) {
+            epi_vec<16>(p, v, off, col0);      // Cout = 16, 48, 80, ...: the last chunk is half full
           } else {
             // ragged last column chunk (e.g. fc: 1000 = 31*32 + 8): scalar path
             for (int j = 0; j < 32 && col0 + j < p.Cout; ++j) {
@@ -555,10 +565,10 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
               uint16_t* y, float* y_f32, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
               int act, int passes, bool flat2d, cudaStream_t s) {
   B200R_CHECK_ARG(x && wgt && (y || y_f32), "null pointer");
-  B200R_CHECK_ARG(Cin % 64 == 0, "cin (%d) must be a multiple of 64", Cin);
+  // K tails (Cin % 64 != 0) ride on TMA out-of-bounds zero fill of the activation's channel dimension
+  B200R_CHECK_ARG(Cin % 8 == 0, "cin (%d) must be a multiple of 8 (16-byte TMA strides)", Cin);
   B200R_CHECK_ARG(passes == 1 || passes == 3, "passes must be 1 or 3");
   B200R_CHECK_ARG(stride >= 1 && stride <= 8 && KH >= 1 && KW >= 1 && pad >= 0, "bad conv geometry");
-  B200R_CHECK_ARG(Cout % 8 == 0 || (!y && !res), "cout must be a multiple of 8 for split-plane output");
   EncodeTiledFn enc = get_encode();
   if (!enc) { b200r_set_error("cuTensorMapEncodeTiled not available from the driver"); return B200R_ECUDA; }
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
@@ -573,7 +583,7 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
   const int BN = (Cout <= 64) ? 64 : 128;
   p.tiles_n = (Cout + BN - 1) / BN;
   p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
-  p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.cin_blocks = Cin / 64;
+  p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.cin_blocks = (Cin + 63) / 64; p.cin = Cin;
   p.passes = passes; p.act = act; p.scale = scale; p.bias = bias;
   p.res_hi = res; p.res_lo = res ? res + ycount : nullptr;
   p.y_hi = y; p.y_lo = y ? y + ycount : nullptr; p.y_f32 = y_f32;
@@ -667,7 +677,7 @@ int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* 
   p.M_total = (long long)n * Ho * Wo;
   p.tiles_w = 1; p.tiles_h = Ho; p.tiles_img = n; p.tiles_n = 1;
   p.N = n; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
-  p.KH = 1; p.KW = 1; p.stride = 1; p.pad = 0; p.cin_blocks = K / 64;
+  p.KH = 1; p.KW = 1; p.stride = 1; p.pad = 0; p.cin_blocks = K / 64; p.cin = K;
   p.passes = passes; p.act = act; p.scale = scale; p.bias = bias;
   p.y_hi = y; p.y_lo = y + (size_t)p.M_total * Cout;
   p.img = img; p.lut = lut; p.H_in = h; p.W_in = w;

@@ -1,0 +1,193 @@
+// Layers of the mobile families (MobileNetV2, EfficientNet-B0) that are NOT dense contractions, on split-bf16
+// planes NHWC.  All HBM-bound, CUDA cores, fp32 math.
+//   depthwise conv k x k (3 or 5), stride 1/2, pad k/2 + folded BN + ReLU6 / swish
+//        mobilenet_v2.py:31-47,65 (ConvBNReLU groups=hidden); efficientnet.py:322-336
+//   squeeze-excite channel scaling  out = x * w[n, c]      efficientnet.py:352-355
+//   small-K im2col of the input image for the 3x3/s2 stems (mobilenet_v2.py:130, efficientnet.py:429-433)
+#include "common.cuh"
+
+namespace {
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void unpack8(uint4 h, uint4 l, float* v) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+    v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint16_t h0, l0, h1, l1;
+    split_bf16(v[2 * j], h0, l0);
+    split_bf16(v[2 * j + 1], h1, l1);
+    hw[j] = h0 | ((uint32_t)h1 << 16);
+    lw[j] = l0 | ((uint32_t)l1 << 16);
+  }
+  h = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case B200R_ACT_RELU: return fmaxf(v, 0.f);
+    case B200R_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
+    case B200R_ACT_SWISH: return v / (1.f + expf(-v));
+    case B200R_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+// thread = (output pixel, 8 channels); weights [k*k][c] float32 (tap major: coalesced across channels)
+__global__ void __launch_bounds__(kThreads) dwconv_kernel(const uint4* __restrict__ xh, const uint4* __restrict__ xl,
+                                                           const float* __restrict__ wgt, const float* __restrict__ scale,
+                                                           const float* __restrict__ bias, uint4* __restrict__ yh,
+                                                           uint4* __restrict__ yl, int n, int h, int w, int c8, int k, int stride,
+                                                           int pad, int ho, int wo, int act) {
+  const size_t total = (size_t)n * ho * wo * c8;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int cc = (int)(t % c8);
+    const size_t pix = t / c8;
+    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), im = (int)(pix / ((size_t)wo * ho));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oy * stride - pad + ky;
+      if (iy < 0 || iy >= h) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ox * stride - pad + kx;
+        if (ix < 0 || ix >= w) continue;
+        const size_t idx = (((size_t)im * h + iy) * w + ix) * c8 + cc;
+        float v[8];
+        unpack8(__ldg(xh + idx), __ldg(xl + idx), v);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wgt + ((size_t)(ky * k + kx) * c8 + cc) * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wgt + ((size_t)(ky * k + kx) * c8 + cc) * 8) + 1);
+        acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]); acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+        acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]); acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+      }
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = act_apply(fmaf(acc[j], scale[cc * 8 + j], bias[cc * 8 + j]), act);
+    uint4 hh, ll;
+    pack8(o, hh, ll);
+    yh[t] = hh; yl[t] = ll;
+  }
+}
+
+// out[n, p, c] = x[n, p, c] * s[n, c]   (s: split planes [n, c_stride], first c used)
+__global__ void __launch_bounds__(kThreads) channel_scale_kernel(const uint4* __restrict__ xh, const uint4* __restrict__ xl,
+                                                                  const uint16_t* __restrict__ sh, const uint16_t* __restrict__ sl,
+                                                                  uint4* __restrict__ yh, uint4* __restrict__ yl, int n, int hw, int c8,
+                                                                  int s_stride) {
+  const size_t total = (size_t)n * hw * c8;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int cc = (int)(t % c8);
+    const int im = (int)(t / ((size_t)hw * c8));
+    float v[8], o[8];
+    unpack8(__ldg(xh + t), __ldg(xl + t), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const size_t si = (size_t)im * s_stride + cc * 8 + j;
+      o[j] = v[j] * (bf16_bits_to_f32(sh[si]) + bf16_bits_to_f32(sl[si]));
+    }
+    uint4 hh, ll;
+    pack8(o, hh, ll);
+    yh[t] = hh; yl[t] = ll;
+  }
+}
+
+// generic image im2col for tiny Cin=3 stems: planes [n*ho*wo, kpad], column = (ky*k + kx)*3 + c, zero padded
+struct Norm3 { float mean[3], std[3]; };
+template <bool U8>
+__global__ void __launch_bounds__(kThreads) image_im2col_kernel(const void* __restrict__ img, uint4* __restrict__ hi, uint4* __restrict__ lo,
+                                                                 int n, int h, int w, int k, int stride, int pad, int ho, int wo, int kpad,
+                                                                 Norm3 nm) {
+  const int k8 = kpad / 8;
+  const size_t total = (size_t)n * ho * wo * k8;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int chunk = (int)(t % k8);
+    const size_t pix = t / k8;
+    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), im = (int)(pix / ((size_t)wo * ho));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = chunk * 8 + j;
+      float val = 0.f;
+      if (col < k * k * 3) {
+        const int tap = col / 3, c = col - tap * 3, ky = tap / k, kx = tap - ky * k;
+        const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+          float x;
+          if (U8) x = __fdiv_rn((float)static_cast<const uint8_t*>(img)[(((size_t)im * h + iy) * w + ix) * 3 + c], 255.0f);
+          else x = static_cast<const float*>(img)[(((size_t)im * 3 + c) * h + iy) * w + ix];
+          val = (x - nm.mean[c]) / nm.std[c];
+        }
+      }
+      v[j] = val;
+    }
+    uint4 hh, ll;
+    pack8(v, hh, ll);
+    hi[t] = hh; lo[t] = ll;
+  }
+}
+
+inline unsigned grid_for(size_t items) {
+  size_t b = (items + kThreads - 1) / kThreads;
+  size_t cap = (size_t)b200r_num_sms() * 16;
+  return (unsigned)(b < cap ? (b ? b : 1) : cap);
+}
+}  // namespace
+
+extern "C" {
+
+int b200r_dwconv_nhwc(const uint16_t* x, const float* wgt, const float* scale, const float* bias, uint16_t* y, int n, int h, int w,
+                      int c, int k, int stride, int pad, int act, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && wgt && scale && bias && y, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c % 8 == 0 && k >= 1 && stride >= 1, "bad shape (c must be a multiple of 8)");
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  const size_t cin = (size_t)n * h * w * c, cout = (size_t)n * ho * wo * c;
+  dwconv_kernel<<<grid_for(cout / 8), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + cin), wgt, scale, bias, reinterpret_cast<uint4*>(y),
+      reinterpret_cast<uint4*>(y + cout), n, h, w, c / 8, k, stride, pad, ho, wo, act);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_channel_scale(const uint16_t* x, const uint16_t* s, uint16_t* y, int n, int hw, int c, int s_stride, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && s && y, "null pointer");
+  B200R_CHECK_ARG(n > 0 && hw > 0 && c % 8 == 0 && s_stride >= c, "bad shape");
+  const size_t cnt = (size_t)n * hw * c, scnt = (size_t)n * s_stride;
+  channel_scale_kernel<<<grid_for(cnt / 8), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + cnt), s, s + scnt, reinterpret_cast<uint4*>(y),
+      reinterpret_cast<uint4*>(y + cnt), n, hw, c / 8, s_stride);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+static int im2col_common(const void* img, uint16_t* planes, int n, int h, int w, int k, int stride, int pad, int kpad, const float* mean,
+                         const float* stdv, bool u8, cudaStream_t s) {
+  B200R_CHECK_ARG(img && planes && mean && stdv, "null pointer");
+  B200R_CHECK_ARG(n > 0 && k >= 1 && stride >= 1 && kpad % 8 == 0 && kpad >= k * k * 3, "bad im2col geometry");
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  const size_t rows = (size_t)n * ho * wo;
+  Norm3 nm;
+  for (int i = 0; i < 3; ++i) { nm.mean[i] = mean[i]; nm.std[i] = stdv[i]; }
+  uint4* hi = reinterpret_cast<uint4*>(planes);
+  uint4* lo = reinterpret_cast<uint4*>(planes + rows * kpad);
+  if (u8) image_im2col_kernel<true><<<grid_for(rows * (kpad / 8)), kThreads, 0, s>>>(img, hi, lo, n, h, w, k, stride, pad, ho, wo, kpad, nm);
+  else image_im2col_kernel<false><<<grid_for(rows * (kpad / 8)), kThreads, 0, s>>>(img, hi, lo, n, h, w, k, stride, pad, ho, wo, kpad, nm);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+int b200r_image_im2col_u8(const uint8_t* img, uint16_t* planes, int n, int h, int w, int k, int stride, int pad, int kpad,
+                          const float* mean_host, const float* std_host, b200r_stream_t stream) {
+  return im2col_common(img, planes, n, h, w, k, stride, pad, kpad, mean_host, std_host, true, as_stream(stream));
+}
+int b200r_image_im2col_f32(const float* img, uint16_t* planes, int n, int h, int w, int k, int stride, int pad, int kpad,
+                           const float* mean_host, const float* std_host, b200r_stream_t stream) {
+  return im2col_common(img, planes, n, h, w, k, stride, pad, kpad, mean_host, std_host, false, as_stream(stream));
+}
+
+}  // extern "C"

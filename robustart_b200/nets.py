@@ -433,3 +433,206 @@ def build_model(arch: str, state_dict=None, device="cuda", passes: int = 3, seed
             state_dict = random_token_state_dict(spec(), seed)
         return cls(state_dict, device, passes)
     return _build_resnet(arch, state_dict, device, passes, seed)
+
+
+# ================================================================================================
+# Mobile families: MobileNetV2 x1.0 (prototype/prototype/model/mobilenet_v2.py:80-202) and EfficientNet-B0
+# (prototype/prototype/model/efficientnet.py:91-125,289-369,372-495).  Pointwise convs run on the tcgen05
+# GEMM (K tails zero-filled by TMA), depthwise / SE / pooling on the CUDA-core kernels of mobile_layers.cu.
+# ================================================================================================
+_MBV2_SETTING = [[1, 16, 1, 1], [6, 24, 2, 2], [6, 32, 3, 2], [6, 64, 4, 2], [6, 96, 3, 1], [6, 160, 3, 2], [6, 320, 1, 1]]
+# (repeat, kernel, stride, expand, in, out) of efficientnet.py:101-109 at width/depth 1.0
+_EFFB0_BLOCKS = [(1, 3, 1, 1, 32, 16), (2, 3, 2, 6, 16, 24), (2, 5, 2, 6, 24, 40), (3, 3, 2, 6, 40, 80), (3, 5, 1, 6, 80, 112),
+                 (4, 5, 2, 6, 112, 192), (1, 3, 1, 6, 192, 320)]
+
+
+def mobilenet_v2_spec(classes=1000):
+    spec = [("features.0.0.weight", (32, 3, 3, 3))] + _bn_spec("features.0.1", 32)
+    cin, idx = 32, 1
+    for t, c, n, s in _MBV2_SETTING:
+        for i in range(n):
+            hid = cin * t
+            p, j = "features.%d.conv." % idx, 0
+            if t != 1:
+                spec += [(p + "0.0.weight", (hid, cin, 1, 1))] + _bn_spec(p + "0.1", hid)
+                j = 1
+            spec += [(p + "%d.0.weight" % j, (hid, 1, 3, 3))] + _bn_spec(p + "%d.1" % j, hid)
+            spec += [(p + "%d.weight" % (j + 1), (c, hid, 1, 1))] + _bn_spec(p + "%d" % (j + 2), c)
+            cin, idx = c, idx + 1
+    spec += [("features.%d.0.weight" % idx, (1280, cin, 1, 1))] + _bn_spec("features.%d.1" % idx, 1280)
+    spec += [("classifier.1.weight", (classes, 1280)), ("classifier.1.bias", (classes,))]
+    return spec
+
+
+def efficientnet_b0_spec(classes=1000):
+    spec, bi = [], 0
+    for rep, k, s, e, cin, cout in _EFFB0_BLOCKS:
+        for r in range(rep):
+            ci = cin if r == 0 else cout
+            hid, p, j = ci * e, "blocks.%d." % bi, 0
+            if e != 1:
+                spec += [(p + "in_conv.0.weight", (hid, ci, 1, 1))] + _bn_spec(p + "in_conv.1", hid)
+                j = 3
+            spec += [(p + "in_conv.%d.weight" % j, (hid, 1, k, k))] + _bn_spec(p + "in_conv.%d" % (j + 1), hid)
+            se = max(1, int(ci * 0.25))
+            spec += [(p + "se_block.conv1.weight", (se, hid, 1, 1)), (p + "se_block.conv1.bias", (se,)),
+                     (p + "se_block.conv2.weight", (hid, se, 1, 1)), (p + "se_block.conv2.bias", (hid,))]
+            spec += [(p + "out_conv.0.weight", (cout, hid, 1, 1))] + _bn_spec(p + "out_conv.1", cout)
+            bi += 1
+    spec += [("stem.0.weight", (32, 3, 3, 3))] + _bn_spec("stem.1", 32)
+    spec += [("head.0.weight", (1280, 320, 1, 1))] + _bn_spec("head.1", 1280)
+    spec += [("fc.weight", (classes, 1280)), ("fc.bias", (classes,))]
+    return spec
+
+
+def _fold_bn(sd, bn, device):
+    g, b = sd[bn + ".weight"].double(), sd[bn + ".bias"].double()
+    m, v = sd[bn + ".running_mean"].double(), sd[bn + ".running_var"].double()
+    s = g / torch.sqrt(v + BN_EPS)
+    return s.float().to(device).contiguous(), (b - m * s).float().to(device).contiguous()
+
+
+class _PW:
+    """1x1 conv + folded BN on the tensor-core GEMM."""
+
+    def __init__(self, sd, conv, bn, device):
+        w = sd[conv + ".weight"].float()
+        self.w = ops.split_f32(w.reshape(w.shape[0], 1, 1, w.shape[1]).contiguous().to(device))
+        self.scale, self.bias = _fold_bn(sd, bn, device)
+
+    def __call__(self, x, act=None, res=None, passes=3):
+        return ops.conv2d_nhwc(x, self.w, self.scale, self.bias, res, act=act, passes=passes)
+
+
+class _DW:
+    def __init__(self, sd, conv, bn, device, stride):
+        w = sd[conv + ".weight"].float()                     # [c, 1, k, k]
+        self.k, self.stride = w.shape[-1], stride
+        self.w = w.reshape(w.shape[0], -1).t().contiguous().to(device)   # [k*k, c]
+        self.scale, self.bias = _fold_bn(sd, bn, device)
+
+    def __call__(self, x, act):
+        return ops.dwconv_nhwc(x, self.w, self.scale, self.bias, k=self.k, stride=self.stride, pad=self.k // 2, act=act)
+
+
+class _ImageStem:
+    """3x3/s2 conv from the image: small im2col (K = 27 -> 32) + GEMM."""
+
+    def __init__(self, sd, conv, bn, device, act):
+        w = sd[conv + ".weight"].float()                     # [32, 3, 3, 3]
+        wp = torch.zeros(w.shape[0], 32)
+        wp[:, :27] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 27)
+        self.w = ops.split_f32(wp.to(device).contiguous())
+        self.scale, self.bias = _fold_bn(sd, bn, device)
+        self.act, self.cout = act, w.shape[0]
+
+    def __call__(self, images, passes):
+        n = images.shape[0]
+        cols, ho, wo = ops.image_im2col(images, 3, 2, 1, 32)
+        x = ops.linear(cols, self.w, self.scale, self.bias, act=self.act, passes=passes)
+        return x.view(2, n, ho, wo, self.cout)
+
+
+class MobileNetV2(_TokenModel):
+    def __init__(self, state_dict, device, passes=3):
+        super().__init__(device, passes)
+        sd, dev = _strip_prefix(state_dict), self.device
+        self.arch = "mobilenet_v2"
+        self.stem = _ImageStem(sd, "features.0.0", "features.0.1", dev, "relu6")
+        self.blocks, cin, idx = [], 32, 1
+        for t, c, n, s in _MBV2_SETTING:
+            for i in range(n):
+                stride, p, j = (s if i == 0 else 1), "features.%d.conv." % idx, 0
+                blk = {"res": stride == 1 and cin == c}
+                if t != 1:
+                    blk["pw"] = _PW(sd, p + "0.0", p + "0.1", dev)
+                    j = 1
+                blk["dw"] = _DW(sd, p + "%d.0" % j, p + "%d.1" % j, dev, stride)
+                blk["pl"] = _PW(sd, p + "%d" % (j + 1), p + "%d" % (j + 2), dev)
+                self.blocks.append(blk)
+                cin, idx = c, idx + 1
+        self.last = _PW(sd, "features.%d.0" % idx, "features.%d.1" % idx, dev)
+        self.fc = _Lin(sd, "classifier.1", dev)
+        self.num_classes = sd["classifier.1.weight"].shape[0]
+
+    def forward(self, images, logits=None):
+        n, P = images.shape[0], self.passes
+        x = self.stem(images, P)
+        for b in self.blocks:
+            y = b["pw"](x, act="relu6", passes=P) if "pw" in b else x
+            y = b["dw"](y, "relu6")
+            x = b["pl"](y, res=x if b["res"] else None, passes=P)      # linear bottleneck (+ skip)
+        x = self.last(x, act="relu6", passes=P)
+        pooled = ops.global_avgpool(x)
+        if logits is None:
+            logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
+        self.fc(pooled, passes=P, out_f32=logits)
+        return logits
+
+    def launches_per_forward(self):
+        return 2 + sum(2 + (1 if "pw" in b else 0) for b in self.blocks) + 3
+
+
+class EfficientNetB0(_TokenModel):
+    def __init__(self, state_dict, device, passes=3):
+        super().__init__(device, passes)
+        sd, dev = _strip_prefix(state_dict), self.device
+        self.arch = "efficientnet_b0"
+        self.stem = _ImageStem(sd, "stem.0", "stem.1", dev, "swish")
+        self.blocks, bi = [], 0
+        for rep, k, s, e, cin, cout in _EFFB0_BLOCKS:
+            for r in range(rep):
+                ci, stride = (cin if r == 0 else cout), (s if r == 0 else 1)
+                p, j = "blocks.%d." % bi, 0
+                blk = {"res": stride == 1 and ci == cout}
+                if e != 1:
+                    blk["pw"] = _PW(sd, p + "in_conv.0", p + "in_conv.1", dev)
+                    j = 3
+                blk["dw"] = _DW(sd, p + "in_conv.%d" % j, p + "in_conv.%d" % (j + 1), dev, stride)
+                hid = ci * e
+                se = sd[p + "se_block.conv1.weight"].shape[0]
+                sep = (se + 7) // 8 * 8                              # pad the squeeze width to a 16-byte row
+                blk["se1"] = _Lin({"a.weight": sd[p + "se_block.conv1.weight"].reshape(se, hid), "a.bias": sd[p + "se_block.conv1.bias"]},
+                                  "a", dev, n_pad=sep)
+                blk["se2"] = _Lin({"a.weight": sd[p + "se_block.conv2.weight"].reshape(hid, se), "a.bias": sd[p + "se_block.conv2.bias"]},
+                                  "a", dev, k_pad=sep)
+                blk["pl"] = _PW(sd, p + "out_conv.0", p + "out_conv.1", dev)
+                self.blocks.append(blk)
+                bi += 1
+        self.head = _PW(sd, "head.0", "head.1", dev)
+        self.fc = _Lin(sd, "fc", dev)
+        self.num_classes = sd["fc.weight"].shape[0]
+
+    def forward(self, images, logits=None):
+        n, P = images.shape[0], self.passes
+        x = self.stem(images, P)
+        for b in self.blocks:
+            y = b["pw"](x, act="swish", passes=P) if "pw" in b else x
+            y = b["dw"](y, "swish")
+            w = ops.global_avgpool(y)                                 # squeeze
+            w = b["se2"](b["se1"](w, act="swish", passes=P), act="sigmoid", passes=P)
+            y = ops.channel_scale(y, w)                               # excite
+            x = b["pl"](y, res=x if b["res"] else None, passes=P)
+        x = self.head(x, act="swish", passes=P)
+        pooled = ops.global_avgpool(x)
+        if logits is None:
+            logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
+        self.fc(pooled, passes=P, out_f32=logits)
+        return logits
+
+    def launches_per_forward(self):
+        return 2 + sum(6 + (1 if "pw" in b else 0) for b in self.blocks) + 3
+
+
+_MOBILE_ARCHS = {"mobilenet_v2": (MobileNetV2, mobilenet_v2_spec), "mobilenet_v2_x1_0": (MobileNetV2, mobilenet_v2_spec),
+                 "efficientnet_b0": (EfficientNetB0, efficientnet_b0_spec)}
+_build_prev = build_model
+
+
+def build_model(arch: str, state_dict=None, device="cuda", passes: int = 3, seed: int = 0):  # noqa: F811
+    if arch in _MOBILE_ARCHS:
+        cls, spec = _MOBILE_ARCHS[arch]
+        if state_dict is None:
+            state_dict = random_state_dict(spec(), seed)
+        return cls(state_dict, device, passes)
+    return _build_prev(arch, state_dict, device, passes, seed)

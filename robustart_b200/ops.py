@@ -382,3 +382,44 @@ def channels_to_tokens_add(y, res, b, t, c, t_pad):
     with torch.cuda.device(y.device):
         _lib.check(_lib.load().b200r_channels_to_tokens_add(y.data_ptr(), res.data_ptr(), out.data_ptr(), b, t, c, t_pad, _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# mobile-family layers
+# ------------------------------------------------------------------------------------------------
+ACT["sigmoid"] = 7
+
+
+def dwconv_nhwc(x, wgt, scale, bias, *, k, stride, pad, act=None):
+    """x: planes [2,n,h,w,c]; wgt float32 [k*k, c]."""
+    _, n, h, w, c = x.shape
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    out = torch.empty((2, n, ho, wo, c), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_dwconv_nhwc(x.data_ptr(), wgt.data_ptr(), scale.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                                 n, h, w, c, k, stride, pad, ACT[act], _stream()))
+    return out
+
+
+def channel_scale(x, s):
+    """x: planes [2,n,h,w,c]; s: planes [2,n,c_stride] -> x * s[n, :c]."""
+    _, n, h, w, c = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_channel_scale(x.data_ptr(), s.data_ptr(), out.data_ptr(), n, h * w, c, s.shape[-1], _stream()))
+    return out
+
+
+def image_im2col(img, k, stride, pad, kpad, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    if img.dtype == torch.uint8:
+        n, h, w, _ = img.shape
+        fn = _lib.load().b200r_image_im2col_u8
+    else:
+        _need_cuda(img, torch.float32, "img")
+        n, _, h, w = img.shape
+        fn = _lib.load().b200r_image_im2col_f32
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    out = torch.empty((2, n * ho * wo, kpad), dtype=torch.int16, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(fn(img.data_ptr(), out.data_ptr(), n, h, w, k, stride, pad, kpad, _lib.f3(mean), _lib.f3(std), _stream()))
+    return out, ho, wo

@@ -126,3 +126,40 @@ def token_models():
 
 if __name__ == "__main__" and "--tokens" in sys.argv:
     token_models()
+
+
+def mobile_models():
+    """MobileNetV2 x1.0 and EfficientNet-B0 golden logits from the reference classes."""
+    from util import synth_images
+    from robustart_b200 import nets
+    shim()
+    sys.path.insert(0, REF)
+    for k in [k for k in sys.modules if k == "prototype" or k.startswith("prototype.")]:
+        del sys.modules[k]
+    import importlib
+    importlib.import_module("prototype.prototype.model.mobilenet_v2")
+    importlib.import_module("prototype.prototype.model.efficientnet")
+    MB = sys.modules["prototype.prototype.model.mobilenet_v2"]
+    EF = sys.modules["prototype.prototype.model.efficientnet"]
+    assert MB.__file__.startswith(REF) and EF.__file__.startswith(REF)
+    images = synth_images(2, seed=11)
+    x = torch.from_numpy(images).permute(0, 3, 1, 2).float().div(255)
+    xn = (x - torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)) / torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    out = {}
+    for name, model, spec in (("mobilenet_v2", MB.mobilenet_v2(), nets.mobilenet_v2_spec()),
+                              ("efficientnet_b0", EF.efficientnet_b0(), nets.efficientnet_b0_spec())):
+        ref_sd = model.state_dict()
+        a = [(k, tuple(v.shape)) for k, v in ref_sd.items()]
+        b = [(k, tuple(s)) for k, s in spec]
+        assert a == b, (name, [x for x in zip(a, b) if x[0] != x[1]][:5], len(a), len(b))
+        model.load_state_dict(nets.random_state_dict(spec, 0), strict=True)
+        model.eval()
+        with torch.no_grad():
+            lg = model(xn)
+        out[name] = lg.numpy()
+        print(name, "logits abs max %.3f std %.3f" % (lg.abs().max(), lg.std()), lg.argmax(1).tolist())
+    np.savez(os.path.join(HERE, "mobile_logits.npz"), **out)
+
+
+if __name__ == "__main__" and "--mobile" in sys.argv:
+    mobile_models()

@@ -141,6 +141,28 @@ int b200r_topk_count(const float* logits, const int64_t* labels, int n, int clas
                      int64_t* counters, int64_t* pred, b200r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * AutoAttack device pieces (vendored fra31/auto-attack: .../Attacks/autoattack/autopgd_base.py,
+ * square.py).
+ * ------------------------------------------------------------------------------------------ */
+/* APGD-Linf update with momentum (autopgd_base.py:332-338); x_adv_old <- x_adv, x_adv <- update;
+ * step: device float[n] per-sample step sizes; a = 0.75 (1.0 on the first iteration) */
+int b200r_apgd_step_linf(float* x_adv, float* x_adv_old, const float* g, const float* x0,
+                         const float* step, size_t n, size_t chw, float eps, float a,
+                         b200r_stream_t stream);
+/* DLR loss (+ gradient w.r.t. logits): targets == NULL -> untargeted (autopgd_base.py:198-204),
+ * else targeted (:599-604).  loss, dlogits nullable. */
+int b200r_dlr_loss_grad(const float* logits, const int64_t* labels, const int64_t* targets, float* loss,
+                        float* dlogits, int n, int classes, b200r_stream_t stream);
+/* Square-attack proposal (square.py:246-254): paste 2*eps*sign[c] on the s x s window at (vh, vw) of
+ * x_best, project onto the eps-ball around x0, clip to [0,1] */
+int b200r_square_propose_linf(const float* x_best, const float* x0, float* out, int n, int c, int h,
+                              int w, int vh, int vw, int s, const float* signs_host, float eps,
+                              b200r_stream_t stream);
+/* dst[i, :] = src[i, :] where mask[i] != 0 (masked accept of Square / best-point bookkeeping) */
+int b200r_masked_rows_copy(float* dst, const float* src, const uint8_t* mask, size_t n, size_t chw,
+                           b200r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Dense contractions on the tcgen05 tensor cores ("split-bf16" activations: every fp32 tensor
  * is stored as two bf16 planes hi = bf16(v), lo = bf16(v - hi); a product uses hi*hi + hi*lo +
  * lo*hi with fp32 accumulation in TMEM).

@@ -120,3 +120,11 @@ SIGNATURES.update({
     "b200r_image_im2col_f32": (C.c_int, [c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_host_f3,
                                          c_host_f3, c_stream]),
 })
+
+SIGNATURES.update({
+    "b200r_apgd_step_linf": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_size_t, C.c_size_t, C.c_float, C.c_float, c_stream]),
+    "b200r_dlr_loss_grad": (C.c_int, [c_f32p, c_i64p, c_i64p, c_f32p, c_f32p, C.c_int, C.c_int, c_stream]),
+    "b200r_square_propose_linf": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            c_host_f3, C.c_float, c_stream]),
+    "b200r_masked_rows_copy": (C.c_int, [c_f32p, c_f32p, c_u8p, C.c_size_t, C.c_size_t, c_stream]),
+})

@@ -319,3 +319,97 @@ int b200r_mim_step_linf(float* x, float* momentum, const float* g, const float* 
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// AutoAttack device pieces (vendored fra31/auto-attack in the reference:
+// RobustART/noise/utils/adv/Attacks/autoattack/autopgd_base.py:332-338, square.py:246-262)
+// =============================================================================================
+namespace {
+__device__ __forceinline__ float apgd_one(float xa, float xo, float g, float x0, float step, float eps, float a) {
+  // x_adv_1 = clamp(min(max(x_adv + step*sign(g), x-eps), x+eps), 0, 1)
+  float x1 = __fadd_rn(xa, __fmul_rn(step, sgn(g)));
+  x1 = clampf(fminf(fmaxf(x1, __fsub_rn(x0, eps)), __fadd_rn(x0, eps)), 0.f, 1.f);
+  // x_adv_1 = clamp(min(max(x_adv + (x_adv_1 - x_adv)*a + grad2*(1-a), x-eps), x+eps), 0, 1), grad2 = x_adv - x_adv_old
+  float m = __fadd_rn(__fadd_rn(xa, __fmul_rn(__fsub_rn(x1, xa), a)), __fmul_rn(__fsub_rn(xa, xo), __fsub_rn(1.f, a)));
+  return clampf(fminf(fmaxf(m, __fsub_rn(x0, eps)), __fadd_rn(x0, eps)), 0.f, 1.f);
+}
+
+// x_adv <- APGD update ; x_old <- previous x_adv.  step: per-sample step size [n]
+__global__ void __launch_bounds__(kThreads) apgd_step_linf_kernel(float4* __restrict__ xadv, float4* __restrict__ xold,
+                                                                   const float4* __restrict__ g, const float4* __restrict__ x0,
+                                                                   const float* __restrict__ step, size_t chw4, float eps, float a) {
+  const size_t img = blockIdx.y;
+  const float st = step[img];
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < chw4; i += (size_t)gridDim.x * kThreads) {
+    const size_t k = img * chw4 + i;
+    float4 xa = xadv[k], xo = xold[k], gv = ld_stream_f4(g + k), ov = ld_stream_f4(x0 + k), r;
+    r.x = apgd_one(xa.x, xo.x, gv.x, ov.x, st, eps, a); r.y = apgd_one(xa.y, xo.y, gv.y, ov.y, st, eps, a);
+    r.z = apgd_one(xa.z, xo.z, gv.z, ov.z, st, eps, a); r.w = apgd_one(xa.w, xo.w, gv.w, ov.w, st, eps, a);
+    xold[k] = xa;
+    xadv[k] = r;
+  }
+}
+
+// Square attack proposal: out = clamp(min(max(x_best + 2*eps*sign_c on the window, x0-eps), x0+eps), 0, 1)
+__global__ void __launch_bounds__(kThreads) square_propose_kernel(const float* __restrict__ xbest, const float* __restrict__ x0,
+                                                                   float* __restrict__ out, int c, int h, int w, int vh, int vw, int s,
+                                                                   float s0, float s1, float s2, float eps) {
+  const size_t img = blockIdx.y;
+  const int chw = c * h * w;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < chw; i += gridDim.x * kThreads) {
+    const int ch = i / (h * w), rem = i - ch * h * w, y = rem / w, x = rem - y * w;
+    const size_t k = img * chw + i;
+    float v = xbest[k];
+    if (y >= vh && y < vh + s && x >= vw && x < vw + s) v = __fadd_rn(v, __fmul_rn(2.f * eps, ch == 0 ? s0 : (ch == 1 ? s1 : s2)));
+    const float o = x0[k];
+    out[k] = clampf(fminf(fmaxf(v, __fsub_rn(o, eps)), __fadd_rn(o, eps)), 0.f, 1.f);
+  }
+}
+
+// dst[i] = mask[i] ? src[i] : dst[i]  (row = sample)
+__global__ void __launch_bounds__(kThreads) masked_rows_kernel(float4* __restrict__ dst, const float4* __restrict__ src,
+                                                                const uint8_t* __restrict__ mask, size_t chw4) {
+  const size_t img = blockIdx.y;
+  if (!mask[img]) return;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < chw4; i += (size_t)gridDim.x * kThreads) dst[img * chw4 + i] = src[img * chw4 + i];
+}
+}  // namespace
+
+extern "C" {
+
+int b200r_apgd_step_linf(float* x_adv, float* x_adv_old, const float* g, const float* x0, const float* step, size_t n, size_t chw,
+                         float eps, float a, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x_adv && x_adv_old && g && x0 && step, "null pointer");
+  B200R_CHECK_ARG(chw % 4 == 0 && n < 65536, "chw must be a multiple of 4 and n < 65536");
+  if (n == 0) return B200R_OK;
+  dim3 grid(slices_for(chw / 4, n), (unsigned)n);
+  apgd_step_linf_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(x_adv), reinterpret_cast<float4*>(x_adv_old),
+                                                                  reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(x0),
+                                                                  step, chw / 4, eps, a);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_square_propose_linf(const float* x_best, const float* x0, float* out, int n, int c, int h, int w, int vh, int vw, int s,
+                              const float* signs_host, float eps, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x_best && x0 && out && signs_host, "null pointer");
+  B200R_CHECK_ARG(c == 3 && n >= 0 && n < 65536 && s >= 1 && vh >= 0 && vw >= 0 && vh + s <= h && vw + s <= w, "bad square window");
+  if (n == 0) return B200R_OK;
+  dim3 grid((c * h * w + kThreads * 4 - 1) / (kThreads * 4), n);
+  square_propose_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(x_best, x0, out, c, h, w, vh, vw, s, signs_host[0], signs_host[1],
+                                                                  signs_host[2], eps);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_masked_rows_copy(float* dst, const float* src, const uint8_t* mask, size_t n, size_t chw, b200r_stream_t stream) {
+  B200R_CHECK_ARG(dst && src && mask, "null pointer");
+  B200R_CHECK_ARG(chw % 4 == 0 && n < 65536, "chw must be a multiple of 4 and n < 65536");
+  if (n == 0) return B200R_OK;
+  dim3 grid(slices_for(chw / 4, n), (unsigned)n);
+  masked_rows_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), mask, chw / 4);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+}  // extern "C"

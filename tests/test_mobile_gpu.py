@@ -35,7 +35,7 @@ def test_se_scale_and_small_channel_gemm(cuda):
     s = torch.rand(4, 96, device=cuda)
     y = ops.merge_f32(ops.channel_scale(ops.split_f32(x), ops.split_f32(s)))
     ref = ops.merge_f32(ops.split_f32(x)) * ops.merge_f32(ops.split_f32(s)).view(4, 1, 1, 96)
-    assert (y - ref).abs().max().item() < 1e-5
+    assert (y - ref).abs().max().item() < 1e-4     # the product is re-split to 16 significant bits
     # pointwise conv with K tail (cin = 24 -> zero filled to 64) and narrow / ragged outputs
     for cin, cout in [(24, 144), (16, 96), (96, 24), (32, 16), (144, 40), (8, 8)]:
         xx = torch.randn(2, 28, 28, cin, device=cuda)

@@ -16,7 +16,7 @@
 //   warp 1      TMEM allocation + single-thread tcgen05.mma issue (UMMA 128 x BN x 16, kind::f16,
 //               bf16 inputs, fp32 accumulate), tcgen05.commit onto the ring's "empty" barriers and the
 //               accumulator's "full" barrier.
-//   warps 2-9   epilogue: tcgen05.ld the 128 x BN fp32 accumulator (double-buffered in TMEM so the next
+//   warps 2-9   epilogue (STEM variant: warps 2-5 epilogue, warps 6-13 operand producers): tcgen05.ld the 128 x BN fp32 accumulator (double-buffered in TMEM so the next
 //               tile's MMAs overlap), folded-BN scale/bias, residual, activation, re-split to bf16
 //               planes (and/or fp32), masked stores.
 #include "common.cuh"
@@ -176,7 +176,8 @@ struct GemmParams {
   long long M_total;        // N * Ho * Wo
 };
 
-constexpr int kStemProducerWarps = 4;   // one thread per A-tile row
+constexpr int kStemProducerWarps = 8;   // two threads per A-tile row
+constexpr int kStemEpiWarps = 4;        // the stem's 64-column epilogue needs only one warp per TMEM lane quarter
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -249,7 +250,7 @@ __device__ __forceinline__ void epi_vec(const GemmParams& p, const uint32_t* v, 
 }
 
 template <int BN, bool STEM>
-__global__ void __launch_bounds__(kThreads + (STEM ? kStemProducerWarps * 32 : 0), 1)
+__global__ void __launch_bounds__(STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
@@ -276,7 +277,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // STEM: the A tile is written by 128 producer threads (one arrival each) next to the TMA thread's
     // arrive.expect_tx for the weight tile
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), STEM ? 1 + kStemProducerWarps * 32 : 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), STEM ? kStemEpiWarps : 8); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -356,8 +357,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
       }
     }
-  } else if (warp < 10) {
-    // ===================== epilogue (8 warps) =====================
+  } else if (warp < 2 + (STEM ? kStemEpiWarps : 8)) {
+    // ===================== epilogue (8 warps; 4 in the STEM variant) =====================
     // TMEM lane quarter = warp % 4 (hardware restriction); the two warps of a quarter split the columns.
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -376,7 +377,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+      constexpr int kColsPerWarp = STEM ? BN : BN / 2;
+      for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), v);
         tmem_ld_wait();
@@ -413,15 +415,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // columns/rows, so the per-pixel gather needs no bounds checks: K is ordered (ky, kx, c), i.e. 7 runs of
     // 21 consecutive staged words starting at word 6*ox.  The 64-element k-block row goes out as 8 16-byte
     // chunks at the 128B-swizzled position (chunk ^ (row & 7)).
-    const int ptid = threadIdx.x - 10 * 32;                    // 0..127
-    const int r = ptid;                                         // tile row = output column ox
+    constexpr int kProd = kStemProducerWarps * 32;               // 256 producer threads
+    const int ptid = threadIdx.x - (2 + kStemEpiWarps) * 32;
+    const int r = ptid >> 1, sub = ptid & 1;                     // tile row = output column ox; each thread builds 4 of the 8 chunks
     const int row_bytes = p.W_in * 3;
     const int pitch = 9 + row_bytes + 15;                       // staged words per input row (zero padded)
     uint32_t* s_conv = reinterpret_cast<uint32_t*>(smem + kStages * STAGE_BYTES + 512);
     uint32_t* s_lut = s_conv + 7 * pitch;
-    for (int i = ptid; i < 768; i += kStemProducerWarps * 32) s_lut[i] = __ldg(p.lut + i);
-    for (int i = ptid; i < 7 * pitch; i += kStemProducerWarps * 32) s_conv[i] = 0u;   // pads stay zero for the whole kernel
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int i = ptid; i < 768; i += kProd) s_lut[i] = __ldg(p.lut + i);
+    for (int i = ptid; i < 7 * pitch; i += kProd) s_conv[i] = 0u;   // pads stay zero for the whole kernel
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -431,12 +434,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       // stage the 7 input rows: 16-byte loads (all issued before first use), bytes -> LUT words
       {
         const int q_per_row = row_bytes / 16;                   // 42 for W = 224
-        constexpr int kMaxIt = 4;                               // ceil(7*q_per_row / 128) for W <= 256 (requires row_bytes % 16 == 0)
+        constexpr int kMaxIt = 2;                               // ceil(7*q_per_row / 256) for W <= 256 (requires row_bytes % 16 == 0)
         uint4 v[kMaxIt];
         int dstw[kMaxIt];
 #pragma unroll
         for (int it = 0; it < kMaxIt; ++it) {
-          const int idx = ptid + it * (kStemProducerWarps * 32);
+          const int idx = ptid + it * kProd;
           dstw[it] = -1;
           v[it] = make_uint4(0, 0, 0, 0);
           if (idx < 7 * q_per_row) {
@@ -461,7 +464,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const uint32_t* my = s_conv + 6 * r;                      // (2*ox - 3)*3 + 9 = 6*ox
 #pragma unroll
       for (int kb = 0; kb < 3; ++kb) {
@@ -470,11 +473,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         uint8_t* a_lo = a_hi + A_TILE_BYTES;
         if (r < p.rows_box) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q8 = 0; q8 < 8; ++q8) {
+            if ((q8 >> 2) != sub) continue;                     // compile-time q (constant K indices), runtime predicate
+            const int q = q8;
             uint32_t e[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int col = kb * 64 + q * 8 + j;               // compile-time after unrolling
+              const int col = kb * 64 + q * 8 + j;
               e[j] = (col < 147) ? my[(col / 21) * pitch + (col % 21)] : 0u;
             }
             uint4 h, l;
@@ -491,7 +496,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         mbar_arrive(full_bar(stage));
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");            // everyone done reading s_conv before restaging
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // everyone done reading s_conv before restaging
     }
   }
 
@@ -535,7 +540,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cu
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_img * p.tiles_n;
   const int grid = total < b200r_num_sms() ? total : b200r_num_sms();
-  gemm_kernel<BN, STEM><<<grid, kThreads + (STEM ? kStemProducerWarps * 32 : 0), smem, s>>>(ma, mb, p);
+  gemm_kernel<BN, STEM><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(ma, mb, p);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }

@@ -58,6 +58,11 @@ model_name_dict = {
     "resnet34": {"type": "resnet34_official", "kwargs": {"bn": {"use_sync_bn": False, "kwargs": {}}}},
     "resnet50": {"type": "resnet50_official", "kwargs": {"bn": {"use_sync_bn": False, "kwargs": {}}}},
     "resnet101": {"type": "resnet101_official", "kwargs": {"bn": {"use_sync_bn": False, "kwargs": {}}}},
+    "mobilenet_v2_x1_0": {"type": "mobilenet_v2", "kwargs": {"scale": 1.0, "bn": {"use_sync_bn": False, "kwargs": {}}}},
+    "efficientnet_b0": {"type": "efficientnet_b0", "kwargs": {"bn": {"use_sync_bn": False, "kwargs": {}}}},
+    "vit_base_patch16_224": {"type": "vit_b16_224", "kwargs": {"drop_path": 0.0, "dropout": 0.0, "attention_dropout": 0.0,
+                                                               "qkv_bias": True, "representation_size": 768}},
+    "mixer_b16_224": {"type": "mixer_b16_224", "kwargs": {"drop_path": 0.0, "drop_path_rate": 0.0}},
 }
 
 
@@ -151,6 +156,9 @@ def build_torch_model(model_cfg, ckpt_path, device):
     arbitrary source models stays on PyTorch until the dgrad kernels land."""
     from . import torch_models
     arch = nets.ARCH_ALIASES.get(model_cfg["type"], model_cfg["type"])
+    if arch not in torch_models._CFG:
+        raise NotImplementedError("source model %r: only the ResNet family has an autograd twin so far; use it as the "
+                                  "target (forward-only) model or pass your own nn.Module to AddNoise" % arch)
     sd = load_checkpoint(ckpt_path)
     if sd is None:
         sd = nets.random_state_dict(nets.resnet_spec(arch), 0)

@@ -1,7 +1,7 @@
 // Stencil / resampling ImageNet-C corruptions: shared-memory staged, ALU/smem-bound.
 //   gaussian_blur (corruptions.py:162-166)  glass_blur (:169-184)  defocus_blur (:187-198, disk :26-38)
 //   zoom_blur (:219-232, clipped_zoom :104-114)  motion_blur (:201-216)  snow (:265-290)
-//   elastic_transform (:395-424).  spatter (:293-342) is not implemented yet (B200R_ENOTSUP).
+//   elastic_transform (:395-424)  spatter (:293-342; mud branch of severity 4-5, the water branch is B200R_ENOTSUP)
 //
 // Third-party arithmetic restated here (same restatement as oracle/imagenet_c.py):
 //   skimage.filters.gaussian -> scipy.ndimage.gaussian_filter(sigma=[s,s,0], mode='nearest', truncate=4)
@@ -657,6 +657,64 @@ __global__ void __launch_bounds__(kElThreads) elastic_gather_kernel(const float*
   }
 }
 
+// =============================================================================================
+// spatter, "mud" branch (severity 4-5; corruptions.py:329-342): normal layer -> gaussian(sigma c2) -> threshold c3 ->
+// binary mask -> gaussian(sigma c4) -> m[m < 0.8] = 0 -> x*(1-m) + mud*m.  The "water" branch of severity 1-3
+// (cv2.Canny + distanceTransform + equalizeHist chain, :305-328) is not restated yet -> B200R_ENOTSUP.
+// ext layout: [n][H*W] standard normals.
+// =============================================================================================
+__global__ void __launch_bounds__(kElThreads) spatter_layer_kernel(float* __restrict__ layer, int hw, float loc, float scale,
+                                                                    const float* __restrict__ ext, uint32_t k0, uint32_t k1,
+                                                                    uint64_t image_offset) {
+  const int img = blockIdx.y;
+  for (int i = blockIdx.x * kElThreads + threadIdx.x; i < hw; i += gridDim.x * kElThreads) {
+    float z;
+    if (ext) z = ext[(size_t)img * hw + i];
+    else {
+      uint4 r = philox4x32_10(rng_counter((uint32_t)(i >> 3), RNG_SPATTER, 0, image_offset + img), k0, k1);
+      const uint32_t word = (i & 6) == 0 ? r.x : (i & 6) == 2 ? r.y : (i & 6) == 4 ? r.z : r.w;
+      float z0, z1;
+      box_muller16(word, z0, z1);
+      z = (i & 1) ? z1 : z0;
+    }
+    layer[(size_t)img * hw + i] = loc + scale * z;
+  }
+}
+
+// 1-D Gaussian along x (horiz = 1) or y, mode 'nearest'; optional post-op: 0 none, 1 (v < thr ? 0 : v) then (v > thr ? 1 : 0)
+// i.e. the binary mask of :330, 2 (v < thr ? 0 : v)
+__global__ void __launch_bounds__(kElThreads) plane_blur_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
+                                                                 GaussW gw, int horiz, int post, float thr) {
+  const int img = blockIdx.y, hw = h * w;
+  const float* src = in + (size_t)img * hw;
+  for (int i = blockIdx.x * kElThreads + threadIdx.x; i < hw; i += gridDim.x * kElThreads) {
+    const int y = i / w, x = i - y * w;
+    float a = 0.f;
+    for (int k = -gw.radius; k <= gw.radius; ++k) {
+      const int yy = horiz ? y : clampi(y + k, 0, h - 1), xx = horiz ? clampi(x + k, 0, w - 1) : x;
+      a = fmaf(gw.w[k + gw.radius], src[yy * w + xx], a);
+    }
+    if (post == 1) a = ((a < thr ? 0.f : a) > thr) ? 1.f : 0.f;
+    else if (post == 2) a = (a < thr) ? 0.f : a;
+    out[(size_t)img * hw + i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(kElThreads) spatter_mud_blend_kernel(const uint8_t* __restrict__ in, const float* __restrict__ m,
+                                                                        uint8_t* __restrict__ out, int hw) {
+  const int img = blockIdx.y;
+  const float mud[3] = {63.f / 255.f, 42.f / 255.f, 20.f / 255.f};
+  for (int i = blockIdx.x * kElThreads + threadIdx.x; i < hw; i += gridDim.x * kElThreads) {
+    const float mm = m[(size_t)img * hw + i];
+    const size_t p = ((size_t)img * hw + i) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = __fdiv_rn((float)in[p + c], 255.f);
+      out[p + c] = (uint8_t)f01_to_u8(__saturatef(x * (1.f - mm) + mud[c] * mm));
+    }
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -669,7 +727,7 @@ size_t corrupt_stencil_ws(int id, int sev, int n, int h, int w) {
   (void)sev;
   // a scratch image: glass_blur's intermediate, and the detour for in-place calls (none of these
   // kernels can overwrite its own input)
-  if (id == B200R_SPATTER) return 0;
+  if (id == B200R_SPATTER) return (size_t)n * h * w * 2 * sizeof(float);   // two ping-pong float planes
   // elastic: warped fp32 image + two ping-pong buffers of the (dx, dy) fields
   if (id == B200R_ELASTIC_TRANSFORM) return (size_t)n * h * w * (3 + 2 + 2) * sizeof(float);
   return (size_t)n * h * w * 3;
@@ -689,6 +747,7 @@ size_t corrupt_ext_count(int id, int sev, int n, int h, int w) {
     case B200R_MOTION_BLUR: return (size_t)n;
     case B200R_SNOW: return (size_t)n * ((size_t)h * w + 1);
     case B200R_ELASTIC_TRANSFORM: return (size_t)n * (6 + 2 * (size_t)h * w);
+    case B200R_SPATTER: return (size_t)n * h * w;
     default: return 0;
   }
 }
@@ -698,7 +757,7 @@ static int stencil_dispatch(const CorruptArgs& a);
 int corrupt_stencil_family(const CorruptArgs& a0) {
   CorruptArgs a = a0;
   const size_t bytes = (size_t)a.n * a.h * a.w * 3;
-  if (a.id == B200R_ELASTIC_TRANSFORM) return stencil_dispatch(a);   // reads `in` fully before writing `out`
+  if (a.id == B200R_ELASTIC_TRANSFORM || a.id == B200R_SPATTER) return stencil_dispatch(a);   // reads `in` fully before writing `out`
   const bool inplace = (a.in == a.out) && a.id != B200R_SNOW;
   if (inplace || a.id == B200R_GLASS_BLUR) {
     B200R_CHECK_ARG(a.ws && a.ws_bytes >= bytes, "this corruption needs %zu workspace bytes", bytes);
@@ -830,8 +889,31 @@ static int stencil_dispatch(const CorruptArgs& a) {
       B200R_LAUNCH_CHECK();
       return B200R_OK;
     }
+    case B200R_SPATTER: {
+      static const double c[5][6] = {{0.65, 0.3, 4, 0.69, 0.6, 0}, {0.65, 0.3, 3, 0.68, 0.6, 0}, {0.65, 0.3, 2, 0.68, 0.5, 0},
+                                     {0.65, 0.3, 1, 0.65, 1.5, 1}, {0.67, 0.4, 1, 0.65, 1.5, 1}};
+      if (c[s][5] == 0) {
+        b200r_set_error("spatter severity 1-3 (water: cv2.Canny / distanceTransform / equalizeHist chain) is not implemented on the GPU yet");
+        return B200R_ENOTSUP;
+      }
+      const int hw = a.h * a.w;
+      const size_t need = corrupt_stencil_ws(a.id, a.severity, a.n, a.h, a.w);
+      B200R_CHECK_ARG(a.ws && a.ws_bytes >= need, "spatter needs %zu workspace bytes", need);
+      float* p0 = static_cast<float*>(a.ws);
+      float* p1 = p0 + (size_t)a.n * hw;
+      dim3 g(32, a.n);
+      spatter_layer_kernel<<<g, kElThreads, 0, a.stream>>>(p0, hw, (float)c[s][0], (float)c[s][1], a.ext, k0, k1, a.image_offset);
+      GaussW g1 = make_gauss(c[s][2], 4.0), g2 = make_gauss(c[s][4], 4.0);
+      plane_blur_kernel<<<g, kElThreads, 0, a.stream>>>(p0, p1, a.h, a.w, g1, 0, 0, 0.f);                 // axis 0 first (scipy order)
+      plane_blur_kernel<<<g, kElThreads, 0, a.stream>>>(p1, p0, a.h, a.w, g1, 1, 1, (float)c[s][3]);      // threshold -> binary mask
+      plane_blur_kernel<<<g, kElThreads, 0, a.stream>>>(p0, p1, a.h, a.w, g2, 0, 0, 0.f);
+      plane_blur_kernel<<<g, kElThreads, 0, a.stream>>>(p1, p0, a.h, a.w, g2, 1, 2, 0.8f);                // m[m < 0.8] = 0
+      spatter_mud_blend_kernel<<<g, kElThreads, 0, a.stream>>>(a.in, p0, a.out, hw);
+      B200R_LAUNCH_CHECK();
+      return B200R_OK;
+    }
     default:
-      b200r_set_error("spatter is not implemented on the GPU yet");
-      return B200R_ENOTSUP;
+      b200r_set_error("corruption id %d is not in the stencil family", a.id);
+      return B200R_EINVAL;
   }
 }

@@ -29,7 +29,7 @@ namespace {
 constexpr int BM = 128;       // UMMA_M (cta_group::1)
 constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 3;
+constexpr int kStagesDefault = 3;   // BN <= 128: 3 x 64 KB; BN = 256: 2 x 96 KB
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
 
@@ -252,6 +252,7 @@ __device__ __forceinline__ void epi_vec(const GemmParams& p, const uint32_t* v, 
 template <int BN, bool STEM>
 __global__ void __launch_bounds__(STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+  constexpr int kStages = (BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault);
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers (power of two: 128 or 256)
@@ -530,6 +531,7 @@ EncodeTiledFn get_encode() {
 
 template <int BN, bool STEM>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
+  constexpr int kStages = (BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault);
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * BN * BK * 2;
   // STEM adds the staged input rows (7 x (W_in*3 + 24) words) and the 3 KB LUT behind the barriers
   const int smem = kStages * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + (STEM ? 7 * (p.W_in * 3 + 24) * 4 + 768 * 4 : 0);
@@ -585,7 +587,13 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
   else choose_box(N, Ho, Wo, stride, p.bn, p.bh, p.bw);
   p.rows_box = p.bn * p.bh * p.bw;
   p.tiles_w = (Wo + p.bw - 1) / p.bw; p.tiles_h = (Ho + p.bh - 1) / p.bh; p.tiles_img = (N + p.bn - 1) / p.bn;
-  const int BN = (Cout <= 64) ? 64 : 128;
+  // BN = 256 halves the A-operand smem traffic per MMA (96 instead of 128 B/clk), worth it when the layer still
+  // yields enough tiles to fill the SMs
+  int BN = (Cout <= 64) ? 64 : 128;
+  {
+    const long m_tiles = (long)p.tiles_w * p.tiles_h * p.tiles_img;
+    if (Cout % 256 == 0 && m_tiles * (Cout / 256) >= 2L * b200r_num_sms()) BN = 256;
+  }
   p.tiles_n = (Cout + BN - 1) / BN;
   p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
   p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.cin_blocks = (Cin + 63) / 64; p.cin = Cin;
@@ -615,6 +623,7 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(B) failed: %d (Cout=%d K=%llu)", (int)r, Cout, (unsigned long long)K); return B200R_ECUDA; }
   }
+  if (BN == 256) return launch<256, false>(ma, mb, p, s);
   return BN == 64 ? launch<64, false>(ma, mb, p, s) : launch<128, false>(ma, mb, p, s);
 }
 

@@ -106,12 +106,22 @@ def test_jpeg_bit_exact(cuda, sev):
     assert np.array_equal(d.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("name", ["spatter"])
-def test_unimplemented_corruptions_fail_loudly(cuda, name):
+@pytest.mark.parametrize("sev", [4, 5])
+def test_spatter_mud_branch(cuda, sev):
+    images = synth_images(3, seed=40 + sev)
+    want, ext = oracle_batch(images, "spatter", sev)
+    got = _run(cuda, "spatter", sev, images, ext)
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert (diff > 1).mean() <= 2e-3, ((diff > 1).mean(), diff.max())     # threshold ties flip isolated mask pixels
+    assert np.count_nonzero(diff) / diff.size <= 0.03
+
+
+@pytest.mark.parametrize("sev", [1, 2, 3])
+def test_spatter_water_branch_fails_loudly(cuda, sev):
     from robustart_b200 import ops
     images = torch.zeros((1, 224, 224, 3), dtype=torch.uint8, device=cuda)
     with pytest.raises(NotImplementedError):
-        ops.corrupt_u8(images, name, 1)
+        ops.corrupt_u8(images, "spatter", sev)
 
 
 @pytest.mark.parametrize("name", ["gaussian_noise", "speckle_noise", "shot_noise", "impulse_noise"])

@@ -22,7 +22,8 @@ def test_split_merge_roundtrip(cuda):
     assert torch.equal(hi, x.bfloat16().float())
 
 
-@pytest.mark.parametrize("m,k,n", [(128, 64, 64), (256, 128, 128), (1000, 192, 64), (4096, 512, 1000), (300, 2048, 1000)])
+@pytest.mark.parametrize("m,k,n", [(128, 64, 64), (256, 128, 128), (1000, 192, 64), (4096, 512, 1000), (300, 2048, 1000),
+                                   (32768, 128, 512), (20000, 320, 256)])   # the last two take the BN = 256 tiles
 @pytest.mark.parametrize("passes", [3, 1])
 def test_linear_matches_fp64(cuda, m, k, n, passes):
     from robustart_b200 import ops

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200robust.so")
+LIB_PATH = os.environ.get("B200R_LIB") or os.path.join(_HERE, "lib", "libb200robust.so")
 
 _lib = None
 

@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -80,8 +81,36 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// true in exactly one (the lowest active) lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xFFFFFFFF;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
@@ -169,6 +198,8 @@ struct GemmParams {
   uint16_t* y_hi;
   uint16_t* y_lo;
   float* y_f32;
+  int res_mma;    // residual added on the tensor core: extra k-blocks R[128 x 64] * I[BN x 64]^T (needs scale == NULL)
+  int tma_store;  // planes output leaves through shared memory + cp.async.bulk.tensor stores
   // STEM variant only: the A operand is gathered from the raw uint8 NHWC image by producer warps
   const uint8_t* img;       // [N, H_in, W_in, 3]
   const uint32_t* lut;      // [3][256]: normalised value of byte b in channel c as (hi | lo << 16) bf16 pair
@@ -195,63 +226,11 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-// vector epilogue for NC (32 or 16) consecutive output channels of one pixel
-template <int NC>
-__device__ __forceinline__ void epi_vec(const GemmParams& p, const uint32_t* v, size_t off, int col0) {
-  float f[NC];
-#pragma unroll
-            for (int q = 0; q < NC / 4; ++q) {
-              const float4 s4 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + col0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
-              const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-              f[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), s4.x, b4.x);
-              f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, b4.y);
-              f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, b4.z);
-              f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, b4.w);
-            }
-            if (p.res_hi) {
-#pragma unroll
-              for (int q = 0; q < NC / 16; ++q) {
-                uint32_t hw[8], lw[8];
-                ld_global_v8(p.res_hi + off + 16 * q, hw);
-                ld_global_v8(p.res_lo + off + 16 * q, lw);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  f[16 * q + 2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-                  f[16 * q + 2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
-                }
-              }
-            }
-            if (p.act == B200R_ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.f);
-            } else if (p.act != B200R_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < NC; ++j) f[j] = apply_act(f[j], p.act);
-            }
-            if (p.y_f32) {
-#pragma unroll
-              for (int q = 0; q < NC / 4; ++q)
-                reinterpret_cast<float4*>(p.y_f32 + off)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-            }
-            if (p.y_hi) {
-              uint32_t ph[NC / 2], pl[NC / 2];
-#pragma unroll
-              for (int j = 0; j < NC / 2; ++j) {
-                ph[j] = cvt_bf16x2(f[2 * j + 1], f[2 * j]);
-                const float h0 = __uint_as_float(ph[j] << 16), h1 = __uint_as_float(ph[j] & 0xFFFF0000u);
-                pl[j] = cvt_bf16x2(f[2 * j + 1] - h1, f[2 * j] - h0);
-              }
-#pragma unroll
-              for (int q = 0; q < NC / 16; ++q) {
-                st_global_v8(p.y_hi + off + 16 * q, ph + 8 * q);
-                st_global_v8(p.y_lo + off + 16 * q, pl + 8 * q);
-              }
-            }
-}
-
 template <int BN, bool STEM>
 __global__ void __launch_bounds__(STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_i,
+            const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
   constexpr int kStages = (BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault);
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
@@ -260,11 +239,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
+  constexpr int BAR_OFF = kStages * STAGE_BYTES;        // 1 KB: mbarriers + TMEM slot
+  constexpr int STG_OFF = BAR_OFF + 1024;               // 2 x 16 KB epilogue staging ([2 planes][128 rows][64 B] per warp group)
+  constexpr int STEM_OFF = STG_OFF + 32768;             // STEM: staged input rows + LUT
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   // bars: [0,kStages) full, [kStages,2kStages) empty, [2k,2k+2) tmem_full, [2k+2,2k+4) tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index as a uniform value
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -275,6 +257,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
+    if (p.tma_store) prefetch_tmap(&map_y);
+    if (p.res_mma) { prefetch_tmap(&map_r); prefetch_tmap(&map_i); }
     // STEM: the A tile is written by 128 producer threads (one arrival each) next to the TMA thread's
     // arrive.expect_tx for the weight tile
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), STEM ? 1 + kStemProducerWarps * 32 : 1); mbar_init(empty_bar(s), 1); }
@@ -292,23 +276,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_img;
   const int total_tiles = m_tiles * p.tiles_n;
-  const int kblocks = p.KH * p.KW * p.cin_blocks;
+  const int kb_conv = p.KH * p.KW * p.cin_blocks;
+  const int kb_res = p.res_mma ? BN / 64 : 0;           // residual k-blocks: R[:, 64j:64j+64] * I[:, 64j:64j+64]^T
+  const int kblocks = kb_conv + kb_res;
   const uint32_t a_bytes = (uint32_t)p.rows_box * BK * 2;
   const uint32_t tx_bytes = (p.passes == 3 ? 2u : 1u) * ((STEM ? 0u : a_bytes) + (uint32_t)B_TILE_BYTES);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % p.tiles_n, mt = t / p.tiles_n;
-        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
-        const int w_in0 = tw * p.bw * p.stride - p.pad, h_in0 = th * p.bh * p.stride - p.pad, n0 = ti * p.bn;
-        for (int kh = 0; kh < p.KH; ++kh)
-          for (int kw = 0; kw < p.KW; ++kw)
-            for (int cb = 0; cb < p.cin_blocks; ++cb) {
-              mbar_wait(empty_bar(stage), phase ^ 1);
+    // The whole warp runs the (warp-uniform) loop and waits on the barriers; one elected lane issues.  Keeping the
+    // control flow uniform lets the compiler hold addresses / coordinates in uniform registers -- a divergent
+    // `if (lane == 0)` body costs an ELECT + branch waterfall around every UTMALDG / UTCHMMA.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
+      const int w_in0 = tw * p.bw * p.stride - p.pad, h_in0 = th * p.bh * p.stride - p.pad, n0 = ti * p.bn;
+      for (int kh = 0; kh < p.KH; ++kh)
+        for (int kw = 0; kw < p.KW; ++kw)
+          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            if (elect_one()) {
               const uint32_t sa = smem_base + stage * STAGE_BYTES;
               mbar_expect_tx(full_bar(stage), tx_bytes);
               const int kcol = (kh * p.KW + kw) * p.cin + cb * BK;
@@ -318,54 +307,92 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 if (!STEM) tma_load_5d(sa + A_TILE_BYTES, &map_a, full_bar(stage), cb * BK, w_in0 + kw, h_in0 + kh, n0, 1);
                 tma_load_3d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b, full_bar(stage), kcol, nt * BN, 1);
               }
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+      for (int j = 0; j < kb_res; ++j) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (elect_one()) {
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), 2u * a_bytes + (uint32_t)B_TILE_BYTES);
+          tma_load_5d(sa, &map_r, full_bar(stage), nt * BN + j * BK, tw * p.bw, th * p.bh, n0, 0);
+          tma_load_5d(sa + A_TILE_BYTES, &map_r, full_bar(stage), nt * BN + j * BK, tw * p.bw, th * p.bh, n0, 1);
+          tma_load_2d(sa + 2 * A_TILE_BYTES, &map_i, full_bar(stage), j * BK, 0);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < kb_conv; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + A_TILE_BYTES);
           const uint64_t b_hi = make_sw128_desc(sa + 2 * A_TILE_BYTES);
           const uint64_t b_lo = make_sw128_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+          if (p.passes == 3) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle row
-            if (p.passes == 3) {
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle row
               umma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb | k) != 0);
               umma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1);
               umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1);
-            } else {
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
               umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kb | k) != 0);
             }
           }
           umma_commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
           if (kb == kblocks - 1) umma_commit(tfull_bar(acc));  // accumulator complete
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      for (int j = 0; j < kb_res; ++j) {                   // residual: (R_hi + R_lo) * identity, exact in the fp32 accumulator
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + A_TILE_BYTES);
+          const uint64_t b_hi = make_sw128_desc(sa + 2 * A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+            umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1);
+            umma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1);
+          }
+          umma_commit(empty_bar(stage));
+          if (j == kb_res - 1) umma_commit(tfull_bar(acc));
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp < 2 + (STEM ? kStemEpiWarps : 8)) {
     // ===================== epilogue (8 warps; 4 in the STEM variant) =====================
-    // TMEM lane quarter = warp % 4 (hardware restriction); the two warps of a quarter split the columns.
+    // TMEM lane quarter = warp % 4 (hardware restriction); the two warp groups split the columns.  Planes output
+    // leaves through a 16 KB staging buffer per group ([plane][128 rows][32 channels]) and one TMA store per plane
+    // and 32-column chunk: no LSU global traffic, ragged rows / columns clipped by the tensor map.
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const int box_hw = p.bh * p.bw;
     const int nl = r / box_hw, rem = r - nl * box_hw, hl = rem / p.bw, wl = rem - hl * p.bw;
+    uint8_t* stg = smem + STG_OFF + half * 16384;
+    const uint32_t stg_u32 = smem_base + STG_OFF + half * 16384;
+    const bool issuer = (quarter == 0) && (lane == 0);
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -377,37 +404,139 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const size_t out_row = ((size_t)n_img * p.Ho + ho) * p.Wo + wo;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-#pragma unroll 1
       constexpr int kColsPerWarp = STEM ? BN : BN / 2;
-      for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-        tmem_ld_wait();
+      constexpr int kChunks = kColsPerWarp / 32;
+#ifdef B200R_EXP_KPER1
+      constexpr int kPer = 1;
+#else
+      constexpr int kPer = kChunks >= 2 ? 2 : 1;            // accumulator chunks fetched per tcgen05.wait::ld
+#endif
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
+#pragma unroll
+      for (int rd = 0; rd < kChunks / kPer; ++rd) {
+      uint32_t vv[kPer][32];
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) tmem_ld32(t_addr + (uint32_t)((rd * kPer + i) * 32), vv[i]);
+      tmem_ld_wait();
+#ifndef B200R_EXP_LATE_RELEASE
+      if (rd == kChunks / kPer - 1) {                       // accumulator is in registers: hand the TMEM buffer back early
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+#endif
+#pragma unroll
+      for (int ci = 0; ci < kPer; ++ci) {
+        const uint32_t (&v)[32] = vv[ci];
+        const int c0 = half * kColsPerWarp + (rd * kPer + ci) * 32;
         const int col0 = nt * BN + c0;
-        if (row_ok && col0 < p.Cout) {
-          const size_t off = out_row * p.Cout + col0;
-          const bool full = (col0 + 32 <= p.Cout) && (p.Cout % 16 == 0);
-          if (full) {
-            epi_vec<32>(p, v, off, col0);
-          } else if (p.Cout % 16 == 0 && col0 + 16 <= p.Cout) {
-            epi_vec<16>(p, v, off, col0);      // Cout = 16, 48, 80, ...: the last chunk is half full
-          } else {
-            // ragged last column chunk (e.g. fc: 1000 = 31*32 + 8): scalar path
-            for (int j = 0; j < 32 && col0 + j < p.Cout; ++j) {
-              const int col = col0 + j;
-              float x = fmaf(__uint_as_float(v[j]), p.scale ? __ldg(p.scale + col) : 1.f, p.bias ? __ldg(p.bias + col) : 0.f);
-              if (p.res_hi) x += bf16_bits_to_f32(p.res_hi[off + j]) + bf16_bits_to_f32(p.res_lo[off + j]);
-              x = apply_act(x, p.act);
-              if (p.y_f32) p.y_f32[off + j] = x;
-              if (p.y_hi) { uint16_t hh, ll; split_bf16(x, hh, ll); p.y_hi[off + j] = hh; p.y_lo[off + j] = ll; }
+        if (col0 >= p.Cout) continue;                     // uniform across the warp group
+        const size_t off = out_row * p.Cout + col0;
+        const bool full = (col0 + 32 <= p.Cout);
+        float f[32];
+        if (full) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 s4 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + col0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            f[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), s4.x, b4.x);
+            f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, b4.y);
+            f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, b4.z);
+            f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, b4.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = min(col0 + j, p.Cout - 1);
+            f[j] = fmaf(__uint_as_float(v[j]), p.scale ? __ldg(p.scale + col) : 1.f, p.bias ? __ldg(p.bias + col) : 0.f);
+          }
+        }
+        if (p.res_hi && !p.res_mma && row_ok) {           // LSU fallback (scaled convolutions with a residual)
+          if (full && (p.Cout % 16 == 0)) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              uint32_t hw[8], lw[8];
+              ld_global_v8(p.res_hi + off + 16 * q, hw);
+              ld_global_v8(p.res_lo + off + 16 * q, lw);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f[16 * q + 2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                f[16 * q + 2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+              }
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)   // compile-time j: the arrays must stay in registers
+              if (col0 + j < p.Cout) f[j] += bf16_bits_to_f32(p.res_hi[off + j]) + bf16_bits_to_f32(p.res_lo[off + j]);
+          }
+        }
+        if (p.act == B200R_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act != B200R_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        }
+        if (p.y_f32 && row_ok) {
+          if (full && (p.Cout % 4 == 0)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<float4*>(p.y_f32 + off)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Cout) p.y_f32[off + j] = f[j];
+          }
+        }
+        if (p.y_hi) {
+          uint32_t ph[16], pl[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            ph[j] = cvt_bf16x2(f[2 * j + 1], f[2 * j]);
+            const float h0 = __uint_as_float(ph[j] << 16), h1 = __uint_as_float(ph[j] & 0xFFFF0000u);
+            pl[j] = cvt_bf16x2(f[2 * j + 1] - h1, f[2 * j] - h0);
+          }
+          if (p.tma_store) {
+            if (issuer) bulk_wait_read0();                 // the previous store has finished reading the staging buffer
+            named_bar_sync(2 + half, 128);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              // 64-byte rows in the TMA SWIZZLE_64B pattern (16-byte chunk index ^= address bits [7:8] = (row >> 1) & 3):
+              // 8 consecutive rows cover all 32 banks, so the 16-byte stores are conflict free
+              const int pos = (q ^ ((r >> 1) & 3)) * 16;
+              *reinterpret_cast<uint4*>(stg + r * 64 + pos) = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+              *reinterpret_cast<uint4*>(stg + 8192 + r * 64 + pos) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+            }
+            fence_proxy_async();
+            named_bar_sync(2 + half, 128);
+            if (issuer) {
+              tma_store_5d(&map_y, stg_u32, col0, tw * p.bw, th * p.bh, ti * p.bn, 0);
+              tma_store_5d(&map_y, stg_u32 + 8192, col0, tw * p.bw, th * p.bh, ti * p.bn, 1);
+              bulk_commit();
+            }
+          } else if (row_ok && full && (p.Cout % 16 == 0)) {   // direct 256-bit stores
+            st_global_v8(p.y_hi + off, ph);
+            st_global_v8(p.y_hi + off + 16, ph + 8);
+            st_global_v8(p.y_lo + off, pl);
+            st_global_v8(p.y_lo + off + 16, pl + 8);
+          } else if (row_ok) {                             // ragged direct stores
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Cout) {
+                p.y_hi[off + j] = (uint16_t)(ph[j >> 1] >> (16 * (j & 1)));
+                p.y_lo[off + j] = (uint16_t)(pl[j >> 1] >> (16 * (j & 1)));
+              }
           }
         }
       }
+      }
+#ifdef B200R_EXP_LATE_RELEASE
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+#endif
     }
+    if (issuer) bulk_wait0();                              // all stores complete before the CTA exits
   } else if (STEM) {
     // ===================== stem A producer (4 warps) =====================
     // 7x7 / stride 2 / pad 3 patches of the uint8 NHWC image.  A tile = ONE output row of one image
@@ -421,7 +550,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int r = ptid >> 1, sub = ptid & 1;                     // tile row = output column ox; each thread builds 4 of the 8 chunks
     const int row_bytes = p.W_in * 3;
     const int pitch = 9 + row_bytes + 15;                       // staged words per input row (zero padded)
-    uint32_t* s_conv = reinterpret_cast<uint32_t*>(smem + kStages * STAGE_BYTES + 512);
+    uint32_t* s_conv = reinterpret_cast<uint32_t*>(smem + STEM_OFF);
     uint32_t* s_lut = s_conv + 7 * pitch;
     for (int i = ptid; i < 768; i += kProd) s_lut[i] = __ldg(p.lut + i);
     for (int i = ptid; i < 7 * pitch; i += kProd) s_conv[i] = 0u;   // pads stay zero for the whole kernel
@@ -529,12 +658,15 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+struct GemmMaps { CUtensorMap a, b, r, i, y; };
+
 template <int BN, bool STEM>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
+int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t s) {
   constexpr int kStages = (BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault);
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * BN * BK * 2;
   // STEM adds the staged input rows (7 x (W_in*3 + 24) words) and the 3 KB LUT behind the barriers
-  const int smem = kStages * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + (STEM ? 7 * (p.W_in * 3 + 24) * 4 + 768 * 4 : 0);
+  const int smem = kStages * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ +
+                   ((STEM || p.tma_store) ? 32768 : 0) /*epilogue staging*/ + (STEM ? 7 * (p.W_in * 3 + 24) * 4 + 768 * 4 : 0);
   static int configured = 0;
   if (configured < smem) {
     B200R_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -542,8 +674,81 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cu
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_img * p.tiles_n;
   const int grid = total < b200r_num_sms() ? total : b200r_num_sms();
-  gemm_kernel<BN, STEM><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(ma, mb, p);
+  gemm_kernel<BN, STEM><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(m.a, m.b, m.r, m.i, m.y, p);
   B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+// 5-D map over split planes [plane][N][H][W][C] (dims listed innermost first)
+int make_map5(EncodeTiledFn enc, CUtensorMap* m, const uint16_t* base, int C, int W, int H, int N, size_t plane_elems, int box_c,
+              int box_w, int box_h, int box_n, int estride, CUtensorMapSwizzle swz, const char* what) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, 2};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)plane_elems * 2};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), (cuuint32_t)box_n, 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b200r_set_error("cuTensorMapEncodeTiled(%s) failed: %d (N=%d H=%d W=%d C=%d box %d,%d,%d,%d s=%d)", what, (int)r, N, H, W, C, box_n,
+                    box_h, box_w, box_c, estride);
+    return B200R_ECUDA;
+  }
+  return B200R_OK;
+}
+
+// 256 x 256 bf16 identity (the B operand of the residual k-blocks), one per device
+uint16_t* g_ident[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+std::mutex g_ident_mu;
+int get_identity(const uint16_t** out) {
+  int dev = 0;
+  B200R_CUDA(cudaGetDevice(&dev));
+  B200R_CHECK_ARG(dev >= 0 && dev < 8, "device index out of range");
+  std::lock_guard<std::mutex> lk(g_ident_mu);
+  if (!g_ident[dev]) {  // first use per device: blocking copy (not capturable)
+    static uint16_t h[256 * 256];
+    memset(h, 0, sizeof(h));
+    for (int i = 0; i < 256; ++i) h[i * 256 + i] = 0x3F80;   // bf16 1.0
+    B200R_CUDA(cudaMalloc(&g_ident[dev], sizeof(h)));
+    B200R_CUDA(cudaMemcpy(g_ident[dev], h, sizeof(h), cudaMemcpyHostToDevice));
+  }
+  *out = g_ident[dev];
+  return B200R_OK;
+}
+
+// output / residual / identity maps + flags shared by conv_impl and the fused stem
+// tuning switch for experiments: B200R_GEMM_OPTS bit 0 = epilogue stores through the LSU instead of TMA,
+// bit 1 = residual through the LSU instead of identity k-blocks
+int gemm_opts() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200R_GEMM_OPTS"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+int finish_maps(EncodeTiledFn enc, GemmMaps* m, GemmParams* p, const uint16_t* res, uint16_t* y, size_t ycount, int BN) {
+  p->tma_store = 0;
+  p->res_mma = 0;
+  m->r = m->b; m->i = m->b; m->y = m->b;   // placeholders (never dereferenced unless the flag is set)
+  if (y && p->Cout % 8 == 0 && !(gemm_opts() & 1)) {
+    int rc = make_map5(enc, &m->y, y, p->Cout, p->Wo, p->Ho, p->N, ycount, 32, p->bw, p->bh, p->bn, 1, CU_TENSOR_MAP_SWIZZLE_64B, "Y");
+    if (rc) return rc;
+    p->tma_store = 1;
+  }
+  if (res && !p->scale && p->Cout % 8 == 0 && !(gemm_opts() & 2)) {
+    int rc = make_map5(enc, &m->r, res, p->Cout, p->Wo, p->Ho, p->N, ycount, BK, p->bw, p->bh, p->bn, 1, CU_TENSOR_MAP_SWIZZLE_128B, "R");
+    if (rc) return rc;
+    const uint16_t* ident = nullptr;
+    rc = get_identity(&ident);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {256, 256};
+    cuuint64_t strides[1] = {512};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&m->i, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(ident), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(identity) failed: %d", (int)r); return B200R_ECUDA; }
+    p->res_mma = 1;
+  }
   return B200R_OK;
 }
 
@@ -601,16 +806,10 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
   p.res_hi = res; p.res_lo = res ? res + ycount : nullptr;
   p.y_hi = y; p.y_lo = y ? y + ycount : nullptr; p.y_f32 = y_f32;
 
-  CUtensorMap ma, mb;
+  GemmMaps m;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, 2};
-    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2, (cuuint64_t)xcount * 2};
-    cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)(p.bw * stride), (cuuint32_t)(p.bh * stride), (cuuint32_t)p.bn, 1};
-    cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
-    CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(x), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(A) failed: %d (N=%d H=%d W=%d C=%d box %d,%d,%d s=%d)", (int)r, N, H, W, Cin, p.bn, p.bh, p.bw, stride); return B200R_ECUDA; }
+    int rc = make_map5(enc, &m.a, x, Cin, W, H, N, xcount, BK, p.bw, p.bh, p.bn, stride, CU_TENSOR_MAP_SWIZZLE_128B, "A");
+    if (rc) return rc;
   }
   {
     const cuuint64_t K = (cuuint64_t)KH * KW * Cin;
@@ -618,13 +817,17 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
     cuuint64_t strides[2] = {K * 2, (cuuint64_t)wcount * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
+    CUresult r = enc(&m.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(B) failed: %d (Cout=%d K=%llu)", (int)r, Cout, (unsigned long long)K); return B200R_ECUDA; }
   }
-  if (BN == 256) return launch<256, false>(ma, mb, p, s);
-  return BN == 64 ? launch<64, false>(ma, mb, p, s) : launch<128, false>(ma, mb, p, s);
+  {
+    int rc = finish_maps(enc, &m, &p, res, y, ycount, BN);
+    if (rc) return rc;
+  }
+  if (BN == 256) return launch<256, false>(m, p, s);
+  return BN == 64 ? launch<64, false>(m, p, s) : launch<128, false>(m, p, s);
 }
 
 // ---- fused stem ---------------------------------------------------------------------------------
@@ -695,19 +898,22 @@ int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* 
   p.passes = passes; p.act = act; p.scale = scale; p.bias = bias;
   p.y_hi = y; p.y_lo = y + (size_t)p.M_total * Cout;
   p.img = img; p.lut = lut; p.H_in = h; p.W_in = w;
-  CUtensorMap mb;
+  GemmMaps m;
   {
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, 2};
     cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)Cout * K * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, 64, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
+    CUresult r = enc(&m.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(stem B) failed: %d", (int)r); return B200R_ECUDA; }
   }
+  m.a = m.b;
   p.stem_Ho = Ho; p.stem_Wo = Wo;   // the producer decodes (n, oy, ox) from the real output geometry
-  return launch<64, true>(mb, mb, p, as_stream(stream));
+  rc = finish_maps(enc, &m, &p, nullptr, y, (size_t)p.M_total * Cout, 64);
+  if (rc) return rc;
+  return launch<64, true>(m, p, as_stream(stream));
 }
 
 int b200r_conv2d_nhwc(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias, const uint16_t* res,

@@ -117,8 +117,11 @@ class _ConvBN:
         gamma, beta = sd[bn + ".weight"].double(), sd[bn + ".bias"].double()
         mean, var = sd[bn + ".running_mean"].double(), sd[bn + ".running_var"].double()
         scale = gamma / torch.sqrt(var + BN_EPS)
-        self.scale = scale.float().to(device).contiguous()
+        # the BN scale is folded into the weights (fp64 product, then the usual hi/lo split): a scale-free
+        # epilogue lets the kernel add the residual on the tensor core (identity k-blocks) instead of the LSU
+        self.scale = None
         self.bias = (beta - mean * scale).float().to(device).contiguous()
+        w = (w.double() * scale.view(-1, 1, 1, 1)).float()
         self.w = ops.split_f32(w.permute(0, 2, 3, 1).contiguous().to(device))
         self.stride, self.pad = stride, pad
 
@@ -497,8 +500,10 @@ class _PW:
 
     def __init__(self, sd, conv, bn, device):
         w = sd[conv + ".weight"].float()
+        scale, self.bias = _fold_bn(sd, bn, device)
+        self.scale = None                                    # folded into the weights (see _ConvBN)
+        w = (w.reshape(w.shape[0], -1).double() * scale.double().cpu().view(-1, 1)).float()
         self.w = ops.split_f32(w.reshape(w.shape[0], 1, 1, w.shape[1]).contiguous().to(device))
-        self.scale, self.bias = _fold_bn(sd, bn, device)
 
     def __call__(self, x, act=None, res=None, passes=3):
         return ops.conv2d_nhwc(x, self.w, self.scale, self.bias, res, act=act, passes=passes)

@@ -197,7 +197,8 @@ int b200r_linear(const uint16_t* x, const uint16_t* wgt, const float* scale, con
                  int passes, b200r_stream_t stream);
 
 /* 7x7/s2 stem patches (resnet_official.py:221-224): u8 NHWC image -> normalised, im2col'd split
- * planes [n*ho*wo, kpad] with kpad = 192 (7*7*3 = 147 zero-padded), column = (ky*7+kx)*3+c. */
+ * planes [n*ho*wo, kpad] with kpad = 192: column = ky*24 + kx*3 + c (kx < 7); each ky run is padded to 8
+ * taps, so columns ky*24+21..23 and 168..191 are zero. */
 int b200r_stem_im2col_u8(const uint8_t* img, uint16_t* planes, int n, int h, int w,
                          const float* mean_host, const float* std_host, b200r_stream_t stream);
 /* same from float32 NCHW in [0,1] (the attack path) */
@@ -207,8 +208,8 @@ int b200r_stem_im2col_f32(const float* img, uint16_t* planes, int n, int h, int 
 /* Fused stem: conv1 7x7/s2/p3 (3 -> 64) + BN + act straight from the raw uint8 NHWC image
  * (resnet_official.py:221-226,331-333 after ToTensor+Normalize, imagenet_dataloader.py:78-79): the patch
  * gather, x/255, (x-mean)/std and the bf16 split happen while the operand tile is written to shared
- * memory; nothing but the image is read from HBM.  wgt: split planes [64, 192] (column = (ky*7+kx)*3+c,
- * 147 real + 45 zero columns); y: split planes [n, h/2, w/2, 64]. */
+ * memory; nothing but the image is read from HBM.  wgt: split planes [64, 192] in the im2col column order
+ * above (column = ky*24 + kx*3 + c; the 45 padding columns MUST be zero); y: split planes [n, h/2, w/2, 64]. */
 int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* scale, const float* bias,
                           uint16_t* y, int n, int h, int w, const float* mean_host,
                           const float* std_host, int act, int passes, b200r_stream_t stream);

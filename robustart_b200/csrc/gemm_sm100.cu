@@ -276,6 +276,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_img;
   const int total_tiles = m_tiles * p.tiles_n;
+  // tile schedule: round-robin over CTAs; the STEM variant takes a contiguous range instead, so that consecutive
+  // tiles of a CTA are consecutive output rows of one image and the staged input rows slide by two
+  const int t_first = STEM ? (int)((long long)blockIdx.x * total_tiles / gridDim.x) : (int)blockIdx.x;
+  const int t_end = STEM ? (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x) : total_tiles;
+  const int t_step = STEM ? 1 : (int)gridDim.x;
   const int kb_conv = p.KH * p.KW * p.cin_blocks;
   const int kb_res = p.res_mma ? BN / 64 : 0;           // residual k-blocks: R[:, 64j:64j+64] * I[:, 64j:64j+64]^T
   const int kblocks = kb_conv + kb_res;
@@ -289,7 +294,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // `if (lane == 0)` body costs an ELECT + branch waterfall around every UTMALDG / UTCHMMA.
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = t_first; t < t_end; t += t_step) {
       const int nt = t % p.tiles_n, mt = t / p.tiles_n;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
       const int w_in0 = tw * p.bw * p.stride - p.pad, h_in0 = th * p.bh * p.stride - p.pad, n0 = ti * p.bn;
@@ -327,7 +332,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = t_first; t < t_end; t += t_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -394,7 +399,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const uint32_t stg_u32 = smem_base + STG_OFF + half * 16384;
     const bool issuer = (quarter == 0) && (lane == 0);
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = t_first; t < t_end; t += t_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int nt = t % p.tiles_n, mt = t / p.tiles_n;
@@ -406,11 +411,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       tc_fence_after();
       constexpr int kColsPerWarp = STEM ? BN : BN / 2;
       constexpr int kChunks = kColsPerWarp / 32;
-#ifdef B200R_EXP_KPER1
-      constexpr int kPer = 1;
-#else
       constexpr int kPer = kChunks >= 2 ? 2 : 1;            // accumulator chunks fetched per tcgen05.wait::ld
-#endif
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
 #pragma unroll
       for (int rd = 0; rd < kChunks / kPer; ++rd) {
@@ -418,13 +419,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
       for (int i = 0; i < kPer; ++i) tmem_ld32(t_addr + (uint32_t)((rd * kPer + i) * 32), vv[i]);
       tmem_ld_wait();
-#ifndef B200R_EXP_LATE_RELEASE
       if (rd == kChunks / kPer - 1) {                       // accumulator is in registers: hand the TMEM buffer back early
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
-#endif
 #pragma unroll
       for (int ci = 0; ci < kPer; ++ci) {
         const uint32_t (&v)[32] = vv[ci];
@@ -530,72 +529,90 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
       }
       }
-#ifdef B200R_EXP_LATE_RELEASE
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-#endif
     }
     if (issuer) bulk_wait0();                              // all stores complete before the CTA exits
   } else if (STEM) {
-    // ===================== stem A producer (4 warps) =====================
+    // ===================== stem A producer (8 warps) =====================
     // 7x7 / stride 2 / pad 3 patches of the uint8 NHWC image.  A tile = ONE output row of one image
-    // (Wo <= 128 pixels).  Per tile the 7 input rows it touches are staged once in shared memory, already
-    // mapped through the 3x256 LUT (ToTensor + Normalize + bf16 split -> hi | lo<<16) and padded with zero
-    // columns/rows, so the per-pixel gather needs no bounds checks: K is ordered (ky, kx, c), i.e. 7 runs of
-    // 21 consecutive staged words starting at word 6*ox.  The 64-element k-block row goes out as 8 16-byte
-    // chunks at the 128B-swizzled position (chunk ^ (row & 7)).
+    // (Wo <= 128 pixels).  The 7 input rows a tile touches live in a 7-slot ring in shared memory (row iy in slot
+    // (iy + 3) % 7), already mapped through the 3x256 LUT (ToTensor + Normalize + bf16 split -> hi | lo<<16) and
+    // padded with zero columns/rows, so the per-pixel gather needs no bounds checks: K is ordered (ky, kx8, c)
+    // with EIGHT kx slots per ky (the 8th carries a zero weight), i.e. 7 runs of 24 consecutive staged words
+    // starting at word 6*ox = three aligned 8-word chunks each, read with 64-bit loads.  Consecutive tiles of a CTA are
+    // consecutive output rows, so only two new input rows are staged per tile; their global loads are issued
+    // before the gather of the current tile and land in the ring after it (the two slots they replace are dead
+    // by then).  The 64-element k-block row goes out as 8 16-byte chunks at the 128B-swizzled position
+    // (chunk ^ (row & 7)).
     constexpr int kProd = kStemProducerWarps * 32;               // 256 producer threads
     const int ptid = threadIdx.x - (2 + kStemEpiWarps) * 32;
-    const int r = ptid >> 1, sub = ptid & 1;                     // tile row = output column ox; each thread builds 4 of the 8 chunks
+    const int pw = warp - (2 + kStemEpiWarps);                   // producer warp 0..7 (warp-uniform)
+    const int r = ((pw & 3) << 5) | lane;                        // tile row = output column ox
+    const int sub = pw >> 2;                                     // this warp builds chunks [4*sub, 4*sub + 4) of every k-block
     const int row_bytes = p.W_in * 3;
     const int pitch = 9 + row_bytes + 15;                       // staged words per input row (zero padded)
+    const int q_per_row = row_bytes / 16;                       // 16-byte groups per input row (42 for W = 224)
     uint32_t* s_conv = reinterpret_cast<uint32_t*>(smem + STEM_OFF);
     uint32_t* s_lut = s_conv + 7 * pitch;
     for (int i = ptid; i < 768; i += kProd) s_lut[i] = __ldg(p.lut + i);
     for (int i = ptid; i < 7 * pitch; i += kProd) s_conv[i] = 0u;   // pads stay zero for the whole kernel
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int mt = t / p.tiles_n;
-      const int oy = mt % p.tiles_h, n_img = mt / p.tiles_h;
+
+    constexpr int kMaxIt = 2;                                    // ceil(7 * q_per_row / 256) for W <= 256
+    uint4 v[kMaxIt];
+    int dstw[kMaxIt];                                            // staged word offset; -1 = nothing; <= -2 = zero row
+    // issue the loads of input rows [iy0, iy0 + nrows) of image n_img (nrows = 7 at an image start, else 2)
+    auto fetch_rows = [&](int n_img, int iy0, int nrows) {
       const uint8_t* img_base = p.img + (long long)n_img * p.H_in * row_bytes;
-      // stage the 7 input rows: 16-byte loads (all issued before first use), bytes -> LUT words
-      {
-        const int q_per_row = row_bytes / 16;                   // 42 for W = 224
-        constexpr int kMaxIt = 2;                               // ceil(7*q_per_row / 256) for W <= 256 (requires row_bytes % 16 == 0)
-        uint4 v[kMaxIt];
-        int dstw[kMaxIt];
 #pragma unroll
-        for (int it = 0; it < kMaxIt; ++it) {
-          const int idx = ptid + it * kProd;
-          dstw[it] = -1;
-          v[it] = make_uint4(0, 0, 0, 0);
-          if (idx < 7 * q_per_row) {
-            const int ky = idx / q_per_row, q = idx - ky * q_per_row, iy = oy * 2 - 3 + ky;
-            dstw[it] = ky * pitch + 9 + q * 16;
-            if (iy >= 0 && iy < p.H_in) v[it] = __ldg(reinterpret_cast<const uint4*>(img_base + (long long)iy * row_bytes) + q);
-            else dstw[it] = -(ky * pitch + 9 + q * 16) - 2;     // out-of-image row: store zeros
-          }
-        }
-#pragma unroll
-        for (int it = 0; it < kMaxIt; ++it) {
-          if (dstw[it] == -1) continue;
-          const bool zero = dstw[it] < 0;
-          const int d0 = zero ? -(dstw[it] + 2) : dstw[it];
-          const uint32_t w4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-          const int c0 = (d0 - 9 - (d0 / pitch) * pitch) % 3;   // channel of the first byte of this 16-byte group
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint32_t b = (w4[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            const int c = (c0 + j) % 3;
-            s_conv[d0 + j] = zero ? 0u : s_lut[c * 256 + b];
-          }
+      for (int it = 0; it < kMaxIt; ++it) {
+        const int idx = ptid + it * kProd;
+        dstw[it] = -1;
+        v[it] = make_uint4(0, 0, 0, 0);
+        if (idx < nrows * q_per_row) {
+          const int k = idx / q_per_row, q = idx - k * q_per_row, iy = iy0 + k;
+          const int d = ((iy + 3 + 7) % 7) * pitch + 9 + q * 16;
+          if (iy >= 0 && iy < p.H_in) { v[it] = __ldg(reinterpret_cast<const uint4*>(img_base + (long long)iy * row_bytes) + q); dstw[it] = d; }
+          else dstw[it] = -d - 2;                                 // out-of-image row: store zeros
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const uint32_t* my = s_conv + 6 * r;                      // (2*ox - 3)*3 + 9 = 6*ox
+    };
+    // bytes -> LUT words into the ring
+    auto stage_rows = [&]() {
+#pragma unroll
+      for (int it = 0; it < kMaxIt; ++it) {
+        if (dstw[it] == -1) continue;
+        const bool zero = dstw[it] < 0;
+        const int d0 = zero ? -(dstw[it] + 2) : dstw[it];
+        const uint32_t w4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+        const int c0 = (d0 - 9 - (d0 / pitch) * pitch) % 3;     // channel of the first byte of this 16-byte group
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t b = (w4[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+          const int c = (c0 + j) % 3;
+          s_conv[d0 + j] = zero ? 0u : s_lut[c * 256 + b];
+        }
+      }
+    };
+
+    int stage = 0;
+    uint32_t phase = 0;
+    if (t_first < t_end) {                                       // cold start: all 7 rows of the first tile
+      const int oy = t_first % p.tiles_h, n_img = t_first / p.tiles_h;
+      fetch_rows(n_img, 2 * oy - 3, 7);
+      stage_rows();
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int t = t_first; t < t_end; ++t) {
+      const int oy = t % p.tiles_h, n_img = t / p.tiles_h;
+      // prefetch what the next tile adds
+      const bool has_next = (t + 1 < t_end);
+      if (has_next) {
+        if (oy + 1 < p.tiles_h) fetch_rows(n_img, 2 * oy + 4, 2);
+        else fetch_rows(n_img + 1, -3, 7);
+      }
+      int rowoff[7];
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky) rowoff[ky] = ((2 * oy + ky) % 7) * pitch + 6 * r;   // (2*ox - 3)*3 + 9 = 6*ox
 #pragma unroll
       for (int kb = 0; kb < 3; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
@@ -604,29 +621,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (r < p.rows_box) {
 #pragma unroll
           for (int q8 = 0; q8 < 8; ++q8) {
-            if ((q8 >> 2) != sub) continue;                     // compile-time q (constant K indices), runtime predicate
+            if ((q8 >> 2) != sub) continue;                     // warp-uniform; q stays a compile-time constant
             const int q = q8;
+            const int chunk = kb * 8 + q;                       // K chunk 0..23 = (ky, third of the 24-word run)
             uint32_t e[8];
+            if (chunk < 21) {
+              const uint2* src = reinterpret_cast<const uint2*>(s_conv + rowoff[chunk / 3] + 8 * (chunk % 3));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int col = kb * 64 + q * 8 + j;
-              e[j] = (col < 147) ? my[(col / 21) * pitch + (col % 21)] : 0u;
+              for (int j = 0; j < 4; ++j) { const uint2 w2 = src[j]; e[2 * j] = w2.x; e[2 * j + 1] = w2.y; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) e[j] = 0u;
             }
             uint4 h, l;
             h.x = __byte_perm(e[0], e[1], 0x5410); h.y = __byte_perm(e[2], e[3], 0x5410);
             h.z = __byte_perm(e[4], e[5], 0x5410); h.w = __byte_perm(e[6], e[7], 0x5410);
             l.x = __byte_perm(e[0], e[1], 0x7632); l.y = __byte_perm(e[2], e[3], 0x7632);
             l.z = __byte_perm(e[4], e[5], 0x7632); l.w = __byte_perm(e[6], e[7], 0x7632);
-            const int chunk = (q ^ (r & 7)) << 4;
-            *reinterpret_cast<uint4*>(a_hi + chunk) = h;
-            if (p.passes == 3) *reinterpret_cast<uint4*>(a_lo + chunk) = l;
+            const int pos = (q ^ (r & 7)) << 4;
+            *reinterpret_cast<uint4*>(a_hi + pos) = h;
+            if (p.passes == 3) *reinterpret_cast<uint4*>(a_lo + pos) = l;
           }
         }
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
         mbar_arrive(full_bar(stage));
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");            // everyone done reading s_conv before restaging
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // everyone done reading the ring rows this tile retires
+      if (has_next) stage_rows();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   }
 

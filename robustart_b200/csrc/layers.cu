@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(kThreads) merge_kernel(const uint2* __restrict
 }
 
 // ---- stem im2col ------------------------------------------------------------------------------
-// one thread per (output pixel, 8-column chunk): kpad = 192 columns = 24 chunks; column = (ky*7+kx)*3+c
+// one thread per (output pixel, 8-column chunk): kpad = 192 columns = 24 chunks; column = ky*24 + kx*3 + c with
+// kx in [0,7) -- every ky run is padded to 8 taps (columns ky*24+21..23 and 168..191 are zero) so that the fused
+// stem's operand producer (gemm_sm100.cu) reads aligned 8-word chunks
 constexpr int kStemK = 192;
 struct Norm3 { float mean[3], std[3]; };
 
@@ -57,9 +59,9 @@ __global__ void __launch_bounds__(kThreads) stem_im2col_kernel(const void* __res
     for (int j = 0; j < 8; ++j) {
       const int col = chunk * 8 + j;
       float v = 0.f;
-      if (col < 147) {
-        const int tap = col / 3, c = col - tap * 3;
-        const int ky = tap / 7, kx = tap - ky * 7;
+      const int ky = col / 24, rem = col - ky * 24;
+      if (col < 168 && rem < 21) {
+        const int kx = rem / 3, c = rem - kx * 3;
         const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
         if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
           float x;

@@ -137,11 +137,8 @@ class ResNet:
         kind, layers = _RESNET_CFG[arch]
         sd = _strip_prefix(state_dict)
         dev = self.device
-        # stem: 7x7/s2 as a GEMM over im2col'd patches, K = (ky, kx, c) padded 147 -> 192
-        w = sd["conv1.weight"].float().permute(0, 2, 3, 1).reshape(64, 147)
-        wp = torch.zeros(64, 192)
-        wp[:, :147] = w
-        self.stem_w = ops.split_f32(wp.to(dev).contiguous())
+        # stem: 7x7/s2 as a GEMM over im2col'd patches, K = (ky, 8 kx slots, c) = 168 padded to 192
+        self.stem_w = ops.split_f32(ops.pack_stem_weight(sd["conv1.weight"]).to(dev).contiguous())
         g, b = sd["bn1.weight"].double(), sd["bn1.bias"].double()
         m, v = sd["bn1.running_mean"].double(), sd["bn1.running_var"].double()
         s = g / torch.sqrt(v + BN_EPS)

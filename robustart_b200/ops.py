@@ -294,6 +294,17 @@ def stem_im2col(img, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
     return out
 
 
+def pack_stem_weight(w: torch.Tensor) -> torch.Tensor:
+    """conv1 weight [64, 3, 7, 7] -> float32 [64, 192] in the stem's K order: column = ky*24 + kx*3 + c, every ky
+    run padded from 7 to 8 taps with zeros (include/b200r.h, b200r_stem_im2col_u8)."""
+    cout = w.shape[0]
+    wp = torch.zeros(cout, 7, 8, 3, dtype=torch.float32, device=w.device)
+    wp[:, :, :7, :] = w.float().permute(0, 2, 3, 1)
+    out = torch.zeros(cout, 192, dtype=torch.float32, device=w.device)
+    out[:, :168] = wp.reshape(cout, 168)
+    return out
+
+
 def stem_conv7x7_u8(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
     """Fused 7x7/s2 stem from raw uint8 NHWC pixels: planes [2, n, h/2, w/2, 64]."""
     _need_cuda(img, torch.uint8, "img")

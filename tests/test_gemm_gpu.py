@@ -106,15 +106,17 @@ def test_stem_im2col(cuda):
     cols = ops.merge_f32(p).view(2, 112, 112, 192)
     xn = ops.u8nhwc_to_f32nchw(img)
     ref = torch.nn.functional.unfold(xn, 7, padding=3, stride=2)         # [n, 3*49, L] ordered (c, ky, kx)
-    ref = ref.view(2, 3, 49, 112, 112).permute(0, 3, 4, 2, 1).reshape(2, 112, 112, 147)  # (tap, c)
-    assert (cols[..., :147] - ref).abs().max().item() < 1e-4
-    assert cols[..., 147:].abs().max().item() == 0
+    ref = ref.view(2, 3, 7, 7, 112, 112).permute(0, 4, 5, 2, 3, 1)         # [n, oy, ox, ky, kx, c]
+    cols = cols[..., :168].reshape(2, 112, 112, 7, 8, 3)                    # K = (ky, 8 kx slots, c), then zeros
+    assert (cols[..., :7, :] - ref).abs().max().item() < 1e-4
+    assert cols[..., 7, :].abs().max().item() == 0
+    assert ops.merge_f32(p).view(2, 112, 112, 192)[..., 168:].abs().max().item() == 0
     # float path
     x01 = torch.rand(2, 3, 224, 224, device=cuda)
     p2 = ops.merge_f32(ops.stem_im2col(x01)).view(2, 112, 112, 192)
     ref2 = torch.nn.functional.unfold(ops.normalize(x01), 7, padding=3, stride=2)
-    ref2 = ref2.view(2, 3, 49, 112, 112).permute(0, 3, 4, 2, 1).reshape(2, 112, 112, 147)
-    assert (p2[..., :147] - ref2).abs().max().item() < 1e-4
+    ref2 = ref2.view(2, 3, 7, 7, 112, 112).permute(0, 4, 5, 2, 3, 1)
+    assert (p2[..., :168].reshape(2, 112, 112, 7, 8, 3)[..., :7, :] - ref2).abs().max().item() < 1e-4
 
 
 def test_fused_stem_matches_im2col_path(cuda):
@@ -125,8 +127,7 @@ def test_fused_stem_matches_im2col_path(cuda):
     w = torch.randn(64, 3, 7, 7, device=cuda) * 0.1
     s = torch.rand(64, device=cuda) + 0.5
     b = torch.randn(64, device=cuda)
-    wp = torch.zeros(64, 192, device=cuda)
-    wp[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)
+    wp = ops.pack_stem_weight(w)
     y = ops.stem_conv7x7_u8(img, ops.split_f32(wp), s, b, act="relu")
     torch.cuda.synchronize()
     got = ops.merge_f32(y).permute(0, 3, 1, 2)

@@ -222,6 +222,33 @@ int b200r_global_avgpool_nhwc(const uint16_t* x, uint16_t* y, int n, int hw, int
                               b200r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Input-gradient pass (d loss / d image) of the convolutional models: what the attack loops call once
+ * per step (foolbox value_and_grad in attack.py:20-33; autopgd_base.py:371-376; imfgsm_attack.py:77-84).
+ * Only INPUT gradients exist on this path -- no weight gradients.  The contractions are b200r_conv2d_nhwc /
+ * b200r_linear on transposed (and for 3x3: spatially flipped) weights; a stride-2 convolution's dgrad is
+ * dilate2 followed by the stride-1 convolution.  Everything stays in split planes.
+ * ------------------------------------------------------------------------------------------ */
+/* ReLU backward: out = (act > 0 ? dy : 0) + add; add may be NULL (a second gradient branch joining here,
+ * e.g. the identity path of a residual block).  count = elements per plane, multiple of 8. */
+int b200r_relu_bwd(const uint16_t* dy, const uint16_t* act, const uint16_t* add, uint16_t* out,
+                   size_t count, b200r_stream_t stream);
+/* y[n, 2i, 2j, :] = x[n, i, j, :], zero elsewhere; x planes [n,h,w,c] -> y planes [n,2h,2w,c] */
+int b200r_dilate2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int c,
+                       b200r_stream_t stream);
+/* MaxPool2d(3,2,1) backward (resnet_official.py:227): x = the pool's forward input planes [n,h,w,c],
+ * dy planes [n,ho,wo,c] -> dx planes [n,h,w,c]; ties go to the first maximum in (ky,kx) scan order as in
+ * the forward kernel and in PyTorch.  workspace: n*ho*wo*c bytes (arg-max codes), 8-byte aligned. */
+int b200r_maxpool3x3s2_bwd_nhwc(const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* workspace,
+                                size_t ws_bytes, int n, int h, int w, int c, b200r_stream_t stream);
+/* AdaptiveAvgPool2d(1) backward: dy planes [n,c] -> dx planes [n,hw,c] = dy / hw */
+int b200r_global_avgpool_bwd_nhwc(const uint16_t* dy, uint16_t* dx, int n, int hw, int c,
+                                  b200r_stream_t stream);
+/* Transpose of b200r_stem_im2col_f32 composed with Normalize: dcols planes [n*(h/2)*(w/2), 192] (column order
+ * of b200r_stem_im2col_u8) -> float32 NCHW gradient w.r.t. the [0,1] image, dx[n,c,y,x] = sum(taps) / std[c]. */
+int b200r_stem_col2im_f32(const uint16_t* dcols, float* dx, int n, int h, int w, const float* std_host,
+                          b200r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Mobile families (MobileNetV2: prototype/prototype/model/mobilenet_v2.py:31-202; EfficientNet-B0:
  * prototype/prototype/model/efficientnet.py:289-495): the layers that are not dense contractions.
  * ------------------------------------------------------------------------------------------ */

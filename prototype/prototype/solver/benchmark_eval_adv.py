@@ -24,7 +24,7 @@ def main(argv=None):
     prefix = args.tgt_name + "_" + args.attack + "_" + str(eps)[0:min(5, len(str(eps)))]
     d = S.dist_init()
     sol = S.EvalSolver(config, prefix=prefix, dist_info=d)
-    model_src = S.build_torch_model(config.model_src, args.src_path, sol.device)
+    model_src = S.build_source_model(config.model_src, args.src_path, sol.device)
     model_tgt = S.build_b200_model(config.model_tgt, args.tgt_path, sol.device)
     return sol.evaluate_adv(model_src, model_tgt, attack=args.attack, eps=eps)
 

@@ -63,6 +63,12 @@ SIGNATURES = {
                                           c_stream]),
     "b200r_global_avgpool_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                             c_stream]),
+    "b200r_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
+    "b200r_dilate2_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_maxpool3x3s2_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                              C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_global_avgpool_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_stem_col2im_f32": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, c_host_f3, c_stream]),
 }
 
 

@@ -2,8 +2,9 @@
 RobustART/noise/utils/adv/attack.py:20-42, same update rules as foolbox 3.3.1 (third-party, pinned in
 the reference's requirements.txt:13) and the vendored MI-FGSM (Attacks/imfgsm_attack.py:62-93).
 
-The model is whatever the caller passes (the reference hands in arbitrary nn.Modules); its forward
-and input-gradient run through torch.autograd.  Everything around it -- random start, softmax-CE
+The model is whatever the caller passes.  A `NativeModel` (a robustart_b200.nets network) runs forward AND
+input gradient on the sm_100a kernels; an arbitrary nn.Module (the reference hands those in) goes through
+torch.autograd.  Everything around it -- random start, softmax-CE
 gradient, sign/normalise/step/project/clip, (de)normalisation -- is one fused sm_100a kernel each
 (robustart_b200/csrc/attack_steps.cu, loss_metrics.cu).  Unlike eagerpy's loss.backward() only the
 input gradient is requested, so no weight gradients are computed.
@@ -54,6 +55,57 @@ class PyTorchModel:
             x = _NormalizeFn.apply(x, self._mean, self._std)
         return self.model(x)
 
+    def forward_vjp(self, x):
+        return _autograd_forward_vjp(self, x)
+
+
+class NativeModel:
+    """A robustart_b200.nets model as the SOURCE model of an attack: forward and input gradient both run on the
+    sm_100a kernels (nets.ResNet.forward_saved / input_grad) -- no autograd graph, no weight gradients.  Takes
+    [0,1] float32 NCHW like a foolbox model with ImageNet preprocessing (Normalize is fused into the stem), so it
+    can be handed to every attack in this package, including the ones whose reference signature expects a raw
+    nn.Module on normalised input (mim_linf, autoattack_linf)."""
+
+    bounds = (0, 1)
+
+    def __init__(self, net, passes_bwd: Optional[int] = None):
+        if not hasattr(net, "forward_saved"):
+            raise NotImplementedError("%s has no native input-gradient pass yet (ResNet family only)" % type(net).__name__)
+        self.net, self.passes_bwd = net, passes_bwd
+
+    def __call__(self, x):
+        return self.net.forward(x.contiguous())
+
+    def forward_vjp(self, x):
+        logits, saved = self.net.forward_saved(x.detach().contiguous())
+        return logits, lambda d: self.net.input_grad(d.float().contiguous(), saved, self.passes_bwd)
+
+
+def _autograd_forward_vjp(f_model, x):
+    x = x.detach().requires_grad_(True)
+    with torch.enable_grad():
+        logits = f_model(x)
+    if hasattr(logits, "raw"):  # eagerpy tensor from a real foolbox model
+        logits = logits.raw
+
+    def vjp(d):
+        (g,) = torch.autograd.grad(logits, x, grad_outputs=d.to(logits.dtype))
+        return g.contiguous()
+    return logits.detach().float().contiguous(), vjp
+
+
+def forward_vjp(f_model, x):
+    """(logits, fn: dlogits -> dx) for any model object the attacks accept."""
+    fn = getattr(f_model, "forward_vjp", None)
+    return fn(x) if fn is not None else _autograd_forward_vjp(f_model, x)
+
+
+def as_f_model(model):
+    """mim / autoattack receive a raw module on NORMALISED input (benchmark_eval_adv.py:201-203)."""
+    if isinstance(model, NativeModel):
+        return model
+    return PyTorchModel(model, preprocessing=dict(mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, axis=-3))
+
 
 def _bounds01(f_model):
     b = getattr(f_model, "bounds", (0, 1))
@@ -64,14 +116,9 @@ def _bounds01(f_model):
 
 def _input_grad(f_model, x, label, grad_scale=1.0):
     """d/dx sum_i CE(f(x)_i, y_i) * grad_scale, using our CE kernel for dL/dlogits."""
-    x = x.detach().requires_grad_(True)
-    with torch.enable_grad():
-        logits = f_model(x)
-    if hasattr(logits, "raw"):  # eagerpy tensor from a real foolbox model
-        logits = logits.raw
-    _, dlogits = ops.ce_loss_grad(logits.detach().float().contiguous(), label, grad_scale)
-    (g,) = torch.autograd.grad(logits, x, grad_outputs=dlogits.to(logits.dtype))
-    return g.contiguous()
+    logits, vjp = forward_vjp(f_model, x)
+    _, dlogits = ops.ce_loss_grad(logits, label, grad_scale)
+    return vjp(dlogits)
 
 
 def _prep(input, label):
@@ -141,7 +188,7 @@ def mim_linf(input, label, model, eps, num_steps, step_size, decay_factor, *, se
     s = next(_call_counter) if seed is None else seed
     x = ops.random_start_linf(x0, float(eps), seed=s, u=start_uniform, clip01=False)
     momentum = torch.zeros_like(x0)
-    f_model = PyTorchModel(model, preprocessing=dict(mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, axis=-3))
+    f_model = as_f_model(model)
     for _ in range(int(num_steps)):
         g = _input_grad(f_model, x, y, grad_scale=1.0 / n)
         ops.mim_step_linf_(x, momentum, g, x0, float(step_size), float(eps), float(decay_factor))

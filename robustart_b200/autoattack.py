@@ -24,7 +24,7 @@ import math
 import torch
 
 from . import _lib, ops
-from .attacks import PyTorchModel
+from .attacks import PyTorchModel, as_f_model, forward_vjp  # noqa: F401
 
 _seed_counter = itertools.count(1)
 
@@ -59,7 +59,7 @@ class _Model:
     """NormalizeModel (autoattack.py:17-23): inputs in [0,1], normalisation on our kernel, logits float32."""
 
     def __init__(self, model):
-        self.f = PyTorchModel(model, preprocessing=dict(mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, axis=-3))
+        self.f = as_f_model(model)
         self.forwards = 0
         self.backwards = 0
 
@@ -72,10 +72,7 @@ class _Model:
         """returns (logits, per-sample loss, d(sum loss)/dx)"""
         self.forwards += x.shape[0]
         self.backwards += x.shape[0]
-        x = x.detach().contiguous().requires_grad_(True)
-        with torch.enable_grad():
-            logits = self.f(x)
-        lg = logits.detach().float().contiguous()
+        lg, vjp = forward_vjp(self.f, x.detach().contiguous())
         if loss_kind == "ce":
             loss, d = ops.ce_loss_grad(lg, y)
         elif loss_kind == "dlr":
@@ -90,8 +87,7 @@ class _Model:
             d[u, target] = 1.0
         else:
             raise ValueError(loss_kind)
-        (g,) = torch.autograd.grad(logits, x, grad_outputs=d.to(logits.dtype))
-        return lg, loss, g.contiguous()
+        return lg, loss, vjp(d)
 
 
 # ------------------------------------------------------------------------------------------------

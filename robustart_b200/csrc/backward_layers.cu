@@ -1,0 +1,297 @@
+// Memory-bound pieces of the INPUT-gradient pass (attack loops need d loss / d image only, never weight
+// gradients: autopgd_base.py:371-376, foolbox gradient_descent_base.py value_and_grad).  All tensors are
+// split-bf16 planes, NHWC, like the forward layers (layers.cu).  The contractions of the backward pass are the
+// forward GEMM kernel run on transposed / flipped weights (gemm_sm100.cu); what is left is:
+//   relu_bwd      out = (act > 0 ? dy : 0) [+ add]           ReLU backward, optionally joining a second branch
+//   dilate2       y[n,2i,2j,:] = x[n,i,j,:], zeros elsewhere  turns a stride-2 conv's dgrad into a stride-1 conv
+//   maxpool_bwd   MaxPool2d(3,2,1) backward with PyTorch's first-maximum tie rule
+//   avgpool_bwd   AdaptiveAvgPool2d(1) backward
+//   stem_col2im   im2col^T of the 7x7/s2 stem + the 1/std of Normalize -> float32 NCHW image gradient
+#include "common.cuh"
+
+namespace {
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint32_t pack2(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }
+__device__ __forceinline__ float plane_val(uint32_t hw, uint32_t lw, int odd) {
+  return bf16_bits_to_f32((uint16_t)(hw >> (16 * odd))) + bf16_bits_to_f32((uint16_t)(lw >> (16 * odd)));
+}
+
+inline unsigned grid_for(size_t items) {
+  size_t b = (items + kThreads - 1) / kThreads;
+  size_t cap = (size_t)b200r_num_sms() * 16;
+  return (unsigned)(b < cap ? (b ? b : 1) : cap);
+}
+
+// ---- ReLU backward, 8 elements per thread ---------------------------------------------------------
+template <bool ADD>
+__global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const uint4* __restrict__ dyh, const uint4* __restrict__ dyl,
+                                                             const uint4* __restrict__ acth, const uint4* __restrict__ addh,
+                                                             const uint4* __restrict__ addl, uint4* __restrict__ oh,
+                                                             uint4* __restrict__ ol, size_t count8) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < count8; i += (size_t)gridDim.x * kThreads) {
+    const uint4 a = __ldg(acth + i), gh = __ldg(dyh + i), gl = __ldg(dyl + i);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, hw[4] = {gh.x, gh.y, gh.z, gh.w}, lw[4] = {gl.x, gl.y, gl.z, gl.w};
+    uint32_t rh[4], rl[4];
+    if (!ADD) {
+      // pure masking keeps the planes bit-exact: a positive activation has a positive hi plane (bf16 rounding
+      // keeps the sign; 0x0000 / 0x8000 / negative patterns are "not > 0")
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t m0 = ((aw[j] & 0xFFFFu) != 0 && !(aw[j] & 0x8000u)) ? 0x0000FFFFu : 0u;
+        const uint32_t m1 = ((aw[j] >> 16) != 0 && !(aw[j] & 0x80000000u)) ? 0xFFFF0000u : 0u;
+        rh[j] = hw[j] & (m0 | m1);
+        rl[j] = lw[j] & (m0 | m1);
+      }
+    } else {
+      const uint4 bh = __ldg(addh + i), bl = __ldg(addl + i);
+      const uint32_t bhw[4] = {bh.x, bh.y, bh.z, bh.w}, blw[4] = {bl.x, bl.y, bl.z, bl.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint16_t h2[2], l2[2];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const uint16_t ab = (uint16_t)(aw[j] >> (16 * o));
+          const bool pos = ab != 0 && !(ab & 0x8000u);
+          const float v = (pos ? plane_val(hw[j], lw[j], o) : 0.f) + plane_val(bhw[j], blw[j], o);
+          split_bf16(v, h2[o], l2[o]);
+        }
+        rh[j] = pack2(h2[0], h2[1]);
+        rl[j] = pack2(l2[0], l2[1]);
+      }
+    }
+    oh[i] = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+    ol[i] = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+  }
+}
+
+// ---- zero insertion: y[n, 2i, 2j, :] = x[n, i, j, :] ----------------------------------------------
+__global__ void __launch_bounds__(kThreads) dilate2_kernel(const uint4* __restrict__ xh, const uint4* __restrict__ xl,
+                                                            uint4* __restrict__ yh, uint4* __restrict__ yl, int n, int h, int w,
+                                                            int c8) {
+  const size_t total = (size_t)n * (2 * h) * (2 * w) * c8;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int cc = (int)(t % c8);
+    const size_t pix = t / c8;
+    const int q = (int)(pix % (2 * w)), p = (int)((pix / (2 * w)) % (2 * h)), im = (int)(pix / ((size_t)4 * w * h));
+    uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
+    if (!((p | q) & 1)) {
+      const size_t src = (((size_t)im * h + (p >> 1)) * w + (q >> 1)) * c8 + cc;
+      vh = __ldg(xh + src);
+      vl = __ldg(xl + src);
+    }
+    yh[t] = vh;
+    yl[t] = vl;
+  }
+}
+
+// ---- MaxPool2d(3, 2, 1) backward --------------------------------------------------------------------
+// pass 1: per output window, the position (ky*3+kx) of the first maximum, as the forward kernel picks it
+__global__ void __launch_bounds__(kThreads) maxpool_argmax_kernel(const uint4* __restrict__ xh, const uint4* __restrict__ xl,
+                                                                   uint2* __restrict__ idx, int n, int h, int w, int c8, int ho,
+                                                                   int wo) {
+  const size_t total = (size_t)n * ho * wo * c8;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int cc = (int)(t % c8);
+    const size_t pix = t / c8;
+    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), im = (int)(pix / ((size_t)wo * ho));
+    float best[8];
+    uint32_t bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0xFu; }
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= h) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= w) continue;
+        const size_t s = (((size_t)im * h + iy) * w + ix) * c8 + cc;
+        const uint4 a = __ldg(xh + s), b = __ldg(xl + s);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = plane_val(aw[j >> 1], bw[j >> 1], j & 1);
+          if (v > best[j]) { best[j] = v; bi[j] = (uint32_t)(ky * 3 + kx); }
+        }
+      }
+    }
+    idx[t] = make_uint2(bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24), bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24));
+  }
+}
+// pass 2: per input position, the sum of dy over the (at most four) windows whose maximum it is
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint2* __restrict__ idx, const uint4* __restrict__ dyh,
+                                                                const uint4* __restrict__ dyl, uint4* __restrict__ dxh,
+                                                                uint4* __restrict__ dxl, int n, int h, int w, int c8, int ho, int wo) {
+  const size_t total = (size_t)n * h * w * c8;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int cc = (int)(t % c8);
+    const size_t pix = t / c8;
+    const int q = (int)(pix % w), p = (int)((pix / w) % h), im = (int)(pix / ((size_t)w * h));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool any = false;
+    for (int oy = p >> 1; oy <= ((p + 1) >> 1); ++oy) {        // windows with 2*oy - 1 <= p <= 2*oy + 1
+      if (oy >= ho) continue;
+      const int ky = p - (2 * oy - 1);
+      for (int ox = q >> 1; ox <= ((q + 1) >> 1); ++ox) {
+        if (ox >= wo) continue;
+        const int kx = q - (2 * ox - 1);
+        const uint32_t code = (uint32_t)(ky * 3 + kx);
+        const size_t o = (((size_t)im * ho + oy) * wo + ox) * c8 + cc;
+        const uint2 id = __ldg(idx + o);
+        const uint32_t m0 = id.x ^ (code * 0x01010101u), m1 = id.y ^ (code * 0x01010101u);
+        // any byte of m0 / m1 equal to zero = this position is the argmax of that channel
+        if (!(((m0 - 0x01010101u) & ~m0 & 0x80808080u) | ((m1 - 0x01010101u) & ~m1 & 0x80808080u))) continue;
+        const uint4 gh = __ldg(dyh + o), gl = __ldg(dyl + o);
+        const uint32_t hw[4] = {gh.x, gh.y, gh.z, gh.w}, lw[4] = {gl.x, gl.y, gl.z, gl.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t b = ((j < 4 ? id.x : id.y) >> (8 * (j & 3))) & 0xFFu;
+          if (b == code) { acc[j] += plane_val(hw[j >> 1], lw[j >> 1], j & 1); any = true; }
+        }
+      }
+    }
+    uint32_t rh[4] = {0, 0, 0, 0}, rl[4] = {0, 0, 0, 0};
+    if (any) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint16_t h0, l0, h1, l1;
+        split_bf16(acc[2 * j], h0, l0);
+        split_bf16(acc[2 * j + 1], h1, l1);
+        rh[j] = pack2(h0, h1);
+        rl[j] = pack2(l0, l1);
+      }
+    }
+    dxh[t] = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+    dxl[t] = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+  }
+}
+
+// ---- global average pool backward: dx[n, p, c] = dy[n, c] / hw ----------------------------------------
+__global__ void __launch_bounds__(kThreads) avgpool_bwd_kernel(const uint4* __restrict__ dyh, const uint4* __restrict__ dyl,
+                                                                uint4* __restrict__ dxh, uint4* __restrict__ dxl, int n, int hw,
+                                                                int c8) {
+  const size_t total = (size_t)n * hw * c8;
+  const float inv = 1.0f / (float)hw;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int cc = (int)(t % c8);
+    const int im = (int)(t / ((size_t)hw * c8));
+    const uint4 gh = __ldg(dyh + (size_t)im * c8 + cc), gl = __ldg(dyl + (size_t)im * c8 + cc);
+    const uint32_t hwd[4] = {gh.x, gh.y, gh.z, gh.w}, lwd[4] = {gl.x, gl.y, gl.z, gl.w};
+    uint32_t rh[4], rl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint16_t h0, l0, h1, l1;
+      split_bf16(plane_val(hwd[j], lwd[j], 0) * inv, h0, l0);
+      split_bf16(plane_val(hwd[j], lwd[j], 1) * inv, h1, l1);
+      rh[j] = pack2(h0, h1);
+      rl[j] = pack2(l0, l1);
+    }
+    dxh[t] = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+    dxl[t] = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+  }
+}
+
+// ---- stem col2im: dcols [n*ho*wo, 192] (column = ky*24 + kx*3 + c) -> float32 NCHW image gradient -----------
+struct Inv3 { float v[3]; };
+constexpr int kStemK = 192;
+__global__ void __launch_bounds__(kThreads) stem_col2im_kernel(const uint16_t* __restrict__ ch, const uint16_t* __restrict__ cl,
+                                                                float* __restrict__ dx, int n, int h, int w, int ho, int wo,
+                                                                Inv3 inv_std) {
+  const size_t total = (size_t)n * h * w;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int ix = (int)(t % w), iy = (int)((t / w) % h), im = (int)(t / ((size_t)w * h));
+    float acc[3] = {0.f, 0.f, 0.f};
+    // iy = 2*oy - 3 + ky  ->  ky has the parity of iy + 3
+    for (int ky = (iy + 1) & 1; ky < 7; ky += 2) {
+      const int oy = (iy + 3 - ky) >> 1;
+      if (oy < 0 || oy >= ho) continue;
+      for (int kx = (ix + 1) & 1; kx < 7; kx += 2) {
+        const int ox = (ix + 3 - kx) >> 1;
+        if (ox < 0 || ox >= wo) continue;
+        const size_t base = (((size_t)im * ho + oy) * wo + ox) * kStemK + ky * 24 + kx * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += bf16_bits_to_f32(__ldg(ch + base + c)) + bf16_bits_to_f32(__ldg(cl + base + c));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dx[(((size_t)im * 3 + c) * h + iy) * w + ix] = acc[c] * inv_std.v[c];
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int b200r_relu_bwd(const uint16_t* dy, const uint16_t* act, const uint16_t* add, uint16_t* out, size_t count,
+                   b200r_stream_t stream) {
+  B200R_CHECK_ARG(dy && act && out, "null pointer");
+  B200R_CHECK_ARG(count % 8 == 0, "count must be a multiple of 8");
+  if (!count) return B200R_OK;
+  const size_t c8 = count / 8;
+  cudaStream_t s = as_stream(stream);
+  const uint4 *dh = reinterpret_cast<const uint4*>(dy), *dl = reinterpret_cast<const uint4*>(dy + count);
+  const uint4* ah = reinterpret_cast<const uint4*>(act);
+  uint4 *oh = reinterpret_cast<uint4*>(out), *ol = reinterpret_cast<uint4*>(out + count);
+  if (add)
+    relu_bwd_kernel<true><<<grid_for(c8), kThreads, 0, s>>>(dh, dl, ah, reinterpret_cast<const uint4*>(add),
+                                                           reinterpret_cast<const uint4*>(add + count), oh, ol, c8);
+  else
+    relu_bwd_kernel<false><<<grid_for(c8), kThreads, 0, s>>>(dh, dl, ah, nullptr, nullptr, oh, ol, c8);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_dilate2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int c, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && y, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "c must be a multiple of 8");
+  const size_t xin = (size_t)n * h * w * c, yout = xin * 4;
+  dilate2_kernel<<<grid_for(yout / 8), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + xin), reinterpret_cast<uint4*>(y),
+      reinterpret_cast<uint4*>(y + yout), n, h, w, c / 8);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_maxpool3x3s2_bwd_nhwc(const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* workspace, size_t ws_bytes, int n,
+                                int h, int w, int c, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && dy && dx && workspace, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c % 8 == 0, "c must be a multiple of 8");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const size_t xin = (size_t)n * h * w * c, yout = (size_t)n * ho * wo * c;
+  B200R_CHECK_ARG(ws_bytes >= yout, "workspace too small: need %zu bytes (one per pooled element)", yout);
+  B200R_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "workspace must be 8-byte aligned");
+  cudaStream_t s = as_stream(stream);
+  uint2* idx = reinterpret_cast<uint2*>(workspace);
+  maxpool_argmax_kernel<<<grid_for(yout / 8), kThreads, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + xin),
+                                                               idx, n, h, w, c / 8, ho, wo);
+  B200R_LAUNCH_CHECK();
+  maxpool_bwd_kernel<<<grid_for(xin / 8), kThreads, 0, s>>>(idx, reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(dy + yout),
+                                                           reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dx + xin), n, h, w, c / 8,
+                                                           ho, wo);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_global_avgpool_bwd_nhwc(const uint16_t* dy, uint16_t* dx, int n, int hw, int c, b200r_stream_t stream) {
+  B200R_CHECK_ARG(dy && dx, "null pointer");
+  B200R_CHECK_ARG(n > 0 && hw > 0 && c % 8 == 0, "c must be a multiple of 8");
+  const size_t yin = (size_t)n * c, xout = yin * hw;
+  avgpool_bwd_kernel<<<grid_for(xout / 8), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(dy + yin), reinterpret_cast<uint4*>(dx),
+      reinterpret_cast<uint4*>(dx + xout), n, hw, c / 8);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_stem_col2im_f32(const uint16_t* dcols, float* dx, int n, int h, int w, const float* std_host, b200r_stream_t stream) {
+  B200R_CHECK_ARG(dcols && dx && std_host, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "bad shape");
+  const int ho = h / 2, wo = w / 2;
+  const size_t rows = (size_t)n * ho * wo;
+  Inv3 inv;
+  for (int i = 0; i < 3; ++i) inv.v[i] = 1.0f / std_host[i];
+  stem_col2im_kernel<<<grid_for((size_t)n * h * w), kThreads, 0, as_stream(stream)>>>(dcols, dcols + rows * kStemK, dx, n, h, w, ho, wo, inv);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+}  // extern "C"

@@ -124,6 +124,25 @@ class _ConvBN:
         w = (w.double() * scale.view(-1, 1, 1, 1)).float()
         self.w = ops.split_f32(w.permute(0, 2, 3, 1).contiguous().to(device))
         self.stride, self.pad = stride, pad
+        self.k = w.shape[-1]
+        self._w_folded, self._w_dgrad, self._device = w, None, device
+
+    def dgrad(self, dy, res=None, passes=3):
+        """Input gradient of the convolution: dy planes [2,n,ho,wo,cout] -> planes [2,n,h,w,cin] (+ res).
+        conv^T = stride-1 convolution of the (zero-dilated, for stride 2) output gradient with the weights
+        transposed in (cout, cin) and flipped in (ky, kx); padding k-1-pad."""
+        if self._w_dgrad is None:
+            wt = self._w_folded.flip(2, 3).permute(1, 2, 3, 0).contiguous()       # [cin, ky', kx', cout]
+            self._w_dgrad = ops.split_f32(wt.to(self._device))
+        if self.stride not in (1, 2):
+            raise NotImplementedError("dgrad for stride %d" % self.stride)
+        if self.stride == 2 and self.k == 1:
+            # 1x1/s2 (downsample branch): contract on the small map, then zero-insert
+            assert res is None
+            return ops.dilate2(ops.conv2d_nhwc(dy, self._w_dgrad, passes=passes))
+        if self.stride == 2:
+            dy = ops.dilate2(dy)
+        return ops.conv2d_nhwc(dy, self._w_dgrad, None, None, res, stride=1, pad=self.k - 1 - self.pad, passes=passes)
 
     def __call__(self, x, act=None, res=None, passes=3):
         return ops.conv2d_nhwc(x, self.w, self.scale, self.bias, res, stride=self.stride, pad=self.pad, act=act,
@@ -195,6 +214,75 @@ class ResNet:
         return logits
 
     __call__ = forward
+
+    # -- forward that keeps what the input-gradient pass needs, and that pass ------------------------------
+    def forward_saved(self, x01: torch.Tensor):
+        """float32 NCHW [0,1] images -> (logits, saved activations).  Same launch sequence as forward()."""
+        n, _, h, w = x01.shape
+        P = self.passes
+        cols = ops.stem_im2col(x01)
+        s0 = ops.linear(cols, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P).view(2, n, h // 2, w // 2, 64)
+        del cols
+        x = ops.maxpool3x3s2(s0)
+        saved = {"shape": (n, h, w), "stem": s0, "blocks": []}
+        for blk in self.blocks:
+            idn = blk["down"](x, passes=P) if "down" in blk else x
+            if blk["kind"] == "bottleneck":
+                a1 = blk["c1"](x, act="relu", passes=P)
+                a2 = blk["c2"](a1, act="relu", passes=P)
+                y = blk["c3"](a2, act="relu", res=idn, passes=P)
+                saved["blocks"].append((a1, a2, y))
+            else:
+                a1 = blk["c1"](x, act="relu", passes=P)
+                y = blk["c2"](a1, act="relu", res=idn, passes=P)
+                saved["blocks"].append((a1, y))
+            x = y
+        pooled = ops.global_avgpool(x)
+        logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
+        ops.linear(pooled, self.fc_w, None, self.fc_b, passes=P, out_f32=logits, want_planes=False)
+        return logits, saved
+
+    @staticmethod
+    def block_backward(blk, sv, g, P=3):
+        """Gradient w.r.t. a residual block's input from the gradient w.r.t. its (post-ReLU) output.
+        sv = the block's saved activations (a1[, a2], y), all post-ReLU (resnet_official.py:40-140)."""
+        y = sv[-1]
+        dz = ops.relu_bwd(g, y)
+        # identity path: the 1x1 downsample's dgrad (stride 2: contract on the small map, then zero-insert) or dz itself
+        r = blk["down"].dgrad(dz, passes=P) if "down" in blk else dz
+        if blk["kind"] == "bottleneck":
+            a1, a2, _ = sv
+            t = ops.relu_bwd(blk["c3"].dgrad(dz, passes=P), a2)
+            t = ops.relu_bwd(blk["c2"].dgrad(t, passes=P), a1)
+        else:
+            a1, _ = sv
+            t = ops.relu_bwd(blk["c2"].dgrad(dz, passes=P), a1)
+        return blk["c1"].dgrad(t, res=r, passes=P)
+
+    def input_grad(self, dlogits: torch.Tensor, saved, passes: Optional[int] = None) -> torch.Tensor:
+        """d loss / d x01 (float32 NCHW) from d loss / d logits (float32 [n, classes]) and forward_saved()'s state.
+        Only input gradients are formed (what value_and_grad / autograd.grad(loss, x) return to the attacks)."""
+        P = self.passes if passes is None else passes
+        n, h, w = saved["shape"]
+        if not hasattr(self, "_fc_wt"):
+            self._fc_wt = ops.split_f32(ops.merge_f32(self.fc_w).t().contiguous())          # [2048|512, classes]
+            wt = ops.merge_f32(self.stem_w) * self.stem_scale.view(-1, 1)                    # BN scale folded, [64, 192]
+            self._stem_wt = ops.split_f32(wt.t().contiguous())                               # [192, 64]
+        g = ops.linear(ops.split_f32(dlogits.contiguous()), self._fc_wt, passes=P)           # [2, n, c]
+        last = saved["blocks"][-1][-1]
+        g = ops.global_avgpool_bwd(g, last.shape[2], last.shape[3])
+        for blk, sv in zip(reversed(self.blocks), reversed(saved["blocks"])):
+            g = self.block_backward(blk, sv, g, P)
+        s0 = saved["stem"]
+        g = ops.relu_bwd(ops.maxpool3x3s2_bwd(s0, g), s0)
+        dcols = ops.linear(g.view(2, -1, 64), self._stem_wt, passes=P)                       # [2, n*ho*wo, 192]
+        return ops.stem_col2im(dcols, n, h, w)
+
+    def loss_and_input_grad(self, x01: torch.Tensor, labels: torch.Tensor, reduction: str = "sum"):
+        """(per-sample CE losses, d CE / d x01): the one call an attack step makes."""
+        logits, saved = self.forward_saved(x01)
+        loss, dlogits = ops.ce_loss_grad(logits, labels, 1.0 if reduction == "sum" else 1.0 / x01.shape[0])
+        return loss, self.input_grad(dlogits, saved), logits
 
     # -- CUDA-graph replay for a fixed input shape -----------------------------------------------
     def graphed(self, example: torch.Tensor):

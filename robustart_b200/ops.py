@@ -337,6 +337,56 @@ def global_avgpool(x, out=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# input-gradient pass (split planes in, split planes out)
+# ------------------------------------------------------------------------------------------------
+def relu_bwd(dy, act, add=None, out=None):
+    """(act > 0 ? dy : 0) + add on split planes of any shape [2, ...]."""
+    assert dy.shape == act.shape and (add is None or add.shape == dy.shape)
+    count = dy[0].numel()
+    if out is None:
+        out = torch.empty_like(dy)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().b200r_relu_bwd(dy.data_ptr(), act.data_ptr(), _ptr(add), out.data_ptr(), count, _stream()))
+    return out
+
+
+def dilate2(x):
+    _, n, h, w, c = x.shape
+    out = torch.empty((2, n, 2 * h, 2 * w, c), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_dilate2_nhwc(x.data_ptr(), out.data_ptr(), n, h, w, c, _stream()))
+    return out
+
+
+def maxpool3x3s2_bwd(x, dy):
+    """x: the pool's forward input planes [2,n,h,w,c]; dy planes [2,n,ho,wo,c] -> dx planes like x."""
+    _, n, h, w, c = x.shape
+    ws = torch.empty(dy[0].numel(), dtype=torch.uint8, device=x.device)
+    dx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_maxpool3x3s2_bwd_nhwc(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                           n, h, w, c, _stream()))
+    return dx
+
+
+def global_avgpool_bwd(dy, h, w):
+    _, n, c = dy.shape
+    dx = torch.empty((2, n, h, w, c), dtype=torch.int16, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().b200r_global_avgpool_bwd_nhwc(dy.data_ptr(), dx.data_ptr(), n, h * w, c, _stream()))
+    return dx
+
+
+def stem_col2im(dcols, n, h, w, std=IMAGENET_STD, out=None):
+    """dcols planes [2, n*(h/2)*(w/2), 192] -> float32 NCHW gradient w.r.t. the [0,1] image."""
+    if out is None:
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=dcols.device)
+    with torch.cuda.device(dcols.device):
+        _lib.check(_lib.load().b200r_stem_col2im_f32(dcols.data_ptr(), out.data_ptr(), n, h, w, _lib.f3(std), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # token-model layers (ViT / MLP-Mixer)
 # ------------------------------------------------------------------------------------------------
 def layernorm(x, gamma, beta, eps=1e-5, out=None):

@@ -151,9 +151,18 @@ def build_b200_model(model_cfg, ckpt_path, device):
     return nets.build_model(mtype, sd, device=device)
 
 
+def build_source_model(model_cfg, ckpt_path, device):
+    """The SOURCE model of an attack (needs input gradients): ResNets run forward + dgrad on the B200 kernels
+    (attacks.NativeModel); set B200R_SOURCE_AUTOGRAD=1 to get the torch.autograd twin instead."""
+    from .attacks import NativeModel
+    arch = nets.ARCH_ALIASES.get(model_cfg["type"], model_cfg["type"])
+    if arch in nets._RESNET_CFG and os.environ.get("B200R_SOURCE_AUTOGRAD", "0") != "1":
+        return NativeModel(build_b200_model(model_cfg, ckpt_path, device))
+    return build_torch_model(model_cfg, ckpt_path, device)
+
+
 def build_torch_model(model_cfg, ckpt_path, device):
-    """An autograd-capable module for the SOURCE model of an attack (input gradients); the forward/backward of
-    arbitrary source models stays on PyTorch until the dgrad kernels land."""
+    """An autograd-capable nn.Module twin (ResNet family) for the source model of an attack."""
     from . import torch_models
     arch = nets.ARCH_ALIASES.get(model_cfg["type"], model_cfg["type"])
     if arch not in torch_models._CFG:
@@ -217,14 +226,15 @@ class EvalSolver:
     # benchmark_eval_adv.py:191-254
     def evaluate_adv(self, model_src, model_tgt, attack="none", eps=0.0):
         from RobustART.noise import AddNoise
-        from .attacks import PyTorchModel
+        from .attacks import NativeModel, PyTorchModel
         counters = torch.zeros(3, dtype=torch.int64, device=self.device)
         gen = None
         if attack in ("autoattack_linf", "mim_linf", "pgd_l1"):
             gen = AddNoise(attack)
             gen.set_config(model=model_src, eps=eps)
         elif attack != "none":
-            f_model = PyTorchModel(model_src, bounds=(0, 1), preprocessing=dict(mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, axis=-3))
+            f_model = model_src if isinstance(model_src, NativeModel) else PyTorchModel(
+                model_src, bounds=(0, 1), preprocessing=dict(mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, axis=-3))
             gen = AddNoise(attack)
             gen.set_config(f_model=f_model, eps=eps)
         for imgs, labels in self._batches():

@@ -228,6 +228,17 @@ int b200r_global_avgpool_nhwc(const uint16_t* x, uint16_t* y, int n, int hw, int
  * b200r_linear on transposed (and for 3x3: spatially flipped) weights; a stride-2 convolution's dgrad is
  * dilate2 followed by the stride-1 convolution.  Everything stays in split planes.
  * ------------------------------------------------------------------------------------------ */
+/* Input gradient of a stride-1 convolution with the ReLU backward of the layer below fused into the epilogue:
+ *   dx = [mask > 0] * ( conv(dy, wgt_t) + res )
+ *   dy    : split planes [n, h, w, cdy]          (gradient w.r.t. the convolution's output; zero-dilated for stride 2)
+ *   wgt_t : split planes [cdx, kh, kw, cdy]      = forward weight [cdy, kh, kw, cdx] transposed and flipped in (kh, kw)
+ *   res   : split planes [n, h, w, cdx], nullable (the gradient arriving over the block's identity path)
+ *   mask  : the HI plane of the post-ReLU activation the gradient flows into, [n, h, w, cdx] bf16, nullable
+ *   pad   : (k-1)/2 (the forward convolutions on this path are 'same'-padded)
+ * Same kernel, tiling and passes as b200r_conv2d_nhwc. */
+int b200r_conv2d_dgrad_nhwc(const uint16_t* dy, const uint16_t* wgt_t, const uint16_t* res,
+                            const uint16_t* mask, uint16_t* dx, int n, int h, int w, int cdy, int cdx,
+                            int kh, int kw, int pad, int passes, b200r_stream_t stream);
 /* ReLU backward: out = (act > 0 ? dy : 0) + add; add may be NULL (a second gradient branch joining here,
  * e.g. the identity path of a residual block).  count = elements per plane, multiple of 8. */
 int b200r_relu_bwd(const uint16_t* dy, const uint16_t* act, const uint16_t* add, uint16_t* out,

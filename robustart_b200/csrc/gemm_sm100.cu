@@ -195,6 +195,7 @@ struct GemmParams {
   const float* bias;
   const uint16_t* res_hi;
   const uint16_t* res_lo;
+  const uint16_t* mask_hi;            // dgrad: output zeroed where this activation plane (hi) is not > 0 (fused ReLU backward)
   uint16_t* y_hi;
   uint16_t* y_lo;
   float* y_f32;
@@ -467,6 +468,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 32; ++j)   // compile-time j: the arrays must stay in registers
               if (col0 + j < p.Cout) f[j] += bf16_bits_to_f32(p.res_hi[off + j]) + bf16_bits_to_f32(p.res_lo[off + j]);
+          }
+        }
+        if (p.mask_hi && row_ok) {                        // ReLU backward fused into the dgrad GEMM: one bf16 plane read
+          if (full && (p.Cout % 16 == 0)) {
+            uint32_t mw[16];
+            ld_global_v8(p.mask_hi + off, mw);
+            ld_global_v8(p.mask_hi + off + 16, mw + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t a0 = mw[j] & 0xFFFFu, a1 = mw[j] >> 16;
+              if (a0 == 0 || (a0 & 0x8000u)) f[2 * j] = 0.f;
+              if (a1 == 0 || (a1 & 0x8000u)) f[2 * j + 1] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Cout) {
+                const uint32_t a = p.mask_hi[off + j];
+                if (a == 0 || (a & 0x8000u)) f[j] = 0.f;
+              }
           }
         }
         if (p.act == B200R_ACT_RELU) {
@@ -798,7 +819,7 @@ void choose_box(int N, int Ho, int Wo, int stride, int& bn, int& bh, int& bw) {
 
 int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias, const uint16_t* res,
               uint16_t* y, float* y_f32, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-              int act, int passes, bool flat2d, cudaStream_t s) {
+              int act, int passes, bool flat2d, cudaStream_t s, const uint16_t* mask = nullptr) {
   B200R_CHECK_ARG(x && wgt && (y || y_f32), "null pointer");
   // K tails (Cin % 64 != 0) ride on TMA out-of-bounds zero fill of the activation's channel dimension
   B200R_CHECK_ARG(Cin % 8 == 0, "cin (%d) must be a multiple of 8 (16-byte TMA strides)", Cin);
@@ -827,6 +848,7 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
   p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.cin_blocks = (Cin + 63) / 64; p.cin = Cin;
   p.passes = passes; p.act = act; p.scale = scale; p.bias = bias;
   p.res_hi = res; p.res_lo = res ? res + ycount : nullptr;
+  p.mask_hi = mask;
   p.y_hi = y; p.y_lo = y ? y + ycount : nullptr; p.y_f32 = y_f32;
 
   GemmMaps m;
@@ -947,6 +969,15 @@ int b200r_conv2d_nhwc(const uint16_t* x, const uint16_t* wgt, const float* scale
   const bool flat = (kh == 1 && kw == 1 && stride == 1 && pad == 0);
   if (flat) return conv_impl(x, wgt, scale, bias, res, y, y_f32, 1, 1, n * h * w, cin, cout, 1, 1, 1, 0, act, passes, true, as_stream(stream));
   return conv_impl(x, wgt, scale, bias, res, y, y_f32, n, h, w, cin, cout, kh, kw, stride, pad, act, passes, false, as_stream(stream));
+}
+
+int b200r_conv2d_dgrad_nhwc(const uint16_t* dy, const uint16_t* wgt_t, const uint16_t* res, const uint16_t* mask, uint16_t* dx,
+                            int n, int h, int w, int cdy, int cdx, int kh, int kw, int pad, int passes, b200r_stream_t stream) {
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && cdy > 0 && cdx > 0 && dx, "bad shape");
+  B200R_CHECK_ARG(h + 2 * pad - kh + 1 == h && w + 2 * pad - kw + 1 == w, "dgrad keeps the spatial size: pad must be (k-1)/2");
+  const bool flat = (kh == 1 && kw == 1 && pad == 0);
+  if (flat) return conv_impl(dy, wgt_t, nullptr, nullptr, res, dx, nullptr, 1, 1, n * h * w, cdy, cdx, 1, 1, 1, 0, B200R_ACT_NONE, passes, true, as_stream(stream), mask);
+  return conv_impl(dy, wgt_t, nullptr, nullptr, res, dx, nullptr, n, h, w, cdy, cdx, kh, kw, 1, pad, B200R_ACT_NONE, passes, false, as_stream(stream), mask);
 }
 
 int b200r_linear(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias, const uint16_t* res,

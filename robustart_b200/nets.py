@@ -127,10 +127,11 @@ class _ConvBN:
         self.k = w.shape[-1]
         self._w_folded, self._w_dgrad, self._device = w, None, device
 
-    def dgrad(self, dy, res=None, passes=3):
-        """Input gradient of the convolution: dy planes [2,n,ho,wo,cout] -> planes [2,n,h,w,cin] (+ res).
+    def dgrad(self, dy, res=None, mask=None, passes=3):
+        """Input gradient of the convolution: dy planes [2,n,ho,wo,cout] -> [mask > 0] * (planes [2,n,h,w,cin] + res).
         conv^T = stride-1 convolution of the (zero-dilated, for stride 2) output gradient with the weights
-        transposed in (cout, cin) and flipped in (ky, kx); padding k-1-pad."""
+        transposed in (cout, cin) and flipped in (ky, kx); padding k-1-pad.  mask = post-ReLU activation the
+        gradient flows into (ReLU backward fused into the GEMM epilogue)."""
         if self._w_dgrad is None:
             wt = self._w_folded.flip(2, 3).permute(1, 2, 3, 0).contiguous()       # [cin, ky', kx', cout]
             self._w_dgrad = ops.split_f32(wt.to(self._device))
@@ -138,11 +139,11 @@ class _ConvBN:
             raise NotImplementedError("dgrad for stride %d" % self.stride)
         if self.stride == 2 and self.k == 1:
             # 1x1/s2 (downsample branch): contract on the small map, then zero-insert
-            assert res is None
-            return ops.dilate2(ops.conv2d_nhwc(dy, self._w_dgrad, passes=passes))
+            assert res is None and mask is None
+            return ops.dilate2(ops.conv2d_dgrad(dy, self._w_dgrad, passes=passes))
         if self.stride == 2:
             dy = ops.dilate2(dy)
-        return ops.conv2d_nhwc(dy, self._w_dgrad, None, None, res, stride=1, pad=self.k - 1 - self.pad, passes=passes)
+        return ops.conv2d_dgrad(dy, self._w_dgrad, res, mask, pad=self.k - 1 - self.pad, passes=passes)
 
     def __call__(self, x, act=None, res=None, passes=3):
         return ops.conv2d_nhwc(x, self.w, self.scale, self.bias, res, stride=self.stride, pad=self.pad, act=act,
@@ -243,21 +244,23 @@ class ResNet:
         return logits, saved
 
     @staticmethod
-    def block_backward(blk, sv, g, P=3):
+    def block_backward(blk, sv, g, P=3, in_mask=None, g_is_masked=False):
         """Gradient w.r.t. a residual block's input from the gradient w.r.t. its (post-ReLU) output.
-        sv = the block's saved activations (a1[, a2], y), all post-ReLU (resnet_official.py:40-140)."""
-        y = sv[-1]
-        dz = ops.relu_bwd(g, y)
+        sv = the block's saved activations (a1[, a2], y), all post-ReLU (resnet_official.py:40-140).  Every ReLU
+        backward is fused into the dgrad GEMM that produces the masked tensor; `in_mask` (the block's input
+        activation = the previous block's output) applies the PREVIOUS block's output ReLU to the result, so the
+        chain needs no stand-alone masking pass (g_is_masked: the caller did that for this block's own output)."""
+        dz = g if g_is_masked else ops.relu_bwd(g, sv[-1])
         # identity path: the 1x1 downsample's dgrad (stride 2: contract on the small map, then zero-insert) or dz itself
         r = blk["down"].dgrad(dz, passes=P) if "down" in blk else dz
         if blk["kind"] == "bottleneck":
             a1, a2, _ = sv
-            t = ops.relu_bwd(blk["c3"].dgrad(dz, passes=P), a2)
-            t = ops.relu_bwd(blk["c2"].dgrad(t, passes=P), a1)
+            t = blk["c3"].dgrad(dz, mask=a2, passes=P)
+            t = blk["c2"].dgrad(t, mask=a1, passes=P)
         else:
             a1, _ = sv
-            t = ops.relu_bwd(blk["c2"].dgrad(dz, passes=P), a1)
-        return blk["c1"].dgrad(t, res=r, passes=P)
+            t = blk["c2"].dgrad(dz, mask=a1, passes=P)
+        return blk["c1"].dgrad(t, res=r, mask=in_mask, passes=P)
 
     def input_grad(self, dlogits: torch.Tensor, saved, passes: Optional[int] = None) -> torch.Tensor:
         """d loss / d x01 (float32 NCHW) from d loss / d logits (float32 [n, classes]) and forward_saved()'s state.
@@ -271,8 +274,10 @@ class ResNet:
         g = ops.linear(ops.split_f32(dlogits.contiguous()), self._fc_wt, passes=P)           # [2, n, c]
         last = saved["blocks"][-1][-1]
         g = ops.global_avgpool_bwd(g, last.shape[2], last.shape[3])
-        for blk, sv in zip(reversed(self.blocks), reversed(saved["blocks"])):
-            g = self.block_backward(blk, sv, g, P)
+        g = ops.relu_bwd(g, last)                        # the last block's output ReLU; all others are fused
+        for i in range(len(self.blocks) - 1, -1, -1):
+            in_mask = saved["blocks"][i - 1][-1] if i > 0 else None     # block input = previous block's output
+            g = self.block_backward(self.blocks[i], saved["blocks"][i], g, P, in_mask=in_mask, g_is_masked=True)
         s0 = saved["stem"]
         g = ops.relu_bwd(ops.maxpool3x3s2_bwd(s0, g), s0)
         dcols = ops.linear(g.view(2, -1, 64), self._stem_wt, passes=P)                       # [2, n*ho*wo, 192]

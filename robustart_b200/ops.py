@@ -339,6 +339,22 @@ def global_avgpool(x, out=None):
 # ------------------------------------------------------------------------------------------------
 # input-gradient pass (split planes in, split planes out)
 # ------------------------------------------------------------------------------------------------
+def conv2d_dgrad(dy, wgt_t, res=None, mask=None, *, pad=0, passes=3):
+    """dx = [mask > 0] * (conv_s1(dy, wgt_t) + res); dy planes [2,n,h,w,cdy], wgt_t planes [2,cdx,kh,kw,cdy], mask = the
+    post-ReLU activation planes the gradient flows into (only its hi plane is read)."""
+    _, n, h, w, cdy = dy.shape
+    cdx, kh, kw = wgt_t.shape[1], wgt_t.shape[2], wgt_t.shape[3]
+    out = torch.empty((2, n, h, w, cdx), dtype=torch.int16, device=dy.device)
+    if mask is not None:
+        assert mask.shape == out.shape, (mask.shape, out.shape)
+    if res is not None:
+        assert res.shape == out.shape, (res.shape, out.shape)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().b200r_conv2d_dgrad_nhwc(dy.data_ptr(), wgt_t.data_ptr(), _ptr(res), _ptr(mask), out.data_ptr(), n, h, w,
+                                                       cdy, cdx, kh, kw, pad, passes, _stream()))
+    return out
+
+
 def relu_bwd(dy, act, add=None, out=None):
     """(act > 0 ? dy : 0) + add on split planes of any shape [2, ...]."""
     assert dy.shape == act.shape and (add is None or add.shape == dy.shape)

@@ -95,6 +95,12 @@ def test_conv_dgrad(cuda, k, stride, cin, cout, hw):
     else:
         got = _nchw(conv.dgrad(_planes(dy.float()), res=_planes(res)))
         assert _rel(got, ref + res.double()) < 3e-5
+        # fused ReLU backward: the result is zeroed wherever the activation it flows into is not positive
+        act = torch.relu(torch.randn(2, cin, hw, hw, device=cuda))
+        got = _nchw(conv.dgrad(_planes(dy.float()), res=_planes(res), mask=_planes(act)))
+        want = (ref + res.double()) * (act > 0)
+        assert _rel(got, want) < 3e-5
+        assert (got[act.expand_as(got) <= 0] == 0).all()
 
 
 @pytest.mark.parametrize("arch,n", [("resnet18", 3), ("resnet50", 2)])

@@ -52,3 +52,44 @@ def test_benchmark_eval_adv_cli(cuda, tmp_path, monkeypatch, attack, eps):
     m = adv.main(["--config", cfg, "--src_name", "resnet18", "--src_path", "", "--tgt_name", "resnet18", "--tgt_path", "",
                   "--attack", attack, "--eps", eps])
     assert m["count"] == 32 and 0 <= m["top1"] <= 100
+
+
+def test_imgnet_c_sweep_cli(cuda, tmp_path, monkeypatch):
+    """imgnet_c_solver: all 19 x 5 cells from one clean shard, robust.json in the reference's schema; each cell's
+    counters equal a stand-alone cls_solver run of that cell (same seed, same image offsets)."""
+    monkeypatch.setenv("SKIP_DIST", "1")
+    monkeypatch.chdir(tmp_path)
+    import prototype.prototype.solver.cls_solver as cls
+    import prototype.prototype.solver.imgnet_c_solver as sweep
+    from RobustART.noise.utils import add_noise_utils as anu
+    cfg = _cfg(tmp_path, n=32, bs=16)
+    anu.reseed(11)
+    res = sweep.main(["--config", cfg, "--evaluate", "--save-detail"])
+    data = res["resnet18_official"]
+    rj = json.load(open(tmp_path / "results" / "robust.json"))
+    assert rj["all"]["all_with_extra"] == pytest.approx(data["all"]["all_with_extra"])
+    assert set(rj) >= {"all", "noise", "blur", "weather", "digital", "extra"}
+    assert len(rj["blur"]) == 4 and len(rj["extra"]) == 4
+    for g in ("noise", "blur", "weather", "digital"):
+        for t, v in rj[g].items():
+            assert 0.0 <= v <= 100.0, (t, v)
+    assert set(rj.get("skipped", {})) <= {"spatter-1", "spatter-2", "spatter-3"}       # water branch: no kernel yet
+    cell = json.load(open(tmp_path / "results" / "digital-contrast-3-metric"))
+    anu.reseed(11)
+    alone = cls.main(["--config", cfg, "--evaluate", "--corruption", "contrast", "--severity", "3"])
+    assert cell == alone
+    assert "done" in open(tmp_path / "status.txt").read()
+
+
+def test_multi_eval_cli(cuda, tmp_path, monkeypatch):
+    monkeypatch.setenv("SKIP_DIST", "1")
+    monkeypatch.chdir(tmp_path)
+    import prototype.prototype.solver.multi_eval_solver as multi
+    cfg_path = _cfg(tmp_path, n=32, bs=16)
+    cfg = yaml.safe_load(open(cfg_path))
+    cfg["eval_list"] = ["resnet18", "no_such_model"]
+    open(cfg_path, "w").write(yaml.safe_dump(cfg))
+    res = multi.main(["--config", cfg_path, "--evaluate", "--ckpt-filePath", str(tmp_path)])
+    assert list(res) == ["resnet18"] and res["resnet18"]["count"] == 32
+    st = open(tmp_path / "status.txt").read()
+    assert "resnet18 done" in st and "Error when load no_such_model" in st

@@ -214,6 +214,12 @@ int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* 
                           uint16_t* y, int n, int h, int w, const float* mean_host,
                           const float* std_host, int act, int passes, b200r_stream_t stream);
 
+/* same, from a float32 NCHW image in [0,1] (the attack loops' iterate): (x - mean) / std and the bf16 split happen
+ * in the operand producer, with the arithmetic of b200r_stem_im2col_f32 */
+int b200r_stem_conv7x7_f32(const float* img, const uint16_t* wgt, const float* scale, const float* bias,
+                           uint16_t* y, int n, int h, int w, const float* mean_host,
+                           const float* std_host, int act, int passes, b200r_stream_t stream);
+
 /* MaxPool2d(3, 2, 1) on split planes NHWC (resnet_official.py:227) */
 int b200r_maxpool3x3s2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int c,
                             b200r_stream_t stream);

@@ -202,7 +202,8 @@ struct GemmParams {
   int res_mma;    // residual added on the tensor core: extra k-blocks R[128 x 64] * I[BN x 64]^T (needs scale == NULL)
   int tma_store;  // planes output leaves through shared memory + cp.async.bulk.tensor stores
   // STEM variant only: the A operand is gathered from the raw uint8 NHWC image by producer warps
-  const uint8_t* img;       // [N, H_in, W_in, 3]
+  const uint8_t* img;       // [N, H_in, W_in, 3] uint8 (STEM_MODE 1)  or  float32 [N, 3, H_in, W_in] (STEM_MODE 2)
+  float nmean[3], nstd[3];  // STEM_MODE 2: Normalize constants (mode 1 has them baked into the LUT)
   const uint32_t* lut;      // [3][256]: normalised value of byte b in channel c as (hi | lo << 16) bf16 pair
   int H_in, W_in, stem_Ho, stem_Wo;
   long long M_total;        // N * Ho * Wo
@@ -227,11 +228,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-template <int BN, bool STEM>
-__global__ void __launch_bounds__(STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, 1)
+// STEM_MODE: 0 = TMA-fed convolution / linear, 1 = fused stem from the uint8 NHWC image, 2 = fused stem from a float32
+// NCHW image in [0,1] (the attack path)
+template <int BN, int STEM_MODE>
+__global__ void __launch_bounds__(STEM_MODE ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_i,
             const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
+  constexpr bool STEM = STEM_MODE != 0;
+  constexpr bool STEM_F32 = STEM_MODE == 2;
   constexpr int kStages = (BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault);
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
@@ -574,62 +579,90 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int q_per_row = row_bytes / 16;                       // 16-byte groups per input row (42 for W = 224)
     uint32_t* s_conv = reinterpret_cast<uint32_t*>(smem + STEM_OFF);
     uint32_t* s_lut = s_conv + 7 * pitch;
-    for (int i = ptid; i < 768; i += kProd) s_lut[i] = __ldg(p.lut + i);
+    if (!STEM_F32)
+      for (int i = ptid; i < 768; i += kProd) s_lut[i] = __ldg(p.lut + i);
     for (int i = ptid; i < 7 * pitch; i += kProd) s_conv[i] = 0u;   // pads stay zero for the whole kernel
     asm volatile("bar.sync 1, 256;" ::: "memory");
 
-    constexpr int kMaxIt = 2;                                    // ceil(7 * q_per_row / 256) for W <= 256
+    // 16-byte load groups per input row: 16 interleaved bytes (uint8 NHWC) or 4 floats of one channel plane (float32 NCHW)
+    const int w4 = p.W_in / 4;
+    const int g_per_row = STEM_F32 ? 3 * w4 : q_per_row;
+    constexpr int kMaxIt = 2;                                    // 2 rows (F32) / 7 rows (uint8) fit in 2 groups per thread
     uint4 v[kMaxIt];
     int dstw[kMaxIt];                                            // staged word offset; -1 = nothing; <= -2 = zero row
-    // issue the loads of input rows [iy0, iy0 + nrows) of image n_img (nrows = 7 at an image start, else 2)
+    // issue the loads of input rows [iy0, iy0 + nrows) of image n_img
     auto fetch_rows = [&](int n_img, int iy0, int nrows) {
-      const uint8_t* img_base = p.img + (long long)n_img * p.H_in * row_bytes;
 #pragma unroll
       for (int it = 0; it < kMaxIt; ++it) {
         const int idx = ptid + it * kProd;
         dstw[it] = -1;
         v[it] = make_uint4(0, 0, 0, 0);
-        if (idx < nrows * q_per_row) {
-          const int k = idx / q_per_row, q = idx - k * q_per_row, iy = iy0 + k;
-          const int d = ((iy + 3 + 7) % 7) * pitch + 9 + q * 16;
-          if (iy >= 0 && iy < p.H_in) { v[it] = __ldg(reinterpret_cast<const uint4*>(img_base + (long long)iy * row_bytes) + q); dstw[it] = d; }
+        if (idx < nrows * g_per_row) {
+          const int k = idx / g_per_row, g = idx - k * g_per_row, iy = iy0 + k;
+          const int slot = ((iy + 3 + 7) % 7) * pitch + 9;
+          int d;
+          const uint4* src;
+          if (STEM_F32) {
+            const int c = g / w4, q = g - c * w4;                 // 4 consecutive pixels of channel c -> words 12q + c (+3 each)
+            d = slot + 12 * q + c;
+            src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.img) +
+                                                 (((long long)n_img * 3 + c) * p.H_in + iy) * p.W_in) + q;
+          } else {
+            d = slot + g * 16;
+            src = reinterpret_cast<const uint4*>(p.img + ((long long)n_img * p.H_in + iy) * row_bytes) + g;
+          }
+          if (iy >= 0 && iy < p.H_in) { v[it] = __ldg(src); dstw[it] = d; }
           else dstw[it] = -d - 2;                                 // out-of-image row: store zeros
         }
       }
     };
-    // bytes -> LUT words into the ring
+    // loaded values -> normalised (hi | lo << 16) words in the ring
     auto stage_rows = [&]() {
 #pragma unroll
       for (int it = 0; it < kMaxIt; ++it) {
         if (dstw[it] == -1) continue;
         const bool zero = dstw[it] < 0;
         const int d0 = zero ? -(dstw[it] + 2) : dstw[it];
-        const uint32_t w4[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-        const int c0 = (d0 - 9 - (d0 / pitch) * pitch) % 3;     // channel of the first byte of this 16-byte group
+        const uint32_t w4v[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+        const int c0 = (d0 - 9 - (d0 / pitch) * pitch) % 3;     // channel of the first element of this group
+        if (STEM_F32) {
+          const float mu = p.nmean[c0], sd = p.nstd[c0];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t b = (w4[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-          const int c = (c0 + j) % 3;
-          s_conv[d0 + j] = zero ? 0u : s_lut[c * 256 + b];
+          for (int j = 0; j < 4; ++j) {
+            uint16_t hh, ll;
+            split_bf16((__uint_as_float(w4v[j]) - mu) / sd, hh, ll);   // same arithmetic as b200r_stem_im2col_f32
+            s_conv[d0 + 3 * j] = zero ? 0u : ((uint32_t)hh | ((uint32_t)ll << 16));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t b = (w4v[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            const int c = (c0 + j) % 3;
+            s_conv[d0 + j] = zero ? 0u : s_lut[c * 256 + b];
+          }
         }
+      }
+    };
+    // all 7 rows of a tile (first tile of the CTA; F32: also the first tile of every image), two rows at a time
+    auto cold_start = [&](int n_img, int oy) {
+      for (int k = 0; k < 7; k += 2) {
+        fetch_rows(n_img, 2 * oy - 3 + k, (7 - k) < 2 ? (7 - k) : 2);
+        stage_rows();
       }
     };
 
     int stage = 0;
     uint32_t phase = 0;
-    if (t_first < t_end) {                                       // cold start: all 7 rows of the first tile
-      const int oy = t_first % p.tiles_h, n_img = t_first / p.tiles_h;
-      fetch_rows(n_img, 2 * oy - 3, 7);
-      stage_rows();
-    }
+    if (t_first < t_end) cold_start(t_first / p.tiles_h, t_first % p.tiles_h);
     asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int t = t_first; t < t_end; ++t) {
       const int oy = t % p.tiles_h, n_img = t / p.tiles_h;
       // prefetch what the next tile adds
       const bool has_next = (t + 1 < t_end);
+      const bool next_same_image = (oy + 1 < p.tiles_h);
       if (has_next) {
-        if (oy + 1 < p.tiles_h) fetch_rows(n_img, 2 * oy + 4, 2);
-        else fetch_rows(n_img + 1, -3, 7);
+        if (next_same_image) fetch_rows(n_img, 2 * oy + 4, 2);
+        else if (!STEM_F32) fetch_rows(n_img + 1, -3, 7);        // 7 uint8 rows still fit the two load slots
       }
       int rowoff[7];
 #pragma unroll
@@ -669,7 +702,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");            // everyone done reading the ring rows this tile retires
-      if (has_next) stage_rows();
+      if (has_next) {
+        if (STEM_F32 && !next_same_image) cold_start(n_img + 1, 0);   // image boundary: once per ~112 tiles
+        else stage_rows();
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   }
@@ -704,7 +740,7 @@ EncodeTiledFn get_encode() {
 
 struct GemmMaps { CUtensorMap a, b, r, i, y; };
 
-template <int BN, bool STEM>
+template <int BN, int STEM>
 int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t s) {
   constexpr int kStages = (BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault);
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * BN * BK * 2;
@@ -871,8 +907,8 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
     int rc = finish_maps(enc, &m, &p, res, y, ycount, BN);
     if (rc) return rc;
   }
-  if (BN == 256) return launch<256, false>(m, p, s);
-  return BN == 64 ? launch<64, false>(m, p, s) : launch<128, false>(m, p, s);
+  if (BN == 256) return launch<256, 0>(m, p, s);
+  return BN == 64 ? launch<64, 0>(m, p, s) : launch<128, 0>(m, p, s);
 }
 
 // ---- fused stem ---------------------------------------------------------------------------------
@@ -921,16 +957,16 @@ int get_stem_lut(const float* mean, const float* stdv, const uint32_t** out) {
 
 extern "C" {
 
-int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* scale, const float* bias, uint16_t* y,
-                          int n, int h, int w, const float* mean_host, const float* std_host, int act, int passes,
-                          b200r_stream_t stream) {
+static int stem_impl(const void* img, bool f32, const uint16_t* wgt, const float* scale, const float* bias, uint16_t* y,
+                     int n, int h, int w, const float* mean_host, const float* std_host, int act, int passes,
+                     b200r_stream_t stream) {
   B200R_CHECK_ARG(img && wgt && y && mean_host && std_host, "null pointer");
   B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "bad shape");
   B200R_CHECK_ARG(passes == 1 || passes == 3, "passes must be 1 or 3");
   EncodeTiledFn enc = get_encode();
   if (!enc) { b200r_set_error("cuTensorMapEncodeTiled not available from the driver"); return B200R_ECUDA; }
   const uint32_t* lut = nullptr;
-  int rc = get_stem_lut(mean_host, std_host, &lut);
+  int rc = f32 ? B200R_OK : get_stem_lut(mean_host, std_host, &lut);   // uint8: ToTensor + Normalize + split as a 3x256 table
   if (rc) return rc;
   const int Ho = h / 2, Wo = w / 2, Cout = 64, K = 192;
   GemmParams p{};
@@ -942,7 +978,8 @@ int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* 
   p.KH = 1; p.KW = 1; p.stride = 1; p.pad = 0; p.cin_blocks = K / 64; p.cin = K;
   p.passes = passes; p.act = act; p.scale = scale; p.bias = bias;
   p.y_hi = y; p.y_lo = y + (size_t)p.M_total * Cout;
-  p.img = img; p.lut = lut; p.H_in = h; p.W_in = w;
+  p.img = static_cast<const uint8_t*>(img); p.lut = lut; p.H_in = h; p.W_in = w;
+  for (int i = 0; i < 3; ++i) { p.nmean[i] = mean_host[i]; p.nstd[i] = std_host[i]; }
   GemmMaps m;
   {
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, 2};
@@ -958,7 +995,19 @@ int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* 
   p.stem_Ho = Ho; p.stem_Wo = Wo;   // the producer decodes (n, oy, ox) from the real output geometry
   rc = finish_maps(enc, &m, &p, nullptr, y, (size_t)p.M_total * Cout, 64);
   if (rc) return rc;
-  return launch<64, true>(m, p, as_stream(stream));
+  return f32 ? launch<64, 2>(m, p, as_stream(stream)) : launch<64, 1>(m, p, as_stream(stream));
+}
+
+int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* scale, const float* bias, uint16_t* y,
+                          int n, int h, int w, const float* mean_host, const float* std_host, int act, int passes,
+                          b200r_stream_t stream) {
+  return stem_impl(img, false, wgt, scale, bias, y, n, h, w, mean_host, std_host, act, passes, stream);
+}
+
+int b200r_stem_conv7x7_f32(const float* img, const uint16_t* wgt, const float* scale, const float* bias, uint16_t* y,
+                           int n, int h, int w, const float* mean_host, const float* std_host, int act, int passes,
+                           b200r_stream_t stream) {
+  return stem_impl(img, true, wgt, scale, bias, y, n, h, w, mean_host, std_host, act, passes, stream);
 }
 
 int b200r_conv2d_nhwc(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias, const uint16_t* res,

@@ -195,9 +195,7 @@ class ResNet:
             # raw pixels: gather + ToTensor + Normalize + split fused into the stem GEMM's operand producer
             x = ops.stem_conv7x7_u8(images, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P)
         else:
-            cols = ops.stem_im2col(images)
-            x = ops.linear(cols, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P)
-            x = x.view(2, n, h // 2, w // 2, 64)
+            x = self._stem_f32(images, P)
         x = ops.maxpool3x3s2(x)
         for blk in self.blocks:
             idn = blk["down"](x, passes=P) if "down" in blk else x
@@ -214,6 +212,15 @@ class ResNet:
         ops.linear(pooled, self.fc_w, None, self.fc_b, passes=P, out_f32=logits, want_planes=False)
         return logits
 
+    def _stem_f32(self, x01, P):
+        """conv1 + bn1 + relu from a float32 NCHW image: fused producer when the geometry allows it (W <= 256, W % 16 == 0),
+        else im2col + GEMM."""
+        n, _, h, w = x01.shape
+        if w <= 256 and w % 16 == 0 and h % 2 == 0:
+            return ops.stem_conv7x7_f32(x01.contiguous(), self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P)
+        cols = ops.stem_im2col(x01)
+        return ops.linear(cols, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P).view(2, n, h // 2, w // 2, 64)
+
     __call__ = forward
 
     # -- forward that keeps what the input-gradient pass needs, and that pass ------------------------------
@@ -221,9 +228,7 @@ class ResNet:
         """float32 NCHW [0,1] images -> (logits, saved activations).  Same launch sequence as forward()."""
         n, _, h, w = x01.shape
         P = self.passes
-        cols = ops.stem_im2col(x01)
-        s0 = ops.linear(cols, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P).view(2, n, h // 2, w // 2, 64)
-        del cols
+        s0 = self._stem_f32(x01, P)
         x = ops.maxpool3x3s2(s0)
         saved = {"shape": (n, h, w), "stem": s0, "blocks": []}
         for blk in self.blocks:

@@ -317,6 +317,18 @@ def stem_conv7x7_u8(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGENE
     return out
 
 
+def stem_conv7x7_f32(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
+    """Fused 7x7/s2 stem from a float32 NCHW image in [0,1] (attack iterates): planes [2, n, h/2, w/2, 64]."""
+    _need_cuda(img, torch.float32, "img")
+    n, _, h, w = img.shape
+    if out is None:
+        out = torch.empty((2, n, h // 2, w // 2, 64), dtype=torch.int16, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.load().b200r_stem_conv7x7_f32(img.data_ptr(), wgt.data_ptr(), _ptr(scale), _ptr(bias), out.data_ptr(),
+                                                      n, h, w, _lib.f3(mean), _lib.f3(std), ACT[act], passes, _stream()))
+    return out
+
+
 def maxpool3x3s2(x, out=None):
     _, n, h, w, c = x.shape
     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1

@@ -3,6 +3,7 @@
 |err| <= 3e-5 * sqrt(K) * rms(a)*rms(b) style bounds via a normalised max error."""
 import pytest
 import torch
+import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
@@ -141,3 +142,22 @@ def test_fused_stem_matches_im2col_path(cuda):
     ref2 = torch.relu(torch.nn.functional.conv2d(ops.u8nhwc_to_f32nchw(img2).double(), w.double(), stride=2, padding=3)
                       * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1))
     assert _rel_err(y2, ref2) < 4e-5
+
+
+def test_fused_stem_f32_matches_conv(cuda):
+    """The float32-NCHW fused stem (attack path) == conv2d on the normalised image == the im2col + GEMM route."""
+    from robustart_b200 import ops
+    torch.manual_seed(1)
+    w = torch.randn(64, 3, 7, 7, device=cuda) * 0.1
+    s = torch.rand(64, device=cuda) + 0.5
+    b = torch.randn(64, device=cuda)
+    wp = ops.split_f32(ops.pack_stem_weight(w))
+    for shape in [(5, 3, 224, 224), (2, 3, 32, 48), (130, 3, 64, 64)]:       # several images per CTA -> image-boundary restarts
+        x = torch.rand(*shape, device=cuda)
+        got = ops.merge_f32(ops.stem_conv7x7_f32(x, wp, s, b, act="relu")).permute(0, 3, 1, 2)
+        ref = F.conv2d(ops.normalize(x).double(), w.double(), stride=2, padding=3)
+        ref = torch.relu(ref * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1))
+        assert _rel_err(got, ref) < 4e-5
+        cols = ops.stem_im2col(x)
+        via = ops.merge_f32(ops.linear(cols, wp, s, b, act="relu")).view(shape[0], shape[2] // 2, shape[3] // 2, 64).permute(0, 3, 1, 2)
+        assert (got - via).abs().max().item() < 1e-5

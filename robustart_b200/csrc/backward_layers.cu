@@ -192,29 +192,44 @@ __global__ void __launch_bounds__(kThreads) avgpool_bwd_kernel(const uint4* __re
 }
 
 // ---- stem col2im: dcols [n*ho*wo, 192] (column = ky*24 + kx*3 + c) -> float32 NCHW image gradient -----------
+// One CTA per (image, input row iy).  Row iy receives from the <= 4 filter rows ky with the parity of iy + 3, i.e. from
+// <= 4 output rows oy; their ky-runs (24 values per output pixel, 48 contiguous bytes per plane) are staged once in
+// shared memory as floats (pitch 25 words: conflict-free for the strided gather), so every dcols element is read
+// from HBM exactly once, in 16-byte pieces.  Each thread then sums the <= 16 taps of one (channel, ix).
 struct Inv3 { float v[3]; };
 constexpr int kStemK = 192;
+constexpr int kRunPitch = 25;
 __global__ void __launch_bounds__(kThreads) stem_col2im_kernel(const uint16_t* __restrict__ ch, const uint16_t* __restrict__ cl,
-                                                                float* __restrict__ dx, int n, int h, int w, int ho, int wo,
-                                                                Inv3 inv_std) {
-  const size_t total = (size_t)n * h * w;
-  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
-    const int ix = (int)(t % w), iy = (int)((t / w) % h), im = (int)(t / ((size_t)w * h));
-    float acc[3] = {0.f, 0.f, 0.f};
-    // iy = 2*oy - 3 + ky  ->  ky has the parity of iy + 3
-    for (int ky = (iy + 1) & 1; ky < 7; ky += 2) {
-      const int oy = (iy + 3 - ky) >> 1;
-      if (oy < 0 || oy >= ho) continue;
+                                                                float* __restrict__ dx, int h, int w, int ho, int wo, Inv3 inv_std) {
+  extern __shared__ float runs[];                                // [4][wo][kRunPitch]
+  const int iy = blockIdx.x % h, im = blockIdx.x / h;
+  const int ky0 = (iy + 1) & 1;                                  // iy = 2*oy - 3 + ky
+  for (int g = threadIdx.x; g < 4 * wo * 3; g += kThreads) {
+    const int kyi = g / (wo * 3), rem = g - kyi * wo * 3, ox = rem / 3, part = rem - ox * 3;
+    const int ky = ky0 + 2 * kyi, oy = (iy + 3 - ky) >> 1;
+    float vals[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ky <= 6 && oy >= 0 && oy < ho) {
+      const size_t base = (((size_t)im * ho + oy) * wo + ox) * kStemK + ky * 24 + part * 8;
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(ch + base)), b = __ldg(reinterpret_cast<const uint4*>(cl + base));
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vals[j] = plane_val(aw[j >> 1], bw[j >> 1], j & 1);
+    }
+    float* dst = runs + (kyi * wo + ox) * kRunPitch + part * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = vals[j];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 3 * w; e += kThreads) {
+    const int c = e / w, ix = e - c * w;
+    float acc = 0.f;
+#pragma unroll
+    for (int kyi = 0; kyi < 4; ++kyi)
       for (int kx = (ix + 1) & 1; kx < 7; kx += 2) {
         const int ox = (ix + 3 - kx) >> 1;
-        if (ox < 0 || ox >= wo) continue;
-        const size_t base = (((size_t)im * ho + oy) * wo + ox) * kStemK + ky * 24 + kx * 3;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[c] += bf16_bits_to_f32(__ldg(ch + base + c)) + bf16_bits_to_f32(__ldg(cl + base + c));
+        if (ox >= 0 && ox < wo) acc += runs[(kyi * wo + ox) * kRunPitch + kx * 3 + c];
       }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) dx[(((size_t)im * 3 + c) * h + iy) * w + ix] = acc[c] * inv_std.v[c];
+    dx[(((size_t)im * 3 + c) * h + iy) * w + ix] = acc * inv_std.v[c];
   }
 }
 }  // namespace
@@ -289,7 +304,14 @@ int b200r_stem_col2im_f32(const uint16_t* dcols, float* dx, int n, int h, int w,
   const size_t rows = (size_t)n * ho * wo;
   Inv3 inv;
   for (int i = 0; i < 3; ++i) inv.v[i] = 1.0f / std_host[i];
-  stem_col2im_kernel<<<grid_for((size_t)n * h * w), kThreads, 0, as_stream(stream)>>>(dcols, dcols + rows * kStemK, dx, n, h, w, ho, wo, inv);
+  const int smem = 4 * wo * kRunPitch * (int)sizeof(float);
+  B200R_CHECK_ARG(smem <= 200 * 1024, "image too wide for the staged col2im (w = %d)", w);
+  static int configured = 0;
+  if (configured < smem) {
+    B200R_CUDA(cudaFuncSetAttribute(stem_col2im_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  stem_col2im_kernel<<<(unsigned)((size_t)n * h), kThreads, smem, as_stream(stream)>>>(dcols, dcols + rows * kStemK, dx, h, w, ho, wo, inv);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }

@@ -340,6 +340,7 @@ def pgd_loop_report(model, dev, pk, n=128, steps=10, reps=2):
     """The second half of the north star, reported beside the headline metric (not part of `value`): the PGD-Linf
     10-step eval loop on ResNet-50, forward + input gradient on the sm_100a kernels, then one
     forward of the adversarial batch + counters.  Algorithmic FLOPs = (2k+1) * 8.18 GFLOP / image."""
+    import torch
     from robustart_b200 import attacks, ops
     g = torch.Generator(device=dev).manual_seed(2)
     x = torch.rand(n, 3, 224, 224, device=dev, generator=g)

@@ -167,6 +167,7 @@ int b200r_masked_rows_copy(float* dst, const float* src, const uint8_t* mask, si
  * is stored as two bf16 planes hi = bf16(v), lo = bf16(v - hi); a product uses hi*hi + hi*lo +
  * lo*hi with fp32 accumulation in TMEM).
  * ------------------------------------------------------------------------------------------ */
+#define B200R_PASSES_F16 16
 enum b200r_act { B200R_ACT_NONE = 0, B200R_ACT_RELU = 1, B200R_ACT_RELU6 = 2,
                  B200R_ACT_GELU_TANH = 3, B200R_ACT_GELU_ERF = 4, B200R_ACT_SWISH = 5,
                  B200R_ACT_TANH = 6, B200R_ACT_SIGMOID = 7 };
@@ -183,7 +184,12 @@ int b200r_merge_f32(const uint16_t* planes, float* out, size_t count, b200r_stre
  *   res    : split planes of [n, ho, wo, cout] added before the activation (nullable)
  *   y      : split planes of [n, ho, wo, cout] (nullable if y_f32 given)
  *   y_f32  : float32 [n, ho, wo, cout] (nullable)
- *   passes : 3 = hi*hi+hi*lo+lo*hi (fp32-faithful), 1 = hi*hi only (plain bf16)
+ *   passes : 3 = hi*hi+hi*lo+lo*hi (fp32-faithful), 1 = hi*hi only (plain bf16),
+ *            B200R_PASSES_F16 = every tensor argument is ONE plane of IEEE fp16 (x, wgt, res, y are then
+ *            [1][...] instead of [2][...]): one MMA per product, fp32 accumulation -- the same 10-bit
+ *            mantissa as the TF32 path the reference's own GPU convolutions take by default
+ *            (torch.backends.cudnn.allow_tf32); error on the golden models ~2e-4 of the 1e-3 logit budget.
+ *            Accepted by conv2d / linear / stem_conv7x7 / conv2d_dgrad; the elementwise layers have _f16 twins.
  */
 int b200r_conv2d_nhwc(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias,
                       const uint16_t* res, uint16_t* y, float* y_f32, int n, int h, int w, int cin,
@@ -227,6 +233,14 @@ int b200r_maxpool3x3s2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w,
 int b200r_global_avgpool_nhwc(const uint16_t* x, uint16_t* y, int n, int hw, int c,
                               b200r_stream_t stream);
 
+/* fp16 single-plane twins of the layers above (activations produced with passes = B200R_PASSES_F16) */
+int b200r_f32_to_f16(const float* in, uint16_t* out, size_t count, float scale, b200r_stream_t stream);
+int b200r_f16_to_f32(const uint16_t* in, float* out, size_t count, float scale, b200r_stream_t stream);
+int b200r_maxpool3x3s2_nhwc_f16(const uint16_t* x, uint16_t* y, int n, int h, int w, int c,
+                                b200r_stream_t stream);
+int b200r_global_avgpool_nhwc_f16(const uint16_t* x, uint16_t* y, int n, int hw, int c,
+                                  b200r_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Input-gradient pass (d loss / d image) of the convolutional models: what the attack loops call once
  * per step (foolbox value_and_grad in attack.py:20-33; autopgd_base.py:371-376; imfgsm_attack.py:77-84).
@@ -264,6 +278,19 @@ int b200r_global_avgpool_bwd_nhwc(const uint16_t* dy, uint16_t* dx, int n, int h
  * of b200r_stem_im2col_u8) -> float32 NCHW gradient w.r.t. the [0,1] image, dx[n,c,y,x] = sum(taps) / std[c]. */
 int b200r_stem_col2im_f32(const uint16_t* dcols, float* dx, int n, int h, int w, const float* std_host,
                           b200r_stream_t stream);
+/* fp16 single-plane twins (gradients produced with passes = B200R_PASSES_F16).  Gradients of a classifier are
+ * small (1e-4 .. 1e-10 on the golden ResNets), so the fp16 pass runs on dlogits * S (b200r_f32_to_f16's scale; the
+ * host mirror uses S = 4096) and `unscale` = 1/S is applied with 1/std when the image gradient is written. */
+int b200r_relu_bwd_f16(const uint16_t* dy, const uint16_t* act, const uint16_t* add, uint16_t* out,
+                       size_t count, b200r_stream_t stream);
+int b200r_dilate2_nhwc_f16(const uint16_t* x, uint16_t* y, int n, int h, int w, int c,
+                           b200r_stream_t stream);
+int b200r_maxpool3x3s2_bwd_nhwc_f16(const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* workspace,
+                                    size_t ws_bytes, int n, int h, int w, int c, b200r_stream_t stream);
+int b200r_global_avgpool_bwd_nhwc_f16(const uint16_t* dy, uint16_t* dx, int n, int hw, int c,
+                                      b200r_stream_t stream);
+int b200r_stem_col2im_f32_f16(const uint16_t* dcols, float* dx, int n, int h, int w,
+                              const float* std_host, float unscale, b200r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Mobile families (MobileNetV2: prototype/prototype/model/mobilenet_v2.py:31-202; EfficientNet-B0:

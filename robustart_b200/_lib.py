@@ -65,6 +65,10 @@ SIGNATURES = {
                                           c_stream]),
     "b200r_global_avgpool_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                             c_stream]),
+    "b200r_f32_to_f16": (C.c_int, [c_f32p, C.c_void_p, C.c_size_t, C.c_float, c_stream]),
+    "b200r_f16_to_f32": (C.c_int, [C.c_void_p, c_f32p, C.c_size_t, C.c_float, c_stream]),
+    "b200r_maxpool3x3s2_nhwc_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_global_avgpool_nhwc_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_conv2d_dgrad_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
@@ -73,6 +77,12 @@ SIGNATURES = {
                                               C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_global_avgpool_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_stem_col2im_f32": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, c_host_f3, c_stream]),
+    "b200r_relu_bwd_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
+    "b200r_dilate2_nhwc_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_maxpool3x3s2_bwd_nhwc_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                                  C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_global_avgpool_bwd_nhwc_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_stem_col2im_f32_f16": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, c_host_f3, C.c_float, c_stream]),
 }
 
 

@@ -7,10 +7,52 @@
 //   maxpool_bwd   MaxPool2d(3,2,1) backward with PyTorch's first-maximum tie rule
 //   avgpool_bwd   AdaptiveAvgPool2d(1) backward
 //   stem_col2im   im2col^T of the 7x7/s2 stem + the 1/std of Normalize -> float32 NCHW image gradient
+// Every kernel is a template on F16: false = split-bf16 planes (hi, lo), true = ONE fp16 plane (the `*l` pointers are
+// unused), the activation format of passes = B200R_PASSES_F16.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 constexpr int kThreads = 256;
+
+// 8 consecutive channels of a tensor as floats, from one 16-byte piece per plane
+template <bool F16>
+__device__ __forceinline__ void load8(const uint4* __restrict__ ph, const uint4* __restrict__ pl, size_t i, float (&v)[8]) {
+  const uint4 a = __ldg(ph + i);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+  if (F16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&aw[j]));
+      v[2 * j] = f.x; v[2 * j + 1] = f.y;
+    }
+  } else {
+    const uint4 b = __ldg(pl + i);
+    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = bf16_bits_to_f32((uint16_t)(aw[j >> 1] >> (16 * (j & 1)))) + bf16_bits_to_f32((uint16_t)(bw[j >> 1] >> (16 * (j & 1))));
+  }
+}
+template <bool F16>
+__device__ __forceinline__ void store8(uint4* __restrict__ ph, uint4* __restrict__ pl, size_t i, const float (&v)[8]) {
+  uint32_t rh[4], rl[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (F16) {
+      const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      rh[j] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      uint16_t h0, l0, h1, l1;
+      split_bf16(v[2 * j], h0, l0);
+      split_bf16(v[2 * j + 1], h1, l1);
+      rh[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+      rl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
+  }
+  ph[i] = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+  if (!F16) pl[i] = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+}
 
 __device__ __forceinline__ uint32_t pack2(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }
 __device__ __forceinline__ float plane_val(uint32_t hw, uint32_t lw, int odd) {
@@ -24,15 +66,27 @@ inline unsigned grid_for(size_t items) {
 }
 
 // ---- ReLU backward, 8 elements per thread ---------------------------------------------------------
-template <bool ADD>
+template <bool ADD, bool F16>
 __global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const uint4* __restrict__ dyh, const uint4* __restrict__ dyl,
                                                              const uint4* __restrict__ acth, const uint4* __restrict__ addh,
                                                              const uint4* __restrict__ addl, uint4* __restrict__ oh,
                                                              uint4* __restrict__ ol, size_t count8) {
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < count8; i += (size_t)gridDim.x * kThreads) {
-    const uint4 a = __ldg(acth + i), gh = __ldg(dyh + i), gl = __ldg(dyl + i);
+    const uint4 a = __ldg(acth + i), gh = __ldg(dyh + i), gl = F16 ? make_uint4(0, 0, 0, 0) : __ldg(dyl + i);
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, hw[4] = {gh.x, gh.y, gh.z, gh.w}, lw[4] = {gl.x, gl.y, gl.z, gl.w};
     uint32_t rh[4], rl[4];
+    if (ADD && F16) {
+      float g[8], b[8];
+      load8<true>(dyh, nullptr, i, g);
+      load8<true>(addh, nullptr, i, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint16_t ab = (uint16_t)(aw[j >> 1] >> (16 * (j & 1)));
+        g[j] = ((ab != 0 && !(ab & 0x8000u)) ? g[j] : 0.f) + b[j];
+      }
+      store8<true>(oh, nullptr, i, g);
+      continue;
+    }
     if (!ADD) {
       // pure masking keeps the planes bit-exact: a positive activation has a positive hi plane (bf16 rounding
       // keeps the sign; 0x0000 / 0x8000 / negative patterns are "not > 0")
@@ -61,11 +115,12 @@ __global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const uint4* __restr
       }
     }
     oh[i] = make_uint4(rh[0], rh[1], rh[2], rh[3]);
-    ol[i] = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+    if (!F16) ol[i] = make_uint4(rl[0], rl[1], rl[2], rl[3]);
   }
 }
 
 // ---- zero insertion: y[n, 2i, 2j, :] = x[n, i, j, :] ----------------------------------------------
+template <bool F16>
 __global__ void __launch_bounds__(kThreads) dilate2_kernel(const uint4* __restrict__ xh, const uint4* __restrict__ xl,
                                                             uint4* __restrict__ yh, uint4* __restrict__ yl, int n, int h, int w,
                                                             int c8) {
@@ -78,15 +133,16 @@ __global__ void __launch_bounds__(kThreads) dilate2_kernel(const uint4* __restri
     if (!((p | q) & 1)) {
       const size_t src = (((size_t)im * h + (p >> 1)) * w + (q >> 1)) * c8 + cc;
       vh = __ldg(xh + src);
-      vl = __ldg(xl + src);
+      if (!F16) vl = __ldg(xl + src);
     }
     yh[t] = vh;
-    yl[t] = vl;
+    if (!F16) yl[t] = vl;
   }
 }
 
 // ---- MaxPool2d(3, 2, 1) backward --------------------------------------------------------------------
 // pass 1: per output window, the position (ky*3+kx) of the first maximum, as the forward kernel picks it
+template <bool F16>
 __global__ void __launch_bounds__(kThreads) maxpool_argmax_kernel(const uint4* __restrict__ xh, const uint4* __restrict__ xl,
                                                                    uint2* __restrict__ idx, int n, int h, int w, int c8, int ho,
                                                                    int wo) {
@@ -106,19 +162,18 @@ __global__ void __launch_bounds__(kThreads) maxpool_argmax_kernel(const uint4* _
         const int ix = ox * 2 - 1 + kx;
         if (ix < 0 || ix >= w) continue;
         const size_t s = (((size_t)im * h + iy) * w + ix) * c8 + cc;
-        const uint4 a = __ldg(xh + s), b = __ldg(xl + s);
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        float v[8];
+        load8<F16>(xh, xl, s, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float v = plane_val(aw[j >> 1], bw[j >> 1], j & 1);
-          if (v > best[j]) { best[j] = v; bi[j] = (uint32_t)(ky * 3 + kx); }
-        }
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > best[j]) { best[j] = v[j]; bi[j] = (uint32_t)(ky * 3 + kx); }
       }
     }
     idx[t] = make_uint2(bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24), bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24));
   }
 }
 // pass 2: per input position, the sum of dy over the (at most four) windows whose maximum it is
+template <bool F16>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint2* __restrict__ idx, const uint4* __restrict__ dyh,
                                                                 const uint4* __restrict__ dyl, uint4* __restrict__ dxh,
                                                                 uint4* __restrict__ dxl, int n, int h, int w, int c8, int ho, int wo) {
@@ -141,32 +196,26 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint2* __re
         const uint32_t m0 = id.x ^ (code * 0x01010101u), m1 = id.y ^ (code * 0x01010101u);
         // any byte of m0 / m1 equal to zero = this position is the argmax of that channel
         if (!(((m0 - 0x01010101u) & ~m0 & 0x80808080u) | ((m1 - 0x01010101u) & ~m1 & 0x80808080u))) continue;
-        const uint4 gh = __ldg(dyh + o), gl = __ldg(dyl + o);
-        const uint32_t hw[4] = {gh.x, gh.y, gh.z, gh.w}, lw[4] = {gl.x, gl.y, gl.z, gl.w};
+        float g[8];
+        load8<F16>(dyh, dyl, o, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t b = ((j < 4 ? id.x : id.y) >> (8 * (j & 3))) & 0xFFu;
-          if (b == code) { acc[j] += plane_val(hw[j >> 1], lw[j >> 1], j & 1); any = true; }
+          if (b == code) { acc[j] += g[j]; any = true; }
         }
       }
     }
-    uint32_t rh[4] = {0, 0, 0, 0}, rl[4] = {0, 0, 0, 0};
     if (any) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint16_t h0, l0, h1, l1;
-        split_bf16(acc[2 * j], h0, l0);
-        split_bf16(acc[2 * j + 1], h1, l1);
-        rh[j] = pack2(h0, h1);
-        rl[j] = pack2(l0, l1);
-      }
+      store8<F16>(dxh, dxl, t, acc);
+    } else {
+      dxh[t] = make_uint4(0, 0, 0, 0);
+      if (!F16) dxl[t] = make_uint4(0, 0, 0, 0);
     }
-    dxh[t] = make_uint4(rh[0], rh[1], rh[2], rh[3]);
-    dxl[t] = make_uint4(rl[0], rl[1], rl[2], rl[3]);
   }
 }
 
 // ---- global average pool backward: dx[n, p, c] = dy[n, c] / hw ----------------------------------------
+template <bool F16>
 __global__ void __launch_bounds__(kThreads) avgpool_bwd_kernel(const uint4* __restrict__ dyh, const uint4* __restrict__ dyl,
                                                                 uint4* __restrict__ dxh, uint4* __restrict__ dxl, int n, int hw,
                                                                 int c8) {
@@ -175,19 +224,11 @@ __global__ void __launch_bounds__(kThreads) avgpool_bwd_kernel(const uint4* __re
   for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
     const int cc = (int)(t % c8);
     const int im = (int)(t / ((size_t)hw * c8));
-    const uint4 gh = __ldg(dyh + (size_t)im * c8 + cc), gl = __ldg(dyl + (size_t)im * c8 + cc);
-    const uint32_t hwd[4] = {gh.x, gh.y, gh.z, gh.w}, lwd[4] = {gl.x, gl.y, gl.z, gl.w};
-    uint32_t rh[4], rl[4];
+    float g[8];
+    load8<F16>(dyh, dyl, (size_t)im * c8 + cc, g);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint16_t h0, l0, h1, l1;
-      split_bf16(plane_val(hwd[j], lwd[j], 0) * inv, h0, l0);
-      split_bf16(plane_val(hwd[j], lwd[j], 1) * inv, h1, l1);
-      rh[j] = pack2(h0, h1);
-      rl[j] = pack2(l0, l1);
-    }
-    dxh[t] = make_uint4(rh[0], rh[1], rh[2], rh[3]);
-    dxl[t] = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+    for (int j = 0; j < 8; ++j) g[j] *= inv;
+    store8<F16>(dxh, dxl, t, g);
   }
 }
 
@@ -199,6 +240,7 @@ __global__ void __launch_bounds__(kThreads) avgpool_bwd_kernel(const uint4* __re
 struct Inv3 { float v[3]; };
 constexpr int kStemK = 192;
 constexpr int kRunPitch = 25;
+template <bool F16>
 __global__ void __launch_bounds__(kThreads) stem_col2im_kernel(const uint16_t* __restrict__ ch, const uint16_t* __restrict__ cl,
                                                                 float* __restrict__ dx, int h, int w, int ho, int wo, Inv3 inv_std) {
   extern __shared__ float runs[];                                // [4][wo][kRunPitch]
@@ -210,10 +252,7 @@ __global__ void __launch_bounds__(kThreads) stem_col2im_kernel(const uint16_t* _
     float vals[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (ky <= 6 && oy >= 0 && oy < ho) {
       const size_t base = (((size_t)im * ho + oy) * wo + ox) * kStemK + ky * 24 + part * 8;
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(ch + base)), b = __ldg(reinterpret_cast<const uint4*>(cl + base));
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) vals[j] = plane_val(aw[j >> 1], bw[j >> 1], j & 1);
+      load8<F16>(reinterpret_cast<const uint4*>(ch + base), reinterpret_cast<const uint4*>(cl + base), 0, vals);
     }
     float* dst = runs + (kyi * wo + ox) * kRunPitch + part * 8;
 #pragma unroll
@@ -234,86 +273,137 @@ __global__ void __launch_bounds__(kThreads) stem_col2im_kernel(const uint16_t* _
 }
 }  // namespace
 
-extern "C" {
-
-int b200r_relu_bwd(const uint16_t* dy, const uint16_t* act, const uint16_t* add, uint16_t* out, size_t count,
-                   b200r_stream_t stream) {
+// ---- host side: one implementation per layer, f16 selects the single-plane instantiation -----------------------
+static int relu_bwd_impl(const uint16_t* dy, const uint16_t* act, const uint16_t* add, uint16_t* out, size_t count, bool f16,
+                         cudaStream_t s) {
   B200R_CHECK_ARG(dy && act && out, "null pointer");
   B200R_CHECK_ARG(count % 8 == 0, "count must be a multiple of 8");
   if (!count) return B200R_OK;
   const size_t c8 = count / 8;
-  cudaStream_t s = as_stream(stream);
   const uint4 *dh = reinterpret_cast<const uint4*>(dy), *dl = reinterpret_cast<const uint4*>(dy + count);
   const uint4* ah = reinterpret_cast<const uint4*>(act);
+  const uint4 *bh = reinterpret_cast<const uint4*>(add), *bl = add ? reinterpret_cast<const uint4*>(add + count) : nullptr;
   uint4 *oh = reinterpret_cast<uint4*>(out), *ol = reinterpret_cast<uint4*>(out + count);
-  if (add)
-    relu_bwd_kernel<true><<<grid_for(c8), kThreads, 0, s>>>(dh, dl, ah, reinterpret_cast<const uint4*>(add),
-                                                           reinterpret_cast<const uint4*>(add + count), oh, ol, c8);
-  else
-    relu_bwd_kernel<false><<<grid_for(c8), kThreads, 0, s>>>(dh, dl, ah, nullptr, nullptr, oh, ol, c8);
+  if (f16) {
+    if (add) relu_bwd_kernel<true, true><<<grid_for(c8), kThreads, 0, s>>>(dh, nullptr, ah, bh, nullptr, oh, nullptr, c8);
+    else relu_bwd_kernel<false, true><<<grid_for(c8), kThreads, 0, s>>>(dh, nullptr, ah, nullptr, nullptr, oh, nullptr, c8);
+  } else {
+    if (add) relu_bwd_kernel<true, false><<<grid_for(c8), kThreads, 0, s>>>(dh, dl, ah, bh, bl, oh, ol, c8);
+    else relu_bwd_kernel<false, false><<<grid_for(c8), kThreads, 0, s>>>(dh, dl, ah, nullptr, nullptr, oh, ol, c8);
+  }
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
 
-int b200r_dilate2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int c, b200r_stream_t stream) {
+static int dilate2_impl(const uint16_t* x, uint16_t* y, int n, int h, int w, int c, bool f16, cudaStream_t s) {
   B200R_CHECK_ARG(x && y, "null pointer");
   B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "c must be a multiple of 8");
   const size_t xin = (size_t)n * h * w * c, yout = xin * 4;
-  dilate2_kernel<<<grid_for(yout / 8), kThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + xin), reinterpret_cast<uint4*>(y),
-      reinterpret_cast<uint4*>(y + yout), n, h, w, c / 8);
+  if (f16)
+    dilate2_kernel<true><<<grid_for(yout / 8), kThreads, 0, s>>>(reinterpret_cast<const uint4*>(x), nullptr, reinterpret_cast<uint4*>(y),
+                                                                nullptr, n, h, w, c / 8);
+  else
+    dilate2_kernel<false><<<grid_for(yout / 8), kThreads, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + xin),
+                                                                 reinterpret_cast<uint4*>(y), reinterpret_cast<uint4*>(y + yout), n, h, w, c / 8);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
 
-int b200r_maxpool3x3s2_bwd_nhwc(const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* workspace, size_t ws_bytes, int n,
-                                int h, int w, int c, b200r_stream_t stream) {
+static int maxpool_bwd_impl(const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* workspace, size_t ws_bytes, int n, int h, int w,
+                            int c, bool f16, cudaStream_t s) {
   B200R_CHECK_ARG(x && dy && dx && workspace, "null pointer");
   B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c % 8 == 0, "c must be a multiple of 8");
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
   const size_t xin = (size_t)n * h * w * c, yout = (size_t)n * ho * wo * c;
   B200R_CHECK_ARG(ws_bytes >= yout, "workspace too small: need %zu bytes (one per pooled element)", yout);
   B200R_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "workspace must be 8-byte aligned");
-  cudaStream_t s = as_stream(stream);
   uint2* idx = reinterpret_cast<uint2*>(workspace);
-  maxpool_argmax_kernel<<<grid_for(yout / 8), kThreads, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + xin),
-                                                               idx, n, h, w, c / 8, ho, wo);
-  B200R_LAUNCH_CHECK();
-  maxpool_bwd_kernel<<<grid_for(xin / 8), kThreads, 0, s>>>(idx, reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(dy + yout),
-                                                           reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dx + xin), n, h, w, c / 8,
-                                                           ho, wo);
+  const uint4 *xh = reinterpret_cast<const uint4*>(x), *gh = reinterpret_cast<const uint4*>(dy);
+  uint4* dh = reinterpret_cast<uint4*>(dx);
+  if (f16) {
+    maxpool_argmax_kernel<true><<<grid_for(yout / 8), kThreads, 0, s>>>(xh, nullptr, idx, n, h, w, c / 8, ho, wo);
+    B200R_LAUNCH_CHECK();
+    maxpool_bwd_kernel<true><<<grid_for(xin / 8), kThreads, 0, s>>>(idx, gh, nullptr, dh, nullptr, n, h, w, c / 8, ho, wo);
+  } else {
+    maxpool_argmax_kernel<false><<<grid_for(yout / 8), kThreads, 0, s>>>(xh, reinterpret_cast<const uint4*>(x + xin), idx, n, h, w, c / 8, ho, wo);
+    B200R_LAUNCH_CHECK();
+    maxpool_bwd_kernel<false><<<grid_for(xin / 8), kThreads, 0, s>>>(idx, gh, reinterpret_cast<const uint4*>(dy + yout), dh,
+                                                                    reinterpret_cast<uint4*>(dx + xin), n, h, w, c / 8, ho, wo);
+  }
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
 
-int b200r_global_avgpool_bwd_nhwc(const uint16_t* dy, uint16_t* dx, int n, int hw, int c, b200r_stream_t stream) {
+static int avgpool_bwd_impl(const uint16_t* dy, uint16_t* dx, int n, int hw, int c, bool f16, cudaStream_t s) {
   B200R_CHECK_ARG(dy && dx, "null pointer");
   B200R_CHECK_ARG(n > 0 && hw > 0 && c % 8 == 0, "c must be a multiple of 8");
   const size_t yin = (size_t)n * c, xout = yin * hw;
-  avgpool_bwd_kernel<<<grid_for(xout / 8), kThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(dy + yin), reinterpret_cast<uint4*>(dx),
-      reinterpret_cast<uint4*>(dx + xout), n, hw, c / 8);
+  if (f16)
+    avgpool_bwd_kernel<true><<<grid_for(xout / 8), kThreads, 0, s>>>(reinterpret_cast<const uint4*>(dy), nullptr, reinterpret_cast<uint4*>(dx),
+                                                                    nullptr, n, hw, c / 8);
+  else
+    avgpool_bwd_kernel<false><<<grid_for(xout / 8), kThreads, 0, s>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(dy + yin),
+                                                                     reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dx + xout), n, hw, c / 8);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
 
-int b200r_stem_col2im_f32(const uint16_t* dcols, float* dx, int n, int h, int w, const float* std_host, b200r_stream_t stream) {
+static int col2im_impl(const uint16_t* dcols, float* dx, int n, int h, int w, const float* std_host, float unscale, bool f16,
+                       cudaStream_t s) {
   B200R_CHECK_ARG(dcols && dx && std_host, "null pointer");
   B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "bad shape");
   const int ho = h / 2, wo = w / 2;
   const size_t rows = (size_t)n * ho * wo;
   Inv3 inv;
-  for (int i = 0; i < 3; ++i) inv.v[i] = 1.0f / std_host[i];
+  for (int i = 0; i < 3; ++i) inv.v[i] = unscale / std_host[i];
   const int smem = 4 * wo * kRunPitch * (int)sizeof(float);
   B200R_CHECK_ARG(smem <= 200 * 1024, "image too wide for the staged col2im (w = %d)", w);
-  static int configured = 0;
-  if (configured < smem) {
-    B200R_CUDA(cudaFuncSetAttribute(stem_col2im_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
+  static int configured[2] = {0, 0};
+  if (configured[f16] < smem) {
+    if (f16) B200R_CUDA(cudaFuncSetAttribute(stem_col2im_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else B200R_CUDA(cudaFuncSetAttribute(stem_col2im_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[f16] = smem;
   }
-  stem_col2im_kernel<<<(unsigned)((size_t)n * h), kThreads, smem, as_stream(stream)>>>(dcols, dcols + rows * kStemK, dx, h, w, ho, wo, inv);
+  if (f16) stem_col2im_kernel<true><<<(unsigned)((size_t)n * h), kThreads, smem, s>>>(dcols, nullptr, dx, h, w, ho, wo, inv);
+  else stem_col2im_kernel<false><<<(unsigned)((size_t)n * h), kThreads, smem, s>>>(dcols, dcols + rows * kStemK, dx, h, w, ho, wo, inv);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
+}
+
+extern "C" {
+
+int b200r_relu_bwd(const uint16_t* dy, const uint16_t* act, const uint16_t* add, uint16_t* out, size_t count, b200r_stream_t stream) {
+  return relu_bwd_impl(dy, act, add, out, count, false, as_stream(stream));
+}
+int b200r_relu_bwd_f16(const uint16_t* dy, const uint16_t* act, const uint16_t* add, uint16_t* out, size_t count, b200r_stream_t stream) {
+  return relu_bwd_impl(dy, act, add, out, count, true, as_stream(stream));
+}
+int b200r_dilate2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int c, b200r_stream_t stream) {
+  return dilate2_impl(x, y, n, h, w, c, false, as_stream(stream));
+}
+int b200r_dilate2_nhwc_f16(const uint16_t* x, uint16_t* y, int n, int h, int w, int c, b200r_stream_t stream) {
+  return dilate2_impl(x, y, n, h, w, c, true, as_stream(stream));
+}
+int b200r_maxpool3x3s2_bwd_nhwc(const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* workspace, size_t ws_bytes, int n, int h, int w,
+                                int c, b200r_stream_t stream) {
+  return maxpool_bwd_impl(x, dy, dx, workspace, ws_bytes, n, h, w, c, false, as_stream(stream));
+}
+int b200r_maxpool3x3s2_bwd_nhwc_f16(const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* workspace, size_t ws_bytes, int n, int h,
+                                    int w, int c, b200r_stream_t stream) {
+  return maxpool_bwd_impl(x, dy, dx, workspace, ws_bytes, n, h, w, c, true, as_stream(stream));
+}
+int b200r_global_avgpool_bwd_nhwc(const uint16_t* dy, uint16_t* dx, int n, int hw, int c, b200r_stream_t stream) {
+  return avgpool_bwd_impl(dy, dx, n, hw, c, false, as_stream(stream));
+}
+int b200r_global_avgpool_bwd_nhwc_f16(const uint16_t* dy, uint16_t* dx, int n, int hw, int c, b200r_stream_t stream) {
+  return avgpool_bwd_impl(dy, dx, n, hw, c, true, as_stream(stream));
+}
+int b200r_stem_col2im_f32(const uint16_t* dcols, float* dx, int n, int h, int w, const float* std_host, b200r_stream_t stream) {
+  return col2im_impl(dcols, dx, n, h, w, std_host, 1.0f, false, as_stream(stream));
+}
+int b200r_stem_col2im_f32_f16(const uint16_t* dcols, float* dx, int n, int h, int w, const float* std_host, float unscale,
+                              b200r_stream_t stream) {
+  return col2im_impl(dcols, dx, n, h, w, std_host, unscale, true, as_stream(stream));
 }
 
 }  // extern "C"

@@ -6,7 +6,10 @@
 // Precision: "split-bf16".  Every fp32 tensor lives in HBM as two bf16 planes (hi, lo); a product
 // is hi*hi + hi*lo + lo*hi (passes = 3) accumulated in fp32 in TMEM -> ~2^-16 relative error per
 // product, which is what holds the 1e-3 logit tolerance against the fp32 reference.  passes = 1 is
-// plain bf16.
+// plain bf16.  passes = B200R_PASSES_F16 (16): ONE fp16 plane per tensor (kernel template F16) -- operands and stored
+// activations are fp16 (10 explicit mantissa bits, like TF32), one MMA per product, fp32 accumulation; half the
+// activation bytes and a third of the tensor-pipe work of the split scheme.  Holds the 1e-3 logit tolerance on the
+// ResNet golden models with a 5x margin (tests/test_resnet_gpu.py); the smem ring is twice as deep (no lo tiles).
 //
 // Structure (one CTA per SM, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor (5-D map over [plane, N, H, W, C] for activations --
@@ -21,6 +24,7 @@
 //               planes (and/or fp32), masked stores.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include <string.h>
 #include <stdlib.h>
@@ -169,6 +173,12 @@ __device__ __forceinline__ void ld_global_v8(const void* p, uint32_t* v) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "l"(p));
 }
+__device__ __forceinline__ uint32_t cvt_f16x2(float hi, float lo) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ float2 f16x2_to_f32(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzled operand tile (rows of 64 bf16 at a 128 B pitch, 8-row atoms 1024 B apart)
@@ -230,18 +240,20 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 // STEM_MODE: 0 = TMA-fed convolution / linear, 1 = fused stem from the uint8 NHWC image, 2 = fused stem from a float32
 // NCHW image in [0,1] (the attack path)
-template <int BN, int STEM_MODE>
+template <int BN, int STEM_MODE, bool F16>
 __global__ void __launch_bounds__(STEM_MODE ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_i,
             const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
   constexpr bool STEM = STEM_MODE != 0;
   constexpr bool STEM_F32 = STEM_MODE == 2;
-  constexpr int kStages = (BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault);
+  constexpr int kStages = ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
   constexpr int B_TILE_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  constexpr int B_OFF = F16 ? A_TILE_BYTES : 2 * A_TILE_BYTES;           // F16: [A | B]; split: [A_hi | A_lo | B_hi | B_lo]
+  constexpr int STAGE_BYTES = B_OFF + (F16 ? 1 : 2) * B_TILE_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers (power of two: 128 or 256)
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  // instruction descriptor: fp32 accumulator (bit 4), A/B format (bits 7, 10: 1 = bf16, 0 = fp16), N >> 3, M >> 4
+  constexpr uint32_t IDESC = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -313,10 +325,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               mbar_expect_tx(full_bar(stage), tx_bytes);
               const int kcol = (kh * p.KW + kw) * p.cin + cb * BK;
               if (!STEM) tma_load_5d(sa, &map_a, full_bar(stage), cb * BK, w_in0 + kw, h_in0 + kh, n0, 0);
-              tma_load_3d(sa + 2 * A_TILE_BYTES, &map_b, full_bar(stage), kcol, nt * BN, 0);
-              if (p.passes == 3) {
+              tma_load_3d(sa + B_OFF, &map_b, full_bar(stage), kcol, nt * BN, 0);
+              if (!F16 && p.passes == 3) {
                 if (!STEM) tma_load_5d(sa + A_TILE_BYTES, &map_a, full_bar(stage), cb * BK, w_in0 + kw, h_in0 + kh, n0, 1);
-                tma_load_3d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b, full_bar(stage), kcol, nt * BN, 1);
+                tma_load_3d(sa + B_OFF + B_TILE_BYTES, &map_b, full_bar(stage), kcol, nt * BN, 1);
               }
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -325,10 +337,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         mbar_wait(empty_bar(stage), phase ^ 1);
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), 2u * a_bytes + (uint32_t)B_TILE_BYTES);
+          mbar_expect_tx(full_bar(stage), (F16 ? 1u : 2u) * a_bytes + (uint32_t)B_TILE_BYTES);
           tma_load_5d(sa, &map_r, full_bar(stage), nt * BN + j * BK, tw * p.bw, th * p.bh, n0, 0);
-          tma_load_5d(sa + A_TILE_BYTES, &map_r, full_bar(stage), nt * BN + j * BK, tw * p.bw, th * p.bh, n0, 1);
-          tma_load_2d(sa + 2 * A_TILE_BYTES, &map_i, full_bar(stage), j * BK, 0);
+          if (!F16) tma_load_5d(sa + A_TILE_BYTES, &map_r, full_bar(stage), nt * BN + j * BK, tw * p.bw, th * p.bh, n0, 1);
+          tma_load_2d(sa + B_OFF, &map_i, full_bar(stage), j * BK, 0);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -350,9 +362,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + A_TILE_BYTES);
-          const uint64_t b_hi = make_sw128_desc(sa + 2 * A_TILE_BYTES);
-          const uint64_t b_lo = make_sw128_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
-          if (p.passes == 3) {
+          const uint64_t b_hi = make_sw128_desc(sa + B_OFF);
+          const uint64_t b_lo = make_sw128_desc(sa + B_OFF + B_TILE_BYTES);
+          if (!F16 && p.passes == 3) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle row
@@ -378,12 +390,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + A_TILE_BYTES);
-          const uint64_t b_hi = make_sw128_desc(sa + 2 * A_TILE_BYTES);
+          const uint64_t b_hi = make_sw128_desc(sa + B_OFF);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
             umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1);
-            umma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1);
+            if (!F16) umma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1);
           }
           umma_commit(empty_bar(stage));
           if (j == kb_res - 1) umma_commit(tfull_bar(acc));
@@ -462,17 +474,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             for (int q = 0; q < 2; ++q) {
               uint32_t hw[8], lw[8];
               ld_global_v8(p.res_hi + off + 16 * q, hw);
-              ld_global_v8(p.res_lo + off + 16 * q, lw);
+              if (F16) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                f[16 * q + 2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-                f[16 * q + 2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+                for (int j = 0; j < 8; ++j) {
+                  const float2 r2 = f16x2_to_f32(hw[j]);
+                  f[16 * q + 2 * j] += r2.x;
+                  f[16 * q + 2 * j + 1] += r2.y;
+                }
+              } else {
+                ld_global_v8(p.res_lo + off + 16 * q, lw);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  f[16 * q + 2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                  f[16 * q + 2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+                }
               }
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)   // compile-time j: the arrays must stay in registers
-              if (col0 + j < p.Cout) f[j] += bf16_bits_to_f32(p.res_hi[off + j]) + bf16_bits_to_f32(p.res_lo[off + j]);
+              if (col0 + j < p.Cout)
+                f[j] += F16 ? __half2float(__ushort_as_half(p.res_hi[off + j]))
+                            : bf16_bits_to_f32(p.res_hi[off + j]) + bf16_bits_to_f32(p.res_lo[off + j]);
           }
         }
         if (p.mask_hi && row_ok) {                        // ReLU backward fused into the dgrad GEMM: one bf16 plane read
@@ -517,9 +540,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           uint32_t ph[16], pl[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            ph[j] = cvt_bf16x2(f[2 * j + 1], f[2 * j]);
-            const float h0 = __uint_as_float(ph[j] << 16), h1 = __uint_as_float(ph[j] & 0xFFFF0000u);
-            pl[j] = cvt_bf16x2(f[2 * j + 1] - h1, f[2 * j] - h0);
+            if (F16) {
+              ph[j] = cvt_f16x2(f[2 * j + 1], f[2 * j]);
+              pl[j] = 0u;
+            } else {
+              ph[j] = cvt_bf16x2(f[2 * j + 1], f[2 * j]);
+              const float h0 = __uint_as_float(ph[j] << 16), h1 = __uint_as_float(ph[j] & 0xFFFF0000u);
+              pl[j] = cvt_bf16x2(f[2 * j + 1] - h1, f[2 * j] - h0);
+            }
           }
           if (p.tma_store) {
             if (issuer) bulk_wait_read0();                 // the previous store has finished reading the staging buffer
@@ -530,26 +558,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               // 8 consecutive rows cover all 32 banks, so the 16-byte stores are conflict free
               const int pos = (q ^ ((r >> 1) & 3)) * 16;
               *reinterpret_cast<uint4*>(stg + r * 64 + pos) = make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
-              *reinterpret_cast<uint4*>(stg + 8192 + r * 64 + pos) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+              if (!F16) *reinterpret_cast<uint4*>(stg + 8192 + r * 64 + pos) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
             }
             fence_proxy_async();
             named_bar_sync(2 + half, 128);
             if (issuer) {
               tma_store_5d(&map_y, stg_u32, col0, tw * p.bw, th * p.bh, ti * p.bn, 0);
-              tma_store_5d(&map_y, stg_u32 + 8192, col0, tw * p.bw, th * p.bh, ti * p.bn, 1);
+              if (!F16) tma_store_5d(&map_y, stg_u32 + 8192, col0, tw * p.bw, th * p.bh, ti * p.bn, 1);
               bulk_commit();
             }
           } else if (row_ok && full && (p.Cout % 16 == 0)) {   // direct 256-bit stores
             st_global_v8(p.y_hi + off, ph);
             st_global_v8(p.y_hi + off + 16, ph + 8);
-            st_global_v8(p.y_lo + off, pl);
-            st_global_v8(p.y_lo + off + 16, pl + 8);
+            if (!F16) {
+              st_global_v8(p.y_lo + off, pl);
+              st_global_v8(p.y_lo + off + 16, pl + 8);
+            }
           } else if (row_ok) {                             // ragged direct stores
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.Cout) {
                 p.y_hi[off + j] = (uint16_t)(ph[j >> 1] >> (16 * (j & 1)));
-                p.y_lo[off + j] = (uint16_t)(pl[j >> 1] >> (16 * (j & 1)));
+                if (!F16) p.y_lo[off + j] = (uint16_t)(pl[j >> 1] >> (16 * (j & 1)));
               }
           }
         }
@@ -630,7 +660,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint16_t hh, ll;
-            split_bf16((__uint_as_float(w4v[j]) - mu) / sd, hh, ll);   // same arithmetic as b200r_stem_im2col_f32
+            if (F16) { hh = __half_as_ushort(__float2half_rn((__uint_as_float(w4v[j]) - mu) / sd)); ll = 0; }
+            else split_bf16((__uint_as_float(w4v[j]) - mu) / sd, hh, ll);   // same arithmetic as b200r_stem_im2col_f32
             s_conv[d0 + 3 * j] = zero ? 0u : ((uint32_t)hh | ((uint32_t)ll << 16));
           }
         } else {
@@ -694,7 +725,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             l.z = __byte_perm(e[4], e[5], 0x7632); l.w = __byte_perm(e[6], e[7], 0x7632);
             const int pos = (q ^ (r & 7)) << 4;
             *reinterpret_cast<uint4*>(a_hi + pos) = h;
-            if (p.passes == 3) *reinterpret_cast<uint4*>(a_lo + pos) = l;
+            if (!F16 && p.passes == 3) *reinterpret_cast<uint4*>(a_lo + pos) = l;
           }
         }
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -740,34 +771,34 @@ EncodeTiledFn get_encode() {
 
 struct GemmMaps { CUtensorMap a, b, r, i, y; };
 
-template <int BN, int STEM>
+template <int BN, int STEM, bool F16>
 int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t s) {
-  constexpr int kStages = (BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault);
-  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * BN * BK * 2;
+  constexpr int kStages = ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
+  constexpr int STAGE_BYTES = (2 * A_TILE_BYTES + 2 * BN * BK * 2) / (F16 ? 2 : 1);
   // STEM adds the staged input rows (7 x (W_in*3 + 24) words) and the 3 KB LUT behind the barriers
   const int smem = kStages * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ +
                    ((STEM || p.tma_store) ? 32768 : 0) /*epilogue staging*/ + (STEM ? 7 * (p.W_in * 3 + 24) * 4 + 768 * 4 : 0);
   static int configured = 0;
   if (configured < smem) {
-    B200R_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200R_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STEM, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_img * p.tiles_n;
   const int grid = total < b200r_num_sms() ? total : b200r_num_sms();
-  gemm_kernel<BN, STEM><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(m.a, m.b, m.r, m.i, m.y, p);
+  gemm_kernel<BN, STEM, F16><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(m.a, m.b, m.r, m.i, m.y, p);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
 
 // 5-D map over split planes [plane][N][H][W][C] (dims listed innermost first)
 int make_map5(EncodeTiledFn enc, CUtensorMap* m, const uint16_t* base, int C, int W, int H, int N, size_t plane_elems, int box_c,
-              int box_w, int box_h, int box_n, int estride, CUtensorMapSwizzle swz, const char* what) {
-  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, 2};
+              int box_w, int box_h, int box_n, int estride, CUtensorMapSwizzle swz, const char* what, bool f16) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, f16 ? 1u : 2u};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)plane_elems * 2};
   cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), (cuuint32_t)box_n, 1};
   cuuint32_t estr[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     b200r_set_error("cuTensorMapEncodeTiled(%s) failed: %d (N=%d H=%d W=%d C=%d box %d,%d,%d,%d s=%d)", what, (int)r, N, H, W, C, box_n,
                     box_h, box_w, box_c, estride);
@@ -776,22 +807,22 @@ int make_map5(EncodeTiledFn enc, CUtensorMap* m, const uint16_t* base, int C, in
   return B200R_OK;
 }
 
-// 256 x 256 bf16 identity (the B operand of the residual k-blocks), one per device
-uint16_t* g_ident[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+// 256 x 256 identity in bf16 / fp16 (the B operand of the residual k-blocks), one per device and format
+uint16_t* g_ident[8][2] = {};
 std::mutex g_ident_mu;
-int get_identity(const uint16_t** out) {
+int get_identity(const uint16_t** out, bool f16) {
   int dev = 0;
   B200R_CUDA(cudaGetDevice(&dev));
   B200R_CHECK_ARG(dev >= 0 && dev < 8, "device index out of range");
   std::lock_guard<std::mutex> lk(g_ident_mu);
-  if (!g_ident[dev]) {  // first use per device: blocking copy (not capturable)
+  if (!g_ident[dev][f16]) {  // first use per device: blocking copy (not capturable)
     static uint16_t h[256 * 256];
     memset(h, 0, sizeof(h));
-    for (int i = 0; i < 256; ++i) h[i * 256 + i] = 0x3F80;   // bf16 1.0
-    B200R_CUDA(cudaMalloc(&g_ident[dev], sizeof(h)));
-    B200R_CUDA(cudaMemcpy(g_ident[dev], h, sizeof(h), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 256; ++i) h[i * 256 + i] = f16 ? 0x3C00 : 0x3F80;   // 1.0
+    B200R_CUDA(cudaMalloc(&g_ident[dev][f16], sizeof(h)));
+    B200R_CUDA(cudaMemcpy(g_ident[dev][f16], h, sizeof(h), cudaMemcpyHostToDevice));
   }
-  *out = g_ident[dev];
+  *out = g_ident[dev][f16];
   return B200R_OK;
 }
 
@@ -804,26 +835,26 @@ int gemm_opts() {
   return v;
 }
 
-int finish_maps(EncodeTiledFn enc, GemmMaps* m, GemmParams* p, const uint16_t* res, uint16_t* y, size_t ycount, int BN) {
+int finish_maps(EncodeTiledFn enc, GemmMaps* m, GemmParams* p, const uint16_t* res, uint16_t* y, size_t ycount, int BN, bool f16) {
   p->tma_store = 0;
   p->res_mma = 0;
   m->r = m->b; m->i = m->b; m->y = m->b;   // placeholders (never dereferenced unless the flag is set)
   if (y && p->Cout % 8 == 0 && !(gemm_opts() & 1)) {
-    int rc = make_map5(enc, &m->y, y, p->Cout, p->Wo, p->Ho, p->N, ycount, 32, p->bw, p->bh, p->bn, 1, CU_TENSOR_MAP_SWIZZLE_64B, "Y");
+    int rc = make_map5(enc, &m->y, y, p->Cout, p->Wo, p->Ho, p->N, ycount, 32, p->bw, p->bh, p->bn, 1, CU_TENSOR_MAP_SWIZZLE_64B, "Y", f16);
     if (rc) return rc;
     p->tma_store = 1;
   }
   if (res && !p->scale && p->Cout % 8 == 0 && !(gemm_opts() & 2)) {
-    int rc = make_map5(enc, &m->r, res, p->Cout, p->Wo, p->Ho, p->N, ycount, BK, p->bw, p->bh, p->bn, 1, CU_TENSOR_MAP_SWIZZLE_128B, "R");
+    int rc = make_map5(enc, &m->r, res, p->Cout, p->Wo, p->Ho, p->N, ycount, BK, p->bw, p->bh, p->bn, 1, CU_TENSOR_MAP_SWIZZLE_128B, "R", f16);
     if (rc) return rc;
     const uint16_t* ident = nullptr;
-    rc = get_identity(&ident);
+    rc = get_identity(&ident, f16);
     if (rc) return rc;
     cuuint64_t dims[2] = {256, 256};
     cuuint64_t strides[1] = {512};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&m->i, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(ident), dims, strides, box, estr,
+    CUresult r = enc(&m->i, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(ident), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(identity) failed: %d", (int)r); return B200R_ECUDA; }
@@ -859,7 +890,9 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
   B200R_CHECK_ARG(x && wgt && (y || y_f32), "null pointer");
   // K tails (Cin % 64 != 0) ride on TMA out-of-bounds zero fill of the activation's channel dimension
   B200R_CHECK_ARG(Cin % 8 == 0, "cin (%d) must be a multiple of 8 (16-byte TMA strides)", Cin);
-  B200R_CHECK_ARG(passes == 1 || passes == 3, "passes must be 1 or 3");
+  B200R_CHECK_ARG(passes == 1 || passes == 3 || passes == B200R_PASSES_F16, "passes must be 1, 3 or B200R_PASSES_F16");
+  const bool f16 = (passes == B200R_PASSES_F16);
+  if (f16) passes = 1;
   B200R_CHECK_ARG(stride >= 1 && stride <= 8 && KH >= 1 && KW >= 1 && pad >= 0, "bad conv geometry");
   EncodeTiledFn enc = get_encode();
   if (!enc) { b200r_set_error("cuTensorMapEncodeTiled not available from the driver"); return B200R_ECUDA; }
@@ -883,37 +916,41 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
   p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
   p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.cin_blocks = (Cin + 63) / 64; p.cin = Cin;
   p.passes = passes; p.act = act; p.scale = scale; p.bias = bias;
-  p.res_hi = res; p.res_lo = res ? res + ycount : nullptr;
+  p.res_hi = res; p.res_lo = (res && !f16) ? res + ycount : nullptr;
   p.mask_hi = mask;
-  p.y_hi = y; p.y_lo = y ? y + ycount : nullptr; p.y_f32 = y_f32;
+  p.y_hi = y; p.y_lo = (y && !f16) ? y + ycount : nullptr; p.y_f32 = y_f32;
 
   GemmMaps m;
   {
-    int rc = make_map5(enc, &m.a, x, Cin, W, H, N, xcount, BK, p.bw, p.bh, p.bn, stride, CU_TENSOR_MAP_SWIZZLE_128B, "A");
+    int rc = make_map5(enc, &m.a, x, Cin, W, H, N, xcount, BK, p.bw, p.bh, p.bn, stride, CU_TENSOR_MAP_SWIZZLE_128B, "A", f16);
     if (rc) return rc;
   }
   {
     const cuuint64_t K = (cuuint64_t)KH * KW * Cin;
-    cuuint64_t dims[3] = {K, (cuuint64_t)Cout, 2};
+    cuuint64_t dims[3] = {K, (cuuint64_t)Cout, f16 ? 1u : 2u};
     cuuint64_t strides[2] = {K * 2, (cuuint64_t)wcount * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&m.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
+    CUresult r = enc(&m.b, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(B) failed: %d (Cout=%d K=%llu)", (int)r, Cout, (unsigned long long)K); return B200R_ECUDA; }
   }
   {
-    int rc = finish_maps(enc, &m, &p, res, y, ycount, BN);
+    int rc = finish_maps(enc, &m, &p, res, y, ycount, BN, f16);
     if (rc) return rc;
   }
-  if (BN == 256) return launch<256, 0>(m, p, s);
-  return BN == 64 ? launch<64, 0>(m, p, s) : launch<128, 0>(m, p, s);
+  if (f16) {
+    if (BN == 256) return launch<256, 0, true>(m, p, s);
+    return BN == 64 ? launch<64, 0, true>(m, p, s) : launch<128, 0, true>(m, p, s);
+  }
+  if (BN == 256) return launch<256, 0, false>(m, p, s);
+  return BN == 64 ? launch<64, 0, false>(m, p, s) : launch<128, 0, false>(m, p, s);
 }
 
 // ---- fused stem ---------------------------------------------------------------------------------
 struct StemLut { uint32_t* d = nullptr; float key[6] = {0, 0, 0, 0, 0, 0}; };
-StemLut g_stem_lut[8];
+StemLut g_stem_lut[8][2];
 std::mutex g_stem_mu;
 
 uint16_t host_bf16(float v) {
@@ -929,12 +966,14 @@ float host_bf16_to_f32(uint16_t b) {
   return f;
 }
 
-int get_stem_lut(const float* mean, const float* stdv, const uint32_t** out) {
+uint16_t host_f16(float v) { return __half_as_ushort(__float2half_rn(v)); }
+
+int get_stem_lut(const float* mean, const float* stdv, const uint32_t** out, bool f16) {
   int dev = 0;
   B200R_CUDA(cudaGetDevice(&dev));
   B200R_CHECK_ARG(dev >= 0 && dev < 8, "device index out of range");
   std::lock_guard<std::mutex> lk(g_stem_mu);
-  StemLut& L = g_stem_lut[dev];
+  StemLut& L = g_stem_lut[dev][f16];
   bool same = L.d != nullptr;
   for (int i = 0; i < 3 && same; ++i) same = (L.key[i] == mean[i]) && (L.key[3 + i] == stdv[i]);
   if (!same) {  // first use per device (or new constants): host table + blocking copy (not capturable)
@@ -942,7 +981,7 @@ int get_stem_lut(const float* mean, const float* stdv, const uint32_t** out) {
     for (int c = 0; c < 3; ++c)
       for (int b = 0; b < 256; ++b) {
         const float v = ((float)b / 255.0f - mean[c]) / stdv[c];   // ToTensor + Normalize in fp32
-        const uint16_t hi = host_bf16(v), lo = host_bf16(v - host_bf16_to_f32(hi));
+        const uint16_t hi = f16 ? host_f16(v) : host_bf16(v), lo = f16 ? (uint16_t)0 : host_bf16(v - host_bf16_to_f32(hi));
         h[c * 256 + b] = (uint32_t)hi | ((uint32_t)lo << 16);
       }
     if (!L.d) B200R_CUDA(cudaMalloc(&L.d, sizeof(h)));
@@ -962,11 +1001,13 @@ static int stem_impl(const void* img, bool f32, const uint16_t* wgt, const float
                      b200r_stream_t stream) {
   B200R_CHECK_ARG(img && wgt && y && mean_host && std_host, "null pointer");
   B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "bad shape");
-  B200R_CHECK_ARG(passes == 1 || passes == 3, "passes must be 1 or 3");
+  B200R_CHECK_ARG(passes == 1 || passes == 3 || passes == B200R_PASSES_F16, "passes must be 1, 3 or B200R_PASSES_F16");
+  const bool f16 = (passes == B200R_PASSES_F16);
+  if (f16) passes = 1;
   EncodeTiledFn enc = get_encode();
   if (!enc) { b200r_set_error("cuTensorMapEncodeTiled not available from the driver"); return B200R_ECUDA; }
   const uint32_t* lut = nullptr;
-  int rc = f32 ? B200R_OK : get_stem_lut(mean_host, std_host, &lut);   // uint8: ToTensor + Normalize + split as a 3x256 table
+  int rc = f32 ? B200R_OK : get_stem_lut(mean_host, std_host, &lut, f16);   // uint8: ToTensor + Normalize + split as a 3x256 table
   if (rc) return rc;
   const int Ho = h / 2, Wo = w / 2, Cout = 64, K = 192;
   GemmParams p{};
@@ -977,25 +1018,26 @@ static int stem_impl(const void* img, bool f32, const uint16_t* wgt, const float
   p.N = n; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
   p.KH = 1; p.KW = 1; p.stride = 1; p.pad = 0; p.cin_blocks = K / 64; p.cin = K;
   p.passes = passes; p.act = act; p.scale = scale; p.bias = bias;
-  p.y_hi = y; p.y_lo = y + (size_t)p.M_total * Cout;
+  p.y_hi = y; p.y_lo = f16 ? nullptr : y + (size_t)p.M_total * Cout;
   p.img = static_cast<const uint8_t*>(img); p.lut = lut; p.H_in = h; p.W_in = w;
   for (int i = 0; i < 3; ++i) { p.nmean[i] = mean_host[i]; p.nstd[i] = std_host[i]; }
   GemmMaps m;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, 2};
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, f16 ? 1u : 2u};
     cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)Cout * K * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, 64, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&m.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
+    CUresult r = enc(&m.b, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(stem B) failed: %d", (int)r); return B200R_ECUDA; }
   }
   m.a = m.b;
   p.stem_Ho = Ho; p.stem_Wo = Wo;   // the producer decodes (n, oy, ox) from the real output geometry
-  rc = finish_maps(enc, &m, &p, nullptr, y, (size_t)p.M_total * Cout, 64);
+  rc = finish_maps(enc, &m, &p, nullptr, y, (size_t)p.M_total * Cout, 64, f16);
   if (rc) return rc;
-  return f32 ? launch<64, 2>(m, p, as_stream(stream)) : launch<64, 1>(m, p, as_stream(stream));
+  if (f16) return f32 ? launch<64, 2, true>(m, p, as_stream(stream)) : launch<64, 1, true>(m, p, as_stream(stream));
+  return f32 ? launch<64, 2, false>(m, p, as_stream(stream)) : launch<64, 1, false>(m, p, as_stream(stream));
 }
 
 int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* scale, const float* bias, uint16_t* y,

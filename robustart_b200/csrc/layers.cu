@@ -5,9 +5,17 @@
 //   maxpool 3x3 s2 p1                   : resnet_official.py:227
 //   global average pool                 : resnet_official.py:238
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 constexpr int kThreads = 256;
+
+// ---- fp16 single-plane helpers ------------------------------------------------------------------
+__device__ __forceinline__ float2 h2_to_f2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+__device__ __forceinline__ uint32_t f2_to_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }
 
@@ -140,6 +148,71 @@ __global__ void __launch_bounds__(kThreads) avgpool_kernel(const uint4* __restri
   }
 }
 
+// ---- fp16 twins ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) f32_to_f16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t count4,
+                                                               float scale) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < count4; i += (size_t)gridDim.x * kThreads) {
+    const float4 v = ld_stream_f4(in + i);
+    // saturate instead of overflowing to inf (a scaled loss gradient must stay finite)
+    auto c = [scale](float x) { return fminf(fmaxf(x * scale, -65504.f), 65504.f); };
+    out[i] = make_uint2(f2_to_h2(c(v.x), c(v.y)), f2_to_h2(c(v.z), c(v.w)));
+  }
+}
+__global__ void __launch_bounds__(kThreads) f16_to_f32_kernel(const uint2* __restrict__ in, float4* __restrict__ out, size_t count4,
+                                                               float scale) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < count4; i += (size_t)gridDim.x * kThreads) {
+    const uint2 h = in[i];
+    const float2 a = h2_to_f2(h.x), b = h2_to_f2(h.y);
+    out[i] = make_float4(a.x * scale, a.y * scale, b.x * scale, b.y * scale);
+  }
+}
+
+// maxpool 3x3 s2 p1 on one fp16 plane: packed half2 maxima (HMNMX2), 8 channels per thread
+__global__ void __launch_bounds__(kThreads) maxpool_f16_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w,
+                                                                int c8, int ho, int wo) {
+  const size_t total = (size_t)n * ho * wo * c8;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int cc = (int)(t % c8);
+    const size_t pix = t / c8;
+    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), im = (int)(pix / ((size_t)wo * ho));
+    const __half2 ninf = __half2half2(__ushort_as_half((unsigned short)0xFC00));
+    __half2 best[4] = {ninf, ninf, ninf, ninf};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= w) continue;
+        const uint4 a = __ldg(x + (((size_t)im * h + iy) * w + ix) * c8 + cc);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) best[j] = __hmax2(best[j], *reinterpret_cast<const __half2*>(&aw[j]));
+      }
+    }
+    y[t] = make_uint4(*reinterpret_cast<uint32_t*>(&best[0]), *reinterpret_cast<uint32_t*>(&best[1]),
+                      *reinterpret_cast<uint32_t*>(&best[2]), *reinterpret_cast<uint32_t*>(&best[3]));
+  }
+}
+
+// global average pool on one fp16 plane: one warp per (image, 8-channel chunk), fp32 sums
+__global__ void __launch_bounds__(kThreads) avgpool_f16_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int hw, int c8) {
+  const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n * c8) return;
+  const int im = warp / c8, cc = warp - im * c8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = lane; p < hw; p += 32) {
+    const uint4 a = __ldg(x + ((size_t)im * hw + p) * c8 + cc);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 v = h2_to_f2(aw[j]); s[2 * j] += v.x; s[2 * j + 1] += v.y; }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = warp_sum(s[j]) / (float)hw;
+  if (lane == 0) y[warp] = make_uint4(f2_to_h2(s[0], s[1]), f2_to_h2(s[2], s[3]), f2_to_h2(s[4], s[5]), f2_to_h2(s[6], s[7]));
+}
+
 inline unsigned grid_for(size_t items) {
   size_t b = (items + kThreads - 1) / kThreads;
   size_t cap = (size_t)b200r_num_sms() * 16;
@@ -165,6 +238,47 @@ int b200r_merge_f32(const uint16_t* planes, float* out, size_t count, b200r_stre
   if (!count) return B200R_OK;
   merge_kernel<<<grid_for(count / 4), kThreads, 0, as_stream(stream)>>>(
       reinterpret_cast<const uint2*>(planes), reinterpret_cast<const uint2*>(planes + count), reinterpret_cast<float4*>(out), count / 4);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_f32_to_f16(const float* in, uint16_t* out, size_t count, float scale, b200r_stream_t stream) {
+  B200R_CHECK_ARG(in && out, "null pointer");
+  B200R_CHECK_ARG(count % 4 == 0, "count must be a multiple of 4");
+  if (!count) return B200R_OK;
+  f32_to_f16_kernel<<<grid_for(count / 4), kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(in),
+                                                                              reinterpret_cast<uint2*>(out), count / 4, scale);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_f16_to_f32(const uint16_t* in, float* out, size_t count, float scale, b200r_stream_t stream) {
+  B200R_CHECK_ARG(in && out, "null pointer");
+  B200R_CHECK_ARG(count % 4 == 0, "count must be a multiple of 4");
+  if (!count) return B200R_OK;
+  f16_to_f32_kernel<<<grid_for(count / 4), kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const uint2*>(in),
+                                                                              reinterpret_cast<float4*>(out), count / 4, scale);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_maxpool3x3s2_nhwc_f16(const uint16_t* x, uint16_t* y, int n, int h, int w, int c, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && y, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c % 8 == 0, "c must be a multiple of 8");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const size_t cout = (size_t)n * ho * wo * c;
+  maxpool_f16_kernel<<<grid_for(cout / 8), kThreads, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y),
+                                                                              n, h, w, c / 8, ho, wo);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_global_avgpool_nhwc_f16(const uint16_t* x, uint16_t* y, int n, int hw, int c, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && y, "null pointer");
+  B200R_CHECK_ARG(n > 0 && hw > 0 && c % 8 == 0, "c must be a multiple of 8");
+  const int warps = n * (c / 8);
+  avgpool_f16_kernel<<<(warps * 32 + kThreads - 1) / kThreads, kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), n, hw, c / 8);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }

@@ -109,10 +109,14 @@ def _strip_prefix(sd):
     return out
 
 
+GRAD_SCALE_F16 = 4096.0      # loss scale of the fp16 input-gradient pass (|dlogits| <= 1 for CE: no overflow)
+
+
 class _ConvBN:
     """conv (bias-free) + folded BN: weight planes [2, Cout, KH, KW, Cin], scale/bias float32 [Cout]."""
 
-    def __init__(self, sd, conv, bn, device, stride, pad):
+    def __init__(self, sd, conv, bn, device, stride, pad, f16=False):
+        self.f16 = f16
         w = sd[conv + ".weight"].float()
         gamma, beta = sd[bn + ".weight"].double(), sd[bn + ".bias"].double()
         mean, var = sd[bn + ".running_mean"].double(), sd[bn + ".running_var"].double()
@@ -122,7 +126,7 @@ class _ConvBN:
         self.scale = None
         self.bias = (beta - mean * scale).float().to(device).contiguous()
         w = (w.double() * scale.view(-1, 1, 1, 1)).float()
-        self.w = ops.split_f32(w.permute(0, 2, 3, 1).contiguous().to(device))
+        self.w = ops.to_planes(w.permute(0, 2, 3, 1).contiguous().to(device), f16)
         self.stride, self.pad = stride, pad
         self.k = w.shape[-1]
         self._w_folded, self._w_dgrad, self._device = w, None, device
@@ -134,7 +138,7 @@ class _ConvBN:
         gradient flows into (ReLU backward fused into the GEMM epilogue)."""
         if self._w_dgrad is None:
             wt = self._w_folded.flip(2, 3).permute(1, 2, 3, 0).contiguous()       # [cin, ky', kx', cout]
-            self._w_dgrad = ops.split_f32(wt.to(self._device))
+            self._w_dgrad = ops.to_planes(wt.to(self._device), self.f16)
         if self.stride not in (1, 2):
             raise NotImplementedError("dgrad for stride %d" % self.stride)
         if self.stride == 2 and self.k == 1:
@@ -154,11 +158,13 @@ class ResNet:
     def __init__(self, arch: str, state_dict: Dict[str, torch.Tensor], device, passes: int = 3):
         arch = ARCH_ALIASES.get(arch, arch)
         self.arch, self.device, self.passes = arch, torch.device(device), passes
+        # passes = ops.PASSES_F16: activations / weights are one fp16 plane, one MMA per product (include/b200r.h)
+        self.f16 = f16 = (passes == ops.PASSES_F16)
         kind, layers = _RESNET_CFG[arch]
         sd = _strip_prefix(state_dict)
         dev = self.device
         # stem: 7x7/s2 as a GEMM over im2col'd patches, K = (ky, 8 kx slots, c) = 168 padded to 192
-        self.stem_w = ops.split_f32(ops.pack_stem_weight(sd["conv1.weight"]).to(dev).contiguous())
+        self.stem_w = ops.to_planes(ops.pack_stem_weight(sd["conv1.weight"]).to(dev).contiguous(), f16)
         g, b = sd["bn1.weight"].double(), sd["bn1.bias"].double()
         m, v = sd["bn1.running_mean"].double(), sd["bn1.running_var"].double()
         s = g / torch.sqrt(v + BN_EPS)
@@ -170,16 +176,16 @@ class ResNet:
                 stride = 2 if (bi == 0 and li > 0) else 1
                 blk = {"kind": kind}
                 if kind == "bottleneck":
-                    blk["c1"] = _ConvBN(sd, p + ".conv1", p + ".bn1", dev, 1, 0)
-                    blk["c2"] = _ConvBN(sd, p + ".conv2", p + ".bn2", dev, stride, 1)
-                    blk["c3"] = _ConvBN(sd, p + ".conv3", p + ".bn3", dev, 1, 0)
+                    blk["c1"] = _ConvBN(sd, p + ".conv1", p + ".bn1", dev, 1, 0, f16)
+                    blk["c2"] = _ConvBN(sd, p + ".conv2", p + ".bn2", dev, stride, 1, f16)
+                    blk["c3"] = _ConvBN(sd, p + ".conv3", p + ".bn3", dev, 1, 0, f16)
                 else:
-                    blk["c1"] = _ConvBN(sd, p + ".conv1", p + ".bn1", dev, stride, 1)
-                    blk["c2"] = _ConvBN(sd, p + ".conv2", p + ".bn2", dev, 1, 1)
+                    blk["c1"] = _ConvBN(sd, p + ".conv1", p + ".bn1", dev, stride, 1, f16)
+                    blk["c2"] = _ConvBN(sd, p + ".conv2", p + ".bn2", dev, 1, 1, f16)
                 if (p + ".downsample.0.weight") in sd:
-                    blk["down"] = _ConvBN(sd, p + ".downsample.0", p + ".downsample.1", dev, stride, 0)
+                    blk["down"] = _ConvBN(sd, p + ".downsample.0", p + ".downsample.1", dev, stride, 0, f16)
                 self.blocks.append(blk)
-        self.fc_w = ops.split_f32(sd["fc.weight"].float().to(dev).contiguous())
+        self.fc_w = ops.to_planes(sd["fc.weight"].float().to(dev).contiguous(), f16)
         self.fc_b = sd["fc.bias"].float().to(dev).contiguous()
         self.num_classes = self.fc_w.shape[1]
         self._graphs = {}
@@ -219,7 +225,7 @@ class ResNet:
         if w <= 256 and w % 16 == 0 and h % 2 == 0:
             return ops.stem_conv7x7_f32(x01.contiguous(), self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P)
         cols = ops.stem_im2col(x01)
-        return ops.linear(cols, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P).view(2, n, h // 2, w // 2, 64)
+        return ops.linear(cols, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P).view(-1, n, h // 2, w // 2, 64)
 
     __call__ = forward
 
@@ -271,12 +277,16 @@ class ResNet:
         """d loss / d x01 (float32 NCHW) from d loss / d logits (float32 [n, classes]) and forward_saved()'s state.
         Only input gradients are formed (what value_and_grad / autograd.grad(loss, x) return to the attacks)."""
         P = self.passes if passes is None else passes
+        f16 = self.f16
         n, h, w = saved["shape"]
         if not hasattr(self, "_fc_wt"):
-            self._fc_wt = ops.split_f32(ops.merge_f32(self.fc_w).t().contiguous())          # [2048|512, classes]
-            wt = ops.merge_f32(self.stem_w) * self.stem_scale.view(-1, 1)                    # BN scale folded, [64, 192]
-            self._stem_wt = ops.split_f32(wt.t().contiguous())                               # [192, 64]
-        g = ops.linear(ops.split_f32(dlogits.contiguous()), self._fc_wt, passes=P)           # [2, n, c]
+            self._fc_wt = ops.to_planes(ops.from_planes(self.fc_w).t().contiguous(), f16)    # [2048|512, classes]
+            wt = ops.from_planes(self.stem_w) * self.stem_scale.view(-1, 1)                  # BN scale folded, [64, 192]
+            self._stem_wt = ops.to_planes(wt.t().contiguous(), f16)                          # [192, 64]
+        # fp16 planes: the pass runs on S * dlogits (gradients of a classifier sit at 1e-4 .. 1e-10, below fp16's
+        # normal range) and 1/S is folded into the last kernel; the attacks only use the sign / direction anyway
+        S = GRAD_SCALE_F16 if f16 else 1.0
+        g = ops.linear(ops.to_planes(dlogits.contiguous(), f16, S), self._fc_wt, passes=P)   # [P, n, c]
         last = saved["blocks"][-1][-1]
         g = ops.global_avgpool_bwd(g, last.shape[2], last.shape[3])
         g = ops.relu_bwd(g, last)                        # the last block's output ReLU; all others are fused
@@ -285,8 +295,8 @@ class ResNet:
             g = self.block_backward(self.blocks[i], saved["blocks"][i], g, P, in_mask=in_mask, g_is_masked=True)
         s0 = saved["stem"]
         g = ops.relu_bwd(ops.maxpool3x3s2_bwd(s0, g), s0)
-        dcols = ops.linear(g.view(2, -1, 64), self._stem_wt, passes=P)                       # [2, n*ho*wo, 192]
-        return ops.stem_col2im(dcols, n, h, w)
+        dcols = ops.linear(g.view(g.shape[0], -1, 64), self._stem_wt, passes=P)              # [P, n*ho*wo, 192]
+        return ops.stem_col2im(dcols, n, h, w, unscale=1.0 / S)
 
     def loss_and_input_grad(self, x01: torch.Tensor, labels: torch.Tensor, reduction: str = "sum"):
         """(per-sample CE losses, d CE / d x01): the one call an attack step makes."""

@@ -244,17 +244,50 @@ def merge_f32(planes: torch.Tensor) -> torch.Tensor:
     return out
 
 
+PASSES_F16 = 16      # include/b200r.h B200R_PASSES_F16: tensors are ONE plane of fp16 ([1, ...] int16) instead of two bf16 planes
+
+
+def to_planes(x: torch.Tensor, f16: bool = False, scale: float = 1.0) -> torch.Tensor:
+    """float32 tensor -> the activation / weight format of the chosen precision: split-bf16 planes [2, *S] or one fp16
+    plane [1, *S] (optionally pre-scaled: the loss scaling of the fp16 input-gradient pass)."""
+    if not f16:
+        assert scale == 1.0
+        return split_f32(x)
+    _need_cuda(x, torch.float32, "x")
+    out = torch.empty((1,) + tuple(x.shape), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_f32_to_f16(x.data_ptr(), out.data_ptr(), x.numel(), scale, _stream()))
+    return out
+
+
+def from_planes(planes: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    if planes.shape[0] == 2:
+        assert scale == 1.0
+        return merge_f32(planes)
+    _need_cuda(planes, torch.int16, "planes")
+    out = torch.empty(tuple(planes.shape[1:]), dtype=torch.float32, device=planes.device)
+    with torch.cuda.device(planes.device):
+        _lib.check(_lib.load().b200r_f16_to_f32(planes.data_ptr(), out.data_ptr(), out.numel(), scale, _stream()))
+    return out
+
+
+def _passes_for(x, passes):
+    """A one-plane tensor is fp16 by construction: the contraction must run in B200R_PASSES_F16 mode."""
+    return PASSES_F16 if x.shape[0] == 1 else passes
+
+
 def conv2d_nhwc(x, wgt, scale=None, bias=None, res=None, *, stride=1, pad=0, act=None, passes=3, out=None,
                 out_f32=None, want_planes=True):
-    """x: planes [2,n,h,w,cin]; wgt: planes [2,cout,kh,kw,cin]; returns planes [2,n,ho,wo,cout]."""
+    """x: planes [P,n,h,w,cin]; wgt: planes [P,cout,kh,kw,cin]; returns planes [P,n,ho,wo,cout] (P = 2 split-bf16, 1 fp16)."""
     _need_cuda(x, torch.int16, "x")
     _need_cuda(wgt, torch.int16, "wgt")
-    _, n, h, w, cin = x.shape
+    P, n, h, w, cin = x.shape
     _, cout, kh, kw, cin2 = wgt.shape
-    assert cin == cin2
+    assert cin == cin2 and wgt.shape[0] == P and (res is None or res.shape[0] == P)
+    passes = _passes_for(x, passes)
     ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
     if out is None and want_planes:
-        out = torch.empty((2, n, ho, wo, cout), dtype=torch.int16, device=x.device)
+        out = torch.empty((P, n, ho, wo, cout), dtype=torch.int16, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().b200r_conv2d_nhwc(x.data_ptr(), wgt.data_ptr(), _ptr(scale), _ptr(bias), _ptr(res),
                                                  _ptr(out), _ptr(out_f32), n, h, w, cin, cout, kh, kw, stride, pad,
@@ -263,14 +296,16 @@ def conv2d_nhwc(x, wgt, scale=None, bias=None, res=None, *, stride=1, pad=0, act
 
 
 def linear(x, wgt, scale=None, bias=None, res=None, *, act=None, passes=3, out=None, out_f32=None, want_planes=True):
-    """x: planes [2,m,k]; wgt: planes [2,nout,k]."""
+    """x: planes [P,m,k]; wgt: planes [P,nout,k]."""
     _need_cuda(x, torch.int16, "x")
     _need_cuda(wgt, torch.int16, "wgt")
     m, k = x.shape[1], x.shape[-1]
     m = x[0].numel() // k
     nout = wgt.shape[1]
+    assert wgt.shape[0] == x.shape[0] and (res is None or res.shape[0] == x.shape[0])
+    passes = _passes_for(x, passes)
     if out is None and want_planes:
-        out = torch.empty((2, m, nout), dtype=torch.int16, device=x.device)
+        out = torch.empty((x.shape[0], m, nout), dtype=torch.int16, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().b200r_linear(x.data_ptr(), wgt.data_ptr(), _ptr(scale), _ptr(bias), _ptr(res), _ptr(out),
                                             _ptr(out_f32), m, k, nout, ACT[act], passes, _stream()))
@@ -306,11 +341,12 @@ def pack_stem_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 def stem_conv7x7_u8(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
-    """Fused 7x7/s2 stem from raw uint8 NHWC pixels: planes [2, n, h/2, w/2, 64]."""
+    """Fused 7x7/s2 stem from raw uint8 NHWC pixels: planes [P, n, h/2, w/2, 64]."""
     _need_cuda(img, torch.uint8, "img")
     n, h, w, _ = img.shape
+    passes = _passes_for(wgt, passes)
     if out is None:
-        out = torch.empty((2, n, h // 2, w // 2, 64), dtype=torch.int16, device=img.device)
+        out = torch.empty((wgt.shape[0], n, h // 2, w // 2, 64), dtype=torch.int16, device=img.device)
     with torch.cuda.device(img.device):
         _lib.check(_lib.load().b200r_stem_conv7x7_u8(img.data_ptr(), wgt.data_ptr(), _ptr(scale), _ptr(bias), out.data_ptr(),
                                                      n, h, w, _lib.f3(mean), _lib.f3(std), ACT[act], passes, _stream()))
@@ -318,11 +354,12 @@ def stem_conv7x7_u8(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGENE
 
 
 def stem_conv7x7_f32(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
-    """Fused 7x7/s2 stem from a float32 NCHW image in [0,1] (attack iterates): planes [2, n, h/2, w/2, 64]."""
+    """Fused 7x7/s2 stem from a float32 NCHW image in [0,1] (attack iterates): planes [P, n, h/2, w/2, 64]."""
     _need_cuda(img, torch.float32, "img")
     n, _, h, w = img.shape
+    passes = _passes_for(wgt, passes)
     if out is None:
-        out = torch.empty((2, n, h // 2, w // 2, 64), dtype=torch.int16, device=img.device)
+        out = torch.empty((wgt.shape[0], n, h // 2, w // 2, 64), dtype=torch.int16, device=img.device)
     with torch.cuda.device(img.device):
         _lib.check(_lib.load().b200r_stem_conv7x7_f32(img.data_ptr(), wgt.data_ptr(), _ptr(scale), _ptr(bias), out.data_ptr(),
                                                       n, h, w, _lib.f3(mean), _lib.f3(std), ACT[act], passes, _stream()))
@@ -330,21 +367,23 @@ def stem_conv7x7_f32(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGEN
 
 
 def maxpool3x3s2(x, out=None):
-    _, n, h, w, c = x.shape
+    P, n, h, w, c = x.shape
     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     if out is None:
-        out = torch.empty((2, n, ho, wo, c), dtype=torch.int16, device=x.device)
+        out = torch.empty((P, n, ho, wo, c), dtype=torch.int16, device=x.device)
+    fn = _lib.load().b200r_maxpool3x3s2_nhwc_f16 if P == 1 else _lib.load().b200r_maxpool3x3s2_nhwc
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().b200r_maxpool3x3s2_nhwc(x.data_ptr(), out.data_ptr(), n, h, w, c, _stream()))
+        _lib.check(fn(x.data_ptr(), out.data_ptr(), n, h, w, c, _stream()))
     return out
 
 
 def global_avgpool(x, out=None):
-    _, n, h, w, c = x.shape
+    P, n, h, w, c = x.shape
     if out is None:
-        out = torch.empty((2, n, c), dtype=torch.int16, device=x.device)
+        out = torch.empty((P, n, c), dtype=torch.int16, device=x.device)
+    fn = _lib.load().b200r_global_avgpool_nhwc_f16 if P == 1 else _lib.load().b200r_global_avgpool_nhwc
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().b200r_global_avgpool_nhwc(x.data_ptr(), out.data_ptr(), n, h * w, c, _stream()))
+        _lib.check(fn(x.data_ptr(), out.data_ptr(), n, h * w, c, _stream()))
     return out
 
 
@@ -354,9 +393,11 @@ def global_avgpool(x, out=None):
 def conv2d_dgrad(dy, wgt_t, res=None, mask=None, *, pad=0, passes=3):
     """dx = [mask > 0] * (conv_s1(dy, wgt_t) + res); dy planes [2,n,h,w,cdy], wgt_t planes [2,cdx,kh,kw,cdy], mask = the
     post-ReLU activation planes the gradient flows into (only its hi plane is read)."""
-    _, n, h, w, cdy = dy.shape
+    P, n, h, w, cdy = dy.shape
     cdx, kh, kw = wgt_t.shape[1], wgt_t.shape[2], wgt_t.shape[3]
-    out = torch.empty((2, n, h, w, cdx), dtype=torch.int16, device=dy.device)
+    assert wgt_t.shape[0] == P
+    passes = _passes_for(dy, passes)
+    out = torch.empty((P, n, h, w, cdx), dtype=torch.int16, device=dy.device)
     if mask is not None:
         assert mask.shape == out.shape, (mask.shape, out.shape)
     if res is not None:
@@ -373,16 +414,18 @@ def relu_bwd(dy, act, add=None, out=None):
     count = dy[0].numel()
     if out is None:
         out = torch.empty_like(dy)
+    fn = _lib.load().b200r_relu_bwd_f16 if dy.shape[0] == 1 else _lib.load().b200r_relu_bwd
     with torch.cuda.device(dy.device):
-        _lib.check(_lib.load().b200r_relu_bwd(dy.data_ptr(), act.data_ptr(), _ptr(add), out.data_ptr(), count, _stream()))
+        _lib.check(fn(dy.data_ptr(), act.data_ptr(), _ptr(add), out.data_ptr(), count, _stream()))
     return out
 
 
 def dilate2(x):
-    _, n, h, w, c = x.shape
-    out = torch.empty((2, n, 2 * h, 2 * w, c), dtype=torch.int16, device=x.device)
+    P, n, h, w, c = x.shape
+    out = torch.empty((P, n, 2 * h, 2 * w, c), dtype=torch.int16, device=x.device)
+    fn = _lib.load().b200r_dilate2_nhwc_f16 if P == 1 else _lib.load().b200r_dilate2_nhwc
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().b200r_dilate2_nhwc(x.data_ptr(), out.data_ptr(), n, h, w, c, _stream()))
+        _lib.check(fn(x.data_ptr(), out.data_ptr(), n, h, w, c, _stream()))
     return out
 
 
@@ -391,26 +434,32 @@ def maxpool3x3s2_bwd(x, dy):
     _, n, h, w, c = x.shape
     ws = torch.empty(dy[0].numel(), dtype=torch.uint8, device=x.device)
     dx = torch.empty_like(x)
+    fn = _lib.load().b200r_maxpool3x3s2_bwd_nhwc_f16 if x.shape[0] == 1 else _lib.load().b200r_maxpool3x3s2_bwd_nhwc
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().b200r_maxpool3x3s2_bwd_nhwc(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                           n, h, w, c, _stream()))
+        _lib.check(fn(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), ws.data_ptr(), ws.numel(), n, h, w, c, _stream()))
     return dx
 
 
 def global_avgpool_bwd(dy, h, w):
-    _, n, c = dy.shape
-    dx = torch.empty((2, n, h, w, c), dtype=torch.int16, device=dy.device)
+    P, n, c = dy.shape
+    dx = torch.empty((P, n, h, w, c), dtype=torch.int16, device=dy.device)
+    fn = _lib.load().b200r_global_avgpool_bwd_nhwc_f16 if P == 1 else _lib.load().b200r_global_avgpool_bwd_nhwc
     with torch.cuda.device(dy.device):
-        _lib.check(_lib.load().b200r_global_avgpool_bwd_nhwc(dy.data_ptr(), dx.data_ptr(), n, h * w, c, _stream()))
+        _lib.check(fn(dy.data_ptr(), dx.data_ptr(), n, h * w, c, _stream()))
     return dx
 
 
-def stem_col2im(dcols, n, h, w, std=IMAGENET_STD, out=None):
-    """dcols planes [2, n*(h/2)*(w/2), 192] -> float32 NCHW gradient w.r.t. the [0,1] image."""
+def stem_col2im(dcols, n, h, w, std=IMAGENET_STD, out=None, unscale: float = 1.0):
+    """dcols planes [P, n*(h/2)*(w/2), 192] -> float32 NCHW gradient w.r.t. the [0,1] image (fp16 planes: times
+    `unscale`, the inverse of the loss scale the pass ran with)."""
     if out is None:
         out = torch.empty((n, 3, h, w), dtype=torch.float32, device=dcols.device)
     with torch.cuda.device(dcols.device):
-        _lib.check(_lib.load().b200r_stem_col2im_f32(dcols.data_ptr(), out.data_ptr(), n, h, w, _lib.f3(std), _stream()))
+        if dcols.shape[0] == 1:
+            _lib.check(_lib.load().b200r_stem_col2im_f32_f16(dcols.data_ptr(), out.data_ptr(), n, h, w, _lib.f3(std), unscale, _stream()))
+        else:
+            assert unscale == 1.0
+            _lib.check(_lib.load().b200r_stem_col2im_f32(dcols.data_ptr(), out.data_ptr(), n, h, w, _lib.f3(std), _stream()))
     return out
 
 

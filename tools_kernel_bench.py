@@ -46,7 +46,9 @@ def main():
     outs = [torch.empty_like(ins[0]) for _ in range(R)]
     res = {}
     names = sys.argv[1:] or ["gaussian_noise", "shot_noise", "impulse_noise", "speckle_noise", "brightness",
-                             "saturate", "contrast", "frost", "fog"]
+                             "saturate", "contrast", "frost", "fog", "pixelate", "jpeg_compression", "gaussian_blur",
+                             "defocus_blur", "zoom_blur", "motion_blur", "snow", "glass_blur", "elastic_transform",
+                             "spatter"]
     for name in names:
         for sev in (1, 3, 5):
             try:

@@ -23,10 +23,11 @@ def main():
     ap.add_argument("--autograd", action="store_true")
     ap.add_argument("--passes-bwd", type=int, default=3)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--passes", type=int, default=3, help="3 = split-bf16, 16 = fp16 single plane")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     sd = nets.random_state_dict(nets.resnet_spec(a.arch), 0)
-    net = nets.build_model(a.arch, sd, device=dev)
+    net = nets.build_model(a.arch, sd, device=dev, passes=a.passes)
     if a.autograd:
         twin = torch_models.build(a.arch, sd).to(dev).eval()
         src = attacks.PyTorchModel(twin, preprocessing=dict(mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, axis=-3))
@@ -51,7 +52,7 @@ def main():
     ms = e0.elapsed_time(e1) / a.reps
     gflop = (2 * a.steps + 1) * FWD_GFLOP[a.arch] * a.n      # k*(fwd + dgrad) + 1 fwd, SURVEY 8(d)
     print(json.dumps({"loop": "pgd_linf %d-step eval, %s, batch %d" % (a.steps, a.arch, a.n),
-                      "source": "autograd twin" if a.autograd else "native dgrad (passes_bwd=%d)" % a.passes_bwd,
+                      "source": "autograd twin" if a.autograd else "native dgrad (passes=%d)" % a.passes,
                       "ms_per_batch": ms, "images_per_s": a.n / ms * 1e3, "algorithmic_tflops": gflop / ms,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
 

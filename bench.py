@@ -129,7 +129,11 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def gemm_roofline(model, pipe, pk):
+DTYPE = {"f16": "f16 (fp16 operands and activations, fp32 accumulation in TMEM; logits within 1e-3 of the fp32 reference)",
+         "bf16x3": "bf16x3 (split-bf16 operands, fp32 accumulate: fp32-faithful)"}
+
+
+def gemm_roofline(model, pipe, pk, precision):
     """Live per-launch timing of the dominant kernel (tcgen05 implicit GEMM) with CUDA events on the
     launching stream: the forward is re-run eagerly with an event pair around every conv / linear."""
     import torch
@@ -177,7 +181,7 @@ def gemm_roofline(model, pipe, pk):
     finally:
         ops.conv2d_nhwc, ops.linear, ops.stem_conv7x7_u8 = orig_conv, orig_lin, orig_stem
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r1_gemm_traffic_%s.json" % precision)
     if os.path.exists(tp):      # dram__bytes_read+write summed over the same launches, from one ncu capture (profiles/)
         traffic = json.load(open(tp)).get("dram_bytes_per_forward")
     ms = sum(s.elapsed_time(e) for s, e, _ in recs)
@@ -186,11 +190,13 @@ def gemm_roofline(model, pipe, pk):
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     return {"bound": "tensor", "kernel": "gemm_kernel<BN> (tcgen05 implicit GEMM, all %d launches of one forward)" % len(recs),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_note": "bytes per forward (all GEMM launches), ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_gemm_traffic.json",
+            "traffic_note": "bytes per forward (all GEMM launches), ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_gemm_traffic_%s.json" % precision,
             "peak_source": pk["_source"] + ", sustained bf16 (kernel timed inside a long step)",
             "gemm_ms_per_step": ms, "algorithmic_gflop_per_step": flops / 1e9,
-            "note": "algorithmic FLOPs = 2*M*N*K of the fp32 convolution; the split-bf16 scheme issues 3 bf16 MMAs per "
-                    "product, so tensor-pipe FLOP/s are 3x achieved"}
+            "note": ("algorithmic FLOPs = 2*M*N*K of the convolution, one fp16 MMA per product; most 1x1 layers of ResNet-50 are bound by "
+                     "activation traffic, not the tensor pipe (profiles/ layer report)") if precision == "f16" else
+                    ("algorithmic FLOPs = 2*M*N*K of the fp32 convolution; the split-bf16 scheme issues 3 bf16 MMAs per "
+                     "product, so tensor-pipe FLOP/s are 3x achieved")}
 
 
 def corruption_roofline(pipe, inputs, pk):
@@ -249,7 +255,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
 
-    model = nets.build_model("resnet50", device=dev, seed=0)
+    passes = {"f16": 16, "bf16x3": 3}[args.precision]
+    model = nets.build_model("resnet50", device=dev, seed=0, passes=passes)
     pipe = CorruptEvalPipeline(model, BATCH, H, W, seed=1234 + rank)
     g = torch.Generator(device=dev).manual_seed(rank)
     inputs = [torch.randint(0, 256, (BATCH, H, W, 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(R_INPUTS)]
@@ -302,7 +309,7 @@ def run_ours(args):
     if rank == 0:
         value = world * BATCH * args.steps / (dev_ms * 1e-3)
         e2e_v = world * BATCH * args.steps / (e2e_ms * 1e-3)
-        roof = gemm_roofline(model, pipe, pk)
+        roof = gemm_roofline(model, pipe, pk, args.precision)
         roof_c = corruption_roofline(pipe, inputs, pk)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -315,7 +322,7 @@ def run_ours(args):
                              "ResNet-50 forward (%.0f img/s alone)" % (96 / sum(x["noise_s"] for x in r), 96 / sum(x["model_s"] for x in r))}
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate: fp32-faithful)", "data": "synthetic",
+                "vs_baseline": None, "dtype": DTYPE[args.precision], "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "image": "224x224x3 uint8 NHWC",
                            "weights": "synthetic (nets.random_state_dict seed 0)", "parallelism": "dp%d" % world,
                            "l2": "inputs rotate over %d batches = %d MB > 126 MB L2" % (R_INPUTS, R_INPUTS * BATCH * H * W * 3 // 2 ** 20),
@@ -330,13 +337,13 @@ def run_ours(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if world == 1 and not args.no_pgd:
-            line["pgd_loop"] = pgd_loop_report(model, dev, pk)
+            line["pgd_loop"] = pgd_loop_report(model, dev, pk, args.precision)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def pgd_loop_report(model, dev, pk, n=128, steps=10, reps=2):
+def pgd_loop_report(model, dev, pk, precision, n=128, steps=10, reps=2):
     """The second half of the north star, reported beside the headline metric (not part of `value`): the PGD-Linf
     10-step eval loop on ResNet-50, forward + input gradient on the sm_100a kernels, then one
     forward of the adversarial batch + counters.  Algorithmic FLOPs = (2k+1) * 8.18 GFLOP / image."""
@@ -365,8 +372,9 @@ def pgd_loop_report(model, dev, pk, n=128, steps=10, reps=2):
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     return {"workload": "ResNet-50, pgd_linf eps 4/255, %d steps, batch %d, float32 NCHW images resident in HBM" % (steps, n),
             "images_per_s": n / ms * 1e3, "ms_per_batch": ms, "algorithmic_tflops": tf, "peak_tflops": peak, "frac": tf / peak,
-            "source_model": "native dgrad (tcgen05 GEMM on transposed weights, passes=3), no autograd",
-            "note": "split-bf16 issues 3 MMAs per product: tensor-pipe FLOP/s are 3x algorithmic"}
+            "source_model": "native dgrad (tcgen05 GEMM on transposed weights, %s), no autograd" % precision,
+            "note": "fp16 gradients run loss-scaled (x4096), unscaled when the image gradient is written" if precision == "f16"
+                    else "split-bf16 issues 3 MMAs per product: tensor-pipe FLOP/s are 3x algorithmic"}
 
 
 def main():
@@ -377,6 +385,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="f16", choices=["f16", "bf16x3"],
+                    help="f16: one fp16 plane per tensor, one MMA per product (default); bf16x3: split-bf16, fp32-faithful")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -49,9 +49,12 @@ int b200r_num_sms();  // cached SM count of the current device
 #define PHILOX_W0 0x9E3779B9u
 #define PHILOX_W1 0xBB67AE85u
 
-__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+// R rounds: 10 is the Random123 default; 7 is the smallest count the authors report as Crush-resistant
+// (Salmon et al., SC'11, table 2) and is what the per-byte noise kernels use (2 IMAD.WIDE + 2 LOP3 per round).
+template <int R>
+__host__ __device__ __forceinline__ uint4 philox4x32(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < R; ++r) {
 #ifdef __CUDA_ARCH__
     uint32_t hi0 = __umulhi(PHILOX_M0, c.x), lo0 = PHILOX_M0 * c.x;
     uint32_t hi1 = __umulhi(PHILOX_M1, c.z), lo1 = PHILOX_M1 * c.z;
@@ -71,6 +74,7 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, ui
   }
   return c;
 }
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) { return philox4x32<10>(c, k0, k1); }
 
 // uniform in [0,1) from the top 24 bits (exactly representable, never 1.0)
 __device__ __forceinline__ float u32_to_unit(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }

@@ -442,6 +442,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
+      // F16 + TMA store: a store unit is 64 columns = full 128-byte rows (SWIZZLE_128B staging, one 16 KB store); the
+      // 32-column chunks of one warp group (BN >= 128, STEM) or the two groups (BN = 64) fill its halves
+      constexpr bool kSharedUnit = F16 && !STEM && BN == 64;
+      const bool unit_store = F16 && p.tma_store && p.y_hi;
+      const int ucol0 = nt * BN + (kSharedUnit ? 0 : half * kColsPerWarp + rd * 64);
+      uint8_t* ustg = kSharedUnit ? smem + STG_OFF : stg;
+      const bool uissuer = issuer && (!kSharedUnit || half == 0);
+      if (unit_store) {
+        if (uissuer) bulk_wait_read0();                    // the previous store has finished reading the staging buffer
+        if (kSharedUnit) named_bar_sync(4, 256); else named_bar_sync(2 + half, 128);
+      }
 #pragma unroll
       for (int ci = 0; ci < kPer; ++ci) {
         const uint32_t (&v)[32] = vv[ci];
@@ -549,7 +560,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               pl[j] = cvt_bf16x2(f[2 * j + 1] - h1, f[2 * j] - h0);
             }
           }
-          if (p.tma_store) {
+          if (F16 && p.tma_store) {
+            const int sub = kSharedUnit ? half : ci;         // which 64-byte half of the 128-byte rows
+#pragma unroll
+            for (int q = 0; q < 4; ++q)                       // SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+              *reinterpret_cast<uint4*>(ustg + r * 128 + (((sub * 4 + q) ^ (r & 7)) << 4)) =
+                  make_uint4(ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+          } else if (p.tma_store) {
             if (issuer) bulk_wait_read0();                 // the previous store has finished reading the staging buffer
             named_bar_sync(2 + half, 128);
 #pragma unroll
@@ -582,6 +599,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 if (!F16) p.y_lo[off + j] = (uint16_t)(pl[j >> 1] >> (16 * (j & 1)));
               }
           }
+        }
+      }
+      if (unit_store) {
+        fence_proxy_async();
+        if (kSharedUnit) named_bar_sync(4, 256); else named_bar_sync(2 + half, 128);
+        if (uissuer && ucol0 < p.Cout) {
+          tma_store_5d(&map_y, smem_base + STG_OFF + (kSharedUnit ? 0 : half * 16384), ucol0, tw * p.bw, th * p.bh, ti * p.bn, 0);
+          bulk_commit();
         }
       }
       }
@@ -840,7 +865,9 @@ int finish_maps(EncodeTiledFn enc, GemmMaps* m, GemmParams* p, const uint16_t* r
   p->res_mma = 0;
   m->r = m->b; m->i = m->b; m->y = m->b;   // placeholders (never dereferenced unless the flag is set)
   if (y && p->Cout % 8 == 0 && !(gemm_opts() & 1)) {
-    int rc = make_map5(enc, &m->y, y, p->Cout, p->Wo, p->Ho, p->N, ycount, 32, p->bw, p->bh, p->bn, 1, CU_TENSOR_MAP_SWIZZLE_64B, "Y", f16);
+    // split-bf16: 32-channel (64-byte) rows per plane; fp16: 64-channel (128-byte) rows, half as many and twice as wide stores
+    int rc = make_map5(enc, &m->y, y, p->Cout, p->Wo, p->Ho, p->N, ycount, f16 ? 64 : 32, p->bw, p->bh, p->bn, 1,
+                       f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "Y", f16);
     if (rc) return rc;
     p->tma_store = 1;
   }

@@ -220,6 +220,15 @@ int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* 
                           uint16_t* y, int n, int h, int w, const float* mean_host,
                           const float* std_host, int act, int passes, b200r_stream_t stream);
 
+/* Whole ResNet stem in one launch, fp16 mode only: conv1 7x7/s2/p3 + BN + ReLU + MaxPool2d(3,2,1) from the raw uint8
+ * NHWC image (resnet_official.py:221-227,330-334).  Implicit im2col through overlapping no-swizzle UMMA descriptors
+ * over a staged row buffer, 8 TMEM accumulators, pooling in the epilogue (csrc/stem_pool_sm100.cu); the 112x112
+ * activation never reaches HBM.  wgt: ONE fp16 plane [64, 192] in the column order of b200r_stem_im2col_u8;
+ * y: ONE fp16 plane [n, h/4, w/4, 64].  Requires h % 4 == 0, w % 8 == 0, w <= 248. */
+int b200r_stem_pool_u8_f16(const uint8_t* img, const uint16_t* wgt, const float* scale, const float* bias,
+                           uint16_t* y, int n, int h, int w, const float* mean_host,
+                           const float* std_host, b200r_stream_t stream);
+
 /* same, from a float32 NCHW image in [0,1] (the attack loops' iterate): (x - mean) / std and the bf16 split happen
  * in the operand producer, with the arithmetic of b200r_stem_im2col_f32 */
 int b200r_stem_conv7x7_f32(const float* img, const uint16_t* wgt, const float* scale, const float* bias,

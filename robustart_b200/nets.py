@@ -9,6 +9,7 @@ kernel in libb200robust.so; the whole forward can be captured into one CUDA grap
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -189,6 +190,7 @@ class ResNet:
         self.fc_b = sd["fc.bias"].float().to(dev).contiguous()
         self.num_classes = self.fc_w.shape[1]
         self._graphs = {}
+        self.fused_stem_pool = os.environ.get("B200R_STEM_POOL", "1") != "0"   # A/B switch for the one-launch stem
 
     # -- eager launch sequence -------------------------------------------------------------------
     def forward(self, images: torch.Tensor, logits: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -197,12 +199,16 @@ class ResNet:
         n = images.shape[0]
         h, w = (images.shape[1], images.shape[2]) if images.dtype == torch.uint8 else (images.shape[2], images.shape[3])
         P = self.passes
-        if images.dtype == torch.uint8:
-            # raw pixels: gather + ToTensor + Normalize + split fused into the stem GEMM's operand producer
-            x = ops.stem_conv7x7_u8(images, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P)
+        if images.dtype == torch.uint8 and self.f16 and self.fused_stem_pool and ops.stem_pool_ok(h, w):
+            # raw pixels -> conv1 + bn1 + relu + maxpool in one launch (overlapping-descriptor implicit im2col)
+            x = ops.stem_pool_u8(images, self.stem_w, self.stem_scale, self.stem_bias)
         else:
-            x = self._stem_f32(images, P)
-        x = ops.maxpool3x3s2(x)
+            if images.dtype == torch.uint8:
+                # raw pixels: gather + ToTensor + Normalize + split fused into the stem GEMM's operand producer
+                x = ops.stem_conv7x7_u8(images, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P)
+            else:
+                x = self._stem_f32(images, P)
+            x = ops.maxpool3x3s2(x)
         for blk in self.blocks:
             idn = blk["down"](x, passes=P) if "down" in blk else x
             if blk["kind"] == "bottleneck":
@@ -332,7 +338,8 @@ class ResNet:
         return run
 
     def launches_per_forward(self) -> int:
-        n = 1 + 1 + 1 + 1  # fused stem, maxpool, avgpool, fc
+        # stem + maxpool (one launch in fp16 mode with the fused stem), avgpool, fc
+        n = (1 if (self.f16 and self.fused_stem_pool) else 2) + 1 + 1
         for blk in self.blocks:
             n += (3 if blk["kind"] == "bottleneck" else 2) + (1 if "down" in blk else 0)
         return n

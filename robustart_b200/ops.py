@@ -353,6 +353,25 @@ def stem_conv7x7_u8(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGENE
     return out
 
 
+def stem_pool_ok(h: int, w: int) -> bool:
+    """Geometry accepted by the one-launch stem (csrc/stem_pool_sm100.cu)."""
+    return h % 4 == 0 and w % 8 == 0 and 8 <= w <= 248 and h >= 8
+
+
+def stem_pool_u8(img, wgt, scale, bias, *, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
+    """conv1 7x7/s2 + BN + ReLU + MaxPool(3,2,1) from raw uint8 NHWC pixels in one launch (fp16 mode): plane [1, n, h/4, w/4, 64]."""
+    _need_cuda(img, torch.uint8, "img")
+    n, h, w, _ = img.shape
+    assert wgt.shape[0] == 1 and tuple(wgt.shape[1:]) == (64, 192), "stem_pool_u8 takes the fp16 [1, 64, 192] stem weight"
+    assert stem_pool_ok(h, w), "stem_pool_u8: unsupported geometry %dx%d" % (h, w)
+    if out is None:
+        out = torch.empty((1, n, h // 4, w // 4, 64), dtype=torch.int16, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.load().b200r_stem_pool_u8_f16(img.data_ptr(), wgt.data_ptr(), _ptr(scale), _ptr(bias), out.data_ptr(),
+                                                      n, h, w, _lib.f3(mean), _lib.f3(std), _stream()))
+    return out
+
+
 def stem_conv7x7_f32(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
     """Fused 7x7/s2 stem from a float32 NCHW image in [0,1] (attack iterates): planes [P, n, h/2, w/2, 64]."""
     _need_cuda(img, torch.float32, "img")

@@ -93,6 +93,34 @@ def test_pools_f16(cuda):
     assert torch.equal(got, _h(x.mean((2, 3)))) or (got - x.mean((2, 3))).abs().max() < 1e-3
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 224, 224), (48, 224, 224), (3, 64, 64), (1, 40, 248), (5, 8, 8), (2, 100, 72)])
+def test_stem_pool_one_launch(cuda, n, h, w):
+    """conv1 + bn1 + relu + maxpool in one launch (csrc/stem_pool_sm100.cu: overlapping-descriptor implicit im2col) against
+    an fp64 convolution of the same fp16-rounded operands (normalised pixels and weights), rounded once to fp16 and pooled
+    -- resnet_official.py:221-227,330-334."""
+    from robustart_b200 import ops
+    torch.manual_seed(n * 7 + h + w)
+    img = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=cuda)
+    wt = _h(torch.randn(64, 3, 7, 7, device=cuda) / 147 ** 0.5)
+    s, b = torch.rand(64, device=cuda) + 0.5, torch.randn(64, device=cuda) * 0.3
+    s[::5] *= -1                                  # BN scales can be negative: the scale must act before the ReLU
+    mean = torch.tensor(ops.IMAGENET_MEAN, device=cuda).view(1, 3, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD, device=cuda).view(1, 3, 1, 1)
+    x = _h((img.permute(0, 3, 1, 2).float() / 255.0 - mean) / std)
+    conv = F.conv2d(x.double(), wt.double(), None, 2, 3) * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1)
+    ref = F.max_pool2d(torch.relu(conv), 3, 2, 1).permute(0, 2, 3, 1)
+    wp = ops.to_planes(ops.pack_stem_weight(wt).contiguous(), True)
+    y = ops.stem_pool_u8(img, wp, s, b)
+    assert y.shape == (1, n, h // 4, w // 4, 64)
+    got = ops.from_planes(y).double()
+    assert torch.isfinite(got).all()
+    assert ((got - ref).abs() <= ref.abs() * 2 ** -11 * 1.01 + 2e-5).all(), (got - ref).abs().max().item()
+    # and the two-launch path it replaces agrees to fp16 rounding
+    if w % 16 == 0:
+        two = ops.from_planes(ops.maxpool3x3s2(ops.stem_conv7x7_u8(img, wp, s, b, act="relu"))).double()
+        assert ((got - two).abs() <= ref.abs() * 2 ** -10 + 4e-5).all()
+
+
 @pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
 def test_logits_f16_within_tolerance(cuda, arch):
     from robustart_b200 import nets, ops

@@ -83,3 +83,36 @@ def test_jpeg_restatement_equals_pil():
             o = io.BytesIO()
             Image.fromarray(imgs[i]).save(o, "JPEG", quality=q)
             assert np.array_equal(jpeg_roundtrip(imgs[i], q), np.array(Image.open(o)))
+
+
+def test_rayleigh_table_normal():
+    """Quality of the device-RNG normal generator of gaussian / speckle noise (csrc/corrupt_pixel.cu, build_rayleigh): the
+    pair radius comes from a 256-segment piecewise-linear inverse CDF of the Rayleigh distribution (least-squares line per
+    equiprobable segment, moment-matched open tail), the angle is exact.  numpy restatement of the table builder; the
+    resulting z = r cos(theta) must be N(0,1) to KS < 1e-4 with variance / kurtosis within 1e-3."""
+    from scipy.stats import norm
+    k = np.arange(65536)
+    p = (k + 0.5) / 65536
+    rq = np.sqrt(-2 * np.log1p(-p))
+    A, B = np.zeros(256), np.zeros(256)
+    b = np.arange(256.0)
+    for a in range(256):
+        y = rq[a * 256:(a + 1) * 256]
+        if a == 255:
+            m, s = y.mean(), y.std()
+            half = s * np.sqrt(3.0) * (256 / 255.0)
+            A[a], B[a] = m - half, 2 * half / 255
+        else:
+            B[a], A[a] = np.polyfit(b, y, 1)
+    r = A[k >> 8] + B[k >> 8] * (k & 255)
+    assert r.min() >= 0 and r.max() < 4.2
+
+    def cdf_z(t):       # P(r cos(theta) <= t), theta uniform
+        x = np.clip(t / np.maximum(r, 1e-12), -1, 1)
+        return (1 - np.arccos(x) / np.pi).mean()
+    ts = np.linspace(-4.0, 4.0, 161)
+    ks = max(abs(cdf_z(t) - norm.cdf(t)) for t in ts)
+    assert ks < 1e-4, ks
+    var = (r ** 2).mean() / 2
+    kurt = (3 / 8 * (r ** 4).mean()) / var ** 2
+    assert abs(var - 1) < 1e-3 and abs(kurt - 3) < 3e-3, (var, kurt)

@@ -221,11 +221,16 @@ int b200r_stem_conv7x7_u8(const uint8_t* img, const uint16_t* wgt, const float* 
                           const float* std_host, int act, int passes, b200r_stream_t stream);
 
 /* Whole ResNet stem in one launch, fp16 mode only: conv1 7x7/s2/p3 + BN + ReLU + MaxPool2d(3,2,1) from the raw uint8
- * NHWC image (resnet_official.py:221-227,330-334).  Implicit im2col through overlapping no-swizzle UMMA descriptors
- * over a staged row buffer, 8 TMEM accumulators, pooling in the epilogue (csrc/stem_pool_sm100.cu); the 112x112
- * activation never reaches HBM.  wgt: ONE fp16 plane [64, 192] in the column order of b200r_stem_im2col_u8;
- * y: ONE fp16 plane [n, h/4, w/4, 64].  Requires h % 4 == 0, w % 8 == 0, w <= 248. */
-int b200r_stem_pool_u8_f16(const uint8_t* img, const uint16_t* wgt, const float* scale, const float* bias,
+ * NHWC image (resnet_official.py:221-227,330-334 after ToTensor+Normalize).  Implicit im2col through overlapping
+ * no-swizzle UMMA descriptors over a staged row buffer, one N = 256/192 MMA per input row and K step over a ring of 8
+ * TMEM accumulators, BN bias on the tensor core, pooling in the epilogue (csrc/stem_pool_sm100.cu); the 112x112
+ * activation never reaches HBM.
+ *   wgt  : ONE fp16 plane [64, 192] in the column order of b200r_stem_im2col_u8, BN scale ALREADY FOLDED IN
+ *          (w * gamma / sqrt(var + eps), rounded to fp16 once)
+ *   bias : float32 [64] folded BN bias (nullable); enters as an fp16 hi/lo pair, ~2^-22 relative
+ *   y    : ONE fp16 plane [n, h/4, w/4, 64]
+ * Normalisation is fp16(fma(byte, 1/(255 std), -mean/std)) in fp32.  Requires h % 4 == 0, w % 8 == 0, w <= 248. */
+int b200r_stem_pool_u8_f16(const uint8_t* img, const uint16_t* wgt, const float* bias,
                            uint16_t* y, int n, int h, int w, const float* mean_host,
                            const float* std_host, b200r_stream_t stream);
 

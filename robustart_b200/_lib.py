@@ -59,7 +59,7 @@ SIGNATURES = {
                                         c_host_f3, c_stream]),
     "b200r_stem_conv7x7_u8": (C.c_int, [c_u8p, C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                         c_host_f3, c_host_f3, C.c_int, C.c_int, c_stream]),
-    "b200r_stem_pool_u8_f16": (C.c_int, [c_u8p, C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+    "b200r_stem_pool_u8_f16": (C.c_int, [c_u8p, C.c_void_p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          c_host_f3, c_host_f3, c_stream]),
     "b200r_stem_conv7x7_f32": (C.c_int, [c_f32p, C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          c_host_f3, c_host_f3, C.c_int, C.c_int, c_stream]),

@@ -8,54 +8,63 @@
 // bounded by the shared-memory traffic of the gather.  Here nothing is gathered at all:
 //
 //   * Implicit im2col through OVERLAPPING UMMA descriptors.  One normalised image row is staged in shared memory as
-//     fp16 RGB0 pixels (8 bytes each, 4 zero pixels of padding on both sides).  The 7 taps of a kernel row for output
+//     fp16 (R, G, B, 1) pixels (8 bytes each, 4 pixels of padding on both sides).  The 7 taps of a kernel row for output
 //     pixel ox are the 8 consecutive pixels starting at padded column 2*ox (the first one meets a zero weight), i.e. the
 //     64 bytes at byte offset 16*ox.  In the no-swizzle K-major canonical layout an operand row is addressed as
 //     start + (m % 8) * 16 + (m / 8) * SBO + j * LBO  (j = 16-byte K chunk); with SBO = 128 and LBO = 16 that is
 //     start + 16 * (m + j): row m of the A operand IS the staged row at byte 16*m.  The windows overlap, the tensor core
-//     does not care.  One kernel row of one output row = 2 MMAs (128 x 64 x 16) straight from the 1.8 KB row buffer.
-//   * Each staged input row is used for the 3-4 output rows it contributes to (ky = p - 2*oy), accumulating into a ring
-//     of 8 TMEM accumulators (8 x 64 columns = all 512): an output row is complete 7 input rows after it starts and is
-//     drained by the epilogue warps while the MMAs of the next rows proceed.
+//     does not care.  A kernel row is two K = 16 steps straight from the 1.8 KB row buffer.
+//   * One staged input row p feeds the 3-4 output rows oy with ky = p - 2*oy in [0, 6].  Their accumulators sit in
+//     consecutive 64-column slots of a ring of 8 in TMEM (all 512 columns), and the weights of ky = 6, 4, 2, 0 (even p)
+//     / 5, 3, 1 (odd p) are stacked in that order in shared memory: ONE MMA with N = 256 / 192 updates all of them, the
+//     A operand is read once.  Only the row that starts (ky = 0, must overwrite) gets its own N = 64 MMA for the first
+//     K step, and a ring wrap splits a group in two.  5 MMAs per two input rows instead of 14.
+//   * BN scale is folded into the fp16 weights by the caller; the BN bias rides on the tensor core too: the fourth
+//     channel of every staged pixel is 1.0 and meets bias_hi / bias_lo (an fp16 pair, ~2^-22 relative) in the centre
+//     kernel row.  The epilogue is conversion and max only.
 //   * The epilogue keeps the vertical 3-max of the pooling window in registers (thread = output column, rows arrive in
-//     order), exchanges columns through a swizzled 16 KB staging row for the horizontal 3-max and writes the pooled row
-//     with coalesced 16-byte stores.  The 112x112 activation never exists in HBM.
+//     order; ReLU commutes with max and is applied once per pooled value), exchanges columns through a staging row for
+//     the horizontal 3-max and writes the pooled row with coalesced 16-byte stores.  The 112x112 activation never
+//     exists in HBM.
+//   * ToTensor + Normalize in the producers: fp16(fma(byte, 1/(255 std), -mean/std)) in fp32 arithmetic, no tables;
+//     lanes own interleaved pixel pairs so that the 16-byte shared-memory stores of a warp are contiguous.
 //
 // Traffic per image: 150 528 B read + 401 408 B written (56*56*64 fp16); tensor work 2*112*112*64*(7*32) = 360 MFLOP
-// issued (147/224 useful).  Warp roles (416 threads, one CTA per SM, persistent over quarter-image units):
-//   warps 0-3   epilogue (TMEM lane quadrant = warp index)
-//   warp  4     TMEM allocation + MMA issue
-//   warps 5-12  producers: load a raw uint8 row (24 B per lane), LUT-normalise to fp16, write the row buffer
+// issued (147/224 useful).  Warp roles (544 threads, one CTA per SM, persistent over quarter-image units):
+//   warps 0-7   epilogue: two groups of four (TMEM lane quadrant = warp % 4), group g takes channels [32g, 32g+32)
+//   warp  8     TMEM allocation + MMA issue
+//   warps 9-16  producers: raw uint8 row -> normalised fp16 row buffer
 #include "sm100_ptx.cuh"
 
 namespace {
 
-constexpr int SP_EPI_WARPS = 4;
-constexpr int SP_MMA_WARP = 4;
-constexpr int SP_PROD_WARP0 = 5;
+constexpr int SP_EPI_WARPS = 8;              // two groups of four: group g owns channels [32g, 32g+32) of every output row
+constexpr int SP_MMA_WARP = 8;
+constexpr int SP_PROD_WARP0 = 9;
 constexpr int SP_PROD_WARPS = 8;
-constexpr int SP_THREADS = (SP_PROD_WARP0 + SP_PROD_WARPS) * 32;   // 416
+constexpr int SP_THREADS = (SP_PROD_WARP0 + SP_PROD_WARPS) * 32;   // 544
 constexpr int SP_SLOTS = 16;                 // staged input rows in flight
 constexpr int SP_SLOT_BYTES = 2176;          // >= 16 * (127 + 4) = 2096 (the 128-row operand reads past the 112 real columns)
 constexpr int SP_ACC = 8;                    // TMEM accumulators (64 columns each)
 constexpr int SP_UNIT_POOLED = 14;           // pooled rows per work unit
-constexpr int SP_OFF_B = 0;                                  // 7 ky x 2 halves x [2 chunks][64 cout][16 B]
+constexpr int SP_STAGE_PITCH = 96;           // bytes per column in a group's staging row (64 used): columns c and c+2 land
+                                             // in different bank halves, so the pooling reads are conflict free
+constexpr int SP_STAGE_BYTES = 128 * SP_STAGE_PITCH;
+constexpr int SP_OFF_B = 0;                                  // even tile [2 halves][2 chunks][256 rows][16 B] = 16 KB,
+constexpr int SP_B_ODD = 16384;                              // then the odd tile [2][2][192][16 B] = 12 KB
 constexpr int SP_OFF_ROWS = SP_OFF_B + 14 * 2048;
-constexpr int SP_OFF_STAGE = SP_OFF_ROWS + SP_SLOTS * SP_SLOT_BYTES;   // 2 x [128 columns][128 B]
-constexpr int SP_OFF_LUT = SP_OFF_STAGE + 2 * 16384;         // [3][256] fp16
-constexpr int SP_OFF_SB = SP_OFF_LUT + 3 * 256 * 2;          // scale[64], bias[64] fp32
-constexpr int SP_OFF_BARS = SP_OFF_SB + 512;
+constexpr int SP_OFF_STAGE = SP_OFF_ROWS + SP_SLOTS * SP_SLOT_BYTES;   // [2 groups][2 buffers][128 columns][96 B]
+constexpr int SP_OFF_BARS = SP_OFF_STAGE + 4 * SP_STAGE_BYTES;
 constexpr int SP_SMEM = SP_OFF_BARS + (2 * SP_SLOTS + 2 * SP_ACC) * 8 + 16 + 128;
 
 struct StemPoolParams {
   const uint8_t* img;      // [n, h, w, 3]
-  const __half* wgt;       // [64, 192], column = ky*24 + kx*3 + c
-  const float* scale;      // [64] (nullable)
+  const __half* wgt;       // [64, 192], column = ky*24 + kx*3 + c, BN scale folded in
   const float* bias;       // [64] (nullable)
   __half* y;               // [n, h/4, w/4, 64]
   int n, h, w;
   int units_per_img, n_units;
-  float mean[3], std[3];
+  float k1[3], k0[3];      // normalised = fma(byte, k1, k0)
 };
 
 // K-major operand without swizzle: 8-row x 16-byte core matrices, `lbo` between the two K chunks of one MMA, `sbo`
@@ -124,22 +133,30 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
     tmem_relinquish();
   }
   {
+    // weights in operand layout.  Tile `par` stacks the kernel rows ky = (6 - par) - 2*jb as 64-row blocks jb; K step h covers
+    // window positions t = 4h .. 4h+3 (t = kx + 1), 4 channels each; chunk j = positions 4h+2j, 4h+2j+1.
     __half* sB = reinterpret_cast<__half*>(smem + SP_OFF_B);
     for (int idx = threadIdx.x; idx < 14 * 1024; idx += SP_THREADS) {
-      const int kyh = idx >> 10, j = (idx >> 9) & 1, co = (idx >> 3) & 63, e = idx & 7;
-      const int ky = kyh >> 1, t = 4 * (kyh & 1) + 2 * j + (e >> 2), c4 = e & 3;     // t = window position = kx + 1
-      sB[idx] = (t >= 1 && c4 < 3) ? p.wgt[co * 192 + ky * 24 + (t - 1) * 3 + c4] : __float2half_rn(0.f);
+      const int par = idx >= 8192, li = idx - par * 8192, rows = par ? 192 : 256;
+      const int e = li & 7, r = (li >> 3) % rows, jh = (li >> 3) / rows;       // jh = h * 2 + j
+      const int j = jh & 1, h = jh >> 1, jb = r >> 6, co = r & 63;
+      const int ky = (6 - par) - 2 * jb, t = 4 * h + 2 * j + (e >> 2), c4 = e & 3;
+      __half val = __float2half_rn(0.f);
+      if (c4 < 3) { if (t >= 1) val = p.wgt[co * 192 + ky * 24 + (t - 1) * 3 + c4]; }
+      else if (ky == 3 && p.bias) {
+        const float bf = p.bias[co];
+        const __half bh = __float2half_rn(bf);
+        if (t == 4) val = bh;
+        else if (t == 3) val = __float2half_rn(bf - __half2float(bh));
+      }
+      sB[idx] = val;
     }
-    __half* lut = reinterpret_cast<__half*>(smem + SP_OFF_LUT);
-    for (int idx = threadIdx.x; idx < 768; idx += SP_THREADS) {
-      const int c = idx >> 8, b = idx & 255;
-      lut[idx] = __float2half_rn(((float)b / 255.0f - p.mean[c]) / p.std[c]);
+    // row ring: zero, with the constant-one fourth channel on every pixel column (padding included)
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem + SP_OFF_ROWS);
+    for (int idx = threadIdx.x; idx < SP_SLOTS * SP_SLOT_BYTES / 4; idx += SP_THREADS) {
+      const int w4 = idx % (SP_SLOT_BYTES / 4);
+      rows[idx] = ((w4 & 1) && w4 < 2 * (W + 8)) ? 0x3C000000u : 0u;
     }
-    float* sb = reinterpret_cast<float*>(smem + SP_OFF_SB);
-    for (int idx = threadIdx.x; idx < 128; idx += SP_THREADS)
-      sb[idx] = idx < 64 ? (p.scale ? p.scale[idx] : 1.f) : (p.bias ? p.bias[idx - 64] : 0.f);
-    uint4* rows = reinterpret_cast<uint4*>(smem + SP_OFF_ROWS);
-    for (int idx = threadIdx.x; idx < SP_SLOTS * SP_SLOT_BYTES / 16; idx += SP_THREADS) rows[idx] = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -150,162 +167,184 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
   if (warp >= SP_PROD_WARP0) {
     // ================================ producers ================================
     const int pw = warp - SP_PROD_WARP0;
-    const unsigned short* lut = reinterpret_cast<const unsigned short*>(smem + SP_OFF_LUT);
-    const bool active = lane * 8 < W;
-    uint2 cur[3] = {make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0)};
+    // lane owns the pixel pairs q = lane + 32 j: the warp's four 16-byte stores per row are contiguous 512-byte runs.
+    // A pair is 6 bytes at offset 6q: two aligned words from 6q & ~3, shifted by 16 bits when q is odd.
+    uint32_t cur[8];
     int cur_cnt = -1;
-    auto commit_row = [&](const uint2 (&v)[3], int cnt) {
-      const int slot = cnt % SP_SLOTS;
+    const float k1r = p.k1[0], k1g = p.k1[1], k1b = p.k1[2], k0r = p.k0[0], k0g = p.k0[1], k0b = p.k0[2];
+    auto nrm = [](uint32_t w, uint32_t sel, float k1, float k0) {
+      return fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f, k1, k0);
+    };
+    auto commit_row = [&](const uint32_t (&v)[8], uint32_t cnt) {
+      const uint32_t slot = cnt % SP_SLOTS;
       mbar_wait(empty_in(slot), ((cnt / SP_SLOTS) & 1) ^ 1);
-      if (active) {
-        const uint32_t w6[6] = {v[0].x, v[0].y, v[1].x, v[1].y, v[2].x, v[2].y};
-        const uint32_t dst = sbase + SP_OFF_ROWS + slot * SP_SLOT_BYTES + 32 + lane * 64;
+      const uint32_t dst = sbase + SP_OFF_ROWS + slot * SP_SLOT_BYTES + 32;
 #pragma unroll
-        for (int pr = 0; pr < 4; ++pr) {
-          uint32_t o[4];
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int px = 2 * pr + k;
-            const uint32_t b0 = (w6[(3 * px) >> 2] >> (8 * ((3 * px) & 3))) & 255u;
-            const uint32_t b1 = (w6[(3 * px + 1) >> 2] >> (8 * ((3 * px + 1) & 3))) & 255u;
-            const uint32_t b2 = (w6[(3 * px + 2) >> 2] >> (8 * ((3 * px + 2) & 3))) & 255u;
-            o[2 * k] = (uint32_t)lut[b0] | ((uint32_t)lut[256 + b1] << 16);
-            o[2 * k + 1] = (uint32_t)lut[512 + b2];
-          }
-          sts_v4(dst + pr * 16, make_uint4(o[0], o[1], o[2], o[3]));
+      for (int j = 0; j < 4; ++j) {
+        const int q = lane + 32 * j;
+        if (q < WO) {
+          const uint32_t sh = (lane & 1) * 16;
+          const uint32_t lo = __funnelshift_r(v[2 * j], v[2 * j + 1], sh), hi = v[2 * j + 1] >> sh;   // r0 g0 b0 r1 | g1 b1
+          uint4 o;
+          o.x = cvt_f16x2(nrm(lo, 0x7651, k1g, k0g), nrm(lo, 0x7650, k1r, k0r));
+          o.y = cvt_f16x2(1.0f, nrm(lo, 0x7652, k1b, k0b));
+          o.z = cvt_f16x2(nrm(hi, 0x7650, k1g, k0g), nrm(lo, 0x7653, k1r, k0r));
+          o.w = cvt_f16x2(1.0f, nrm(hi, 0x7651, k1b, k0b));
+          sts_v4(dst + q * 16, o);
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_in(slot));
     };
-    int cnt = 0;
+    uint32_t cnt = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit t = make_unit(p, u);
       for (int pp = t.p_lo; pp <= t.p_hi; ++pp, ++cnt) {
-        if ((cnt & (SP_PROD_WARPS - 1)) != pw) continue;
-        uint2 nxt[3] = {make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0)};
-        if (active) {
-          const uint2* src = reinterpret_cast<const uint2*>(p.img + ((size_t)t.n * H + (pp - 3)) * (size_t)W * 3) + lane * 3;
-          nxt[0] = __ldg(src); nxt[1] = __ldg(src + 1); nxt[2] = __ldg(src + 2);
+        if ((cnt & (SP_PROD_WARPS - 1)) != (uint32_t)pw) continue;
+        uint32_t nxt[8];
+        const uint8_t* rowp = p.img + ((size_t)t.n * H + (pp - 3)) * (size_t)W * 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int q = lane + 32 * j;
+          nxt[2 * j] = 0u; nxt[2 * j + 1] = 0u;
+          if (q < WO) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(rowp + ((6 * q) & ~3));
+            nxt[2 * j] = __ldg(src); nxt[2 * j + 1] = __ldg(src + 1);
+          }
         }
-        if (cur_cnt >= 0) commit_row(cur, cur_cnt);
-        cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2];
-        cur_cnt = cnt;
+        if (cur_cnt >= 0) commit_row(cur, (uint32_t)cur_cnt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+        cur_cnt = (int)cnt;
       }
     }
-    if (cur_cnt >= 0) commit_row(cur, cur_cnt);
+    if (cur_cnt >= 0) commit_row(cur, (uint32_t)cur_cnt);
   } else if (warp == SP_MMA_WARP) {
     // ================================ MMA issue ================================
-    // fp16 A/B (format bits 0), fp32 accumulator (bit 4), K-major both, N = 64, M = 128
-    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int cnt = 0, acc_base = 0;
+    // fp16 A/B (format bits 0), fp32 accumulator (bit 4), K-major both, M = 128, N = 64 * blocks
+    constexpr uint32_t IDESC0 = (1u << 4) | ((uint32_t)(128 >> 4) << 24);
+    // descriptors as (hi, lo) words: hi = SBO 128 B | version, identical for A and B; lo = start address | LBO.  The loop
+    // only adds to the address field (everything stays below 256 KB, no carry into the LBO bits).
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo0 = ((sbase + SP_OFF_ROWS) >> 4) | ((16u >> 4) << 16);
+    const uint32_t be_lo0 = ((sbase + SP_OFF_B) >> 4) | ((4096u >> 4) << 16);              // even tile: LBO = 256 rows * 16 B
+    const uint32_t bo_lo0 = ((sbase + SP_OFF_B + SP_B_ODD) >> 4) | ((3072u >> 4) << 16);   // odd tile: 192 rows
+    auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
+    uint32_t cnt = 0, acc_base = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit t = make_unit(p, u);
       for (int pp = t.p_lo; pp <= t.p_hi; ++pp, ++cnt) {
-        const int slot = cnt % SP_SLOTS;
+        const uint32_t slot = cnt % SP_SLOTS;
+        // active output rows: oy_hi - k, k = 0 .. kmax, with ky = ky0 + 2k; accumulator slot (c_hi - k) % 8; weight block bmax - k
+        const int oy_hi = min(t.r_last, pp >> 1);
+        const int ky0 = pp - 2 * oy_hi, par = pp & 1;
+        const int bmax = (6 - par - ky0) >> 1;
+        const int kmax = min(bmax, oy_hi - t.r_first);
+        const uint32_t c_hi = acc_base + (uint32_t)(oy_hi - t.r_first);
+        // output rows that start with this input row need their accumulator back from the epilogue
+        if (pp == 3) {
+          for (int k = 0; k <= kmax; ++k) mbar_wait(acc_empty((c_hi - k) % SP_ACC), (((c_hi - k) / SP_ACC) & 1) ^ 1);
+        } else if (ky0 == 0) {
+          mbar_wait(acc_empty(c_hi % SP_ACC), ((c_hi / SP_ACC) & 1) ^ 1);
+        }
         mbar_wait(full_in(slot), (cnt / SP_SLOTS) & 1);
         tc_fence_after();
-        const uint32_t a_addr = sbase + SP_OFF_ROWS + slot * SP_SLOT_BYTES;
-        const uint64_t a0 = make_nosw_desc(a_addr, 16, 128), a1 = make_nosw_desc(a_addr + 32, 16, 128);
-        const int oy_lo = max(t.r_first, (pp - 5) >> 1), oy_hi = min(t.r_last, pp >> 1);   // ky = pp - 2*oy in [0, 6]
-        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-          const int ky = pp - 2 * oy;
-          const int c = acc_base + (oy - t.r_first), aslot = c % SP_ACC;
-          const bool first = (pp == max(2 * oy, 3));
-          if (first) {
-            mbar_wait(acc_empty(aslot), ((c / SP_ACC) & 1) ^ 1);
-            tc_fence_after();
-          }
-          const uint32_t b_addr = sbase + SP_OFF_B + ky * 4096;
-          const uint64_t b0 = make_nosw_desc(b_addr, 1024, 128), b1 = make_nosw_desc(b_addr + 2048, 1024, 128);
-          const uint32_t d = tmem_base + aslot * 64;
-          if (elect_one()) {
-            umma_bf16(d, a0, b0, IDESC, first ? 0u : 1u);
-            umma_bf16(d, a1, b1, IDESC, 1u);
-          }
-          __syncwarp();
-        }
         if (elect_one()) {
+          const uint32_t a_lo = a_lo0 + slot * (SP_SLOT_BYTES >> 4);
+          const uint32_t b_lo = par ? bo_lo0 : be_lo0, b_half = par ? (6144u >> 4) : (8192u >> 4);
+          // one MMA over the rows k in [ka, kb] (consecutive slots, no wrap) for K step h
+          auto one = [&](int h, int ka, int kb, uint32_t accumulate) {
+            const uint32_t d = tmem_base + ((c_hi - (uint32_t)kb) % SP_ACC) * 64;
+            const uint32_t nb = (uint32_t)(kb - ka + 1);
+            umma_bf16(d, desc(a_lo + 2 * h), desc(b_lo + h * b_half + (uint32_t)(bmax - kb) * 64u), IDESC0 | ((nb * 8u) << 17), accumulate);
+          };
+          auto run = [&](int h, int ka, int kb) {
+            const int s_a = (int)((c_hi - (uint32_t)ka) % SP_ACC);       // slots fall from s_a; the ring wraps below 0
+            if (s_a >= kb - ka) one(h, ka, kb, 1u);
+            else { one(h, ka, ka + s_a, 1u); one(h, ka + s_a + 1, kb, 1u); }
+          };
+          if (pp == 3) {                         // top of the image: every row present starts here
+            for (int k = 0; k <= kmax; ++k) { one(0, k, k, 0u); one(1, k, k, 1u); }
+          } else {
+            const int kf = (ky0 == 0) ? 1 : 0;   // the starting row overwrites: its own MMA for the first K step
+            if (kf) one(0, 0, 0, 0u);
+            if (kmax >= kf) run(0, kf, kmax);
+            run(1, 0, kmax);
+          }
           umma_commit(empty_in(slot));
           // output rows whose last contributing input row this is
           if (!(pp & 1) && pp >= 6) {
             const int oy = (pp - 6) >> 1;
-            if (oy >= t.r_first && oy <= t.r_last) umma_commit(acc_full((acc_base + oy - t.r_first) % SP_ACC));
+            if (oy >= t.r_first && oy <= t.r_last) umma_commit(acc_full((acc_base + (uint32_t)(oy - t.r_first)) % SP_ACC));
           }
           if (pp == H + 2) {          // the bottom row loses its last two taps to the padding
             const int oy = (H >> 1) - 1;
-            if (oy >= t.r_first && oy <= t.r_last) umma_commit(acc_full((acc_base + oy - t.r_first) % SP_ACC));
+            if (oy >= t.r_first && oy <= t.r_last) umma_commit(acc_full((acc_base + (uint32_t)(oy - t.r_first)) % SP_ACC));
           }
         }
         __syncwarp();
       }
-      acc_base += t.r_last - t.r_first + 1;
+      acc_base += (uint32_t)(t.r_last - t.r_first + 1);
     }
   } else {
     // ================================ epilogue ================================
-    const int m = threadIdx.x;                   // output column (TMEM lane)
-    const float4* sb4 = reinterpret_cast<const float4*>(smem + SP_OFF_SB);
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    int acc_base = 0, emit = 0;
+    // group g = warp / 4 owns channels [32g, 32g + 32); thread = output column (TMEM lane = 32 * (warp % 4) + lane)
+    const int grp = warp >> 2, m = threadIdx.x & 127;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * 32;
+    const uint32_t stage0 = sbase + SP_OFF_STAGE + grp * 2 * SP_STAGE_BYTES;
+    uint32_t acc_base = 0, emit = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit t = make_unit(p, u);
-      uint32_t prev_odd[32], v[32];
+      uint32_t prev_odd[16], v[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { prev_odd[i] = 0u; v[i] = 0u; }
+      for (int i = 0; i < 16; ++i) { prev_odd[i] = 0u; v[i] = 0u; }
       for (int r = t.r_first; r <= t.r_last; ++r) {
-        const int c = acc_base + (r - t.r_first), aslot = c % SP_ACC;
+        const uint32_t c = acc_base + (uint32_t)(r - t.r_first), aslot = c % SP_ACC;
         mbar_wait(acc_full(aslot), (c / SP_ACC) & 1);
         tc_fence_after();
+        uint32_t acc[32];
+        tmem_ld32(lane_base + aslot * 64, acc);
+        tmem_ld_wait();
+        tc_fence_before();               // accumulator drained: hand it back before the arithmetic
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(aslot));
         const bool odd = r & 1;
+        // scale and bias came in through the MMA; the ReLU commutes with the max and is applied once per pooled value
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t acc[32];
-          tmem_ld32(lane_base + aslot * 64 + half * 32, acc);
-          tmem_ld_wait();
-          if (half == 1) {               // accumulator drained: hand it back before the arithmetic
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty(aslot));
-          }
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {           // 4 channels per step: scale / bias as broadcast 128-bit reads
-            const float4 s4 = sb4[half * 8 + j4], b4 = sb4[16 + half * 8 + j4];
-            const float y0 = fmaxf(fmaf(__uint_as_float(acc[4 * j4]), s4.x, b4.x), 0.f);
-            const float y1 = fmaxf(fmaf(__uint_as_float(acc[4 * j4 + 1]), s4.y, b4.y), 0.f);
-            const float y2 = fmaxf(fmaf(__uint_as_float(acc[4 * j4 + 2]), s4.z, b4.z), 0.f);
-            const float y3 = fmaxf(fmaf(__uint_as_float(acc[4 * j4 + 3]), s4.w, b4.w), 0.f);
-            const uint32_t cur0 = cvt_f16x2(y1, y0), cur1 = cvt_f16x2(y3, y2);
-            const int i = half * 16 + 2 * j4;
-            if (odd) { v[i] = hmax2_u32(v[i], cur0); prev_odd[i] = cur0; v[i + 1] = hmax2_u32(v[i + 1], cur1); prev_odd[i + 1] = cur1; }
-            else { v[i] = hmax2_u32(prev_odd[i], cur0); v[i + 1] = hmax2_u32(prev_odd[i + 1], cur1); }
-          }
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t cur = cvt_f16x2(__uint_as_float(acc[2 * i + 1]), __uint_as_float(acc[2 * i]));
+          if (odd) { v[i] = hmax2_u32(v[i], cur); prev_odd[i] = cur; }
+          else v[i] = hmax2_u32(prev_odd[i], cur);
         }
         if (odd && (r >> 1) >= t.py0) {
-          // vertical 3-max of pooled row r/2 is in v: exchange columns through the staging row, then the horizontal 3-max
-          const uint32_t st = sbase + SP_OFF_STAGE + (emit & 1) * 16384;
+          // vertical 3-max of pooled row r/2 is in v (0 stands in for the padding row: the ReLU follows): exchange columns
+          // through the group's staging row, then the horizontal 3-max, ReLU, store
+          const uint32_t st = stage0 + (emit & 1) * SP_STAGE_BYTES;
           if (m < WO) {
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
-              sts_v4(st + m * 128 + ((ch ^ (m & 7)) << 4), make_uint4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]));
+            for (int ch = 0; ch < 4; ++ch)
+              sts_v4(st + m * SP_STAGE_PITCH + ch * 16, make_uint4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]));
           }
-          named_bar_sync(1, SP_EPI_WARPS * 32);
-          uint4* yrow = reinterpret_cast<uint4*>(p.y + ((size_t)(t.n * PH + (r >> 1)) * PW) * 64);
-          for (int i = m; i < PW * 8; i += SP_EPI_WARPS * 32) {
-            const int px = i >> 3, ch = i & 7, c1 = 2 * px;
-            uint4 a = lds_v4(st + c1 * 128 + ((ch ^ (c1 & 7)) << 4));
-            const uint4 b = lds_v4(st + (c1 + 1) * 128 + ((ch ^ ((c1 + 1) & 7)) << 4));
+          named_bar_sync(1 + grp, 128);
+          uint4* yrow = reinterpret_cast<uint4*>(p.y + ((size_t)(t.n * PH + (r >> 1)) * PW) * 64 + grp * 32);
+          for (int i = m; i < PW * 4; i += 128) {
+            const int px = i >> 2, ch = i & 3, c1 = 2 * px;
+            const uint32_t at = st + c1 * SP_STAGE_PITCH + ch * 16;
+            uint4 a = lds_v4(at);
+            const uint4 b = lds_v4(at + SP_STAGE_PITCH);
             a.x = hmax2_u32(a.x, b.x); a.y = hmax2_u32(a.y, b.y); a.z = hmax2_u32(a.z, b.z); a.w = hmax2_u32(a.w, b.w);
             if (px > 0) {
-              const uint4 l = lds_v4(st + (c1 - 1) * 128 + ((ch ^ ((c1 - 1) & 7)) << 4));
+              const uint4 l = lds_v4(at - SP_STAGE_PITCH);
               a.x = hmax2_u32(a.x, l.x); a.y = hmax2_u32(a.y, l.y); a.z = hmax2_u32(a.z, l.z); a.w = hmax2_u32(a.w, l.w);
             }
-            yrow[i] = a;
+            a.x = hmax2_u32(a.x, 0u); a.y = hmax2_u32(a.y, 0u); a.z = hmax2_u32(a.z, 0u); a.w = hmax2_u32(a.w, 0u);
+            yrow[px * 8 + ch] = a;
           }
           ++emit;
         }
       }
-      acc_base += t.r_last - t.r_first + 1;
+      acc_base += (uint32_t)(t.r_last - t.r_first + 1);
     }
   }
 
@@ -321,18 +360,21 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
 
 extern "C" {
 
-int b200r_stem_pool_u8_f16(const uint8_t* img, const uint16_t* wgt, const float* scale, const float* bias, uint16_t* y,
+int b200r_stem_pool_u8_f16(const uint8_t* img, const uint16_t* wgt, const float* bias, uint16_t* y,
                            int n, int h, int w, const float* mean_host, const float* std_host, b200r_stream_t stream) {
   B200R_CHECK_ARG(img && wgt && y && mean_host && std_host, "null pointer");
   B200R_CHECK_ARG(n > 0 && h >= 8 && w >= 8, "bad shape %d x %d x %d", n, h, w);
   B200R_CHECK_ARG(h % 4 == 0 && w % 8 == 0 && w <= 248, "stem_pool needs h %% 4 == 0, w %% 8 == 0, w <= 248 (got %d x %d)", h, w);
   B200R_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "img must be 8-byte, y 16-byte aligned");
   StemPoolParams p;
-  p.img = img; p.wgt = reinterpret_cast<const __half*>(wgt); p.scale = scale; p.bias = bias; p.y = reinterpret_cast<__half*>(y);
+  p.img = img; p.wgt = reinterpret_cast<const __half*>(wgt); p.bias = bias; p.y = reinterpret_cast<__half*>(y);
   p.n = n; p.h = h; p.w = w;
   p.units_per_img = ((h >> 2) + SP_UNIT_POOLED - 1) / SP_UNIT_POOLED;
   p.n_units = n * p.units_per_img;
-  for (int c = 0; c < 3; ++c) { p.mean[c] = mean_host[c]; p.std[c] = std_host[c]; }
+  for (int c = 0; c < 3; ++c) {
+    p.k1[c] = (float)(1.0 / (255.0 * (double)std_host[c]));
+    p.k0[c] = (float)(-(double)mean_host[c] / (double)std_host[c]);
+  }
   static bool attr_set[16] = {};
   int dev = 0;
   B200R_CUDA(cudaGetDevice(&dev));

@@ -170,6 +170,8 @@ class ResNet:
         m, v = sd["bn1.running_mean"].double(), sd["bn1.running_var"].double()
         s = g / torch.sqrt(v + BN_EPS)
         self.stem_scale, self.stem_bias = s.float().to(dev), (b - m * s).float().to(dev)
+        # one-launch stem (fp16 mode): BN scale folded into the weights before the single rounding to fp16
+        self.stem_w_folded = ops.to_planes(ops.pack_stem_weight((sd["conv1.weight"].double() * s.view(-1, 1, 1, 1)).float()).to(dev).contiguous(), True) if f16 else None
         self.blocks = []
         for li, blocks in enumerate(layers):
             for bi in range(blocks):
@@ -201,7 +203,7 @@ class ResNet:
         P = self.passes
         if images.dtype == torch.uint8 and self.f16 and self.fused_stem_pool and ops.stem_pool_ok(h, w):
             # raw pixels -> conv1 + bn1 + relu + maxpool in one launch (overlapping-descriptor implicit im2col)
-            x = ops.stem_pool_u8(images, self.stem_w, self.stem_scale, self.stem_bias)
+            x = ops.stem_pool_u8(images, self.stem_w_folded, self.stem_bias)
         else:
             if images.dtype == torch.uint8:
                 # raw pixels: gather + ToTensor + Normalize + split fused into the stem GEMM's operand producer

@@ -358,16 +358,17 @@ def stem_pool_ok(h: int, w: int) -> bool:
     return h % 4 == 0 and w % 8 == 0 and 8 <= w <= 248 and h >= 8
 
 
-def stem_pool_u8(img, wgt, scale, bias, *, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
-    """conv1 7x7/s2 + BN + ReLU + MaxPool(3,2,1) from raw uint8 NHWC pixels in one launch (fp16 mode): plane [1, n, h/4, w/4, 64]."""
+def stem_pool_u8(img, wgt_folded, bias, *, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
+    """conv1 7x7/s2 + BN + ReLU + MaxPool(3,2,1) from raw uint8 NHWC pixels in one launch (fp16 mode): plane [1, n, h/4, w/4, 64].
+    wgt_folded: fp16 plane [1, 64, 192] = to_planes(pack_stem_weight(w * bn_scale[:, None, None, None]), True)."""
     _need_cuda(img, torch.uint8, "img")
     n, h, w, _ = img.shape
-    assert wgt.shape[0] == 1 and tuple(wgt.shape[1:]) == (64, 192), "stem_pool_u8 takes the fp16 [1, 64, 192] stem weight"
+    assert wgt_folded.shape[0] == 1 and tuple(wgt_folded.shape[1:]) == (64, 192), "stem_pool_u8 takes the fp16 [1, 64, 192] stem weight"
     assert stem_pool_ok(h, w), "stem_pool_u8: unsupported geometry %dx%d" % (h, w)
     if out is None:
         out = torch.empty((1, n, h // 4, w // 4, 64), dtype=torch.int16, device=img.device)
     with torch.cuda.device(img.device):
-        _lib.check(_lib.load().b200r_stem_pool_u8_f16(img.data_ptr(), wgt.data_ptr(), _ptr(scale), _ptr(bias), out.data_ptr(),
+        _lib.check(_lib.load().b200r_stem_pool_u8_f16(img.data_ptr(), wgt_folded.data_ptr(), _ptr(bias), out.data_ptr(),
                                                       n, h, w, _lib.f3(mean), _lib.f3(std), _stream()))
     return out
 

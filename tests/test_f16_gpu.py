@@ -101,24 +101,31 @@ def test_stem_pool_one_launch(cuda, n, h, w):
     from robustart_b200 import ops
     torch.manual_seed(n * 7 + h + w)
     img = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=cuda)
-    wt = _h(torch.randn(64, 3, 7, 7, device=cuda) / 147 ** 0.5)
+    wt = torch.randn(64, 3, 7, 7, device=cuda) / 147 ** 0.5
     s, b = torch.rand(64, device=cuda) + 0.5, torch.randn(64, device=cuda) * 0.3
     s[::5] *= -1                                  # BN scales can be negative: the scale must act before the ReLU
-    mean = torch.tensor(ops.IMAGENET_MEAN, device=cuda).view(1, 3, 1, 1)
-    std = torch.tensor(ops.IMAGENET_STD, device=cuda).view(1, 3, 1, 1)
-    x = _h((img.permute(0, 3, 1, 2).float() / 255.0 - mean) / std)
-    conv = F.conv2d(x.double(), wt.double(), None, 2, 3) * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1)
+    wf = _h(wt * s.view(-1, 1, 1, 1))             # the kernel's contract: scale folded, then ONE rounding to fp16
+    # the kernel's normalisation: fp16(fma_f32(byte, 1/(255 std), -mean/std)); fp64 emulates the fused multiply-add exactly
+    k1 = torch.tensor([float(np.float32(1.0 / (255.0 * float(np.float32(sd))))) for sd in ops.IMAGENET_STD], device=cuda, dtype=torch.float64)
+    k0 = torch.tensor([float(np.float32(-float(np.float32(m)) / float(np.float32(sd)))) for m, sd in zip(ops.IMAGENET_MEAN, ops.IMAGENET_STD)],
+                      device=cuda, dtype=torch.float64)
+    x = _h((img.permute(0, 3, 1, 2).double() * k1.view(1, 3, 1, 1) + k0.view(1, 3, 1, 1)).float())
+    sel = list(range(n)) if n <= 8 else [0, 1, n // 3, n // 2, n - 2, n - 1]     # fp64 reference on a few images of the big batch
+    conv = F.conv2d(x[sel].double(), wf.double(), b.double(), 2, 3)
     ref = F.max_pool2d(torch.relu(conv), 3, 2, 1).permute(0, 2, 3, 1)
-    wp = ops.to_planes(ops.pack_stem_weight(wt).contiguous(), True)
-    y = ops.stem_pool_u8(img, wp, s, b)
+    wp = ops.to_planes(ops.pack_stem_weight(wf).contiguous(), True)
+    y = ops.stem_pool_u8(img, wp, b)
     assert y.shape == (1, n, h // 4, w // 4, 64)
     got = ops.from_planes(y).double()
     assert torch.isfinite(got).all()
+    got = got[sel]
+    # one rounding to fp16 on the way out; the bias pair and the fp32 accumulation order add ~1e-6 absolute
     assert ((got - ref).abs() <= ref.abs() * 2 ** -11 * 1.01 + 2e-5).all(), (got - ref).abs().max().item()
-    # and the two-launch path it replaces agrees to fp16 rounding
+    # and the two-launch path it replaces (unfolded fp16 weights, scale in the epilogue, LUT normalisation) agrees to fp16 noise
     if w % 16 == 0:
-        two = ops.from_planes(ops.maxpool3x3s2(ops.stem_conv7x7_u8(img, wp, s, b, act="relu"))).double()
-        assert ((got - two).abs() <= ref.abs() * 2 ** -10 + 4e-5).all()
+        w16 = ops.to_planes(ops.pack_stem_weight(_h(wt)).contiguous(), True)
+        two = ops.from_planes(ops.maxpool3x3s2(ops.stem_conv7x7_u8(img, w16, s, b, act="relu"))).double()[sel]
+        assert (got - two).abs().max().item() < 2e-2 and (got - two).abs().mean().item() < 1e-3
 
 
 @pytest.mark.parametrize("arch", ["resnet18", "resnet50"])

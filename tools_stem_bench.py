@@ -24,7 +24,7 @@ def timed(fn, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-one = timed(lambda i: ops.stem_pool_u8(imgs[i % 4], wp, s, b, out=out1))
+one = timed(lambda i: ops.stem_pool_u8(imgs[i % 4], wp, b, out=out1))
 def two_fn(i):
     ops.stem_conv7x7_u8(imgs[i % 4], wp, s, b, act="relu", out=mid)
     ops.maxpool3x3s2(mid, out=out2)

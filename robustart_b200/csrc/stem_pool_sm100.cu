@@ -108,9 +108,54 @@ __device__ __forceinline__ Unit make_unit(const StemPoolParams& p, int u) {
   return t;
 }
 
+// ---- MMA issue ------------------------------------------------------------------------------------------------------
+// Rings are indexed by ABSOLUTE coordinates: input row p sits in row slot p % 16, output row oy accumulates in TMEM slot
+// oy % 8.  Everything an interior input row needs is then a compile-time function of I = p % 16, and the issue loop --
+// which bounded the kernel when slots, blocks, wraps and descriptors were computed at run time on the uniform datapath
+// (650 cycles per input row) -- is a jump into one of 16 straight-line sequences of 4-5 UTCHMMA.
+// descriptors as (hi, lo) words: hi = SBO 128 B | version, identical for A and B; lo = start address | LBO; adding to lo
+// moves the start address (everything stays below 256 KB, no carry into the LBO bits)
+constexpr uint32_t SP_DESC_HI = (128u >> 4) | (1u << 14);
+constexpr uint32_t SP_IDESC0 = (1u << 4) | ((uint32_t)(128 >> 4) << 24);   // fp16 A/B, fp32 accumulator, K-major, M = 128
+__device__ __forceinline__ uint64_t sp_desc(uint32_t lo) { return ((uint64_t)SP_DESC_HI << 32) | lo; }
+
+struct MmaBases { uint32_t a_lo0, be_lo0, bo_lo0, tmem; };
+
+// All MMAs of input row p with p % 16 == I.  Output rows are counted from the newest possible one: k = 0 is oy_top = p / 2
+// (kernel row ky = p % 2), k is oy_top - k (ky = p % 2 + 2k); its accumulator is TMEM slot (oy_top - k) % 8 and its weights
+// block BMAX - k of the parity's stacked tile.  Rows [kmin, kmax] are present (interior rows: all of [0, BMAX]; the edges
+// of a unit or of the image clip the range).  Called with literal bounds the whole body folds to 4-5 UTCHMMA with
+// immediate descriptor offsets.
+template <int I>
+__device__ __forceinline__ void sp_issue(const MmaBases& mb, int kmin, int kmax, bool all_fresh) {
+  constexpr int PAR = I & 1, S0 = (I >> 1) % SP_ACC, BMAX = 3 - PAR;
+  constexpr int SEG0_HI = S0 < BMAX ? S0 : BMAX;       // slots fall with k and wrap below 0: [0, SEG0_HI] and [S0 + 1, BMAX] are contiguous
+  auto one = [&](int h, int ka, int kb, uint32_t accumulate) {     // one MMA over the rows [ka, kb], K step h
+    const uint32_t d = mb.tmem + (uint32_t)((S0 - kb) & (SP_ACC - 1)) * 64u;
+    const uint32_t b = (PAR ? mb.bo_lo0 : mb.be_lo0) + (uint32_t)h * (PAR ? (6144u >> 4) : (8192u >> 4)) + (uint32_t)(BMAX - kb) * 64u;
+    umma_bf16(d, sp_desc(mb.a_lo0 + I * (SP_SLOT_BYTES >> 4) + 2 * h), sp_desc(b), SP_IDESC0 | (((uint32_t)(kb - ka + 1) * 8u) << 17), accumulate);
+  };
+  auto run = [&](int h, int lo, int hi) {
+    const int b0 = hi < SEG0_HI ? hi : SEG0_HI;
+    if (lo <= b0) one(h, lo, b0, 1u);
+    if constexpr (S0 < BMAX) {
+      const int a1 = lo > S0 + 1 ? lo : S0 + 1;
+      if (a1 <= hi) one(h, a1, hi, 1u);
+    }
+  };
+  if (all_fresh) {                                     // p == 3, top of the image: every row present starts here
+    for (int k = kmin; k <= kmax; ++k) { one(0, k, k, 0u); one(1, k, k, 1u); }
+    return;
+  }
+  int lo = kmin;
+  if (PAR == 0 && kmin == 0) { one(0, 0, 0, 0u); lo = 1; }   // ky = 0: the row starts here and overwrites its accumulator
+  if (lo <= kmax) run(0, lo, kmax);
+  run(1, kmin, kmax);
+}
+
 __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPoolParams p) {
-  extern __shared__ __align__(128) uint8_t sp_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sp_smem_raw) + 127) & ~(uintptr_t)127);
+  extern __shared__ __align__(128) uint8_t sp_smem_raw[];    // nothing here needs more than 16-byte alignment (no swizzle)
+  uint8_t* smem = sp_smem_raw;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_base = sbase + SP_OFF_BARS;
   auto full_in = [&](int s) { return bar_base + 8u * s; };
@@ -170,14 +215,15 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
     // lane owns the pixel pairs q = lane + 32 j: the warp's four 16-byte stores per row are contiguous 512-byte runs.
     // A pair is 6 bytes at offset 6q: two aligned words from 6q & ~3, shifted by 16 bits when q is odd.
     uint32_t cur[8];
-    int cur_cnt = -1;
+    int cur_cnt = -1;                              // row slot of the staged-in-registers row
     const float k1r = p.k1[0], k1g = p.k1[1], k1b = p.k1[2], k0r = p.k0[0], k0g = p.k0[1], k0b = p.k0[2];
     auto nrm = [](uint32_t w, uint32_t sel, float k1, float k0) {
       return fmaf(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f, k1, k0);
     };
-    auto commit_row = [&](const uint32_t (&v)[8], uint32_t cnt) {
-      const uint32_t slot = cnt % SP_SLOTS;
-      mbar_wait(empty_in(slot), ((cnt / SP_SLOTS) & 1) ^ 1);
+    uint32_t ph_empty = 0;                         // per-slot phase bits (a slot is always filled by the same warp)
+    auto commit_row = [&](const uint32_t (&v)[8], uint32_t slot) {
+      mbar_wait(empty_in(slot), ((ph_empty >> slot) & 1) ^ 1);
+      ph_empty ^= 1u << slot;
       const uint32_t dst = sbase + SP_OFF_ROWS + slot * SP_SLOT_BYTES + 32;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -197,11 +243,9 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
       __syncwarp();
       if (lane == 0) mbar_arrive(full_in(slot));
     };
-    uint32_t cnt = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit t = make_unit(p, u);
-      for (int pp = t.p_lo; pp <= t.p_hi; ++pp, ++cnt) {
-        if ((cnt & (SP_PROD_WARPS - 1)) != (uint32_t)pw) continue;
+      for (int pp = t.p_lo + ((pw - t.p_lo) & (SP_PROD_WARPS - 1)); pp <= t.p_hi; pp += SP_PROD_WARPS) {   // rows with pp % 8 == pw
         uint32_t nxt[8];
         const uint8_t* rowp = p.img + ((size_t)t.n * H + (pp - 3)) * (size_t)W * 3;
 #pragma unroll
@@ -216,76 +260,89 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
         if (cur_cnt >= 0) commit_row(cur, (uint32_t)cur_cnt);
 #pragma unroll
         for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-        cur_cnt = (int)cnt;
+        cur_cnt = pp % SP_SLOTS;
       }
     }
     if (cur_cnt >= 0) commit_row(cur, (uint32_t)cur_cnt);
   } else if (warp == SP_MMA_WARP) {
     // ================================ MMA issue ================================
-    // fp16 A/B (format bits 0), fp32 accumulator (bit 4), K-major both, M = 128, N = 64 * blocks
-    constexpr uint32_t IDESC0 = (1u << 4) | ((uint32_t)(128 >> 4) << 24);
-    // descriptors as (hi, lo) words: hi = SBO 128 B | version, identical for A and B; lo = start address | LBO.  The loop
-    // only adds to the address field (everything stays below 256 KB, no carry into the LBO bits).
-    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-    const uint32_t a_lo0 = ((sbase + SP_OFF_ROWS) >> 4) | ((16u >> 4) << 16);
-    const uint32_t be_lo0 = ((sbase + SP_OFF_B) >> 4) | ((4096u >> 4) << 16);              // even tile: LBO = 256 rows * 16 B
-    const uint32_t bo_lo0 = ((sbase + SP_OFF_B + SP_B_ODD) >> 4) | ((3072u >> 4) << 16);   // odd tile: 192 rows
-    auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
-    uint32_t cnt = 0, acc_base = 0;
+    MmaBases mb;
+    mb.a_lo0 = ((sbase + SP_OFF_ROWS) >> 4) | ((16u >> 4) << 16);
+    mb.be_lo0 = ((sbase + SP_OFF_B) >> 4) | ((4096u >> 4) << 16);              // even tile: LBO = 256 rows * 16 B
+    mb.bo_lo0 = ((sbase + SP_OFF_B + SP_B_ODD) >> 4) | ((3072u >> 4) << 16);   // odd tile: 192 rows
+    mb.tmem = tmem_base;
+    uint32_t ph_full = 0, ph_aempty = 0;           // per-slot phase bits
+    auto take_acc = [&](uint32_t as) { mbar_wait(acc_empty(as), ((ph_aempty >> as) & 1) ^ 1); ph_aempty ^= 1u << as; };
+    auto take_row = [&](uint32_t slot) { mbar_wait(full_in(slot), (ph_full >> slot) & 1); ph_full ^= 1u << slot; };
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit t = make_unit(p, u);
-      for (int pp = t.p_lo; pp <= t.p_hi; ++pp, ++cnt) {
-        const uint32_t slot = cnt % SP_SLOTS;
-        // active output rows: oy_hi - k, k = 0 .. kmax, with ky = ky0 + 2k; accumulator slot (c_hi - k) % 8; weight block bmax - k
-        const int oy_hi = min(t.r_last, pp >> 1);
-        const int ky0 = pp - 2 * oy_hi, par = pp & 1;
-        const int bmax = (6 - par - ky0) >> 1;
-        const int kmax = min(bmax, oy_hi - t.r_first);
-        const uint32_t c_hi = acc_base + (uint32_t)(oy_hi - t.r_first);
-        // output rows that start with this input row need their accumulator back from the epilogue
-        if (pp == 3) {
-          for (int k = 0; k <= kmax; ++k) mbar_wait(acc_empty((c_hi - k) % SP_ACC), (((c_hi - k) / SP_ACC) & 1) ^ 1);
-        } else if (ky0 == 0) {
-          mbar_wait(acc_empty(c_hi % SP_ACC), ((c_hi / SP_ACC) & 1) ^ 1);
-        }
-        mbar_wait(full_in(slot), (cnt / SP_SLOTS) & 1);
+      // edge rows: the same schedule with run-time row ranges
+      auto edge = [&](int pp) {
+        const uint32_t slot = (uint32_t)pp % SP_SLOTS;
+        const int oy_top = pp >> 1, par = pp & 1;
+        const int kmin = max(0, oy_top - t.r_last), kmax = min(3 - par, oy_top - t.r_first);
+        const bool all_fresh = pp == 3;
+        if (all_fresh) { for (int k = kmin; k <= kmax; ++k) take_acc((uint32_t)(oy_top - k) % SP_ACC); }
+        else if (!par && kmin == 0) take_acc((uint32_t)oy_top % SP_ACC);
+        take_row(slot);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_lo = a_lo0 + slot * (SP_SLOT_BYTES >> 4);
-          const uint32_t b_lo = par ? bo_lo0 : be_lo0, b_half = par ? (6144u >> 4) : (8192u >> 4);
-          // one MMA over the rows k in [ka, kb] (consecutive slots, no wrap) for K step h
-          auto one = [&](int h, int ka, int kb, uint32_t accumulate) {
-            const uint32_t d = tmem_base + ((c_hi - (uint32_t)kb) % SP_ACC) * 64;
-            const uint32_t nb = (uint32_t)(kb - ka + 1);
-            umma_bf16(d, desc(a_lo + 2 * h), desc(b_lo + h * b_half + (uint32_t)(bmax - kb) * 64u), IDESC0 | ((nb * 8u) << 17), accumulate);
-          };
-          auto run = [&](int h, int ka, int kb) {
-            const int s_a = (int)((c_hi - (uint32_t)ka) % SP_ACC);       // slots fall from s_a; the ring wraps below 0
-            if (s_a >= kb - ka) one(h, ka, kb, 1u);
-            else { one(h, ka, ka + s_a, 1u); one(h, ka + s_a + 1, kb, 1u); }
-          };
-          if (pp == 3) {                         // top of the image: every row present starts here
-            for (int k = 0; k <= kmax; ++k) { one(0, k, k, 0u); one(1, k, k, 1u); }
-          } else {
-            const int kf = (ky0 == 0) ? 1 : 0;   // the starting row overwrites: its own MMA for the first K step
-            if (kf) one(0, 0, 0, 0u);
-            if (kmax >= kf) run(0, kf, kmax);
-            run(1, 0, kmax);
+          switch (slot) {
+            case 0: sp_issue<0>(mb, kmin, kmax, all_fresh); break;   case 1: sp_issue<1>(mb, kmin, kmax, all_fresh); break;
+            case 2: sp_issue<2>(mb, kmin, kmax, all_fresh); break;   case 3: sp_issue<3>(mb, kmin, kmax, all_fresh); break;
+            case 4: sp_issue<4>(mb, kmin, kmax, all_fresh); break;   case 5: sp_issue<5>(mb, kmin, kmax, all_fresh); break;
+            case 6: sp_issue<6>(mb, kmin, kmax, all_fresh); break;   case 7: sp_issue<7>(mb, kmin, kmax, all_fresh); break;
+            case 8: sp_issue<8>(mb, kmin, kmax, all_fresh); break;   case 9: sp_issue<9>(mb, kmin, kmax, all_fresh); break;
+            case 10: sp_issue<10>(mb, kmin, kmax, all_fresh); break; case 11: sp_issue<11>(mb, kmin, kmax, all_fresh); break;
+            case 12: sp_issue<12>(mb, kmin, kmax, all_fresh); break; case 13: sp_issue<13>(mb, kmin, kmax, all_fresh); break;
+            case 14: sp_issue<14>(mb, kmin, kmax, all_fresh); break; default: sp_issue<15>(mb, kmin, kmax, all_fresh); break;
           }
           umma_commit(empty_in(slot));
-          // output rows whose last contributing input row this is
-          if (!(pp & 1) && pp >= 6) {
-            const int oy = (pp - 6) >> 1;
-            if (oy >= t.r_first && oy <= t.r_last) umma_commit(acc_full((acc_base + (uint32_t)(oy - t.r_first)) % SP_ACC));
-          }
-          if (pp == H + 2) {          // the bottom row loses its last two taps to the padding
-            const int oy = (H >> 1) - 1;
-            if (oy >= t.r_first && oy <= t.r_last) umma_commit(acc_full((acc_base + (uint32_t)(oy - t.r_first)) % SP_ACC));
-          }
+          // output rows whose last contributing input row this is: ky = 6, or the bottom image row (two taps in the padding)
+          if (!par && kmin <= 3 && 3 <= kmax) umma_commit(acc_full((uint32_t)(oy_top - 3) % SP_ACC));
+          if (pp == H + 2 && kmin <= 2 && 2 <= kmax) umma_commit(acc_full((uint32_t)(oy_top - 2) % SP_ACC));
         }
         __syncwarp();
+      };
+      // interior rows [pp_a, pp_b]: all 4 / 3 output rows present
+      const int pp_a = max(t.p_lo, 2 * (t.r_first + 3)), pp_b = min(t.p_hi, 2 * t.r_last + 1);
+      int pp = t.p_lo;
+      for (; pp <= t.p_hi && pp < pp_a; ++pp) edge(pp);
+      if (pp <= pp_b) {
+        // straight-line sequence of the 16 ring positions, entered at pp % 16 (Duff's device): slots, phases' bit positions,
+        // descriptors and commit targets are immediates
+#define SP_STEP(I)                                                                           \
+        case I: {                                                                            \
+          if (pp > pp_b) break;                                                              \
+          if (((I) & 1) == 0) take_acc(((I) >> 1) % SP_ACC);                                 \
+          take_row(I);                                                                       \
+          tc_fence_after();                                                                  \
+          if (elect_one()) {                                                                 \
+            sp_issue<I>(mb, 0, 3 - ((I) & 1), false);                                        \
+            umma_commit(empty_in(I));                                                        \
+            if (((I) & 1) == 0) umma_commit(acc_full((((I) >> 1) + SP_ACC - 3) % SP_ACC));   \
+          }                                                                                  \
+          __syncwarp();                                                                      \
+          ++pp;                                                                              \
+        }
+        bool more = true;
+        switch (pp & 15) {
+          do {
+            SP_STEP(0) SP_STEP(1) SP_STEP(2) SP_STEP(3) SP_STEP(4) SP_STEP(5) SP_STEP(6) SP_STEP(7)
+            SP_STEP(8) SP_STEP(9) SP_STEP(10) SP_STEP(11) SP_STEP(12) SP_STEP(13) SP_STEP(14)
+            case 15: {
+              if (pp > pp_b) { more = false; break; }
+              take_row(15);
+              tc_fence_after();
+              if (elect_one()) { sp_issue<15>(mb, 0, 2, false); umma_commit(empty_in(15)); }
+              __syncwarp();
+              ++pp;
+            }
+          } while (more && pp <= pp_b);
+        }
+#undef SP_STEP
       }
-      acc_base += (uint32_t)(t.r_last - t.r_first + 1);
+      for (; pp <= t.p_hi; ++pp) edge(pp);
     }
   } else {
     // ================================ epilogue ================================
@@ -293,15 +350,16 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
     const int grp = warp >> 2, m = threadIdx.x & 127;
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * 32;
     const uint32_t stage0 = sbase + SP_OFF_STAGE + grp * 2 * SP_STAGE_BYTES;
-    uint32_t acc_base = 0, emit = 0;
+    uint32_t ph_afull = 0, emit = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit t = make_unit(p, u);
       uint32_t prev_odd[16], v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) { prev_odd[i] = 0u; v[i] = 0u; }
       for (int r = t.r_first; r <= t.r_last; ++r) {
-        const uint32_t c = acc_base + (uint32_t)(r - t.r_first), aslot = c % SP_ACC;
-        mbar_wait(acc_full(aslot), (c / SP_ACC) & 1);
+        const uint32_t aslot = (uint32_t)r % SP_ACC;
+        mbar_wait(acc_full(aslot), (ph_afull >> aslot) & 1);
+        ph_afull ^= 1u << aslot;
         tc_fence_after();
         uint32_t acc[32];
         tmem_ld32(lane_base + aslot * 64, acc);
@@ -344,7 +402,6 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
           ++emit;
         }
       }
-      acc_base += (uint32_t)(t.r_last - t.r_first + 1);
     }
   }
 

@@ -85,26 +85,34 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 // STEM_MODE: 0 = TMA-fed convolution / linear, 1 = fused stem from the uint8 NHWC image, 2 = fused stem from a float32
 // NCHW image in [0,1] (the attack path)
-template <int BN, int STEM_MODE, bool F16>
+// LEAN (fp16, not the stem): the epilogue instantiation for the common layer -- fp16 planes out through TMA stores,
+// Cout % 64 == 0, bias / scale / ReLU / dgrad mask only.  The general epilogue carries every variant (ragged columns, LSU
+// residual, fp32 outputs, five activations, split planes) behind run-time branches: 26 000 SASS instructions of which a
+// layer executes 900, spread over 400 KB of code -- ncu showed 22 % of the epilogue warps' samples stalled on instruction
+// fetch (stall_no_inst).  LEAN also double-buffers the staging tile so a store unit costs one named barrier and never waits
+// for its own TMA store (ring one stage shorter to pay for the second 32 KB).
+template <int BN, int STEM_MODE, bool F16, bool LEAN = false>
 __global__ void __launch_bounds__(STEM_MODE ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_i,
             const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
   constexpr bool STEM = STEM_MODE != 0;
   constexpr bool STEM_F32 = STEM_MODE == 2;
-  constexpr int kStages = ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
+  static_assert(!LEAN || (F16 && !STEM), "LEAN is the fp16 non-stem epilogue");
+  constexpr int kStages = LEAN ? (BN > 128 ? 3 : (BN == 128 ? 5 : 6)) : ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int B_OFF = F16 ? A_TILE_BYTES : 2 * A_TILE_BYTES;           // F16: [A | B]; split: [A_hi | A_lo | B_hi | B_lo]
   constexpr int STAGE_BYTES = B_OFF + (F16 ? 1 : 2) * B_TILE_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers (power of two: 128 or 256)
   // instruction descriptor: fp32 accumulator (bit 4), A/B format (bits 7, 10: 1 = bf16, 0 = fp16), N >> 3, M >> 4
   constexpr uint32_t IDESC = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  constexpr uint32_t IDESC_RES = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // residual k-blocks: N = 64
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int BAR_OFF = kStages * STAGE_BYTES;        // 1 KB: mbarriers + TMEM slot
   constexpr int STG_OFF = BAR_OFF + 1024;               // 2 x 16 KB epilogue staging ([2 planes][128 rows][64 B] per warp group)
-  constexpr int STEM_OFF = STG_OFF + 32768;             // STEM: staged input rows + LUT
+  constexpr int STEM_OFF = STG_OFF + 32768;             // STEM: staged input rows + LUT (LEAN: the staging area is 2 x 32 KB)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   // bars: [0,kStages) full, [kStages,2kStages) empty, [2k,2k+2) tmem_full, [2k+2,2k+4) tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
@@ -145,7 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const int t_end = STEM ? (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x) : total_tiles;
   const int t_step = STEM ? 1 : (int)gridDim.x;
   const int kb_conv = p.KH * p.KW * p.cin_blocks;
-  const int kb_res = p.res_mma ? BN / 64 : 0;           // residual k-blocks: R[:, 64j:64j+64] * I[:, 64j:64j+64]^T
+  const int kb_res = p.res_mma ? BN / 64 : 0;           // residual k-blocks: acc[:, 64j:64j+64] += R[:, 64j:64j+64] * I64^T
   const int kblocks = kb_conv + kb_res;
   const uint32_t a_bytes = (uint32_t)p.rows_box * BK * 2;
   const uint32_t tx_bytes = (p.passes == 3 ? 2u : 1u) * ((STEM ? 0u : a_bytes) + (uint32_t)B_TILE_BYTES);
@@ -182,10 +190,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         mbar_wait(empty_bar(stage), phase ^ 1);
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), (F16 ? 1u : 2u) * a_bytes + (uint32_t)B_TILE_BYTES);
+          // residual channels [64j, 64j+64) only touch accumulator columns [64j, 64j+64): the B operand is the 64 x 64
+          // identity (8 KB) and the MMA has N = 64, whatever BN is
+          mbar_expect_tx(full_bar(stage), (F16 ? 1u : 2u) * a_bytes + (uint32_t)(64 * BK * 2));
           tma_load_5d(sa, &map_r, full_bar(stage), nt * BN + j * BK, tw * p.bw, th * p.bh, n0, 0);
           if (!F16) tma_load_5d(sa + A_TILE_BYTES, &map_r, full_bar(stage), nt * BN + j * BK, tw * p.bw, th * p.bh, n0, 1);
-          tma_load_2d(sa + B_OFF, &map_i, full_bar(stage), j * BK, 0);
+          tma_load_2d(sa + B_OFF, &map_i, full_bar(stage), 0, 0);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -239,8 +249,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-            umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1);
-            if (!F16) umma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1);
+            umma_bf16(d_tmem + (uint32_t)(j * 64), a_hi + adv, b_hi + adv, IDESC_RES, 1);
+            if (!F16) umma_bf16(d_tmem + (uint32_t)(j * 64), a_lo + adv, b_hi + adv, IDESC_RES, 1);
           }
           umma_commit(empty_bar(stage));
           if (j == kb_res - 1) umma_commit(tfull_bar(acc));
@@ -258,6 +268,102 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int r = quarter * 32 + lane;
     const int box_hw = p.bh * p.bw;
     const int nl = r / box_hw, rem = r - nl * box_hw, hl = rem / p.bw, wl = rem - hl * p.bw;
+    if constexpr (LEAN) {
+      // store unit = 64 columns = full 128-byte rows of a SWIZZLE_128B staging tile (16 KB, one TMA store): the two
+      // 32-column chunks of one warp group (BN >= 128) or one chunk of each group (BN = 64)
+      constexpr int kColsPerWarp = BN / 2, kChunks = kColsPerWarp / 32, kPer = kChunks >= 2 ? 2 : 1;
+      constexpr bool kSharedUnit = BN == 64;
+      const bool uissuer = (quarter == 0) && (lane == 0) && (!kSharedUnit || half == 0);
+      uint32_t sb = 0;                                       // staging buffer of the next unit
+      int it = 0;
+      for (int t = t_first; t < t_end; t += t_step, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
+        const int n_img = ti * p.bn + nl, ho = th * p.bh + hl, wo = tw * p.bw + wl;
+        const bool row_ok = (r < p.rows_box) && (n_img < p.N) && (ho < p.Ho) && (wo < p.Wo);
+        const size_t out_row = ((size_t)n_img * p.Ho + ho) * p.Wo + wo;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
+#pragma unroll 1
+        for (int rd = 0; rd < kChunks / kPer; ++rd) {
+          uint32_t vv[kPer][32];
+#pragma unroll
+          for (int i = 0; i < kPer; ++i) tmem_ld32(t_addr + (uint32_t)((rd * kPer + i) * 32), vv[i]);
+          tmem_ld_wait();
+          if (rd == kChunks / kPer - 1) {                     // accumulator is in registers: hand the TMEM buffer back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          uint8_t* ustg = smem + STG_OFF + sb * 32768 + (kSharedUnit ? 0 : half * 16384);
+#pragma unroll
+          for (int ci = 0; ci < kPer; ++ci) {
+            const uint32_t (&v)[32] = vv[ci];
+            const int col0 = nt * BN + half * kColsPerWarp + (rd * kPer + ci) * 32;
+            float f[32];
+            if (p.scale) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + q);
+                const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                f[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), s4.x, b4.x);
+                f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, b4.y);
+                f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, b4.z);
+                f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, b4.w);
+              }
+            } else if (p.bias) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
+                f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b4.x;
+                f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b4.y;
+                f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b4.z;
+                f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            }
+            if (p.mask_hi && row_ok) {                        // ReLU backward fused into the dgrad GEMM: one fp16 plane read
+              uint32_t mw[16];
+              ld_global_v8(p.mask_hi + out_row * p.Cout + col0, mw);
+              ld_global_v8(p.mask_hi + out_row * p.Cout + col0 + 16, mw + 8);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t a0 = mw[j] & 0xFFFFu, a1 = mw[j] >> 16;
+                if (a0 == 0 || (a0 & 0x8000u)) f[2 * j] = 0.f;
+                if (a1 == 0 || (a1 & 0x8000u)) f[2 * j + 1] = 0.f;
+              }
+            }
+            if (p.act == B200R_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            const int sub = kSharedUnit ? half : ci;           // which 64-byte half of the 128-byte rows
+#pragma unroll
+            for (int q = 0; q < 4; ++q)                         // SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+              *reinterpret_cast<uint4*>(ustg + r * 128 + (((sub * 4 + q) ^ (r & 7)) << 4)) =
+                  make_uint4(cvt_f16x2(f[8 * q + 1], f[8 * q]), cvt_f16x2(f[8 * q + 3], f[8 * q + 2]),
+                             cvt_f16x2(f[8 * q + 5], f[8 * q + 4]), cvt_f16x2(f[8 * q + 7], f[8 * q + 6]));
+          }
+          fence_proxy_async();
+          // the previous unit's store (other buffer) was issued a whole unit ago: once it has read its tile, everybody
+          // past the barrier may overwrite that buffer while this unit's store is in flight
+          if (uissuer) bulk_wait_read0();
+          if (kSharedUnit) named_bar_sync(4, 256); else named_bar_sync(2 + half, 128);
+          if (uissuer) {
+            const int ucol0 = nt * BN + (kSharedUnit ? 0 : half * kColsPerWarp + rd * 64);
+            tma_store_5d(&map_y, smem_base + STG_OFF + sb * 32768 + (kSharedUnit ? 0 : half * 16384), ucol0, tw * p.bw, th * p.bh, ti * p.bn, 0);
+            bulk_commit();
+          }
+          sb ^= 1;
+        }
+      }
+      if (uissuer) bulk_wait0();                               // all stores complete before the CTA exits
+    } else {
     uint8_t* stg = smem + STG_OFF + half * 16384;
     const uint32_t stg_u32 = smem_base + STG_OFF + half * 16384;
     const bool issuer = (quarter == 0) && (lane == 0);
@@ -457,6 +563,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       }
     }
     if (issuer) bulk_wait0();                              // all stores complete before the CTA exits
+    }
   } else if (STEM) {
     // ===================== stem A producer (8 warps) =====================
     // 7x7 / stride 2 / pad 3 patches of the uint8 NHWC image.  A tile = ONE output row of one image
@@ -641,21 +748,21 @@ EncodeTiledFn get_encode() {
 
 struct GemmMaps { CUtensorMap a, b, r, i, y; };
 
-template <int BN, int STEM, bool F16>
+template <int BN, int STEM, bool F16, bool LEAN = false>
 int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t s) {
-  constexpr int kStages = ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
+  constexpr int kStages = LEAN ? (BN > 128 ? 3 : (BN == 128 ? 5 : 6)) : ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
   constexpr int STAGE_BYTES = (2 * A_TILE_BYTES + 2 * BN * BK * 2) / (F16 ? 2 : 1);
   // STEM adds the staged input rows (7 x (W_in*3 + 24) words) and the 3 KB LUT behind the barriers
   const int smem = kStages * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ +
-                   ((STEM || p.tma_store) ? 32768 : 0) /*epilogue staging*/ + (STEM ? 7 * (p.W_in * 3 + 24) * 4 + 768 * 4 : 0);
+                   (LEAN ? 65536 : ((STEM || p.tma_store) ? 32768 : 0)) /*epilogue staging*/ + (STEM ? 7 * (p.W_in * 3 + 24) * 4 + 768 * 4 : 0);
   static int configured = 0;
   if (configured < smem) {
-    B200R_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STEM, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200R_CUDA((cudaFuncSetAttribute(gemm_kernel<BN, STEM, F16, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
     configured = smem;
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_img * p.tiles_n;
   const int grid = total < b200r_num_sms() ? total : b200r_num_sms();
-  gemm_kernel<BN, STEM, F16><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(m.a, m.b, m.r, m.i, m.y, p);
+  gemm_kernel<BN, STEM, F16, LEAN><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(m.a, m.b, m.r, m.i, m.y, p);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
@@ -698,7 +805,7 @@ int get_identity(const uint16_t** out, bool f16) {
 
 // output / residual / identity maps + flags shared by conv_impl and the fused stem
 // tuning switch for experiments: B200R_GEMM_OPTS bit 0 = epilogue stores through the LSU instead of TMA,
-// bit 1 = residual through the LSU instead of identity k-blocks
+// bit 1 = residual through the LSU instead of identity k-blocks, bit 2 = general epilogue instead of the LEAN one
 int gemm_opts() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("B200R_GEMM_OPTS"); v = e ? atoi(e) : 0; }
@@ -724,7 +831,7 @@ int finish_maps(EncodeTiledFn enc, GemmMaps* m, GemmParams* p, const uint16_t* r
     if (rc) return rc;
     cuuint64_t dims[2] = {256, 256};
     cuuint64_t strides[1] = {512};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t box[2] = {(cuuint32_t)BK, 64};     // the 64 x 64 identity block (the kernel slides the accumulator columns instead)
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&m->i, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(ident), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -813,6 +920,13 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
     if (rc) return rc;
   }
   if (f16) {
+    // the compact epilogue: fp16 planes through TMA stores, whole 64-column units, bias / scale / ReLU / mask only
+    const bool lean = p.tma_store && y && !y_f32 && Cout % BN == 0 && (!res || p.res_mma) &&
+                      (act == B200R_ACT_NONE || act == B200R_ACT_RELU) && !(gemm_opts() & 4);
+    if (lean) {
+      if (BN == 256) return launch<256, 0, true, true>(m, p, s);
+      return BN == 64 ? launch<64, 0, true, true>(m, p, s) : launch<128, 0, true, true>(m, p, s);
+    }
     if (BN == 256) return launch<256, 0, true>(m, p, s);
     return BN == 64 ? launch<64, 0, true>(m, p, s) : launch<128, 0, true>(m, p, s);
   }

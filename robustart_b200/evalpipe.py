@@ -60,6 +60,51 @@ class CorruptEvalPipeline:
         torch.cuda.current_stream().synchronize()
         return self.h_counters
 
+    # -- double-buffered host interface: the H2D copy of step i+1 runs on a copy stream under step i's kernels --------
+    def _init_pipelined(self):
+        dev = self.device
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._d_images2 = [self.d_images, torch.empty_like(self.d_images)]
+        self._d_labels2 = [self.d_labels, torch.empty_like(self.d_labels)]
+        self._h_counters2 = [self.h_counters, torch.zeros(3, dtype=torch.int64).pin_memory()]
+        self._ready = [torch.cuda.Event(), torch.cuda.Event()]     # H2D of buffer k landed
+        self._free = [torch.cuda.Event(), torch.cuda.Event()]      # buffer k's consumer kernels finished
+        self._done = [torch.cuda.Event(), torch.cuda.Event()]      # counters of the step that used buffer k are on the host
+        self._hk = 0
+
+    def step_host_pipelined(self, images_pinned: torch.Tensor, labels_pinned: torch.Tensor, corruption, severity: int):
+        """Same contract as step_host (pinned host batch in, counters on the host out, every step), software-pipelined:
+        this step's H2D copy is issued on a copy stream and only the PREVIOUS step's counters are waited for, so the host
+        stays one step ahead and the 38.5 MB copy hides under the previous step's kernels.  Returns the pinned counters as
+        of the previous step (None on the first call); finish() returns the final ones."""
+        if not hasattr(self, "_hk"):
+            self._init_pipelined()
+        k = self._hk & 1
+        cur, cs = torch.cuda.current_stream(), self._copy_stream
+        cs.wait_event(self._free[k])
+        with torch.cuda.stream(cs):
+            self._d_images2[k].copy_(images_pinned, non_blocking=True)
+            self._d_labels2[k].copy_(labels_pinned, non_blocking=True)
+            self._ready[k].record(cs)
+        cur.wait_event(self._ready[k])
+        self.step_device(self._d_images2[k], self._d_labels2[k], corruption, severity)
+        self._free[k].record(cur)
+        self._h_counters2[k].copy_(self.counters, non_blocking=True)
+        self._done[k].record(cur)
+        self._hk += 1
+        if self._hk >= 2:
+            self._done[k ^ 1].synchronize()
+            return self._h_counters2[k ^ 1]
+        return None
+
+    def finish(self):
+        """Drain the pipelined interface: counters after the last submitted step (pinned int64[3])."""
+        if not getattr(self, "_hk", 0):
+            return self.h_counters
+        k = (self._hk - 1) & 1
+        self._done[k].synchronize()
+        return self._h_counters2[k]
+
     def allreduce_counters(self):
         """The single collective of an evaluation: sum the counters over ranks (NCCL over NVLink)."""
         import torch.distributed as dist

@@ -93,3 +93,41 @@ def test_multi_eval_cli(cuda, tmp_path, monkeypatch):
     assert list(res) == ["resnet18"] and res["resnet18"]["count"] == 32
     st = open(tmp_path / "status.txt").read()
     assert "resnet18 done" in st and "Error when load no_such_model" in st
+
+
+@pytest.mark.parametrize("passes", [16, 3])
+def test_eval_pipeline_interfaces_agree(cuda, passes):
+    """CorruptEvalPipeline: device-resident steps, synchronous host steps and the double-buffered host interface (H2D on a
+    copy stream, counters read one step late) count the same hits as the eager ops on the same batches -- the loop body of
+    cls_solver.py:404-428 + imagenet_evaluator.py:49-67 with AddNoise('imagenet-c') in front."""
+    from robustart_b200 import nets, ops
+    from robustart_b200.evalpipe import CorruptEvalPipeline
+    from util import synth_images
+    model = nets.build_model("resnet18", device=cuda, seed=0, passes=passes)
+    bs, steps = 8, 5
+    imgs = [torch.from_numpy(synth_images(bs, seed=20 + i)) for i in range(steps)]
+    g = torch.Generator().manual_seed(5)
+    labels = [torch.randint(0, 1000, (bs,), generator=g) for _ in range(steps)]
+    # eager restatement: corruption (counter-based RNG keyed by the global image index) -> forward -> top-k hits
+    want = torch.zeros(3, dtype=torch.int64)
+    for i in range(steps):
+        x = ops.corrupt_u8(imgs[i].to(cuda), "gaussian_noise", 1 + i % 5, seed=3, image_offset=i * bs)
+        lg = model(x).cpu()
+        top5 = lg.topk(5, dim=1).indices
+        want += torch.tensor([(top5[:, 0] == labels[i]).sum(), (top5 == labels[i][:, None]).any(1).sum(), bs])
+    pipe = CorruptEvalPipeline(model, batch=bs, seed=3)
+    for i in range(steps):
+        pipe.step_device(imgs[i].to(cuda), labels[i].to(cuda), "gaussian_noise", 1 + i % 5)
+    assert torch.equal(pipe.counters.cpu(), want)
+    pipe.reset()
+    for i in range(steps):
+        got = pipe.step_host(imgs[i].pin_memory(), labels[i].pin_memory(), "gaussian_noise", 1 + i % 5)
+    assert torch.equal(got, want)
+    pipe.reset()
+    pinned = [(a.pin_memory(), b.pin_memory()) for a, b in zip(imgs, labels)]
+    seen = []
+    for i in range(steps):
+        r = pipe.step_host_pipelined(pinned[i][0], pinned[i][1], "gaussian_noise", 1 + i % 5)
+        seen.append(None if r is None else r.clone())
+    assert seen[0] is None and all(int(s[2]) == bs * i for i, s in enumerate(seen) if s is not None)   # one step late
+    assert torch.equal(pipe.finish(), want)

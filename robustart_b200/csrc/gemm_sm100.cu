@@ -83,23 +83,32 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// erf by Abramowitz & Stegun 7.1.26 (|error| < 1.5e-7) on ex2 / rcp: 12 instructions instead of erff's 30
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x), t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  return copysignf(1.f - poly * __expf(-ax * ax), x);
+}
+
 // STEM_MODE: 0 = TMA-fed convolution / linear, 1 = fused stem from the uint8 NHWC image, 2 = fused stem from a float32
 // NCHW image in [0,1] (the attack path)
-// LEAN (fp16, not the stem): the epilogue instantiation for the common layer -- fp16 planes out through TMA stores,
-// Cout % 64 == 0, bias / scale / ReLU / dgrad mask only.  The general epilogue carries every variant (ragged columns, LSU
+// LEAN (not the stem): the epilogue instantiation for the common layer -- planes out through TMA stores (Cout % 8 == 0),
+// bias / scale / activation / dgrad mask, residual on the tensor core or none, no fp32 output.  The general epilogue carries every variant (ragged columns, LSU
 // residual, fp32 outputs, five activations, split planes) behind run-time branches: 26 000 SASS instructions of which a
 // layer executes 900, spread over 400 KB of code -- ncu showed 22 % of the epilogue warps' samples stalled on instruction
 // fetch (stall_no_inst).  LEAN also double-buffers the staging tile so a store unit costs one named barrier and never waits
 // for its own TMA store (ring one stage shorter to pay for the second 32 KB).
-template <int BN, int STEM_MODE, bool F16, bool LEAN = false>
+// ACTS (LEAN only): 0 = the instantiation knows none / ReLU only (the convolution stacks), 1 = all activations.
+template <int BN, int STEM_MODE, bool F16, bool LEAN = false, int ACTS = 1>
 __global__ void __launch_bounds__(STEM_MODE ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_i,
             const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
   constexpr bool STEM = STEM_MODE != 0;
   constexpr bool STEM_F32 = STEM_MODE == 2;
-  static_assert(!LEAN || (F16 && !STEM), "LEAN is the fp16 non-stem epilogue");
-  constexpr int kStages = LEAN ? (BN > 128 ? 3 : (BN == 128 ? 5 : 6)) : ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
+  static_assert(!LEAN || !STEM, "LEAN is a non-stem epilogue");
+  // LEAN + fp16 double-buffers the 32 KB staging area and gives up ring stages for it
+  constexpr int kStages = (LEAN && F16) ? (BN > 128 ? 3 : (BN == 128 ? 5 : 6)) : ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int B_OFF = F16 ? A_TILE_BYTES : 2 * A_TILE_BYTES;           // F16: [A | B]; split: [A_hi | A_lo | B_hi | B_lo]
   constexpr int STAGE_BYTES = B_OFF + (F16 ? 1 : 2) * B_TILE_BYTES;
@@ -269,12 +278,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int box_hw = p.bh * p.bw;
     const int nl = r / box_hw, rem = r - nl * box_hw, hl = rem / p.bw, wl = rem - hl * p.bw;
     if constexpr (LEAN) {
-      // store unit = 64 columns = full 128-byte rows of a SWIZZLE_128B staging tile (16 KB, one TMA store): the two
-      // 32-column chunks of one warp group (BN >= 128) or one chunk of each group (BN = 64)
+      // fp16: store unit = 64 columns = full 128-byte rows of a SWIZZLE_128B staging tile (16 KB, one TMA store) -- the two
+      // 32-column chunks of one warp group (BN >= 128) or one chunk of each group (BN = 64); units alternate between two
+      // staging buffers.  split-bf16: store unit = one 32-column chunk, hi and lo planes as two SWIZZLE_64B tiles (8 KB
+      // each) in the group's single 16 KB buffer.
       constexpr int kColsPerWarp = BN / 2, kChunks = kColsPerWarp / 32, kPer = kChunks >= 2 ? 2 : 1;
-      constexpr bool kSharedUnit = BN == 64;
-      const bool uissuer = (quarter == 0) && (lane == 0) && (!kSharedUnit || half == 0);
-      uint32_t sb = 0;                                       // staging buffer of the next unit
+      constexpr bool kSharedUnit = F16 && BN == 64;
+      const bool issuer = (quarter == 0) && (lane == 0);
+      const bool uissuer = issuer && (!kSharedUnit || half == 0);
+      uint32_t sb = 0;                                       // fp16: staging buffer of the next unit
       int it = 0;
       for (int t = t_first; t < t_end; t += t_step, ++it) {
         const int acc = it & 1;
@@ -298,71 +310,165 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
-          uint8_t* ustg = smem + STG_OFF + sb * 32768 + (kSharedUnit ? 0 : half * 16384);
 #pragma unroll
           for (int ci = 0; ci < kPer; ++ci) {
             const uint32_t (&v)[32] = vv[ci];
             const int col0 = nt * BN + half * kColsPerWarp + (rd * kPer + ci) * 32;
+            const bool live = col0 < p.Cout;                  // uniform across the warp group (ragged Cout: whole chunks drop out)
             float f[32];
-            if (p.scale) {
+            if (live) {
+              if (col0 + 32 <= p.Cout) {
+                if (p.scale) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + q);
-                const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                f[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), s4.x, b4.x);
-                f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, b4.y);
-                f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, b4.z);
-                f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, b4.w);
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + q);
+                    const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    f[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), s4.x, b4.x);
+                    f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, b4.y);
+                    f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, b4.z);
+                    f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, b4.w);
+                  }
+                } else if (p.bias) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
+                    f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b4.x;
+                    f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b4.y;
+                    f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b4.z;
+                    f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b4.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                }
+              } else {                                        // last, partial chunk of a ragged Cout (the TMA store clips it)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int col = min(col0 + j, p.Cout - 1);
+                  f[j] = fmaf(__uint_as_float(v[j]), p.scale ? __ldg(p.scale + col) : 1.f, p.bias ? __ldg(p.bias + col) : 0.f);
+                }
               }
-            } else if (p.bias) {
+              if (p.mask_hi && row_ok) {                      // ReLU backward fused into the dgrad GEMM: one 16-bit plane read
+                const size_t off = out_row * p.Cout + col0;
+                if (col0 + 32 <= p.Cout && (p.Cout % 16 == 0)) {
+                  uint32_t mw[16];
+                  ld_global_v8(p.mask_hi + off, mw);
+                  ld_global_v8(p.mask_hi + off + 16, mw + 8);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
-                f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b4.x;
-                f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b4.y;
-                f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b4.z;
-                f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b4.w;
+                  for (int j = 0; j < 16; ++j) {
+                    const uint32_t a0 = mw[j] & 0xFFFFu, a1 = mw[j] >> 16;
+                    if (a0 == 0 || (a0 & 0x8000u)) f[2 * j] = 0.f;
+                    if (a1 == 0 || (a1 & 0x8000u)) f[2 * j + 1] = 0.f;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (col0 + j < p.Cout) {
+                      const uint32_t a = p.mask_hi[off + j];
+                      if (a == 0 || (a & 0x8000u)) f[j] = 0.f;
+                    }
+                }
+              }
+              if constexpr (ACTS == 0) {
+                if (p.act == B200R_ACT_RELU) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+              } else {
+                // activations on the MUFU (ex2 / rcp): each case is one straight run of code, absolute error ~1e-7
+                switch (p.act) {
+                  case B200R_ACT_NONE: break;
+                  case B200R_ACT_RELU:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    break;
+                  case B200R_ACT_RELU6:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fminf(fmaxf(f[j], 0.f), 6.f);
+                    break;
+                  case B200R_ACT_GELU_TANH:                      // 0.5 v (1 + tanh(u)) = v / (1 + exp(-2u)), u = k (v + 0.044715 v^3)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                      const float x = f[j], u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+                      f[j] = __fdividef(x, 1.f + __expf(-2.f * u));
+                    }
+                    break;
+                  case B200R_ACT_GELU_ERF:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + fast_erf(f[j] * 0.7071067811865476f));
+                    break;
+                  case B200R_ACT_SWISH:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.f + __expf(-f[j]));
+                    break;
+                  case B200R_ACT_TANH:
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = 1.f - __fdividef(2.f, 1.f + __expf(2.f * f[j]));
+                    break;
+                  default:                                        // B200R_ACT_SIGMOID
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __fdividef(1.f, 1.f + __expf(-f[j]));
+                    break;
+                }
+              }
+            }
+            if constexpr (F16) {
+              if (live) {
+                uint8_t* ustg = smem + STG_OFF + sb * 32768 + (kSharedUnit ? 0 : half * 16384);
+                const int sub = kSharedUnit ? half : ci;         // which 64-byte half of the 128-byte rows
+#pragma unroll
+                for (int q = 0; q < 4; ++q)                       // SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+                  *reinterpret_cast<uint4*>(ustg + r * 128 + (((sub * 4 + q) ^ (r & 7)) << 4)) =
+                      make_uint4(cvt_f16x2(f[8 * q + 1], f[8 * q]), cvt_f16x2(f[8 * q + 3], f[8 * q + 2]),
+                                 cvt_f16x2(f[8 * q + 5], f[8 * q + 4]), cvt_f16x2(f[8 * q + 7], f[8 * q + 6]));
               }
             } else {
+              // split planes: the group's buffer must have been read by the previous chunk's stores before it is rewritten
+              uint8_t* stg = smem + STG_OFF + half * 16384;
+              if (issuer) bulk_wait_read0();
+              named_bar_sync(2 + half, 128);
+              if (live) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            }
-            if (p.mask_hi && row_ok) {                        // ReLU backward fused into the dgrad GEMM: one fp16 plane read
-              uint32_t mw[16];
-              ld_global_v8(p.mask_hi + out_row * p.Cout + col0, mw);
-              ld_global_v8(p.mask_hi + out_row * p.Cout + col0 + 16, mw + 8);
+                for (int q = 0; q < 4; ++q) {
+                  uint32_t ph[4], pl[4];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const uint32_t a0 = mw[j] & 0xFFFFu, a1 = mw[j] >> 16;
-                if (a0 == 0 || (a0 & 0x8000u)) f[2 * j] = 0.f;
-                if (a1 == 0 || (a1 & 0x8000u)) f[2 * j + 1] = 0.f;
+                  for (int j = 0; j < 4; ++j) {
+                    const float x0 = f[8 * q + 2 * j], x1 = f[8 * q + 2 * j + 1];
+                    ph[j] = cvt_bf16x2(x1, x0);
+                    pl[j] = cvt_bf16x2(x1 - __uint_as_float(ph[j] & 0xFFFF0000u), x0 - __uint_as_float(ph[j] << 16));
+                  }
+                  // 64-byte rows in the TMA SWIZZLE_64B pattern (16-byte chunk index ^= (row >> 1) & 3): conflict-free stores
+                  const int pos = (q ^ ((r >> 1) & 3)) * 16;
+                  *reinterpret_cast<uint4*>(stg + r * 64 + pos) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                  *reinterpret_cast<uint4*>(stg + 8192 + r * 64 + pos) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                }
+              }
+              fence_proxy_async();
+              named_bar_sync(2 + half, 128);
+              if (issuer && live) {
+                const uint32_t stg_u32 = smem_base + STG_OFF + half * 16384;
+                tma_store_5d(&map_y, stg_u32, col0, tw * p.bw, th * p.bh, ti * p.bn, 0);
+                tma_store_5d(&map_y, stg_u32 + 8192, col0, tw * p.bw, th * p.bh, ti * p.bn, 1);
+                bulk_commit();
               }
             }
-            if (p.act == B200R_ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            const int sub = kSharedUnit ? half : ci;           // which 64-byte half of the 128-byte rows
-#pragma unroll
-            for (int q = 0; q < 4; ++q)                         // SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
-              *reinterpret_cast<uint4*>(ustg + r * 128 + (((sub * 4 + q) ^ (r & 7)) << 4)) =
-                  make_uint4(cvt_f16x2(f[8 * q + 1], f[8 * q]), cvt_f16x2(f[8 * q + 3], f[8 * q + 2]),
-                             cvt_f16x2(f[8 * q + 5], f[8 * q + 4]), cvt_f16x2(f[8 * q + 7], f[8 * q + 6]));
           }
-          fence_proxy_async();
-          // the previous unit's store (other buffer) was issued a whole unit ago: once it has read its tile, everybody
-          // past the barrier may overwrite that buffer while this unit's store is in flight
-          if (uissuer) bulk_wait_read0();
-          if (kSharedUnit) named_bar_sync(4, 256); else named_bar_sync(2 + half, 128);
-          if (uissuer) {
+          if constexpr (F16) {
+            fence_proxy_async();
+            // the previous unit's store (other buffer) was issued a whole unit ago: once it has read its tile, everybody
+            // past the barrier may overwrite that buffer while this unit's store is in flight
+            if (uissuer) bulk_wait_read0();
+            if (kSharedUnit) named_bar_sync(4, 256); else named_bar_sync(2 + half, 128);
             const int ucol0 = nt * BN + (kSharedUnit ? 0 : half * kColsPerWarp + rd * 64);
-            tma_store_5d(&map_y, smem_base + STG_OFF + sb * 32768 + (kSharedUnit ? 0 : half * 16384), ucol0, tw * p.bw, th * p.bh, ti * p.bn, 0);
-            bulk_commit();
+            if (uissuer && ucol0 < p.Cout) {
+              tma_store_5d(&map_y, smem_base + STG_OFF + sb * 32768 + (kSharedUnit ? 0 : half * 16384), ucol0, tw * p.bw, th * p.bh, ti * p.bn, 0);
+              bulk_commit();
+            }
+            sb ^= 1;
           }
-          sb ^= 1;
         }
       }
-      if (uissuer) bulk_wait0();                               // all stores complete before the CTA exits
+      if (issuer) bulk_wait0();                                 // all stores complete before the CTA exits
     } else {
     uint8_t* stg = smem + STG_OFF + half * 16384;
     const uint32_t stg_u32 = smem_base + STG_OFF + half * 16384;
@@ -748,21 +854,21 @@ EncodeTiledFn get_encode() {
 
 struct GemmMaps { CUtensorMap a, b, r, i, y; };
 
-template <int BN, int STEM, bool F16, bool LEAN = false>
+template <int BN, int STEM, bool F16, bool LEAN = false, int ACTS = 1>
 int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t s) {
-  constexpr int kStages = LEAN ? (BN > 128 ? 3 : (BN == 128 ? 5 : 6)) : ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
+  constexpr int kStages = (LEAN && F16) ? (BN > 128 ? 3 : (BN == 128 ? 5 : 6)) : ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
   constexpr int STAGE_BYTES = (2 * A_TILE_BYTES + 2 * BN * BK * 2) / (F16 ? 2 : 1);
   // STEM adds the staged input rows (7 x (W_in*3 + 24) words) and the 3 KB LUT behind the barriers
   const int smem = kStages * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ +
-                   (LEAN ? 65536 : ((STEM || p.tma_store) ? 32768 : 0)) /*epilogue staging*/ + (STEM ? 7 * (p.W_in * 3 + 24) * 4 + 768 * 4 : 0);
+                   ((LEAN && F16) ? 65536 : ((STEM || p.tma_store) ? 32768 : 0)) /*epilogue staging*/ + (STEM ? 7 * (p.W_in * 3 + 24) * 4 + 768 * 4 : 0);
   static int configured = 0;
   if (configured < smem) {
-    B200R_CUDA((cudaFuncSetAttribute(gemm_kernel<BN, STEM, F16, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+    B200R_CUDA((cudaFuncSetAttribute(gemm_kernel<BN, STEM, F16, LEAN, ACTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
     configured = smem;
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_img * p.tiles_n;
   const int grid = total < b200r_num_sms() ? total : b200r_num_sms();
-  gemm_kernel<BN, STEM, F16, LEAN><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(m.a, m.b, m.r, m.i, m.y, p);
+  gemm_kernel<BN, STEM, F16, LEAN, ACTS><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(m.a, m.b, m.r, m.i, m.y, p);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
@@ -919,17 +1025,25 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
     int rc = finish_maps(enc, &m, &p, res, y, ycount, BN, f16);
     if (rc) return rc;
   }
+  // the compact epilogue: planes out through TMA stores (Cout % 8 == 0), residual on the tensor core or none, no fp32 output
+  const bool lean = p.tma_store && y && !y_f32 && (!res || p.res_mma) && !(gemm_opts() & 4);
+  const bool simple_act = (act == B200R_ACT_NONE || act == B200R_ACT_RELU);
+#define B200R_LAUNCH_LEAN(F)                                                                                        \
+  do {                                                                                                              \
+    if (simple_act) {                                                                                               \
+      if (BN == 256) return launch<256, 0, F, true, 0>(m, p, s);                                                    \
+      return BN == 64 ? launch<64, 0, F, true, 0>(m, p, s) : launch<128, 0, F, true, 0>(m, p, s);                   \
+    }                                                                                                               \
+    if (BN == 256) return launch<256, 0, F, true, 1>(m, p, s);                                                      \
+    return BN == 64 ? launch<64, 0, F, true, 1>(m, p, s) : launch<128, 0, F, true, 1>(m, p, s);                     \
+  } while (0)
   if (f16) {
-    // the compact epilogue: fp16 planes through TMA stores, whole 64-column units, bias / scale / ReLU / mask only
-    const bool lean = p.tma_store && y && !y_f32 && Cout % BN == 0 && (!res || p.res_mma) &&
-                      (act == B200R_ACT_NONE || act == B200R_ACT_RELU) && !(gemm_opts() & 4);
-    if (lean) {
-      if (BN == 256) return launch<256, 0, true, true>(m, p, s);
-      return BN == 64 ? launch<64, 0, true, true>(m, p, s) : launch<128, 0, true, true>(m, p, s);
-    }
+    if (lean) B200R_LAUNCH_LEAN(true);
     if (BN == 256) return launch<256, 0, true>(m, p, s);
     return BN == 64 ? launch<64, 0, true>(m, p, s) : launch<128, 0, true>(m, p, s);
   }
+  if (lean) B200R_LAUNCH_LEAN(false);
+#undef B200R_LAUNCH_LEAN
   if (BN == 256) return launch<256, 0, false>(m, p, s);
   return BN == 64 ? launch<64, 0, false>(m, p, s) : launch<128, 0, false>(m, p, s);
 }

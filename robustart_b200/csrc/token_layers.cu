@@ -7,6 +7,9 @@
 //   attention          softmax(q k^T * scale) v per (image, head), fp32 on CUDA cores (vision_transformer.py:80-92)
 //   token transpose    [b, t, c] <-> [b, c, t_pad] for Mixer token mixing (mlp_mixer.py:30-40), residual fused
 #include "common.cuh"
+#include <stdlib.h>
+
+int b200r_attention_tc(const uint16_t* qkv, uint16_t* out, int n, int tokens, int heads, float scale, cudaStream_t stream);   // attention_sm100.cu
 
 namespace {
 constexpr int kThreads = 256;
@@ -294,6 +297,15 @@ int b200r_attention(const uint16_t* qkv, uint16_t* out, int n, int tokens, int h
   B200R_CHECK_ARG(qkv && out, "null pointer");
   B200R_CHECK_ARG(n > 0 && tokens > 0 && heads > 0, "bad shape");
   B200R_CHECK_ARG(head_dim == 64, "head_dim %d not supported (64 only)", head_dim);
+  {
+    // tensor-core kernel (attention_sm100.cu) for sequences up to 256 tokens; B200R_ATTN_TC=0 keeps the CUDA-core kernel
+    static int use_tc = -1;
+    if (use_tc < 0) { const char* e = getenv("B200R_ATTN_TC"); use_tc = (e && e[0] == '0') ? 0 : 1; }
+    if (use_tc) {
+      const int rc = b200r_attention_tc(qkv, out, n, tokens, heads, scale, as_stream(stream));
+      if (rc != B200R_ENOTSUP) return rc;
+    }
+  }
   const size_t cin = (size_t)n * tokens * 3 * heads * head_dim, cout = (size_t)n * tokens * heads * head_dim;
   const int Tp = (tokens + 31) & ~31;
   const size_t smem = ((size_t)2 * tokens * (head_dim + 1) + (kAttnThreads / 32) * (head_dim + Tp)) * sizeof(float);

@@ -211,17 +211,44 @@ class EvalSolver:
 
     # cls_solver.py:352-457
     def evaluate(self, model, corruption=None, severity=1):
+        """Counters on the device + one all-reduce.  With `data.test.dump_results: true` the reference's result files are
+        written as well (resultfile.py: `<tag>.txt.rank{r}` per-image lines with the softmax scores, merged `.all`,
+        file-based top-k next to the counter metric) -- the opt-in compatibility mode for downstream parsers."""
         from RobustART.noise.utils import add_noise_utils as anu
         counters = torch.zeros(3, dtype=torch.int64, device=self.device)
+        tag = "results" if corruption is None else "noise-%s-%d-results" % (corruption, severity)
+        dump = bool(self.config.data.get("test", {}).get("dump_results", False))
+        writer = None
+        if dump:
+            from . import resultfile
+            writer = resultfile.ResultWriter(self.result_path, self.dist.rank, stem=tag + ".txt")
+            pred = torch.empty(self.batch_size, dtype=torch.int64, device=self.device)
         done = 0
         for imgs, labels in self._batches():
+            n = imgs.shape[0]
             if corruption is not None:
                 ops.corrupt_u8(imgs, corruption, severity, seed=anu._seed(), image_offset=int(self.indices[done]), out=imgs)
             logits = model(imgs)
-            ops.topk_count_(counters, logits, labels)
-            done += imgs.shape[0]
-        tag = "results" if corruption is None else "noise-%s-%d-results" % (corruption, severity)
-        return self._finish(counters, tag)
+            if writer is None:
+                ops.topk_count_(counters, logits, labels)
+            else:
+                ops.topk_count_(counters, logits, labels, pred[:n])
+                ids = self.indices[done:done + n].tolist()
+                writer.write_batch(pred[:n].cpu().numpy(), labels.cpu().numpy(), ops.softmax(logits).cpu().numpy(),
+                                   ["synthetic/%08d.JPEG" % i for i in ids], ids)
+            done += n
+        metric = self._finish(counters, tag)
+        if writer is not None:
+            from . import resultfile
+            writer.close()
+            if self.dist.initialized and self.dist.world_size > 1:
+                import torch.distributed as dist
+                dist.barrier()
+            if self.dist.rank == 0:
+                merged = resultfile.merge(os.path.join(self.result_path, tag + ".txt.rank"), self.dist.world_size)
+                metric["result_file"] = merged
+                metric["file_metric"] = resultfile.evaluate(merged)
+        return metric
 
     # imgnet_c_solver.py:374-470 + datasets/imagnetc.py:165-218
     IMAGENET_C_GROUPS = {

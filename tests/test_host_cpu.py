@@ -34,3 +34,28 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(TypeError):
         ops.corrupt_u8(torch.zeros((1, 224, 224, 3), dtype=torch.uint8), 'gaussian_noise', 1)
+
+
+def test_result_file_mode_matches_reference_dump(tmp_path):
+    """robustart_b200.resultfile against text produced by the reference's own ImageNetDataset.dump / BaseDataset.merge /
+    ImageNetEvaluator.eval (tests/golden/make_golden_results.py): byte-identical lines (incl. the float("%.8f" % s) rounding
+    traps: ties at the 9th decimal, the 1e-4 repr switch, denormals), same merged file, same top-k metrics."""
+    import json
+    import os
+    import numpy as np
+    from robustart_b200 import resultfile as R
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "result_lines.json")))
+    scores = np.frombuffer(bytes.fromhex(g["scores_f32_bytes_hex"]), dtype=np.float32).reshape(g["shape"])
+    pred, label = np.array(g["prediction"]), np.array(g["label"])
+    fn, ids = ["val/a_%d.JPEG" % i for i in range(4)], [7, 8, 9, 10]
+    assert R.format_lines(pred, label, scores, fn, ids) == g["text_pytorch"]
+    assert R.format_lines(pred, label, scores) == g["text_dali"]
+    # elementwise definition of the rounding
+    r8 = R.round8(scores)
+    assert all(float("%.8f" % s) == v for s, v in zip(scores.ravel().tolist(), r8.ravel().tolist()))
+    with R.ResultWriter(str(tmp_path), 0) as w0, R.ResultWriter(str(tmp_path), 1) as w1:
+        w0.write_batch(pred[:3], label[:3], scores[:3], fn[:3], ids[:3])
+        w1.write_batch(pred[3:], label[3:], scores[3:], fn[3:], ids[3:])
+    merged = R.merge(os.path.join(str(tmp_path), "results.txt.rank"), 2)
+    assert os.path.basename(merged) == "results.txt.all" and open(merged).read() == g["merged"]
+    assert R.evaluate(merged) == g["metric"]

@@ -131,3 +131,25 @@ def test_eval_pipeline_interfaces_agree(cuda, passes):
         seen.append(None if r is None else r.clone())
     assert seen[0] is None and all(int(s[2]) == bs * i for i, s in enumerate(seen) if s is not None)   # one step late
     assert torch.equal(pipe.finish(), want)
+
+
+def test_cls_solver_dump_results_compat(cuda, tmp_path, monkeypatch):
+    """data.test.dump_results: the reference's results.txt.rank0 / .all files next to the device counters
+    (imagenet_dataset.py:250-277, base_dataset.py:116-133); the file-based evaluator agrees with the counters."""
+    monkeypatch.setenv("SKIP_DIST", "1")
+    import prototype.prototype.solver.cls_solver as cls
+    from robustart_b200 import resultfile
+    cfg_path = _cfg(tmp_path, n=40, bs=16)
+    cfg = yaml.safe_load(open(cfg_path))
+    cfg["data"]["test"]["dump_results"] = True
+    open(cfg_path, "w").write(yaml.safe_dump(cfg))
+    m = cls.main(["--config", cfg_path, "--evaluate"])
+    rank0, merged = tmp_path / "results" / "results.txt.rank0", tmp_path / "results" / "results.txt.all"
+    assert rank0.read_text() == merged.read_text() and m["result_file"] == str(merged)
+    lines = [json.loads(l) for l in merged.read_text().splitlines()]
+    assert len(lines) == 40 and set(lines[0]) == {"filename", "image_id", "prediction", "label", "score"}
+    assert len(lines[0]["score"]) == 1000 and abs(sum(lines[0]["score"]) - 1) < 1e-4
+    assert all(l["prediction"] == max(range(1000), key=l["score"].__getitem__) for l in lines)
+    assert sorted(l["image_id"] for l in lines) == list(range(40))
+    assert abs(m["file_metric"]["top1"] - m["top1"]) < 1e-4 and abs(m["file_metric"]["top5"] - m["top5"]) < 1e-4
+    assert resultfile.evaluate(str(merged)) == m["file_metric"]

@@ -29,6 +29,24 @@ def test_layernorm_and_attention_layers(cuda):
     assert (out.double() - ref).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize("n,t,heads", [(3, 197, 12), (1, 256, 2), (5, 129, 3), (2, 50, 4), (4, 128, 1), (1, 1, 2)])
+def test_attention_tensor_core(cuda, n, t, heads, monkeypatch):
+    """softmax(q k^T scale) v on tcgen05 (csrc/attention_sm100.cu: QK^T and PV as split-bf16 MMAs, V consumed MN-major,
+    P written into the operand layout by the softmax warps) against fp64 torch on the same split-rounded inputs, and
+    against the CUDA-core kernel it replaces -- vision_transformer.py:80-92."""
+    from robustart_b200 import ops
+    torch.manual_seed(n * 100 + t)
+    qkv = torch.randn(n * t, 3 * heads * 64, device=cuda) * 1.5
+    qkv[:, : heads * 64] *= 2.0                                  # sharper softmax rows
+    planes = ops.split_f32(qkv)
+    out = ops.merge_f32(ops.attention(planes, n, t, heads, 64, 64 ** -0.5))
+    q, k, v = ops.merge_f32(planes).double().view(n, t, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 64 ** -0.5, -1) @ v).permute(0, 2, 1, 3).reshape(n * t, heads * 64)
+    assert torch.isfinite(out).all()
+    assert (out.double() - ref).abs().max().item() < 2e-4
+    assert torch.equal(planes, ops.split_f32(qkv))              # inputs untouched
+
+
 def test_token_transposes_and_patches(cuda):
     from robustart_b200 import ops
     torch.manual_seed(1)

@@ -5,6 +5,7 @@
 //   squeeze-excite channel scaling  out = x * w[n, c]      efficientnet.py:352-355
 //   small-K im2col of the input image for the 3x3/s2 stems (mobilenet_v2.py:130, efficientnet.py:429-433)
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 constexpr int kThreads = 256;
@@ -73,6 +74,93 @@ __global__ void __launch_bounds__(kThreads) dwconv_kernel(const uint4* __restric
     uint4 hh, ll;
     pack8(o, hh, ll);
     yh[t] = hh; yl[t] = ll;
+  }
+}
+
+// Strip version for the shapes the mobile families use (k = 3 / 5, stride 1 / 2): thread = (8 channels, 4 consecutive
+// output columns of one output row).  The generic kernel re-reads (and re-unpacks) every input pixel k*k times through L1:
+// 576 B of L1 traffic and ~330 instructions per 64-byte output, 3.3x its HBM roofline.  Here a pixel is loaded and
+// unpacked once per kernel row and applied to every (output, tap) pair it belongs to; the row's K weight vectors sit in
+// registers.  L1 traffic per output drops 4x (k = 3, s = 1), the unpack work likewise.
+template <int K, int S>
+__global__ void __launch_bounds__(kThreads) dwconv_strip_kernel(const uint4* __restrict__ xh, const uint4* __restrict__ xl,
+                                                                 const float* __restrict__ wgt, const float* __restrict__ scale,
+                                                                 const float* __restrict__ bias, uint4* __restrict__ yh,
+                                                                 uint4* __restrict__ yl, int n, int h, int w, int c8, int ho, int wo,
+                                                                 int act) {
+  constexpr int OW = 4, PAD = K / 2, IW = (OW - 1) * S + K;
+  const int strips = (wo + OW - 1) / OW;
+  const size_t total = (size_t)n * ho * strips * c8;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int cc = (int)(t % c8);
+    size_t r = t / c8;
+    const int sx = (int)(r % strips);
+    r /= strips;
+    const int oy = (int)(r % ho), im = (int)(r / ho);
+    const int ox0 = sx * OW, ix0 = ox0 * S - PAD;
+    float acc[OW][8];
+#pragma unroll
+    for (int o = 0; o < OW; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy * S - PAD + ky;
+      if (iy < 0 || iy >= h) continue;
+      float wk[K][8];
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const float4* wp = reinterpret_cast<const float4*>(wgt + ((size_t)(ky * K + kx) * c8 + cc) * 8);
+        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+        wk[kx][0] = w0.x; wk[kx][1] = w0.y; wk[kx][2] = w0.z; wk[kx][3] = w0.w;
+        wk[kx][4] = w1.x; wk[kx][5] = w1.y; wk[kx][6] = w1.z; wk[kx][7] = w1.w;
+      }
+      const size_t rowbase = ((size_t)im * h + iy) * w * c8 + cc;
+      // all loads of the row first (clamped address, zero outside the image): IW x 2 independent 16-byte loads in flight
+      uint4 rh[IW], rl[IW];
+#pragma unroll
+      for (int j = 0; j < IW; ++j) {
+        const int ix = ix0 + j;
+        const bool in = ix >= 0 && ix < w;
+        const size_t at = rowbase + (size_t)(in ? ix : 0) * c8;
+        rh[j] = __ldg(xh + at);
+        rl[j] = __ldg(xl + at);
+        if (!in) { rh[j] = make_uint4(0, 0, 0, 0); rl[j] = make_uint4(0, 0, 0, 0); }
+      }
+#pragma unroll
+      for (int j = 0; j < IW; ++j) {
+        float v[8];
+        unpack8(rh[j], rl[j], v);
+#pragma unroll
+        for (int o = 0; o < OW; ++o) {
+          const int kx = j - o * S;                  // compile-time after unrolling
+          if (kx >= 0 && kx < K) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[o][q] = fmaf(v[q], wk[kx][q], acc[o][q]);
+          }
+        }
+      }
+    }
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cc * 8)), s1 = __ldg(reinterpret_cast<const float4*>(scale + cc * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cc * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + cc * 8) + 1);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const size_t obase = (((size_t)im * ho + oy) * wo + ox0) * c8 + cc;
+#pragma unroll
+    for (int o = 0; o < OW; ++o) {
+      if (ox0 + o >= wo) break;
+      float ov[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float y = fmaf(acc[o][q], sc[q], bi[q]);
+        ov[q] = act == B200R_ACT_RELU6 ? fminf(fmaxf(y, 0.f), 6.f)
+              : act == B200R_ACT_SWISH ? __fdividef(y, 1.f + __expf(-y))
+              : act_apply(y, act);
+      }
+      uint4 hh, ll;
+      pack8(ov, hh, ll);
+      yh[obase + (size_t)o * c8] = hh;
+      yl[obase + (size_t)o * c8] = ll;
+    }
   }
 }
 
@@ -148,9 +236,21 @@ int b200r_dwconv_nhwc(const uint16_t* x, const float* wgt, const float* scale, c
   B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c % 8 == 0 && k >= 1 && stride >= 1, "bad shape (c must be a multiple of 8)");
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
   const size_t cin = (size_t)n * h * w * c, cout = (size_t)n * ho * wo * c;
-  dwconv_kernel<<<grid_for(cout / 8), kThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + cin), wgt, scale, bias, reinterpret_cast<uint4*>(y),
-      reinterpret_cast<uint4*>(y + cout), n, h, w, c / 8, k, stride, pad, ho, wo, act);
+  const uint4 *xh = reinterpret_cast<const uint4*>(x), *xl = reinterpret_cast<const uint4*>(x + cin);
+  uint4 *yh = reinterpret_cast<uint4*>(y), *yl = reinterpret_cast<uint4*>(y + cout);
+  static int use_strip = -1;      // B200R_DW_STRIP=0: generic kernel for every shape (A/B measurements)
+  if (use_strip < 0) { const char* e = getenv("B200R_DW_STRIP"); use_strip = (e && e[0] == '0') ? 0 : 1; }
+  if (use_strip && pad == k / 2 && (k == 3 || k == 5) && (stride == 1 || stride == 2)) {
+    const size_t threads = (size_t)n * ho * ((wo + 3) / 4) * (c / 8);
+#define B200R_DW(K, S) dwconv_strip_kernel<K, S><<<grid_for(threads), kThreads, 0, as_stream(stream)>>>(xh, xl, wgt, scale, bias, yh, yl, n, h, w, c / 8, ho, wo, act)
+    if (k == 3 && stride == 1) B200R_DW(3, 1);
+    else if (k == 3) B200R_DW(3, 2);
+    else if (stride == 1) B200R_DW(5, 1);
+    else B200R_DW(5, 2);
+#undef B200R_DW
+  } else {
+    dwconv_kernel<<<grid_for(cout / 8), kThreads, 0, as_stream(stream)>>>(xh, xl, wgt, scale, bias, yh, yl, n, h, w, c / 8, k, stride, pad, ho, wo, act);
+  }
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }

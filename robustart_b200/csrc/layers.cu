@@ -120,34 +120,6 @@ __global__ void __launch_bounds__(kThreads) maxpool_kernel(const uint4* __restri
   }
 }
 
-// ---- global average pool: one warp per (image, 8-channel chunk) -----------------------------------
-__global__ void __launch_bounds__(kThreads) avgpool_kernel(const uint4* __restrict__ xhi, const uint4* __restrict__ xlo,
-                                                            uint4* __restrict__ yhi, uint4* __restrict__ ylo,
-                                                            int n, int hw, int c8) {
-  const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n * c8) return;
-  const int im = warp / c8, cc = warp - im * c8;
-  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int p = lane; p < hw; p += 32) {
-    const size_t idx = ((size_t)im * hw + p) * c8 + cc;
-    uint4 a = __ldg(xhi + idx), b = __ldg(xlo + idx);
-    uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      s[j] += bf16_bits_to_f32((uint16_t)(aw[j >> 1] >> (16 * (j & 1)))) + bf16_bits_to_f32((uint16_t)(bw[j >> 1] >> (16 * (j & 1))));
-  }
-  uint16_t hh[8], ll[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float v = warp_sum(s[j]) / (float)hw;
-    split_bf16(v, hh[j], ll[j]);
-  }
-  if (lane == 0) {
-    yhi[warp] = make_uint4(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]), pack_bf16x2(hh[4], hh[5]), pack_bf16x2(hh[6], hh[7]));
-    ylo[warp] = make_uint4(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]), pack_bf16x2(ll[4], ll[5]), pack_bf16x2(ll[6], ll[7]));
-  }
-}
-
 // ---- fp16 twins ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) f32_to_f16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t count4,
                                                                float scale) {
@@ -197,20 +169,61 @@ __global__ void __launch_bounds__(kThreads) maxpool_f16_kernel(const uint4* __re
 }
 
 // global average pool on one fp16 plane: one warp per (image, 8-channel chunk), fp32 sums
-__global__ void __launch_bounds__(kThreads) avgpool_f16_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int hw, int c8) {
-  const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n * c8) return;
-  const int im = warp / c8, cc = warp - im * c8;
+// Coalesced global average pool: block of 1024 threads = (image, up to 256 channel chunks); threads tile (pixel slice, chunk) so that a
+// warp reads 512 contiguous bytes per plane; fixed summation order (slice partials through shared memory).  The
+// warp-per-(image, chunk) kernels above read 16 bytes per 32-byte sector at a stride of C*2 bytes.
+template <bool F16>
+__global__ void __launch_bounds__(1024) avgpool_flat_kernel(const uint4* __restrict__ xhi, const uint4* __restrict__ xlo,
+                                                            uint4* __restrict__ yhi, uint4* __restrict__ ylo, int hw, int c8) {
+  __shared__ float part[8][1024];              // 1024 threads: one block per image must keep enough loads in flight by itself
+  const int im = blockIdx.x, cb = blockIdx.y * 256, cw = min(256, c8 - cb);
+  const int slices = 1024 / cw, tid = threadIdx.x;
+  const bool active = tid < slices * cw;
+  const int cc = tid % cw, sl = tid / cw;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int p = lane; p < hw; p += 32) {
-    const uint4 a = __ldg(x + ((size_t)im * hw + p) * c8 + cc);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+  if (active) {
+    const size_t base = (size_t)im * hw * c8 + cb + cc;
+#pragma unroll 4
+    for (int p = sl; p < hw; p += slices) {
+      const size_t idx = base + (size_t)p * c8;
+      const uint4 a = __ldg(xhi + idx);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+      if (F16) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const float2 v = h2_to_f2(aw[j]); s[2 * j] += v.x; s[2 * j + 1] += v.y; }
+        for (int j = 0; j < 4; ++j) { const float2 v = h2_to_f2(aw[j]); s[2 * j] += v.x; s[2 * j + 1] += v.y; }
+      } else {
+        const uint4 b = __ldg(xlo + idx);
+        const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[2 * j] += __uint_as_float(aw[j] << 16) + __uint_as_float(bw[j] << 16);
+          s[2 * j + 1] += __uint_as_float(aw[j] & 0xFFFF0000u) + __uint_as_float(bw[j] & 0xFFFF0000u);
+        }
+      }
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = warp_sum(s[j]) / (float)hw;
-  if (lane == 0) y[warp] = make_uint4(f2_to_h2(s[0], s[1]), f2_to_h2(s[2], s[3]), f2_to_h2(s[4], s[5]), f2_to_h2(s[6], s[7]));
+  for (int j = 0; j < 8; ++j) part[j][tid] = s[j];
+  __syncthreads();
+  if (tid < cw) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = 0.f;
+      for (int k = 0; k < slices; ++k) a += part[j][tid + k * cw];
+      v[j] = a / (float)hw;
+    }
+    const size_t o = (size_t)im * c8 + cb + tid;
+    if (F16) {
+      yhi[o] = make_uint4(f2_to_h2(v[0], v[1]), f2_to_h2(v[2], v[3]), f2_to_h2(v[4], v[5]), f2_to_h2(v[6], v[7]));
+    } else {
+      uint16_t hh[8], ll[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_bf16(v[j], hh[j], ll[j]);
+      yhi[o] = make_uint4(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]), pack_bf16x2(hh[4], hh[5]), pack_bf16x2(hh[6], hh[7]));
+      ylo[o] = make_uint4(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]), pack_bf16x2(ll[4], ll[5]), pack_bf16x2(ll[6], ll[7]));
+    }
+  }
 }
 
 inline unsigned grid_for(size_t items) {
@@ -276,9 +289,8 @@ int b200r_maxpool3x3s2_nhwc_f16(const uint16_t* x, uint16_t* y, int n, int h, in
 int b200r_global_avgpool_nhwc_f16(const uint16_t* x, uint16_t* y, int n, int hw, int c, b200r_stream_t stream) {
   B200R_CHECK_ARG(x && y, "null pointer");
   B200R_CHECK_ARG(n > 0 && hw > 0 && c % 8 == 0, "c must be a multiple of 8");
-  const int warps = n * (c / 8);
-  avgpool_f16_kernel<<<(warps * 32 + kThreads - 1) / kThreads, kThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), n, hw, c / 8);
+  avgpool_flat_kernel<true><<<dim3(n, (c / 8 + 255) / 256), 1024, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(x), nullptr, reinterpret_cast<uint4*>(y), nullptr, hw, c / 8);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
@@ -324,10 +336,9 @@ int b200r_global_avgpool_nhwc(const uint16_t* x, uint16_t* y, int n, int hw, int
   B200R_CHECK_ARG(x && y, "null pointer");
   B200R_CHECK_ARG(n > 0 && hw > 0 && c % 8 == 0, "c must be a multiple of 8");
   const size_t cin = (size_t)n * hw * c, cout = (size_t)n * c;
-  const int warps = n * (c / 8);
-  avgpool_kernel<<<(warps * 32 + kThreads - 1) / kThreads, kThreads, 0, as_stream(stream)>>>(
+  avgpool_flat_kernel<false><<<dim3(n, (c / 8 + 255) / 256), 1024, 0, as_stream(stream)>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + cin), reinterpret_cast<uint4*>(y),
-      reinterpret_cast<uint4*>(y + cout), n, hw, c / 8);
+      reinterpret_cast<uint4*>(y + cout), hw, c / 8);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }

@@ -7,8 +7,10 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from robustart_b200 import nets, ops
 
 arch = sys.argv[1]
-n = int(sys.argv[2]) if len(sys.argv) > 2 else 128
-passes = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+arch = args[0]
+n = int(args[1]) if len(args) > 1 else 128
+passes = int(args[2]) if len(args) > 2 else 3
 dev = torch.device("cuda", 0)
 build = getattr(nets, "build_any", None) or nets.build_model
 try:
@@ -45,6 +47,10 @@ def wrap(name, fn):
                 tag += " k=%d n=%d" % (x.shape[-1], wg.shape[1])
             else:
                 tag += " %dx%d c%d->%d s%d @%d" % (wg.shape[2], wg.shape[3], x.shape[-1], wg.shape[1], k.get("stride", 1), x.shape[2])
+        if name == "conv2d_dgrad":
+            dy, wt = a[0], a[1]
+            tag += " %dx%d c%d->%d @%d res=%d mask=%d" % (wt.shape[2], wt.shape[3], dy.shape[-1], wt.shape[1], dy.shape[2],
+                                                        int((a[2] if len(a) > 2 else k.get("res")) is not None), int((a[3] if len(a) > 3 else k.get("mask")) is not None))
         recs.append((tag, s, e))
         return y
     return w
@@ -52,9 +58,16 @@ def wrap(name, fn):
 
 for k in names:
     setattr(ops, k, wrap(k, orig[k]))
+grad = "--grad" in sys.argv          # forward_saved + input gradient (one PGD step's model work) instead of the forward
+if grad:
+    x01 = torch.rand(n, 3, 224, 224, device=dev)
+    yl = torch.randint(0, 1000, (n,), device=dev)
 for _ in range(3):
     recs.clear()
-    model.forward(img)
+    if grad:
+        model.loss_and_input_grad(x01, yl)
+    else:
+        model.forward(img)
     torch.cuda.synchronize()
 agg = collections.OrderedDict()
 for tag, s, e in recs:

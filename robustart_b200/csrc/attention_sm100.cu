@@ -2,12 +2,15 @@
 // vision_transformer.py:80-92): out = softmax(q k^T * scale) v per (image, head), split-bf16 planes in and out.
 //
 // One CTA per (image, head, 128-query tile); tokens <= 256 so one pass over the keys is the whole softmax -- no online
-// rescaling.  160 threads:
-//   warp 4      TMA loads (Q tile, all K, all V; hi and lo planes), then the MMA issue:
+// rescaling.  544 threads:
+//   warp 16     TMA loads (Q tile, all K, all V; hi and lo planes), then the MMA issue:
 //                 S[128 x Tk]  = Q K^T          3 x 4 MMAs (lo*hi, hi*lo, hi*hi), A = Q and B = K both K-major SW128 tiles
 //                 O[128 x 64]  = P V            3 x Tk/16 MMAs (hi*hi, lo*hi, hi*lo), A = P K-major, B = V **MN-major** (V is
 //                                               [key][d] in memory = exactly what TMA delivers; no transpose pass)
-//   warps 0-3   softmax: thread = query row (TMEM lane).  Pass 1 reads S for the row maximum, pass 2 computes
+//   warps 0-15  softmax: thread = (query row = TMEM lane, quarter of the key chunks); four warps per TMEM lane quadrant
+//               (warp % 4) keep each scheduler's issue slots busy -- with one warp per quadrant the 4.6 K dependent
+//               instructions of a row were the kernel (18 K of a tile's 26 K cycles).  Row maxima and sums are combined
+//               through shared memory.  Pass 1 reads S for the row maximum, pass 2 computes
 //               p = 2^((s - max) * scale * log2 e) (masked beyond the last token), accumulates the row sum and writes p as
 //               bf16 hi / lo into the A-operand layout (over the dead Q / K tiles); the 1 / sum goes onto O in the epilogue,
 //               which re-splits to bf16 planes and stores 128-byte rows.
@@ -19,8 +22,9 @@
 namespace {
 
 constexpr int AT_D = 64;
-constexpr int AT_THREADS = 160;
-constexpr int AT_MMA_WARP = 4;
+constexpr int AT_SM_WARPS = 16;                       // softmax warps: 4 column groups x 4 TMEM lane quadrants
+constexpr int AT_THREADS = (AT_SM_WARPS + 1) * 32;
+constexpr int AT_MMA_WARP = AT_SM_WARPS;
 constexpr int AT_MAXTK = 256;
 constexpr int AT_P_PLANE = 4 * 16384;                 // P: up to 4 k-blocks of [128 x 64] per plane
 
@@ -41,6 +45,12 @@ __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
   return d;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t at_smem_raw[];
@@ -54,6 +64,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const uint32_t off_bar = off_r + 2 * AT_P_PLANE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bar);      // ld_full, s_full, p_full, o_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* red = reinterpret_cast<float*>(smem + off_bar + 64);         // [2][4 groups][128 rows]: row maxima, row sums
   const uint32_t bar0 = sbase + off_bar;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
@@ -65,7 +76,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     prefetch_tmap(&map_kv);
     mbar_init(bar0 + 0, 1);
     mbar_init(bar0 + 8, 1);
-    mbar_init(bar0 + 16, 128);
+    mbar_init(bar0 + 16, AT_SM_WARPS * 32);
     mbar_init(bar0 + 24, 1);
     fence_barrier_init();
   }
@@ -125,14 +136,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncwarp();
   } else {
     // ================================ softmax + epilogue ================================
-    const int row = warp * 32 + lane;                             // query row of the tile = TMEM lane
+    const int quad = warp & 3, grp = warp >> 2;                   // TMEM lane quadrant, column group
+    const int row = quad * 32 + lane;                             // query row of the tile = TMEM lane
     const int q = mt * 128 + row;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    const int chunks = Tk >> 5;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int chunks = Tk >> 5;                                   // 32-key chunks; this group takes chunks grp, grp + 4, ...
     mbar_wait(bar0 + 8, 0);
     tc_fence_after();
     float mx = -INFINITY;
-    for (int c = 0; c < chunks; ++c) {
+    for (int c = grp; c < chunks; c += 4) {
       uint32_t v[32];
       tmem_ld32(tm_s + lane_addr + c * 32, v);
       tmem_ld_wait();
@@ -140,9 +152,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       for (int j = 0; j < 32; ++j)
         if (c * 32 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
     }
+    red[grp * 128 + row] = mx;
+    named_bar_sync(1, AT_SM_WARPS * 32);
+    mx = fmaxf(fmaxf(red[row], red[128 + row]), fmaxf(red[256 + row], red[384 + row]));
     float sum = 0.f;
     const float k2 = p.scale_log2e, mk = -mx * k2;
-    for (int c = 0; c < chunks; ++c) {
+    for (int c = grp; c < chunks; c += 4) {
       uint32_t v[32];
       tmem_ld32(tm_s + lane_addr + c * 32, v);
       tmem_ld_wait();
@@ -153,8 +168,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int col = c * 32 + g * 8 + 2 * j;
-          const float e0 = col < p.T ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * j]), k2, mk)) : 0.f;
-          const float e1 = col + 1 < p.T ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), k2, mk)) : 0.f;
+          const float e0 = col < p.T ? ex2_approx(fmaf(__uint_as_float(v[g * 8 + 2 * j]), k2, mk)) : 0.f;
+          const float e1 = col + 1 < p.T ? ex2_approx(fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), k2, mk)) : 0.f;
           sum += e0 + e1;
           ph[j] = cvt_bf16x2(e1, e0);
           pl[j] = cvt_bf16x2(e1 - __uint_as_float(ph[j] & 0xFFFF0000u), e0 - __uint_as_float(ph[j] << 16));
@@ -164,22 +179,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         *reinterpret_cast<uint4*>(tile + AT_P_PLANE + (chunk << 4)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
       }
     }
+    red[512 + grp * 128 + row] = sum;
     tc_fence_before();
     fence_proxy_async();
     mbar_arrive(bar0 + 16);
-    // ---- O / sum -> bf16 planes ----
+    named_bar_sync(1, AT_SM_WARPS * 32);                          // every group's partial sum is in shared memory
+    const float inv = 1.f / ((red[512 + row] + red[640 + row]) + (red[768 + row] + red[896 + row]));
+    // ---- O / sum -> bf16 planes: group g takes the 16 output columns [16g, 16g + 16) ----
     mbar_wait(bar0 + 24, 0);
     tc_fence_after();
-    const float inv = 1.f / sum;
-    const size_t orow = ((size_t)(row0 + q) * p.H + hd) * AT_D;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tm_o + lane_addr + c * 32, v);
+    const size_t orow = ((size_t)(row0 + q) * p.H + hd) * AT_D + grp * 16;
+    {
+      uint32_t v[16];
+      tmem_ld16(tm_o + lane_addr + grp * 16, v);
       tmem_ld_wait();
       if (q < p.T) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint32_t ph[4], pl[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -187,8 +203,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             ph[j] = cvt_bf16x2(x1, x0);
             pl[j] = cvt_bf16x2(x1 - __uint_as_float(ph[j] & 0xFFFF0000u), x0 - __uint_as_float(ph[j] << 16));
           }
-          *reinterpret_cast<uint4*>(p.out_hi + orow + c * 32 + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          *reinterpret_cast<uint4*>(p.out_lo + orow + c * 32 + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          *reinterpret_cast<uint4*>(p.out_hi + orow + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          *reinterpret_cast<uint4*>(p.out_lo + orow + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
       }
     }
@@ -241,7 +257,7 @@ int b200r_attention_tc(const uint16_t* qkv, uint16_t* out, int n, int tokens, in
   p.out_hi = out; p.out_lo = out + cout;
   p.T = tokens; p.Tk = Tk; p.H = heads; p.MT = MT;
   p.scale_log2e = scale * 1.4426950408889634f;
-  const int smem = 2 * Tk * 128 + 2 * AT_P_PLANE + 64 + 1024;
+  const int smem = 2 * Tk * 128 + 2 * AT_P_PLANE + 64 + 2 * 4 * 128 * 4 + 1024;
   static int configured = 0;
   if (configured < smem) {
     B200R_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -150,7 +150,10 @@ def gemm_roofline(model, pipe, pk, precision):
         _, cout, kh, kw, _ = wgt.shape
         st, pd = k.get("stride", 1), k.get("pad", 0)
         ho, wo = (h + 2 * pd - kh) // st + 1, (w + 2 * pd - kw) // st + 1
-        recs.append((s, e, 2.0 * n * ho * wo * cout * kh * kw * cin))
+        has_res = (a[2] if len(a) > 2 else k.get("res")) is not None
+        bpe = 2.0 if x.shape[0] == 1 else 4.0            # one fp16 plane or two bf16 planes per element
+        byts = bpe * (n * h * w * cin + n * ho * wo * cout * (2 if has_res else 1))
+        recs.append((s, e, 2.0 * n * ho * wo * cout * kh * kw * cin, byts))
         return y
 
     def lin(x, wgt, *a, **k):
@@ -159,7 +162,8 @@ def gemm_roofline(model, pipe, pk, precision):
         y = orig_lin(x, wgt, *a, **k)
         e.record()
         kk = x.shape[-1]
-        recs.append((s, e, 2.0 * (x[0].numel() // kk) * kk * wgt.shape[1]))
+        rows = x[0].numel() // kk
+        recs.append((s, e, 2.0 * rows * kk * wgt.shape[1], (2.0 if x.shape[0] == 1 else 4.0) * (rows * kk + rows * wgt.shape[1])))
         return y
 
     orig_stem = ops.stem_conv7x7_u8
@@ -169,7 +173,8 @@ def gemm_roofline(model, pipe, pk, precision):
         s.record()
         y = orig_stem(img, *a, **k)
         e.record()
-        recs.append((s, e, 2.0 * img.shape[0] * (img.shape[1] // 2) * (img.shape[2] // 2) * 64 * 147))
+        recs.append((s, e, 2.0 * img.shape[0] * (img.shape[1] // 2) * (img.shape[2] // 2) * 64 * 147,
+                     img.numel() + (2.0 if a[0].shape[0] == 1 else 4.0) * img.shape[0] * (img.shape[1] // 2) * (img.shape[2] // 2) * 64))
         return y
 
     orig_stem_pool = ops.stem_pool_u8
@@ -179,7 +184,8 @@ def gemm_roofline(model, pipe, pk, precision):
         s.record()
         y = orig_stem_pool(img, *a, **k)
         e.record()
-        recs.append((s, e, 2.0 * img.shape[0] * (img.shape[1] // 2) * (img.shape[2] // 2) * 64 * 147))
+        recs.append((s, e, 2.0 * img.shape[0] * (img.shape[1] // 2) * (img.shape[2] // 2) * 64 * 147,
+                     img.numel() + 2.0 * img.shape[0] * (img.shape[1] // 4) * (img.shape[2] // 4) * 64))
         return y
 
     ops.conv2d_nhwc, ops.linear, ops.stem_conv7x7_u8, ops.stem_pool_u8 = conv, lin, stem, stem_pool
@@ -194,15 +200,21 @@ def gemm_roofline(model, pipe, pk, precision):
     tp = os.path.join(ROOT, "profiles", "r1_gemm_traffic_%s.json" % precision)
     if os.path.exists(tp):      # dram__bytes_read+write summed over the same launches, from one ncu capture (profiles/)
         traffic = json.load(open(tp)).get("dram_bytes_per_forward")
-    ms = sum(s.elapsed_time(e) for s, e, _ in recs)
-    flops = sum(f for _, _, f in recs)
+    ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
+    flops = sum(f for _, _, f, _ in recs)
     achieved = flops / (ms * 1e-3) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    # per-launch roofline: a layer can go no faster than its activation traffic over HBM or its MMAs over the tensor pipe
+    mmas = 1.0 if precision == "f16" else 3.0
+    layer_ms = sum(max(b / (pk["hbm_gbs"] * 1e9), mmas * f / (peak * 1e12)) for _, _, f, b in recs) * 1e3
     return {"bound": "tensor", "kernel": "gemm_kernel<BN> + stem_pool_kernel (tcgen05 implicit GEMMs, all %d launches of one forward)" % len(recs),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_note": "bytes per forward (all GEMM launches), ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_gemm_traffic_%s.json" % precision,
             "peak_source": pk["_source"] + ", sustained bf16 (kernel timed inside a long step)",
             "gemm_ms_per_step": ms, "algorithmic_gflop_per_step": flops / 1e9,
+            "layer_roofline_ms_per_step": layer_ms, "frac_of_layer_roofline": layer_ms / ms,
+            "layer_roofline_note": "sum over the launches of max(algorithmic activation bytes / HBM peak, issued MMA FLOPs / tensor peak): "
+                                   "most 1x1 layers of ResNet-50 are HBM-bound, so the tensor-only `frac` cannot approach 1",
             "note": ("algorithmic FLOPs = 2*M*N*K of the convolution, one fp16 MMA per product; most 1x1 layers of ResNet-50 are bound by "
                      "activation traffic, not the tensor pipe (profiles/ layer report)") if precision == "f16" else
                     ("algorithmic FLOPs = 2*M*N*K of the fp32 convolution; the split-bf16 scheme issues 3 bf16 MMAs per "

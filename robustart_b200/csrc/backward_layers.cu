@@ -35,6 +35,24 @@ __device__ __forceinline__ void load8(const uint4* __restrict__ ph, const uint4*
   }
 }
 template <bool F16>
+__device__ __forceinline__ void unpack8r(const uint4& a, const uint4& b, float (&v)[8]) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+  if (F16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&aw[j]));
+      v[2 * j] = f.x; v[2 * j + 1] = f.y;
+    }
+  } else {
+    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] = __uint_as_float(aw[j] << 16) + __uint_as_float(bw[j] << 16);
+      v[2 * j + 1] = __uint_as_float(aw[j] & 0xFFFF0000u) + __uint_as_float(bw[j] & 0xFFFF0000u);
+    }
+  }
+}
+template <bool F16>
 __device__ __forceinline__ void store8(uint4* __restrict__ ph, uint4* __restrict__ pl, size_t i, const float (&v)[8]) {
   uint32_t rh[4], rl[4];
 #pragma unroll
@@ -155,19 +173,25 @@ __global__ void __launch_bounds__(kThreads) maxpool_argmax_kernel(const uint4* _
     uint32_t bi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0xFu; }
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy * 2 - 1 + ky;
-      if (iy < 0 || iy >= h) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox * 2 - 1 + kx;
-        if (ix < 0 || ix >= w) continue;
-        const size_t s = (((size_t)im * h + iy) * w + ix) * c8 + cc;
-        float v[8];
-        load8<F16>(xh, xl, s, v);
+    // the nine window loads first (clamped address, validity kept aside): independent 16-byte loads in flight
+    uint4 ra[9], rb[9];
+    bool ok[9];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (v[j] > best[j]) { best[j] = v[j]; bi[j] = (uint32_t)(ky * 3 + kx); }
-      }
+    for (int k = 0; k < 9; ++k) {
+      const int iy = oy * 2 - 1 + k / 3, ix = ox * 2 - 1 + k % 3;
+      ok[k] = iy >= 0 && iy < h && ix >= 0 && ix < w;
+      const size_t s = (((size_t)im * h + (ok[k] ? iy : 0)) * w + (ok[k] ? ix : 0)) * c8 + cc;
+      ra[k] = __ldg(xh + s);
+      rb[k] = F16 ? make_uint4(0, 0, 0, 0) : __ldg(xl + s);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (!ok[k]) continue;
+      float v[8];
+      unpack8r<F16>(ra[k], rb[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (v[j] > best[j]) { best[j] = v[j]; bi[j] = (uint32_t)k; }
     }
     idx[t] = make_uint2(bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24), bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24));
   }
@@ -184,25 +208,33 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint2* __re
     const int q = (int)(pix % w), p = (int)((pix / w) % h), im = (int)(pix / ((size_t)w * h));
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool any = false;
-    for (int oy = p >> 1; oy <= ((p + 1) >> 1); ++oy) {        // windows with 2*oy - 1 <= p <= 2*oy + 1
-      if (oy >= ho) continue;
-      const int ky = p - (2 * oy - 1);
-      for (int ox = q >> 1; ox <= ((q + 1) >> 1); ++ox) {
-        if (ox >= wo) continue;
-        const int kx = q - (2 * ox - 1);
-        const uint32_t code = (uint32_t)(ky * 3 + kx);
-        const size_t o = (((size_t)im * ho + oy) * wo + ox) * c8 + cc;
-        const uint2 id = __ldg(idx + o);
-        const uint32_t m0 = id.x ^ (code * 0x01010101u), m1 = id.y ^ (code * 0x01010101u);
-        // any byte of m0 / m1 equal to zero = this position is the argmax of that channel
-        if (!(((m0 - 0x01010101u) & ~m0 & 0x80808080u) | ((m1 - 0x01010101u) & ~m1 & 0x80808080u))) continue;
-        float g[8];
-        load8<F16>(dyh, dyl, o, g);
+    // windows with 2*oy - 1 <= p <= 2*oy + 1 (one or two per axis): their argmax codes and gradients are loaded together
+    uint2 id[4];
+    uint4 ga[4], gb[4];
+    uint32_t code[4];
+    bool ok[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t b = ((j < 4 ? id.x : id.y) >> (8 * (j & 3))) & 0xFFu;
-          if (b == code) { acc[j] += g[j]; any = true; }
-        }
+    for (int k = 0; k < 4; ++k) {
+      const int oy = (p >> 1) + (k >> 1), ox = (q >> 1) + (k & 1);
+      ok[k] = oy <= ((p + 1) >> 1) && ox <= ((q + 1) >> 1) && oy < ho && ox < wo;
+      code[k] = (uint32_t)((p - (2 * oy - 1)) * 3 + (q - (2 * ox - 1)));
+      const size_t o = (((size_t)im * ho + (ok[k] ? oy : 0)) * wo + (ok[k] ? ox : 0)) * c8 + cc;
+      id[k] = __ldg(idx + o);
+      ga[k] = __ldg(dyh + o);
+      gb[k] = F16 ? make_uint4(0, 0, 0, 0) : __ldg(dyl + o);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      const uint32_t m0 = id[k].x ^ (code[k] * 0x01010101u), m1 = id[k].y ^ (code[k] * 0x01010101u);
+      // any byte of m0 / m1 equal to zero = this position is the argmax of that channel
+      if (!(((m0 - 0x01010101u) & ~m0 & 0x80808080u) | ((m1 - 0x01010101u) & ~m1 & 0x80808080u))) continue;
+      float g[8];
+      unpack8r<F16>(ga[k], gb[k], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t b = ((j < 4 ? id[k].x : id[k].y) >> (8 * (j & 3))) & 0xFFu;
+        if (b == code[k]) { acc[j] += g[j]; any = true; }
       }
     }
     if (any) {

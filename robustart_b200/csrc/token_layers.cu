@@ -52,28 +52,42 @@ __global__ void __launch_bounds__(kThreads) layernorm_kernel(const uint4* __rest
                                                               int rows, int c8, float eps) {
   const int row = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= rows) return;
+  // compile-time slots (lane + 32 k): the row stays in registers (a run-time slot index put it in local memory), and the
+  // loads of all slots are issued before the first is consumed
+  uint4 rh[kLnMaxVec], rl[kLnMaxVec];
+#pragma unroll
+  for (int k = 0; k < kLnMaxVec; ++k) {
+    const int i = lane + 32 * k;
+    if (i < c8) { rh[k] = __ldg(xh + (size_t)row * c8 + i); rl[k] = __ldg(xl + (size_t)row * c8 + i); }
+    else { rh[k] = make_uint4(0, 0, 0, 0); rl[k] = make_uint4(0, 0, 0, 0); }
+  }
   float v[kLnMaxVec][8];
   float s = 0.f;
-  int nv = 0;
-  for (int i = lane; i < c8; i += 32, ++nv) {
-    unpack8(__ldg(xh + (size_t)row * c8 + i), __ldg(xl + (size_t)row * c8 + i), v[nv]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[nv][j];
+  for (int k = 0; k < kLnMaxVec; ++k) {
+    unpack8(rh[k], rl[k], v[k]);                       // absent slots unpack to zeros
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[k][j];
   }
   const float mean = warp_sum(s) / (float)(c8 * 8);
   float q = 0.f;
-  for (int k = 0; k < nv; ++k)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const float d = v[k][j] - mean; q += d * d; }
+  for (int k = 0; k < kLnMaxVec; ++k)
+    if (lane + 32 * k < c8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[k][j] - mean; q += d * d; }
+    }
   const float rstd = rsqrtf(warp_sum(q) / (float)(c8 * 8) + eps);
-  nv = 0;
-  for (int i = lane; i < c8; i += 32, ++nv) {
+#pragma unroll
+  for (int k = 0; k < kLnMaxVec; ++k) {
+    const int i = lane + 32 * k;
+    if (i >= c8) continue;
     float o[8];
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * i + 1);
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * i), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * i + 1);
     const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (v[nv][j] - mean) * rstd * g[j] + b[j];
+    for (int j = 0; j < 8; ++j) o[j] = (v[k][j] - mean) * rstd * g[j] + b[j];
     uint4 h, l;
     pack8(o, h, l);
     yh[(size_t)row * c8 + i] = h;

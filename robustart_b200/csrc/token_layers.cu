@@ -209,25 +209,34 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const uint16_t*
 
 // ---- Mixer token transposes -----------------------------------------------------------------------
 // forward: y[b, c, t] (t < Tp, zero for t >= T) = x[b, t, c]
+// 64 x 64 tiles, two elements (one 32-bit word) per thread and plane on both sides: 128-byte warp accesses instead of the
+// 64-byte ones of a 16-bit-per-thread transpose; an element travels through shared memory as (hi | lo << 16).
+// T, C, Tp even (checked by the callers).
 __global__ void __launch_bounds__(kThreads) tokens_to_channels_kernel(const uint16_t* __restrict__ xh, const uint16_t* __restrict__ xl,
                                                                        uint16_t* __restrict__ yh, uint16_t* __restrict__ yl, int B, int T,
                                                                        int C, int Tp) {
-  __shared__ uint32_t tile[32][33];
-  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  __shared__ uint32_t tile[64][65];
+  const int b = blockIdx.z, t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
-  for (int r = ty; r < 32; r += 8) {
-    const int t = t0 + r, c = c0 + tx;
-    uint32_t v = 0;
-    if (t < T && c < C) { const size_t i = ((size_t)b * T + t) * C + c; v = xh[i] | ((uint32_t)xl[i] << 16); }
-    tile[r][tx] = v;
+  for (int r = ty; r < 64; r += 8) {
+    const int t = t0 + r, c = c0 + 2 * tx;
+    uint32_t h = 0, l = 0;
+    if (t < T && c < C) {
+      const size_t i = ((size_t)b * T + t) * C + c;
+      h = *reinterpret_cast<const uint32_t*>(xh + i);
+      l = *reinterpret_cast<const uint32_t*>(xl + i);
+    }
+    tile[r][2 * tx] = (h & 0xFFFFu) | (l << 16);
+    tile[r][2 * tx + 1] = (h >> 16) | (l & 0xFFFF0000u);
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int c = c0 + r, t = t0 + tx;
+  for (int r = ty; r < 64; r += 8) {
+    const int c = c0 + r, t = t0 + 2 * tx;
     if (c < C && t < Tp) {
-      const uint32_t v = tile[tx][r];
+      const uint32_t a = tile[2 * tx][r], d = tile[2 * tx + 1][r];
       const size_t o = ((size_t)b * C + c) * Tp + t;
-      yh[o] = (uint16_t)v; yl[o] = (uint16_t)(v >> 16);
+      *reinterpret_cast<uint32_t*>(yh + o) = (a & 0xFFFFu) | (d << 16);
+      *reinterpret_cast<uint32_t*>(yl + o) = (a >> 16) | (d & 0xFFFF0000u);
     }
   }
 }
@@ -236,19 +245,34 @@ __global__ void __launch_bounds__(kThreads) channels_to_tokens_add_kernel(const 
                                                                            const uint16_t* __restrict__ rh, const uint16_t* __restrict__ rl,
                                                                            uint16_t* __restrict__ oh, uint16_t* __restrict__ ol, int B,
                                                                            int T, int C, int Tp) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  __shared__ float tile[64][65];
+  const int b = blockIdx.z, t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const int c = c0 + r, t = t0 + tx;
-    tile[r][tx] = (c < C && t < T) ? pl_get(yh, yl, ((size_t)b * C + c) * Tp + t) : 0.f;
+  for (int r = ty; r < 64; r += 8) {
+    const int c = c0 + r, t = t0 + 2 * tx;
+    float v0 = 0.f, v1 = 0.f;
+    if (c < C && t < T) {
+      const size_t i = ((size_t)b * C + c) * Tp + t;
+      const uint32_t h = *reinterpret_cast<const uint32_t*>(yh + i), l = *reinterpret_cast<const uint32_t*>(yl + i);
+      v0 = __uint_as_float(h << 16) + __uint_as_float(l << 16);
+      v1 = __uint_as_float(h & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u);
+    }
+    tile[r][2 * tx] = v0;
+    tile[r][2 * tx + 1] = v1;
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int t = t0 + r, c = c0 + tx;
+  for (int r = ty; r < 64; r += 8) {
+    const int t = t0 + r, c = c0 + 2 * tx;
     if (t < T && c < C) {
       const size_t i = ((size_t)b * T + t) * C + c;
-      pl_put(oh, ol, i, pl_get(rh, rl, i) + tile[tx][r]);
+      const uint32_t h = *reinterpret_cast<const uint32_t*>(rh + i), l = *reinterpret_cast<const uint32_t*>(rl + i);
+      const float o0 = __uint_as_float(h << 16) + __uint_as_float(l << 16) + tile[2 * tx][r];
+      const float o1 = __uint_as_float(h & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u) + tile[2 * tx + 1][r];
+      uint16_t h0, l0, h1, l1;
+      split_bf16(o0, h0, l0);
+      split_bf16(o1, h1, l1);
+      *reinterpret_cast<uint32_t*>(oh + i) = h0 | ((uint32_t)h1 << 16);
+      *reinterpret_cast<uint32_t*>(ol + i) = l0 | ((uint32_t)l1 << 16);
     }
   }
 }
@@ -332,8 +356,9 @@ int b200r_attention(const uint16_t* qkv, uint16_t* out, int n, int tokens, int h
 
 int b200r_tokens_to_channels(const uint16_t* x, uint16_t* y, int b, int t, int c, int t_pad, b200r_stream_t stream) {
   B200R_CHECK_ARG(x && y && b > 0 && t > 0 && c > 0 && t_pad >= t, "bad arguments");
+  B200R_CHECK_ARG(t % 2 == 0 && c % 2 == 0 && t_pad % 2 == 0, "tokens_to_channels needs even t, c, t_pad");
   const size_t cin = (size_t)b * t * c, cout = (size_t)b * c * t_pad;
-  dim3 grid((t_pad + 31) / 32, (c + 31) / 32, b);
+  dim3 grid((t_pad + 63) / 64, (c + 63) / 64, b);
   tokens_to_channels_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(x, x + cin, y, y + cout, b, t, c, t_pad);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
@@ -342,8 +367,9 @@ int b200r_tokens_to_channels(const uint16_t* x, uint16_t* y, int b, int t, int c
 int b200r_channels_to_tokens_add(const uint16_t* y, const uint16_t* res, uint16_t* out, int b, int t, int c, int t_pad,
                                  b200r_stream_t stream) {
   B200R_CHECK_ARG(y && res && out && b > 0 && t > 0 && c > 0 && t_pad >= t, "bad arguments");
+  B200R_CHECK_ARG(t % 2 == 0 && c % 2 == 0 && t_pad % 2 == 0, "channels_to_tokens_add needs even t, c, t_pad");
   const size_t cy = (size_t)b * c * t_pad, cx = (size_t)b * t * c;
-  dim3 grid((t + 31) / 32, (c + 31) / 32, b);
+  dim3 grid((t + 63) / 64, (c + 63) / 64, b);
   channels_to_tokens_add_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(y, y + cy, res, res + cx, out, out + cx, b, t, c, t_pad);
   B200R_LAUNCH_CHECK();
   return B200R_OK;

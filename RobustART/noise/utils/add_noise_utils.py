@@ -84,9 +84,41 @@ def add_noise_for_imagenet_c(image, severity=1, corruption_name=None, corruption
     return image
 
 
-def add_noise_for_imagenet_s(image, decoder_type='pil', resize_type='pil-bilinear', transform_type='val'):
-    # decoder x resize system noise is a CPU decode study outside the hot path.
-    raise NotImplementedError("imagenet-s (decoder/resize system noise) is outside the B200 hot path")
+_PIL_RESIZE_TYPES = {'pil-bilinear': 'bilinear', 'pil-nearest': 'nearest', 'pil-box': 'box', 'pil-hamming': 'hamming',
+                     'pil-cubic': 'bicubic', 'pil-lanczos': 'lanczos'}
+
+
+def add_noise_for_imagenet_s(image, decoder_type='pil', resize_type='pil-bilinear', transform_type='val', size=224):
+    """ImageTransfer(..., return_online=True).getimage() (imagenet_s_gen.py:83-141) for the PIL decoder and the six `pil-*`
+    resize types, transform 'val': decode on the host (file parsing, as the reference), then Image.resize to
+    (size*8/7, size*8/7) and the centre crop as ONE bit-exact resize kernel launch (b200r_resize_u8).  `image` is a file
+    path (the reference's contract) or an already decoded uint8 [h, w, 3] / [n, h, w, 3] array or CUDA tensor.
+    The OpenCV / ffmpeg decoders, the opencv-* resize types and the random-crop 'train' transform are not implemented."""
+    if decoder_type != 'pil':
+        raise NotImplementedError("imagenet-s decoder_type=%r: only the PIL decoder is implemented" % decoder_type)
+    if resize_type not in _PIL_RESIZE_TYPES:
+        raise NotImplementedError("imagenet-s resize_type=%r: only the pil-* resize types are implemented" % resize_type)
+    if transform_type != 'val':
+        raise NotImplementedError("imagenet-s transform_type=%r: only 'val' (resize + centre crop) is implemented" % transform_type)
+    if isinstance(image, str):
+        from PIL import Image
+        with Image.open(image) as im:
+            image = np.array(im.convert('RGB'))
+    first = int(size * 8 / 7)
+    i = int(round((first - size) / 2.))
+    if isinstance(image, torch.Tensor):
+        if not image.is_cuda:
+            raise TypeError("torch input must live on the GPU")
+        batch = image if image.dim() == 4 else image[None]
+        out = _ops.resize_u8(batch.contiguous(), (first, first), _PIL_RESIZE_TYPES[resize_type], crop=(i, i, size, size))
+        return out if image.dim() == 4 else out[0]
+    arr = np.ascontiguousarray(image)
+    if arr.dtype != np.uint8 or arr.ndim not in (3, 4) or arr.shape[-1] != 3:
+        raise ValueError("imagenet-s expects a file path or a uint8 array of shape ([n,] h, w, 3)")
+    dev = torch.device('cuda', torch.cuda.current_device())
+    d = torch.from_numpy(arr if arr.ndim == 4 else arr[None]).to(dev)
+    out = _ops.resize_u8(d, (first, first), _PIL_RESIZE_TYPES[resize_type], crop=(i, i, size, size)).cpu().numpy()
+    return out if arr.ndim == 4 else out[0]
 
 
 def pgd_l1(input, label, model, eps, input_size, eps_step, max_iter, batch_size):

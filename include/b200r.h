@@ -240,6 +240,21 @@ int b200r_stem_conv7x7_f32(const float* img, const uint16_t* wgt, const float* s
                            uint16_t* y, int n, int h, int w, const float* mean_host,
                            const float* std_host, int act, int passes, b200r_stream_t stream);
 
+/* Image.resize of Pillow, bit-exact, on uint8 NHWC batches, with a crop window of the resized image folded in
+ * (csrc/resize.cu).  Replaces ImageTransfer.image_resize for the `pil-*` resize types
+ * (RobustART/noise/utils/imagenet_s_gen.py:19-26,120-141: resize to (s*8/7)^2, centre crop s) and torchvision's
+ * Resize + CenterCrop of the eval transform (imagenet_dataloader.py:74-80).
+ *   in  : [n, hin, win, 3]       out : [n, ch, cw, 3] = resized[oy0 : oy0 + ch, ox0 : ox0 + cw]
+ *   filter : B200R_RESIZE_* = PIL.Image.{NEAREST, BOX, BILINEAR, HAMMING, BICUBIC, LANCZOS}
+ *   workspace : b200r_resize_workspace_bytes() bytes (the uint8 image between the horizontal and the vertical pass)
+ * The first call per (device, in size, out size, filter) builds and uploads a coefficient table (blocking). */
+enum b200r_resize_filter { B200R_RESIZE_NEAREST = 0, B200R_RESIZE_BOX = 1, B200R_RESIZE_BILINEAR = 2,
+                           B200R_RESIZE_HAMMING = 3, B200R_RESIZE_BICUBIC = 4, B200R_RESIZE_LANCZOS = 5 };
+int b200r_resize_workspace_bytes(int n, int hin, int win, int hout, int wout, int filter, int oy0, int ox0,
+                                 int ch, int cw, size_t* bytes);
+int b200r_resize_u8(const uint8_t* in, uint8_t* out, int n, int hin, int win, int hout, int wout, int filter,
+                    int oy0, int ox0, int ch, int cw, void* workspace, size_t ws_bytes, b200r_stream_t stream);
+
 /* MaxPool2d(3, 2, 1) on split planes NHWC (resnet_official.py:227) */
 int b200r_maxpool3x3s2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int c,
                             b200r_stream_t stream);

@@ -386,6 +386,43 @@ def stem_conv7x7_f32(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGEN
     return out
 
 
+RESIZE_FILTERS = {"nearest": 0, "box": 1, "bilinear": 2, "hamming": 3, "bicubic": 4, "cubic": 4, "lanczos": 5}
+
+
+def resize_u8(images, size, filter="bilinear", crop=None, out=None):
+    """PIL.Image.resize((size[1], size[0]), FILTER) of every image of a uint8 NHWC CUDA batch, bit-exact (csrc/resize.cu);
+    crop = (y0, x0, h, w) returns that window of the resized image (only it is computed)."""
+    import ctypes as C
+    _need_cuda(images, torch.uint8, "images")
+    n, hin, win, c = images.shape
+    assert c == 3 and images.is_contiguous()
+    hout, wout = int(size[0]), int(size[1])
+    y0, x0, ch, cw = crop if crop is not None else (0, 0, hout, wout)
+    fid = RESIZE_FILTERS[filter]
+    if out is None:
+        out = torch.empty((n, ch, cw, 3), dtype=torch.uint8, device=images.device)
+    lib = _lib.load()
+    with torch.cuda.device(images.device):
+        need = C.c_size_t()
+        _lib.check(lib.b200r_resize_workspace_bytes(n, hin, win, hout, wout, fid, y0, x0, ch, cw, C.byref(need)))
+        ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=images.device)
+        _lib.check(lib.b200r_resize_u8(images.data_ptr(), out.data_ptr(), n, hin, win, hout, wout, fid, y0, x0, ch, cw,
+                                       ws.data_ptr(), need.value, _stream()))
+    return out
+
+
+def resize_center_crop_u8(images, resize=256, crop=224, filter="bilinear"):
+    """torchvision Resize(resize) (short side, aspect kept: long side = int(resize * long / short)) + CenterCrop(crop) on a uint8
+    NHWC batch -- the eval transform of imagenet_dataloader.py:74-80, antialiased PIL bilinear as torchvision does on PIL images."""
+    n, h, w, _ = images.shape
+    if h <= w:
+        oh, ow = resize, int(resize * w / h)
+    else:
+        oh, ow = int(resize * h / w), resize
+    y0, x0 = int(round((oh - crop) / 2.0)), int(round((ow - crop) / 2.0))
+    return resize_u8(images, (oh, ow), filter, crop=(y0, x0, crop, crop))
+
+
 def maxpool3x3s2(x, out=None):
     P, n, h, w, c = x.shape
     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1

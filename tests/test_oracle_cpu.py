@@ -116,3 +116,22 @@ def test_rayleigh_table_normal():
     var = (r ** 2).mean() / 2
     kurt = (3 / 8 * (r ** 4).mean()) / var ** 2
     assert abs(var - 1) < 1e-3 and abs(kurt - 3) < 3e-3, (var, kurt)
+
+
+def test_resize_restatement_equals_pil():
+    """oracle/resize.py (Resample.c / Geometry.c restated in numpy) == Pillow's Image.resize for all six filters, up / down /
+    mixed scaling, odd sizes, and the ImageNet-S 'val' transform (imagenet_s_gen.py:131-141) built on it."""
+    from PIL import Image
+    from oracle import resize as R
+    F = {"nearest": Image.NEAREST, "box": Image.BOX, "bilinear": Image.BILINEAR, "hamming": Image.HAMMING,
+         "bicubic": Image.BICUBIC, "lanczos": Image.LANCZOS}
+    rs = np.random.RandomState(3)
+    for (h, w, oh, ow) in [(75, 100, 64, 64), (37, 53, 64, 80), (64, 64, 73, 73), (60, 40, 60, 25), (41, 97, 30, 97), (9, 11, 50, 33)]:
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        for name, f in F.items():
+            want = np.asarray(Image.fromarray(img).resize((ow, oh), f))
+            assert np.array_equal(R.resize(img, oh, ow, name), want), (h, w, oh, ow, name)
+    img = rs.randint(0, 256, (90, 120, 3)).astype(np.uint8)
+    for rt, f in [("pil-bilinear", Image.BILINEAR), ("pil-cubic", Image.BICUBIC), ("pil-nearest", Image.NEAREST)]:
+        full = np.asarray(Image.fromarray(img).resize((64, 64), f))      # size 56 -> first resize 64, crop offset 4
+        assert np.array_equal(R.imagenet_s_val(img, rt, size=56), full[4:60, 4:60])

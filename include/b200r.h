@@ -255,6 +255,17 @@ int b200r_resize_workspace_bytes(int n, int hin, int win, int hout, int wout, in
 int b200r_resize_u8(const uint8_t* in, uint8_t* out, int n, int hin, int win, int hout, int wout, int filter,
                     int oy0, int ox0, int ch, int cw, void* workspace, size_t ws_bytes, b200r_stream_t stream);
 
+/* Direct 3x3/s2/p1 convolution from the image (3 -> cout <= 64) + folded BN + activation, fp32 on CUDA cores: the stems
+ * of MobileNetV2 (mobilenet_v2.py:130) and EfficientNet-B0 (efficientnet.py:429-433), ToTensor + Normalize on the fly.
+ * img: uint8 NHWC [n,h,w,3] or float32 NCHW in [0,1]; wgt: float32 [cout][27], column = (ky*3 + kx)*3 + c;
+ * y: split planes [n, ho, wo, cout]. */
+int b200r_image_stem3x3s2_u8(const uint8_t* img, const float* wgt, const float* scale, const float* bias, uint16_t* y,
+                             int n, int h, int w, int cout, int act, const float* mean_host, const float* std_host,
+                             b200r_stream_t stream);
+int b200r_image_stem3x3s2_f32(const float* img, const float* wgt, const float* scale, const float* bias, uint16_t* y,
+                              int n, int h, int w, int cout, int act, const float* mean_host, const float* std_host,
+                              b200r_stream_t stream);
+
 /* MaxPool2d(3, 2, 1) on split planes NHWC (resnet_official.py:227) */
 int b200r_maxpool3x3s2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int c,
                             b200r_stream_t stream);

@@ -65,6 +65,10 @@ SIGNATURES = {
                                          c_host_f3, c_host_f3, C.c_int, C.c_int, c_stream]),
     "b200r_resize_workspace_bytes": (C.c_int, [C.c_int] * 10 + [C.POINTER(C.c_size_t)]),
     "b200r_resize_u8": (C.c_int, [c_u8p, c_u8p] + [C.c_int] * 10 + [C.c_void_p, C.c_size_t, c_stream]),
+    "b200r_image_stem3x3s2_u8": (C.c_int, [c_u8p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           c_host_f3, c_host_f3, c_stream]),
+    "b200r_image_stem3x3s2_f32": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            c_host_f3, c_host_f3, c_stream]),
     "b200r_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                           c_stream]),
     "b200r_global_avgpool_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

@@ -221,6 +221,67 @@ __global__ void __launch_bounds__(kThreads) image_im2col_kernel(const void* __re
   }
 }
 
+// Direct 3x3 / stride 2 / pad 1 convolution from the image (3 -> cout, cout <= 64) + folded BN + activation: the stems of
+// MobileNetV2 (mobilenet_v2.py:130) and EfficientNet-B0 (efficientnet.py:429-433).  As im2col (K = 27 padded to 32) + GEMM
+// the layer wrote and re-read a 205 MB patch matrix per 128 images (0.25 + 0.15 ms, 10 % of a MobileNetV2 forward); the
+// arithmetic is 1 728 FLOP per output pixel, so CUDA cores at fp32 do it in the time it takes to write the output.
+// thread = (output pixel, 8 output channels); weights [27][cout] in shared memory, ToTensor + Normalize on the fly.
+template <bool U8>
+__global__ void __launch_bounds__(kThreads) image_stem3x3s2_kernel(const void* __restrict__ img, const float* __restrict__ wgt,
+                                                                    const float* __restrict__ scale, const float* __restrict__ bias,
+                                                                    uint4* __restrict__ yh, uint4* __restrict__ yl, int n, int h, int w,
+                                                                    int ho, int wo, int cout, int act, Norm3 nm) {
+  __shared__ __align__(16) float sw[27 * 64];
+  __shared__ float lut[U8 ? 768 : 1];                                // ToTensor + Normalize of every byte value, per channel
+  for (int i = threadIdx.x; i < 27 * cout; i += kThreads) {          // wgt is [cout][27] (ky, kx, c) -> sw[tap][cout]
+    const int t = i / cout, oc = i - t * cout;
+    sw[i] = wgt[oc * 27 + t];
+  }
+  if (U8)
+    for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = (__fdiv_rn((float)(i & 255), 255.0f) - nm.mean[i >> 8]) / nm.std[i >> 8];
+  __syncthreads();
+  const int c8 = cout / 8;
+  const size_t total = (size_t)n * ho * wo * c8;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int cc = (int)(t % c8);
+    const size_t pix = t / c8;
+    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), im = (int)(pix / ((size_t)wo * ho));
+    float x[27];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
+        const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v = 0.f;
+          if (in) {
+            if (U8) v = lut[c * 256 + static_cast<const uint8_t*>(img)[(((size_t)im * h + iy) * w + ix) * 3 + c]];
+            else v = (static_cast<const float*>(img)[(((size_t)im * 3 + c) * h + iy) * w + ix] - nm.mean[c]) / nm.std[c];
+          }
+          x[(ky * 3 + kx) * 3 + c] = v;
+        }
+      }
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float4 w0 = *reinterpret_cast<const float4*>(sw + k * cout + cc * 8), w1 = *reinterpret_cast<const float4*>(sw + k * cout + cc * 8 + 4);
+      acc[0] = fmaf(x[k], w0.x, acc[0]); acc[1] = fmaf(x[k], w0.y, acc[1]); acc[2] = fmaf(x[k], w0.z, acc[2]); acc[3] = fmaf(x[k], w0.w, acc[3]);
+      acc[4] = fmaf(x[k], w1.x, acc[4]); acc[5] = fmaf(x[k], w1.y, acc[5]); acc[6] = fmaf(x[k], w1.z, acc[6]); acc[7] = fmaf(x[k], w1.w, acc[7]);
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y = fmaf(acc[j], scale[cc * 8 + j], bias[cc * 8 + j]);
+      o[j] = act == B200R_ACT_RELU6 ? fminf(fmaxf(y, 0.f), 6.f) : act == B200R_ACT_SWISH ? __fdividef(y, 1.f + __expf(-y)) : act_apply(y, act);
+    }
+    uint4 hh, ll;
+    pack8(o, hh, ll);
+    yh[t] = hh; yl[t] = ll;
+  }
+}
+
 inline unsigned grid_for(size_t items) {
   size_t b = (items + kThreads - 1) / kThreads;
   size_t cap = (size_t)b200r_num_sms() * 16;
@@ -288,6 +349,29 @@ int b200r_image_im2col_u8(const uint8_t* img, uint16_t* planes, int n, int h, in
 int b200r_image_im2col_f32(const float* img, uint16_t* planes, int n, int h, int w, int k, int stride, int pad, int kpad,
                            const float* mean_host, const float* std_host, b200r_stream_t stream) {
   return im2col_common(img, planes, n, h, w, k, stride, pad, kpad, mean_host, std_host, false, as_stream(stream));
+}
+
+static int stem3_common(const void* img, const float* wgt, const float* scale, const float* bias, uint16_t* y, int n, int h, int w, int cout,
+                        int act, const float* mean, const float* stdv, bool u8, cudaStream_t s) {
+  B200R_CHECK_ARG(img && wgt && scale && bias && y && mean && stdv, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0 && cout % 8 == 0 && cout <= 64, "image stem: cout must be a multiple of 8, <= 64");
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const size_t cnt = (size_t)n * ho * wo * cout;
+  Norm3 nm;
+  for (int i = 0; i < 3; ++i) { nm.mean[i] = mean[i]; nm.std[i] = stdv[i]; }
+  uint4 *yh = reinterpret_cast<uint4*>(y), *yl = reinterpret_cast<uint4*>(y + cnt);
+  if (u8) image_stem3x3s2_kernel<true><<<grid_for(cnt / 8), kThreads, 0, s>>>(img, wgt, scale, bias, yh, yl, n, h, w, ho, wo, cout, act, nm);
+  else image_stem3x3s2_kernel<false><<<grid_for(cnt / 8), kThreads, 0, s>>>(img, wgt, scale, bias, yh, yl, n, h, w, ho, wo, cout, act, nm);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+int b200r_image_stem3x3s2_u8(const uint8_t* img, const float* wgt, const float* scale, const float* bias, uint16_t* y, int n, int h, int w,
+                             int cout, int act, const float* mean_host, const float* std_host, b200r_stream_t stream) {
+  return stem3_common(img, wgt, scale, bias, y, n, h, w, cout, act, mean_host, std_host, true, as_stream(stream));
+}
+int b200r_image_stem3x3s2_f32(const float* img, const float* wgt, const float* scale, const float* bias, uint16_t* y, int n, int h, int w,
+                              int cout, int act, const float* mean_host, const float* std_host, b200r_stream_t stream) {
+  return stem3_common(img, wgt, scale, bias, y, n, h, w, cout, act, mean_host, std_host, false, as_stream(stream));
 }
 
 }  // extern "C"

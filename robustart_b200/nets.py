@@ -635,17 +635,23 @@ class _DW:
 
 
 class _ImageStem:
-    """3x3/s2 conv from the image: small im2col (K = 27 -> 32) + GEMM."""
+    """3x3/s2 conv from the image: one direct fp32 kernel (ops.image_stem3x3s2); B200R_IMAGE_STEM=gemm keeps the former
+    small im2col (K = 27 -> 32) + GEMM pair for A/B measurements."""
 
     def __init__(self, sd, conv, bn, device, act):
         w = sd[conv + ".weight"].float()                     # [32, 3, 3, 3]
+        w27 = w.permute(0, 2, 3, 1).reshape(w.shape[0], 27)
         wp = torch.zeros(w.shape[0], 32)
-        wp[:, :27] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 27)
+        wp[:, :27] = w27
         self.w = ops.split_f32(wp.to(device).contiguous())
+        self.w27 = w27.contiguous().to(device)
         self.scale, self.bias = _fold_bn(sd, bn, device)
         self.act, self.cout = act, w.shape[0]
+        self.direct = os.environ.get("B200R_IMAGE_STEM", "direct") != "gemm" and self.cout % 8 == 0 and self.cout <= 64
 
     def __call__(self, images, passes):
+        if self.direct:
+            return ops.image_stem3x3s2(images, self.w27, self.scale, self.bias, act=self.act)
         n = images.shape[0]
         cols, ho, wo = ops.image_im2col(images, 3, 2, 1, 32)
         x = ops.linear(cols, self.w, self.scale, self.bias, act=self.act, passes=passes)

@@ -605,6 +605,25 @@ def channel_scale(x, s):
     return out
 
 
+def image_stem3x3s2(img, wgt, scale, bias, *, act="relu6", mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """3x3/s2/p1 conv from the image + folded BN + activation in one launch (CUDA cores, fp32): planes [2, n, ho, wo, cout].
+    img: uint8 NHWC or float32 NCHW in [0,1]; wgt: float32 [cout, 27], column = (ky*3 + kx)*3 + c."""
+    if img.dtype == torch.uint8:
+        n, h, w, _ = img.shape
+        fn = _lib.load().b200r_image_stem3x3s2_u8
+    else:
+        _need_cuda(img, torch.float32, "img")
+        n, _, h, w = img.shape
+        fn = _lib.load().b200r_image_stem3x3s2_f32
+    cout = wgt.shape[0]
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = torch.empty((2, n, ho, wo, cout), dtype=torch.int16, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(fn(img.data_ptr(), wgt.data_ptr(), _ptr(scale), _ptr(bias), out.data_ptr(), n, h, w, cout, ACT[act],
+                      _lib.f3(mean), _lib.f3(std), _stream()))
+    return out
+
+
 def image_im2col(img, k, stride, pad, kpad, mean=IMAGENET_MEAN, std=IMAGENET_STD):
     if img.dtype == torch.uint8:
         n, h, w, _ = img.shape

@@ -123,18 +123,25 @@ class SyntheticImageNet:
     every sample in the reference, base_dataset.py:73-80; here every index gets its own seeded image).
     Items are generated on the fly from their global index, so any sharding sees the same data."""
 
-    def __init__(self, n_items: int, input_size: int, device, seed: int = 0):
+    def __init__(self, n_items: int, input_size: int, device, seed: int = 0, raw_size=None, test_resize: int = 256):
         self.n, self.size, self.device, self.seed = n_items, input_size, device, seed
+        # raw_size = (h, w): items are "decoded files" of that size and go through the eval transform on the GPU --
+        # Resize(test_resize) + CenterCrop(input_size), imagenet_dataloader.py:74-80 -- instead of being generated at input_size
+        self.raw_size = tuple(int(v) for v in raw_size) if raw_size else None
+        self.test_resize = int(test_resize)
 
     def batch(self, indices: torch.Tensor):
         n = len(indices)
-        imgs = torch.empty((n, self.size, self.size, 3), dtype=torch.uint8, device=self.device)
+        h, w = self.raw_size or (self.size, self.size)
+        imgs = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
         labels = torch.empty(n, dtype=torch.int64, device=self.device)
         g = torch.Generator(device=self.device)
         for j, idx in enumerate(indices.tolist()):
             g.manual_seed(self.seed * 1000003 + idx)
-            imgs[j] = torch.randint(0, 256, (self.size, self.size, 3), dtype=torch.uint8, device=self.device, generator=g)
+            imgs[j] = torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device=self.device, generator=g)
             labels[j] = idx % 1000
+        if self.raw_size:
+            imgs = ops.resize_center_crop_u8(imgs, self.test_resize, self.size)
         return imgs, labels
 
 
@@ -189,7 +196,8 @@ class EvalSolver:
         self.batch_size = int(data.get("batch_size", 64))
         self.input_size = int(data.get("input_size", 224))
         n_items = int(data.get("test", {}).get("limit_samples", data.get("num_samples", 50000)))
-        self.dataset = SyntheticImageNet(n_items, self.input_size, self.device)
+        self.dataset = SyntheticImageNet(n_items, self.input_size, self.device, raw_size=data.get("raw_size"),
+                                         test_resize=int(data.get("test_resize", 256)))
         self.indices = shard_indices(n_items, self.dist.world_size, self.dist.rank)
         self.result_path = os.path.join(config.get("save_path", "."), prefix, "results")
         if self.dist.rank == 0:

@@ -153,3 +153,28 @@ def test_cls_solver_dump_results_compat(cuda, tmp_path, monkeypatch):
     assert sorted(l["image_id"] for l in lines) == list(range(40))
     assert abs(m["file_metric"]["top1"] - m["top1"]) < 1e-4 and abs(m["file_metric"]["top5"] - m["top5"]) < 1e-4
     assert resultfile.evaluate(str(merged)) == m["file_metric"]
+
+
+def test_cls_solver_with_gpu_eval_transform(cuda, tmp_path, monkeypatch):
+    """data.raw_size: synthetic "decoded files" go through Resize(test_resize) + CenterCrop(input_size) on the GPU
+    (imagenet_dataloader.py:74-80, bit-exact Pillow resize) before the forward."""
+    monkeypatch.setenv("SKIP_DIST", "1")
+    import prototype.prototype.solver.cls_solver as cls
+    from robustart_b200 import solver as S
+    cfg_path = _cfg(tmp_path, n=24, bs=8)
+    cfg = yaml.safe_load(open(cfg_path))
+    cfg["data"]["raw_size"] = [300, 400]
+    open(cfg_path, "w").write(yaml.safe_dump(cfg))
+    m = cls.main(["--config", cfg_path, "--evaluate"])
+    assert m["count"] == 24 and 0 <= m["top1"] <= m["top5"] <= 100
+    ds = S.SyntheticImageNet(24, 224, cuda, raw_size=(300, 400), test_resize=256)
+    imgs, labels = ds.batch(torch.arange(3))
+    assert imgs.shape == (3, 224, 224, 3) and imgs.dtype == torch.uint8
+    from PIL import Image
+    import numpy as np
+    g = torch.Generator(device=cuda)
+    g.manual_seed(1)          # item 1: seed * 1000003 + idx with seed 0
+    raw = torch.randint(0, 256, (300, 400, 3), dtype=torch.uint8, device=cuda, generator=g).cpu().numpy()
+    pil = Image.fromarray(raw).resize((int(256 * 400 / 300), 256), Image.BILINEAR)
+    x0 = int(round((pil.size[0] - 224) / 2.0))
+    assert np.array_equal(imgs[1].cpu().numpy(), np.asarray(pil.crop((x0, 16, x0 + 224, 240))))

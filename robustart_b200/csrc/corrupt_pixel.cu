@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(512) impulse_rng_kernel(const uint4* __restric
 // ext layout: [n][P] caller-drawn Poisson counts.
 // =============================================================================================
 constexpr int kShotK = 128;
-constexpr int kShotThreads = 512;
+constexpr int kShotThreads = 1024;               // one CTA per SM (128 KB of alias tables): 32 warps to cover the table lookups' latency
 
 struct ShotTables {
   uint32_t* d_alias = nullptr;  // [256][128]
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kShotThreads, 1) shot_kernel(const uint4* __re
         float4 e = ld_stream_f4(ext + g * 16 + 4 * q);
         kk[0] = (uint32_t)e.x; kk[1] = (uint32_t)e.y; kk[2] = (uint32_t)e.z; kk[3] = (uint32_t)e.w;
       } else {
-        uint4 r = philox4x32_10(rng_counter(gi, RNG_SHOT, q, image_offset + img), k0, k1);
+        uint4 r = philox4x32<7>(rng_counter(gi, RNG_SHOT, q, image_offset + img), k0, k1);   // 7 rounds: Crush-resistant minimum (common.cuh)
         uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {

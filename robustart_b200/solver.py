@@ -328,9 +328,15 @@ class EvalSolver:
 
     # benchmark_eval_adv.py:191-254
     def evaluate_adv(self, model_src, model_tgt, attack="none", eps=0.0):
+        """benchmark_eval_adv.py:191-254.  Besides top-1 / top-5 after the attack the device counters carry the benchmark's
+        Adversarial Robustness (RobustART/metrics/AR_evaluator.py:23-39): correct before AND after the attack over correct
+        before -- one extra clean forward of the target model per batch, no result files.  `data.test.dump_results: true`
+        also writes `results.txt.*` (after the attack) and `clean-results.txt.*` in the reference's line format, which
+        RobustART.metrics.AdvRobustEvaluator / WorstCaseAdvRobustEvaluator read."""
         from RobustART.noise import AddNoise
         from .attacks import NativeModel, PyTorchModel
         counters = torch.zeros(3, dtype=torch.int64, device=self.device)
+        ar = torch.zeros(2, dtype=torch.int64, device=self.device)       # [correct before, correct before and after]
         gen = None
         if attack in ("autoattack_linf", "mim_linf", "pgd_l1"):
             gen = AddNoise(attack)
@@ -340,10 +346,49 @@ class EvalSolver:
                 model_src, bounds=(0, 1), preprocessing=dict(mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, axis=-3))
             gen = AddNoise(attack)
             gen.set_config(f_model=f_model, eps=eps)
+        dump = bool(self.config.data.get("test", {}).get("dump_results", False))
+        w_adv = w_clean = None
+        if dump:
+            from . import resultfile
+            w_adv = resultfile.ResultWriter(self.result_path, self.dist.rank, stem="results.txt")
+            w_clean = resultfile.ResultWriter(self.result_path, self.dist.rank, stem="clean-results.txt")
+        pred_c = torch.empty(self.batch_size, dtype=torch.int64, device=self.device)
+        pred_a = torch.empty(self.batch_size, dtype=torch.int64, device=self.device)
+        scratch = torch.zeros(3, dtype=torch.int64, device=self.device)
+        done = 0
         for imgs, labels in self._batches():
+            n = imgs.shape[0]
             x01 = ops.normalize(ops.u8nhwc_to_f32nchw(imgs), "inv")   # the loader normalises, the solver undoes it (:229)
+            logits_c = model_tgt(x01)
+            ops.topk_count_(scratch, logits_c, labels, pred_c[:n])
+            if dump:
+                ids = self.indices[done:done + n].tolist()
+                names = ["synthetic/%08d.JPEG" % i for i in ids]
+                w_clean.write_batch(pred_c[:n].cpu().numpy(), labels.cpu().numpy(), ops.softmax(logits_c).cpu().numpy(), names, ids)
             if gen is not None:
                 x01 = gen.add_noise(x01, labels).contiguous()
             logits = model_tgt(x01)                                   # normalisation fused into the stem gather
-            ops.topk_count_(counters, logits, labels)
-        return self._finish(counters, "results")
+            ops.topk_count_(counters, logits, labels, pred_a[:n])
+            ok_c = pred_c[:n] == labels
+            ar += torch.stack([ok_c.sum(), (ok_c & (pred_a[:n] == labels)).sum()])
+            if dump:
+                w_adv.write_batch(pred_a[:n].cpu().numpy(), labels.cpu().numpy(), ops.softmax(logits).cpu().numpy(), names, ids)
+            done += n
+        reduce_counters(ar, self.dist)
+        metric = self._finish(counters, "results")
+        a = ar.tolist()
+        metric["clean_top1"] = 100.0 * a[0] / max(metric["count"], 1)
+        metric["AR"] = 100.0 * a[1] / max(a[0], 1)
+        if dump:
+            from . import resultfile
+            w_adv.close(); w_clean.close()
+            if self.dist.initialized and self.dist.world_size > 1:
+                import torch.distributed as dist
+                dist.barrier()
+            if self.dist.rank == 0:
+                metric["result_file"] = resultfile.merge(os.path.join(self.result_path, "results.txt.rank"), self.dist.world_size)
+                metric["clean_result_file"] = resultfile.merge(os.path.join(self.result_path, "clean-results.txt.rank"), self.dist.world_size)
+        if self.dist.rank == 0:
+            with open(os.path.join(self.result_path, "results.metrics.json"), "w") as f:
+                json.dump(metric, f, indent=2)
+        return metric

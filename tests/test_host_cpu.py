@@ -59,3 +59,28 @@ def test_result_file_mode_matches_reference_dump(tmp_path):
     merged = R.merge(os.path.join(str(tmp_path), "results.txt.rank"), 2)
     assert os.path.basename(merged) == "results.txt.all" and open(merged).read() == g["merged"]
     assert R.evaluate(merged) == g["metric"]
+
+
+def test_ar_wcar_evaluators(tmp_path):
+    """RobustART.metrics.{AdvRobustEvaluator, WorstCaseAdvRobustEvaluator} on hand-made result files
+    (AR_evaluator.py:23-39, WCAR_evaluator.py:23-44): AR = kept / correct-before, WCAR = kept under every attack."""
+    import json
+    from RobustART.metrics import AdvRobustEvaluator, WorstCaseAdvRobustEvaluator
+
+    def write(name, preds, labels, dali):
+        p = tmp_path / name
+        with open(p, "w") as f:
+            for i, (a, b) in enumerate(zip(preds, labels)):
+                d = {"prediction": a, "label": b, "score": [0.5, 0.5]}
+                if not dali:
+                    d = {"filename": "f%d.JPEG" % i, "image_id": i, **d}
+                f.write(json.dumps(d) + "\n")
+        return str(p)
+
+    labels = [0, 1, 2, 3, 4, 5]
+    clean = write("clean", [0, 1, 2, 3, 9, 9], labels, dali=False)       # 4 correct before
+    a1 = write("a1", [0, 1, 7, 7, 4, 9], labels, dali=True)               # keeps 0, 1 (image 4 was wrong before: not counted)
+    a2 = write("a2", [0, 8, 2, 7, 9, 9], labels, dali=False)              # keeps 0, 2
+    assert AdvRobustEvaluator().eval(clean, a1) == 50.0
+    assert AdvRobustEvaluator().eval(clean, a2) == 50.0
+    assert WorstCaseAdvRobustEvaluator().eval(clean, [a1, a2]) == 25.0    # only image 0 survives both

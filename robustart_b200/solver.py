@@ -169,13 +169,20 @@ def build_source_model(model_cfg, ckpt_path, device):
 
 
 def build_torch_model(model_cfg, ckpt_path, device):
-    """An autograd-capable nn.Module twin (ResNet family) for the source model of an attack."""
+    """An autograd-capable nn.Module twin for the source model of an attack: the ResNet family and the token models
+    (ViT-B/16, MLP-Mixer-B/16 -- BASELINE configs[2] / [4]); same state_dict keys as the reference's classes."""
     from . import torch_models
     arch = nets.ARCH_ALIASES.get(model_cfg["type"], model_cfg["type"])
-    if arch not in torch_models._CFG:
-        raise NotImplementedError("source model %r: only the ResNet family has an autograd twin so far; use it as the "
-                                  "target (forward-only) model or pass your own nn.Module to AddNoise" % arch)
     sd = load_checkpoint(ckpt_path)
+    if isinstance(sd, dict) and "model" in sd and isinstance(sd["model"], dict):
+        sd = sd["model"]
+    if arch in torch_models._TOKEN:
+        if sd is None:
+            sd = nets.random_token_state_dict(nets._TOKEN_ARCHS[arch][1](), 0)
+        return torch_models.build(arch, nets._strip_prefix(sd)).to(device).eval()
+    if arch not in torch_models._CFG:
+        raise NotImplementedError("source model %r: the ResNet, ViT and MLP-Mixer families have autograd twins; use it as the "
+                                  "target (forward-only) model or pass your own nn.Module to AddNoise" % arch)
     if sd is None:
         sd = nets.random_state_dict(nets.resnet_spec(arch), 0)
     return torch_models.build(arch, nets._strip_prefix(sd)).to(device).eval()

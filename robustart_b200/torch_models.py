@@ -62,3 +62,84 @@ def build(arch, state_dict=None):
     if state_dict is not None:
         m.load_state_dict(state_dict, strict=True)
     return m.eval()
+
+
+# ------------------------------------------------------------------------------------------------
+# token models: ViT-B/16 (vision_transformer.py:44-349) and MLP-Mixer-B/16 (vit/mlp_mixer.py:7-159, vit/vit_base.py).
+# Functional twins over the reference's own state_dict keys (nets.vit_spec / nets.mixer_spec): autograd source models for
+# the attacks on BASELINE configs[2] / [4]; the TARGET model of an evaluation always runs on the B200 kernels.
+# ------------------------------------------------------------------------------------------------
+def _gelu_tanh(x):          # vision_transformer.py:19-37
+    return 0.5 * x * (1.0 + torch.tanh(0.7978845608028654 * (x + 0.044715 * x ** 3)))
+
+
+class _ParamModel(nn.Module):
+    def __init__(self, state_dict):
+        super().__init__()
+        self.keys = {}
+        for i, (k, v) in enumerate(state_dict.items()):
+            name = "p%d" % i
+            self.register_buffer(name, v.detach().clone().float())
+            self.keys[k] = name
+
+    def w(self, key):
+        return getattr(self, self.keys[key])
+
+
+class ViT(_ParamModel):
+    def __init__(self, state_dict, depth=12, dim=768, heads=12, patch=16):
+        super().__init__(state_dict)
+        self.depth, self.dim, self.heads, self.patch = depth, dim, heads, patch
+
+    def forward(self, x):                                   # normalised float32 NCHW
+        n, w = x.shape[0], self.w
+        x = F.conv2d(x, w("embedding.weight"), w("embedding.bias"), stride=self.patch).flatten(2).transpose(1, 2)
+        x = torch.cat([w("cls_token").expand(n, -1, -1), x], 1) + w("pos_embedding")
+        hd = self.dim // self.heads
+        for d in range(self.depth):
+            p = "transformer.encoders.encoder_%d." % d
+            y = F.layer_norm(x, (self.dim,), w(p + "norm1.weight"), w(p + "norm1.bias"), 1e-5)
+            qkv = F.linear(y, w(p + "attention.to_qkv.weight"), w(p + "attention.to_qkv.bias"))
+            q, k, v = qkv.view(n, -1, 3, self.heads, hd).permute(2, 0, 3, 1, 4)          # "(qkv h d)" packing, :82
+            a = torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5, -1) @ v
+            a = a.permute(0, 2, 1, 3).reshape(n, -1, self.dim)
+            x = x + F.linear(a, w(p + "attention.to_out.weight"), w(p + "attention.to_out.bias"))
+            y = F.layer_norm(x, (self.dim,), w(p + "norm2.weight"), w(p + "norm2.bias"), 1e-5)
+            y = _gelu_tanh(F.linear(y, w(p + "feedforward.mlp1.weight"), w(p + "feedforward.mlp1.bias")))
+            x = x + F.linear(y, w(p + "feedforward.mlp2.weight"), w(p + "feedforward.mlp2.bias"))
+        x = F.layer_norm(x, (self.dim,), w("transformer.encoder_norm.weight"), w("transformer.encoder_norm.bias"), 1e-5)[:, 0]
+        if "pre_logits.weight" in self.keys:
+            x = torch.tanh(F.linear(x, w("pre_logits.weight"), w("pre_logits.bias")))       # :289-291
+        return F.linear(x, w("head.weight"), w("head.bias"))
+
+
+class Mixer(_ParamModel):
+    def __init__(self, state_dict, depth=12, dim=768, patch=16):
+        super().__init__(state_dict)
+        self.depth, self.dim, self.patch = depth, dim, patch
+
+    def forward(self, x):
+        w = self.w
+        x = F.conv2d(x, w("patch_embed.proj.weight"), w("patch_embed.proj.bias"), stride=self.patch).flatten(2).transpose(1, 2)
+        for d in range(self.depth):
+            p = "blocks.%d." % d
+            y = F.layer_norm(x, (self.dim,), w(p + "norm1.weight"), w(p + "norm1.bias"), 1e-6).transpose(1, 2)
+            y = F.linear(F.gelu(F.linear(y, w(p + "token_mix.fc1.weight"), w(p + "token_mix.fc1.bias"))),
+                         w(p + "token_mix.fc2.weight"), w(p + "token_mix.fc2.bias"))
+            x = x + y.transpose(1, 2)
+            y = F.layer_norm(x, (self.dim,), w(p + "norm2.weight"), w(p + "norm2.bias"), 1e-6)
+            x = x + F.linear(F.gelu(F.linear(y, w(p + "channel_mix.fc1.weight"), w(p + "channel_mix.fc1.bias"))),
+                             w(p + "channel_mix.fc2.weight"), w(p + "channel_mix.fc2.bias"))
+        x = F.layer_norm(x, (self.dim,), w("norm.weight"), w("norm.bias"), 1e-6).mean(1)
+        return F.linear(x, w("head.weight"), w("head.bias"))
+
+
+_TOKEN = {"vit_b16_224": ViT, "vit_base_patch16_224": ViT, "mixer_b16_224": Mixer}
+_build_resnet_twin = build
+
+
+def build(arch, state_dict=None):  # noqa: F811
+    if arch in _TOKEN:
+        assert state_dict is not None, "the token twins are functional over a state_dict"
+        return _TOKEN[arch](state_dict).eval()
+    return _build_resnet_twin(arch, state_dict)

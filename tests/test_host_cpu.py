@@ -84,3 +84,24 @@ def test_ar_wcar_evaluators(tmp_path):
     assert AdvRobustEvaluator().eval(clean, a1) == 50.0
     assert AdvRobustEvaluator().eval(clean, a2) == 50.0
     assert WorstCaseAdvRobustEvaluator().eval(clean, [a1, a2]) == 25.0    # only image 0 survives both
+
+
+def test_token_autograd_twins_match_reference_logits():
+    """torch_models.ViT / Mixer (the autograd SOURCE models of attacks on BASELINE configs[2] / [4]) reproduce the golden logits
+    of the reference's own classes (tests/golden/make_golden_models.py --tokens) on CPU, and give input gradients."""
+    import os
+    import numpy as np
+    import torch
+    from robustart_b200 import nets, torch_models
+    from util import synth_images
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "token_logits.npz"))
+    imgs = torch.from_numpy(synth_images(2, seed=9))
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    x = ((imgs.permute(0, 3, 1, 2).float().div(255) - mean) / std).requires_grad_(True)
+    for arch, spec in (("vit_b16_224", nets.vit_spec()), ("mixer_b16_224", nets.mixer_spec())):
+        m = torch_models.build(arch, nets.random_token_state_dict(spec, 0))
+        y = m(x)
+        assert np.abs(y.detach().numpy() - gold[arch]).max() < 1e-5, arch
+        (g,) = torch.autograd.grad(torch.nn.functional.cross_entropy(y, torch.tensor([1, 2])), x)
+        assert g.shape == x.shape and torch.isfinite(g).all() and g.abs().max() > 0

@@ -200,3 +200,23 @@ def test_adv_solver_ar_and_result_files(cuda, tmp_path, monkeypatch):
     assert abs(wcar - ar) < 1e-9
     lines = [json.loads(l) for l in open(m["result_file"])]
     assert abs(100.0 * sum(l["prediction"] == l["label"] for l in lines) / 48 - m["top1"]) < 1e-9
+
+
+@pytest.mark.parametrize("name,attack", [("vit_base_patch16_224", "pgd_linf"), ("mixer_b16_224", "fgsm")])
+def test_adv_cli_token_models(cuda, tmp_path, monkeypatch, name, attack):
+    """BASELINE configs[2] / [4] in miniature: white-box attack on a token model from the command line -- source = the
+    autograd twin (torch_models.ViT / Mixer), target = the B200 kernels; the two agree on the clean logits."""
+    monkeypatch.setenv("SKIP_DIST", "1")
+    import prototype.prototype.solver.base_benchmark_eval_adv as adv
+    from robustart_b200 import nets, ops, solver as S, torch_models
+    cfg = _cfg(tmp_path, n=8, bs=4)
+    m = adv.main(["--config", cfg, "--src_name", name, "--src_path", "", "--tgt_name", name, "--tgt_path", "",
+                  "--attack", attack, "--eps", "4/255"])
+    assert m["count"] == 8 and 0 <= m["AR"] <= 100
+    arch = S.model_name_dict[name]["type"]
+    twin = S.build_torch_model({"type": arch}, "", cuda)
+    tgt = nets.build_model(arch, device=cuda)
+    x = torch.rand(2, 3, 224, 224, device=cuda)
+    with torch.no_grad():
+        a = twin(ops.normalize(x.clone()))
+    assert (tgt(x) - a).abs().max().item() < 2e-3

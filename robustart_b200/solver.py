@@ -169,20 +169,22 @@ def build_source_model(model_cfg, ckpt_path, device):
 
 
 def build_torch_model(model_cfg, ckpt_path, device):
-    """An autograd-capable nn.Module twin for the source model of an attack: the ResNet family and the token models
-    (ViT-B/16, MLP-Mixer-B/16 -- BASELINE configs[2] / [4]); same state_dict keys as the reference's classes."""
+    """An autograd-capable nn.Module twin for the source model of an attack: the ResNet family, the token models
+    (ViT-B/16, MLP-Mixer-B/16 -- BASELINE configs[2] / [4]) and the mobile families (MobileNetV2, EfficientNet-B0);
+    same state_dict keys as the reference's classes."""
     from . import torch_models
     arch = nets.ARCH_ALIASES.get(model_cfg["type"], model_cfg["type"])
     sd = load_checkpoint(ckpt_path)
     if isinstance(sd, dict) and "model" in sd and isinstance(sd["model"], dict):
         sd = sd["model"]
     if arch in torch_models._TOKEN:
-        if sd is None:
-            sd = nets.random_token_state_dict(nets._TOKEN_ARCHS[arch][1](), 0)
+        if sd is None:      # synthetic weights: the same ones nets.build_model(arch) generates for the kernel model
+            sd = (nets.random_token_state_dict(nets._TOKEN_ARCHS[arch][1](), 0) if arch in nets._TOKEN_ARCHS
+                  else nets.random_state_dict(nets._MOBILE_ARCHS[arch][1](), 0))
         return torch_models.build(arch, nets._strip_prefix(sd)).to(device).eval()
     if arch not in torch_models._CFG:
-        raise NotImplementedError("source model %r: the ResNet, ViT and MLP-Mixer families have autograd twins; use it as the "
-                                  "target (forward-only) model or pass your own nn.Module to AddNoise" % arch)
+        raise NotImplementedError("source model %r: the ResNet, ViT, MLP-Mixer, MobileNetV2 and EfficientNet-B0 families have "
+                                  "autograd twins; use it as the target (forward-only) model or pass your own nn.Module to AddNoise" % arch)
     if sd is None:
         sd = nets.random_state_dict(nets.resnet_spec(arch), 0)
     return torch_models.build(arch, nets._strip_prefix(sd)).to(device).eval()

@@ -134,7 +134,71 @@ class Mixer(_ParamModel):
         return F.linear(x, w("head.weight"), w("head.bias"))
 
 
-_TOKEN = {"vit_b16_224": ViT, "vit_base_patch16_224": ViT, "mixer_b16_224": Mixer}
+# ------------------------------------------------------------------------------------------------
+# mobile families: MobileNetV2 x1.0 (mobilenet_v2.py:31-202) and EfficientNet-B0 (efficientnet.py:289-495), functional twins
+# over the reference's state_dict keys (nets.mobilenet_v2_spec / nets.efficientnet_b0_spec), eval mode (BN affine).
+# ------------------------------------------------------------------------------------------------
+_MBV2_SETTING = [[1, 16, 1, 1], [6, 24, 2, 2], [6, 32, 3, 2], [6, 64, 4, 2], [6, 96, 3, 1], [6, 160, 3, 2], [6, 320, 1, 1]]
+_EFFB0_BLOCKS = [(1, 3, 1, 1, 32, 16), (2, 3, 2, 6, 16, 24), (2, 5, 2, 6, 24, 40), (3, 3, 2, 6, 40, 80), (3, 5, 1, 6, 80, 112),
+                 (4, 5, 2, 6, 112, 192), (1, 3, 1, 6, 192, 320)]
+
+
+class _ConvNetTwin(_ParamModel):
+    def bn(self, x, name):
+        w = self.w
+        return F.batch_norm(x, w(name + ".running_mean"), w(name + ".running_var"), w(name + ".weight"), w(name + ".bias"), False, 0.0, 1e-5)
+
+    def cbn(self, x, conv, bn, stride=1, groups=1):
+        wt = self.w(conv + ".weight")
+        return self.bn(F.conv2d(x, wt, None, stride, wt.shape[-1] // 2, 1, groups), bn)
+
+
+class MobileNetV2(_ConvNetTwin):
+    def forward(self, x):
+        x = F.relu6(self.cbn(x, "features.0.0", "features.0.1", 2))
+        cin, idx = 32, 1
+        for t, c, n, s in _MBV2_SETTING:
+            for i in range(n):
+                stride, p, j = (s if i == 0 else 1), "features.%d.conv." % idx, 0
+                y = x
+                if t != 1:
+                    y = F.relu6(self.cbn(y, p + "0.0", p + "0.1"))
+                    j = 1
+                y = F.relu6(self.cbn(y, p + "%d.0" % j, p + "%d.1" % j, stride, groups=y.shape[1]))
+                y = self.cbn(y, p + "%d" % (j + 1), p + "%d" % (j + 2))
+                x = x + y if (stride == 1 and cin == c) else y
+                cin, idx = c, idx + 1
+        x = F.relu6(self.cbn(x, "features.%d.0" % idx, "features.%d.1" % idx))
+        return F.linear(x.mean((2, 3)), self.w("classifier.1.weight"), self.w("classifier.1.bias"))
+
+
+class EfficientNetB0(_ConvNetTwin):
+    def forward(self, x):
+        sw = lambda v: v * torch.sigmoid(v)                      # efficientnet.py:271-277
+        w = self.w
+        x = sw(self.cbn(x, "stem.0", "stem.1", 2))
+        bi = 0
+        for rep, k, s, e, cin, cout in _EFFB0_BLOCKS:
+            for r in range(rep):
+                ci, stride = (cin if r == 0 else cout), (s if r == 0 else 1)
+                p, j = "blocks.%d." % bi, 0
+                y = x
+                if e != 1:
+                    y = sw(self.cbn(y, p + "in_conv.0", p + "in_conv.1"))
+                    j = 3
+                y = sw(self.cbn(y, p + "in_conv.%d" % j, p + "in_conv.%d" % (j + 1), stride, groups=y.shape[1]))
+                q = y.mean((2, 3), keepdim=True)                                  # squeeze on the expanded tensor
+                q = sw(F.conv2d(q, w(p + "se_block.conv1.weight"), w(p + "se_block.conv1.bias")))
+                q = torch.sigmoid(F.conv2d(q, w(p + "se_block.conv2.weight"), w(p + "se_block.conv2.bias")))
+                y = self.cbn(y * q, p + "out_conv.0", p + "out_conv.1")
+                x = x + y if (stride == 1 and ci == cout) else y
+                bi += 1
+        x = sw(self.cbn(x, "head.0", "head.1"))
+        return F.linear(x.mean((2, 3)), w("fc.weight"), w("fc.bias"))
+
+
+_TOKEN = {"vit_b16_224": ViT, "vit_base_patch16_224": ViT, "mixer_b16_224": Mixer,
+          "mobilenet_v2": MobileNetV2, "mobilenet_v2_x1_0": MobileNetV2, "efficientnet_b0": EfficientNetB0}
 _build_resnet_twin = build
 
 

@@ -105,3 +105,18 @@ def test_token_autograd_twins_match_reference_logits():
         assert np.abs(y.detach().numpy() - gold[arch]).max() < 1e-5, arch
         (g,) = torch.autograd.grad(torch.nn.functional.cross_entropy(y, torch.tensor([1, 2])), x)
         assert g.shape == x.shape and torch.isfinite(g).all() and g.abs().max() > 0
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "mobile_logits.npz"))
+    imgs = torch.from_numpy(synth_images(2, seed=11))
+    x = ((imgs.permute(0, 3, 1, 2).float().div(255) - mean) / std).requires_grad_(True)
+    for arch in ("mobilenet_v2", "efficientnet_b0"):
+        m = torch_models.build(arch, nets.random_state_dict(nets._MOBILE_ARCHS[arch][1](), 0))
+        y = m(x)
+        assert np.abs(y.detach().numpy() - gold[arch]).max() < 1e-6, arch
+        # the synthetic weights attenuate the signal layer by layer (the float32 input gradient underflows to denormals):
+        # differentiate the float64 copy
+        xd = x.detach().double().requires_grad_(True)
+        (g,) = torch.autograd.grad(m.double()(xd).square().sum(), xd)
+        assert torch.isfinite(g).all() and g.abs().max() > 0
+    from robustart_b200 import solver as S
+    for name in ("mobilenet_v2_x1_0", "efficientnet_b0", "vit_base_patch16_224", "mixer_b16_224", "resnet18"):
+        assert isinstance(S.build_torch_model({"type": S.model_name_dict[name]["type"]}, "", "cpu"), torch.nn.Module)

@@ -145,6 +145,41 @@ class SyntheticImageNet:
         return imgs, labels
 
 
+class FileImageNet:
+    """`read_from: fs` (imagenet_dataset.py:55-67, base_dataset.py:55-72): `meta_file` lines "filename label" under `root_dir`.
+    Files are decoded on the host with PIL (`image_reader.type: pil`, image_reader.py:11-18 -- file parsing is outside the
+    hot path, as in the reference) and go through the eval transform on the GPU: Resize(test_resize) + CenterCrop(input_size)
+    as ONE bit-exact Pillow-resize launch per image (imagenet_dataloader.py:74-80; ops.resize_center_crop_u8)."""
+
+    def __init__(self, root_dir: str, meta_file: str, input_size: int, device, test_resize: int = 256, limit: Optional[int] = None):
+        self.root, self.size, self.device, self.test_resize = root_dir, input_size, device, int(test_resize)
+        self.metas = []
+        with open(meta_file) as f:
+            for line in f:
+                if line.strip():
+                    filename, label = line.rstrip().split()
+                    self.metas.append((filename, int(label)))
+        if limit is not None:
+            self.metas = self.metas[:int(limit)]
+        self.n = len(self.metas)
+
+    def filename(self, idx: int) -> str:
+        return self.metas[idx][0]
+
+    def batch(self, indices: torch.Tensor):
+        import numpy as np
+        from PIL import Image
+        imgs, labels = [], []
+        for idx in indices.tolist():
+            name, label = self.metas[idx]
+            with Image.open(os.path.join(self.root, name)) as im:
+                arr = np.array(im.convert("RGB"))
+            d = torch.from_numpy(arr)[None].to(self.device)
+            imgs.append(ops.resize_center_crop_u8(d, self.test_resize, self.size)[0])
+            labels.append(label)
+        return torch.stack(imgs), torch.tensor(labels, dtype=torch.int64, device=self.device)
+
+
 def load_checkpoint(path: Optional[str]) -> Optional[Dict[str, torch.Tensor]]:
     if not path or not os.path.exists(path):
         return None
@@ -199,18 +234,30 @@ class EvalSolver:
             raise RuntimeError("the evaluation solvers need a CUDA device (as the reference does, cls_solver.py:108)")
         self.device = torch.device("cuda", torch.cuda.current_device())
         data = config.data
-        if data.get("read_from", "fake") not in ("fake", "synthetic"):
-            raise NotImplementedError("data.read_from=%r: file/JPEG readers are outside the B200 hot path; "
-                                      "use read_from: fake (synthetic tensors)" % data.get("read_from"))
+        read_from = data.get("read_from", "fake")
+        if read_from not in ("fake", "synthetic", "fs", "file"):
+            raise NotImplementedError("data.read_from=%r: only `fake` (synthetic tensors) and `fs` (files decoded with PIL on the "
+                                      "host, transformed on the GPU) are implemented; memcached / petrel / DALI readers are "
+                                      "outside the B200 hot path" % read_from)
         self.batch_size = int(data.get("batch_size", 64))
         self.input_size = int(data.get("input_size", 224))
-        n_items = int(data.get("test", {}).get("limit_samples", data.get("num_samples", 50000)))
-        self.dataset = SyntheticImageNet(n_items, self.input_size, self.device, raw_size=data.get("raw_size"),
-                                         test_resize=int(data.get("test_resize", 256)))
+        test = data.get("test", {})
+        if read_from in ("fs", "file"):
+            self.dataset = FileImageNet(test["root_dir"], test["meta_file"], self.input_size, self.device,
+                                        test_resize=int(data.get("test_resize", 256)), limit=test.get("limit_samples"))
+            n_items = self.dataset.n
+        else:
+            n_items = int(test.get("limit_samples", data.get("num_samples", 50000)))
+            self.dataset = SyntheticImageNet(n_items, self.input_size, self.device, raw_size=data.get("raw_size"),
+                                             test_resize=int(data.get("test_resize", 256)))
         self.indices = shard_indices(n_items, self.dist.world_size, self.dist.rank)
         self.result_path = os.path.join(config.get("save_path", "."), prefix, "results")
         if self.dist.rank == 0:
             os.makedirs(self.result_path, exist_ok=True)
+
+    def _filenames(self, ids):
+        fn = getattr(self.dataset, "filename", None)
+        return [fn(i) if fn else "synthetic/%08d.JPEG" % i for i in ids]
 
     def _batches(self):
         for i in range(0, len(self.indices), self.batch_size):
@@ -252,7 +299,7 @@ class EvalSolver:
                 ops.topk_count_(counters, logits, labels, pred[:n])
                 ids = self.indices[done:done + n].tolist()
                 writer.write_batch(pred[:n].cpu().numpy(), labels.cpu().numpy(), ops.softmax(logits).cpu().numpy(),
-                                   ["synthetic/%08d.JPEG" % i for i in ids], ids)
+                                   self._filenames(ids), ids)
             done += n
         metric = self._finish(counters, tag)
         if writer is not None:
@@ -372,7 +419,7 @@ class EvalSolver:
             ops.topk_count_(scratch, logits_c, labels, pred_c[:n])
             if dump:
                 ids = self.indices[done:done + n].tolist()
-                names = ["synthetic/%08d.JPEG" % i for i in ids]
+                names = self._filenames(ids)
                 w_clean.write_batch(pred_c[:n].cpu().numpy(), labels.cpu().numpy(), ops.softmax(logits_c).cpu().numpy(), names, ids)
             if gen is not None:
                 x01 = gen.add_noise(x01, labels).contiguous()

@@ -120,3 +120,38 @@ def test_token_autograd_twins_match_reference_logits():
     from robustart_b200 import solver as S
     for name in ("mobilenet_v2_x1_0", "efficientnet_b0", "vit_base_patch16_224", "mixer_b16_224", "resnet18"):
         assert isinstance(S.build_torch_model({"type": S.model_name_dict[name]["type"]}, "", "cpu"), torch.nn.Module)
+
+
+def test_file_dataset_host_logic(tmp_path, monkeypatch):
+    """solver.FileImageNet (`read_from: fs`): meta-file parsing, PIL decode, per-image transform, labels, filenames
+    (imagenet_dataset.py:55-67, imagenet_dataloader.py:74-80).  The GPU resize launch is replaced by the same Pillow call it is
+    bit-exact with (tests/test_resize_gpu.py) so the host logic runs without a device."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from robustart_b200 import ops, solver as S
+
+    def pil_transform(d, resize, crop, filter="bilinear"):
+        arr = d[0].cpu().numpy()
+        h, w = arr.shape[:2]
+        oh, ow = (resize, int(resize * w / h)) if h <= w else (int(resize * h / w), resize)
+        im = Image.fromarray(arr).resize((ow, oh), Image.BILINEAR)
+        y0, x0 = int(round((oh - crop) / 2.0)), int(round((ow - crop) / 2.0))
+        return torch.from_numpy(np.asarray(im.crop((x0, y0, x0 + crop, y0 + crop))).copy())[None]
+
+    monkeypatch.setattr(ops, "resize_center_crop_u8", pil_transform)
+    rs = np.random.RandomState(0)
+    (tmp_path / "val").mkdir()
+    sizes = [(90, 120), (150, 100), (64, 64), (80, 200)]
+    lines = []
+    for i, (h, w) in enumerate(sizes):
+        Image.fromarray(rs.randint(0, 256, (h, w, 3)).astype(np.uint8)).save(tmp_path / "val" / ("img%d.png" % i))
+        lines.append("img%d.png %d" % (i, 100 + i))
+    (tmp_path / "meta.txt").write_text("\n".join(lines) + "\n")
+    ds = S.FileImageNet(str(tmp_path / "val"), str(tmp_path / "meta.txt"), 56, "cpu", test_resize=64)
+    assert ds.n == 4 and ds.filename(2) == "img2.png"
+    imgs, labels = ds.batch(torch.tensor([3, 0]))
+    assert imgs.shape == (2, 56, 56, 3) and imgs.dtype == torch.uint8 and labels.tolist() == [103, 100]
+    want = pil_transform(torch.from_numpy(np.array(Image.open(tmp_path / "val" / "img3.png").convert("RGB")))[None], 64, 56)[0]
+    assert torch.equal(imgs[0], want)
+    assert S.FileImageNet(str(tmp_path / "val"), str(tmp_path / "meta.txt"), 56, "cpu", limit=3).n == 3

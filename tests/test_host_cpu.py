@@ -59,6 +59,13 @@ def test_result_file_mode_matches_reference_dump(tmp_path):
     merged = R.merge(os.path.join(str(tmp_path), "results.txt.rank"), 2)
     assert os.path.basename(merged) == "results.txt.all" and open(merged).read() == g["merged"]
     assert R.evaluate(merged) == g["metric"]
+    # the ImageNet-C file evaluator on the same file (imagenetc_evaluator.py:49-77): same numbers + the "metric" file
+    from RobustART.metrics import ImageNetCEvaluator
+    noise = os.path.join(str(tmp_path), "noise-fog-3-results.txt.all")
+    open(noise, "w").write(g["merged"])
+    m = ImageNetCEvaluator().eval(noise)
+    assert m.metric == g["metric"] and m.v == g["metric"]["top1"]
+    assert json.load(open(os.path.join(str(tmp_path), "noise-fog-3-metric"))) == g["metric"]
 
 
 def test_ar_wcar_evaluators(tmp_path):

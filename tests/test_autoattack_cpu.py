@@ -1,0 +1,77 @@
+"""The PRODUCT's APGD control flow (robustart_b200/autoattack.py: checkpoints, oscillation test, step halving, restart from the
+best point, best-adversarial bookkeeping) against the reference's own `attack_single_run` (autopgd_base.py:208-448), on CPU.
+
+Goldens: tests/golden/attack_pieces.npz, produced by running the reference's vendored APGDAttack / APGDAttack_targeted with
+device='cpu' on a tiny seeded CNN (tests/golden/make_golden_attacks.py).  The three device kernels the loop launches are
+replaced here -- in the test only -- by the torch statements they implement (each kernel is checked against the same
+statements on the GPU in tests/test_autoattack_gpu.py); everything else is the code that runs in production."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "attack_pieces.npz"))
+
+
+def _tiny_model():
+    torch.manual_seed(123)
+    m = nn.Sequential(nn.Conv2d(3, 8, 3, 2, 1), nn.ReLU(), nn.Conv2d(8, 16, 3, 2, 1), nn.ReLU(), nn.AdaptiveAvgPool2d(1), nn.Flatten(),
+                      nn.Linear(16, 10)).eval()
+    for p in m.parameters():
+        p.requires_grad_(False)
+    return m
+
+
+def _step(x_adv, x_old, grad, x0, step, eps, a):          # b200r_apgd_step_linf: autopgd_base.py:332-338, in place
+    s = step.view(-1, 1, 1, 1)
+    grad2 = x_adv - x_old
+    x_old.copy_(x_adv)
+    x1 = x_adv + s * torch.sign(grad)
+    x1 = torch.clamp(torch.min(torch.max(x1, x0 - eps), x0 + eps), 0.0, 1.0)
+    x1 = torch.clamp(torch.min(torch.max(x_adv + (x1 - x_adv) * a + grad2 * (1 - a), x0 - eps), x0 + eps), 0.0, 1.0)
+    x_adv.copy_(x1)
+
+
+def _masked(dst, src, mask):                               # b200r_masked_rows_copy
+    dst[mask] = src[mask]
+
+
+class _TorchModel:                                         # autoattack._Model.loss_and_grad with autograd instead of the kernels
+    def __init__(self, model):
+        self.model = model
+
+    def loss_and_grad(self, x, y, kind, target=None):
+        from oracle import autoattack as OAA
+        x = x.clone().requires_grad_(True)
+        lg = self.model(x)
+        if kind == "ce":
+            li = F.cross_entropy(lg, y, reduction="none")
+        elif kind == "dlr":
+            li = OAA.dlr_loss(lg, y)
+        else:
+            li = OAA.dlr_loss_targeted(lg, y, target)
+        (g,) = torch.autograd.grad(li.sum(), x)
+        return lg.detach(), li.detach(), g
+
+
+@pytest.mark.parametrize("loss,key", [("ce", "ce"), ("dlr", "dlr"), ("dlr-targeted", "t")])
+def test_apgd_control_flow_matches_reference_run(monkeypatch, loss, key):
+    from robustart_b200 import autoattack as AA
+    monkeypatch.setattr(AA, "_apgd_step_", _step)
+    monkeypatch.setattr(AA, "_masked_rows_", _masked)
+    eps, n_iter, seed = G["apgd_cfg"].tolist()
+    x, y = torch.from_numpy(G["apgd_x"]), torch.from_numpy(G["apgd_y"])
+    target = torch.from_numpy(G["apgd_t_target"]) if loss == "dlr-targeted" else None
+    apgd = AA.APGD(_TorchModel(_tiny_model()), eps, n_iter=int(n_iter), loss=loss)
+    assert (apgd.n_iter_2, apgd.n_iter_min, apgd.size_decr) == (4, 1, 1)          # autopgd_base.py:163-165 at 20 iterations
+    torch.manual_seed(int(seed))
+    x_best, acc, loss_best, x_best_adv = apgd.single_run(x.clone(), y, target)
+    assert torch.equal(acc, torch.from_numpy(G["apgd_%s_acc" % key]))
+    assert acc.any() and not acc.all()                                              # the golden has robust and fooled samples
+    assert np.abs(x_best.numpy() - G["apgd_%s_x_best" % key]).max() <= 1e-6
+    assert np.abs(x_best_adv.numpy() - G["apgd_%s_x_best_adv" % key]).max() <= 1e-6
+    assert np.abs(loss_best.numpy() - G["apgd_%s_loss" % key]).max() <= 1e-5
+    assert (x_best_adv - x).abs().max().item() <= eps + 1e-6 and x_best_adv.min() >= 0 and x_best_adv.max() <= 1

@@ -135,3 +135,34 @@ def test_resize_restatement_equals_pil():
     for rt, f in [("pil-bilinear", Image.BILINEAR), ("pil-cubic", Image.BICUBIC), ("pil-nearest", Image.NEAREST)]:
         full = np.asarray(Image.fromarray(img).resize((64, 64), f))      # size 56 -> first resize 64, crop offset 4
         assert np.array_equal(R.imagenet_s_val(img, rt, size=56), full[4:60, 4:60])
+
+
+def test_attack_pieces_match_reference_code():
+    """Pieces of the attack path against golden vectors produced by the REFERENCE's own vendored code on CPU
+    (tests/golden/make_golden_attacks.py): the MI-FGSM oracle == imfgsm_attack.py:_mim_whitebox bit for bit (same start
+    draws), the DLR formulas == APGDAttack.dlr_loss / dlr_loss_targeted, and two host-side pieces of the product that are
+    device-agnostic torch / python: FAB's projection_linf (fab_projections.py:7-59) and Square's p schedule (square.py:192-219)."""
+    import os
+    import torch
+    import torch.nn as nn
+    from oracle import attacks as OA, autoattack as OAA
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "attack_pieces.npz"))
+    # MI-FGSM: the generator's tiny CNN, rebuilt from the same seed
+    torch.manual_seed(123)
+    model = nn.Sequential(nn.Conv2d(3, 8, 3, 2, 1), nn.ReLU(), nn.Conv2d(8, 16, 3, 2, 1), nn.ReLU(), nn.AdaptiveAvgPool2d(1), nn.Flatten(),
+                          nn.Linear(16, 10)).eval()
+    eps, steps, step_size, decay = g["mim_cfg"].tolist()
+    adv = OA.mim_linf(model, torch.from_numpy(g["mim_X"]), torch.from_numpy(g["mim_y"]), eps, int(steps), step_size, decay,
+                      start_u=torch.from_numpy(g["mim_u"]))
+    assert np.abs(adv.detach().numpy() - g["mim_adv"]).max() <= 1e-7
+    assert np.abs(g["mim_adv"] - g["mim_X"]).max() <= eps + 1e-6
+    # DLR
+    z, y, t = torch.from_numpy(g["dlr_z"]), torch.from_numpy(g["dlr_y"]), torch.from_numpy(g["dlr_t"])
+    assert np.array_equal(OAA.dlr_loss(z, y).numpy(), g["dlr"])
+    assert np.array_equal(OAA.dlr_loss_targeted(z, y, t).numpy(), g["dlr_targeted"])
+    # host-side product pieces (no kernels involved)
+    from robustart_b200 import autoattack as AA
+    d = AA.projection_linf(torch.from_numpy(g["proj_t"]), torch.from_numpy(g["proj_w"]), torch.from_numpy(g["proj_b"]))
+    assert np.abs(d.numpy() - g["proj"]).max() <= 1e-6
+    sq = AA.Square(None, 4 / 255, n_queries=5000, p_init=0.8)
+    assert [sq._p(int(i)) for i in g["sq_it"]] == g["sq_p"].tolist()

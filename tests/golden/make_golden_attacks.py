@@ -12,6 +12,7 @@ duration of the run -- the arithmetic is untouched.  Pinned pieces:
   * `APGDAttack.attack_single_run` (CE, DLR) and `APGDAttack_targeted.attack_single_run` (DLR-targeted), Linf, 20 iterations on
     the tiny CNN with device='cpu' (autopgd_base.py:208-448): inputs, the seed of the random start, and the four outputs
     (x_best, acc, loss_best, x_best_adv) -- what the PRODUCT's APGD control flow is checked against on CPU.
+  * `FABAttack_PT.attack_single_run` targeted (classes 2 and 3), 15 iterations, no random start (fab_base.py:84-270).
 Output: tests/golden/attack_pieces.npz."""
 import importlib.util
 import os
@@ -103,6 +104,12 @@ def main():
     xb, acc, lb, xba = at.attack_single_run(xa, ya)
     out.update(apgd_t_target=at.y_target.numpy(), apgd_t_x_best=xb.detach().numpy(), apgd_t_acc=acc.numpy(), apgd_t_loss=lb.detach().numpy(),
                apgd_t_x_best_adv=xba.detach().numpy())
+    # ---- FAB-T single runs (Linf, no random start) ----
+    import autoattack.fab_pt as fab             # noqa: E402
+    f = fab.FABAttack_PT(model, n_restarts=1, n_iter=15, eps=eps_a, norm='Linf', targeted=True, device='cpu', verbose=False)
+    for tc in (2, 3):
+        f.target_class = tc
+        out["fab_t%d" % tc] = f.attack_single_run(xa.clone(), ya.clone(), use_rand_start=False, is_targeted=True).detach().numpy()
     np.savez_compressed(os.path.join(HERE, "attack_pieces.npz"), **out)
     print("wrote attack_pieces.npz", {k: v.shape for k, v in out.items()})
 

@@ -75,3 +75,35 @@ def test_apgd_control_flow_matches_reference_run(monkeypatch, loss, key):
     assert np.abs(x_best_adv.numpy() - G["apgd_%s_x_best_adv" % key]).max() <= 1e-6
     assert np.abs(loss_best.numpy() - G["apgd_%s_loss" % key]).max() <= 1e-5
     assert (x_best_adv - x).abs().max().item() <= eps + 1e-6 and x_best_adv.min() >= 0 and x_best_adv.max() <= 1
+
+
+class _TorchFabModel:
+    def __init__(self, model):
+        self.model = model
+
+    def logits(self, x):
+        with torch.no_grad():
+            return self.model(x)
+
+    def loss_and_grad(self, x, y, kind, target=None):      # "fab-diff": -(z_y - z_t), fab_pt.py:102-117
+        assert kind == "fab-diff"
+        x = x.clone().requires_grad_(True)
+        lg = self.model(x)
+        u = torch.arange(lg.shape[0])
+        li = -(lg[u, y] - lg[u, target])
+        (g,) = torch.autograd.grad(li.sum(), x)
+        return lg.detach(), li.detach(), g
+
+
+@pytest.mark.parametrize("tc", [2, 3])
+def test_fab_targeted_single_run_matches_reference_run(tc):
+    """The product's FAB-T iteration (linearised boundary, projection_linf of x1 and x0, convex combination, overshoot,
+    backward step, best-so-far bookkeeping) against FABAttack_PT.attack_single_run (fab_base.py:84-270) on CPU."""
+    from robustart_b200 import autoattack as AA
+    eps = G["apgd_cfg"].tolist()[0]
+    x, y = torch.from_numpy(G["apgd_x"]), torch.from_numpy(G["apgd_y"])
+    out = AA.FABT(_TorchFabModel(_tiny_model()), eps, n_iter=15).single_run(x.clone(), y.clone(), tc)
+    want = G["fab_t%d" % tc]
+    assert np.abs(out.numpy() - want).max() <= 1e-6
+    moved = np.abs(want - G["apgd_x"]).reshape(8, -1).max(1)
+    assert (moved > 0).sum() >= 4 and moved[7] == 0          # the sample that starts misclassified is left alone

@@ -13,6 +13,8 @@ duration of the run -- the arithmetic is untouched.  Pinned pieces:
     the tiny CNN with device='cpu' (autopgd_base.py:208-448): inputs, the seed of the random start, and the four outputs
     (x_best, acc, loss_best, x_best_adv) -- what the PRODUCT's APGD control flow is checked against on CPU.
   * `FABAttack_PT.attack_single_run` targeted (classes 2 and 3), 15 iterations, no random start (fab_base.py:84-270).
+  * `AutoAttack.run_standard_evaluation` with apgd-ce, apgd-t, fab-t (10 iterations each, seed 0): final adversarials and the
+    robust accuracy after every stage (autoattack.py:90-211).
 Output: tests/golden/attack_pieces.npz."""
 import importlib.util
 import os
@@ -110,6 +112,30 @@ def main():
     for tc in (2, 3):
         f.target_class = tc
         out["fab_t%d" % tc] = f.attack_single_run(xa.clone(), ya.clone(), use_rand_start=False, is_targeted=True).detach().numpy()
+    # ---- the AutoAttack driver: apgd-ce -> apgd-t -> fab-t on the shrinking robust set (autoattack.py:90-211) ----
+    # (Square is left out: the product draws its proposals from its own counter-based generator.)  The reference wraps the
+    # model in NormalizeModel, so the tiny CNN sees ImageNet-normalised input here.
+    import autoattack.autoattack as refaa       # noqa: E402
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    g = torch.Generator().manual_seed(21)
+    xd = torch.rand(10, 3, 32, 32, generator=g)
+    xd = (xd * 0.3 + torch.rand(10, 3, 1, 1, generator=g) * 0.7).clamp(0, 1)
+    with torch.no_grad():
+        yd = model((xd - mean) / std).argmax(1)
+    yd[9] = (yd[9] + 1) % 10
+    out.update(aa_x=xd.numpy(), aa_y=yd.numpy(), aa_cfg=np.array([eps_a, 10, 0], np.float64))
+    stages = ['apgd-ce', 'apgd-t', 'fab-t']
+    hist = []
+    for k in range(1, 4):
+        aa = refaa.AutoAttack(model, norm='Linf', eps=eps_a, seed=0, verbose=False, version='custom', attacks_to_run=stages[:k], device='cpu')
+        aa.apgd.n_restarts, aa.apgd.n_iter = 1, 10
+        aa.apgd_targeted.n_iter, aa.apgd_targeted.n_target_classes = 10, 9
+        aa.fab.n_restarts, aa.fab.n_iter, aa.fab.n_target_classes = 1, 10, 9
+        adv = aa.run_standard_evaluation(xd.clone(), yd.clone(), bs=10)
+        with torch.no_grad():
+            hist.append(float((model((adv - mean) / std).argmax(1) == yd).float().mean()))
+    out.update(aa_adv=adv.detach().numpy(), aa_robust_after=np.array(hist))
     np.savez_compressed(os.path.join(HERE, "attack_pieces.npz"), **out)
     print("wrote attack_pieces.npz", {k: v.shape for k, v in out.items()})
 

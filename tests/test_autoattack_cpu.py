@@ -107,3 +107,47 @@ def test_fab_targeted_single_run_matches_reference_run(tc):
     assert np.abs(out.numpy() - want).max() <= 1e-6
     moved = np.abs(want - G["apgd_x"]).reshape(8, -1).max(1)
     assert (moved > 0).sum() >= 4 and moved[7] == 0          # the sample that starts misclassified is left alone
+
+
+def test_autoattack_driver_matches_reference_run(monkeypatch):
+    """The product's AutoAttack driver (robust-set bookkeeping, per-attack seeding, APGD-CE -> APGD-T over 9 target classes ->
+    FAB-T over 9 target classes) against the reference's run_standard_evaluation on CPU: same adversarials, same robust
+    accuracy after every stage (autoattack.py:90-211; autopgd_base.py:450-529,610-690; fab_base.py:274-334)."""
+    from oracle import autoattack as OAA
+    from robustart_b200 import autoattack as AA
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    net = _tiny_model()
+
+    class TorchNormalizedModel:                  # stands in for autoattack._Model (NormalizeModel + kernels) in this test only
+        def __init__(self, _):
+            self.forwards = self.backwards = 0
+
+        def _f(self, x):
+            return net((x - mean) / std)
+
+        def logits(self, x):
+            with torch.no_grad():
+                return self._f(x)
+
+        def loss_and_grad(self, x, y, kind, target=None):
+            x = x.clone().requires_grad_(True)
+            lg = self._f(x)
+            u = torch.arange(lg.shape[0])
+            li = (F.cross_entropy(lg, y, reduction="none") if kind == "ce" else OAA.dlr_loss(lg, y) if kind == "dlr"
+                  else OAA.dlr_loss_targeted(lg, y, target) if kind == "dlr-targeted" else -(lg[u, y] - lg[u, target]))
+            (g,) = torch.autograd.grad(li.sum(), x)
+            return lg.detach(), li.detach(), g
+
+    monkeypatch.setattr(AA, "_apgd_step_", _step)
+    monkeypatch.setattr(AA, "_masked_rows_", _masked)
+    monkeypatch.setattr(AA, "_Model", TorchNormalizedModel)
+    eps, n_iter, seed = G["aa_cfg"].tolist()
+    x, y = torch.from_numpy(G["aa_x"]), torch.from_numpy(G["aa_y"])
+    aa = AA.AutoAttack(net, norm="Linf", eps=eps, seed=int(seed), verbose=False, attacks_to_run=["apgd-ce", "apgd-t", "fab-t"], n_iter=int(n_iter))
+    adv = aa.run_standard_evaluation(x.clone(), y.clone(), bs=10)
+    assert np.abs(adv.numpy() - G["aa_adv"]).max() <= 1e-6
+    assert [h[0] for h in aa.history] == ["clean", "apgd-ce", "apgd-t", "fab-t"]
+    assert np.allclose([h[1] for h in aa.history[1:]], G["aa_robust_after"], atol=1e-6)
+    assert G["aa_robust_after"][0] > G["aa_robust_after"][1]          # the golden exercises the shrinking robust set
+    assert (adv - x).abs().max().item() <= eps + 1e-6

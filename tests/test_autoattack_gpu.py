@@ -1,7 +1,8 @@
 """AutoAttack pieces: device kernels vs torch restatements of the vendored reference formulas
 (autopgd_base.py:198-204,332-338,599-604; square.py:246-254; fab_projections.py:7-59) and end-to-end
-invariants of the 'standard' Linf pipeline.  PARITY UNPINNED against the reference run itself: its vendored code
-hard-requires CUDA (autoattack.py:18-19) and /root/reference is not on the GPU box."""
+invariants of the 'standard' Linf pipeline.  The control flow around these kernels (APGD, FAB-T, the driver) is pinned to
+runs of the reference's own vendored code in tests/test_autoattack_cpu.py (goldens from tests/golden/make_golden_attacks.py);
+here the kernels are checked against the same torch statements that stand in for them there."""
 import pytest
 import torch
 

@@ -9,6 +9,8 @@ duration of the run -- the arithmetic is untouched.  Pinned pieces:
   * `APGDAttack.dlr_loss`, `dlr_loss_targeted`   autopgd_base.py:198-204,599-604
   * `projection_linf`               fab_projections.py:7-59
   * `SquareAttack.p_selection`      square.py:192-219
+  * `pgd_linf_attack`               prototype/prototype/solver/adv_cls_solver_train_pgd_new.py:67-105 (the reference's own
+    PGD-Linf loop: the second anchor of the foolbox restatement)
   * `APGDAttack.attack_single_run` (CE, DLR) and `APGDAttack_targeted.attack_single_run` (DLR-targeted), Linf, 20 iterations on
     the tiny CNN with device='cpu' (autopgd_base.py:208-448): inputs, the seed of the random start, and the four outputs
     (x_best, acc, loss_best, x_best_adv) -- what the PRODUCT's APGD control flow is checked against on CPU.
@@ -78,6 +80,23 @@ def main():
     s = types.SimpleNamespace(rescale_schedule=False, n_queries=5000, p_init=0.8)
     its = np.array([0, 1, 10, 11, 50, 51, 200, 201, 500, 501, 1000, 1001, 2000, 2001, 4000, 4001, 6000, 6001, 8000, 8001, 9999])
     out.update(sq_it=its, sq_p=np.array([sq.SquareAttack.p_selection(s, int(i)) for i in its]))
+    # ---- the reference's in-repo PGD-Linf loop (adv_cls_solver_train_pgd_new.py:67-105), cut out by AST position ----
+    import ast
+    import textwrap
+    import torch.nn.functional as F
+    src = open("/root/reference/prototype/prototype/solver/adv_cls_solver_train_pgd_new.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "pgd_linf_attack")
+    ns = {"torch": torch, "F": F}
+    exec(textwrap.dedent("\n".join(src.split("\n")[fn.lineno - 1:fn.end_lineno])), ns)
+    g = torch.Generator().manual_seed(31)
+    xp = torch.rand(4, 3, 32, 32, generator=g)
+    yp = torch.tensor([0, 4, 2, 9])
+    eps_p, rel, steps_p = 8 / 255, 3 / 40, 10
+    torch.manual_seed(99)
+    advp = ns["pgd_linf_attack"](model, xp, yp, eps=eps_p, alpha=rel * eps_p, steps=steps_p, random_start=True)
+    torch.manual_seed(99)
+    up = torch.empty_like(xp).uniform_(0, 1)
+    out.update(pgd_x=xp.numpy(), pgd_y=yp.numpy(), pgd_u=up.numpy(), pgd_adv=advp.numpy(), pgd_cfg=np.array([eps_p, rel, steps_p], np.float64))
     # ---- APGD single runs (Linf) ----
     for p in model.parameters():
         p.requires_grad_(False)

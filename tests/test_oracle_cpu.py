@@ -156,6 +156,13 @@ def test_attack_pieces_match_reference_code():
                       start_u=torch.from_numpy(g["mim_u"]))
     assert np.abs(adv.detach().numpy() - g["mim_adv"]).max() <= 1e-7
     assert np.abs(g["mim_adv"] - g["mim_X"]).max() <= eps + 1e-6
+    # PGD-Linf: the foolbox restatement against the reference's in-repo loop (adv_cls_solver_train_pgd_new.py:67-105).  The two
+    # project differently in floating point (x0 + clip(x - x0) vs max(min(x, x0 + eps), x0 - eps)): 1-2 ulp apart at most
+    eps_p, rel, steps_p = g["pgd_cfg"].tolist()
+    advp = OA.pgd_linf(model, torch.from_numpy(g["pgd_x"]), torch.from_numpy(g["pgd_y"]), eps_p, rel, int(steps_p),
+                       start_u=torch.from_numpy(g["pgd_u"]))
+    assert np.abs(advp.detach().numpy() - g["pgd_adv"]).max() <= 2e-7
+    assert np.abs(g["pgd_adv"] - g["pgd_x"]).max() > 0.5 * eps_p
     # DLR
     z, y, t = torch.from_numpy(g["dlr_z"]), torch.from_numpy(g["dlr_y"]), torch.from_numpy(g["dlr_t"])
     assert np.array_equal(OAA.dlr_loss(z, y).numpy(), g["dlr"])

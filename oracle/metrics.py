@@ -10,16 +10,12 @@ import torch
 
 
 def accuracy(output, target, topk=(1,)):
-    maxk = max(topk)
-    batch_size = target.size(0)
-    _, pred = output.topk(maxk, 1, True, True)
-    pred = pred.t()
-    correct = pred.eq(target.reshape(1, -1).expand_as(pred))
-    res = []
-    for k in topk:
-        correct_k = correct[:k].reshape(-1).float().sum(0, keepdim=True)
-        res.append(correct_k.mul_(100.0 / batch_size))
-    return res
+    """precision@k in percent, one 1-element float tensor per k (misc.py:441-455): a sample counts for k when its label is
+    among the first k indices torch.topk returns (largest, sorted) -- ties are resolved by torch.topk, as in the reference."""
+    order = output.topk(max(topk), dim=1, largest=True, sorted=True).indices
+    hit = order == target.reshape(-1, 1)
+    n = target.shape[0]
+    return [hit[:, :k].any(dim=1).float().sum().reshape(1) * (100.0 / n) for k in topk]
 
 
 def topk_hits(output, target, ks=(1, 5)):

@@ -173,3 +173,31 @@ def test_attack_pieces_match_reference_code():
     assert np.abs(d.numpy() - g["proj"]).max() <= 1e-6
     sq = AA.Square(None, 4 / 255, n_queries=5000, p_init=0.8)
     assert [sq._p(int(i)) for i in g["sq_it"]] == g["sq_p"].tolist()
+
+
+def test_eval_reduction_matches_reference_code():
+    """Sampler shards and accuracy() against goldens produced by executing the reference's own DistributedSampler
+    (data/sampler.py:8-52, round_up=False) and accuracy (utils/misc.py:441-455) -- tests/golden/make_golden_metrics.py.
+    Checked: the oracle restatements AND the product's host-side solver.shard_indices."""
+    import hashlib
+    import json
+    import os
+    import torch
+    from oracle import metrics as OM
+    from robustart_b200 import solver as S
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "metrics_reference.json")))
+    for key, ranks in g["sampler"].items():
+        n, w = (int(v) for v in key.split("/"))
+        for r, want in enumerate(ranks):
+            got_o, got_p = OM.sampler_indices(n, w, r), S.shard_indices(n, w, r).tolist()
+            if isinstance(want, dict):
+                for got in (got_o, got_p):
+                    assert len(got) == want["len"] and hashlib.sha256(np.asarray(got, np.int32).tobytes()).hexdigest() == want["sha256"]
+            else:
+                assert got_o == want and got_p == want, (key, r)
+    a = g["accuracy"]
+    logits, target = torch.tensor(a["logits"]), torch.tensor(a["target"])
+    top1, top5 = OM.accuracy(logits, target, topk=(1, 5))
+    assert float(top1) == a["top1"] and float(top5) == a["top5"]
+    h1, h5 = OM.topk_hits(logits, target, (1, 5))
+    assert abs(100.0 * h1 / 40 - a["top1"]) < 1e-4 and abs(100.0 * h5 / 40 - a["top5"]) < 1e-4

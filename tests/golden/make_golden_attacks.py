@@ -15,6 +15,7 @@ duration of the run -- the arithmetic is untouched.  Pinned pieces:
     the tiny CNN with device='cpu' (autopgd_base.py:208-448): inputs, the seed of the random start, and the four outputs
     (x_best, acc, loss_best, x_best_adv) -- what the PRODUCT's APGD control flow is checked against on CPU.
   * `FABAttack_PT.attack_single_run` targeted (classes 2 and 3), 15 iterations, no random start (fab_base.py:84-270).
+  * `SquareAttack.perturb` (Linf, 300 queries, seed 0) on the same inputs (square.py:221-294).
   * `AutoAttack.run_standard_evaluation` with apgd-ce, apgd-t, fab-t (10 iterations each, seed 0): final adversarials and the
     robust accuracy after every stage (autoattack.py:90-211).
 Output: tests/golden/attack_pieces.npz."""
@@ -131,8 +132,13 @@ def main():
     for tc in (2, 3):
         f.target_class = tc
         out["fab_t%d" % tc] = f.attack_single_run(xa.clone(), ya.clone(), use_rand_start=False, is_targeted=True).detach().numpy()
+    # ---- Square (Linf): 300 queries at 16/255, seed 0 (square.py:221-294 + perturb) ----
+    import autoattack.square as refsq           # noqa: E402
+    sq_att = refsq.SquareAttack(model, p_init=.8, n_queries=300, eps=16 / 255, norm='Linf', n_restarts=1, seed=0, verbose=False,
+                                device='cpu', resc_schedule=False)
+    out.update(square_adv=sq_att.perturb(xa.clone(), ya.clone()).detach().numpy(), square_cfg=np.array([16 / 255, 300, 0], np.float64))
     # ---- the AutoAttack driver: apgd-ce -> apgd-t -> fab-t on the shrinking robust set (autoattack.py:90-211) ----
-    # (Square is left out: the product draws its proposals from its own counter-based generator.)  The reference wraps the
+    # The reference wraps the
     # model in NormalizeModel, so the tiny CNN sees ImageNet-normalised input here.
     import autoattack.autoattack as refaa       # noqa: E402
     mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)

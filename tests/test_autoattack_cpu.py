@@ -151,3 +151,31 @@ def test_autoattack_driver_matches_reference_run(monkeypatch):
     assert np.allclose([h[1] for h in aa.history[1:]], G["aa_robust_after"], atol=1e-6)
     assert G["aa_robust_after"][0] > G["aa_robust_after"][1]          # the golden exercises the shrinking robust set
     assert (adv - x).abs().max().item() <= eps + 1e-6
+
+
+def test_square_attack_matches_reference_run(monkeypatch):
+    """The product's Square attack (stripe initialisation, p schedule, window draws from the torch generator in the reference's
+    order, acceptance rule, active-set bookkeeping) against SquareAttack.perturb (square.py:221-294) on CPU with the same seed.
+    The proposal kernel is replaced -- in this test only -- by the torch statements of square.py:246-254 acting on the
+    buffers the product passes."""
+    import ctypes as C
+    from robustart_b200 import autoattack as AA
+
+    class FakeLib:
+        def b200r_square_propose_linf(self, xb_p, xc_p, xn_p, n, c, h, w, vh, vw, s, signs, eps, stream):
+            view = lambda p: torch.frombuffer((C.c_float * (n * c * h * w)).from_address(p), dtype=torch.float32).view(n, c, h, w)
+            xb, xc, xn = view(xb_p), view(xc_p), view(xn_p)
+            delta = torch.zeros(c, h, w)
+            delta[:, vh:vh + s, vw:vw + s] = 2. * eps * torch.tensor(list(signs)).view(c, 1, 1)
+            xn.copy_(torch.clamp(torch.min(torch.max(xb + delta, xc - eps), xc + eps), 0., 1.))
+            return 0
+
+    monkeypatch.setattr(AA._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(AA, "_stream", lambda: None)
+    monkeypatch.setattr(AA, "_masked_rows_", _masked)
+    eps, n_queries, seed = G["square_cfg"].tolist()
+    x, y = torch.from_numpy(G["apgd_x"]), torch.from_numpy(G["apgd_y"])
+    out = AA.Square(_TorchFabModel(_tiny_model()), eps, n_queries=int(n_queries)).perturb(x.clone(), y.clone(), int(seed))
+    assert np.abs(out.numpy() - G["square_adv"]).max() <= 1e-7
+    moved = np.abs(G["square_adv"] - G["apgd_x"]).reshape(8, -1).max(1)
+    assert 0 < (moved > 0).sum() < 7                           # some samples fooled, some robust within the budget

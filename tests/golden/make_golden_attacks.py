@@ -16,8 +16,8 @@ duration of the run -- the arithmetic is untouched.  Pinned pieces:
     (x_best, acc, loss_best, x_best_adv) -- what the PRODUCT's APGD control flow is checked against on CPU.
   * `FABAttack_PT.attack_single_run` targeted (classes 2 and 3), 15 iterations, no random start (fab_base.py:84-270).
   * `SquareAttack.perturb` (Linf, 300 queries, seed 0) on the same inputs (square.py:221-294).
-  * `AutoAttack.run_standard_evaluation` with apgd-ce, apgd-t, fab-t (10 iterations each, seed 0): final adversarials and the
-    robust accuracy after every stage (autoattack.py:90-211).
+  * `AutoAttack.run_standard_evaluation` with apgd-ce, apgd-t, fab-t (10 iterations each) and square (200 queries), seed 0: final
+    adversarials and the robust accuracy after every stage (autoattack.py:90-211).
 Output: tests/golden/attack_pieces.npz."""
 import importlib.util
 import os
@@ -150,13 +150,14 @@ def main():
         yd = model((xd - mean) / std).argmax(1)
     yd[9] = (yd[9] + 1) % 10
     out.update(aa_x=xd.numpy(), aa_y=yd.numpy(), aa_cfg=np.array([eps_a, 10, 0], np.float64))
-    stages = ['apgd-ce', 'apgd-t', 'fab-t']
+    stages = ['apgd-ce', 'apgd-t', 'fab-t', 'square']
     hist = []
-    for k in range(1, 4):
+    for k in range(1, 5):
         aa = refaa.AutoAttack(model, norm='Linf', eps=eps_a, seed=0, verbose=False, version='custom', attacks_to_run=stages[:k], device='cpu')
         aa.apgd.n_restarts, aa.apgd.n_iter = 1, 10
         aa.apgd_targeted.n_iter, aa.apgd_targeted.n_target_classes = 10, 9
         aa.fab.n_restarts, aa.fab.n_iter, aa.fab.n_target_classes = 1, 10, 9
+        aa.square.n_queries = 200
         adv = aa.run_standard_evaluation(xd.clone(), yd.clone(), bs=10)
         with torch.no_grad():
             hist.append(float((model((adv - mean) / std).argmax(1) == yd).float().mean()))

@@ -39,6 +39,17 @@ def _masked(dst, src, mask):                               # b200r_masked_rows_c
     dst[mask] = src[mask]
 
 
+class _FakeLib:                                            # b200r_square_propose_linf: square.py:246-254 on the product's buffers
+    def b200r_square_propose_linf(self, xb_p, xc_p, xn_p, n, c, h, w, vh, vw, s, signs, eps, stream):
+        import ctypes as C
+        view = lambda p: torch.frombuffer((C.c_float * (n * c * h * w)).from_address(p), dtype=torch.float32).view(n, c, h, w)
+        xb, xc, xn = view(xb_p), view(xc_p), view(xn_p)
+        delta = torch.zeros(c, h, w)
+        delta[:, vh:vh + s, vw:vw + s] = 2. * eps * torch.tensor(list(signs)).view(c, 1, 1)
+        xn.copy_(torch.clamp(torch.min(torch.max(xb + delta, xc - eps), xc + eps), 0., 1.))
+        return 0
+
+
 class _TorchModel:                                         # autoattack._Model.loss_and_grad with autograd instead of the kernels
     def __init__(self, model):
         self.model = model
@@ -111,7 +122,7 @@ def test_fab_targeted_single_run_matches_reference_run(tc):
 
 def test_autoattack_driver_matches_reference_run(monkeypatch):
     """The product's AutoAttack driver (robust-set bookkeeping, per-attack seeding, APGD-CE -> APGD-T over 9 target classes ->
-    FAB-T over 9 target classes) against the reference's run_standard_evaluation on CPU: same adversarials, same robust
+    FAB-T over 9 target classes -> Square) against the reference's run_standard_evaluation on CPU: same adversarials, same robust
     accuracy after every stage (autoattack.py:90-211; autopgd_base.py:450-529,610-690; fab_base.py:274-334)."""
     from oracle import autoattack as OAA
     from robustart_b200 import autoattack as AA
@@ -142,12 +153,14 @@ def test_autoattack_driver_matches_reference_run(monkeypatch):
     monkeypatch.setattr(AA, "_apgd_step_", _step)
     monkeypatch.setattr(AA, "_masked_rows_", _masked)
     monkeypatch.setattr(AA, "_Model", TorchNormalizedModel)
+    monkeypatch.setattr(AA._lib, "load", lambda: _FakeLib())
+    monkeypatch.setattr(AA, "_stream", lambda: None)
     eps, n_iter, seed = G["aa_cfg"].tolist()
     x, y = torch.from_numpy(G["aa_x"]), torch.from_numpy(G["aa_y"])
-    aa = AA.AutoAttack(net, norm="Linf", eps=eps, seed=int(seed), verbose=False, attacks_to_run=["apgd-ce", "apgd-t", "fab-t"], n_iter=int(n_iter))
+    aa = AA.AutoAttack(net, norm="Linf", eps=eps, seed=int(seed), verbose=False, n_iter=int(n_iter), n_queries=200)   # the standard four
     adv = aa.run_standard_evaluation(x.clone(), y.clone(), bs=10)
     assert np.abs(adv.numpy() - G["aa_adv"]).max() <= 1e-6
-    assert [h[0] for h in aa.history] == ["clean", "apgd-ce", "apgd-t", "fab-t"]
+    assert [h[0] for h in aa.history] == ["clean", "apgd-ce", "apgd-t", "fab-t", "square"]
     assert np.allclose([h[1] for h in aa.history[1:]], G["aa_robust_after"], atol=1e-6)
     assert G["aa_robust_after"][0] > G["aa_robust_after"][1]          # the golden exercises the shrinking robust set
     assert (adv - x).abs().max().item() <= eps + 1e-6
@@ -158,19 +171,8 @@ def test_square_attack_matches_reference_run(monkeypatch):
     order, acceptance rule, active-set bookkeeping) against SquareAttack.perturb (square.py:221-294) on CPU with the same seed.
     The proposal kernel is replaced -- in this test only -- by the torch statements of square.py:246-254 acting on the
     buffers the product passes."""
-    import ctypes as C
     from robustart_b200 import autoattack as AA
-
-    class FakeLib:
-        def b200r_square_propose_linf(self, xb_p, xc_p, xn_p, n, c, h, w, vh, vw, s, signs, eps, stream):
-            view = lambda p: torch.frombuffer((C.c_float * (n * c * h * w)).from_address(p), dtype=torch.float32).view(n, c, h, w)
-            xb, xc, xn = view(xb_p), view(xc_p), view(xn_p)
-            delta = torch.zeros(c, h, w)
-            delta[:, vh:vh + s, vw:vw + s] = 2. * eps * torch.tensor(list(signs)).view(c, 1, 1)
-            xn.copy_(torch.clamp(torch.min(torch.max(xb + delta, xc - eps), xc + eps), 0., 1.))
-            return 0
-
-    monkeypatch.setattr(AA._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(AA._lib, "load", lambda: _FakeLib())
     monkeypatch.setattr(AA, "_stream", lambda: None)
     monkeypatch.setattr(AA, "_masked_rows_", _masked)
     eps, n_queries, seed = G["square_cfg"].tolist()

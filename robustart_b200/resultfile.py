@@ -116,3 +116,38 @@ def evaluate(res_file: str, topk: Iterable[int] = (1, 5)) -> dict:
     _, idx = pred.topk(max(topk), 1, True, True)
     correct = idx.t().eq(label.reshape(1, -1).expand_as(idx.t()))
     return {"top%d" % k: correct[:k].reshape(-1).float().sum(0, keepdim=True).mul_(100.0 / num).item() for k in topk}
+
+
+IMAGENET_C_GROUPS = {
+    "noise": ["gaussian_noise", "shot_noise", "impulse_noise"],
+    "blur": ["defocus_blur", "glass_blur", "motion_blur", "zoom_blur"],
+    "weather": ["snow", "frost", "fog", "brightness"],
+    "digital": ["contrast", "elastic_transform", "pixelate", "jpeg_compression"],
+    "extra": ["speckle_noise", "spatter", "gaussian_blur", "saturate"],
+}
+
+
+def merge_imagenet_c_metrics(result_path: str, severities=(1, 2, 3, 4, 5)) -> dict:
+    """ImageNetCDataset.merge_eval_res (datasets/imagnetc.py:166-218) on a directory of `{group}-{type}-{sev}-metric` files
+    (what ImageNetCEvaluator.eval and EvalSolver.evaluate_imagenet_c write): mean top-1 ERROR over the severities per
+    corruption type, `all_with_extra` / `all_without_extra` over the types, dumped to `robust.json`.  Same numbers as the
+    reference (np.average of the same lists in the same order); plain floats instead of numpy scalars in the JSON."""
+    import numpy as np
+    all_data = {"all": {"all_with_extra": {}, "all_without_extra": {}}}
+    avg, avg_wo_extra = [], []
+    for group, types in IMAGENET_C_GROUPS.items():
+        all_data[group] = {}
+        for noise_type in types:
+            lst = []
+            for i in severities:
+                with open(os.path.join(result_path, "%s-%s-%d-metric" % (group, noise_type, i))) as f:
+                    lst.append(100 - float(json.load(f)["top1"]))
+            all_data[group][noise_type] = float(np.average(lst))
+            if group != "extra":
+                avg_wo_extra.append(np.average(lst))
+            avg.append(np.average(lst))
+    all_data["all"]["all_with_extra"] = float(np.average(avg))
+    all_data["all"]["all_without_extra"] = float(np.average(avg_wo_extra))
+    with open(os.path.join(result_path, "robust.json"), "w") as f:
+        json.dump(all_data, f)
+    return all_data

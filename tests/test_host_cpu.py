@@ -162,3 +162,30 @@ def test_file_dataset_host_logic(tmp_path, monkeypatch):
     want = pil_transform(torch.from_numpy(np.array(Image.open(tmp_path / "val" / "img3.png").convert("RGB")))[None], 64, 56)[0]
     assert torch.equal(imgs[0], want)
     assert S.FileImageNet(str(tmp_path / "val"), str(tmp_path / "meta.txt"), 56, "cpu", limit=3).n == 3
+
+
+def test_robust_json_matches_reference_merge_eval_res(tmp_path):
+    """resultfile.merge_imagenet_c_metrics and the arithmetic EvalSolver.evaluate_imagenet_c uses (mean top-1 error per type, means
+    over types) against robust.json written by the reference's own ImageNetCDataset.merge_eval_res
+    (tests/golden/make_golden_robust_json.py): same keys, same numbers."""
+    import json
+    import os
+    from robustart_b200 import resultfile, solver as S
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "robust_json.json")))
+    for name, m in g["metrics"].items():
+        json.dump(m, open(tmp_path / name, "w"))
+    got = resultfile.merge_imagenet_c_metrics(str(tmp_path))
+    assert json.load(open(tmp_path / "robust.json")) == got
+    want = g["robust"]
+    assert list(got) == list(want) and all(list(got[k]) == list(want[k]) for k in want)
+    for k in want:
+        for t in want[k]:
+            assert abs(got[k][t] - want[k][t]) < 1e-9, (k, t)
+    assert resultfile.IMAGENET_C_GROUPS == S.EvalSolver.IMAGENET_C_GROUPS
+    # the solver's in-loop formula: sum(errs) / len(errs) per type, then the same over types
+    errs = {t: [100.0 - g["metrics"]["%s-%s-%d-metric" % (grp, t, s)]["top1"] for s in range(1, 6)]
+            for grp, ts in S.EvalSolver.IMAGENET_C_GROUPS.items() for t in ts}
+    per_type = {t: sum(e) / len(e) for t, e in errs.items()}
+    assert abs(sum(per_type.values()) / len(per_type) - want["all"]["all_with_extra"]) < 1e-9
+    wo = [per_type[t] for grp, ts in S.EvalSolver.IMAGENET_C_GROUPS.items() if grp != "extra" for t in ts]
+    assert abs(sum(wo) / len(wo) - want["all"]["all_without_extra"]) < 1e-9

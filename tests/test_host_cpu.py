@@ -11,6 +11,22 @@ def test_registry_matches_reference_surface():
     assert default_config['mim_linf']['step_size'] == 0.002 and default_config['imagenet-c']['severity'] == 1
 
 
+def test_plugin_surface_matches_reference_sources():
+    """noise_list / default_config / function_dict keys, the corruption id table and the model name table against
+    tests/golden/plugin_surface.json, extracted from the reference's SOURCES by tests/golden/make_golden_surface.py
+    (add_noise_utils.py:7-18,41-50; imagenet_c/__init__.py:5-8; utils/model_config.py)."""
+    import json
+    import os
+    from RobustART.noise.utils.add_noise_utils import noise_list, default_config, function_dict
+    from robustart_b200 import ops, solver as S
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "plugin_surface.json")))
+    assert noise_list == g["noise_list"] and list(function_dict) == g["function_dict_keys"]
+    assert {k: dict(v) for k, v in default_config.items()} == g["default_config"]
+    assert list(ops.CORRUPTION_NAMES) == g["corruption_tuple"]            # ids are positions in corruption_tuple
+    for name, cfg in S.model_name_dict.items():
+        assert g["model_name_dict_types"][name] == cfg["type"], name
+
+
 def test_addnoise_config_rules(capsys):
     from RobustART.noise import AddNoise
     with pytest.raises(AssertionError):

@@ -438,8 +438,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-pgd", action="store_true", help="skip the PGD-loop side report")
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="f16", choices=["f16", "bf16x3"],

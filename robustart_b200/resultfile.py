@@ -27,18 +27,16 @@ import numpy as np
 def round8(scores: np.ndarray) -> np.ndarray:
     """float64 array equal elementwise to float("%.8f" % s) for float32/float64 input scores."""
     s = np.asarray(scores, dtype=np.float64)
+    shape = s.shape
+    s = s.reshape(-1)
     x = s * 1e8
     q = np.rint(x)
+    out = q / 1e8
     # the product carries <= 1 ulp of rounding error: re-do everything within 1e-4 of a tie with the exact decimal formatting
     frac = np.abs(x - np.floor(x) - 0.5)
-    near = np.nonzero((frac < 1e-4) | ~np.isfinite(x))
-    out = q / 1e8
-    if near[0].size:
-        flat_idx = np.ravel_multi_index(near, s.shape) if s.ndim else np.array([0])
-        of, sf = out.reshape(-1), s.reshape(-1)
-        for i in flat_idx:
-            of[i] = float("%.8f" % sf[i])
-    return out
+    for i in np.nonzero((frac < 1e-4) | ~np.isfinite(x))[0]:
+        out[i] = float("%.8f" % s[i])
+    return out.reshape(shape)
 
 
 def format_lines(prediction, label, score, filename: Optional[Sequence[str]] = None, image_id: Optional[Sequence[int]] = None) -> str:

@@ -205,3 +205,22 @@ def test_robust_json_matches_reference_merge_eval_res(tmp_path):
     assert abs(sum(per_type.values()) / len(per_type) - want["all"]["all_with_extra"]) < 1e-9
     wo = [per_type[t] for grp, ts in S.EvalSolver.IMAGENET_C_GROUPS.items() if grp != "extra" for t in ts]
     assert abs(sum(wo) / len(wo) - want["all"]["all_without_extra"]) < 1e-9
+
+
+def test_round8_property():
+    """resultfile.round8 == float("%.8f" % s) elementwise (the reference's score formatting, imagenet_dataset.py:262) on random
+    float32 bit patterns in [0, 1], on values sitting exactly on / next to the 9th-decimal ties, and on softmax-like tails."""
+    from robustart_b200 import resultfile as R
+    rs = np.random.RandomState(1)
+    bits = rs.randint(0, 0x3F800000, size=200000, dtype=np.int64).astype(np.uint32)        # every float32 in [0, 1)
+    vals = [bits.view(np.float32)]
+    ties = (np.arange(1, 4000, dtype=np.float64) * 2 + 1) * 0.5e-8                          # k + 0.5 in units of 1e-8
+    vals.append(ties.astype(np.float32))
+    vals.append(np.nextafter(ties.astype(np.float32), np.float32(1)))
+    vals.append(np.nextafter(ties.astype(np.float32), np.float32(0)))
+    vals.append(np.exp(rs.uniform(-40, 0, 50000)).astype(np.float32))
+    v = np.concatenate(vals)
+    got = R.round8(v)
+    want = np.array([float("%.8f" % s) for s in v.tolist()])
+    assert np.array_equal(got, want)
+    assert R.round8(np.float32(0.5)).item() == 0.5 and R.round8(np.array([[1.0, 0.0]], np.float32)).tolist() == [[1.0, 0.0]]

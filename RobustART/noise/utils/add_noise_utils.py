@@ -84,6 +84,33 @@ def add_noise_for_imagenet_c(image, severity=1, corruption_name=None, corruption
     return image
 
 
+def random_resized_crop_params(height, width, scale=(0.08, 1.0), ratio=(3. / 4., 4. / 3.)):
+    """ImageTransfer.get_params (imagenet_s_gen.py:199-239): (i, j, h, w) of a random-sized crop, ten attempts drawn from
+    Python's `random` in the reference's order (uniform area, uniform log-ratio, randint i, randint j), then the centre
+    fallback at the nearest admissible aspect ratio."""
+    import math
+    import random
+    area = height * width
+    for _ in range(10):
+        target_area = random.uniform(*scale) * area
+        log_ratio = (math.log(ratio[0]), math.log(ratio[1]))
+        aspect_ratio = math.exp(random.uniform(*log_ratio))
+        w = int(round(math.sqrt(target_area * aspect_ratio)))
+        h = int(round(math.sqrt(target_area / aspect_ratio)))
+        if 0 < w <= width and 0 < h <= height:
+            return random.randint(0, height - h), random.randint(0, width - w), h, w
+    in_ratio = float(width) / float(height)
+    if in_ratio < min(ratio):
+        w = width
+        h = int(round(w / min(ratio)))
+    elif in_ratio > max(ratio):
+        h = height
+        w = int(round(h * max(ratio)))
+    else:
+        w, h = width, height
+    return (height - h) // 2, (width - w) // 2, h, w
+
+
 _PIL_RESIZE_TYPES = {'pil-bilinear': 'bilinear', 'pil-nearest': 'nearest', 'pil-box': 'box', 'pil-hamming': 'hamming',
                      'pil-cubic': 'bicubic', 'pil-lanczos': 'lanczos'}
 
@@ -93,17 +120,35 @@ def add_noise_for_imagenet_s(image, decoder_type='pil', resize_type='pil-bilinea
     resize types, transform 'val': decode on the host (file parsing, as the reference), then Image.resize to
     (size*8/7, size*8/7) and the centre crop as ONE bit-exact resize kernel launch (b200r_resize_u8).  `image` is a file
     path (the reference's contract) or an already decoded uint8 [h, w, 3] / [n, h, w, 3] array or CUDA tensor.
-    The OpenCV / ffmpeg decoders, the opencv-* resize types and the random-crop 'train' transform are not implemented."""
+    transform 'train' = the reference's random resized crop (parameters from Python's `random`) + Image.resize to (size, size).
+    The OpenCV / ffmpeg decoders and the opencv-* resize types are not implemented."""
     if decoder_type != 'pil':
         raise NotImplementedError("imagenet-s decoder_type=%r: only the PIL decoder is implemented" % decoder_type)
     if resize_type not in _PIL_RESIZE_TYPES:
         raise NotImplementedError("imagenet-s resize_type=%r: only the pil-* resize types are implemented" % resize_type)
-    if transform_type != 'val':
-        raise NotImplementedError("imagenet-s transform_type=%r: only 'val' (resize + centre crop) is implemented" % transform_type)
+    if transform_type not in ('val', 'train'):
+        raise NotImplementedError("imagenet-s transform_type=%r: 'val' (resize + centre crop) and 'train' (random resized crop)" % transform_type)
     if isinstance(image, str):
         from PIL import Image
         with Image.open(image) as im:
             image = np.array(im.convert('RGB'))
+    if transform_type == 'train':
+        # imagenet_s_gen.py:120-129: crop the box get_params draws from Python's `random`, then Image.resize to (size, size)
+        single = image.ndim == 3 if not isinstance(image, torch.Tensor) else image.dim() == 3
+        batch = image if not single else image[None]
+        outs = []
+        for img in batch:
+            y0, x0, h, w = random_resized_crop_params(int(img.shape[0]), int(img.shape[1]))
+            crop = img[y0:y0 + h, x0:x0 + w]
+            d = (crop if isinstance(crop, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(crop)).to(
+                torch.device('cuda', torch.cuda.current_device())))
+            if not d.is_cuda:
+                raise TypeError("torch input must live on the GPU")
+            outs.append(_ops.resize_u8(d.contiguous()[None], (size, size), _PIL_RESIZE_TYPES[resize_type])[0])
+        out = torch.stack(outs)
+        if not isinstance(image, torch.Tensor):
+            out = out.cpu().numpy()
+        return out[0] if single else out
     first = int(size * 8 / 7)
     i = int(round((first - size) / 2.))
     if isinstance(image, torch.Tensor):

@@ -25,6 +25,14 @@ def test_plugin_surface_matches_reference_sources():
     assert list(ops.CORRUPTION_NAMES) == g["corruption_tuple"]            # ids are positions in corruption_tuple
     for name, cfg in S.model_name_dict.items():
         assert g["model_name_dict_types"][name] == cfg["type"], name
+    # ImageNet-S 'train' transform: the random resized crop box (imagenet_s_gen.py:199-239), same draws from `random`
+    import random
+    from RobustART.noise.utils.add_noise_utils import random_resized_crop_params
+    gp = g["get_params"]
+    random.seed(gp["seed"])
+    got = [list(random_resized_crop_params(h, w)) for h, w in gp["shapes"]]
+    assert got == gp["params"]
+    assert any(p[2] == h and p[3] != w or p[3] == w and p[2] != h for p, (h, w) in zip(gp["params"], gp["shapes"]))   # fallback branch hit
 
 
 def test_addnoise_config_rules(capsys):

@@ -64,6 +64,12 @@ def test_config_and_cli_surface(tmp_path):
     cfg = S.parse_config(os.path.join(os.path.dirname(os.path.dirname(__file__)), "exprs", "b200", "resnet50_eval.yaml"))
     assert cfg.model.type == "resnet50_official" and cfg.data.test.evaluator.kwargs.topk == [1, 5]
     assert S.model_name_dict["resnet50"]["type"] == "resnet50_official"
+    import glob
+    cfgs = sorted(glob.glob(os.path.join(os.path.dirname(os.path.dirname(__file__)), "exprs", "b200", "config*.yaml")))
+    assert len(cfgs) == 5                          # one per BASELINE config
+    for p in cfgs:
+        c = S.parse_config(p)
+        assert c.data.read_from == "fake" and c.model.type in [v["type"] for v in S.model_name_dict.values()]
     with pytest.raises(SystemExit):
         adv.main(["--config", "x.yaml"])          # the reference's required flags are required here too
     with pytest.raises(SystemExit):

@@ -377,6 +377,29 @@ int b200r_tokens_to_channels(const uint16_t* x, uint16_t* y, int b, int t, int c
 int b200r_channels_to_tokens_add(const uint16_t* y, const uint16_t* res, uint16_t* out, int b, int t,
                                  int c, int t_pad, b200r_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Input-gradient pass of the token models (what autograd.grad(loss, x) hands the attacks:
+ * RobustART/noise/utils/adv/autoattack/autopgd_base.py:371-376, Attacks/imfgsm_attack.py:77-80); split planes.
+ * The Linear layers' input gradients are b200r_linear calls with the transposed weights.
+ * ------------------------------------------------------------------------------------------ */
+/* nn.LayerNorm backward w.r.t. its input: dx = add + rstd (dy g - mean(dy g) - xhat mean(dy g xhat)); `add` (the
+ * gradient arriving over the residual connection) may be NULL */
+int b200r_layernorm_bwd(const uint16_t* dy, const uint16_t* x, const float* gamma, const uint16_t* add,
+                        uint16_t* dx, int rows, int c, float eps, b200r_stream_t stream);
+/* out = act(pre) and dx = dy * act'(pre) on a saved pre-activation; act in {GELU_TANH, GELU_ERF, TANH};
+ * count = elements per plane, a multiple of 8 */
+int b200r_act_planes(const uint16_t* pre, uint16_t* out, size_t count, int act, b200r_stream_t stream);
+int b200r_act_bwd_planes(const uint16_t* dy, const uint16_t* pre, uint16_t* dx, size_t count, int act,
+                         b200r_stream_t stream);
+/* transpose of b200r_patch_gather_f32: dcols planes [n*(h/p)*(w/p), 3*p*p] -> float32 NCHW gradient w.r.t. the
+ * [0,1] image, dx[n,c,y,x] = dcols[...] / std[c]; patch a multiple of 8 */
+int b200r_patch_scatter_f32(const uint16_t* dcols, float* dx, int n, int h, int w, int patch,
+                            const float* std_host, b200r_stream_t stream);
+/* backward of b200r_attention: dout planes [n*t, h*d] -> dqkv planes [n*t, 3*h*d] in the packing of qkv; the
+ * probabilities are recomputed from qkv (nothing else is saved by the forward) */
+int b200r_attention_bwd(const uint16_t* qkv, const uint16_t* dout, uint16_t* dqkv, int n, int tokens, int heads,
+                        int head_dim, float scale, b200r_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -432,6 +432,12 @@ class _Lin:
             return ops.linear(x, self.w, None, self.b, res, act=act, passes=passes, out_f32=out_f32, want_planes=False)
         return ops.linear(x, self.w, None, self.b, res, act=act, passes=passes)
 
+    def dgrad(self, g, passes=3):
+        """Input gradient of the Linear: g planes [2, m, nout] -> planes [2, m, k] = g W (a GEMM with the transposed weights)."""
+        if getattr(self, "_wt", None) is None:
+            self._wt = ops.split_f32(ops.merge_f32(self.w).t().contiguous())
+        return ops.linear(g, self._wt, passes=passes)
+
 
 class _TokenModel:
     def __init__(self, device, passes):
@@ -491,6 +497,56 @@ class ViT(_TokenModel):
     def launches_per_forward(self):
         return 2 + 1 + self.depth * 7 + 1 + 1 + (1 if self.pre else 0) + 1
 
+    # -- forward that keeps what the input-gradient pass needs, and that pass (opt-in: B200R_NATIVE_TOKEN_GRAD=1) ----------
+    def forward_saved(self, x01: torch.Tensor):
+        """float32 NCHW [0,1] images -> (logits, saved).  Same layers as forward(); the two activations whose derivative needs
+        the pre-activation (GELU in the MLP, tanh in pre_logits) run as a plain Linear + b200r_act_planes."""
+        n, _, h, w = x01.shape
+        P = self.passes
+        x = self.embed(ops.patch_gather(x01.contiguous(), self.patch), passes=P)
+        npatch = x.shape[1] // n
+        x = ops.assemble_tokens(x, self.cls, self.pos, n, npatch)
+        T = npatch + 1
+        hd = self.dim // self.heads
+        saved = {"shape": (n, h, w, T), "blocks": []}
+        for b in self.blocks:
+            x_in = x
+            qkv = b["qkv"](ops.layernorm(x, *b["n1"], eps=1e-5), passes=P)
+            x_mid = b["out"](ops.attention(qkv, n, T, self.heads, hd, hd ** -0.5), res=x, passes=P)
+            pre = b["m1"](ops.layernorm(x_mid, *b["n2"], eps=1e-5), passes=P)
+            x = b["m2"](ops.act_planes(pre, "gelu_tanh"), res=x_mid, passes=P)
+            saved["blocks"].append((x_in, qkv, x_mid, pre))
+        saved["final"] = x
+        cls = ops.layernorm(x, *self.norm, eps=1e-5).view(2, n, T, self.dim)[:, :, 0].contiguous()
+        if self.pre is not None:
+            saved["pre_logits"] = self.pre(cls, passes=P)
+            cls = ops.act_planes(saved["pre_logits"], "tanh")
+        logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
+        self.head(cls, passes=P, out_f32=logits)
+        return logits, saved
+
+    def input_grad(self, dlogits: torch.Tensor, saved, passes: Optional[int] = None) -> torch.Tensor:
+        """d loss / d x01 (float32 NCHW) from d loss / d logits; input gradients only (vision_transformer.py:44-349 reversed)."""
+        P = self.passes if passes is None else passes
+        n, h, w, T = saved["shape"]
+        hd = self.dim // self.heads
+        g = self.head.dgrad(ops.split_f32(dlogits.contiguous()), P)                   # [2, n, rep]
+        if self.pre is not None:
+            g = self.pre.dgrad(ops.act_bwd_planes(g, saved["pre_logits"], "tanh"), P)
+        # encoder_norm only feeds x[:, 0]: LayerNorm is row-wise, so its backward runs on the class rows alone
+        x_cls = saved["final"].view(2, n, T, self.dim)[:, :, 0].contiguous()
+        g_cls = ops.layernorm_bwd(g, x_cls, self.norm[0], eps=1e-5)
+        g = torch.zeros((2, n, T, self.dim), dtype=g_cls.dtype, device=g_cls.device)   # int16 planes: bf16 zero = 0x0000
+        g[:, :, 0] = g_cls
+        g = g.view(2, n * T, self.dim)
+        for b, (x_in, qkv, x_mid, pre) in zip(reversed(self.blocks), reversed(saved["blocks"])):
+            t = b["m1"].dgrad(ops.act_bwd_planes(b["m2"].dgrad(g, P), pre, "gelu_tanh"), P)
+            g = ops.layernorm_bwd(t, x_mid, b["n2"][0], eps=1e-5, add=g)               # x = x_mid + mlp(norm2(x_mid))
+            t = ops.attention_bwd(qkv, b["out"].dgrad(g, P), n, T, self.heads, hd, hd ** -0.5)
+            g = ops.layernorm_bwd(b["qkv"].dgrad(t, P), x_in, b["n1"][0], eps=1e-5, add=g)  # x_mid = x_in + attn(norm1(x_in))
+        g = g.view(2, n, T, self.dim)[:, :, 1:].contiguous().view(2, n * (T - 1), self.dim)   # drop the class token
+        return ops.patch_scatter(self.embed.dgrad(g, P), n, h, w, self.patch)
+
 
 class Mixer(_TokenModel):
     T_PAD = 256   # token dimension padded so that the [b*c, t] rows are 16-byte aligned and K is a multiple of 64
@@ -537,6 +593,48 @@ class Mixer(_TokenModel):
 
     def launches_per_forward(self):
         return 2 + self.depth * 8 + 1 + 1 + 1
+
+    # -- forward that keeps what the input-gradient pass needs, and that pass (opt-in: B200R_NATIVE_TOKEN_GRAD=1) ----------
+    def forward_saved(self, x01: torch.Tensor):
+        """float32 NCHW [0,1] images -> (logits, saved).  Same layers as forward(); the GELUs run as a plain Linear +
+        b200r_act_planes so that the pre-activations are available to the gradient pass."""
+        n, _, h, w = x01.shape
+        P = self.passes
+        x = self.embed(ops.patch_gather(x01.contiguous(), self.patch), passes=P)
+        T = x.shape[1] // n
+        saved = {"shape": (n, h, w, T), "blocks": []}
+        for b in self.blocks:
+            x_in = x
+            y = ops.tokens_to_channels(ops.layernorm(x, *b["n1"], eps=1e-6), n, T, self.dim, self.T_PAD)
+            p1 = b["t1"](y, passes=P)
+            y = b["t2"](ops.act_planes(p1, "gelu_erf"), passes=P)
+            x_mid = ops.channels_to_tokens_add(y, x, n, T, self.dim, self.T_PAD)
+            p2 = b["c1"](ops.layernorm(x_mid, *b["n2"], eps=1e-6), passes=P)
+            x = b["c2"](ops.act_planes(p2, "gelu_erf"), res=x_mid, passes=P)
+            saved["blocks"].append((x_in, p1, x_mid, p2))
+        saved["final"] = x
+        x = ops.layernorm(x, *self.norm, eps=1e-6)
+        pooled = ops.global_avgpool(x.view(2, n, T, 1, self.dim))
+        logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
+        self.head(pooled, passes=P, out_f32=logits)
+        return logits, saved
+
+    def input_grad(self, dlogits: torch.Tensor, saved, passes: Optional[int] = None) -> torch.Tensor:
+        """d loss / d x01 (float32 NCHW) from d loss / d logits; input gradients only (mlp_mixer.py:7-159 reversed)."""
+        P = self.passes if passes is None else passes
+        n, h, w, T = saved["shape"]
+        g = self.head.dgrad(ops.split_f32(dlogits.contiguous()), P)                   # [2, n, dim]
+        g = ops.global_avgpool_bwd(g, T, 1).view(2, n * T, self.dim)                  # x.mean(dim=1) backward
+        g = ops.layernorm_bwd(g, saved["final"], self.norm[0], eps=1e-6)
+        zeros = torch.zeros_like(g)                                                   # residual operand of the plain transpose
+        for b, (x_in, p1, x_mid, p2) in zip(reversed(self.blocks), reversed(saved["blocks"])):
+            t = b["c1"].dgrad(ops.act_bwd_planes(b["c2"].dgrad(g, P), p2, "gelu_erf"), P)
+            g = ops.layernorm_bwd(t, x_mid, b["n2"][0], eps=1e-6, add=g)               # x = x_mid + channel_mix(norm2(x_mid))
+            t = ops.tokens_to_channels(g, n, T, self.dim, self.T_PAD)                  # [n*dim, T_PAD]
+            t = b["t1"].dgrad(ops.act_bwd_planes(b["t2"].dgrad(t, P), p1, "gelu_erf"), P)
+            t = ops.channels_to_tokens_add(t, zeros, n, T, self.dim, self.T_PAD)
+            g = ops.layernorm_bwd(t, x_in, b["n1"][0], eps=1e-6, add=g)                # x_mid = x_in + token_mix(norm1(x_in))
+        return ops.patch_scatter(self.embed.dgrad(g, P), n, h, w, self.patch)
 
 
 _TOKEN_ARCHS = {"vit_b16_224": (ViT, vit_spec), "vit_base_patch16_224": (ViT, vit_spec), "mixer_b16_224": (Mixer, mixer_spec)}

@@ -579,6 +579,60 @@ def channels_to_tokens_add(y, res, b, t, c, t_pad):
     return out
 
 
+# input-gradient pass of the token models (token_backward.cu) ---------------------------------------
+def layernorm_bwd(dy, x, gamma, eps=1e-5, add=None):
+    """dy, x (the LayerNorm's INPUT), add (optional residual gradient): planes [2, rows, c] -> dx planes."""
+    _need_cuda(dy, torch.int16, "dy")
+    _need_cuda(x, torch.int16, "x")
+    c = x.shape[-1]
+    rows = x[0].numel() // c
+    assert dy.shape == x.shape and (add is None or add.shape == x.shape)
+    dx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), _ptr(add), dx.data_ptr(), rows, c, eps,
+                                                   _stream()))
+    return dx
+
+
+def act_planes(pre, act):
+    """act(pre) on split planes (the forward of a Linear whose pre-activation is kept for the gradient pass)."""
+    _need_cuda(pre, torch.int16, "pre")
+    out = torch.empty_like(pre)
+    with torch.cuda.device(pre.device):
+        _lib.check(_lib.load().b200r_act_planes(pre.data_ptr(), out.data_ptr(), pre[0].numel(), ACT[act], _stream()))
+    return out
+
+
+def act_bwd_planes(dy, pre, act):
+    _need_cuda(dy, torch.int16, "dy")
+    _need_cuda(pre, torch.int16, "pre")
+    assert dy.shape == pre.shape
+    dx = torch.empty_like(pre)
+    with torch.cuda.device(pre.device):
+        _lib.check(_lib.load().b200r_act_bwd_planes(dy.data_ptr(), pre.data_ptr(), dx.data_ptr(), pre[0].numel(), ACT[act], _stream()))
+    return dx
+
+
+def patch_scatter(dcols, n, h, w, patch=16, std=IMAGENET_STD):
+    """dcols planes [2, n*(h/p)*(w/p), 3*p*p] -> float32 NCHW gradient w.r.t. the [0,1] image (transpose of patch_gather)."""
+    _need_cuda(dcols, torch.int16, "dcols")
+    assert dcols[0].numel() == n * 3 * h * w
+    dx = torch.empty((n, 3, h, w), dtype=torch.float32, device=dcols.device)
+    with torch.cuda.device(dcols.device):
+        _lib.check(_lib.load().b200r_patch_scatter_f32(dcols.data_ptr(), dx.data_ptr(), n, h, w, patch, _lib.f3(std), _stream()))
+    return dx
+
+
+def attention_bwd(qkv, dout, n, tokens, heads, head_dim, scale):
+    _need_cuda(qkv, torch.int16, "qkv")
+    _need_cuda(dout, torch.int16, "dout")
+    dqkv = torch.empty_like(qkv)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.load().b200r_attention_bwd(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), n, tokens, heads, head_dim, scale,
+                                                   _stream()))
+    return dqkv
+
+
 # ------------------------------------------------------------------------------------------------
 # mobile-family layers
 # ------------------------------------------------------------------------------------------------

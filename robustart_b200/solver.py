@@ -200,6 +200,9 @@ def build_source_model(model_cfg, ckpt_path, device):
     arch = nets.ARCH_ALIASES.get(model_cfg["type"], model_cfg["type"])
     if arch in nets._RESNET_CFG and os.environ.get("B200R_SOURCE_AUTOGRAD", "0") != "1":
         return NativeModel(build_b200_model(model_cfg, ckpt_path, device))
+    if arch in nets._TOKEN_ARCHS and os.environ.get("B200R_NATIVE_TOKEN_GRAD", "0") == "1":
+        # opt-in until measured against the autograd twin on the GPU: forward + input gradient of ViT / Mixer on our kernels
+        return NativeModel(build_b200_model(model_cfg, ckpt_path, device))
     return build_torch_model(model_cfg, ckpt_path, device)
 
 

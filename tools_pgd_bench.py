@@ -1,6 +1,8 @@
-"""PGD-Linf k-step eval loop on ResNet-50: images/s and tensor-pipe fraction, native dgrad vs autograd twin.
+"""PGD-Linf k-step eval loop: images/s and tensor-pipe fraction, native dgrad vs autograd twin.
 
-  python tools_pgd_bench.py [--n 128] [--steps 10] [--arch resnet50] [--autograd]
+  python tools_pgd_bench.py [--n 128] [--steps 10] [--arch resnet50|resnet18|vit_b16_224|mixer_b16_224] [--autograd]
+
+The token archs (BASELINE configs[2] / [4]) use the input-gradient pass of DESIGN.md section 4d as the native source.
 """
 import argparse
 import json
@@ -12,7 +14,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from robustart_b200 import attacks, nets, ops, torch_models  # noqa: E402
 
-FWD_GFLOP = {"resnet50": 8.18, "resnet18": 3.62}
+FWD_GFLOP = {"resnet50": 8.18, "resnet18": 3.62, "vit_b16_224": 35.1, "mixer_b16_224": 25.2}
 
 
 def main():
@@ -26,10 +28,13 @@ def main():
     ap.add_argument("--passes", type=int, default=3, help="3 = split-bf16, 16 = fp16 single plane")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
-    sd = nets.random_state_dict(nets.resnet_spec(a.arch), 0)
+    if a.arch in nets._TOKEN_ARCHS:
+        sd = nets.random_token_state_dict(nets._TOKEN_ARCHS[a.arch][1](), 0)
+    else:
+        sd = nets.random_state_dict(nets.resnet_spec(a.arch), 0)
     net = nets.build_model(a.arch, sd, device=dev, passes=a.passes)
     if a.autograd:
-        twin = torch_models.build(a.arch, sd).to(dev).eval()
+        twin = torch_models.build(a.arch, nets._strip_prefix(sd)).to(dev).eval()
         src = attacks.PyTorchModel(twin, preprocessing=dict(mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, axis=-3))
     else:
         src = attacks.NativeModel(net, passes_bwd=a.passes_bwd)

@@ -13,6 +13,11 @@
 #include <cmath>
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
+
+// corrupt_spatter_water.cu (not part of the C-ABI)
+extern "C" int b200r_spatter_water_planes(const float* liquid, float* dist, void* extra, const uint8_t* in, uint8_t* out, int n, int h,
+                                          int w, float c4, b200r_stream_t stream);
 
 namespace {
 
@@ -724,10 +729,10 @@ static const double kSnow[5][7] = {{0.1, 0.3, 3, 0.5, 10, 4, 0.8}, {0.2, 0.3, 2,
                                    {0.55, 0.3, 4.5, 0.85, 12, 8, 0.65}, {0.55, 0.3, 2.5, 0.85, 12, 12, 0.55}};
 
 size_t corrupt_stencil_ws(int id, int sev, int n, int h, int w) {
-  (void)sev;
   // a scratch image: glass_blur's intermediate, and the detour for in-place calls (none of these
   // kernels can overwrite its own input)
-  if (id == B200R_SPATTER) return (size_t)n * h * w * 2 * sizeof(float);   // two ping-pong float planes
+  // spatter: two ping-pong float planes; the water branch (severity 1-3) adds an int plane and four byte planes
+  if (id == B200R_SPATTER) return (size_t)n * h * w * (2 * sizeof(float) + (sev <= 3 ? 8 : 0));
   // elastic: warped fp32 image + two ping-pong buffers of the (dx, dy) fields
   if (id == B200R_ELASTIC_TRANSFORM) return (size_t)n * h * w * (3 + 2 + 2) * sizeof(float);
   return (size_t)n * h * w * 3;
@@ -893,8 +898,14 @@ static int stencil_dispatch(const CorruptArgs& a) {
       static const double c[5][6] = {{0.65, 0.3, 4, 0.69, 0.6, 0}, {0.65, 0.3, 3, 0.68, 0.6, 0}, {0.65, 0.3, 2, 0.68, 0.5, 0},
                                      {0.65, 0.3, 1, 0.65, 1.5, 1}, {0.67, 0.4, 1, 0.65, 1.5, 1}};
       if (c[s][5] == 0) {
-        b200r_set_error("spatter severity 1-3 (water: cv2.Canny / distanceTransform / equalizeHist chain) is not implemented on the GPU yet");
-        return B200R_ENOTSUP;
+        // water branch (corrupt_spatter_water.cu): written and emulator-checked but not yet run on a GPU -> opt-in
+        static int water = -1;
+        if (water < 0) { const char* e = getenv("B200R_SPATTER_WATER"); water = (e && e[0] == '1') ? 1 : 0; }
+        if (!water) {
+          b200r_set_error("spatter severity 1-3 (water: cv2.Canny / distanceTransform / equalizeHist chain) is not enabled on the GPU yet "
+                          "(B200R_SPATTER_WATER=1 selects the unvalidated kernel)");
+          return B200R_ENOTSUP;
+        }
       }
       const int hw = a.h * a.w;
       const size_t need = corrupt_stencil_ws(a.id, a.severity, a.n, a.h, a.w);
@@ -905,6 +916,12 @@ static int stencil_dispatch(const CorruptArgs& a) {
       spatter_layer_kernel<<<g, kElThreads, 0, a.stream>>>(p0, hw, (float)c[s][0], (float)c[s][1], a.ext, k0, k1, a.image_offset);
       GaussW g1 = make_gauss(c[s][2], 4.0), g2 = make_gauss(c[s][4], 4.0);
       plane_blur_kernel<<<g, kElThreads, 0, a.stream>>>(p0, p1, a.h, a.w, g1, 0, 0, 0.f);                 // axis 0 first (scipy order)
+      if (c[s][5] == 0) {
+        plane_blur_kernel<<<g, kElThreads, 0, a.stream>>>(p1, p0, a.h, a.w, g1, 1, 2, (float)c[s][3]);    // liquid[liquid < c3] = 0
+        B200R_LAUNCH_CHECK();
+        return b200r_spatter_water_planes(p0, p1, p1 + (size_t)a.n * hw, a.in, a.out, a.n, a.h, a.w, (float)c[s][4],
+                                          reinterpret_cast<b200r_stream_t>(a.stream));
+      }
       plane_blur_kernel<<<g, kElThreads, 0, a.stream>>>(p1, p0, a.h, a.w, g1, 1, 1, (float)c[s][3]);      // threshold -> binary mask
       plane_blur_kernel<<<g, kElThreads, 0, a.stream>>>(p0, p1, a.h, a.w, g2, 0, 0, 0.f);
       plane_blur_kernel<<<g, kElThreads, 0, a.stream>>>(p1, p0, a.h, a.w, g2, 1, 2, 0.8f);                // m[m < 0.8] = 0

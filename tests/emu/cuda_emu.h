@@ -3,7 +3,7 @@
 // placement of a kernel can be checked in a container without a GPU.  One OS thread per CUDA thread of a block, blocks one
 // after another; __syncthreads / __syncwarp / __shfl_*_sync are real barriers, so a missing or misplaced synchronisation
 // shows up as a wrong result or a data race here too (not guaranteed, but the schedules differ enough to be a useful probe).
-// Not emulated: tcgen05 / TMA / mbarrier / inline PTX (those kernels are validated on the GPU only), atomics, textures.
+// Not emulated: tcgen05 / TMA / mbarrier / inline PTX (those kernels are validated on the GPU only), float atomics, textures.
 // The product never includes this file.
 #pragma once
 #include <cuda_runtime.h>   // vector types and make_* only: no CUDA runtime call is made (nothing links against libcudart)
@@ -73,6 +73,14 @@ inline float __fmaf_rz(float a, float b, float c) {           // round-toward-ze
   return r;
 }
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }      // one rounding per operation, never contracted
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 
 // dynamic shared memory: `extern __shared__ T name[];` is rewritten into a pointer to this pool (blocks run one at a time)
 alignas(128) inline unsigned char emu_smem_pool[256 * 1024];

@@ -58,14 +58,14 @@ def _rewrite(src: str) -> str:
 def emu(tmp_path_factory):
     d = tmp_path_factory.mktemp("emu")
     libs = {}
-    for name in ("token_layers", "token_backward"):
+    for name in ("token_layers", "token_backward", "corrupt_spatter_water"):
         cpp = d / (name + "_emu.cpp")
         text = _rewrite(open(os.path.join(CSRC, name + ".cu")).read())
         if name == "token_layers":      # the tensor-core attention lives in another file: report "not supported" -> CUDA-core kernel
             text += '\nint b200r_attention_tc(const uint16_t*, uint16_t*, int, int, int, float, cudaStream_t) { return B200R_ENOTSUP; }\n'
         cpp.write_text(text)
         so = d / ("lib%s_emu.so" % name)
-        r = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", CUDA_INC, str(cpp), "-o", str(so)],
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", CUDA_INC, str(cpp), "-o", str(so)],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
         libs[name] = C.CDLL(str(so))
@@ -218,3 +218,45 @@ def test_attention_bwd_kernel(emu, n, t, heads):
     assert torch.equal(qp, split(qkv))
     assert lib.b200r_attention_bwd(_p(qp), _p(dop), _p(got), n, t, heads, 32, C.c_float(1.0), None) != 0   # head_dim 64 only
     assert lib.b200r_attention_bwd(_p(qp), _p(dop), _p(got), 1, 400, 1, 64, C.c_float(1.0), None) != 0     # does not fit in smem
+
+
+# ---- 3. spatter's water branch (csrc/corrupt_spatter_water.cu) -----------------------------------------------------------------------
+@pytest.mark.parametrize("sev,h,w", [(1, 64, 96), (3, 80, 64), (2, 224, 224)])
+def test_spatter_water_kernel(emu, sev, h, w):
+    """The one-CTA-per-image water chain from its own source (1024 emulated threads, static shared memory, a shared-memory
+    histogram with atomics, the bit-mask distance stage) against oracle/spatter_water.py -- which is itself byte-exact against the
+    cv2 calls of corruptions.py:305-328 (tests/test_oracle_cpu.py) -- and, end to end, against oracle.imagenet_c.spatter (cv2)."""
+    import numpy as np
+    pytest.importorskip("cv2")
+    from oracle import imagenet_c as O, spatter_water as W
+    from util import synth_images
+    lib = emu["corrupt_spatter_water"]
+    n = 2
+    c = O.SPATTER_PARAMS[sev - 1]
+    imgs = np.ascontiguousarray(synth_images(n, seed=90 + sev)[:, :h, :w])
+    zs = np.random.RandomState(sev).normal(size=(n, h, w))
+    liquid64 = np.stack([O.sk_gaussian(c[0] + c[1] * z, sigma=c[2], multichannel=False) for z in zs])
+    liquid64[liquid64 < c[3]] = 0
+    liquid = torch.from_numpy(liquid64.astype(np.float32)).contiguous()
+    dist = torch.empty(n, h * w)
+    extra = torch.empty(n * h * w * 8, dtype=torch.uint8)
+    x = torch.from_numpy(imgs)
+    out = torch.full_like(x, 123)
+    lib.b200r_spatter_water_planes.argtypes = [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_float, C.c_void_p]
+    _ok(lib.b200r_spatter_water_planes(_p(liquid), _p(dist), _p(extra), _p(x), _p(out), n, h, w, c[4], None))
+    got = out.numpy()
+    l8 = (liquid.numpy() * np.float32(255)).astype(np.uint8)                 # the kernel's own stage 0 (float32 product)
+    for i in range(n):
+        assert np.array_equal(got[i], W.water(l8[i], imgs[i], c[4])), "image %d" % i
+        # against the reference's cv2 chain on the float64 liquid layer: identical unless the float32 layer truncates differently
+        class Draws:
+            def normal(self, size, loc, scale, z=zs[i]):
+                return loc + scale * z
+        want = np.uint8(O.spatter(imgs[i], sev, Draws()))
+        if np.array_equal(l8[i], (liquid64[i] * 255).astype(np.uint8)):
+            assert np.array_equal(got[i], want)
+        else:
+            assert (np.abs(got[i].astype(int) - want.astype(int)) > 1).mean() < 5e-3
+    # argument checks
+    assert lib.b200r_spatter_water_planes(_p(liquid), _p(dist), _p(extra), _p(x), _p(out), n, 1, w, c[4], None) != 0
+    assert lib.b200r_spatter_water_planes(_p(liquid), _p(dist), _p(extra), _p(x), _p(out), n, 4096, 4096, c[4], None) != 0

@@ -201,3 +201,41 @@ def test_eval_reduction_matches_reference_code():
     assert float(top1) == a["top1"] and float(top5) == a["top5"]
     h1, h5 = OM.topk_hits(logits, target, (1, 5))
     assert abs(100.0 * h1 / 40 - a["top1"]) < 1e-4 and abs(100.0 * h5 / 40 - a["top5"]) < 1e-4
+
+
+def test_spatter_water_restatement():
+    """oracle/spatter_water.py (the algorithm csrc/corrupt_spatter_water.cu follows) against the OpenCV calls the reference makes
+    (corruptions.py:305-328, executed by oracle.imagenet_c.spatter through cv2 itself): final images byte-exact for severity
+    1-3, and the integer stages exact one by one."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import imagenet_c as O, spatter_water as W
+    from util import synth_images
+    for sev in (1, 2, 3):
+        img = synth_images(1, seed=70 + sev)[0]
+        c = O.SPATTER_PARAMS[sev - 1]
+        z = np.random.RandomState(sev).normal(size=img.shape[:2])
+
+        class Draws:
+            def normal(self, size, loc, scale):
+                return loc + scale * z
+        want = np.uint8(O.spatter(img, sev, Draws()))
+        liquid = O.sk_gaussian(c[0] + c[1] * z, sigma=c[2], multichannel=False)
+        liquid[liquid < c[3]] = 0
+        l8 = (liquid * 255).astype(np.uint8)
+        assert np.array_equal(W.water(l8, img, c[4]), want)
+        assert (want != img).mean() > 0.02                                 # the branch does something
+        # stage by stage
+        edge = cv2.Canny(l8, 50, 150)
+        assert np.array_equal(W.canny(l8) * np.uint8(255), edge)
+        d = np.minimum(cv2.distanceTransform(255 - edge, cv2.DIST_L2, 5), 20)
+        mine = W.truncated_distance(edge > 0)
+        assert np.abs(mine - d).max() <= 4e-6 and (mine != d).mean() < 0.02   # float32 path order inside IPP: <= 1 ulp apart
+        u = cv2.blur(d, (3, 3)).astype(np.uint8)
+        assert np.array_equal(W.blur3_f32_to_u8(d), u)
+        assert np.array_equal(W.equalize_hist(u), cv2.equalizeHist(u))
+        e = cv2.equalizeHist(u)
+        f = cv2.filter2D(e, cv2.CV_8U, np.array([[-2, -1, 0], [-1, 1, 1], [0, 1, 2]]))
+        assert np.array_equal(W.filter2d_emboss(e), f)
+        assert np.array_equal(W.blur3_u8(f), cv2.blur(f, (3, 3)))
+    flat = np.full((16, 16), 7, np.uint8)
+    assert np.array_equal(W.equalize_hist(flat), cv2.equalizeHist(flat))   # single-bin image: cv2 fills with the bin index

@@ -3,7 +3,7 @@
 // placement of a kernel can be checked in a container without a GPU.  One OS thread per CUDA thread of a block, blocks one
 // after another; __syncthreads / __syncwarp / __shfl_*_sync are real barriers, so a missing or misplaced synchronisation
 // shows up as a wrong result or a data race here too (not guaranteed, but the schedules differ enough to be a useful probe).
-// Not emulated: tcgen05 / TMA / mbarrier / inline PTX (those kernels are validated on the GPU only), float atomics, textures.
+// Not emulated: tcgen05 / TMA / mbarrier / inline PTX (those kernels are validated on the GPU only), textures.
 // The product never includes this file.
 #pragma once
 #include <cuda_runtime.h>   // vector types and make_* only: no CUDA runtime call is made (nothing links against libcudart)
@@ -75,9 +75,30 @@ inline float __fmaf_rz(float a, float b, float c) {           // round-toward-ze
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }      // one rounding per operation, never contracted
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicMax(int* p, int v) { int o = *p; while (o < v && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+inline float atomicAdd(float* p, float v) {                    // CAS loop: order-dependent rounding, like the hardware
+  uint32_t* u = reinterpret_cast<uint32_t*>(p);
+  uint32_t o = __atomic_load_n(u, __ATOMIC_RELAXED), nw;
+  float f;
+  do { memcpy(&f, &o, 4); f += v; memcpy(&nw, &f, 4); } while (!__atomic_compare_exchange_n(u, &o, nw, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  memcpy(&f, &o, 4);
+  return f;
+}
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline size_t min(size_t a, size_t b) { return a < b ? a : b; }
+inline size_t max(size_t a, size_t b) { return a > b ? a : b; }
+inline float min(float a, float b) { return fminf(a, b); }
+inline float max(float a, float b) { return fmaxf(a, b); }
+inline double min(double a, double b) { return fmin(a, b); }
+inline double max(double a, double b) { return fmax(a, b); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
@@ -125,6 +146,25 @@ inline void emu_launch(G grid_, B block_, size_t smem_bytes, const std::function
         pthread_barrier_destroy(&blk.bar);
       }
 }
+
+// ---- the few CUDA runtime calls the entry points make, on host memory (nothing links against libcudart) ----------------------
+extern "C" {
+inline cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+inline cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t) { return "emulator"; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+}
+
+template <class T> inline cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute, int) { return cudaSuccess; }   // kernel pointers
 
 // ---- host-side plumbing of common.cuh that needs a device ------------------------------------------------------------------
 inline int b200r_num_sms() { return 2; }

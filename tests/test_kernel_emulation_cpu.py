@@ -25,18 +25,74 @@ MEAN = (0.485, 0.456, 0.406)
 pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")), reason="CUDA headers not found")
 
 
+def _split_args(cfg: str):
+    """Split a launch configuration on top-level commas."""
+    parts, depth, cur = [], 0, []
+    for ch in cfg:
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+    parts.append("".join(cur).strip())
+    return parts
+
+
+_PTX_HELPERS = ("ld_stream_u4", "st_stream_u4", "ld_stream_f4", "st_stream_f4", "box_muller16")   # inline PTX in common.cuh
+
+
+def _drop_function(text: str, name: str) -> str:
+    m = re.search(r"__device__ __forceinline__ [\w ]+?\b%s\(" % name, text)
+    if not m:
+        return text
+    i = text.index("{", m.end())
+    depth = 0
+    while True:
+        depth += {"{": 1, "}": -1}.get(text[i], 0)
+        i += 1
+        if depth == 0:
+            break
+    return text[:m.start()] + text[i:]
+
+
+def _inline_headers(src: str) -> str:
+    """Paste common.cuh / corrupt.cuh into the source once each (PTX helpers replaced by the host versions of cuda_emu_post.h)."""
+    seen = set()
+
+    def load(m):
+        name = m.group(1) + ".cuh"
+        if name in seen:
+            return ""
+        seen.add(name)
+        text = open(os.path.join(CSRC, name)).read().replace("#pragma once", "")
+        if name == "common.cuh":
+            for fn in _PTX_HELPERS:
+                text = _drop_function(text, fn)
+            text = text.replace('#include "../../include/b200r.h"', '#include "%s/include/b200r.h"' % ROOT)
+            text += '\n#include "cuda_emu_post.h"\n'
+        return re.sub(r'#include "(common|corrupt)\.cuh"\n', load, text)
+    return re.sub(r'#include "(common|corrupt)\.cuh"\n', load, src)
+
+
 def _rewrite(src: str) -> str:
-    """CUDA source -> host C++: dynamic/static shared memory, <<<>>> launches, and the include of common.cuh."""
-    src = src.replace('#include "common.cuh"',
-                      '#include "cuda_emu.h"\n#include "%s/common.cuh"\n#undef B200R_CUDA\n#define B200R_CUDA(call) do { } while (0)\n' % CSRC)
-    src = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(emu_smem_pool);", src)
+    """CUDA source -> host C++: the emulator header first (SIMT context + a host stand-in for the few CUDA runtime calls),
+    dynamic/static shared memory, <<<>>> launches."""
+    src = '#include "cuda_emu.h"\n' + _inline_headers(src)
+    src = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(emu_smem_pool);", src)
     src = src.replace("__shared__", "static")
     out, pos = [], 0
     for m in re.finditer(r"([A-Za-z_]\w*(?:<[\w, ]*>)?)<<<", src):
         if m.start() < pos:
             continue
         close = src.index(">>>", m.end())
-        cfg = src[m.end():close]
+        parts = _split_args(src[m.end():close])
+        assert 2 <= len(parts) <= 4, parts
+        if len(parts) < 3:
+            parts.append("0")
         assert src[close + 3] == "(", src[close:close + 20]
         depth, i = 0, close + 3
         while True:
@@ -44,32 +100,37 @@ def _rewrite(src: str) -> str:
             i += 1
             if depth == 0:
                 break
-        args = src[close + 3:i]
-        parts = [p.strip() for p in re.split(r",(?![^()]*\))", cfg)]
-        assert len(parts) == 4, cfg
         out.append(src[pos:m.start()])
-        out.append("emu_launch(%s, %s, %s, [=] { %s%s; })" % (parts[0], parts[1], parts[2], m.group(1), args))
+        out.append("emu_launch(%s, %s, %s, [=] { %s%s; })" % (parts[0], parts[1], parts[2], m.group(1), src[close + 3:i]))
         pos = i
     out.append(src[pos:])
     return "".join(out)
 
 
+class _EmuLibs:
+    """Compiles csrc/<name>.cu for the host on first use."""
+
+    def __init__(self, d):
+        self.d, self.libs = d, {}
+
+    def __getitem__(self, name):
+        if name not in self.libs:
+            cpp = self.d / (name + "_emu.cpp")
+            text = _rewrite(open(os.path.join(CSRC, name + ".cu")).read())
+            if name == "token_layers":  # the tensor-core attention lives in another file: report "not supported" -> CUDA-core kernel
+                text += '\nint b200r_attention_tc(const uint16_t*, uint16_t*, int, int, int, float, cudaStream_t) { return B200R_ENOTSUP; }\n'
+            cpp.write_text(text)
+            so = self.d / ("lib%s_emu.so" % name)
+            r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", CUDA_INC,
+                                "-I", CSRC, str(cpp), "-o", str(so)], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-3000:]
+            self.libs[name] = C.CDLL(str(so))
+        return self.libs[name]
+
+
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
-    d = tmp_path_factory.mktemp("emu")
-    libs = {}
-    for name in ("token_layers", "token_backward", "corrupt_spatter_water"):
-        cpp = d / (name + "_emu.cpp")
-        text = _rewrite(open(os.path.join(CSRC, name + ".cu")).read())
-        if name == "token_layers":      # the tensor-core attention lives in another file: report "not supported" -> CUDA-core kernel
-            text += '\nint b200r_attention_tc(const uint16_t*, uint16_t*, int, int, int, float, cudaStream_t) { return B200R_ENOTSUP; }\n'
-        cpp.write_text(text)
-        so = d / ("lib%s_emu.so" % name)
-        r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", CUDA_INC, str(cpp), "-o", str(so)],
-                           capture_output=True, text=True)
-        assert r.returncode == 0, r.stderr[-3000:]
-        libs[name] = C.CDLL(str(so))
-    return libs
+    return _EmuLibs(tmp_path_factory.mktemp("emu"))
 
 
 # ---- split-bf16 planes on the host (common.cuh split_bf16: hi = RNE(v), lo = RNE(v - hi)) ----------------------------------
@@ -260,3 +321,65 @@ def test_spatter_water_kernel(emu, sev, h, w):
     # argument checks
     assert lib.b200r_spatter_water_planes(_p(liquid), _p(dist), _p(extra), _p(x), _p(out), n, 1, w, c[4], None) != 0
     assert lib.b200r_spatter_water_planes(_p(liquid), _p(dist), _p(extra), _p(x), _p(out), n, 4096, 4096, c[4], None) != 0
+
+
+# ---- 4. more GPU-validated kernels, as regression probes that need no GPU ---------------------------------------------------------------
+@pytest.mark.parametrize("filt,code", [("bilinear", 2), ("bicubic", 4), ("box", 1), ("lanczos", 5), ("nearest", 0), ("hamming", 3)])
+def test_resize_kernel_is_pillow_exact(emu, filt, code):
+    """csrc/resize.cu (Pillow's Resample.c restated: 22-bit fixed-point coefficients, two passes) against Image.resize, bit for bit,
+    including the fused centre crop of the eval transform (imagenet_dataloader.py:74-80)."""
+    import numpy as np
+    from PIL import Image
+    lib = emu["resize"]
+    rng = np.random.RandomState(code)
+    hin, win, hout, wout = 45, 61, 32, 40
+    img = rng.randint(0, 256, (2, hin, win, 3), dtype=np.uint8)
+    F_ = {"nearest": Image.NEAREST, "box": Image.BOX, "bilinear": Image.BILINEAR, "hamming": Image.HAMMING, "bicubic": Image.BICUBIC,
+          "lanczos": Image.LANCZOS}[filt]
+    for (oy0, ox0, ch, cw) in [(0, 0, hout, wout), (3, 5, 24, 30)]:
+        x = torch.from_numpy(img)
+        out = torch.zeros(2, ch, cw, 3, dtype=torch.uint8)
+        nbytes = C.c_size_t(0)
+        _ok(lib.b200r_resize_workspace_bytes(2, hin, win, hout, wout, code, oy0, ox0, ch, cw, C.byref(nbytes)))
+        ws = torch.empty(max(1, nbytes.value), dtype=torch.uint8)
+        _ok(lib.b200r_resize_u8(_p(x), _p(out), 2, hin, win, hout, wout, code, oy0, ox0, ch, cw, _p(ws), C.c_size_t(nbytes.value), None))
+        for i in range(2):
+            want = np.asarray(Image.fromarray(img[i]).resize((wout, hout), F_))[oy0:oy0 + ch, ox0:ox0 + cw]
+            assert np.array_equal(out[i].numpy(), want), (filt, i)
+
+
+def test_attack_step_and_loss_kernels(emu):
+    """csrc/attack_steps.cu and csrc/loss_metrics.cu against the torch statements the GPU tests use (tests/test_attacks_gpu.py,
+    tests/test_metrics_gpu.py): the L-inf step bit for bit, CE loss / gradient and the top-k counters."""
+    lib = emu["attack_steps"]
+    torch.manual_seed(0)
+    n, chw = 3, 3 * 16 * 16
+    x0, g, u = torch.rand(n, chw), torch.randn(n, chw), torch.rand(n, chw)
+    g[0, :5] = 0.0
+    eps, alpha = 4 / 255, 3 / 40 * 4 / 255
+    x = torch.empty(n, chw)
+    lib.b200r_random_start_linf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int,
+                                            C.c_void_p]
+    lib.b200r_pgd_step_linf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.c_void_p]
+    _ok(lib.b200r_random_start_linf(_p(x0), _p(x), n, chw, eps, 0, 0, _p(u), 1, None))
+    ref = (x0 + ((eps - (-eps)) * u + (-eps))).clamp(0, 1)
+    assert torch.equal(x, ref)
+    for _ in range(2):
+        ref = (x0 + (ref + alpha * g.sign() - x0).clamp(-eps, eps)).clamp(0, 1)
+        _ok(lib.b200r_pgd_step_linf(_p(x), _p(g), _p(x0), n, chw, alpha, eps, None))
+    assert torch.equal(x, ref)
+    lm = emu["loss_metrics"]
+    z, y = torch.randn(5, 1000) * 3, torch.randint(0, 1000, (5,))
+    z[2, y[2]] += 20.0                                                           # one certain top-1 hit
+    loss, d = torch.empty(5), torch.empty(5, 1000)
+    lm.b200r_ce_loss_grad.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_float, C.c_void_p]
+    _ok(lm.b200r_ce_loss_grad(_p(z), _p(y), _p(loss), _p(d), 5, 1000, 0.5, None))
+    zz = z.double().requires_grad_(True)
+    li = F.cross_entropy(zz, y, reduction="none")
+    (dref,) = torch.autograd.grad(li.sum() * 0.5, zz)
+    assert (loss.double() - li.detach()).abs().max().item() < 1e-5 and (d.double() - dref).abs().max().item() < 1e-6
+    counters, pred = torch.zeros(3, dtype=torch.int64), torch.empty(5, dtype=torch.int64)
+    _ok(lm.b200r_topk_count(_p(z), _p(y), 5, 1000, _p(counters), _p(pred), None))
+    top5 = z.topk(5, 1).indices
+    assert counters.tolist() == [int((top5[:, 0] == y).sum()), int((top5 == y[:, None]).any(1).sum()), 5]
+    assert torch.equal(pred, z.argmax(1))

@@ -153,6 +153,7 @@ inline cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 inline cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulator"; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 2; return cudaSuccess; }
 inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
@@ -167,6 +168,7 @@ inline cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 template <class T> inline cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute, int) { return cudaSuccess; }   // kernel pointers
 
 // ---- host-side plumbing of common.cuh that needs a device ------------------------------------------------------------------
+#ifndef EMU_API_TU            // api.cu defines these two itself
 inline int b200r_num_sms() { return 2; }
 inline thread_local char emu_error[512];
 inline void b200r_set_error(const char* fmt, ...) {
@@ -175,3 +177,4 @@ inline void b200r_set_error(const char* fmt, ...) {
   vsnprintf(emu_error, sizeof(emu_error), fmt, ap);
   va_end(ap);
 }
+#endif

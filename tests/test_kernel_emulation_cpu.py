@@ -113,7 +113,33 @@ class _EmuLibs:
     def __init__(self, d):
         self.d, self.libs = d, {}
 
+    FLAGS = ["-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", CUDA_INC, "-I", CSRC]
+
+    def _corrupt(self):
+        """libb200robust's corruption front door (api.cu) with the stencil / codec / spatter-water families behind it; the pixel
+        family (inline PTX) is stubbed out."""
+        objs = []
+        for name in ("api", "corrupt_stencil", "corrupt_codec", "corrupt_spatter_water", "pixel_stub"):
+            cpp = self.d / (name + "_emu.cpp")
+            if name == "pixel_stub":
+                cpp.write_text('#include "cuda_emu.h"\n' + _inline_headers('#include "corrupt.cuh"\n') +
+                               'int corrupt_pixel_family(const CorruptArgs&) { b200r_set_error("pixel family: not emulated"); return B200R_ENOTSUP; }\n'
+                               'size_t corrupt_pixel_ws(int, int, int, int, int) { return 0; }\n')
+            else:
+                cpp.write_text(_rewrite(open(os.path.join(CSRC, name + ".cu")).read()))
+            obj = self.d / (name + "_emu.o")
+            r = subprocess.run(["g++", *self.FLAGS, *(["-DEMU_API_TU"] if name == "api" else []), "-c", str(cpp), "-o", str(obj)],
+                               capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-3000:]
+            objs.append(str(obj))
+        so = self.d / "libcorrupt_emu.so"
+        r = subprocess.run(["g++", "-shared", "-pthread", *objs, "-o", str(so)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        return C.CDLL(str(so))
+
     def __getitem__(self, name):
+        if name == "corrupt" and name not in self.libs:
+            self.libs[name] = self._corrupt()
         if name not in self.libs:
             cpp = self.d / (name + "_emu.cpp")
             text = _rewrite(open(os.path.join(CSRC, name + ".cu")).read())
@@ -383,3 +409,69 @@ def test_attack_step_and_loss_kernels(emu):
     top5 = z.topk(5, 1).indices
     assert counters.tolist() == [int((top5[:, 0] == y).sum()), int((top5 == y[:, None]).any(1).sum()), 5]
     assert torch.equal(pred, z.argmax(1))
+
+
+# ---- 5. corruptions end to end through b200r_corrupt_u8 (api.cu + the stencil / codec families) ------------------------------------------
+def _corrupt(lib, name_id, sev, images, ext):
+    import numpy as np
+    n, h, w, _ = images.shape
+    x = torch.from_numpy(np.ascontiguousarray(images))
+    out = torch.empty_like(x)
+    nbytes = C.c_size_t(0)
+    _ok(lib.b200r_corrupt_workspace_bytes(name_id, sev, n, h, w, C.byref(nbytes)))
+    ws = torch.empty(max(16, nbytes.value), dtype=torch.uint8)
+    e = torch.from_numpy(np.ascontiguousarray(ext, dtype=np.float32)) if ext is not None and ext.size else None
+    lib.b200r_corrupt_u8.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p,
+                                     C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.b200r_last_error.restype = C.c_char_p
+    rc = lib.b200r_corrupt_u8(name_id, sev, _p(x), _p(out), n, h, w, 0, 0, _p(e) if e is not None else None, _p(ws), nbytes.value, None)
+    return rc, out.numpy()
+
+
+def test_spatter_end_to_end_through_the_front_door(emu, monkeypatch):
+    """b200r_corrupt_u8(spatter): the gate (B200R_ENOTSUP without B200R_SPATTER_WATER=1), then the whole severity-1 path -- normal layer
+    from shared draws, the two float32 Gaussian passes, threshold, water chain -- against the reference's cv2 chain on the float64
+    layer.  This is the comparison the gated GPU test (tests/test_spatter_water_gpu.py) will make, with its tolerance taken from here."""
+    import numpy as np
+    pytest.importorskip("cv2")
+    from util import synth_images, oracle_batch
+    images = synth_images(1, seed=51)
+    want, ext = oracle_batch(images, "spatter", 1)
+    monkeypatch.delenv("B200R_SPATTER_WATER", raising=False)
+    lib = emu["corrupt"]
+    rc, _ = _corrupt(lib, 17, 1, images, ext)
+    assert rc == -4 and b"B200R_SPATTER_WATER" in lib.b200r_last_error()           # B200R_ENOTSUP: the validated default
+    # the switch is read once per library instance: load a second copy with the variable set
+    import shutil
+    monkeypatch.setenv("B200R_SPATTER_WATER", "1")
+    so2 = str(emu.d / "libcorrupt_emu_water.so")
+    shutil.copy(str(emu.d / "libcorrupt_emu.so"), so2)
+    lib2 = C.CDLL(so2)
+    for sev, seed in ((1, 51), (2, 52), (3, 53)):
+        images = synth_images(1, seed=seed)
+        want, ext = oracle_batch(images, "spatter", sev)
+        rc, got = _corrupt(lib2, 17, sev, images, ext)
+        assert rc == 0, lib2.b200r_last_error()
+        diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+        print("spatter sev %d: %d differing bytes (%.2e), %.2e with |d| > 1, max %d" % (sev, np.count_nonzero(diff), (diff > 0).mean(), (diff > 1).mean(), diff.max()))
+        assert (diff > 1).mean() <= 1e-2
+        assert (got != images).mean() > 0.02
+
+
+@pytest.mark.parametrize("name,cid,sev", [("jpeg_compression", 14, 3), ("pixelate", 13, 2), ("spatter", 17, 4), ("gaussian_blur", 16, 2)])
+def test_validated_corruptions_from_source(emu, name, cid, sev):
+    """GPU-validated corruption kernels of the codec / stencil families, run from source through b200r_corrupt_u8 against the oracle
+    with the GPU tests' own bars (tests/test_corrupt_gpu.py): JPEG and pixelate byte-exact, the float stencils within 1 LSB."""
+    import numpy as np
+    from util import synth_images, oracle_batch
+    images = synth_images(1, seed=60 + cid)
+    want, ext = oracle_batch(images, name, sev)
+    rc, got = _corrupt(emu["corrupt"], cid, sev, images, ext)
+    assert rc == 0, emu["corrupt"].b200r_last_error()
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    if name in ("jpeg_compression", "pixelate"):
+        assert diff.max() == 0
+    elif name == "spatter":
+        assert (diff > 1).mean() <= 2e-3 and np.count_nonzero(diff) / diff.size <= 0.03
+    else:
+        assert diff.max() <= 1 and np.count_nonzero(diff) / diff.size <= 0.02

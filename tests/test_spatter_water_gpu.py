@@ -27,8 +27,10 @@ def test_spatter_water_branch(cuda, sev):
     got = _run(cuda, "spatter", sev, images, ext)
     diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
     # the liquid layer is float32 on the GPU and float64 in the reference: a pixel whose uint8 truncation differs can move a Canny
-    # edge by a pixel; everything downstream of identical edges is byte-exact (emulator test)
-    assert (diff > 1).mean() <= 1e-2, ((diff > 1).mean(), diff.max())
+    # edge by a pixel; everything downstream of identical edges is byte-exact.  On the host emulator the whole path through
+    # b200r_corrupt_u8 came out with ZERO differing bytes for severity 1-3 (tests/test_kernel_emulation_cpu.py), so expect 0 here too;
+    # the bar below only leaves room for the rare truncation flip
+    assert (diff > 1).mean() <= 2e-3, ((diff > 1).mean(), diff.max())
     assert (want != images).mean() > 0.02 and (got != images).mean() > 0.02
     # device RNG path: same statistics of the change, deterministic per seed
     d = torch.from_numpy(images).to(cuda)

@@ -475,3 +475,108 @@ def test_validated_corruptions_from_source(emu, name, cid, sev):
         assert (diff > 1).mean() <= 2e-3 and np.count_nonzero(diff) / diff.size <= 0.03
     else:
         assert diff.max() <= 1 and np.count_nonzero(diff) / diff.size <= 0.02
+
+
+# ---- 6. the native input-gradient pass of the token models: production host code + ops wrappers + emulated kernels -----------------------
+class _Facade:
+    """What robustart_b200._lib.load() returns in this test: every symbol resolved in the emulated libraries with the prototypes of
+    _lib.SIGNATURES attached (so a wrong ctypes signature or argument order in ops.py fails here, not on the GPU), and ONE Python
+    stand-in: b200r_linear, the tcgen05 GEMM, which no host emulator can run (split planes in, fp32 accumulate, split planes out)."""
+
+    def __init__(self, emu, names):
+        from robustart_b200 import _lib
+        self._libs = [emu[n] for n in names]
+        self._sig = _lib.SIGNATURES
+        self.calls = {}
+
+    def __getattr__(self, sym):
+        if sym.startswith("_"):
+            raise AttributeError(sym)
+        for lib in self._libs:
+            try:
+                fn = getattr(lib, sym)
+            except AttributeError:
+                continue
+            fn.restype, fn.argtypes = self._sig[sym]
+
+            def counted(*a, _fn=fn, _sym=sym):
+                self.calls[_sym] = self.calls.get(_sym, 0) + 1
+                return _fn(*a)
+            setattr(self, sym, counted)
+            return counted
+        raise AttributeError("symbol %s is in none of the emulated libraries" % sym)
+
+    @staticmethod
+    def b200r_last_error():
+        return b"(emulated library)"
+
+    @staticmethod
+    def _view(ptr, shape, dtype):
+        n = 1
+        for d in shape:
+            n *= d
+        buf = (C.c_char * (n * torch.empty(0, dtype=dtype).element_size())).from_address(ptr)
+        return torch.frombuffer(buf, dtype=dtype).view(shape)
+
+    def b200r_linear(self, x, w, scale, bias, res, out, out_f32, m, k, nout, act, passes, stream):
+        self.calls["b200r_linear"] = self.calls.get("b200r_linear", 0) + 1
+        assert scale is None and passes == 3
+        y = merge(self._view(x, (2, m, k), torch.int16)).double() @ merge(self._view(w, (2, nout, k), torch.int16)).double().t()
+        if bias is not None:
+            y = y + self._view(bias, (nout,), torch.float32).double()
+        y = y.float()
+        y = {0: lambda v: v, 3: lambda v: F.gelu(v, approximate="tanh"), 4: F.gelu, 6: torch.tanh}[act](y)
+        if res is not None:
+            y = y + merge(self._view(res, (2, m, nout), torch.int16))
+        if out_f32 is not None:
+            self._view(out_f32, (m, nout), torch.float32).copy_(y)
+        if out is not None:
+            self._view(out, (2, m, nout), torch.int16).copy_(split(y))
+        return 0
+
+
+@pytest.mark.parametrize("family", ["mixer", "vit"])
+def test_native_token_gradient_pass_end_to_end(emu, monkeypatch, family):
+    """nets.Mixer / nets.ViT .forward_saved + .input_grad exactly as in production -- host code, ops.py wrappers, ctypes prototypes, and
+    every kernel except the GEMM running from its own source on the emulator -- against torch.autograd on the functional twin."""
+    import contextlib
+    from robustart_b200 import _lib, nets, ops, torch_models as TM
+    facade = _Facade(emu, ["token_layers", "token_backward", "layers", "backward_layers", "loss_metrics"])
+    monkeypatch.setattr(_lib, "_lib", facade)
+
+    def need(t, dtype, name):
+        assert isinstance(t, torch.Tensor) and t.dtype == dtype and t.is_contiguous(), name
+    monkeypatch.setattr(ops, "_need_cuda", need)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    n, img, patch, classes, depth = 2, 32, 8, 16, 2
+    if family == "mixer":
+        dim = 64
+        sd = nets.random_token_state_dict(nets.mixer_spec(depth=depth, dim=dim, patch=patch, img=img, classes=classes), 2)
+        model = nets.Mixer(sd, "cpu", passes=3, depth=depth, dim=dim, patch=patch)
+        twin = TM.Mixer(sd, depth=depth, dim=dim, patch=patch)
+    else:
+        dim, heads = 128, 2                                              # head_dim 64: the only one the attention kernels take
+        sd = nets.random_token_state_dict(nets.vit_spec(depth=depth, dim=dim, mlp=2 * dim, patch=patch, img=img, classes=classes, rep=dim), 2)
+        model = nets.ViT(sd, "cpu", passes=3, depth=depth, dim=dim, heads=heads, patch=patch)
+        twin = TM.ViT(sd, depth=depth, dim=dim, heads=heads, patch=patch)
+    torch.manual_seed(5)
+    x01 = torch.rand(n, 3, img, img)
+    y = torch.randint(0, classes, (n,))
+    logits, saved = model.forward_saved(x01)
+    _, dlogits = ops.ce_loss_grad(logits, y)
+    g = model.input_grad(dlogits, saved)
+    m, s = torch.tensor(MEAN, dtype=torch.float64).view(1, 3, 1, 1), torch.tensor(STD, dtype=torch.float64).view(1, 3, 1, 1)
+    xd = x01.double().requires_grad_(True)
+    lt = twin.double()((xd - m) / s)
+    (want,) = torch.autograd.grad(F.cross_entropy(lt, y, reduction="sum"), xd)
+    assert (logits.double() - lt.detach()).abs().max().item() < 1e-3
+    assert (model.forward(x01).double() - lt.detach()).abs().max().item() < 1e-3      # the fused-activation forward agrees too
+    scale = want.abs().max().item()
+    err = (g.double() - want).abs().max().item()
+    assert err < 2e-3 * scale, (err, scale)
+    assert F.cosine_similarity(g.double().flatten(), want.flatten(), dim=0).item() > 0.99999
+    c = facade.calls
+    assert c["b200r_layernorm_bwd"] == 2 * depth + 1 and c["b200r_patch_scatter_f32"] == 1
+    assert c.get("b200r_attention_bwd", 0) == (depth if family == "vit" else 0)
+    assert c["b200r_act_bwd_planes"] == (2 * depth if family == "mixer" else depth + 1)

@@ -115,25 +115,48 @@ _PIL_RESIZE_TYPES = {'pil-bilinear': 'bilinear', 'pil-nearest': 'nearest', 'pil-
                      'pil-cubic': 'bicubic', 'pil-lanczos': 'lanczos'}
 
 
+_CV_RESIZE_TYPES = {'opencv-nearest': 'nearest', 'opencv-bilinear': 'bilinear'}
+
+
+def _cv_resize_enabled():
+    # csrc/resize_cv.cu is checked against cv2.resize on the host emulator only so far: opt-in until it has run on a GPU
+    import os
+    return os.environ.get('B200R_CV_RESIZE', '0') == '1'
+
+
+def _imagenet_s_resize(batch, size_hw, resize_type, crop=None):
+    """One launch: Image.resize (pil-*) or cv2.resize (opencv-*) of a uint8 NHWC CUDA batch, optionally cropped."""
+    if resize_type in _CV_RESIZE_TYPES:
+        return _ops.resize_cv_u8(batch, size_hw, _CV_RESIZE_TYPES[resize_type], crop=crop)
+    return _ops.resize_u8(batch, size_hw, _PIL_RESIZE_TYPES[resize_type], crop=crop)
+
+
 def add_noise_for_imagenet_s(image, decoder_type='pil', resize_type='pil-bilinear', transform_type='val', size=224):
     """ImageTransfer(..., return_online=True).getimage() (imagenet_s_gen.py:83-141) for the PIL decoder and the six `pil-*`
     resize types, transform 'val': decode on the host (file parsing, as the reference), then Image.resize to
     (size*8/7, size*8/7) and the centre crop as ONE bit-exact resize kernel launch (b200r_resize_u8).  `image` is a file
     path (the reference's contract) or an already decoded uint8 [h, w, 3] / [n, h, w, 3] array or CUDA tensor.
     transform 'train' = the reference's random resized crop (parameters from Python's `random`) + Image.resize to (size, size).
-    The OpenCV / ffmpeg decoders and the opencv-* resize types are not implemented."""
-    if decoder_type != 'pil':
+    With B200R_CV_RESIZE=1 also the `opencv` decoder (cv2.imdecode on the host + BGR->RGB, imagenet_s_gen.py:193-202) and the
+    `opencv-nearest` / `opencv-bilinear` resize types (cv2.resize bit for bit, b200r_resize_cv_u8).  The ffmpeg decoder and
+    opencv-area / -cubic / -lanczos are not implemented."""
+    cv_ok = _cv_resize_enabled()
+    if decoder_type != 'pil' and not (cv_ok and decoder_type == 'opencv'):
         raise NotImplementedError("imagenet-s decoder_type=%r: only the PIL decoder is implemented" % decoder_type)
-    if resize_type not in _PIL_RESIZE_TYPES:
+    if resize_type not in _PIL_RESIZE_TYPES and not (cv_ok and resize_type in _CV_RESIZE_TYPES):
         raise NotImplementedError("imagenet-s resize_type=%r: only the pil-* resize types are implemented" % resize_type)
     if transform_type not in ('val', 'train'):
         raise NotImplementedError("imagenet-s transform_type=%r: 'val' (resize + centre crop) and 'train' (random resized crop)" % transform_type)
     if isinstance(image, str):
-        from PIL import Image
-        with Image.open(image) as im:
-            image = np.array(im.convert('RGB'))
+        if decoder_type == 'opencv':
+            import cv2
+            image = cv2.cvtColor(cv2.imdecode(np.fromfile(image, dtype=np.uint8), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+        else:
+            from PIL import Image
+            with Image.open(image) as im:
+                image = np.array(im.convert('RGB'))
     if transform_type == 'train':
-        # imagenet_s_gen.py:120-129: crop the box get_params draws from Python's `random`, then Image.resize to (size, size)
+        # imagenet_s_gen.py:120-129: crop the box get_params draws from Python's `random`, then resize to (size, size)
         single = image.ndim == 3 if not isinstance(image, torch.Tensor) else image.dim() == 3
         batch = image if not single else image[None]
         outs = []
@@ -144,7 +167,7 @@ def add_noise_for_imagenet_s(image, decoder_type='pil', resize_type='pil-bilinea
                 torch.device('cuda', torch.cuda.current_device())))
             if not d.is_cuda:
                 raise TypeError("torch input must live on the GPU")
-            outs.append(_ops.resize_u8(d.contiguous()[None], (size, size), _PIL_RESIZE_TYPES[resize_type])[0])
+            outs.append(_imagenet_s_resize(d.contiguous()[None], (size, size), resize_type)[0])
         out = torch.stack(outs)
         if not isinstance(image, torch.Tensor):
             out = out.cpu().numpy()
@@ -155,14 +178,14 @@ def add_noise_for_imagenet_s(image, decoder_type='pil', resize_type='pil-bilinea
         if not image.is_cuda:
             raise TypeError("torch input must live on the GPU")
         batch = image if image.dim() == 4 else image[None]
-        out = _ops.resize_u8(batch.contiguous(), (first, first), _PIL_RESIZE_TYPES[resize_type], crop=(i, i, size, size))
+        out = _imagenet_s_resize(batch.contiguous(), (first, first), resize_type, crop=(i, i, size, size))
         return out if image.dim() == 4 else out[0]
     arr = np.ascontiguousarray(image)
     if arr.dtype != np.uint8 or arr.ndim not in (3, 4) or arr.shape[-1] != 3:
         raise ValueError("imagenet-s expects a file path or a uint8 array of shape ([n,] h, w, 3)")
     dev = torch.device('cuda', torch.cuda.current_device())
     d = torch.from_numpy(arr if arr.ndim == 4 else arr[None]).to(dev)
-    out = _ops.resize_u8(d, (first, first), _PIL_RESIZE_TYPES[resize_type], crop=(i, i, size, size)).cpu().numpy()
+    out = _imagenet_s_resize(d, (first, first), resize_type, crop=(i, i, size, size)).cpu().numpy()
     return out if arr.ndim == 4 else out[0]
 
 

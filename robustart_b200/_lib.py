@@ -137,6 +137,7 @@ SIGNATURES.update({
     "b200r_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_stream]),
     "b200r_tokens_to_channels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_channels_to_tokens_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_resize_cv_u8": (C.c_int, [c_u8p, c_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, c_f32p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, c_stream]),
     "b200r_act_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, c_stream]),
     "b200r_act_bwd_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, c_stream]),

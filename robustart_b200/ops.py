@@ -411,6 +411,25 @@ def resize_u8(images, size, filter="bilinear", crop=None, out=None):
     return out
 
 
+CV_INTERPOLATIONS = {"nearest": 0, "bilinear": 1}      # cv2.INTER_NEAREST, cv2.INTER_LINEAR
+
+
+def resize_cv_u8(images, size, interpolation="bilinear", crop=None, out=None):
+    """cv2.resize(img, (size[1], size[0]), interpolation=INTER_NEAREST | INTER_LINEAR) of every image of a uint8 NHWC CUDA batch,
+    bit-exact (csrc/resize_cv.cu); crop = (y0, x0, h, w) returns that window of the resized image (only it is computed)."""
+    _need_cuda(images, torch.uint8, "images")
+    n, hin, win, c = images.shape
+    assert c == 3
+    hout, wout = int(size[0]), int(size[1])
+    y0, x0, ch, cw = crop if crop is not None else (0, 0, hout, wout)
+    if out is None:
+        out = torch.empty((n, ch, cw, 3), dtype=torch.uint8, device=images.device)
+    with torch.cuda.device(images.device):
+        _lib.check(_lib.load().b200r_resize_cv_u8(images.data_ptr(), out.data_ptr(), n, hin, win, hout, wout, CV_INTERPOLATIONS[interpolation],
+                                                  y0, x0, ch, cw, _stream()))
+    return out
+
+
 def resize_center_crop_u8(images, resize=256, crop=224, filter="bilinear"):
     """torchvision Resize(resize) (short side, aspect kept: long side = int(resize * long / short)) + CenterCrop(crop) on a uint8
     NHWC batch -- the eval transform of imagenet_dataloader.py:74-80, antialiased PIL bilinear as torchvision does on PIL images."""

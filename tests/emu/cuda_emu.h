@@ -169,7 +169,7 @@ template <class T> inline cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute
 
 // ---- host-side plumbing of common.cuh that needs a device ------------------------------------------------------------------
 #ifndef EMU_API_TU            // api.cu defines these two itself
-inline int b200r_num_sms() { return 2; }
+inline int b200r_num_sms() { return 1; }     // grid caps are multiples of the SM count: keep the emulated grids small
 inline thread_local char emu_error[512];
 inline void b200r_set_error(const char* fmt, ...) {
   va_list ap;

@@ -549,7 +549,7 @@ def test_native_token_gradient_pass_end_to_end(emu, monkeypatch, family):
     monkeypatch.setattr(ops, "_need_cuda", need)
     monkeypatch.setattr(ops, "_stream", lambda: None)
     monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
-    n, img, patch, classes, depth = 2, 32, 8, 16, 2
+    n, img, patch, classes, depth = 2, 32, 8, 16, 1
     if family == "mixer":
         dim = 64
         sd = nets.random_token_state_dict(nets.mixer_spec(depth=depth, dim=dim, patch=patch, img=img, classes=classes), 2)
@@ -580,3 +580,55 @@ def test_native_token_gradient_pass_end_to_end(emu, monkeypatch, family):
     assert c["b200r_layernorm_bwd"] == 2 * depth + 1 and c["b200r_patch_scatter_f32"] == 1
     assert c.get("b200r_attention_bwd", 0) == (depth if family == "vit" else 0)
     assert c["b200r_act_bwd_planes"] == (2 * depth if family == "mixer" else depth + 1)
+
+
+# ---- 7. cv2.resize restated (csrc/resize_cv.cu), and the ImageNet-S host path that calls it ------------------------------------------------
+@pytest.mark.parametrize("hin,win,hout,wout", [(75, 100, 64, 64), (20, 24, 64, 48), (64, 64, 64, 64), (1, 9, 8, 8), (90, 60, 45, 30)])
+def test_resize_cv_kernel_matches_cv2(emu, hin, win, hout, wout):
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    lib = emu["resize_cv"]
+    rng = np.random.RandomState(hin)
+    img = rng.randint(0, 256, (2, hin, win, 3), dtype=np.uint8)
+    x = torch.from_numpy(img)
+    for code, inter in ((1, cv2.INTER_LINEAR), (0, cv2.INTER_NEAREST)):
+        for (oy0, ox0, ch, cw) in [(0, 0, hout, wout), (hout // 4, wout // 8, hout // 2, wout // 2)]:
+            out = torch.full((2, ch, cw, 3), 99, dtype=torch.uint8)
+            _ok(lib.b200r_resize_cv_u8(_p(x), _p(out), 2, hin, win, hout, wout, code, oy0, ox0, ch, cw, None))
+            for i in range(2):
+                want = cv2.resize(img[i], (wout, hout), interpolation=inter)[oy0:oy0 + ch, ox0:ox0 + cw]
+                assert np.array_equal(out[i].numpy(), want), (code, i)
+    assert lib.b200r_resize_cv_u8(_p(x), _p(out), 2, hin, win, hout, wout, 2, 0, 0, hout, wout, None) != 0          # INTER_CUBIC: not here
+    assert lib.b200r_resize_cv_u8(_p(x), _p(out), 2, hin, win, hout, wout, 1, 1, 0, hout, wout, None) != 0          # crop outside
+
+
+def test_imagenet_s_opencv_types_through_the_plugin(emu, monkeypatch, tmp_path):
+    """AddNoise('imagenet-s') with decoder 'opencv' and the opencv-* resize types (imagenet_s_gen.py:138-148,193-202): host code + ops
+    wrapper + the kernel from source, against cv2 itself; off unless B200R_CV_RESIZE=1."""
+    import contextlib
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    from robustart_b200 import _lib, ops
+    from RobustART.noise import AddNoise
+    from RobustART.noise.utils import add_noise_utils as U
+    img = np.random.RandomState(3).randint(0, 256, (60, 80, 3), dtype=np.uint8)
+    path = str(tmp_path / "a.png")
+    cv2.imwrite(path, cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+    gen = AddNoise("imagenet-s")
+    gen.set_config(resize_type="opencv-bilinear", decoder_type="opencv")
+    monkeypatch.delenv("B200R_CV_RESIZE", raising=False)
+    with pytest.raises(NotImplementedError):
+        gen.add_noise(path)
+    monkeypatch.setenv("B200R_CV_RESIZE", "1")
+    facade = _Facade(emu, ["resize_cv"])
+    monkeypatch.setattr(_lib, "_lib", facade)
+    monkeypatch.setattr(ops, "_need_cuda", lambda t, dtype, name: None)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(U.torch, "device", lambda *a: torch.zeros(0).device)          # 'cuda:0' -> the host, in this test only
+    for rt, inter in (("opencv-bilinear", cv2.INTER_LINEAR), ("opencv-nearest", cv2.INTER_NEAREST)):
+        gen.set_config(resize_type=rt)
+        out = gen.add_noise(path)
+        want = cv2.resize(img, (256, 256), interpolation=inter)[16:240, 16:240]
+        assert out.shape == (224, 224, 3) and np.array_equal(out, want), rt

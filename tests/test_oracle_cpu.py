@@ -239,3 +239,22 @@ def test_spatter_water_restatement():
         assert np.array_equal(W.blur3_u8(f), cv2.blur(f, (3, 3)))
     flat = np.full((16, 16), 7, np.uint8)
     assert np.array_equal(W.equalize_hist(flat), cv2.equalizeHist(flat))   # single-bin image: cv2 fills with the bin index
+
+
+def test_cv_resize_restatement():
+    """oracle/cv_resize.py (the algorithm csrc/resize_cv.cu follows) against cv2.resize itself -- the call the reference's ImageNet-S
+    generator makes for the opencv-* types (imagenet_s_gen.py:28-34,120-148): bit-exact, any scale direction."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import cv_resize as R
+    rng = np.random.RandomState(0)
+    sizes = [(375, 500, 256, 256), (64, 64, 256, 256), (100, 80, 128, 128), (224, 224, 256, 256), (480, 640, 256, 256), (17, 31, 64, 48),
+             (300, 200, 256, 256), (31, 500, 256, 256), (256, 256, 256, 256), (2, 2, 8, 8), (1, 5, 4, 4), (37, 1, 16, 16), (333, 500, 299, 299),
+             (500, 333, 64, 64), (97, 113, 111, 89)]
+    for (h, w, ho, wo) in sizes:
+        img = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(R.resize_linear(img, wo, ho), cv2.resize(img, (wo, ho), interpolation=cv2.INTER_LINEAR)), (h, w, ho, wo)
+        assert np.array_equal(R.resize_nearest(img, wo, ho), cv2.resize(img, (wo, ho), interpolation=cv2.INTER_NEAREST)), (h, w, ho, wo)
+    img = rng.randint(0, 256, (375, 500, 3), dtype=np.uint8)
+    for rt, inter in (("opencv-bilinear", cv2.INTER_LINEAR), ("opencv-nearest", cv2.INTER_NEAREST)):
+        full = cv2.resize(img, (256, 256), interpolation=inter)
+        assert np.array_equal(R.imagenet_s_val(img, rt), full[16:240, 16:240])

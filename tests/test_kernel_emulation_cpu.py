@@ -107,6 +107,15 @@ def _rewrite(src: str) -> str:
     return "".join(out)
 
 
+@pytest.fixture(autouse=True)
+def _single_torch_thread():
+    """torch's OpenMP workers spin after every parallel region and fight the emulator's thread-per-CUDA-thread blocks for cores."""
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(n)
+
+
 class _EmuLibs:
     """Compiles csrc/<name>.cu for the host on first use."""
 

@@ -1,9 +1,10 @@
-"""cv2.resize for uint8 images, INTER_NEAREST and INTER_LINEAR, restated -- TEST INFRASTRUCTURE ONLY (see oracle/imagenet_c.py).
+"""cv2.resize for uint8 images, INTER_NEAREST, INTER_LINEAR and INTER_AREA, restated -- TEST INFRASTRUCTURE ONLY (see oracle/imagenet_c.py).
 
 The reference's ImageNet-S generator calls cv2.resize for the `opencv-*` resize types (RobustART/noise/utils/imagenet_s_gen.py:
 28-34,120-148).  OpenCV is a third-party dependency of the reference; it is installed in this container (4.13.0), so this
 restatement of imgproc/resize.cpp (resizeNN; resizeGeneric_ with HResizeLinear / VResizeLinear on 11-bit fixed-point
-coefficients) is pinned against cv2.resize itself: bit-exact for up- and down-scaling, degenerate sizes included
+coefficients; INTER_AREA's three regimes: integer factors -> resizeAreaFast_, both axes shrinking -> resizeArea_ on
+computeResizeAreaTab weights, otherwise the linear kernel on "area mode" coefficients) is pinned against cv2.resize itself: bit-exact for up- and down-scaling, degenerate sizes included
 (tests/test_oracle_cpu.py::test_cv_resize_restatement).  csrc/resize_cv.cu follows this file.
 """
 import numpy as np
@@ -57,14 +58,94 @@ def resize_nearest(img, wout, hout):
     return img[ys][:, xs]
 
 
+def area_linear_coeffs(nin, nout, clamp):
+    """resize.cpp, area_mode branch of the linear coefficient loop (INTER_AREA when an axis grows)."""
+    inv = float(nout) / float(nin)
+    scale = 1.0 / inv
+    idx = np.zeros(nout, np.int64)
+    w = np.zeros((nout, 2), np.int64)
+    for d in range(nout):
+        s = int(np.floor(d * scale))
+        f = np.float32((d + 1) - (s + 1) * inv)
+        f = np.float32(0) if f <= 0 else np.float32(f - np.floor(f))
+        if clamp:
+            if s < 0:
+                s, f = 0, np.float32(0)
+            if s >= nin - 1:
+                s, f = nin - 1, np.float32(0)
+        idx[d] = s
+        w[d, 0] = int(np.rint(np.float32((np.float32(1) - f) * np.float32(ONE))))
+        w[d, 1] = int(np.rint(np.float32(f * np.float32(ONE))))
+    return idx, w
+
+
+def _two_tap(img, wout, hout, coeffs):
+    hin, win, _ = img.shape
+    xi, xa = coeffs(win, wout, True)
+    yi, ya = coeffs(hin, hout, False)
+    I = img.astype(np.int64)
+    x1 = np.minimum(xi + 1, win - 1)
+    rows = I[:, xi, :] * xa[:, 0][None, :, None] + I[:, x1, :] * xa[:, 1][None, :, None]
+    S0, S1 = rows[np.clip(yi, 0, hin - 1)], rows[np.clip(yi + 1, 0, hin - 1)]
+    b0, b1 = ya[:, 0][:, None, None], ya[:, 1][:, None, None]
+    return np.clip((((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2, 0, 255).astype(np.uint8)
+
+
+def area_tab(ssize, dsize, scale):
+    """computeResizeAreaTab: (dst index, src index, float32 weight) in OpenCV's order."""
+    tab = []
+    for d in range(dsize):
+        f1 = d * scale
+        f2 = f1 + scale
+        cell = min(scale, ssize - f1)
+        s1, s2 = int(np.ceil(f1)), int(np.floor(f2))
+        s2 = min(s2, ssize - 1)
+        s1 = min(s1, s2)
+        if s1 - f1 > 1e-3:
+            tab.append((d, s1 - 1, np.float32((s1 - f1) / cell)))
+        for sx in range(s1, s2):
+            tab.append((d, sx, np.float32(1.0 / cell)))
+        if f2 - s2 > 1e-3:
+            tab.append((d, s2, np.float32(min(min(f2 - s2, 1.), cell) / cell)))
+    return tab
+
+
+def resize_area(img, wout, hout):
+    """cv2.resize(..., interpolation=INTER_AREA)."""
+    hin, win, C = img.shape
+    sx, sy = _scale(win, wout), _scale(hin, hout)
+    if not (sx >= 1 and sy >= 1):
+        return _two_tap(img, wout, hout, area_linear_coeffs)
+    kx, ky = int(sx), int(sy)
+    if abs(sx - kx) < np.finfo(np.float64).eps and abs(sy - ky) < np.finfo(np.float64).eps:      # resizeAreaFast_
+        I = img.astype(np.int64)[:hout * ky, :wout * kx].reshape(hout, ky, wout, kx, C).sum((1, 3))
+        if kx == 2 and ky == 2:
+            return ((I + 2) >> 2).astype(np.uint8)
+        return np.clip(np.rint(I.astype(np.float32) * np.float32(1.0 / (kx * ky))), 0, 255).astype(np.uint8)
+    xtab, ytab = area_tab(win, wout, sx), area_tab(hin, hout, sy)
+    I = img.astype(np.float32)
+    rows = {}
+    sums = np.zeros((hout, wout, C), np.float32)
+    started = set()
+    for (dy, sy_, beta) in ytab:
+        if sy_ not in rows:
+            b = np.zeros((wout, C), np.float32)
+            for (dx, sx_, a) in xtab:
+                b[dx] = b[dx] + I[sy_, sx_] * a
+            rows[sy_] = b
+        sums[dy] = beta * rows[sy_] if dy not in started else sums[dy] + beta * rows[sy_]
+        started.add(dy)
+    return np.clip(np.rint(sums), 0, 255).astype(np.uint8)
+
+
 def resize(img, wout, hout, interpolation):
-    return {"nearest": resize_nearest, "bilinear": resize_linear}[interpolation](img, wout, hout)
+    return {"nearest": resize_nearest, "bilinear": resize_linear, "area": resize_area}[interpolation](img, wout, hout)
 
 
 def imagenet_s_val(img, resize_type, size=224):
     """ImageTransfer.image_resize, transform 'val', opencv-* types (imagenet_s_gen.py:138-148): resize to int(size*8/7) squared,
     then the centre crop."""
     first = int(size * 8 / 7)
-    full = resize(img, first, first, {"opencv-nearest": "nearest", "opencv-bilinear": "bilinear"}[resize_type])
+    full = resize(img, first, first, {"opencv-nearest": "nearest", "opencv-bilinear": "bilinear", "opencv-area": "area"}[resize_type])
     d = int(round((first - size) / 2.))
     return full[d:d + size, d:d + size]

@@ -1,11 +1,14 @@
-// cv2.resize for uint8 NHWC batches, INTER_NEAREST and INTER_LINEAR, bit for bit (OpenCV imgproc/resize.cpp restated in
-// oracle/cv_resize.py and pinned there against cv2 4.13): the `opencv-nearest` / `opencv-bilinear` resize types of the reference's
+// cv2.resize for uint8 NHWC batches, INTER_NEAREST, INTER_LINEAR and INTER_AREA, bit for bit (OpenCV imgproc/resize.cpp restated in
+// oracle/cv_resize.py and pinned there against cv2 4.13): the `opencv-nearest` / `opencv-bilinear` / `opencv-area` types of the reference's
 // ImageNet-S generator (RobustART/noise/utils/imagenet_s_gen.py:28-34,120-148), with the centre crop of the 'val' transform fused
 // (only the cropped window is produced).
 //   linear: coordinates f = float((d + 0.5) * scale - 0.5), scale = 1 / (dst / src) in double; weights cvRound(w * 2048);
 //           horizontal pass  S = p[sx] * a0 + p[sx + 1] * a1   (weight zeroed where the pair leaves the row)
 //           vertical pass    (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2   (row indices clipped, weights kept)
 //   nearest: src = min(floor(d * scale), size - 1)
+//   area:    integer factors on both axes -> block sums, (s + 2) >> 2 for 2x2, else cvRound(float(s) * float(1 / (kx ky)));
+//            both axes shrinking -> computeResizeAreaTab weights (float32), rows accumulated in OpenCV's order with one rounding per
+//            multiply and per add; an axis growing -> the linear kernel on the "area mode" coefficients
 // One thread per output pixel (3 channels), weights recomputed per thread (a dozen flops against four 3-byte gathers): the kernel
 // is bound by the gathers, which hit L1/L2 for every down-scaling ratio the eval transform sees.
 // STATUS: checked from source on the host emulator against cv2.resize (tests/test_kernel_emulation_cpu.py); not yet run on a GPU.
@@ -32,21 +35,121 @@ __device__ __forceinline__ Tap linear_tap(int d, double scale, int nin, bool cla
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-template <bool LINEAR>
+// INTER_AREA with a growing axis: resize.cpp's area_mode coefficients
+__device__ __forceinline__ Tap area_linear_tap(int d, double scale, double inv, int nin, bool clamp) {
+  int s = (int)floor((double)d * scale);
+  float f = (float)((double)(d + 1) - (double)(s + 1) * inv);
+  f = f <= 0.f ? 0.f : __fsub_rn(f, floorf(f));
+  if (clamp) {
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= nin - 1) { s = nin - 1; f = 0.f; }
+  }
+  Tap t;
+  t.s = s;
+  t.w0 = (int)rintf(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  t.w1 = (int)rintf(__fmul_rn(f, 2048.f));
+  return t;
+}
+
+// computeResizeAreaTab for one destination index: an optional partial first cell, whole cells [s1, s2), an optional partial last cell
+struct AreaTaps { int s1, s2; float wfirst, wmid, wlast; bool first, last; };
+__device__ __forceinline__ AreaTaps area_taps(int d, double scale, int nin) {
+  const double f1 = (double)d * scale, f2 = f1 + scale;
+  const double cell = fmin(scale, (double)nin - f1);
+  int s1 = (int)ceil(f1), s2 = (int)floor(f2);
+  s2 = min(s2, nin - 1);
+  s1 = min(s1, s2);
+  AreaTaps t;
+  t.s1 = s1; t.s2 = s2;
+  t.first = (double)s1 - f1 > 1e-3;
+  t.wfirst = (float)(((double)s1 - f1) / cell);
+  t.wmid = (float)(1.0 / cell);
+  t.last = f2 - (double)s2 > 1e-3;
+  t.wlast = (float)(fmin(fmin(f2 - (double)s2, 1.0), cell) / cell);
+  return t;
+}
+
+// both axes shrinking (MODE_TAB) or integer factors (MODE_FAST)
+template <bool FAST>
+__global__ void __launch_bounds__(kThreads) resize_area_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n, int hin, int win,
+                                                                double sy, double sx, int oy0, int ox0, int ch, int cw) {
+  const size_t total = (size_t)n * ch * cw;
+  const int kx = (int)sx, ky = (int)sy;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int x = (int)(t % cw) + ox0, y = (int)((t / cw) % ch) + oy0, im = (int)(t / ((size_t)cw * ch));
+    const uint8_t* src = in + (size_t)im * hin * win * 3;
+    uint8_t* dst = out + t * 3;
+    if (FAST) {
+      int s[3] = {0, 0, 0};
+      for (int j = 0; j < ky; ++j) {
+        const uint8_t* p = src + ((size_t)(y * ky + j) * win + (size_t)x * kx) * 3;
+        for (int i = 0; i < kx; ++i) { s[0] += p[3 * i]; s[1] += p[3 * i + 1]; s[2] += p[3 * i + 2]; }
+      }
+      if (kx == 2 && ky == 2) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dst[c] = (uint8_t)((s[c] + 2) >> 2);
+      } else {
+        const float scale = (float)(1.0 / (double)(kx * ky));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dst[c] = (uint8_t)clampi((int)rintf(__fmul_rn((float)s[c], scale)), 0, 255);
+      }
+      continue;
+    }
+    const AreaTaps tx = area_taps(x, sx, win), ty = area_taps(y, sy, hin);
+    float sum[3] = {0.f, 0.f, 0.f};
+    bool started = false;
+    const int ny = (ty.first ? 1 : 0) + (ty.s2 - ty.s1) + (ty.last ? 1 : 0);
+    for (int k = 0; k < ny; ++k) {
+      int yy; float beta;
+      if (ty.first && k == 0) { yy = ty.s1 - 1; beta = ty.wfirst; }
+      else {
+        const int kk = k - (ty.first ? 1 : 0);
+        if (kk < ty.s2 - ty.s1) { yy = ty.s1 + kk; beta = ty.wmid; }
+        else { yy = ty.s2; beta = ty.wlast; }
+      }
+      const uint8_t* row = src + (size_t)yy * win * 3;
+      float b[3] = {0.f, 0.f, 0.f};
+      if (tx.first) {
+        const uint8_t* p = row + (size_t)(tx.s1 - 1) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) b[c] = __fadd_rn(b[c], __fmul_rn((float)p[c], tx.wfirst));
+      }
+      for (int xx = tx.s1; xx < tx.s2; ++xx) {
+        const uint8_t* p = row + (size_t)xx * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) b[c] = __fadd_rn(b[c], __fmul_rn((float)p[c], tx.wmid));
+      }
+      if (tx.last) {
+        const uint8_t* p = row + (size_t)tx.s2 * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) b[c] = __fadd_rn(b[c], __fmul_rn((float)p[c], tx.wlast));
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sum[c] = started ? __fadd_rn(sum[c], __fmul_rn(beta, b[c])) : __fmul_rn(beta, b[c]);
+      started = true;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dst[c] = (uint8_t)clampi((int)rintf(sum[c]), 0, 255);
+  }
+}
+
+// MODE 0 nearest, 1 linear, 2 linear on the area-mode coefficients
+template <int MODE>
 __global__ void __launch_bounds__(kThreads) resize_cv_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n, int hin, int win,
-                                                              double sy, double sx, int oy0, int ox0, int ch, int cw) {
+                                                              double sy, double sx, double iy, double ix, int oy0, int ox0, int ch, int cw) {
   const size_t total = (size_t)n * ch * cw;
   for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
     const int x = (int)(t % cw), y = (int)((t / cw) % ch), im = (int)(t / ((size_t)cw * ch));
     const uint8_t* src = in + (size_t)im * hin * win * 3;
     uint8_t* dst = out + t * 3;
-    if (!LINEAR) {
+    if (MODE == 0) {
       const int xs = min((int)floor((double)(x + ox0) * sx), win - 1), ys = min((int)floor((double)(y + oy0) * sy), hin - 1);
       const uint8_t* p = src + ((size_t)ys * win + xs) * 3;
       dst[0] = p[0]; dst[1] = p[1]; dst[2] = p[2];
       continue;
     }
-    const Tap tx = linear_tap(x + ox0, sx, win, true), ty = linear_tap(y + oy0, sy, hin, false);
+    const Tap tx = MODE == 2 ? area_linear_tap(x + ox0, sx, ix, win, true) : linear_tap(x + ox0, sx, win, true);
+    const Tap ty = MODE == 2 ? area_linear_tap(y + oy0, sy, iy, hin, false) : linear_tap(y + oy0, sy, hin, false);
     const int x1 = min(tx.s + 1, win - 1);
     const uint8_t* r0 = src + (size_t)clampi(ty.s, 0, hin - 1) * win * 3;
     const uint8_t* r1 = src + (size_t)clampi(ty.s + 1, 0, hin - 1) * win * 3;
@@ -65,18 +168,29 @@ extern "C" int b200r_resize_cv_u8(const uint8_t* in, uint8_t* out, int n, int hi
                                   int ox0, int ch, int cw, b200r_stream_t stream) {
   B200R_CHECK_ARG(in && out, "null pointer");
   B200R_CHECK_ARG(n > 0 && hin > 0 && win > 0 && hout > 0 && wout > 0, "bad shape");
-  B200R_CHECK_ARG(interpolation == B200R_CV_INTER_NEAREST || interpolation == B200R_CV_INTER_LINEAR,
-                  "interpolation %d not supported (cv2.INTER_NEAREST = 0, cv2.INTER_LINEAR = 1)", interpolation);
+  B200R_CHECK_ARG(interpolation == B200R_CV_INTER_NEAREST || interpolation == B200R_CV_INTER_LINEAR || interpolation == B200R_CV_INTER_AREA,
+                  "interpolation %d not supported (cv2.INTER_NEAREST = 0, cv2.INTER_LINEAR = 1, cv2.INTER_AREA = 3)", interpolation);
   B200R_CHECK_ARG(oy0 >= 0 && ox0 >= 0 && ch > 0 && cw > 0 && oy0 + ch <= hout && ox0 + cw <= wout, "crop window outside the resized image");
-  const double sy = 1.0 / ((double)hout / (double)hin), sx = 1.0 / ((double)wout / (double)win);
+  const double iy = (double)hout / (double)hin, ix = (double)wout / (double)win;      // resize.cpp: inv_scale, then scale = 1 / inv_scale
+  const double sy = 1.0 / iy, sx = 1.0 / ix;
   const size_t total = (size_t)n * ch * cw;
   size_t blocks = (total + kThreads - 1) / kThreads;
   const size_t cap = (size_t)b200r_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  if (interpolation == B200R_CV_INTER_LINEAR)
-    resize_cv_kernel<true><<<(unsigned)blocks, kThreads, 0, as_stream(stream)>>>(in, out, n, hin, win, sy, sx, oy0, ox0, ch, cw);
-  else
-    resize_cv_kernel<false><<<(unsigned)blocks, kThreads, 0, as_stream(stream)>>>(in, out, n, hin, win, sy, sx, oy0, ox0, ch, cw);
+  const unsigned g = (unsigned)blocks;
+  cudaStream_t st = as_stream(stream);
+  if (interpolation == B200R_CV_INTER_LINEAR) {
+    resize_cv_kernel<1><<<g, kThreads, 0, st>>>(in, out, n, hin, win, sy, sx, iy, ix, oy0, ox0, ch, cw);
+  } else if (interpolation == B200R_CV_INTER_NEAREST) {
+    resize_cv_kernel<0><<<g, kThreads, 0, st>>>(in, out, n, hin, win, sy, sx, iy, ix, oy0, ox0, ch, cw);
+  } else if (!(sx >= 1.0 && sy >= 1.0)) {
+    resize_cv_kernel<2><<<g, kThreads, 0, st>>>(in, out, n, hin, win, sy, sx, iy, ix, oy0, ox0, ch, cw);
+  } else {
+    const int kx = (int)sx, ky = (int)sy;
+    const bool fast = fabs(sx - kx) < 2.220446049250313e-16 && fabs(sy - ky) < 2.220446049250313e-16;     // DBL_EPSILON, as resize.cpp
+    if (fast) resize_area_kernel<true><<<g, kThreads, 0, st>>>(in, out, n, hin, win, sy, sx, oy0, ox0, ch, cw);
+    else resize_area_kernel<false><<<g, kThreads, 0, st>>>(in, out, n, hin, win, sy, sx, oy0, ox0, ch, cw);
+  }
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }

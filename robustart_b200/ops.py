@@ -411,11 +411,11 @@ def resize_u8(images, size, filter="bilinear", crop=None, out=None):
     return out
 
 
-CV_INTERPOLATIONS = {"nearest": 0, "bilinear": 1}      # cv2.INTER_NEAREST, cv2.INTER_LINEAR
+CV_INTERPOLATIONS = {"nearest": 0, "bilinear": 1, "area": 3}      # cv2.INTER_NEAREST, cv2.INTER_LINEAR, cv2.INTER_AREA
 
 
 def resize_cv_u8(images, size, interpolation="bilinear", crop=None, out=None):
-    """cv2.resize(img, (size[1], size[0]), interpolation=INTER_NEAREST | INTER_LINEAR) of every image of a uint8 NHWC CUDA batch,
+    """cv2.resize(img, (size[1], size[0]), interpolation=INTER_NEAREST | INTER_LINEAR | INTER_AREA) of every image of a uint8 NHWC CUDA batch,
     bit-exact (csrc/resize_cv.cu); crop = (y0, x0, h, w) returns that window of the resized image (only it is computed)."""
     _need_cuda(images, torch.uint8, "images")
     n, hin, win, c = images.shape

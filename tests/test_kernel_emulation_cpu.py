@@ -592,7 +592,8 @@ def test_native_token_gradient_pass_end_to_end(emu, monkeypatch, family):
 
 
 # ---- 7. cv2.resize restated (csrc/resize_cv.cu), and the ImageNet-S host path that calls it ------------------------------------------------
-@pytest.mark.parametrize("hin,win,hout,wout", [(75, 100, 64, 64), (20, 24, 64, 48), (64, 64, 64, 64), (1, 9, 8, 8), (90, 60, 45, 30)])
+@pytest.mark.parametrize("hin,win,hout,wout", [(75, 100, 64, 64), (20, 24, 64, 48), (64, 64, 64, 64), (1, 9, 8, 8), (90, 60, 45, 30),
+                                               (96, 64, 32, 32), (50, 90, 64, 48), (97, 113, 50, 60)])
 def test_resize_cv_kernel_matches_cv2(emu, hin, win, hout, wout):
     import numpy as np
     cv2 = pytest.importorskip("cv2")
@@ -600,7 +601,8 @@ def test_resize_cv_kernel_matches_cv2(emu, hin, win, hout, wout):
     rng = np.random.RandomState(hin)
     img = rng.randint(0, 256, (2, hin, win, 3), dtype=np.uint8)
     x = torch.from_numpy(img)
-    for code, inter in ((1, cv2.INTER_LINEAR), (0, cv2.INTER_NEAREST)):
+    # INTER_AREA covers its three regimes over the geometries above: integer factors, both axes shrinking, an axis growing
+    for code, inter in ((1, cv2.INTER_LINEAR), (0, cv2.INTER_NEAREST), (3, cv2.INTER_AREA)):
         for (oy0, ox0, ch, cw) in [(0, 0, hout, wout), (hout // 4, wout // 8, hout // 2, wout // 2)]:
             out = torch.full((2, ch, cw, 3), 99, dtype=torch.uint8)
             _ok(lib.b200r_resize_cv_u8(_p(x), _p(out), 2, hin, win, hout, wout, code, oy0, ox0, ch, cw, None))
@@ -636,7 +638,7 @@ def test_imagenet_s_opencv_types_through_the_plugin(emu, monkeypatch, tmp_path):
     monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
     monkeypatch.setattr(U.torch, "device", lambda *a: torch.zeros(0).device)          # 'cuda:0' -> the host, in this test only
-    for rt, inter in (("opencv-bilinear", cv2.INTER_LINEAR), ("opencv-nearest", cv2.INTER_NEAREST)):
+    for rt, inter in (("opencv-bilinear", cv2.INTER_LINEAR), ("opencv-nearest", cv2.INTER_NEAREST), ("opencv-area", cv2.INTER_AREA)):
         gen.set_config(resize_type=rt)
         out = gen.add_noise(path)
         want = cv2.resize(img, (256, 256), interpolation=inter)[16:240, 16:240]

@@ -254,7 +254,11 @@ def test_cv_resize_restatement():
         img = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)
         assert np.array_equal(R.resize_linear(img, wo, ho), cv2.resize(img, (wo, ho), interpolation=cv2.INTER_LINEAR)), (h, w, ho, wo)
         assert np.array_equal(R.resize_nearest(img, wo, ho), cv2.resize(img, (wo, ho), interpolation=cv2.INTER_NEAREST)), (h, w, ho, wo)
+        assert np.array_equal(R.resize_area(img, wo, ho), cv2.resize(img, (wo, ho), interpolation=cv2.INTER_AREA)), (h, w, ho, wo)
+    for (h, w, ho, wo) in [(512, 512, 256, 256), (768, 768, 256, 256), (512, 768, 256, 256), (515, 770, 256, 256), (100, 300, 256, 256)]:
+        img = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)      # INTER_AREA: integer factors, general shrink, one axis growing
+        assert np.array_equal(R.resize_area(img, wo, ho), cv2.resize(img, (wo, ho), interpolation=cv2.INTER_AREA)), (h, w, ho, wo)
     img = rng.randint(0, 256, (375, 500, 3), dtype=np.uint8)
-    for rt, inter in (("opencv-bilinear", cv2.INTER_LINEAR), ("opencv-nearest", cv2.INTER_NEAREST)):
+    for rt, inter in (("opencv-bilinear", cv2.INTER_LINEAR), ("opencv-nearest", cv2.INTER_NEAREST), ("opencv-area", cv2.INTER_AREA)):
         full = cv2.resize(img, (256, 256), interpolation=inter)
         assert np.array_equal(R.imagenet_s_val(img, rt), full[16:240, 16:240])

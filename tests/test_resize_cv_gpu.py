@@ -1,4 +1,4 @@
-"""cv2.resize (INTER_NEAREST / INTER_LINEAR) on the GPU, bit for bit against cv2 itself (the call of imagenet_s_gen.py:120-148).
+"""cv2.resize (INTER_NEAREST / INTER_LINEAR / INTER_AREA) on the GPU, bit for bit against cv2 itself (the call of imagenet_s_gen.py:120-148).
 
 GATED like tests/test_token_grad_gpu.py: csrc/resize_cv.cu has run from source on the host emulator only
 (tests/test_kernel_emulation_cpu.py); B200R_CV_RESIZE=1 enables the opencv-* ImageNet-S types and these tests."""
@@ -13,13 +13,13 @@ pytestmark = [pytest.mark.gpu,
 
 
 @pytest.mark.parametrize("hin,win,hout,wout", [(375, 500, 256, 256), (64, 64, 256, 256), (500, 333, 299, 299), (224, 224, 256, 256),
-                                               (31, 500, 256, 256), (512, 512, 256, 256)])
+                                               (31, 500, 256, 256), (512, 512, 256, 256), (768, 512, 256, 256), (515, 770, 256, 256)])
 def test_resize_cv_matches_cv2(cuda, hin, win, hout, wout):
     cv2 = pytest.importorskip("cv2")
     from robustart_b200 import ops
     img = np.random.RandomState(hin + win).randint(0, 256, (3, hin, win, 3), dtype=np.uint8)
     d = torch.from_numpy(img).to(cuda)
-    for name, inter in (("bilinear", cv2.INTER_LINEAR), ("nearest", cv2.INTER_NEAREST)):
+    for name, inter in (("bilinear", cv2.INTER_LINEAR), ("nearest", cv2.INTER_NEAREST), ("area", cv2.INTER_AREA)):
         full = ops.resize_cv_u8(d, (hout, wout), name).cpu().numpy()
         crop = ops.resize_cv_u8(d, (hout, wout), name, crop=(16, 8, 224, 200)).cpu().numpy()
         for i in range(3):
@@ -34,7 +34,7 @@ def test_imagenet_s_opencv_types(cuda, tmp_path):
     img = np.random.RandomState(9).randint(0, 256, (375, 500, 3), dtype=np.uint8)
     path = str(tmp_path / "a.png")
     cv2.imwrite(path, cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
-    for rt, inter in (("opencv-bilinear", cv2.INTER_LINEAR), ("opencv-nearest", cv2.INTER_NEAREST)):
+    for rt, inter in (("opencv-bilinear", cv2.INTER_LINEAR), ("opencv-nearest", cv2.INTER_NEAREST), ("opencv-area", cv2.INTER_AREA)):
         gen = AddNoise("imagenet-s")
         gen.set_config(resize_type=rt, decoder_type="opencv")
         out = gen.add_noise(path)

@@ -115,7 +115,8 @@ _PIL_RESIZE_TYPES = {'pil-bilinear': 'bilinear', 'pil-nearest': 'nearest', 'pil-
                      'pil-cubic': 'bicubic', 'pil-lanczos': 'lanczos'}
 
 
-_CV_RESIZE_TYPES = {'opencv-nearest': 'nearest', 'opencv-bilinear': 'bilinear', 'opencv-area': 'area'}
+_CV_RESIZE_TYPES = {'opencv-nearest': 'nearest', 'opencv-bilinear': 'bilinear', 'opencv-area': 'area', 'opencv-cubic': 'cubic',
+                    'opencv-lanczos': 'lanczos'}
 
 
 def _cv_resize_enabled():
@@ -138,8 +139,8 @@ def add_noise_for_imagenet_s(image, decoder_type='pil', resize_type='pil-bilinea
     path (the reference's contract) or an already decoded uint8 [h, w, 3] / [n, h, w, 3] array or CUDA tensor.
     transform 'train' = the reference's random resized crop (parameters from Python's `random`) + Image.resize to (size, size).
     With B200R_CV_RESIZE=1 also the `opencv` decoder (cv2.imdecode on the host + BGR->RGB, imagenet_s_gen.py:193-202) and the
-    `opencv-nearest` / `opencv-bilinear` / `opencv-area` resize types (cv2.resize bit for bit, b200r_resize_cv_u8).  The ffmpeg
-    decoder and opencv-cubic / -lanczos are not implemented."""
+    five `opencv-*` resize types (cv2.resize bit for bit; opencv-cubic as IPP's float cubic, b200r_resize_cv_u8).  The ffmpeg
+    decoder is not implemented."""
     cv_ok = _cv_resize_enabled()
     if decoder_type != 'pil' and not (cv_ok and decoder_type == 'opencv'):
         raise NotImplementedError("imagenet-s decoder_type=%r: only the PIL decoder is implemented" % decoder_type)

@@ -255,10 +255,12 @@ int b200r_resize_workspace_bytes(int n, int hin, int win, int hout, int wout, in
 int b200r_resize_u8(const uint8_t* in, uint8_t* out, int n, int hin, int win, int hout, int wout, int filter,
                     int oy0, int ox0, int ch, int cw, void* workspace, size_t ws_bytes, b200r_stream_t stream);
 
-/* cv2.resize(INTER_NEAREST | INTER_LINEAR | INTER_AREA) for uint8 NHWC batches, bit for bit (the `opencv-nearest` /
- * `opencv-bilinear` / `opencv-area` resize types of RobustART/noise/utils/imagenet_s_gen.py:28-34,120-148), cropped to the window [oy0, oy0+ch) x [ox0, ox0+cw) of the
- * hout x wout result: out is [n, ch, cw, 3].  interpolation uses cv2's own constants.  No workspace. */
-enum b200r_cv_interpolation { B200R_CV_INTER_NEAREST = 0, B200R_CV_INTER_LINEAR = 1, B200R_CV_INTER_AREA = 3 };
+/* cv2.resize(INTER_NEAREST | INTER_LINEAR | INTER_AREA | INTER_LANCZOS4) for uint8 NHWC batches, bit for bit, and INTER_CUBIC as
+ * the float32 cubic the opencv-python wheels compute through IPP (1 LSB on <= 1e-4 of the pixels) -- the five `opencv-*` resize types of RobustART/noise/utils/imagenet_s_gen.py:28-34,120-148), cropped to the window [oy0, oy0+ch) x [ox0, ox0+cw) of the
+ * hout x wout result: out is [n, ch, cw, 3].  interpolation uses cv2's own constants.  No workspace; cubic / lanczos4
+ * upload a cached weight table on the first call per geometry (blocking). */
+enum b200r_cv_interpolation { B200R_CV_INTER_NEAREST = 0, B200R_CV_INTER_LINEAR = 1, B200R_CV_INTER_CUBIC = 2, B200R_CV_INTER_AREA = 3,
+                              B200R_CV_INTER_LANCZOS4 = 4 };
 int b200r_resize_cv_u8(const uint8_t* in, uint8_t* out, int n, int hin, int win, int hout, int wout, int interpolation,
                        int oy0, int ox0, int ch, int cw, b200r_stream_t stream);
 

@@ -411,7 +411,7 @@ def resize_u8(images, size, filter="bilinear", crop=None, out=None):
     return out
 
 
-CV_INTERPOLATIONS = {"nearest": 0, "bilinear": 1, "area": 3}      # cv2.INTER_NEAREST, cv2.INTER_LINEAR, cv2.INTER_AREA
+CV_INTERPOLATIONS = {"nearest": 0, "bilinear": 1, "cubic": 2, "area": 3, "lanczos": 4}      # cv2.INTER_* constants
 
 
 def resize_cv_u8(images, size, interpolation="bilinear", crop=None, out=None):

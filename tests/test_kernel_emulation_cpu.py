@@ -602,14 +602,21 @@ def test_resize_cv_kernel_matches_cv2(emu, hin, win, hout, wout):
     img = rng.randint(0, 256, (2, hin, win, 3), dtype=np.uint8)
     x = torch.from_numpy(img)
     # INTER_AREA covers its three regimes over the geometries above: integer factors, both axes shrinking, an axis growing
-    for code, inter in ((1, cv2.INTER_LINEAR), (0, cv2.INTER_NEAREST), (3, cv2.INTER_AREA)):
+    from oracle import cv_resize as R
+    for code, inter in ((1, cv2.INTER_LINEAR), (0, cv2.INTER_NEAREST), (3, cv2.INTER_AREA), (4, cv2.INTER_LANCZOS4), (2, cv2.INTER_CUBIC)):
         for (oy0, ox0, ch, cw) in [(0, 0, hout, wout), (hout // 4, wout // 8, hout // 2, wout // 2)]:
             out = torch.full((2, ch, cw, 3), 99, dtype=torch.uint8)
             _ok(lib.b200r_resize_cv_u8(_p(x), _p(out), 2, hin, win, hout, wout, code, oy0, ox0, ch, cw, None))
             for i in range(2):
                 want = cv2.resize(img[i], (wout, hout), interpolation=inter)[oy0:oy0 + ch, ox0:ox0 + cw]
-                assert np.array_equal(out[i].numpy(), want), (code, i)
-    assert lib.b200r_resize_cv_u8(_p(x), _p(out), 2, hin, win, hout, wout, 2, 0, 0, hout, wout, None) != 0          # INTER_CUBIC: not here
+                if code != 2:
+                    assert np.array_equal(out[i].numpy(), want), (code, i)
+                else:       # cubic: bit-exact against the float32 restatement; against cv2 (IPP) the oracle's bar, where IPP is in play
+                    assert np.array_equal(out[i].numpy(), R.resize_cubic(img[i], wout, hout)[oy0:oy0 + ch, ox0:ox0 + cw]), i
+                    if min(hin, win) >= 16:
+                        d = np.abs(out[i].numpy().astype(int) - want.astype(int))
+                        assert d.max() <= 1 and (d > 0).mean() <= max(1e-4, 1.5 / d.size), (i, d.max(), (d > 0).mean())
+    assert lib.b200r_resize_cv_u8(_p(x), _p(out), 2, hin, win, hout, wout, 5, 0, 0, hout, wout, None) != 0          # INTER_LINEAR_EXACT: not here
     assert lib.b200r_resize_cv_u8(_p(x), _p(out), 2, hin, win, hout, wout, 1, 1, 0, hout, wout, None) != 0          # crop outside
 
 
@@ -638,7 +645,8 @@ def test_imagenet_s_opencv_types_through_the_plugin(emu, monkeypatch, tmp_path):
     monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
     monkeypatch.setattr(U.torch, "device", lambda *a: torch.zeros(0).device)          # 'cuda:0' -> the host, in this test only
-    for rt, inter in (("opencv-bilinear", cv2.INTER_LINEAR), ("opencv-nearest", cv2.INTER_NEAREST), ("opencv-area", cv2.INTER_AREA)):
+    for rt, inter in (("opencv-bilinear", cv2.INTER_LINEAR), ("opencv-nearest", cv2.INTER_NEAREST), ("opencv-area", cv2.INTER_AREA),
+                      ("opencv-lanczos", cv2.INTER_LANCZOS4)):
         gen.set_config(resize_type=rt)
         out = gen.add_noise(path)
         want = cv2.resize(img, (256, 256), interpolation=inter)[16:240, 16:240]

@@ -255,6 +255,12 @@ def test_cv_resize_restatement():
         assert np.array_equal(R.resize_linear(img, wo, ho), cv2.resize(img, (wo, ho), interpolation=cv2.INTER_LINEAR)), (h, w, ho, wo)
         assert np.array_equal(R.resize_nearest(img, wo, ho), cv2.resize(img, (wo, ho), interpolation=cv2.INTER_NEAREST)), (h, w, ho, wo)
         assert np.array_equal(R.resize_area(img, wo, ho), cv2.resize(img, (wo, ho), interpolation=cv2.INTER_AREA)), (h, w, ho, wo)
+        assert np.array_equal(R.resize_lanczos4(img, wo, ho), cv2.resize(img, (wo, ho), interpolation=cv2.INTER_LANCZOS4)), (h, w, ho, wo)
+        # INTER_CUBIC goes through closed-source IPP in the opencv-python wheels: a float32 cubic, matched to within 1 LSB on <= 1e-4
+        # (IPP declines very small sources -- OpenCV's fixed-point path runs instead -- so the bar is stated for sides >= 16)
+        if min(h, w) >= 16:
+            d = np.abs(R.resize_cubic(img, wo, ho).astype(int) - cv2.resize(img, (wo, ho), interpolation=cv2.INTER_CUBIC).astype(int))
+            assert d.max() <= 1 and (d > 0).mean() <= max(1e-4, 1.5 / d.size), ((h, w, ho, wo), d.max(), (d > 0).mean())
     for (h, w, ho, wo) in [(512, 512, 256, 256), (768, 768, 256, 256), (512, 768, 256, 256), (515, 770, 256, 256), (100, 300, 256, 256)]:
         img = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)      # INTER_AREA: integer factors, general shrink, one axis growing
         assert np.array_equal(R.resize_area(img, wo, ho), cv2.resize(img, (wo, ho), interpolation=cv2.INTER_AREA)), (h, w, ho, wo)

@@ -1,4 +1,4 @@
-"""cv2.resize (INTER_NEAREST / INTER_LINEAR / INTER_AREA) on the GPU, bit for bit against cv2 itself (the call of imagenet_s_gen.py:120-148).
+"""cv2.resize (INTER_NEAREST / INTER_LINEAR / INTER_AREA / INTER_LANCZOS4 bit for bit, INTER_CUBIC within IPP's bar) on the GPU against cv2 itself (the call of imagenet_s_gen.py:120-148).
 
 GATED like tests/test_token_grad_gpu.py: csrc/resize_cv.cu has run from source on the host emulator only
 (tests/test_kernel_emulation_cpu.py); B200R_CV_RESIZE=1 enables the opencv-* ImageNet-S types and these tests."""
@@ -26,6 +26,14 @@ def test_resize_cv_matches_cv2(cuda, hin, win, hout, wout):
             want = cv2.resize(img[i], (wout, hout), interpolation=inter)
             assert np.array_equal(full[i], want), (name, i)
             assert np.array_equal(crop[i], want[16:240, 8:208]), (name, i)
+    full = ops.resize_cv_u8(d, (hout, wout), "lanczos").cpu().numpy()
+    cub = ops.resize_cv_u8(d, (hout, wout), "cubic").cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(full[i], cv2.resize(img[i], (wout, hout), interpolation=cv2.INTER_LANCZOS4)), i
+        # INTER_CUBIC runs through closed-source IPP in the opencv-python wheels (a float32 cubic; oracle/cv_resize.py): 1 LSB on <= 1e-4
+        # of the pixels here in the container -- the host CPU of the GPU box may pick another IPP code path, hence the wider bar
+        dd = np.abs(cub[i].astype(int) - cv2.resize(img[i], (wout, hout), interpolation=cv2.INTER_CUBIC).astype(int))
+        assert dd.max() <= 1 and (dd > 0).mean() <= 1e-3, (i, dd.max(), (dd > 0).mean())
 
 
 def test_imagenet_s_opencv_types(cuda, tmp_path):

@@ -52,8 +52,9 @@ def test_activation_forward_and_backward(cuda, act):
     (want,) = torch.autograd.grad(y, p, grad_outputs=_rt(ops, dy).double())
     got_y = ops.merge_f32(ops.act_planes(ops.split_f32(pre), act))
     got_d = ops.merge_f32(ops.act_bwd_planes(ops.split_f32(dy), ops.split_f32(pre), act))
-    assert (got_y.double() - y.detach()).abs().max().item() < 2e-5
-    assert (got_d.double() - want).abs().max().item() < 5e-5
+    # split planes keep ~16 mantissa bits: the bar scales with the magnitude of the result
+    assert (got_y.double() - y.detach()).abs().max().item() < 2e-5 * max(1.0, y.detach().abs().max().item())
+    assert (got_d.double() - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item())
 
 
 @pytest.mark.parametrize("n,t,heads", [(3, 197, 12), (2, 50, 4), (1, 1, 2), (2, 129, 3)])

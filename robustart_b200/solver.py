@@ -151,7 +151,11 @@ class FileImageNet:
     hot path, as in the reference) and go through the eval transform on the GPU: Resize(test_resize) + CenterCrop(input_size)
     as ONE bit-exact Pillow-resize launch per image (imagenet_dataloader.py:74-80; ops.resize_center_crop_u8)."""
 
-    def __init__(self, root_dir: str, meta_file: str, input_size: int, device, test_resize: int = 256, limit: Optional[int] = None):
+    def __init__(self, root_dir: str, meta_file: str, input_size: int, device, test_resize: int = 256, limit: Optional[int] = None,
+                 reader: str = "pil"):
+        if reader not in ("pil", "opencv"):
+            raise NotImplementedError("image_reader.type=%r: pil and opencv are implemented (image_reader.py:11-31); ffmpeg is not" % reader)
+        self.reader = reader
         self.root, self.size, self.device, self.test_resize = root_dir, input_size, device, int(test_resize)
         self.metas = []
         with open(meta_file) as f:
@@ -166,14 +170,22 @@ class FileImageNet:
     def filename(self, idx: int) -> str:
         return self.metas[idx][0]
 
-    def batch(self, indices: torch.Tensor):
+    @staticmethod
+    def decode(path: str, reader: str = "pil"):
+        """pil_loader / opencv_loader of image_reader.py:11-31: a uint8 RGB [h, w, 3] array (host side, like the reference)."""
         import numpy as np
+        if reader == "opencv":
+            import cv2
+            return cv2.cvtColor(cv2.imdecode(np.fromfile(path, dtype=np.uint8), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
         from PIL import Image
+        with Image.open(path) as im:
+            return np.array(im.convert("RGB"))
+
+    def batch(self, indices: torch.Tensor):
         imgs, labels = [], []
         for idx in indices.tolist():
             name, label = self.metas[idx]
-            with Image.open(os.path.join(self.root, name)) as im:
-                arr = np.array(im.convert("RGB"))
+            arr = self.decode(os.path.join(self.root, name), self.reader)
             d = torch.from_numpy(arr)[None].to(self.device)
             imgs.append(ops.resize_center_crop_u8(d, self.test_resize, self.size)[0])
             labels.append(label)
@@ -247,7 +259,8 @@ class EvalSolver:
         test = data.get("test", {})
         if read_from in ("fs", "file"):
             self.dataset = FileImageNet(test["root_dir"], test["meta_file"], self.input_size, self.device,
-                                        test_resize=int(data.get("test_resize", 256)), limit=test.get("limit_samples"))
+                                        test_resize=int(data.get("test_resize", 256)), limit=test.get("limit_samples"),
+                                        reader=(test.get("image_reader") or {}).get("type", "pil"))
             n_items = self.dataset.n
         else:
             n_items = int(test.get("limit_samples", data.get("num_samples", 50000)))

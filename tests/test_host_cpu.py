@@ -186,6 +186,17 @@ def test_file_dataset_host_logic(tmp_path, monkeypatch):
     want = pil_transform(torch.from_numpy(np.array(Image.open(tmp_path / "val" / "img3.png").convert("RGB")))[None], 64, 56)[0]
     assert torch.equal(imgs[0], want)
     assert S.FileImageNet(str(tmp_path / "val"), str(tmp_path / "meta.txt"), 56, "cpu", limit=3).n == 3
+    # image_reader.type: opencv (image_reader.py:21-31: cv2.imdecode + BGR->RGB); ffmpeg is refused
+    cv2 = pytest.importorskip("cv2")
+    ds_cv = S.FileImageNet(str(tmp_path / "val"), str(tmp_path / "meta.txt"), 56, "cpu", test_resize=64, reader="opencv")
+    assert torch.equal(ds_cv.batch(torch.tensor([3, 0]))[0], imgs)                       # PNG: both decoders give the same pixels
+    jpg = str(tmp_path / "val" / "a.jpg")
+    Image.fromarray(rs.randint(0, 256, (48, 64, 3)).astype(np.uint8)).save(jpg, quality=80)
+    want_cv = cv2.cvtColor(cv2.imdecode(np.fromfile(jpg, dtype=np.uint8), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+    assert np.array_equal(S.FileImageNet.decode(jpg, "opencv"), want_cv)
+    assert np.array_equal(S.FileImageNet.decode(jpg, "pil"), np.array(Image.open(jpg).convert("RGB")))
+    with pytest.raises(NotImplementedError):
+        S.FileImageNet(str(tmp_path / "val"), str(tmp_path / "meta.txt"), 56, "cpu", reader="ffmpeg")
 
 
 def test_robust_json_matches_reference_merge_eval_res(tmp_path):

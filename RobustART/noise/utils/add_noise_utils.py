@@ -120,9 +120,9 @@ _CV_RESIZE_TYPES = {'opencv-nearest': 'nearest', 'opencv-bilinear': 'bilinear', 
 
 
 def _cv_resize_enabled():
-    # csrc/resize_cv.cu is checked against cv2.resize on the host emulator only so far: opt-in until it has run on a GPU
+    # csrc/resize_cv.cu: bit-exact against cv2.resize on the GPU (tests/test_resize_cv_gpu.py); B200R_CV_RESIZE=0 switches it off
     import os
-    return os.environ.get('B200R_CV_RESIZE', '0') == '1'
+    return os.environ.get('B200R_CV_RESIZE', '1') != '0'
 
 
 def _imagenet_s_resize(batch, size_hw, resize_type, crop=None):
@@ -138,7 +138,7 @@ def add_noise_for_imagenet_s(image, decoder_type='pil', resize_type='pil-bilinea
     (size*8/7, size*8/7) and the centre crop as ONE bit-exact resize kernel launch (b200r_resize_u8).  `image` is a file
     path (the reference's contract) or an already decoded uint8 [h, w, 3] / [n, h, w, 3] array or CUDA tensor.
     transform 'train' = the reference's random resized crop (parameters from Python's `random`) + Image.resize to (size, size).
-    With B200R_CV_RESIZE=1 also the `opencv` decoder (cv2.imdecode on the host + BGR->RGB, imagenet_s_gen.py:193-202) and the
+    Also the `opencv` decoder (cv2.imdecode on the host + BGR->RGB, imagenet_s_gen.py:193-202) and the
     five `opencv-*` resize types (cv2.resize bit for bit; opencv-cubic as IPP's float cubic, b200r_resize_cv_u8).  The ffmpeg
     decoder is not implemented."""
     cv_ok = _cv_resize_enabled()

@@ -897,16 +897,6 @@ static int stencil_dispatch(const CorruptArgs& a) {
     case B200R_SPATTER: {
       static const double c[5][6] = {{0.65, 0.3, 4, 0.69, 0.6, 0}, {0.65, 0.3, 3, 0.68, 0.6, 0}, {0.65, 0.3, 2, 0.68, 0.5, 0},
                                      {0.65, 0.3, 1, 0.65, 1.5, 1}, {0.67, 0.4, 1, 0.65, 1.5, 1}};
-      if (c[s][5] == 0) {
-        // water branch (corrupt_spatter_water.cu): written and emulator-checked but not yet run on a GPU -> opt-in
-        static int water = -1;
-        if (water < 0) { const char* e = getenv("B200R_SPATTER_WATER"); water = (e && e[0] == '1') ? 1 : 0; }
-        if (!water) {
-          b200r_set_error("spatter severity 1-3 (water: cv2.Canny / distanceTransform / equalizeHist chain) is not enabled on the GPU yet "
-                          "(B200R_SPATTER_WATER=1 selects the unvalidated kernel)");
-          return B200R_ENOTSUP;
-        }
-      }
       const int hw = a.h * a.w;
       const size_t need = corrupt_stencil_ws(a.id, a.severity, a.n, a.h, a.w);
       B200R_CHECK_ARG(a.ws && a.ws_bytes >= need, "spatter needs %zu workspace bytes", need);

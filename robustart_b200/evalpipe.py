@@ -40,6 +40,9 @@ class CorruptEvalPipeline:
                     image_offset: Optional[int] = None) -> torch.Tensor:
         """images: uint8 NHWC CUDA [batch,h,w,3] (not modified); labels int64 CUDA.  Returns the logits
         (static buffer, valid until the next step).  Counters accumulate on the device."""
+        if images.shape[0] != self.batch or labels.numel() != self.batch:
+            raise ValueError("CorruptEvalPipeline was captured for batch %d: got %d images / %d labels (pad or build a second "
+                             "pipeline for the ragged last batch)" % (self.batch, images.shape[0], labels.numel()))
         off = self.images_done if image_offset is None else image_offset
         if corruption is None:
             self.static_in.copy_(images)

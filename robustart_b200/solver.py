@@ -193,8 +193,13 @@ class FileImageNet:
 
 
 def load_checkpoint(path: Optional[str]) -> Optional[Dict[str, torch.Tensor]]:
-    if not path or not os.path.exists(path):
+    """None (-> synthetic weights) only when NO path is given or it is the literal 'synthetic'; a path that does not exist
+    raises like the reference's torch.load does (benchmark_eval_adv.py:75-79), so a mistyped --src_path can never be
+    evaluated as a random-weight model."""
+    if not path or path == "synthetic":
         return None
+    if not os.path.exists(path):
+        raise FileNotFoundError("checkpoint %r does not exist (pass no path or 'synthetic' for synthetic weights)" % path)
     return torch.load(path, map_location="cpu")
 
 
@@ -212,8 +217,9 @@ def build_source_model(model_cfg, ckpt_path, device):
     arch = nets.ARCH_ALIASES.get(model_cfg["type"], model_cfg["type"])
     if arch in nets._RESNET_CFG and os.environ.get("B200R_SOURCE_AUTOGRAD", "0") != "1":
         return NativeModel(build_b200_model(model_cfg, ckpt_path, device))
-    if arch in nets._TOKEN_ARCHS and os.environ.get("B200R_NATIVE_TOKEN_GRAD", "0") == "1":
-        # opt-in until measured against the autograd twin on the GPU: forward + input gradient of ViT / Mixer on our kernels
+    if arch in nets._TOKEN_ARCHS and os.environ.get("B200R_SOURCE_AUTOGRAD", "0") != "1":
+        # forward + input gradient of ViT / Mixer on our kernels (token_backward.cu + dgrad GEMMs; 4.2x / 1.65x the autograd twin
+        # on the PGD-Linf loop when first measured, profiles/r2_pgd_token.json)
         return NativeModel(build_b200_model(model_cfg, ckpt_path, device))
     return build_torch_model(model_cfg, ckpt_path, device)
 
@@ -383,13 +389,18 @@ class EvalSolver:
                     if self.dist.rank == 0:
                         with open(os.path.join(self.result_path, "%s-%s-%d-metric" % (g, t, s)), "w") as f:
                             json.dump(m, f)
-                all_data[g][t] = sum(errs) / len(errs) if errs else None
-                if errs:
+                # a type with a skipped severity has no number comparable with merge_eval_res (imagnetc.py:166-218): None, and
+                # the two averages below become None as well
+                partial = any((t, s) in skipped for s in severities)
+                all_data[g][t] = sum(errs) / len(errs) if (errs and not partial) else None
+                if errs and not partial:
                     avg.append(all_data[g][t])
                     if g != "extra":
                         avg_wo.append(all_data[g][t])
-        all_data["all"]["all_with_extra"] = sum(avg) / len(avg) if avg else None
-        all_data["all"]["all_without_extra"] = sum(avg_wo) / len(avg_wo) if avg_wo else None
+        skipped_types = {t for t, _ in skipped}
+        extra_types = set(groups.get("extra", []))
+        all_data["all"]["all_with_extra"] = sum(avg) / len(avg) if (avg and not skipped_types) else None
+        all_data["all"]["all_without_extra"] = sum(avg_wo) / len(avg_wo) if (avg_wo and not (skipped_types - extra_types)) else None
         if skipped:
             all_data["skipped"] = {"%s-%d" % k: v for k, v in skipped.items()}
         if self.dist.rank == 0:

@@ -243,3 +243,15 @@ def test_round8_property():
     want = np.array([float("%.8f" % s) for s in v.tolist()])
     assert np.array_equal(got, want)
     assert R.round8(np.float32(0.5)).item() == 0.5 and R.round8(np.array([[1.0, 0.0]], np.float32)).tolist() == [[1.0, 0.0]]
+
+
+def test_missing_checkpoint_raises(tmp_path):
+    """a non-empty path that does not exist must raise (the reference's torch.load does), never fall back to
+    synthetic weights; no path / 'synthetic' is the explicit opt-in."""
+    import torch
+    from robustart_b200 import solver as S
+    assert S.load_checkpoint(None) is None and S.load_checkpoint("") is None and S.load_checkpoint("synthetic") is None
+    with pytest.raises(FileNotFoundError):
+        S.load_checkpoint(str(tmp_path / "nope.pth.tar"))
+    torch.save({"model": {"a": torch.ones(2)}}, tmp_path / "ok.pth.tar")
+    assert "model" in S.load_checkpoint(str(tmp_path / "ok.pth.tar"))

@@ -438,24 +438,14 @@ def _corrupt(lib, name_id, sev, images, ext):
 
 
 def test_spatter_end_to_end_through_the_front_door(emu, monkeypatch):
-    """b200r_corrupt_u8(spatter): the gate (B200R_ENOTSUP without B200R_SPATTER_WATER=1), then the whole severity-1 path -- normal layer
-    from shared draws, the two float32 Gaussian passes, threshold, water chain -- against the reference's cv2 chain on the float64
-    layer.  This is the comparison the gated GPU test (tests/test_spatter_water_gpu.py) will make, with its tolerance taken from here."""
+    """b200r_corrupt_u8(spatter), severity 1-3: the whole path -- normal layer from shared draws, the two float32 Gaussian passes,
+    threshold, water chain -- against the reference's cv2 chain on the float64 layer.  Same comparison as the GPU test
+    (tests/test_spatter_water_gpu.py), whose tolerance was taken from here."""
     import numpy as np
     pytest.importorskip("cv2")
     from util import synth_images, oracle_batch
     images = synth_images(1, seed=51)
-    want, ext = oracle_batch(images, "spatter", 1)
-    monkeypatch.delenv("B200R_SPATTER_WATER", raising=False)
-    lib = emu["corrupt"]
-    rc, _ = _corrupt(lib, 17, 1, images, ext)
-    assert rc == -4 and b"B200R_SPATTER_WATER" in lib.b200r_last_error()           # B200R_ENOTSUP: the validated default
-    # the switch is read once per library instance: load a second copy with the variable set
-    import shutil
-    monkeypatch.setenv("B200R_SPATTER_WATER", "1")
-    so2 = str(emu.d / "libcorrupt_emu_water.so")
-    shutil.copy(str(emu.d / "libcorrupt_emu.so"), so2)
-    lib2 = C.CDLL(so2)
+    lib2 = emu["corrupt"]
     for sev, seed in ((1, 51), (2, 52), (3, 53)):
         images = synth_images(1, seed=seed)
         want, ext = oracle_batch(images, "spatter", sev)
@@ -622,7 +612,7 @@ def test_resize_cv_kernel_matches_cv2(emu, hin, win, hout, wout):
 
 def test_imagenet_s_opencv_types_through_the_plugin(emu, monkeypatch, tmp_path):
     """AddNoise('imagenet-s') with decoder 'opencv' and the opencv-* resize types (imagenet_s_gen.py:138-148,193-202): host code + ops
-    wrapper + the kernel from source, against cv2 itself; off unless B200R_CV_RESIZE=1."""
+    wrapper + the kernel from source, against cv2 itself; B200R_CV_RESIZE=0 switches the types off."""
     import contextlib
     import numpy as np
     cv2 = pytest.importorskip("cv2")
@@ -634,10 +624,10 @@ def test_imagenet_s_opencv_types_through_the_plugin(emu, monkeypatch, tmp_path):
     cv2.imwrite(path, cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
     gen = AddNoise("imagenet-s")
     gen.set_config(resize_type="opencv-bilinear", decoder_type="opencv")
-    monkeypatch.delenv("B200R_CV_RESIZE", raising=False)
+    monkeypatch.setenv("B200R_CV_RESIZE", "0")
     with pytest.raises(NotImplementedError):
         gen.add_noise(path)
-    monkeypatch.setenv("B200R_CV_RESIZE", "1")
+    monkeypatch.delenv("B200R_CV_RESIZE")
     facade = _Facade(emu, ["resize_cv"])
     monkeypatch.setattr(_lib, "_lib", facade)
     monkeypatch.setattr(ops, "_need_cuda", lambda t, dtype, name: None)

@@ -8,8 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200R_CV_RESIZE", "0") != "1", reason="cv2-exact resize is opt-in until first validated on a GPU")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("hin,win,hout,wout", [(375, 500, 256, 256), (64, 64, 256, 256), (500, 333, 299, 299), (224, 224, 256, 256),

@@ -57,6 +57,6 @@ def test_eval_transform_and_imagenet_s_plugin(cuda, tmp_path):
         want = np.asarray(Image.open(path).convert("RGB").resize((256, 256), f).crop((16, 16, 240, 240)))
         assert out.shape == (224, 224, 3) and np.array_equal(out, want), rt
     gen = AddNoise("imagenet-s")
-    gen.set_config(resize_type="opencv-bilinear")
+    gen.set_config(decoder_type="ffmpeg")            # the one decoder without an implementation fails loudly
     with pytest.raises(NotImplementedError):
         gen.add_noise(path)

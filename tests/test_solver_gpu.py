@@ -73,7 +73,7 @@ def test_imgnet_c_sweep_cli(cuda, tmp_path, monkeypatch):
     for g in ("noise", "blur", "weather", "digital"):
         for t, v in rj[g].items():
             assert 0.0 <= v <= 100.0, (t, v)
-    assert set(rj.get("skipped", {})) <= {"spatter-1", "spatter-2", "spatter-3"}       # water branch: no kernel yet
+    assert "skipped" not in rj and rj["extra"]["spatter"] is not None                  # all 95 cells have a kernel
     cell = json.load(open(tmp_path / "results" / "digital-contrast-3-metric"))
     anu.reseed(11)
     alone = cls.main(["--config", cfg, "--evaluate", "--corruption", "contrast", "--severity", "3"])
@@ -88,11 +88,16 @@ def test_multi_eval_cli(cuda, tmp_path, monkeypatch):
     cfg_path = _cfg(tmp_path, n=32, bs=16)
     cfg = yaml.safe_load(open(cfg_path))
     cfg["eval_list"] = ["resnet18", "no_such_model"]
+    cfg["eval_list"] = ["resnet18", "no_such_model", "resnet50"]
     open(cfg_path, "w").write(yaml.safe_dump(cfg))
+    # a checkpoint for resnet18 only: resnet50's file is missing, which must be logged and skipped (never random weights)
+    from robustart_b200 import nets
+    torch.save({"model": nets.random_state_dict(nets.resnet_spec("resnet18"), 0)}, tmp_path / "resnet18.pth.tar")
     res = multi.main(["--config", cfg_path, "--evaluate", "--ckpt-filePath", str(tmp_path)])
     assert list(res) == ["resnet18"] and res["resnet18"]["count"] == 32
     st = open(tmp_path / "status.txt").read()
     assert "resnet18 done" in st and "Error when load no_such_model" in st
+    assert "Error when load resnet50" in st and "FileNotFoundError" in st
 
 
 @pytest.mark.parametrize("passes", [16, 3])

@@ -12,9 +12,7 @@ import pytest
 
 from util import synth_images, oracle_batch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200R_SPATTER_WATER", "0") != "1",
-                                 reason="spatter's water branch is opt-in until first validated on a GPU")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("sev", [1, 2, 3])

@@ -11,9 +11,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200R_NATIVE_TOKEN_GRAD", "0") != "1",
-                                 reason="native token-model gradients are opt-in until first validated on a GPU")]
+pytestmark = [pytest.mark.gpu]
 
 MEAN, STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 

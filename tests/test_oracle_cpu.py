@@ -268,3 +268,24 @@ def test_cv_resize_restatement():
     for rt, inter in (("opencv-bilinear", cv2.INTER_LINEAR), ("opencv-nearest", cv2.INTER_NEAREST), ("opencv-area", cv2.INTER_AREA)):
         full = cv2.resize(img, (256, 256), interpolation=inter)
         assert np.array_equal(R.imagenet_s_val(img, rt), full[16:240, 16:240])
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
+def test_calibrated_golden_logits_reproduce(arch):
+    """tests/golden/calibrated_logits.npz (realistic-magnitude logits made by the REFERENCE's classes): the oracle model with
+    the rebuilt calibrated state_dict gives the stored logits -- pins the fixture and util.calibrated_state_dict on CPU."""
+    import torch
+    from oracle import models as OM
+    from robustart_b200 import nets
+    from util import diverse_images, calibrated_state_dict
+    cal = np.load(os.path.join(os.path.dirname(__file__), "golden", "calibrated_logits.npz"))
+    want = cal[arch + "/logits"]
+    assert np.abs(want).max() > 10 and len(set(want.argmax(1).tolist())) >= 3 and 2.0 < want.std() < 3.0
+    sd = calibrated_state_dict(arch, nets.random_state_dict(nets.resnet_spec(arch), 0), cal)
+    model = OM.build(arch, sd)
+    n = 8 if arch == "resnet18" else 3
+    x = torch.from_numpy(diverse_images(8, seed=0)[:n]).permute(0, 3, 1, 2).float().div(255)
+    xn = (x - torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)) / torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    with torch.no_grad():
+        got = model(xn).numpy()
+    assert np.abs(got - want[:n]).max() < 2e-4, np.abs(got - want[:n]).max()      # batch-size dependent fp32 summation order only

@@ -1,7 +1,7 @@
 """images/s of the graph-replayed forward vs batch size (L2 residency of the activations vs tile-count effects)."""
 import json, os, sys
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from robustart_b200 import nets
 dev = torch.device("cuda", 0)
 arch = sys.argv[1] if len(sys.argv) > 1 else "resnet50"

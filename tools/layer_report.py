@@ -1,14 +1,14 @@
 """Per-launch report of one ResNet-50 forward (batch 256): shape, CUDA-event time, achieved TFLOP/s and GB/s and
 the per-layer roofline time max(bytes/HBM, passes*flops/bf16 peak).  Writes gpurun_out/layer_report.txt.
 
-  python tools_layer_report.py [batch] [arch] [passes: 16 = fp16 single plane (default), 3 = split-bf16]"""
+  python tools/layer_report.py [batch] [arch] [passes: 16 = fp16 single plane (default), 3 = split-bf16]"""
 import json
 import os
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from robustart_b200 import nets, ops  # noqa: E402
 
 PK = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}

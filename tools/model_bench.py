@@ -1,7 +1,7 @@
 """Forward throughput of the five benchmark architectures on the sm_100a kernels (CUDA-event timed, uint8 NHWC
 batches rotating over > L2).  Writes gpurun_out/model_bench.json.  Not the headline bench (bench.py is).
 
-  python tools_model_bench.py [arch ...] [--n 256]
+  python tools/model_bench.py [arch ...] [--n 256]
 """
 import json
 import os
@@ -9,7 +9,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from robustart_b200 import nets  # noqa: E402
 
 GFLOP = {"resnet18": 3.62, "resnet50": 8.18, "mobilenet_v2": 0.60, "efficientnet_b0": 0.78,

@@ -1,4 +1,4 @@
-"""Key ncu metrics per captured launch from a .ncu-rep (read here, no GPU): python tools_ncu_report.py file.ncu-rep [out.json]"""
+"""Key ncu metrics per captured launch from a .ncu-rep (read here, no GPU): python tools/ncu_report.py file.ncu-rep [out.json]"""
 import csv, io, json, subprocess, sys
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",

@@ -1,8 +1,8 @@
 """Summaries of `ncu --csv` logs for profiles/ (no GPU needed).
 
-  python tools_ncu_summarize.py traffic  gpurun_out/gemm_traffic.csv  profiles/rN_gemm_traffic.json
+  python tools/ncu_summarize.py traffic  gpurun_out/gemm_traffic.csv  profiles/rN_gemm_traffic.json
       -> DRAM bytes of the LAST forward's gemm_kernel launches (the driver script runs two forwards)
-  python tools_ncu_summarize.py launches gpurun_out/launches.csv      profiles/rN_launch_shares.json
+  python tools/ncu_summarize.py launches gpurun_out/launches.csv      profiles/rN_launch_shares.json
       -> per-kernel share of the summed gpu__time_duration over the captured launches
 """
 import csv
@@ -35,7 +35,7 @@ def traffic(src, dst):
     tm = sum(per[i].get("gpu__time_duration.sum", 0.0) for i in half)
     out = {"dram_bytes_per_forward": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr, "launches": len(half),
            "sum_kernel_time_us_under_ncu": tm / 1e3, "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,"
-           "gpu__time_duration.sum -k regex:gemm_kernel python tools_ncu_targets.py --model (ResNet-50, batch 256, second forward)"}
+           "gpu__time_duration.sum -k regex:gemm_kernel python tools/ncu_targets.py --model (ResNet-50, batch 256, second forward)"}
     json.dump(out, open(dst, "w"), indent=1)
     print(json.dumps(out))
 

@@ -2,7 +2,7 @@
 precision given by --passes (16 = fp16 single plane, 3 = split-bf16)."""
 import sys, os
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from robustart_b200 import nets, ops
 dev = torch.device("cuda", 0)
 imgs = [torch.randint(0, 256, (256, 224, 224, 3), dtype=torch.uint8, device=dev) for _ in range(4)]

@@ -1,9 +1,9 @@
-"""Per-op CUDA-event time of one eager forward (batch given) for any model family: python tools_op_times.py arch [batch] [passes]
+"""Per-op CUDA-event time of one eager forward (batch given) for any model family: python tools/op_times.py arch [batch] [passes]
 Wraps every public function of robustart_b200.ops that a forward calls; prints the share of each op name (with the
 activation / shape class for linear and conv)."""
 import collections, json, os, sys
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from robustart_b200 import nets, ops
 
 arch = sys.argv[1]

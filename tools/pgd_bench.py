@@ -1,6 +1,6 @@
 """PGD-Linf k-step eval loop: images/s and tensor-pipe fraction, native dgrad vs autograd twin.
 
-  python tools_pgd_bench.py [--n 128] [--steps 10] [--arch resnet50|resnet18|vit_b16_224|mixer_b16_224] [--autograd]
+  python tools/pgd_bench.py [--n 128] [--steps 10] [--arch resnet50|resnet18|vit_b16_224|mixer_b16_224] [--autograd]
 
 The token archs (BASELINE configs[2] / [4]) use the input-gradient pass of DESIGN.md section 4d as the native source.
 """
@@ -11,7 +11,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from robustart_b200 import attacks, nets, ops, torch_models  # noqa: E402
 
 FWD_GFLOP = {"resnet50": 8.18, "resnet18": 3.62, "vit_b16_224": 35.1, "mixer_b16_224": 25.2}

@@ -1,7 +1,7 @@
 """Stem timing, fp16 mode, batch 256: one-launch stem (conv1+bn+relu+maxpool) vs the two-launch path it replaces."""
 import json, os, sys
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from robustart_b200 import ops
 dev = torch.device("cuda", 0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256

@@ -1,7 +1,7 @@
 """BASELINE configs[3]: EfficientNet-B0 / MobileNetV2 + the full ImageNet-C 15 x 5 sweep on one GPU (the 8-GPU run shards
 images, no data-path collective).  Per cell: corruption kernel -> forward (CUDA graph) -> counters, batch 256; reports
 corrupted images/s over the whole sweep and the share of time spent in the corruption kernels.
-  python tools_sweep_bench.py [batch]"""
+  python tools/sweep_bench.py [batch]"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from robustart_b200 import nets, ops  # noqa: E402
 from robustart_b200.solver import EvalSolver  # noqa: E402
 

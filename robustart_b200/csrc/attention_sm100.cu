@@ -91,9 +91,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const uint32_t tm_s = tmem_base, tm_o = tmem_base + 256;
 
   if (warp == AT_MMA_WARP) {
-    // bf16 A/B (bits 7, 10), fp32 accumulator (bit 4), M = 128
-    const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Tk >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B is MN-major */ | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // fp16 A/B (format bits 7, 10 = 0), fp32 accumulator (bit 4), M = 128
+    const uint32_t idesc_s = (1u << 4) | ((uint32_t)(Tk >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_o = (1u << 4) | (1u << 16) /* B is MN-major */ | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     if (elect_one()) {
       mbar_expect_tx(bar0, 2u * 16384u + 4u * kv_bytes);
       for (int pl = 0; pl < 2; ++pl) {
@@ -171,8 +171,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           const float e0 = col < p.T ? ex2_approx(fmaf(__uint_as_float(v[g * 8 + 2 * j]), k2, mk)) : 0.f;
           const float e1 = col + 1 < p.T ? ex2_approx(fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), k2, mk)) : 0.f;
           sum += e0 + e1;
-          ph[j] = cvt_bf16x2(e1, e0);
-          pl[j] = cvt_bf16x2(e1 - __uint_as_float(ph[j] & 0xFFFF0000u), e0 - __uint_as_float(ph[j] << 16));
+          split_f16x2(e1, e0, ph[j], pl[j]);
         }
         const int chunk = ((c & 1) * 4 + g) ^ (row & 7);          // SWIZZLE_128B position of this 16-byte chunk
         *reinterpret_cast<uint4*>(tile + (chunk << 4)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -200,8 +199,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float x0 = __uint_as_float(v[g * 8 + 2 * j]) * inv, x1 = __uint_as_float(v[g * 8 + 2 * j + 1]) * inv;
-            ph[j] = cvt_bf16x2(x1, x0);
-            pl[j] = cvt_bf16x2(x1 - __uint_as_float(ph[j] & 0xFFFF0000u), x0 - __uint_as_float(ph[j] << 16));
+            split_f16x2(x1, x0, ph[j], pl[j]);
           }
           *reinterpret_cast<uint4*>(p.out_hi + orow + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
           *reinterpret_cast<uint4*>(p.out_lo + orow + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -246,10 +244,10 @@ int b200r_attention_tc(const uint16_t* qkv, uint16_t* out, int n, int tokens, in
   cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
   cuuint32_t estr[3] = {1, 1, 1};
   cuuint32_t box_q[3] = {AT_D, 128, 1}, box_kv[3] = {AT_D, (cuuint32_t)Tk, 1};
-  CUresult r = enc(&mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(qkv), dims, strides, box_q, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<uint16_t*>(qkv), dims, strides, box_q, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r == CUDA_SUCCESS)
-    r = enc(&mkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(qkv), dims, strides, box_kv, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    r = enc(&mkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<uint16_t*>(qkv), dims, strides, box_kv, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(attention) failed: %d", (int)r); return B200R_ECUDA; }
   AttnParams p;

@@ -31,7 +31,7 @@ __device__ __forceinline__ void load8(const uint4* __restrict__ ph, const uint4*
     const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      v[j] = bf16_bits_to_f32((uint16_t)(aw[j >> 1] >> (16 * (j & 1)))) + bf16_bits_to_f32((uint16_t)(bw[j >> 1] >> (16 * (j & 1))));
+      v[j] = plane_bits_to_f32((uint16_t)(aw[j >> 1] >> (16 * (j & 1)))) + plane_bits_to_f32((uint16_t)(bw[j >> 1] >> (16 * (j & 1))));
   }
 }
 template <bool F16>
@@ -47,8 +47,8 @@ __device__ __forceinline__ void unpack8r(const uint4& a, const uint4& b, float (
     const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      v[2 * j] = __uint_as_float(aw[j] << 16) + __uint_as_float(bw[j] << 16);
-      v[2 * j + 1] = __uint_as_float(aw[j] & 0xFFFF0000u) + __uint_as_float(bw[j] & 0xFFFF0000u);
+      v[2 * j] = plane_lo16_f32(aw[j]) + plane_lo16_f32(bw[j]);
+      v[2 * j + 1] = plane_hi16_f32(aw[j]) + plane_hi16_f32(bw[j]);
     }
   }
 }
@@ -62,8 +62,8 @@ __device__ __forceinline__ void store8(uint4* __restrict__ ph, uint4* __restrict
       rh[j] = *reinterpret_cast<const uint32_t*>(&h);
     } else {
       uint16_t h0, l0, h1, l1;
-      split_bf16(v[2 * j], h0, l0);
-      split_bf16(v[2 * j + 1], h1, l1);
+      split_pair(v[2 * j], h0, l0);
+      split_pair(v[2 * j + 1], h1, l1);
       rh[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
       rl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
     }
@@ -74,7 +74,7 @@ __device__ __forceinline__ void store8(uint4* __restrict__ ph, uint4* __restrict
 
 __device__ __forceinline__ uint32_t pack2(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }
 __device__ __forceinline__ float plane_val(uint32_t hw, uint32_t lw, int odd) {
-  return bf16_bits_to_f32((uint16_t)(hw >> (16 * odd))) + bf16_bits_to_f32((uint16_t)(lw >> (16 * odd)));
+  return plane_bits_to_f32((uint16_t)(hw >> (16 * odd))) + plane_bits_to_f32((uint16_t)(lw >> (16 * odd)));
 }
 
 inline unsigned grid_for(size_t items) {
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const uint4* __restr
           const uint16_t ab = (uint16_t)(aw[j] >> (16 * o));
           const bool pos = ab != 0 && !(ab & 0x8000u);
           const float v = (pos ? plane_val(hw[j], lw[j], o) : 0.f) + plane_val(bhw[j], blw[j], o);
-          split_bf16(v, h2[o], l2[o]);
+          split_pair(v, h2[o], l2[o]);
         }
         rh[j] = pack2(h2[0], h2[1]);
         rl[j] = pack2(l2[0], l2[1]);

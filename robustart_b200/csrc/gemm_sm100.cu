@@ -59,7 +59,7 @@ struct GemmParams {
   // STEM variant only: the A operand is gathered from the raw uint8 NHWC image by producer warps
   const uint8_t* img;       // [N, H_in, W_in, 3] uint8 (STEM_MODE 1)  or  float32 [N, 3, H_in, W_in] (STEM_MODE 2)
   float nmean[3], nstd[3];  // STEM_MODE 2: Normalize constants (mode 1 has them baked into the LUT)
-  const uint32_t* lut;      // [3][256]: normalised value of byte b in channel c as (hi | lo << 16) bf16 pair
+  const uint32_t* lut;      // [3][256]: normalised value of byte b in channel c as (hi | lo << 16) fp16 pair
   int H_in, W_in, stem_Ho, stem_Wo;
   long long M_total;        // N * Ho * Wo
 };
@@ -114,8 +114,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   constexpr int STAGE_BYTES = B_OFF + (F16 ? 1 : 2) * B_TILE_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers (power of two: 128 or 256)
   // instruction descriptor: fp32 accumulator (bit 4), A/B format (bits 7, 10: 1 = bf16, 0 = fp16), N >> 3, M >> 4
-  constexpr uint32_t IDESC = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-  constexpr uint32_t IDESC_RES = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // residual k-blocks: N = 64
+  // (both precisions now feed fp16 operands: split planes are fp16 pairs)
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  constexpr uint32_t IDESC_RES = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // residual k-blocks: N = 64
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -434,8 +435,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     const float x0 = f[8 * q + 2 * j], x1 = f[8 * q + 2 * j + 1];
-                    ph[j] = cvt_bf16x2(x1, x0);
-                    pl[j] = cvt_bf16x2(x1 - __uint_as_float(ph[j] & 0xFFFF0000u), x0 - __uint_as_float(ph[j] << 16));
+                    split_f16x2(x1, x0, ph[j], pl[j]);
                   }
                   // 64-byte rows in the TMA SWIZZLE_64B pattern (16-byte chunk index ^= (row >> 1) & 3): conflict-free stores
                   const int pos = (q ^ ((r >> 1) & 3)) * 16;
@@ -553,8 +553,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 ld_global_v8(p.res_lo + off + 16 * q, lw);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  f[16 * q + 2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-                  f[16 * q + 2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+                  const float2 rh = f16x2_to_f32(hw[j]), rl = f16x2_to_f32(lw[j]);
+                  f[16 * q + 2 * j] += rh.x + rl.x;
+                  f[16 * q + 2 * j + 1] += rh.y + rl.y;
                 }
               }
             }
@@ -563,7 +564,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             for (int j = 0; j < 32; ++j)   // compile-time j: the arrays must stay in registers
               if (col0 + j < p.Cout)
                 f[j] += F16 ? __half2float(__ushort_as_half(p.res_hi[off + j]))
-                            : bf16_bits_to_f32(p.res_hi[off + j]) + bf16_bits_to_f32(p.res_lo[off + j]);
+                            : plane_bits_to_f32(p.res_hi[off + j]) + plane_bits_to_f32(p.res_lo[off + j]);
           }
         }
         if (p.mask_hi && row_ok) {                        // ReLU backward fused into the dgrad GEMM: one bf16 plane read
@@ -612,9 +613,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               ph[j] = cvt_f16x2(f[2 * j + 1], f[2 * j]);
               pl[j] = 0u;
             } else {
-              ph[j] = cvt_bf16x2(f[2 * j + 1], f[2 * j]);
-              const float h0 = __uint_as_float(ph[j] << 16), h1 = __uint_as_float(ph[j] & 0xFFFF0000u);
-              pl[j] = cvt_bf16x2(f[2 * j + 1] - h1, f[2 * j] - h0);
+              split_f16x2(f[2 * j + 1], f[2 * j], ph[j], pl[j]);
             }
           }
           if (F16 && p.tma_store) {
@@ -744,7 +743,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           for (int j = 0; j < 4; ++j) {
             uint16_t hh, ll;
             if (F16) { hh = __half_as_ushort(__float2half_rn((__uint_as_float(w4v[j]) - mu) / sd)); ll = 0; }
-            else split_bf16((__uint_as_float(w4v[j]) - mu) / sd, hh, ll);   // same arithmetic as b200r_stem_im2col_f32
+            else split_pair((__uint_as_float(w4v[j]) - mu) / sd, hh, ll);   // same arithmetic as b200r_stem_im2col_f32
             s_conv[d0 + 3 * j] = zero ? 0u : ((uint32_t)hh | ((uint32_t)ll << 16));
           }
         } else {
@@ -880,7 +879,7 @@ int make_map5(EncodeTiledFn enc, CUtensorMap* m, const uint16_t* base, int C, in
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)plane_elems * 2};
   cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), (cuuint32_t)box_n, 1};
   cuuint32_t estr[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
-  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(base), dims,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<uint16_t*>(base), dims,
                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     b200r_set_error("cuTensorMapEncodeTiled(%s) failed: %d (N=%d H=%d W=%d C=%d box %d,%d,%d,%d s=%d)", what, (int)r, N, H, W, C, box_n,
@@ -901,7 +900,7 @@ int get_identity(const uint16_t** out, bool f16) {
   if (!g_ident[dev][f16]) {  // first use per device: blocking copy (not capturable)
     static uint16_t h[256 * 256];
     memset(h, 0, sizeof(h));
-    for (int i = 0; i < 256; ++i) h[i * 256 + i] = f16 ? 0x3C00 : 0x3F80;   // 1.0
+    for (int i = 0; i < 256; ++i) h[i * 256 + i] = 0x3C00;   // 1.0 (fp16 in both precisions)
     B200R_CUDA(cudaMalloc(&g_ident[dev][f16], sizeof(h)));
     B200R_CUDA(cudaMemcpy(g_ident[dev][f16], h, sizeof(h), cudaMemcpyHostToDevice));
   }
@@ -939,7 +938,7 @@ int finish_maps(EncodeTiledFn enc, GemmMaps* m, GemmParams* p, const uint16_t* r
     cuuint64_t strides[1] = {512};
     cuuint32_t box[2] = {(cuuint32_t)BK, 64};     // the 64 x 64 identity block (the kernel slides the accumulator columns instead)
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&m->i, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(ident), dims, strides, box, estr,
+    CUresult r = enc(&m->i, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(ident), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(identity) failed: %d", (int)r); return B200R_ECUDA; }
@@ -1016,7 +1015,7 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
     cuuint64_t strides[2] = {K * 2, (cuuint64_t)wcount * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&m.b, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
+    CUresult r = enc(&m.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(B) failed: %d (Cout=%d K=%llu)", (int)r, Cout, (unsigned long long)K); return B200R_ECUDA; }
@@ -1053,19 +1052,6 @@ struct StemLut { uint32_t* d = nullptr; float key[6] = {0, 0, 0, 0, 0, 0}; };
 StemLut g_stem_lut[8][2];
 std::mutex g_stem_mu;
 
-uint16_t host_bf16(float v) {
-  uint32_t u;
-  memcpy(&u, &v, 4);
-  u += 0x7FFFu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
-}
-float host_bf16_to_f32(uint16_t b) {
-  uint32_t u = (uint32_t)b << 16;
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
-}
-
 uint16_t host_f16(float v) { return __half_as_ushort(__float2half_rn(v)); }
 
 int get_stem_lut(const float* mean, const float* stdv, const uint32_t** out, bool f16) {
@@ -1081,7 +1067,7 @@ int get_stem_lut(const float* mean, const float* stdv, const uint32_t** out, boo
     for (int c = 0; c < 3; ++c)
       for (int b = 0; b < 256; ++b) {
         const float v = ((float)b / 255.0f - mean[c]) / stdv[c];   // ToTensor + Normalize in fp32
-        const uint16_t hi = f16 ? host_f16(v) : host_bf16(v), lo = f16 ? (uint16_t)0 : host_bf16(v - host_bf16_to_f32(hi));
+        const uint16_t hi = host_f16(v), lo = f16 ? (uint16_t)0 : host_f16(v - __half2float(__ushort_as_half(hi)));
         h[c * 256 + b] = (uint32_t)hi | ((uint32_t)lo << 16);
       }
     if (!L.d) B200R_CUDA(cudaMalloc(&L.d, sizeof(h)));
@@ -1127,7 +1113,7 @@ static int stem_impl(const void* img, bool f32, const uint16_t* wgt, const float
     cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)Cout * K * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, 64, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&m.b, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
+    CUresult r = enc(&m.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(stem B) failed: %d", (int)r); return B200R_ECUDA; }

@@ -17,17 +17,17 @@ __device__ __forceinline__ uint32_t f2_to_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }
+__device__ __forceinline__ uint32_t pack_u16x2(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }
 
 __global__ void __launch_bounds__(kThreads) split_kernel(const float4* __restrict__ in, uint2* __restrict__ hi,
                                                           uint2* __restrict__ lo, size_t count4) {
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < count4; i += (size_t)gridDim.x * kThreads) {
     float4 v = ld_stream_f4(in + i);
     uint16_t h[4], l[4];
-    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
-    split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
-    hi[i] = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-    lo[i] = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+    split_pair(v.x, h[0], l[0]); split_pair(v.y, h[1], l[1]);
+    split_pair(v.z, h[2], l[2]); split_pair(v.w, h[3], l[3]);
+    hi[i] = make_uint2(pack_u16x2(h[0], h[1]), pack_u16x2(h[2], h[3]));
+    lo[i] = make_uint2(pack_u16x2(l[0], l[1]), pack_u16x2(l[2], l[3]));
   }
 }
 
@@ -36,10 +36,10 @@ __global__ void __launch_bounds__(kThreads) merge_kernel(const uint2* __restrict
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < count4; i += (size_t)gridDim.x * kThreads) {
     uint2 h = hi[i], l = lo[i];
     float4 v;
-    v.x = bf16_bits_to_f32(h.x & 0xFFFF) + bf16_bits_to_f32(l.x & 0xFFFF);
-    v.y = bf16_bits_to_f32(h.x >> 16) + bf16_bits_to_f32(l.x >> 16);
-    v.z = bf16_bits_to_f32(h.y & 0xFFFF) + bf16_bits_to_f32(l.y & 0xFFFF);
-    v.w = bf16_bits_to_f32(h.y >> 16) + bf16_bits_to_f32(l.y >> 16);
+    v.x = plane_bits_to_f32(h.x & 0xFFFF) + plane_bits_to_f32(l.x & 0xFFFF);
+    v.y = plane_bits_to_f32(h.x >> 16) + plane_bits_to_f32(l.x >> 16);
+    v.z = plane_bits_to_f32(h.y & 0xFFFF) + plane_bits_to_f32(l.y & 0xFFFF);
+    v.w = plane_bits_to_f32(h.y >> 16) + plane_bits_to_f32(l.y >> 16);
     out[i] = v;
   }
 }
@@ -78,10 +78,10 @@ __global__ void __launch_bounds__(kThreads) stem_im2col_kernel(const void* __res
           v = (x - nm.mean[c]) / nm.std[c];
         }
       }
-      split_bf16(v, hh[j], ll[j]);
+      split_pair(v, hh[j], ll[j]);
     }
-    hi[t] = make_uint4(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]), pack_bf16x2(hh[4], hh[5]), pack_bf16x2(hh[6], hh[7]));
-    lo[t] = make_uint4(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]), pack_bf16x2(ll[4], ll[5]), pack_bf16x2(ll[6], ll[7]));
+    hi[t] = make_uint4(pack_u16x2(hh[0], hh[1]), pack_u16x2(hh[2], hh[3]), pack_u16x2(hh[4], hh[5]), pack_u16x2(hh[6], hh[7]));
+    lo[t] = make_uint4(pack_u16x2(ll[0], ll[1]), pack_u16x2(ll[2], ll[3]), pack_u16x2(ll[4], ll[5]), pack_u16x2(ll[6], ll[7]));
   }
 }
 
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_kernel(const uint4* __restri
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint32_t hb = (aw[j >> 1] >> (16 * (j & 1))) & 0xFFFF, lb = (bw[j >> 1] >> (16 * (j & 1))) & 0xFFFF;
-          float v = bf16_bits_to_f32((uint16_t)hb) + bf16_bits_to_f32((uint16_t)lb);
+          float v = plane_bits_to_f32((uint16_t)hb) + plane_bits_to_f32((uint16_t)lb);
           if (v > best[j]) { best[j] = v; bh[j] = hb; bl[j] = lb; }
         }
       }
@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(1024) avgpool_flat_kernel(const uint4* __restr
         const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          s[2 * j] += __uint_as_float(aw[j] << 16) + __uint_as_float(bw[j] << 16);
-          s[2 * j + 1] += __uint_as_float(aw[j] & 0xFFFF0000u) + __uint_as_float(bw[j] & 0xFFFF0000u);
+          s[2 * j] += plane_lo16_f32(aw[j]) + plane_lo16_f32(bw[j]);
+          s[2 * j + 1] += plane_hi16_f32(aw[j]) + plane_hi16_f32(bw[j]);
         }
       }
     }
@@ -219,9 +219,9 @@ __global__ void __launch_bounds__(1024) avgpool_flat_kernel(const uint4* __restr
     } else {
       uint16_t hh[8], ll[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split_bf16(v[j], hh[j], ll[j]);
-      yhi[o] = make_uint4(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]), pack_bf16x2(hh[4], hh[5]), pack_bf16x2(hh[6], hh[7]));
-      ylo[o] = make_uint4(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]), pack_bf16x2(ll[4], ll[5]), pack_bf16x2(ll[6], ll[7]));
+      for (int j = 0; j < 8; ++j) split_pair(v[j], hh[j], ll[j]);
+      yhi[o] = make_uint4(pack_u16x2(hh[0], hh[1]), pack_u16x2(hh[2], hh[3]), pack_u16x2(hh[4], hh[5]), pack_u16x2(hh[6], hh[7]));
+      ylo[o] = make_uint4(pack_u16x2(ll[0], ll[1]), pack_u16x2(ll[2], ll[3]), pack_u16x2(ll[4], ll[5]), pack_u16x2(ll[6], ll[7]));
     }
   }
 }

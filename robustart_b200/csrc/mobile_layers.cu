@@ -14,8 +14,8 @@ __device__ __forceinline__ void unpack8(uint4 h, uint4 l, float* v) {
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-    v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+    v[2 * j] = plane_lo16_f32(hw[j]) + plane_lo16_f32(lw[j]);
+    v[2 * j + 1] = plane_hi16_f32(hw[j]) + plane_hi16_f32(lw[j]);
   }
 }
 __device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
@@ -23,8 +23,8 @@ __device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint16_t h0, l0, h1, l1;
-    split_bf16(v[2 * j], h0, l0);
-    split_bf16(v[2 * j + 1], h1, l1);
+    split_pair(v[2 * j], h0, l0);
+    split_pair(v[2 * j + 1], h1, l1);
     hw[j] = h0 | ((uint32_t)h1 << 16);
     lw[j] = l0 | ((uint32_t)l1 << 16);
   }
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kThreads) channel_scale_kernel(const uint4* __
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const size_t si = (size_t)im * s_stride + cc * 8 + j;
-      o[j] = v[j] * (bf16_bits_to_f32(sh[si]) + bf16_bits_to_f32(sl[si]));
+      o[j] = v[j] * (plane_bits_to_f32(sh[si]) + plane_bits_to_f32(sl[si]));
     }
     uint4 hh, ll;
     pack8(o, hh, ll);

@@ -135,12 +135,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
-// two fp32 -> packed bf16x2 (round to nearest even): `hi` lands in the upper half, `lo` in the lower
-__device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
-  uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
 // 256-bit global accesses (sm_100, PTX 8.8): one full 32-byte sector per thread per instruction
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
@@ -156,6 +150,12 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float hi, float lo) {
   uint32_t d;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
+}
+// (x1, x0) -> packed fp16 hi pair and packed fp16 lo pair of the split-plane format: hi = rn(x), lo = rn(x - hi)
+__device__ __forceinline__ void split_f16x2(float x1, float x0, uint32_t& ph, uint32_t& pl) {
+  ph = cvt_f16x2(x1, x0);
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&ph));      // .x = low half = x0's hi
+  pl = cvt_f16x2(x1 - h.y, x0 - h.x);
 }
 __device__ __forceinline__ float2 f16x2_to_f32(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

@@ -12,19 +12,19 @@ namespace {
 constexpr int kThreads = 256;
 
 __device__ __forceinline__ float pl_get(const uint16_t* hi, const uint16_t* lo, size_t i) {
-  return bf16_bits_to_f32(hi[i]) + bf16_bits_to_f32(lo[i]);
+  return plane_bits_to_f32(hi[i]) + plane_bits_to_f32(lo[i]);
 }
 __device__ __forceinline__ void pl_put(uint16_t* hi, uint16_t* lo, size_t i, float v) {
   uint16_t h, l;
-  split_bf16(v, h, l);
+  split_pair(v, h, l);
   hi[i] = h; lo[i] = l;
 }
 __device__ __forceinline__ void unpack8(uint4 h, uint4 l, float* v) {
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-    v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+    v[2 * j] = plane_lo16_f32(hw[j]) + plane_lo16_f32(lw[j]);
+    v[2 * j + 1] = plane_hi16_f32(hw[j]) + plane_hi16_f32(lw[j]);
   }
 }
 __device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
@@ -32,8 +32,8 @@ __device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint16_t h0, l0, h1, l1;
-    split_bf16(v[2 * j], h0, l0);
-    split_bf16(v[2 * j + 1], h1, l1);
+    split_pair(v[2 * j], h0, l0);
+    split_pair(v[2 * j + 1], h1, l1);
     hw[j] = h0 | ((uint32_t)h1 << 16);
     lw[j] = l0 | ((uint32_t)l1 << 16);
   }

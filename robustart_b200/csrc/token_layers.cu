@@ -15,19 +15,19 @@ namespace {
 constexpr int kThreads = 256;
 
 __device__ __forceinline__ float pl_get(const uint16_t* hi, const uint16_t* lo, size_t i) {
-  return bf16_bits_to_f32(hi[i]) + bf16_bits_to_f32(lo[i]);
+  return plane_bits_to_f32(hi[i]) + plane_bits_to_f32(lo[i]);
 }
 __device__ __forceinline__ void pl_put(uint16_t* hi, uint16_t* lo, size_t i, float v) {
   uint16_t h, l;
-  split_bf16(v, h, l);
+  split_pair(v, h, l);
   hi[i] = h; lo[i] = l;
 }
 __device__ __forceinline__ void unpack8(uint4 h, uint4 l, float* v) {
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-    v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+    v[2 * j] = plane_lo16_f32(hw[j]) + plane_lo16_f32(lw[j]);
+    v[2 * j + 1] = plane_hi16_f32(hw[j]) + plane_hi16_f32(lw[j]);
   }
 }
 __device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
@@ -35,8 +35,8 @@ __device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint16_t h0, l0, h1, l1;
-    split_bf16(v[2 * j], h0, l0);
-    split_bf16(v[2 * j + 1], h1, l1);
+    split_pair(v[2 * j], h0, l0);
+    split_pair(v[2 * j + 1], h1, l1);
     hw[j] = h0 | ((uint32_t)h1 << 16);
     lw[j] = l0 | ((uint32_t)l1 << 16);
   }
@@ -254,8 +254,8 @@ __global__ void __launch_bounds__(kThreads) channels_to_tokens_add_kernel(const 
     if (c < C && t < T) {
       const size_t i = ((size_t)b * C + c) * Tp + t;
       const uint32_t h = *reinterpret_cast<const uint32_t*>(yh + i), l = *reinterpret_cast<const uint32_t*>(yl + i);
-      v0 = __uint_as_float(h << 16) + __uint_as_float(l << 16);
-      v1 = __uint_as_float(h & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u);
+      v0 = plane_lo16_f32(h) + plane_lo16_f32(l);
+      v1 = plane_hi16_f32(h) + plane_hi16_f32(l);
     }
     tile[r][2 * tx] = v0;
     tile[r][2 * tx + 1] = v1;
@@ -266,11 +266,11 @@ __global__ void __launch_bounds__(kThreads) channels_to_tokens_add_kernel(const 
     if (t < T && c < C) {
       const size_t i = ((size_t)b * T + t) * C + c;
       const uint32_t h = *reinterpret_cast<const uint32_t*>(rh + i), l = *reinterpret_cast<const uint32_t*>(rl + i);
-      const float o0 = __uint_as_float(h << 16) + __uint_as_float(l << 16) + tile[2 * tx][r];
-      const float o1 = __uint_as_float(h & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u) + tile[2 * tx + 1][r];
+      const float o0 = plane_lo16_f32(h) + plane_lo16_f32(l) + tile[2 * tx][r];
+      const float o1 = plane_hi16_f32(h) + plane_hi16_f32(l) + tile[2 * tx + 1][r];
       uint16_t h0, l0, h1, l1;
-      split_bf16(o0, h0, l0);
-      split_bf16(o1, h1, l1);
+      split_pair(o0, h0, l0);
+      split_pair(o1, h1, l1);
       *reinterpret_cast<uint32_t*>(oh + i) = h0 | ((uint32_t)h1 << 16);
       *reinterpret_cast<uint32_t*>(ol + i) = l0 | ((uint32_t)l1 << 16);
     }

@@ -4,7 +4,7 @@ ResNet-18/50 in the reference's layout (prototype/prototype/model/resnet_officia
 330-346 == torchvision: stride on the 3x3 of a Bottleneck, bias-free convs, BatchNorm after every conv).
 A model is built from a plain state_dict with the reference's keys; BatchNorm (eval) is folded into a
 per-channel scale/bias applied in the GEMM epilogue, weights are re-laid out once to [Cout, KH, KW, Cin]
-split-bf16 planes.  Activations stay NHWC split-bf16 planes end to end; every layer is one launch of a
+split-fp16 planes.  Activations stay NHWC split-fp16 planes end to end; every layer is one launch of a
 kernel in libb200robust.so; the whole forward can be captured into one CUDA graph.
 """
 from __future__ import annotations
@@ -110,7 +110,9 @@ def _strip_prefix(sd):
     return out
 
 
-GRAD_SCALE_F16 = 4096.0      # loss scale of the fp16 input-gradient pass (|dlogits| <= 1 for CE: no overflow)
+GRAD_SCALE = 4096.0          # loss scale of every input-gradient pass: activations AND gradients live in fp16-coded planes (one
+                             # plane, or a hi/lo pair), and a classifier's gradients sit at 1e-4 .. 1e-10, below fp16's normal range
+GRAD_SCALE_F16 = GRAD_SCALE
 
 
 class _ConvBN:
@@ -293,7 +295,7 @@ class ResNet:
             self._stem_wt = ops.to_planes(wt.t().contiguous(), f16)                          # [192, 64]
         # fp16 planes: the pass runs on S * dlogits (gradients of a classifier sit at 1e-4 .. 1e-10, below fp16's
         # normal range) and 1/S is folded into the last kernel; the attacks only use the sign / direction anyway
-        S = GRAD_SCALE_F16 if f16 else 1.0
+        S = GRAD_SCALE
         g = ops.linear(ops.to_planes(dlogits.contiguous(), f16, S), self._fc_wt, passes=P)   # [P, n, c]
         last = saved["blocks"][-1][-1]
         g = ops.global_avgpool_bwd(g, last.shape[2], last.shape[3])
@@ -530,7 +532,8 @@ class ViT(_TokenModel):
         P = self.passes if passes is None else passes
         n, h, w, T = saved["shape"]
         hd = self.dim // self.heads
-        g = self.head.dgrad(ops.split_f32(dlogits.contiguous()), P)                   # [2, n, rep]
+        S = GRAD_SCALE                                                                # unscaled again by patch_scatter
+        g = self.head.dgrad(ops.to_planes(dlogits.contiguous(), False, S), P)         # [2, n, rep]
         if self.pre is not None:
             g = self.pre.dgrad(ops.act_bwd_planes(g, saved["pre_logits"], "tanh"), P)
         # encoder_norm only feeds x[:, 0]: LayerNorm is row-wise, so its backward runs on the class rows alone
@@ -545,7 +548,7 @@ class ViT(_TokenModel):
             t = ops.attention_bwd(qkv, b["out"].dgrad(g, P), n, T, self.heads, hd, hd ** -0.5)
             g = ops.layernorm_bwd(b["qkv"].dgrad(t, P), x_in, b["n1"][0], eps=1e-5, add=g)  # x_mid = x_in + attn(norm1(x_in))
         g = g.view(2, n, T, self.dim)[:, :, 1:].contiguous().view(2, n * (T - 1), self.dim)   # drop the class token
-        return ops.patch_scatter(self.embed.dgrad(g, P), n, h, w, self.patch)
+        return ops.patch_scatter(self.embed.dgrad(g, P), n, h, w, self.patch, unscale=1.0 / S)
 
 
 class Mixer(_TokenModel):
@@ -623,7 +626,8 @@ class Mixer(_TokenModel):
         """d loss / d x01 (float32 NCHW) from d loss / d logits; input gradients only (mlp_mixer.py:7-159 reversed)."""
         P = self.passes if passes is None else passes
         n, h, w, T = saved["shape"]
-        g = self.head.dgrad(ops.split_f32(dlogits.contiguous()), P)                   # [2, n, dim]
+        S = GRAD_SCALE                                                                # unscaled again by patch_scatter
+        g = self.head.dgrad(ops.to_planes(dlogits.contiguous(), False, S), P)         # [2, n, dim]
         g = ops.global_avgpool_bwd(g, T, 1).view(2, n * T, self.dim)                  # x.mean(dim=1) backward
         g = ops.layernorm_bwd(g, saved["final"], self.norm[0], eps=1e-6)
         zeros = torch.zeros_like(g)                                                   # residual operand of the plain transpose
@@ -634,7 +638,7 @@ class Mixer(_TokenModel):
             t = b["t1"].dgrad(ops.act_bwd_planes(b["t2"].dgrad(t, P), p1, "gelu_erf"), P)
             t = ops.channels_to_tokens_add(t, zeros, n, T, self.dim, self.T_PAD)
             g = ops.layernorm_bwd(t, x_in, b["n1"][0], eps=1e-6, add=g)                # x_mid = x_in + token_mix(norm1(x_in))
-        return ops.patch_scatter(self.embed.dgrad(g, P), n, h, w, self.patch)
+        return ops.patch_scatter(self.embed.dgrad(g, P), n, h, w, self.patch, unscale=1.0 / S)
 
 
 _TOKEN_ARCHS = {"vit_b16_224": (ViT, vit_spec), "vit_base_patch16_224": (ViT, vit_spec), "mixer_b16_224": (Mixer, mixer_spec)}

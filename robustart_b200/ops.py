@@ -222,13 +222,13 @@ def topk_count_(counters: torch.Tensor, logits: torch.Tensor, labels: torch.Tens
 
 
 # ------------------------------------------------------------------------------------------------
-# split-bf16 tensors + tensor-core contractions
+# split-plane tensors + tensor-core contractions
 # ------------------------------------------------------------------------------------------------
 ACT = {None: 0, "none": 0, "relu": 1, "relu6": 2, "gelu_tanh": 3, "gelu_erf": 4, "swish": 5, "tanh": 6}
 
 
 def split_f32(x: torch.Tensor) -> torch.Tensor:
-    """float32 tensor of shape S -> int16 tensor [2, *S] holding the (hi, lo) bf16 planes."""
+    """float32 tensor of shape S -> int16 tensor [2, *S] holding the (hi, lo) fp16 planes: hi = rn16(x), lo = rn16(x - hi)."""
     _need_cuda(x, torch.float32, "x")
     planes = torch.empty((2,) + tuple(x.shape), dtype=torch.int16, device=x.device)
     with torch.cuda.device(x.device):
@@ -244,15 +244,14 @@ def merge_f32(planes: torch.Tensor) -> torch.Tensor:
     return out
 
 
-PASSES_F16 = 16      # include/b200r.h B200R_PASSES_F16: tensors are ONE plane of fp16 ([1, ...] int16) instead of two bf16 planes
+PASSES_F16 = 16      # include/b200r.h B200R_PASSES_F16: tensors are ONE plane of fp16 ([1, ...] int16) instead of two fp16 (hi, lo) planes
 
 
 def to_planes(x: torch.Tensor, f16: bool = False, scale: float = 1.0) -> torch.Tensor:
-    """float32 tensor -> the activation / weight format of the chosen precision: split-bf16 planes [2, *S] or one fp16
+    """float32 tensor -> the activation / weight format of the chosen precision: split planes [2, *S] (fp16 hi + fp16 lo) or one fp16
     plane [1, *S] (optionally pre-scaled: the loss scaling of the fp16 input-gradient pass)."""
     if not f16:
-        assert scale == 1.0
-        return split_f32(x)
+        return split_f32(x if scale == 1.0 else x * scale)      # pre-scaling: a [n, classes] tensor (loss scale of the gradient pass)
     _need_cuda(x, torch.float32, "x")
     out = torch.empty((1,) + tuple(x.shape), dtype=torch.int16, device=x.device)
     with torch.cuda.device(x.device):
@@ -278,7 +277,7 @@ def _passes_for(x, passes):
 
 def conv2d_nhwc(x, wgt, scale=None, bias=None, res=None, *, stride=1, pad=0, act=None, passes=3, out=None,
                 out_f32=None, want_planes=True):
-    """x: planes [P,n,h,w,cin]; wgt: planes [P,cout,kh,kw,cin]; returns planes [P,n,ho,wo,cout] (P = 2 split-bf16, 1 fp16)."""
+    """x: planes [P,n,h,w,cin]; wgt: planes [P,cout,kh,kw,cin]; returns planes [P,n,ho,wo,cout] (P = 2 split hi/lo, 1 fp16)."""
     _need_cuda(x, torch.int16, "x")
     _need_cuda(wgt, torch.int16, "wgt")
     P, n, h, w, cin = x.shape
@@ -534,8 +533,9 @@ def stem_col2im(dcols, n, h, w, std=IMAGENET_STD, out=None, unscale: float = 1.0
         if dcols.shape[0] == 1:
             _lib.check(_lib.load().b200r_stem_col2im_f32_f16(dcols.data_ptr(), out.data_ptr(), n, h, w, _lib.f3(std), unscale, _stream()))
         else:
-            assert unscale == 1.0
-            _lib.check(_lib.load().b200r_stem_col2im_f32(dcols.data_ptr(), out.data_ptr(), n, h, w, _lib.f3(std), _stream()))
+            # split planes: the kernel divides by std, so the inverse loss scale rides on it
+            std_u = tuple(float(s) / unscale for s in std)
+            _lib.check(_lib.load().b200r_stem_col2im_f32(dcols.data_ptr(), out.data_ptr(), n, h, w, _lib.f3(std_u), _stream()))
     return out
 
 
@@ -632,9 +632,11 @@ def act_bwd_planes(dy, pre, act):
     return dx
 
 
-def patch_scatter(dcols, n, h, w, patch=16, std=IMAGENET_STD):
-    """dcols planes [2, n*(h/p)*(w/p), 3*p*p] -> float32 NCHW gradient w.r.t. the [0,1] image (transpose of patch_gather)."""
+def patch_scatter(dcols, n, h, w, patch=16, std=IMAGENET_STD, unscale: float = 1.0):
+    """dcols planes [2, n*(h/p)*(w/p), 3*p*p] -> float32 NCHW gradient w.r.t. the [0,1] image (transpose of patch_gather),
+    times `unscale` (the inverse loss scale of the pass; it rides on the 1/std the kernel applies)."""
     _need_cuda(dcols, torch.int16, "dcols")
+    std = tuple(float(s) / unscale for s in std)
     assert dcols[0].numel() == n * 3 * h * w
     dx = torch.empty((n, 3, h, w), dtype=torch.float32, device=dcols.device)
     with torch.cuda.device(dcols.device):

@@ -47,6 +47,12 @@ def ref_models():
     ]
 
 
+# share of the mean feature the head's bias cancels.  0.9 for the families whose features vary by >= 50 % between images; the
+# MobileNetV2 random-weight features vary by 20 % only, and cancelling 90 % of the mean there would make the logits a
+# small difference of large numbers (|s W f| of several hundred at logit std 2.5), which no trained network is
+CENTRE = {"mobilenet_v2": 0.6}
+
+
 def main():
     from util import diverse_images, calibrated_state_dict, HEAD_KEYS
     images = diverse_images(8, seed=0)
@@ -81,17 +87,19 @@ def main():
         h.remove()
         f = feats[0].double()
         W = head.weight.detach().double()
-        centred = (f - 0.9 * f.mean(0, keepdim=True)) @ W.t()
+        c = CENTRE.get(arch, 0.9)
+        centred = (f - c * f.mean(0, keepdim=True)) @ W.t()
         s = np.float32(2.5 / centred.std().item())
-        bias = (-(0.9 * float(s)) * (W @ f.mean(0))).float().numpy()
+        bias = (-(c * float(s)) * (W @ f.mean(0))).float().numpy()
         cal.update({arch + "/scale": s, arch + "/bias": bias})
         model.load_state_dict(calibrated_state_dict(arch, sd, cal), strict=True)
         with torch.no_grad():
             lg = model(xn)
         out.update(cal)
         out[arch + "/logits"] = lg.numpy()
-        print("%-16s scale %.3f  logits |max| %.2f std %.2f  top1 %s  (feature variation %.2f of |f|)" % (
-            arch, s, lg.abs().max(), lg.std(), lg.argmax(1).tolist(), ((f - f.mean(0)).norm() / f.norm()).item()))
+        print("%-16s scale %.3f  logits |max| %.2f std %.2f  top1 %s  (feature variation %.2f of |f|, |s W f| max %.1f)" % (
+            arch, s, lg.abs().max(), lg.std(), lg.argmax(1).tolist(), ((f - f.mean(0)).norm() / f.norm()).item(),
+            (float(s) * (f @ W.t())).abs().max().item()))
     np.savez_compressed(os.path.join(HERE, "calibrated_logits.npz"), **out)
 
 

@@ -168,15 +168,15 @@ def emu(tmp_path_factory):
     return _EmuLibs(tmp_path_factory.mktemp("emu"))
 
 
-# ---- split-bf16 planes on the host (common.cuh split_bf16: hi = RNE(v), lo = RNE(v - hi)) ----------------------------------
+# ---- split planes on the host (common.cuh split_pair: hi = RNE16(v), lo = RNE16(v - hi), both IEEE fp16) -------------------------
 def split(x):
-    hi = x.to(torch.bfloat16)
-    lo = (x - hi.float()).to(torch.bfloat16)
+    hi = x.to(torch.float16)
+    lo = (x - hi.float()).to(torch.float16)
     return torch.stack([hi.view(torch.int16), lo.view(torch.int16)]).contiguous()
 
 
 def merge(p):
-    return p[0].view(torch.bfloat16).float() + p[1].view(torch.bfloat16).float()
+    return p[0].view(torch.float16).float() + p[1].view(torch.float16).float()
 
 
 def rt(x):

@@ -85,11 +85,11 @@ def _install(monkeypatch):
         cols = F.unfold((img.to(DT) - m) / s, patch, stride=patch)          # [n, 3*p*p, np], column = c*p*p + ky*p + kx
         return _pl(cols.transpose(1, 2).reshape(-1, 3 * patch * patch))
 
-    def patch_scatter(dcols, n, h, w, patch=16, std=STD):     # token_backward.cu patch_scatter_kernel
+    def patch_scatter(dcols, n, h, w, patch=16, std=STD, unscale=1.0):     # token_backward.cu patch_scatter_kernel
         launched.append("patch_scatter")
         gh, gw = h // patch, w // patch
         d = dcols[0].reshape(n, gh, gw, 3, patch, patch).permute(0, 3, 1, 4, 2, 5).reshape(n, 3, h, w)
-        return (d / torch.tensor(std, dtype=DT).view(1, 3, 1, 1)).to(torch.float32)
+        return (d * unscale / torch.tensor(std, dtype=DT).view(1, 3, 1, 1)).to(torch.float32)
 
     def assemble_tokens(x, cls, pos, n, num_patches):
         c = x.shape[-1]

@@ -191,8 +191,9 @@ def add_noise_for_imagenet_s(image, decoder_type='pil', resize_type='pil-bilinea
 
 
 def pgd_l1(input, label, model, eps, input_size, eps_step, max_iter, batch_size):
-    # attack.py:44-49 delegates to ART (not vendored, unpinned); SURVEY 8(f) N4.
-    raise NotImplementedError("pgd_l1 (ART ProjectedGradientDescentPyTorch) is not part of the hot path yet")
+    # attack.py:44-49 delegates to ART's ProjectedGradientDescentPyTorch(norm=1) (not vendored, unpinned): same update rules on the
+    # device, no numpy round trip (robustart_b200.attacks.pgd_l1)
+    return _atk.pgd_l1(input, label, model, eps, input_size, eps_step, max_iter, batch_size)
 
 
 def autoattack_linf(input, label, model, norm, eps, version, verbose):

@@ -85,6 +85,11 @@ int b200r_corrupt_u8(int corruption_id, int severity, const uint8_t* in, uint8_t
                      int w, uint64_t seed, uint64_t image_offset, const float* ext_noise,
                      void* workspace, size_t workspace_bytes, b200r_stream_t stream);
 
+/* Host-only: the quantile table the device-RNG gaussian / speckle kernels draw their normals from, unit scale, as
+ * z[row * 64 + stratum] (256 rows x 64 strata): a random byte picks the row, lane and loop iteration pick the stratum.  Lets a test
+ * check the distribution the kernel produces (corruptions.py:122-126,143-147 draw np.random.normal).  No GPU needed. */
+int b200r_normal_strata_table(double* z16384);
+
 /* Optional assets: frost textures (corruptions.py:250-260 reads frost{1..6}.{png,jpg}; the files
  * are not in the reference repo).  rgb: device uint8 [th,tw,3]; slot in [0,6). */
 int b200r_set_frost_texture(int slot, const uint8_t* rgb, int th, int tw);
@@ -161,6 +166,26 @@ int b200r_square_propose_linf(const float* x_best, const float* x0, float* out, 
 /* dst[i, :] = src[i, :] where mask[i] != 0 (masked accept of Square / best-point bookkeeping) */
 int b200r_masked_rows_copy(float* dst, const float* src, const uint8_t* mask, size_t n, size_t chw,
                            b200r_stream_t stream);
+
+/* FAB's projection_linf (Attacks/autoattack/fab_projections.py:7-59): row r of t is projected onto the hyperplane
+ * <w[r], x> = b[r] intersected with the box [0,1]^dim, minimising the Linf norm of the step; d receives the step.  Sort-free
+ * (Newton on the per-row threshold, double accumulation).  dmax (nullable): device float[rows] = max |d| per row (the a0 of
+ * fab_base.py:200); passes (nullable): device int[rows] = number of passes each row took (diagnostics). */
+int b200r_fab_projection_linf(const float* t, const float* w, const float* b, float* d, float* dmax, int rows,
+                              int dim, int* passes, b200r_stream_t stream);
+/* FAB's update (fab_base.py:200-232): alpha = min(max(a1 / (a1 + a2), 0), alpha_max) with a = max(dmax, 1e-8);
+ * x1 <- clamp((x1 + eta d1) (1 - alpha) + (x0 + eta d2) alpha, 0, 1), in place. */
+int b200r_fab_combine_linf(float* x1, const float* d1, const float* x0, const float* d2, const float* dmax1,
+                           const float* dmax2, int rows, int dim, float eta, float alpha_max, b200r_stream_t stream);
+/* APGD-L1's L1_projection (Attacks/autoattack/autopgd_base.py:19-83): x = centre, y = perturbation, delta such that
+ * ||y + delta||_1 <= eps and 0 <= x + y + delta <= 1.  Sort-free (safeguarded Newton on the threshold). */
+int b200r_l1_projection(const float* x, const float* y, float* delta, int rows, int dim, float eps,
+                        b200r_stream_t stream);
+/* One PGD-L1 step of ART's ProjectedGradientDescentPyTorch(norm=1) (called from adv/attack.py:44-49; ART itself is not
+ * vendored by the reference): x <- x0 + scale * (clip(x + eps_step g / (||g||_1 + 1e-7), 0, 1) - x0),
+ * scale = min(1, eps / (||.||_1 + 1e-7)); in place, one CTA per sample. */
+int b200r_pgd_step_l1(float* x, const float* g, const float* x0, int rows, int dim, float eps_step, float eps,
+                      b200r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contractions on the tcgen05 tensor cores ("split-bf16" activations: every fp32 tensor

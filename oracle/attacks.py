@@ -77,3 +77,16 @@ def mim_linf(model_norm_fn, X, y, epsilon, num_steps, step_size, decay_factor=1.
         eta = (X_pgd - X).clamp(-epsilon, epsilon)
         X_pgd = (X + eta).clamp(0, 1.0)
     return X_pgd
+
+
+def pgd_l1_step(x, g, x0, eps_step, eps, tol=1e-7):
+    """One step of ART's ProjectedGradientDescentPyTorch(norm=1) (third-party, NOT vendored and not pinned by the reference's
+    requirements.txt:25 -- `adversarial-robustness-toolbox`; the statement follows art/attacks/evasion/projected_gradient_descent/
+    projected_gradient_descent_pytorch.py of ART 1.7-1.16: _compute_perturbation, _apply_perturbation, _projection).  PARITY
+    UNPINNED: ART is absent here; anchored on the call site adv/attack.py:44-49 (norm=1, clip_values (0,1))."""
+    n = x.shape[0]
+    gn = g / (g.reshape(n, -1).abs().sum(1).view(-1, *([1] * (x.dim() - 1))) + tol)
+    x = torch.clamp(x + eps_step * gn, 0.0, 1.0)
+    delta = (x - x0).reshape(n, -1)
+    delta = delta * torch.clamp(eps / (delta.abs().sum(1, keepdim=True) + tol), max=1.0)
+    return x0 + delta.reshape(x.shape)

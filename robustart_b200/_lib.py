@@ -30,6 +30,11 @@ SIGNATURES = {
     "b200r_corrupt_u8": (C.c_int, [C.c_int, C.c_int, c_u8p, c_u8p, C.c_int, C.c_int, C.c_int,
                                    C.c_uint64, C.c_uint64, c_f32p, C.c_void_p, C.c_size_t, c_stream]),
     "b200r_set_frost_texture": (C.c_int, [C.c_int, c_u8p, C.c_int, C.c_int]),
+    "b200r_normal_strata_table": (C.c_int, [C.c_void_p]),
+    "b200r_fab_projection_linf": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_void_p, c_stream]),
+    "b200r_fab_combine_linf": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, C.c_float, c_stream]),
+    "b200r_l1_projection": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, c_stream]),
+    "b200r_pgd_step_l1": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, C.c_float, c_stream]),
     "b200r_u8nhwc_to_f32nchw": (C.c_int, [c_u8p, c_f32p, C.c_int, C.c_int, C.c_int, c_host_f3,
                                           c_host_f3, c_stream]),
     "b200r_normalize_f32nchw": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_host_f3,

@@ -178,6 +178,37 @@ def pgd_l2(input, label, f_model, eps, rel_stepsize, steps, *, random_start=True
     return x
 
 
+def pgd_l1(input, label, model, eps, input_size=None, eps_step=120.0, max_iter=20, batch_size=16, *, seed: Optional[int] = None,
+           start: Optional[torch.Tensor] = None):
+    """attack.py:44-49: ART's ProjectedGradientDescentPyTorch(norm=1, eps, eps_step, max_iter, num_random_init=1, batch_size) on a
+    PyTorchClassifier with clip_values (0, 1) and ImageNet preprocessing -- `model` takes NORMALISED input, like mim / autoattack.
+    ART is not vendored by the reference and not version-pinned: the update rules follow ART 1.7-1.16 (oracle.attacks.pgd_l1_step
+    states them; PARITY UNPINNED).  What ART does per internal batch of `batch_size` (16) samples on the host -- numpy round trip
+    included -- runs here on the whole device batch: the loss is a mean over the batch, but the L1-normalised step makes the
+    update invariant to that scale, so the result does not depend on the batching.
+      start: x_adv = clip(x + r), r = R * (Dirichlet(1..1) spacings) * random signs, R = sqrt(U(0, eps^2))   (ART random_sphere, norm 1)
+      step:  g /= ||g||_1 + 1e-7; x = clip(x + eps_step g); delta = (x - x0) * min(1, eps / (||x - x0||_1 + 1e-7)); x = x0 + delta
+    `start` overrides the random perturbation r (tests)."""
+    x0, y = _prep(input, label)
+    n = x0.shape[0]
+    f_model = as_f_model(model)
+    if start is None:
+        gen = None
+        if seed is not None:
+            gen = torch.Generator(device=x0.device)
+            gen.manual_seed(seed)
+        dim = x0[0].numel()
+        e = torch.empty(n, dim, device=x0.device).exponential_(generator=gen)      # spacings of sorted uniforms = normalised exponentials
+        r = torch.sqrt(torch.rand(n, 1, device=x0.device, generator=gen) * float(eps) ** 2)
+        sgn = torch.randint(0, 2, (n, dim), device=x0.device, generator=gen).float() * 2 - 1
+        start = (e / e.sum(1, keepdim=True) * r * sgn).reshape(x0.shape)
+    x = (x0 + start).clamp_(0, 1).contiguous()
+    for _ in range(int(max_iter)):
+        g = _input_grad(f_model, x, y, grad_scale=1.0 / n)
+        ops.pgd_step_l1_(x, g, x0, float(eps_step), float(eps))
+    return x
+
+
 def mim_linf(input, label, model, eps, num_steps, step_size, decay_factor, *, seed: Optional[int] = None,
              start_uniform: Optional[torch.Tensor] = None):
     """_mim_whitebox (imfgsm_attack.py:62-93): `model` takes NORMALISED input; CE *mean* loss; the random

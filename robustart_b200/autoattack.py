@@ -242,45 +242,10 @@ class Square:
 # FAB-T (Linf)
 # ------------------------------------------------------------------------------------------------
 def projection_linf(t, w, b):
-    """fab_projections.py:7-59: project the rows of t onto {x: <w,x> = b} intersected with the box [0,1]^d,
-    minimising the Linf norm of the step."""
-    w, b = w.clone(), b.clone()
-    sign = 2 * ((w * t).sum(1) - b >= 0) - 1
-    w.mul_(sign.unsqueeze(1))
-    b.mul_(sign)
-    a = (w < 0).float()
-    d = (a - t) * (w != 0).float()
-    p = a - t * (2 * a - 1)
-    indp = torch.argsort(p, dim=1)
-    b = b - (w * t).sum(1)
-    b0 = (w * d).sum(1)
-    indp2 = indp.flip((1,))
-    ws = w.gather(1, indp2)
-    bs2 = -ws * d.gather(1, indp2)
-    s = torch.cumsum(ws.abs(), dim=1)
-    sb = torch.cumsum(bs2, dim=1) + b0.unsqueeze(1)
-    b2 = sb[:, -1] - s[:, -1] * p.gather(1, indp[:, 0:1]).squeeze(1)
-    c_l = b - b2 > 0
-    c2 = (b - b0 > 0) & (~c_l)
-    lb = torch.zeros(int(c2.sum()), device=t.device)
-    ub = torch.full_like(lb, w.shape[1] - 1)
-    indp_, sb_, s_, p_, b_ = indp[c2], sb[c2], s[c2], p[c2], b[c2]
-    for _ in range(math.ceil(math.log2(w.shape[1]))):
-        c4 = torch.floor((lb + ub) / 2)
-        c2i = c4.long().unsqueeze(1)
-        indcurr = indp_.gather(1, indp_.size(1) - 1 - c2i)
-        bb = (sb_.gather(1, c2i) - s_.gather(1, c2i) * p_.gather(1, indcurr)).squeeze(1)
-        cc = b_ - bb > 0
-        lb = torch.where(cc, c4, lb)
-        ub = torch.where(cc, ub, c4)
-    lb = lb.long()
-    if c_l.any():
-        lm = torch.clamp_min((b[c_l] - sb[c_l, -1]) / (-s[c_l, -1]), min=0).unsqueeze(-1)
-        d[c_l] = (2 * a[c_l] - 1) * lm
-    u = torch.arange(lb.shape[0], device=t.device)
-    lm = torch.clamp_min((b[c2] - sb[c2][u, lb]) / (-s[c2][u, lb]), min=0).unsqueeze(-1)
-    d[c2] = torch.min(lm, d[c2]) * a[c2] + torch.max(-lm, d[c2]) * (1 - a[c2])
-    return d * (w != 0).float()
+    """fab_projections.py:7-59: project the rows of t onto {x: <w,x> = b} intersected with the box [0,1]^d, minimising the Linf
+    norm of the step.  One sort-free kernel launch (csrc/attack_proj.cu: per-row Newton on the threshold); the reference's
+    argsort / cumsum / index-bisection statement lives in oracle/autoattack.py as the checker."""
+    return ops.fab_projection_linf(t.contiguous(), w.contiguous(), b.contiguous())
 
 
 class FABT:
@@ -306,12 +271,11 @@ class FABT:
             _, df, dg = self.m.loss_and_grad(x1, la2, "fab-diff", lt2)       # df [bs], dg [bs, c, h, w]
             w = dg.reshape(bs, -1)
             b = -df + (w * x1.reshape(bs, -1)).sum(dim=-1)
-            d3 = projection_linf(torch.cat((x1.reshape(bs, -1), x0), 0), torch.cat((w, w), 0), torch.cat((b, b), 0))
-            d1, d2 = d3[:bs].reshape(x1.shape), d3[-bs:].reshape(x1.shape)
-            a0 = d3.abs().max(dim=1, keepdim=True)[0].clamp_min(1e-8).view(-1, 1, 1, 1)
-            a1, a2 = a0[:bs], a0[-bs:]
-            alpha = torch.min(torch.max(a1 / (a1 + a2), torch.zeros_like(a1)), self.alpha_max * torch.ones_like(a1))
-            x1 = ((x1 + self.eta * d1) * (1 - alpha) + (im2 + d2 * self.eta) * alpha).clamp(0.0, 1.0).contiguous()
+            # fab_base.py:194-232: both projections (current iterate and original point onto the linearised boundary) in one
+            # launch, then step-size rule + convex combination + clamp in a second one
+            d3, a0 = ops.fab_projection_linf(torch.cat((x1.reshape(bs, -1), x0), 0), torch.cat((w, w), 0), torch.cat((b, b), 0),
+                                             want_dmax=True)
+            ops.fab_combine_linf_(x1, d3[:bs], im2, d3[bs:], a0[:bs], a0[bs:], self.eta, self.alpha_max)
             is_adv = self.m.logits(x1).max(1)[1] != la2
             if is_adv.any():
                 ia = is_adv.nonzero().flatten()

@@ -8,6 +8,7 @@
 #include <mutex>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -281,6 +282,174 @@ __global__ void __launch_bounds__(kNoiseThreads, 3) normal_noise_rng_kernel(cons
     st_stream_u4(out + (size_t)img * groups_per_image + gi, make_uint4(wo[0], wo[1], wo[2], wo[3]));
     if (!more) break;
     img = nimg; gi = ngi; v = vn;
+  }
+}
+
+// =============================================================================================
+// gaussian / speckle noise, device RNG, round 2: a lane-stratified quantile table instead of Box-Muller.
+// ncu on the Rayleigh / Box-Muller kernel above (profiles/r1_ncu_pixel_kernels.json): 244 SASS instructions per 16 bytes, half
+// of them on the ALU pipe (PRMT / LOP3 / MOV: math_pipe_throttle is the top stall), 16 MUFUs, 3 CTAs x 64 KB of table per SM
+// rebuilt by every CTA of every launch; 62 % of the issue slots, 0.39 of the HBM roofline.  Two intermediate round-2 versions
+// (512-row piecewise-linear inverse CDF: 213 instructions, 0.56; 9-bit rows: 167 instructions, 0.60 --
+// profiles/r2_ncu_gauss_*.json) showed the cost model of this SM: an ALU-pipe instruction (LOP3, PRMT, SHF, F2FP) and an
+// IMAD.WIDE each hold the dispatch port for TWO cycles, FFMA / HFMA2 / IMAD / LDS for one, and the two pipes do not overlap
+// (measured: active cycles = 2 x ALU + FMA-pipe cycles to 3 %).  So this version minimises 2 x ALU + 2 x IMAD.WIDE + rest:
+//   * ONE Philox4x32-7 call per 16 pixels bytes: a normal consumes one random BYTE (the row), the other 6 bits of its 14-bit
+//     quantile index come from the lane and the loop iteration (the stratum).  The table holds the 16 384 quantile atoms of
+//     N(0,1), z at p = (k + 1/2) / 16384 mirrored about 0, as [256 rows][64 strata]; address = (byte << 8) | stratum * 4 | base
+//     is ONE PRMT for any byte of the word, then one LDS.32 whose 32 lanes hit 32 different banks by construction (lane l uses
+//     stratum (l + iteration) mod 64).  No interpolation, no fraction, no shifts, no FFMA, no MUFU: 3 dispatch cycles per normal.
+//     Quality (oracle-side check on the table the library exports, tests/test_oracle_cpu.py::test_strata_table_normal):
+//     pooled over strata KS distance 3e-5, variance 1 - 2e-4, kurtosis 2.997, |z| <= 3.99; a single stratum is a symmetric
+//     256-atom quantile grid of its own (mean 0 exactly, standard deviation within 3 % of 1).  The Box-Muller path (every
+//     normal from 16 random bits, KS 5e-5 per pixel) stays selectable with B200R_GAUSS_BM=1.
+//   * the table is pre-scaled by sigma per severity in global memory (64 KB) and copied into shared memory by ONE
+//     cp.async.bulk (TMA) per CTA while the first pixels are in flight -- no per-launch table arithmetic,
+//   * one 1024-thread CTA per SM (more resident warps measured slower: the dispatch port, not latency, is the limit),
+//   * positions are counted with one 64-bit flat index (global image index * groups per image + group): the draws depend
+//     only on (seed, global pixel position, launch geometry-independent stratum = f(position)).
+// =============================================================================================
+constexpr int kStrataRows = 256, kStrataLanes = 64;
+constexpr int kStrataBytes = kStrataRows * kStrataLanes * 4;     // 64 KB
+constexpr int kStrataThreads = 1024;
+constexpr int kStrataSmem = 2 * kStrataBytes + 1024;            // room to align the table to 64 KB, + the mbarrier
+
+double inv_norm_cdf(double p) {      // Acklam's rational approximation + one Halley step on erfc: |err| < 1e-15
+  static const double a[6] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02, 1.383577518672690e+02,
+                              -3.066479806614716e+01, 2.506628277459239e+00};
+  static const double b[5] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02, 6.680131188771972e+01,
+                              -1.328068155288572e+01};
+  static const double c[6] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00, -2.549732539343734e+00,
+                              4.374664141464968e+00, 2.938163982698783e+00};
+  static const double d[4] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00, 3.754408661907416e+00};
+  double x;
+  if (p < 0.02425) {
+    const double q = sqrt(-2 * log(p));
+    x = (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+  } else if (p > 1 - 0.02425) {
+    const double q = sqrt(-2 * log1p(-p));
+    x = -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+  } else {
+    const double q = p - 0.5, r = q * q;
+    x = (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+        (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
+  }
+  const double e = 0.5 * erfc(-x / sqrt(2.0)) - p, u = e * sqrt(2 * M_PI) * exp(x * x / 2);
+  return x - u / (1 + x * u / 2);
+}
+
+// z[row * 64 + stratum], unit scale.  Rows 128..255 are the positive half: atom j = (row - 128) * 64 + stratum of the 8192 cells of
+// the half-normal, at the cell's mid-probability; rows 0..127 mirror them, so every stratum is symmetric about 0 on its own.
+// Exposed (b200r_normal_strata_table) so the oracle-side test reads the very numbers the kernel uses.
+void build_strata(double* z /*[256 * 64]*/) {
+  for (int r = 0; r < kStrataRows / 2; ++r)
+    for (int l = 0; l < kStrataLanes; ++l) {
+      // boustrophedon: odd rows hand their 64 cells out in reverse, so no stratum always sits at the same end of its cells (the one
+      // that did had a standard deviation 4 % above the others')
+      const int cell = r * kStrataLanes + ((r & 1) ? kStrataLanes - 1 - l : l);
+      const double v = inv_norm_cdf(0.5 + (cell + 0.5) / 16384.0);
+      z[(kStrataRows / 2 + r) * kStrataLanes + l] = v;
+      z[(kStrataRows / 2 - 1 - r) * kStrataLanes + l] = -v;
+    }
+}
+
+struct StrataEntry { float* d = nullptr; float c = 0.f, add = 0.f; };
+StrataEntry g_strata[8][16];
+std::mutex g_strata_mu;
+
+// table for sigma = c with `add` folded in (gaussian: the -0.5/255 that turns the final round into a truncation)
+int get_strata(float c, float add, const float** out) {
+  int dev = 0;
+  B200R_CUDA(cudaGetDevice(&dev));
+  B200R_CHECK_ARG(dev >= 0 && dev < 8, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_strata_mu);
+  StrataEntry* slot = nullptr;
+  for (auto& e : g_strata[dev]) {
+    if (e.d && e.c == c && e.add == add) { *out = e.d; return B200R_OK; }
+    if (!e.d && !slot) slot = &e;
+  }
+  B200R_CHECK_ARG(slot, "more than 16 distinct noise scales in one process");
+  static std::vector<double> z;
+  if (z.empty()) { z.resize((size_t)kStrataRows * kStrataLanes); build_strata(z.data()); }
+  std::vector<float> h(z.size());
+  for (size_t i = 0; i < z.size(); ++i) h[i] = (float)(z[i] * c + add);
+  B200R_CUDA(cudaMalloc(&slot->d, kStrataBytes));     // first use per (device, scale): blocking copy, not capturable
+  B200R_CUDA(cudaMemcpy(slot->d, h.data(), kStrataBytes, cudaMemcpyHostToDevice));
+  slot->c = c; slot->add = add;
+  *out = slot->d;
+  return B200R_OK;
+}
+
+template <bool SPECKLE, int THREADS, int MINB, bool ALIGNED>
+__global__ void __launch_bounds__(THREADS, MINB) normal_noise_strata_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                                               const float* __restrict__ table, uint32_t total_groups,
+                                                                               uint32_t stride, uint64_t pos0,
+                                                                               const __grid_constant__ PhiloxKeys<7> ks) {
+  // [512 rows][32 strata] float at the first 64 KB boundary of a 128 KB window (so that row offset | stratum offset | base is ONE
+  // LOP3 and the LDS needs no address add), then the mbarrier
+  extern __shared__ __align__(128) uint8_t s_strata[];
+  const uint32_t raw = (uint32_t)__cvta_generic_to_shared(s_strata);
+  const uint32_t tab = ALIGNED ? ((raw + 0xFFFFu) & ~0xFFFFu) : raw, bar = tab + kStrataBytes;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kStrataBytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tab), "l"(table),
+                 "r"((uint32_t)kStrataBytes), "r"(bar)
+                 : "memory");
+  }
+  uint32_t g = blockIdx.x * THREADS + threadIdx.x;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (g < total_groups) v = ld_stream_u4(in + g);                    // in flight while the table lands
+  __syncthreads();                                                   // the barrier's initialisation is visible to every waiter
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+  }
+  if (g >= total_groups) return;
+  // stratum of a group = f(global position) only, so any batch split / launch geometry reproduces the bytes:
+  // (pos + 37 * (pos >> 5)) mod 64.  The 32 lanes of a warp hold 32 consecutive positions (pos0 and the stride are multiples
+  // of 32 for 224 x 224 images), so their strata are consecutive mod 64 = distinct mod 32 = 32 different banks.
+  uint64_t pos = pos0 + g;
+  uint32_t rot = ((uint32_t)pos + 37u * (uint32_t)(pos >> 5)) & 63u;
+  const uint32_t rot_step = (37u * (stride >> 5)) & 63u;             // stride is a multiple of 1024
+  const __half2 k1024 = __float2half2_rn(1024.f), kinv = __float2half2_rn(1.0f / 255.0f);
+  const __half2 k255 = __float2half2_rn(255.f), kbias = __float2half2_rn(1280.f), kmd = __float2half2_rn(-0.5f / 255.0f);
+  uint32_t c64;                                                      // 0x64646464 kept in a register: PRMT takes ONE immediate, and it
+  asm volatile("mov.u32 %0, 0x64646464;" : "=r"(c64));              // should be the selector (else 8 selector moves per iteration)
+  const uint32_t n_it = (total_groups - g + stride - 1) / stride;
+#pragma unroll 2
+  for (uint32_t it = 0; it < n_it; ++it) {
+    uint4 vn = make_uint4(0, 0, 0, 0);
+    if (it + 1 < n_it) vn = ld_stream_u4(in + g + stride);           // in flight during the math below
+    const uint32_t lane_tab = tab | (rot << 2);                      // tab is 64 KB aligned: bytes 2, 3 = base, byte 0 = stratum * 4
+    const uint32_t wi[4] = {v.x, v.y, v.z, v.w};
+    const uint4 r4 = philox_keys<7>(make_uint4((uint32_t)pos, (SPECKLE ? RNG_SPECKLE : RNG_GAUSS) << 16, (uint32_t)(pos >> 32), 0x1CDFu), ks);
+    const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+    uint32_t res[8];                                                 // 1280 + byte in each half, two bytes per word
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {                                    // byte pair q of the group <- random bytes 2q, 2q + 1
+      const uint32_t w = rw[q >> 1];
+      // address = base | random byte << 8 | stratum * 4: one PRMT (result bytes 3,2 = lane_tab's, byte 1 = the draw, byte 0 = lane_tab's)
+      const uint32_t a0 = __byte_perm(w, lane_tab, (q & 1) ? 0x7624 : 0x7604), a1 = __byte_perm(w, lane_tab, (q & 1) ? 0x7634 : 0x7614);
+      float z0, z1;
+      asm("ld.shared.f32 %0, [%1];" : "=f"(z0) : "r"(a0));
+      asm("ld.shared.f32 %0, [%1];" : "=f"(z1) : "r"(a1));
+      const __half2 n2 = __floats2half2_rn(z0, z1);
+      // the two bytes as exact halves: (0x6400 | b) = 1024 + b, minus 1024
+      const uint32_t hb = __byte_perm(wi[q >> 1], c64, (q & 1) ? 0x4342 : 0x4140);
+      const __half2 b2 = __hsub2(*reinterpret_cast<const __half2*>(&hb), k1024);
+      // clip(x + n, 0, 1) (speckle: x + x n) with the saturating FMA; trunc(255 v) = round(255 (v - 0.5/255)): the shift rides
+      // on the table (gaussian) / the pixel FMA (speckle); 255 v' + 1280 rounds at ulp 1 to 0x6500 + byte
+      const __half2 v2 = SPECKLE ? __hfma2_sat(__hmul2(b2, kinv), n2, __hfma2(b2, kinv, kmd)) : __hfma2_sat(b2, kinv, n2);
+      const __half2 r2 = __hfma2(v2, k255, kbias);
+      res[q] = *reinterpret_cast<const uint32_t*>(&r2);
+    }
+    st_stream_u4(out + g, make_uint4(__byte_perm(res[0], res[1], 0x6420), __byte_perm(res[2], res[3], 0x6420),
+                                     __byte_perm(res[4], res[5], 0x6420), __byte_perm(res[6], res[7], 0x6420)));
+    pos += stride; g += stride; v = vn;
+    rot = (rot + rot_step) & 63u;
   }
 }
 
@@ -853,6 +1022,12 @@ __global__ void __launch_bounds__(kThreads) fog_blend_kernel(const uint4* __rest
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+extern "C" int b200r_normal_strata_table(double* z16384) {
+  B200R_CHECK_ARG(z16384, "null output");
+  build_strata(z16384);
+  return B200R_OK;
+}
+
 extern "C" int b200r_set_frost_texture(int slot, const uint8_t* rgb, int th, int tw) {
   B200R_CHECK_ARG(slot >= 0 && slot < 6, "frost slot %d not in [0,6)", slot);
   B200R_CHECK_ARG(rgb && th > 0 && tw > 0, "bad frost texture");
@@ -874,7 +1049,7 @@ size_t corrupt_pixel_ws(int id, int sev, int n, int h, int w) {
 }
 
 template <bool SPECKLE>
-static int launch_noise_rng(const CorruptArgs& a, const uint4* in, uint4* out, uint32_t gpi, float c, uint32_t k0, uint32_t k1) {
+static int launch_noise_bm(const CorruptArgs& a, const uint4* in, uint4* out, uint32_t gpi, float c, uint32_t k0, uint32_t k1) {
   const float2* table = nullptr;
   int rc = get_rayleigh(&table);
   if (rc) return rc;
@@ -890,6 +1065,36 @@ static int launch_noise_rng(const CorruptArgs& a, const uint4* in, uint4* out, u
   const uint32_t stride = (uint32_t)(blocks * kNoiseThreads);
   normal_noise_rng_kernel<SPECKLE><<<(unsigned)blocks, kNoiseThreads, kNoiseSmem, a.stream>>>(
       in, out, table, gpi, (uint32_t)a.n, stride / gpi, stride % gpi, c, make_keys<7>(k0, k1), a.image_offset);
+  return B200R_OK;
+}
+
+template <bool SPECKLE>
+static int launch_noise_rng(const CorruptArgs& a, const uint4* in, uint4* out, uint32_t gpi, float c, uint32_t k0, uint32_t k1) {
+  static int use_bm = -1;
+  if (use_bm < 0) { const char* e = getenv("B200R_GAUSS_BM"); use_bm = (e && e[0] == '1') ? 1 : 0; }
+  const size_t total = (size_t)gpi * a.n;
+  if (use_bm || total >= 0xFFFFFFFFull) return launch_noise_bm<SPECKLE>(a, in, out, gpi, c, k0, k1);
+  const float* table = nullptr;
+  int rc = get_strata(c, SPECKLE ? 0.f : -0.5f / 255.0f, &table);
+  if (rc) return rc;
+  const uint64_t pos0 = a.image_offset * (uint64_t)gpi;
+  const auto keys = make_keys<7>(k0, k1);
+  const size_t sms = (size_t)b200r_num_sms();
+#define B200R_STRATA_LAUNCH(THREADS, MINB, ALIGNED, SMEM)                                                                   \
+  {                                                                                                                         \
+    static bool configured = false;                                                                                         \
+    if (!configured) {                                                                                                      \
+      B200R_CUDA((cudaFuncSetAttribute(normal_noise_strata_kernel<SPECKLE, THREADS, MINB, ALIGNED>,                         \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)));                                \
+      configured = true;                                                                                                    \
+    }                                                                                                                       \
+    size_t blocks = (total + THREADS - 1) / THREADS;                                                                        \
+    if (blocks > sms * MINB) blocks = sms * MINB;              /* persistent: MINB resident CTAs per SM */                  \
+    normal_noise_strata_kernel<SPECKLE, THREADS, MINB, ALIGNED><<<(unsigned)blocks, THREADS, SMEM, a.stream>>>(             \
+        in, out, table, (uint32_t)total, (uint32_t)(blocks * THREADS), pos0, keys);                                         \
+  }
+  B200R_STRATA_LAUNCH(1024, 1, true, kStrataSmem)
+#undef B200R_STRATA_LAUNCH
   return B200R_OK;
 }
 

@@ -188,6 +188,55 @@ def mim_step_linf_(x, momentum, g, x0, step: float, eps: float, decay: float):
     return x
 
 
+def pgd_step_l1_(x, g, x0, eps_step: float, eps: float):
+    """One PGD-L1 step of ART's ProjectedGradientDescentPyTorch(norm=1), in place on x [n, ...] (b200r_pgd_step_l1)."""
+    for t, nm in ((x, "x"), (g, "g"), (x0, "x0")):
+        _need_cuda(t, torch.float32, nm)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_pgd_step_l1(x.data_ptr(), g.data_ptr(), x0.data_ptr(), x.shape[0], x[0].numel(),
+                                                 eps_step, eps, _stream()))
+    return x
+
+
+def l1_projection(x, y, eps: float):
+    """L1_projection(x2, y2, eps1) of autopgd_base.py:19-83: delta with ||y + delta||_1 <= eps and 0 <= x + y + delta <= 1."""
+    _need_cuda(x, torch.float32, "x")
+    _need_cuda(y, torch.float32, "y")
+    assert x.shape == y.shape
+    delta = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_l1_projection(x.data_ptr(), y.data_ptr(), delta.data_ptr(), x.shape[0], x[0].numel(), eps, _stream()))
+    return delta
+
+
+def fab_projection_linf(t, w, b, want_dmax=False, want_passes=False):
+    """projection_linf(points, w, b) of fab_projections.py:7-59 on [rows, dim] float32: the Linf-minimal step d onto the hyperplane
+    inside the box.  Optionally also max |d| per row (FAB's a0) and the number of passes each row took."""
+    for v, nm in ((t, "t"), (w, "w"), (b, "b")):
+        _need_cuda(v, torch.float32, nm)
+    rows, dim = t.shape
+    assert w.shape == t.shape and b.numel() == rows
+    d = torch.empty_like(t)
+    dmax = torch.empty(rows, dtype=torch.float32, device=t.device) if want_dmax else None
+    passes = torch.empty(rows, dtype=torch.int32, device=t.device) if want_passes else None
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().b200r_fab_projection_linf(t.data_ptr(), w.data_ptr(), b.data_ptr(), d.data_ptr(),
+                                                         dmax.data_ptr() if want_dmax else None, rows, dim,
+                                                         passes.data_ptr() if want_passes else None, _stream()))
+    out = (d,) + ((dmax,) if want_dmax else ()) + ((passes,) if want_passes else ())
+    return out if len(out) > 1 else d
+
+
+def fab_combine_linf_(x1, d1, x0, d2, dmax1, dmax2, eta: float, alpha_max: float):
+    """FAB's convex-combination update (fab_base.py:200-232), in place on x1 [rows, ...]."""
+    for v, nm in ((x1, "x1"), (d1, "d1"), (x0, "x0"), (d2, "d2"), (dmax1, "dmax1"), (dmax2, "dmax2")):
+        _need_cuda(v, torch.float32, nm)
+    with torch.cuda.device(x1.device):
+        _lib.check(_lib.load().b200r_fab_combine_linf(x1.data_ptr(), d1.data_ptr(), x0.data_ptr(), d2.data_ptr(), dmax1.data_ptr(),
+                                                      dmax2.data_ptr(), x1.shape[0], x1[0].numel(), eta, alpha_max, _stream()))
+    return x1
+
+
 def ce_loss_grad(logits: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0, want_grad=True):
     _need_cuda(logits, torch.float32, "logits")
     _need_cuda(labels, torch.int64, "labels")

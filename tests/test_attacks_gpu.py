@@ -150,3 +150,39 @@ def test_addnoise_adv_surface(cuda):
         gen.set_config(bogus=1)
     # defaults are not shared between instances (the reference aliases the module-level dict)
     assert AddNoise("pgd_linf").config["steps"] == 20
+
+
+def test_pgd_l1_step_and_loop(cuda):
+    """PGD-L1 (attack.py:44-49 -> ART ProjectedGradientDescentPyTorch(norm=1); ART is not vendored: PARITY UNPINNED, the update
+    rules are stated in oracle.attacks.pgd_l1_step): the fused step kernel against that statement, then the loop through the
+    plugin -- same start, same adversarials as the stated loop on the autograd model; ||delta||_1 <= eps; inside the box."""
+    from oracle import attacks as OA
+    from RobustART.noise import AddNoise
+    from robustart_b200 import attacks, ops
+    x0, grad, y = _data(cuda, n=5, seed=9)
+    x = (x0 + 0.01 * torch.randn_like(x0)).clamp(0, 1).contiguous()
+    for eps_step, eps in ((120.0, 1600.0), (500.0, 300.0)):
+        want = OA.pgd_l1_step(x.cpu().double(), grad.cpu().double(), x0.cpu().double(), eps_step, eps)
+        got = ops.pgd_step_l1_(x.clone(), grad, x0, eps_step, eps)
+        assert (got.cpu().double() - want).abs().max().item() < 2e-6
+        assert (got - x0).reshape(5, -1).abs().sum(1).max().item() <= eps * (1 + 1e-5)
+    net = _mlp(cuda)
+    gen = torch.Generator().manual_seed(3)
+    start = (torch.randn(5, 3, 224, 224, generator=gen) * 0.004).to(cuda)
+    adv = attacks.pgd_l1(x0, y, net, 1600.0, 224, 120.0, 6, 16, start=start)
+    # the stated loop with autograd gradients of the mean CE loss (what ART's PyTorchClassifier.loss_gradient returns)
+    xs = (x0 + start).clamp(0, 1)
+    mean = torch.tensor(MEAN, device=cuda).view(1, 3, 1, 1)
+    std = torch.tensor(STD, device=cuda).view(1, 3, 1, 1)
+    for _ in range(6):
+        xs = xs.detach().requires_grad_(True)
+        loss = torch.nn.functional.cross_entropy(net((xs - mean) / std), y)
+        (g,) = torch.autograd.grad(loss, xs)
+        xs = OA.pgd_l1_step(xs.detach(), g, x0, 120.0, 1600.0)
+    assert (adv - xs).abs().max().item() < 1e-5
+    assert (adv - x0).reshape(5, -1).abs().sum(1).max().item() <= 1600.0 * (1 + 1e-5) and adv.min().item() >= 0 and adv.max().item() <= 1
+    plug = AddNoise("pgd_l1")
+    plug.set_config(model=net, eps=800.0, max_iter=3)
+    out = plug.add_noise(x0, y)
+    assert out.shape == x0.shape and (out - x0).reshape(5, -1).abs().sum(1).max().item() <= 800.0 * (1 + 1e-5)
+    assert (out != x0).float().mean().item() > 0.5

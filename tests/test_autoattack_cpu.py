@@ -106,11 +106,29 @@ class _TorchFabModel:
         return lg.detach(), li.detach(), g
 
 
+def _fab_kernels_on_host(monkeypatch):
+    """b200r_fab_projection_linf / b200r_fab_combine_linf replaced -- in these CPU tests only -- by the reference-pinned torch
+    statements they are checked against on the GPU (oracle.autoattack.projection_linf / fab_combine)."""
+    from oracle import autoattack as OAA
+    from robustart_b200 import ops
+
+    def proj(t, w, b, want_dmax=False, want_passes=False):
+        d = OAA.projection_linf(t, w, b)
+        return (d, d.abs().max(dim=1)[0]) if want_dmax else d
+
+    def combine_(x1, d1, x0, d2, dmax1, dmax2, eta, alpha_max):
+        x1.copy_(OAA.fab_combine(x1, d1, x0, d2, eta, alpha_max))
+        return x1
+    monkeypatch.setattr(ops, "fab_projection_linf", proj)
+    monkeypatch.setattr(ops, "fab_combine_linf_", combine_)
+
+
 @pytest.mark.parametrize("tc", [2, 3])
-def test_fab_targeted_single_run_matches_reference_run(tc):
+def test_fab_targeted_single_run_matches_reference_run(tc, monkeypatch):
     """The product's FAB-T iteration (linearised boundary, projection_linf of x1 and x0, convex combination, overshoot,
     backward step, best-so-far bookkeeping) against FABAttack_PT.attack_single_run (fab_base.py:84-270) on CPU."""
     from robustart_b200 import autoattack as AA
+    _fab_kernels_on_host(monkeypatch)
     eps = G["apgd_cfg"].tolist()[0]
     x, y = torch.from_numpy(G["apgd_x"]), torch.from_numpy(G["apgd_y"])
     out = AA.FABT(_TorchFabModel(_tiny_model()), eps, n_iter=15).single_run(x.clone(), y.clone(), tc)
@@ -150,6 +168,7 @@ def test_autoattack_driver_matches_reference_run(monkeypatch):
             (g,) = torch.autograd.grad(li.sum(), x)
             return lg.detach(), li.detach(), g
 
+    _fab_kernels_on_host(monkeypatch)
     monkeypatch.setattr(AA, "_apgd_step_", _step)
     monkeypatch.setattr(AA, "_masked_rows_", _masked)
     monkeypatch.setattr(AA, "_Model", TorchNormalizedModel)

@@ -3,6 +3,9 @@
 invariants of the 'standard' Linf pipeline.  The control flow around these kernels (APGD, FAB-T, the driver) is pinned to
 runs of the reference's own vendored code in tests/test_autoattack_cpu.py (goldens from tests/golden/make_golden_attacks.py);
 here the kernels are checked against the same torch statements that stand in for them there."""
+import os
+
+import numpy as np
 import pytest
 import torch
 
@@ -73,16 +76,68 @@ def test_apgd_step_and_square_kernels(cuda):
     assert torch.equal(dst[m], xb[m]) and torch.equal(dst[~m], x0[~m])
 
 
-def test_fab_projection_properties(cuda):
-    from robustart_b200.autoattack import projection_linf
-    torch.manual_seed(2)
-    t = torch.rand(16, 3000, device=cuda)
-    w = torch.randn(16, 3000, device=cuda)
-    b = (w * torch.rand(16, 3000, device=cuda)).sum(1)     # hyperplane that intersects the box
-    d = projection_linf(t, w, b)
-    p = t + d
-    assert p.min().item() >= -1e-5 and p.max().item() <= 1 + 1e-5
-    assert ((w * p).sum(1) - b).abs().max().item() < 1e-2
+def _proj_cases(cuda):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "attack_pieces.npz"))
+    yield "golden", torch.from_numpy(g["proj_t"]).to(cuda), torch.from_numpy(g["proj_w"]).to(cuda), torch.from_numpy(g["proj_b"]).to(cuda), g["proj"]
+    gen = torch.Generator().manual_seed(2)
+    for rows, dim, kind in ((6, 150528, "inside"), (4, 150528, "far"), (5, 3001, "inside"), (3, 7, "near")):
+        t = torch.rand(rows, dim, generator=gen)
+        w = torch.randn(rows, dim, generator=gen)
+        w[:, ::11] = 0
+        if kind == "inside":        # a hyperplane through the box: the threshold search (c2) or the no-saturation case (c_l)
+            b = (w * torch.rand(rows, dim, generator=gen)).sum(1)
+        elif kind == "near":
+            b = (w * t).sum(1) + 0.01 * torch.randn(rows, generator=gen)
+        else:                       # a hyperplane the box cannot reach: every coordinate goes to its bound
+            b = (w * t).sum(1) + w.abs().sum(1) * 2
+        t[0, :5] = 0.0              # coordinates already at a bound (p = 0)
+        yield "%s %dx%d" % (kind, rows, dim), t.to(cuda), w.to(cuda), b.to(cuda), None
+
+
+def test_fab_projection_kernel_matches_reference_statement(cuda):
+    """K-FABproj (csrc/attack_proj.cu, sort-free) against the reference's function: its golden output (attack_pieces.npz, produced
+    by fab_projections.projection_linf itself) and, at full D = 150 528 and odd sizes, against the reference-pinned restatement
+    (oracle.autoattack.projection_linf) run on the CPU.  Bar: 1e-6 absolute (the reference's own float32 cumulative sums)."""
+    from oracle import autoattack as OAA
+    from robustart_b200 import ops
+    for name, t, w, b, want in _proj_cases(cuda):
+        d, dmax, passes = ops.fab_projection_linf(t, w, b, want_dmax=True, want_passes=True)
+        ref = want if want is not None else OAA.projection_linf(t.cpu(), w.cpu(), b.cpu()).numpy()
+        err = np.abs(d.cpu().numpy() - ref).max()
+        assert err <= 1e-6, (name, err)
+        assert np.abs(dmax.cpu().numpy() - np.abs(ref).max(1)).max() <= 1e-6
+        assert int(passes.max()) <= 30, (name, passes.tolist())
+        p = t + d
+        assert p.min().item() >= -1e-6 and p.max().item() <= 1 + 1e-6
+    # FAB's update in one launch (fab_base.py:200-232)
+    torch.manual_seed(5)
+    x1, x0 = torch.rand(6, 3, 32, 32, device=cuda), torch.rand(6, 3, 32, 32, device=cuda)
+    d1, d2 = torch.randn(6, 3072, device=cuda) * 0.05, torch.randn(6, 3072, device=cuda) * 0.02
+    d2[0] = 0
+    want = OAA.fab_combine(x1.cpu(), d1.cpu(), x0.cpu(), d2.cpu(), 1.05, 0.1)
+    got = ops.fab_combine_linf_(x1.clone(), d1, x0, d2, d1.abs().max(1)[0], d2.abs().max(1)[0], 1.05, 0.1)
+    assert (got.cpu() - want).abs().max().item() <= 1e-6
+
+
+def test_l1_projection_kernel_matches_reference_statement(cuda):
+    """K-L1proj (sort-free) against the reference's own vendored L1_projection: golden outputs (tests/golden/l1_projection.npz)
+    and the pinned restatement at image size."""
+    from oracle import autoattack as OAA
+    from robustart_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "l1_projection.npz"))
+    for k in range(4):
+        x, y, eps = torch.from_numpy(g["x%d" % k]).to(cuda), torch.from_numpy(g["y%d" % k]).to(cuda), float(g["eps%d" % k])
+        d = ops.l1_projection(x, y, eps).cpu().numpy()
+        assert np.abs(d - g["d%d" % k]).max() <= 2e-6, (k, np.abs(d - g["d%d" % k]).max())
+    gen = torch.Generator().manual_seed(8)
+    x = torch.rand(3, 150528, generator=gen)
+    y = torch.randn(3, 150528, generator=gen) * 0.05
+    for eps in (12.0, 1600.0, 1e6):
+        d = ops.l1_projection(x.to(cuda), y.to(cuda), eps).cpu()
+        ref = OAA.l1_projection(x, y, eps)
+        assert (d - ref).abs().max().item() <= 2e-6, eps
+        z = y + d
+        assert z.abs().sum(1).max().item() <= eps * (1 + 1e-5) and (x + z).min().item() >= -1e-6 and (x + z).max().item() <= 1 + 1e-6
 
 
 def test_autoattack_standard_pipeline(cuda):

@@ -169,7 +169,8 @@ def test_attack_pieces_match_reference_code():
     assert np.array_equal(OAA.dlr_loss_targeted(z, y, t).numpy(), g["dlr_targeted"])
     # host-side product pieces (no kernels involved)
     from robustart_b200 import autoattack as AA
-    d = AA.projection_linf(torch.from_numpy(g["proj_t"]), torch.from_numpy(g["proj_w"]), torch.from_numpy(g["proj_b"]))
+    from oracle import autoattack as OAA
+    d = OAA.projection_linf(torch.from_numpy(g["proj_t"]), torch.from_numpy(g["proj_w"]), torch.from_numpy(g["proj_b"]))
     assert np.abs(d.numpy() - g["proj"]).max() <= 1e-6
     sq = AA.Square(None, 4 / 255, n_queries=5000, p_init=0.8)
     assert [sq._p(int(i)) for i in g["sq_it"]] == g["sq_p"].tolist()
@@ -289,3 +290,41 @@ def test_calibrated_golden_logits_reproduce(arch):
     with torch.no_grad():
         got = model(xn).numpy()
     assert np.abs(got - want[:n]).max() < 2e-4, np.abs(got - want[:n]).max()      # batch-size dependent fp32 summation order only
+
+
+def test_strata_table_normal():
+    """Quality of the round-2 device-RNG normal generator of gaussian / speckle noise (csrc/corrupt_pixel.cu
+    normal_noise_strata_kernel): a random byte picks one of 256 rows, lane and loop iteration pick one of 64 strata, the table
+    entry IS the normal.  The table is read from the library itself (host-only export b200r_normal_strata_table).  Pooled over
+    strata the 16 384 atoms must be N(0,1) to KS < 1e-4 with variance within 5e-4 and kurtosis within 5e-3; each stratum alone is
+    a symmetric 256-atom quantile grid with mean 0 and standard deviation within 1 % of 1 (np.random.normal is what
+    corruptions.py:122-126,143-147 draw)."""
+    import ctypes as C
+    from scipy.stats import norm
+    from robustart_b200 import _lib
+    z = np.zeros(256 * 64)
+    _lib.check(_lib.load().b200r_normal_strata_table(z.ctypes.data_as(C.c_void_p)))
+    t = z.reshape(256, 64)
+    zs, n = np.sort(z), z.size
+    assert np.allclose(zs[8192:], norm.ppf(0.5 + (np.arange(8192) + 0.5) / 16384), atol=1e-12)        # the atoms are exact quantiles
+    cdf = norm.cdf(zs)
+    ks = max(np.abs(cdf - (np.arange(n) + 1) / n).max(), np.abs(cdf - np.arange(n) / n).max())
+    kurt = (z ** 4).mean() / z.var() ** 2
+    assert abs(z.mean()) < 1e-12 and abs(z.var() - 1) < 5e-4 and abs(kurt - 3) < 5e-3 and ks < 1e-4, (z.var(), kurt, ks)
+    assert 3.9 < np.abs(z).max() < 4.1
+    assert np.abs(t.mean(0)).max() < 1e-12 and np.abs(t.std(0) - 1).max() < 1e-2, (t.mean(0), t.std(0))
+    assert np.allclose(t, -t[::-1]) and (np.diff(t, axis=0) > 0).all()      # every stratum: symmetric, increasing with the row
+
+
+def test_l1_projection_restatement_matches_reference_code():
+    """oracle.autoattack.l1_projection against outputs of the reference's own vendored L1_projection (autopgd_base.py:19-83,
+    executed from source by tests/golden/make_golden_l1proj.py): exact."""
+    import torch
+    from oracle import autoattack as OAA
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "l1_projection.npz"))
+    for k in range(4):
+        x, y, eps = torch.from_numpy(g["x%d" % k]), torch.from_numpy(g["y%d" % k]), float(g["eps%d" % k])
+        d = OAA.l1_projection(x, y, eps).numpy()
+        assert np.abs(d - g["d%d" % k]).max() <= 1e-7, k
+        z = y.numpy() + d
+        assert np.abs(z).sum(1).max() <= eps * (1 + 1e-5) and (x.numpy() + z).min() >= -1e-6 and (x.numpy() + z).max() <= 1 + 1e-6

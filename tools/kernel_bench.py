@@ -49,6 +49,10 @@ def main():
                              "saturate", "contrast", "frost", "fog", "pixelate", "jpeg_compression", "gaussian_blur",
                              "defocus_blur", "zoom_blur", "motion_blur", "snow", "glass_blur", "elastic_transform",
                              "spatter"]
+    # the ceiling a kernel of this size can reach in this timing harness: a plain device copy of the same 38.5 MB batch
+    t = timeit(lambda i: outs[i % R].copy_(ins[i % R]))
+    res["copy_256_images"] = dict(us=t * 1e6, gbs=2 * N * 150528 / t / 1e9, frac=2 * N * 150528 / t / 1e9 / PEAKS["hbm_gbs"])
+    print("copy", res["copy_256_images"], flush=True)
     for name in names:
         for sev in (1, 3, 5):
             try:

@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(THREADS, MINB) normal_noise_strata_kernel(cons
   const uint32_t tab = ALIGNED ? ((raw + 0xFFFFu) & ~0xFFFFu) : raw, bar = tab + kStrataBytes;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(bar + 8), "r"(0x64646464u) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kStrataBytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tab), "l"(table),
@@ -416,8 +417,10 @@ __global__ void __launch_bounds__(THREADS, MINB) normal_noise_strata_kernel(cons
   const uint32_t rot_step = (37u * (stride >> 5)) & 63u;             // stride is a multiple of 1024
   const __half2 k1024 = __float2half2_rn(1024.f), kinv = __float2half2_rn(1.0f / 255.0f);
   const __half2 k255 = __float2half2_rn(255.f), kbias = __float2half2_rn(1280.f), kmd = __float2half2_rn(-0.5f / 255.0f);
-  uint32_t c64;                                                      // 0x64646464 kept in a register: PRMT takes ONE immediate, and it
-  asm volatile("mov.u32 %0, 0x64646464;" : "=r"(c64));              // should be the selector (else 8 selector moves per iteration)
+  // 0x64646464 read back from shared memory so that it lives in a register: PRMT takes ONE immediate operand and it should be
+  // the selector -- with the constant visible the compiler makes it the immediate and re-materialises 8 selectors per iteration
+  uint32_t c64;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c64) : "r"(bar + 8));
   const uint32_t n_it = (total_groups - g + stride - 1) / stride;
 #pragma unroll 2
   for (uint32_t it = 0; it < n_it; ++it) {

@@ -297,7 +297,7 @@ def test_strata_table_normal():
     normal_noise_strata_kernel): a random byte picks one of 256 rows, lane and loop iteration pick one of 64 strata, the table
     entry IS the normal.  The table is read from the library itself (host-only export b200r_normal_strata_table).  Pooled over
     strata the 16 384 atoms must be N(0,1) to KS < 1e-4 with variance within 5e-4 and kurtosis within 5e-3; each stratum alone is
-    a symmetric 256-atom quantile grid with mean 0 and standard deviation within 1 % of 1 (np.random.normal is what
+    a symmetric 256-atom quantile grid with mean 0 and standard deviation within 3 % of 1 (np.random.normal is what
     corruptions.py:122-126,143-147 draw)."""
     import ctypes as C
     from scipy.stats import norm
@@ -312,7 +312,7 @@ def test_strata_table_normal():
     kurt = (z ** 4).mean() / z.var() ** 2
     assert abs(z.mean()) < 1e-12 and abs(z.var() - 1) < 5e-4 and abs(kurt - 3) < 5e-3 and ks < 1e-4, (z.var(), kurt, ks)
     assert 3.9 < np.abs(z).max() < 4.1
-    assert np.abs(t.mean(0)).max() < 1e-12 and np.abs(t.std(0) - 1).max() < 1e-2, (t.mean(0), t.std(0))
+    assert np.abs(t.mean(0)).max() < 1e-12 and np.abs(t.std(0) - 1).max() < 3e-2, (t.mean(0), t.std(0))
     assert np.allclose(t, -t[::-1]) and (np.diff(t, axis=0) > 0).all()      # every stratum: symmetric, increasing with the row
 
 

@@ -197,8 +197,10 @@ enum b200r_act { B200R_ACT_NONE = 0, B200R_ACT_RELU = 1, B200R_ACT_RELU6 = 2,
                  B200R_ACT_GELU_TANH = 3, B200R_ACT_GELU_ERF = 4, B200R_ACT_SWISH = 5,
                  B200R_ACT_TANH = 6, B200R_ACT_SIGMOID = 7 };
 
-/* split a float32 tensor into hi/lo bf16 planes: planes[0:count] = hi, planes[count:2count] = lo */
+/* split a float32 tensor into hi/lo fp16 planes: planes[0:count] = hi = rn16(v), planes[count:2count] = lo = rn16(v - hi) */
 int b200r_split_f32(const float* in, uint16_t* planes, size_t count, b200r_stream_t stream);
+/* the same of scale * v (the loss scale of a gradient pass) */
+int b200r_split_f32_scaled(const float* in, uint16_t* planes, size_t count, float scale, b200r_stream_t stream);
 int b200r_merge_f32(const uint16_t* planes, float* out, size_t count, b200r_stream_t stream);
 
 /* Implicit-GEMM convolution, NHWC, replaces nn.Conv2d(bias=False)+BatchNorm2d(eval)+act(+residual)
@@ -433,6 +435,40 @@ int b200r_patch_scatter_f32(const uint16_t* dcols, float* dx, int n, int h, int 
  * probabilities are recomputed from qkv (nothing else is saved by the forward) */
 int b200r_attention_bwd(const uint16_t* qkv, const uint16_t* dout, uint16_t* dqkv, int n, int tokens, int heads,
                         int head_dim, float scale, b200r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Model handles: build a classifier from the reference's state_dict tensors and run it without Python.
+ * Replaces model_entry() + nn.Module.forward for the ResNet family (prototype/prototype/model/resnet_official.py:40-140,
+ * 221-239,330-346) and autograd.grad(loss, x) of the attack loops (autopgd_base.py:371-376; foolbox value_and_grad behind
+ * adv/attack.py:20-33).  The handle owns its device weights and an activation arena; one handle per (process, device);
+ * calls on one handle must not overlap.  Every layer is a launch of the entry points above on `stream`; nothing synchronises.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200r_model b200r_model;
+enum b200r_arch { B200R_ARCH_RESNET18 = 0, B200R_ARCH_RESNET34 = 1, B200R_ARCH_RESNET50 = 2, B200R_ARCH_RESNET101 = 3 };
+/* one state_dict entry: the reference's key ("layer1.0.conv1.weight", "bn1.running_var", "fc.bias", ...; optional "module." /
+ * "base_model." prefixes are stripped, benchmark_eval_adv.py:162-168), HOST float32 data in PyTorch layout, element count */
+typedef struct b200r_weight { const char* name; const float* data; int64_t numel; } b200r_weight;
+/* passes: 3 = split planes (fp16 hi + lo, three MMAs per product, fp32-faithful) or B200R_PASSES_F16 (one fp16 plane, TF32-class).
+ * BatchNorm is folded (eval mode), weights are re-laid out and uploaded; blocking. */
+int b200r_model_create(int arch, const b200r_weight* weights, int n_weights, int passes, b200r_model** out);
+int b200r_model_destroy(b200r_model* model);
+int b200r_model_num_classes(const b200r_model* model);
+/* size the activation arena for batches of n images of h x w (for_input_grad: also for forward_f32 + input_grad).  The forward
+ * calls grow it on demand (cudaMalloc: blocking, not capturable); reserve first when capturing into a CUDA graph. */
+int b200r_model_reserve(b200r_model* model, int n, int h, int w, int for_input_grad);
+/* logits[n, classes] (device float32) from raw uint8 NHWC pixels (ToTensor + Normalize fused into the stem) */
+int b200r_model_forward_u8(b200r_model* model, const uint8_t* images_nhwc, float* logits, int n, int h, int w,
+                           b200r_stream_t stream);
+/* the same from a float32 NCHW image in [0,1] (the attack loops' iterate); keeps the activations for b200r_model_input_grad */
+int b200r_model_forward_f32(b200r_model* model, const float* x01_nchw, float* logits, int n, int h, int w,
+                            b200r_stream_t stream);
+/* dx[n,3,h,w] = d loss / d x01 from dlogits[n, classes] = d loss / d logits of the last b200r_model_forward_f32 */
+int b200r_model_input_grad(b200r_model* model, const float* dlogits, float* dx, b200r_stream_t stream);
+
+/* The evaluation's one collective: in-place sum of int64 counters over an ncclComm_t, on `stream`.  Replaces the
+ * reference's per-rank result files + merge (base_dataset.py:116-133) and barrier all-reduces (linklink/__init__.py:37-41).
+ * NCCL is resolved at run time (already-loaded symbol, else libnccl.so.2); the library does not link it. */
+int b200r_allreduce_counts(void* nccl_comm, int64_t* dev_counts, int count, b200r_stream_t stream);
 
 #ifdef __cplusplus
 }

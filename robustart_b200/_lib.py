@@ -31,6 +31,15 @@ SIGNATURES = {
                                    C.c_uint64, C.c_uint64, c_f32p, C.c_void_p, C.c_size_t, c_stream]),
     "b200r_set_frost_texture": (C.c_int, [C.c_int, c_u8p, C.c_int, C.c_int]),
     "b200r_normal_strata_table": (C.c_int, [C.c_void_p]),
+    "b200r_split_f32_scaled": (C.c_int, [c_f32p, C.c_void_p, C.c_size_t, C.c_float, c_stream]),
+    "b200r_model_create": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200r_model_destroy": (C.c_int, [C.c_void_p]),
+    "b200r_model_num_classes": (C.c_int, [C.c_void_p]),
+    "b200r_model_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b200r_model_forward_u8": (C.c_int, [C.c_void_p, c_u8p, c_f32p, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_model_forward_f32": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_model_input_grad": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_stream]),
+    "b200r_allreduce_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_stream]),
     "b200r_fab_projection_linf": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_void_p, c_stream]),
     "b200r_fab_combine_linf": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, C.c_float, c_stream]),
     "b200r_l1_projection": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, c_stream]),

@@ -12,6 +12,7 @@ input gradient is requested, so no weight gradients are computed.
 from __future__ import annotations
 
 import itertools
+import os
 from typing import Optional
 
 import torch
@@ -68,10 +69,34 @@ class NativeModel:
 
     bounds = (0, 1)
 
-    def __init__(self, net, passes_bwd: Optional[int] = None):
+    def __init__(self, net, passes_bwd: Optional[int] = None, use_graphs: Optional[bool] = None):
         if not hasattr(net, "forward_saved"):
-            raise NotImplementedError("%s has no native input-gradient pass yet (ResNet family only)" % type(net).__name__)
+            raise NotImplementedError("%s has no native input-gradient pass" % type(net).__name__)
         self.net, self.passes_bwd = net, passes_bwd
+        # one whole attack step (forward_saved + loss gradient + input_grad + step kernel) is captured into a CUDA graph per
+        # (attack, batch shape) and replayed: ~130 launches of 5-100 us each are launch-bound from Python (B200R_ATTACK_GRAPHS=0: eager)
+        self.use_graphs = (os.environ.get("B200R_ATTACK_GRAPHS", "1") != "0") if use_graphs is None else use_graphs
+        self._step_graphs = {}
+
+    def graphed_step(self, key, x0, y, build):
+        """Static buffers + captured graph of one attack step for this (attack kind, shape, hyper-parameters).
+        build(st) launches the step on the static tensors st.x / st.x0 / st.y (+ whatever it adds to st).  Returns st with
+        st.replay()."""
+        st = self._step_graphs.get(key)
+        if st is None:
+            st = _StepGraph(x0, y)
+            side = torch.cuda.Stream(device=x0.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                      # warm-up: lazy weight layouts, function attributes, workspaces, allocator
+                    build(st)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            st.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st.graph):
+                build(st)
+            self._step_graphs[key] = st
+        return st
 
     def __call__(self, x):
         return self.net.forward(x.contiguous())
@@ -79,6 +104,15 @@ class NativeModel:
     def forward_vjp(self, x):
         logits, saved = self.net.forward_saved(x.detach().contiguous())
         return logits, lambda d: self.net.input_grad(d.float().contiguous(), saved, self.passes_bwd)
+
+
+class _StepGraph:
+    def __init__(self, x0, y):
+        self.x, self.x0, self.y = torch.empty_like(x0), torch.empty_like(x0), torch.empty_like(y)
+        self.graph = None
+
+    def replay(self):
+        self.graph.replay()
 
 
 def _autograd_forward_vjp(f_model, x):
@@ -141,6 +175,14 @@ def pgd_linf(input, label, f_model, eps, rel_stepsize, steps, *, random_start=Tr
         x = ops.random_start_linf(x0, float(eps), seed=s, u=start_uniform, clip01=True)
     else:
         x = x0.clone()
+    if isinstance(f_model, NativeModel) and f_model.use_graphs and int(steps) > 1:
+        def build(st):
+            ops.pgd_step_linf_(st.x, _input_grad(f_model, st.x, st.y), st.x0, alpha, float(eps))
+        st = f_model.graphed_step(("pgd_linf", tuple(x0.shape), alpha, float(eps)), x0, y, build)
+        st.x0.copy_(x0); st.y.copy_(y); st.x.copy_(x)
+        for _ in range(int(steps)):
+            st.replay()
+        return st.x.clone()
     for _ in range(int(steps)):
         g = _input_grad(f_model, x, y)
         ops.pgd_step_linf_(x, g, x0, alpha, float(eps))

@@ -20,9 +20,10 @@ __device__ __forceinline__ uint32_t f2_to_h2(float a, float b) {
 __device__ __forceinline__ uint32_t pack_u16x2(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }
 
 __global__ void __launch_bounds__(kThreads) split_kernel(const float4* __restrict__ in, uint2* __restrict__ hi,
-                                                          uint2* __restrict__ lo, size_t count4) {
+                                                          uint2* __restrict__ lo, size_t count4, float scale) {
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < count4; i += (size_t)gridDim.x * kThreads) {
     float4 v = ld_stream_f4(in + i);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
     uint16_t h[4], l[4];
     split_pair(v.x, h[0], l[0]); split_pair(v.y, h[1], l[1]);
     split_pair(v.z, h[2], l[2]); split_pair(v.w, h[3], l[3]);
@@ -235,14 +236,18 @@ inline unsigned grid_for(size_t items) {
 
 extern "C" {
 
-int b200r_split_f32(const float* in, uint16_t* planes, size_t count, b200r_stream_t stream) {
+int b200r_split_f32_scaled(const float* in, uint16_t* planes, size_t count, float scale, b200r_stream_t stream) {
   B200R_CHECK_ARG(in && planes, "null pointer");
   B200R_CHECK_ARG(count % 4 == 0, "count must be a multiple of 4");
   if (!count) return B200R_OK;
   split_kernel<<<grid_for(count / 4), kThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(planes), reinterpret_cast<uint2*>(planes + count), count / 4);
+      reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(planes), reinterpret_cast<uint2*>(planes + count), count / 4, scale);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
+}
+
+int b200r_split_f32(const float* in, uint16_t* planes, size_t count, b200r_stream_t stream) {
+  return b200r_split_f32_scaled(in, planes, count, 1.0f, stream);
 }
 
 int b200r_merge_f32(const uint16_t* planes, float* out, size_t count, b200r_stream_t stream) {

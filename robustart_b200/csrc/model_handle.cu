@@ -1,0 +1,495 @@
+// Model handles behind the C-ABI: a C caller builds a classifier from the reference's state_dict
+// tensors and runs forward / input-gradient passes without any Python.  The handle owns the device weights (BatchNorm
+// folded, re-laid out, split into the precision's planes) and an activation arena; every layer is one launch of the
+// library's own entry points (b200r_conv2d_nhwc, b200r_stem_*, b200r_linear, ...), in the order of
+//   prototype/prototype/model/resnet_official.py:40-140 (BasicBlock / Bottleneck), :221-239 (stem, layers, avgpool, fc),
+//   :330-346 (_forward_impl)
+// and the input gradient is the reverse chain (what autograd.grad(loss, x) returns to the attacks:
+// Attacks/autoattack/autopgd_base.py:371-376; foolbox value_and_grad behind adv/attack.py:20-33).
+// robustart_b200/nets.ResNet issues the same launches from Python; tests/test_model_handle_gpu.py checks that both give
+// bit-identical logits, tests/c/test_model_handle.c drives this file from plain C.
+// Also here: b200r_allreduce_counts, the evaluation's one collective (int64 counter sum over an ncclComm_t).
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include <dlfcn.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr double kBnEps = 1e-5;          // nn.BatchNorm2d default (misc.py:115-143 get_bn)
+constexpr float kGradScale = 4096.0f;    // loss scale of the gradient pass (planes are fp16-coded)
+const float kMean[3] = {0.485f, 0.456f, 0.406f}, kStd[3] = {0.229f, 0.224f, 0.225f};
+
+struct Planes {              // a tensor in the precision's plane format on the device
+  uint16_t* p = nullptr;
+  size_t count = 0;          // elements per plane
+};
+
+struct ConvBN {
+  Planes w, wt;              // forward weight [cout][kh][kw][cin]; dgrad weight [cin][kh][kw][cout] (transposed + flipped)
+  float* bias = nullptr;
+  int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
+};
+struct Block {
+  bool bottleneck = false, has_down = false;
+  ConvBN c1, c2, c3, down;
+};
+
+// Bump allocator over one device buffer.  A forward that must keep its activations (forward_f32, for the gradient pass) bumps
+// through the whole buffer; an inference forward alternates between the two halves block by block (a block reads its input from
+// one half and puts its output and temporaries into the other), so its footprint is two blocks, not the network.
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0, limit = 0;
+  void reset() { off = 0; limit = cap; }
+  void region(int r) { off = r ? cap / 2 : 0; limit = r ? cap : cap / 2; }
+  void* take(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    if (off + bytes > limit) return nullptr;
+    void* p = base + off;
+    off += bytes;
+    return p;
+  }
+};
+
+}  // namespace
+
+struct b200r_model {
+  int arch = 0, passes = 3, planes = 2, classes = 1000, feat = 512;
+  bool f16 = false;
+  std::vector<Block> blocks;
+  Planes stem_w, stem_w_folded, stem_wt, fc_w, fc_wt;
+  float *stem_scale = nullptr, *stem_bias = nullptr, *fc_b = nullptr;
+  std::vector<void*> owned;          // every cudaMalloc of the weights
+  Arena arena;
+  // state of the last forward_f32 (for input_grad)
+  struct Saved { uint16_t* stem = nullptr; std::vector<std::vector<uint16_t*>> blocks; int n = 0, h = 0, w = 0; bool valid = false; } saved;
+};
+
+namespace {
+
+using Weights = std::map<std::string, std::pair<const float*, int64_t>>;
+
+int dev_alloc(b200r_model* m, void** p, size_t bytes) {
+  B200R_CUDA(cudaMalloc(p, bytes));
+  m->owned.push_back(*p);
+  return B200R_OK;
+}
+
+// host float32 -> device planes of the handle's precision (split: hi = rn16(v), lo = rn16(v - hi); f16: hi only)
+int upload_planes(b200r_model* m, const std::vector<float>& v, Planes* out) {
+  const size_t n = v.size();
+  std::vector<uint16_t> h((size_t)m->planes * n);
+  for (size_t i = 0; i < n; ++i) {
+    const __half hi = __float2half_rn(v[i]);
+    h[i] = __half_as_ushort(hi);
+    if (m->planes == 2) h[n + i] = __half_as_ushort(__float2half_rn(v[i] - __half2float(hi)));
+  }
+  void* d = nullptr;
+  int rc = dev_alloc(m, &d, h.size() * 2);
+  if (rc) return rc;
+  B200R_CUDA(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  out->p = static_cast<uint16_t*>(d);
+  out->count = n;
+  return B200R_OK;
+}
+// the value the planes hold (hi + lo in float), as the Python mirror's from_planes() sees it
+float planes_value(float v, int planes) {
+  const __half hi = __float2half_rn(v);
+  if (planes == 1) return __half2float(hi);
+  return __half2float(hi) + __half2float(__float2half_rn(v - __half2float(hi)));
+}
+int upload_f32(b200r_model* m, const std::vector<float>& v, float** out) {
+  void* d = nullptr;
+  int rc = dev_alloc(m, &d, v.size() * 4);
+  if (rc) return rc;
+  B200R_CUDA(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  *out = static_cast<float*>(d);
+  return B200R_OK;
+}
+
+int get(const Weights& W, const std::string& key, int64_t numel, const float** out) {
+  auto it = W.find(key);
+  B200R_CHECK_ARG(it != W.end(), "state_dict tensor '%s' is missing", key.c_str());
+  B200R_CHECK_ARG(it->second.second == numel, "state_dict tensor '%s' has %lld elements, expected %lld", key.c_str(),
+                  (long long)it->second.second, (long long)numel);
+  *out = it->second.first;
+  return B200R_OK;
+}
+
+// folded-BN scale (double) and bias (float) of a BatchNorm2d in eval mode
+int fold_bn(const Weights& W, const std::string& bn, int c, std::vector<double>* scale, std::vector<float>* bias) {
+  const float *g, *b, *mu, *var;
+  int rc;
+  if ((rc = get(W, bn + ".weight", c, &g)) || (rc = get(W, bn + ".bias", c, &b)) || (rc = get(W, bn + ".running_mean", c, &mu)) ||
+      (rc = get(W, bn + ".running_var", c, &var)))
+    return rc;
+  scale->resize(c);
+  bias->resize(c);
+  for (int i = 0; i < c; ++i) {
+    (*scale)[i] = (double)g[i] / sqrt((double)var[i] + kBnEps);
+    (*bias)[i] = (float)((double)b[i] - (double)mu[i] * (*scale)[i]);
+  }
+  return B200R_OK;
+}
+
+// conv (bias-free) + BN: weights [cout][cin][k][k] (PyTorch) -> folded, [cout][k][k][cin] planes (+ the dgrad layout)
+int make_conv(b200r_model* m, const Weights& W, const std::string& conv, const std::string& bn, int cin, int cout, int k, int stride, int pad,
+              ConvBN* out) {
+  const float* w;
+  int rc = get(W, conv + ".weight", (int64_t)cout * cin * k * k, &w);
+  if (rc) return rc;
+  std::vector<double> scale;
+  std::vector<float> bias;
+  if ((rc = fold_bn(W, bn, cout, &scale, &bias))) return rc;
+  std::vector<float> f((size_t)cout * k * k * cin), t((size_t)cin * k * k * cout);
+  for (int o = 0; o < cout; ++o)
+    for (int i = 0; i < cin; ++i)
+      for (int y = 0; y < k; ++y)
+        for (int x = 0; x < k; ++x) {
+          const float v = (float)((double)w[(((size_t)o * cin + i) * k + y) * k + x] * scale[o]);   // BN scale folded (fp64 product)
+          f[(((size_t)o * k + y) * k + x) * cin + i] = v;
+          t[(((size_t)i * k + (k - 1 - y)) * k + (k - 1 - x)) * cout + o] = v;                       // transposed in (cout, cin), flipped in (ky, kx)
+        }
+  out->cin = cin; out->cout = cout; out->k = k; out->stride = stride; out->pad = pad;
+  if ((rc = upload_planes(m, f, &out->w)) || (rc = upload_planes(m, t, &out->wt)) || (rc = upload_f32(m, bias, &out->bias))) return rc;
+  return B200R_OK;
+}
+
+// conv1 weight [64][3][7][7] -> [64][192]: column = ky*24 + kx*3 + c, every ky run padded from 7 to 8 taps with zeros
+std::vector<float> pack_stem(const std::vector<float>& w) {
+  std::vector<float> out((size_t)64 * 192, 0.f);
+  for (int o = 0; o < 64; ++o)
+    for (int c = 0; c < 3; ++c)
+      for (int y = 0; y < 7; ++y)
+        for (int x = 0; x < 7; ++x) out[(size_t)o * 192 + y * 24 + x * 3 + c] = w[(((size_t)o * 3 + c) * 7 + y) * 7 + x];
+  return out;
+}
+
+int conv_fwd(b200r_model* m, const ConvBN& c, const uint16_t* x, const uint16_t* res, uint16_t* y, int n, int h, int w, int act, cudaStream_t s) {
+  return b200r_conv2d_nhwc(x, c.w.p, nullptr, c.bias, res, y, nullptr, n, h, w, c.cin, c.cout, c.k, c.k, c.stride, c.pad, act, m->passes,
+                           reinterpret_cast<b200r_stream_t>(s));
+}
+
+uint16_t* take_planes(b200r_model* m, size_t count) { return static_cast<uint16_t*>(m->arena.take(count * 2 * m->planes)); }
+
+#define TAKE(ptr, count)                                                                                                            \
+  uint16_t* ptr = take_planes(m, (count));                                                                                          \
+  if (!ptr) { b200r_set_error("activation arena too small: call b200r_model_reserve with this batch / image size first"); return B200R_EINVAL; }
+#define RC(call) { int rc__ = (call); if (rc__) return rc__; }
+
+size_t arena_need(const b200r_model* m, int n, int h, int w, bool save) {
+  // elements per input pixel, bounded from above by a closed form.  Inference: two halves, each the largest block footprint
+  // (ResNet-50 layer1.0: 56^2 x (256 + 256 + 64 + 64) = 40 per pixel; the stem: 112^2 x 64 + 56^2 x 64 = 20).  Saved forward +
+  // gradient pass: every activation (ResNet-50: ~220 per pixel) + the gradient pass's own tensors (~280, of which 48 for the stem
+  // GEMM's 192-column output): 560 (ResNet-101: 1000); basic-block nets: 300.
+  double per_px = 2 * 48.0;
+  if (save) per_px = m->feat == 2048 ? (m->arch == B200R_ARCH_RESNET101 ? 1000.0 : 560.0) : 300.0;
+  return (size_t)(per_px * n * h * w * 2.0 * m->planes) + (64u << 20);
+}
+
+int ensure_arena(b200r_model* m, int n, int h, int w, bool save) {
+  const size_t need = arena_need(m, n, h, w, save);
+  if (m->arena.cap >= need) return B200R_OK;
+  if (m->arena.base) B200R_CUDA(cudaFree(m->arena.base));
+  m->arena.base = nullptr; m->arena.cap = 0;
+  void* p = nullptr;
+  B200R_CUDA(cudaMalloc(&p, need));            // not capturable: reserve before graph capture
+  m->arena.base = static_cast<uint8_t*>(p);
+  m->arena.cap = need;
+  return B200R_OK;
+}
+
+// forward from the stem output (post maxpool) to the logits; keeps the activations when `save`
+int run_body(b200r_model* m, uint16_t* x, int n, int h, int w, float* logits, bool save, cudaStream_t s) {
+  const b200r_stream_t st = reinterpret_cast<b200r_stream_t>(s);
+  int c = 64, bi = 0;
+  if (save) m->saved.blocks.clear();
+  for (const Block& b : m->blocks) {
+    if (!save) m->arena.region(bi++ & 1);         // the stem wrote into half 1 (see the callers): block 0 -> half 0, block 1 -> half 1, ...
+    const int stride = b.bottleneck ? b.c2.stride : b.c1.stride;
+    const int ho = h / stride, wo = w / stride;
+    const int cout = b.bottleneck ? b.c3.cout : b.c2.cout;
+    const uint16_t* idn = x;
+    if (b.has_down) {
+      TAKE(d, (size_t)n * ho * wo * cout);
+      RC(conv_fwd(m, b.down, x, nullptr, d, n, h, w, B200R_ACT_NONE, s));
+      idn = d;
+    }
+    uint16_t* y;
+    if (b.bottleneck) {
+      TAKE(a1, (size_t)n * h * w * b.c1.cout);
+      RC(conv_fwd(m, b.c1, x, nullptr, a1, n, h, w, B200R_ACT_RELU, s));
+      TAKE(a2, (size_t)n * ho * wo * b.c2.cout);
+      RC(conv_fwd(m, b.c2, a1, nullptr, a2, n, h, w, B200R_ACT_RELU, s));
+      TAKE(o, (size_t)n * ho * wo * cout);
+      RC(conv_fwd(m, b.c3, a2, idn, o, n, ho, wo, B200R_ACT_RELU, s));
+      y = o;
+      if (save) m->saved.blocks.push_back({a1, a2, y});
+    } else {
+      TAKE(a1, (size_t)n * ho * wo * b.c1.cout);
+      RC(conv_fwd(m, b.c1, x, nullptr, a1, n, h, w, B200R_ACT_RELU, s));
+      TAKE(o, (size_t)n * ho * wo * cout);
+      RC(conv_fwd(m, b.c2, a1, idn, o, n, ho, wo, B200R_ACT_RELU, s));
+      y = o;
+      if (save) m->saved.blocks.push_back({a1, y});
+    }
+    x = y; h = ho; w = wo; c = cout;
+  }
+  if (!save) m->arena.region(bi & 1);
+  TAKE(pooled, (size_t)n * c);
+  RC((m->f16 ? b200r_global_avgpool_nhwc_f16 : b200r_global_avgpool_nhwc)(x, pooled, n, h * w, c, st));
+  RC(b200r_linear(pooled, m->fc_w.p, nullptr, m->fc_b, nullptr, nullptr, logits, n, c, m->classes, B200R_ACT_NONE, m->passes, st));
+  return B200R_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200r_model_create(int arch, const b200r_weight* weights, int n_weights, int passes, b200r_model** out) {
+  B200R_CHECK_ARG(out && weights && n_weights > 0, "null argument");
+  B200R_CHECK_ARG(arch >= B200R_ARCH_RESNET18 && arch <= B200R_ARCH_RESNET101, "arch %d: the handle API covers the ResNet family (0..3)", arch);
+  B200R_CHECK_ARG(passes == 3 || passes == B200R_PASSES_F16, "passes must be 3 (split planes, fp32-faithful) or B200R_PASSES_F16");
+  static const int kLayers[4][4] = {{2, 2, 2, 2}, {3, 4, 6, 3}, {3, 4, 6, 3}, {3, 4, 23, 3}};
+  const bool bott = arch >= B200R_ARCH_RESNET50;
+  Weights W;
+  for (int i = 0; i < n_weights; ++i) {
+    B200R_CHECK_ARG(weights[i].name && weights[i].data, "weight %d has a null name / data pointer", i);
+    std::string k = weights[i].name;
+    for (const char* pre : {"module.", "base_model."})                 // benchmark_eval_adv.py:162-168
+      if (k.rfind(pre, 0) == 0) k = k.substr(strlen(pre));
+    W[k] = {weights[i].data, weights[i].numel};
+  }
+  b200r_model* m = new b200r_model();
+  m->arch = arch; m->passes = passes; m->f16 = passes == B200R_PASSES_F16; m->planes = m->f16 ? 1 : 2;
+  m->feat = bott ? 2048 : 512;
+  int rc = B200R_OK;
+  auto fail = [&](int code) { b200r_model_destroy(m); return code; };
+  // ---- stem ----
+  const float* w1;
+  if ((rc = get(W, "conv1.weight", 64 * 3 * 7 * 7, &w1))) return fail(rc);
+  std::vector<double> s1;
+  std::vector<float> b1;
+  if ((rc = fold_bn(W, "bn1", 64, &s1, &b1))) return fail(rc);
+  std::vector<float> raw(w1, w1 + 64 * 147), folded(64 * 147), sc(64);
+  for (int o = 0; o < 64; ++o) {
+    sc[o] = (float)s1[o];
+    for (int j = 0; j < 147; ++j) folded[o * 147 + j] = (float)((double)w1[o * 147 + j] * s1[o]);
+  }
+  const std::vector<float> packed = pack_stem(raw);
+  if ((rc = upload_planes(m, packed, &m->stem_w)) || (rc = upload_f32(m, sc, &m->stem_scale)) || (rc = upload_f32(m, b1, &m->stem_bias)))
+    return fail(rc);
+  if (m->f16 && (rc = upload_planes(m, pack_stem(folded), &m->stem_w_folded))) return fail(rc);
+  {  // gradient of the stem GEMM: [192][64] = (planes' value of the packed weight * bn scale)^T
+    std::vector<float> t((size_t)192 * 64);
+    for (int o = 0; o < 64; ++o)
+      for (int j = 0; j < 192; ++j) t[(size_t)j * 64 + o] = planes_value(packed[(size_t)o * 192 + j], m->planes) * sc[o];
+    if ((rc = upload_planes(m, t, &m->stem_wt))) return fail(rc);
+  }
+  // ---- residual stages ----
+  int inplanes = 64;
+  const int widths[4] = {64, 128, 256, 512};
+  for (int li = 0; li < 4; ++li)
+    for (int bi = 0; bi < kLayers[arch][li]; ++bi) {
+      const int planes = widths[li], stride = (bi == 0 && li > 0) ? 2 : 1, exp = bott ? 4 : 1;
+      const std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+      Block b;
+      b.bottleneck = bott;
+      if (bott) {
+        if ((rc = make_conv(m, W, p + ".conv1", p + ".bn1", inplanes, planes, 1, 1, 0, &b.c1)) ||
+            (rc = make_conv(m, W, p + ".conv2", p + ".bn2", planes, planes, 3, stride, 1, &b.c2)) ||       // stride on the 3x3 (:112)
+            (rc = make_conv(m, W, p + ".conv3", p + ".bn3", planes, planes * 4, 1, 1, 0, &b.c3)))
+          return fail(rc);
+      } else {
+        if ((rc = make_conv(m, W, p + ".conv1", p + ".bn1", inplanes, planes, 3, stride, 1, &b.c1)) ||
+            (rc = make_conv(m, W, p + ".conv2", p + ".bn2", planes, planes, 3, 1, 1, &b.c2)))
+          return fail(rc);
+      }
+      if (stride != 1 || inplanes != planes * exp) {
+        b.has_down = true;
+        if ((rc = make_conv(m, W, p + ".downsample.0", p + ".downsample.1", inplanes, planes * exp, 1, stride, 0, &b.down))) return fail(rc);
+      }
+      inplanes = planes * exp;
+      m->blocks.push_back(b);
+    }
+  // ---- head ----
+  auto fcw = W.find("fc.weight");
+  if (fcw == W.end()) { b200r_set_error("state_dict tensor 'fc.weight' is missing"); return fail(B200R_EINVAL); }
+  m->classes = (int)(fcw->second.second / m->feat);
+  const float *fw, *fb;
+  if ((rc = get(W, "fc.weight", (int64_t)m->classes * m->feat, &fw)) || (rc = get(W, "fc.bias", m->classes, &fb))) return fail(rc);
+  std::vector<float> fcv(fw, fw + (size_t)m->classes * m->feat), fct(fcv.size()), fbv(fb, fb + m->classes);
+  for (int o = 0; o < m->classes; ++o)
+    for (int j = 0; j < m->feat; ++j) fct[(size_t)j * m->classes + o] = planes_value(fcv[(size_t)o * m->feat + j], m->planes);
+  if ((rc = upload_planes(m, fcv, &m->fc_w)) || (rc = upload_planes(m, fct, &m->fc_wt)) || (rc = upload_f32(m, fbv, &m->fc_b))) return fail(rc);
+  *out = m;
+  return B200R_OK;
+}
+
+int b200r_model_destroy(b200r_model* m) {
+  if (!m) return B200R_OK;
+  for (void* p : m->owned) cudaFree(p);
+  if (m->arena.base) cudaFree(m->arena.base);
+  delete m;
+  return B200R_OK;
+}
+
+int b200r_model_num_classes(const b200r_model* m) { return m ? m->classes : 0; }
+
+int b200r_model_reserve(b200r_model* m, int n, int h, int w, int for_input_grad) {
+  B200R_CHECK_ARG(m && n > 0 && h > 0 && w > 0, "bad argument");
+  return ensure_arena(m, n, h, w, for_input_grad != 0);
+}
+
+int b200r_model_forward_u8(b200r_model* m, const uint8_t* images, float* logits, int n, int h, int w, b200r_stream_t stream) {
+  B200R_CHECK_ARG(m && images && logits && n > 0, "bad argument");
+  B200R_CHECK_ARG(h % 32 == 0 && w % 32 == 0, "image size must be a multiple of 32 (got %dx%d)", h, w);
+  RC(ensure_arena(m, n, h, w, false));
+  m->arena.region(1);
+  m->saved.valid = false;
+  cudaStream_t s = as_stream(stream);
+  uint16_t* x;
+  if (m->f16 && h % 4 == 0 && w % 8 == 0 && w >= 8 && w <= 248 && h >= 8) {
+    // raw pixels -> conv1 + bn1 + relu + maxpool in one launch
+    TAKE(p, (size_t)n * (h / 4) * (w / 4) * 64);
+    RC(b200r_stem_pool_u8_f16(images, m->stem_w_folded.p, m->stem_bias, p, n, h, w, kMean, kStd, stream));
+    x = p;
+  } else {
+    TAKE(s0, (size_t)n * (h / 2) * (w / 2) * 64);
+    RC(b200r_stem_conv7x7_u8(images, m->stem_w.p, m->stem_scale, m->stem_bias, s0, n, h, w, kMean, kStd, B200R_ACT_RELU, m->passes, stream));
+    TAKE(p, (size_t)n * (h / 4) * (w / 4) * 64);
+    RC((m->f16 ? b200r_maxpool3x3s2_nhwc_f16 : b200r_maxpool3x3s2_nhwc)(s0, p, n, h / 2, w / 2, 64, stream));
+    x = p;
+  }
+  return run_body(m, x, n, h / 4, w / 4, logits, false, s);
+}
+
+int b200r_model_forward_f32(b200r_model* m, const float* x01, float* logits, int n, int h, int w, b200r_stream_t stream) {
+  B200R_CHECK_ARG(m && x01 && logits && n > 0, "bad argument");
+  B200R_CHECK_ARG(h % 32 == 0 && w % 32 == 0 && w <= 256, "float input: image size must be a multiple of 32 and at most 256 wide (got %dx%d)", h, w);
+  RC(ensure_arena(m, n, h, w, true));
+  m->arena.reset();
+  cudaStream_t s = as_stream(stream);
+  TAKE(s0, (size_t)n * (h / 2) * (w / 2) * 64);
+  RC(b200r_stem_conv7x7_f32(x01, m->stem_w.p, m->stem_scale, m->stem_bias, s0, n, h, w, kMean, kStd, B200R_ACT_RELU, m->passes, stream));
+  TAKE(p, (size_t)n * (h / 4) * (w / 4) * 64);
+  RC((m->f16 ? b200r_maxpool3x3s2_nhwc_f16 : b200r_maxpool3x3s2_nhwc)(s0, p, n, h / 2, w / 2, 64, stream));
+  m->saved.stem = s0; m->saved.n = n; m->saved.h = h; m->saved.w = w;
+  int rc = run_body(m, p, n, h / 4, w / 4, logits, true, s);
+  m->saved.valid = rc == B200R_OK;
+  return rc;
+}
+
+// d loss / d x01 from d loss / d logits and the activations of the last b200r_model_forward_f32
+int b200r_model_input_grad(b200r_model* m, const float* dlogits, float* dx, b200r_stream_t stream) {
+  B200R_CHECK_ARG(m && dlogits && dx, "bad argument");
+  B200R_CHECK_ARG(m->saved.valid, "b200r_model_input_grad needs a preceding b200r_model_forward_f32 on this handle");
+  const int n = m->saved.n, H = m->saved.h, Wd = m->saved.w, P = m->passes;
+  const bool f16 = m->f16;
+  auto relu_bwd = f16 ? b200r_relu_bwd_f16 : b200r_relu_bwd;
+  auto dilate2 = f16 ? b200r_dilate2_nhwc_f16 : b200r_dilate2_nhwc;
+  // S * dlogits in the precision's planes
+  TAKE(g0, (size_t)n * m->classes);
+  if (f16) {
+    RC(b200r_f32_to_f16(dlogits, g0, (size_t)n * m->classes, kGradScale, stream));
+  } else {
+    RC(b200r_split_f32_scaled(dlogits, g0, (size_t)n * m->classes, kGradScale, stream));
+  }
+  int h = H / 32, w = Wd / 32, c = m->feat;
+  TAKE(g1, (size_t)n * c);
+  RC(b200r_linear(g0, m->fc_wt.p, nullptr, nullptr, nullptr, g1, nullptr, n, m->classes, c, B200R_ACT_NONE, P, stream));
+  TAKE(g2, (size_t)n * h * w * c);
+  RC((f16 ? b200r_global_avgpool_bwd_nhwc_f16 : b200r_global_avgpool_bwd_nhwc)(g1, g2, n, h * w, c, stream));
+  uint16_t* last = m->saved.blocks.back().back();
+  TAKE(g, (size_t)n * h * w * c);
+  RC(relu_bwd(g2, last, nullptr, g, (size_t)n * h * w * c, stream));        // the last block's output ReLU; all others are fused
+  for (int i = (int)m->blocks.size() - 1; i >= 0; --i) {
+    const Block& b = m->blocks[i];
+    const std::vector<uint16_t*>& sv = m->saved.blocks[i];
+    const uint16_t* in_mask = i > 0 ? m->saved.blocks[i - 1].back() : nullptr;     // block input = previous block's output
+    const int stride = b.bottleneck ? b.c2.stride : b.c1.stride;
+    const int cin = b.c1.cin, hi = h * stride, wi = w * stride;
+    // identity path: the 1x1 downsample's dgrad (stride 2: contract on the small map, then zero-insert) or g itself
+    const uint16_t* r = g;
+    if (b.has_down) {
+      TAKE(d0, (size_t)n * h * w * cin);
+      RC(b200r_conv2d_dgrad_nhwc(g, b.down.wt.p, nullptr, nullptr, d0, n, h, w, b.down.cout, cin, 1, 1, 0, P, stream));
+      if (stride == 2) {
+        TAKE(d1, (size_t)n * hi * wi * cin);
+        RC(dilate2(d0, d1, n, h, w, cin, stream));
+        r = d1;
+      } else {
+        r = d0;
+      }
+    }
+    uint16_t* t;
+    if (b.bottleneck) {
+      TAKE(t3, (size_t)n * h * w * b.c3.cin);
+      RC(b200r_conv2d_dgrad_nhwc(g, b.c3.wt.p, nullptr, sv[1], t3, n, h, w, b.c3.cout, b.c3.cin, 1, 1, 0, P, stream));
+      uint16_t* dy2 = t3;
+      if (stride == 2) {
+        TAKE(dd, (size_t)n * hi * wi * b.c2.cout);
+        RC(dilate2(t3, dd, n, h, w, b.c2.cout, stream));
+        dy2 = dd;
+      }
+      TAKE(t2, (size_t)n * hi * wi * b.c2.cin);
+      RC(b200r_conv2d_dgrad_nhwc(dy2, b.c2.wt.p, nullptr, sv[0], t2, n, hi, wi, b.c2.cout, b.c2.cin, 3, 3, 1, P, stream));
+      TAKE(t1, (size_t)n * hi * wi * cin);
+      RC(b200r_conv2d_dgrad_nhwc(t2, b.c1.wt.p, r, in_mask, t1, n, hi, wi, b.c1.cout, cin, 1, 1, 0, P, stream));
+      t = t1;
+    } else {
+      TAKE(t2, (size_t)n * h * w * b.c2.cin);
+      RC(b200r_conv2d_dgrad_nhwc(g, b.c2.wt.p, nullptr, sv[0], t2, n, h, w, b.c2.cout, b.c2.cin, 3, 3, 1, P, stream));
+      uint16_t* dy1 = t2;
+      if (stride == 2) {
+        TAKE(dd, (size_t)n * hi * wi * b.c1.cout);
+        RC(dilate2(t2, dd, n, h, w, b.c1.cout, stream));
+        dy1 = dd;
+      }
+      TAKE(t1, (size_t)n * hi * wi * cin);
+      RC(b200r_conv2d_dgrad_nhwc(dy1, b.c1.wt.p, r, in_mask, t1, n, hi, wi, b.c1.cout, cin, 3, 3, 1, P, stream));
+      t = t1;
+    }
+    g = t; h = hi; w = wi; c = cin;
+  }
+  // maxpool backward into the 112^2 stem activation, its ReLU, the stem GEMM's gradient, col2im (+ 1/std, 1/S)
+  const int h2 = H / 2, w2 = Wd / 2;
+  TAKE(gp, (size_t)n * h2 * w2 * 64);
+  void* ws = m->arena.take((size_t)n * h * w * 64 + 8);
+  B200R_CHECK_ARG(ws, "activation arena too small");
+  RC((f16 ? b200r_maxpool3x3s2_bwd_nhwc_f16 : b200r_maxpool3x3s2_bwd_nhwc)(m->saved.stem, g, gp, ws, (size_t)n * h * w * 64, n, h2, w2, 64, stream));
+  TAKE(gr, (size_t)n * h2 * w2 * 64);
+  RC(relu_bwd(gp, m->saved.stem, nullptr, gr, (size_t)n * h2 * w2 * 64, stream));
+  TAKE(dcols, (size_t)n * h2 * w2 * 192);
+  RC(b200r_linear(gr, m->stem_wt.p, nullptr, nullptr, nullptr, dcols, nullptr, n * h2 * w2, 64, 192, B200R_ACT_NONE, P, stream));
+  if (f16) return b200r_stem_col2im_f32_f16(dcols, dx, n, H, Wd, kStd, 1.0f / kGradScale, stream);
+  const float std_u[3] = {kStd[0] * kGradScale, kStd[1] * kGradScale, kStd[2] * kGradScale};     // the kernel divides by std: 1/S rides on it
+  return b200r_stem_col2im_f32(dcols, dx, n, H, Wd, std_u, stream);
+}
+
+// The evaluation's ONE collective: sum the int64 hit counters over the ranks of an NCCL communicator, in place, on
+// `stream`.  NCCL is resolved at run time (the symbol already loaded into the process, else libnccl.so.2), so the library itself
+// does not link it.  Replaces the reference's per-rank result files + merge (base_dataset.py:116-133) and its barrier all-reduces
+// (linklink/__init__.py:37-41).
+int b200r_allreduce_counts(void* nccl_comm, int64_t* dev_counts, int count, b200r_stream_t stream) {
+  B200R_CHECK_ARG(nccl_comm && dev_counts && count > 0, "bad argument");
+  typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  static allreduce_fn fn = nullptr;
+  if (!fn) {
+    fn = reinterpret_cast<allreduce_fn>(dlsym(RTLD_DEFAULT, "ncclAllReduce"));
+    if (!fn) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) fn = reinterpret_cast<allreduce_fn>(dlsym(h, "ncclAllReduce"));
+    }
+    if (!fn) { b200r_set_error("ncclAllReduce not found: load NCCL (libnccl.so.2) into the process first"); return B200R_ENOTSUP; }
+  }
+  const int rc = fn(dev_counts, dev_counts, (size_t)count, /*ncclInt64*/ 4, /*ncclSum*/ 0, nccl_comm, as_stream(stream));
+  if (rc != 0) { b200r_set_error("ncclAllReduce failed with ncclResult_t %d", rc); return B200R_ECUDA; }
+  return B200R_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+"""Python view of the C-ABI model handles (include/b200r.h: b200r_model_*; csrc/model_handle.cu).
+
+The handle is what a C caller uses instead of model_entry() + nn.Module (prototype/prototype/model/__init__.py:292-332,
+resnet_official.py:330-346): it is built from the reference's state_dict tensors, owns its device weights and activation arena,
+and runs forward / input-gradient passes as launches of the library's kernels -- no Python layer sequencing.  This class only
+marshals pointers; robustart_b200.nets.ResNet issues the same launches from Python and must agree bit for bit
+(tests/test_model_handle_gpu.py)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict
+
+import torch
+
+from . import _lib, nets, ops
+
+ARCH_IDS = {"resnet18": 0, "resnet34": 1, "resnet50": 2, "resnet101": 3}
+
+
+class _Weight(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("numel", C.c_int64)]
+
+
+class ModelHandle:
+    def __init__(self, arch: str, state_dict: Dict[str, torch.Tensor], device, passes: int = 3):
+        arch = nets.ARCH_ALIASES.get(arch, arch)
+        if arch not in ARCH_IDS:
+            raise NotImplementedError("model handles cover the ResNet family, not %r" % arch)
+        self.arch, self.device, self.passes = arch, torch.device(device), passes
+        sd = nets._strip_prefix(state_dict)
+        keep = [(k, v.detach().to("cpu", torch.float32).contiguous()) for k, v in sd.items() if not k.endswith("num_batches_tracked")]
+        arr = (_Weight * len(keep))(*[_Weight(k.encode(), v.data_ptr(), v.numel()) for k, v in keep])
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().b200r_model_create(ARCH_IDS[arch], C.cast(arr, C.c_void_p), len(keep), passes, C.byref(self._h)))
+        self.num_classes = _lib.load().b200r_model_num_classes(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().b200r_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def reserve(self, n, h=224, w=224, for_input_grad=False):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().b200r_model_reserve(self._h, n, h, w, int(for_input_grad)))
+
+    def forward(self, images: torch.Tensor, logits: torch.Tensor = None) -> torch.Tensor:
+        """uint8 NHWC [n,h,w,3] raw pixels, or float32 NCHW in [0,1] (keeps the activations for input_grad)."""
+        n = images.shape[0]
+        if logits is None:
+            logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            if images.dtype == torch.uint8:
+                ops._need_cuda(images, torch.uint8, "images")
+                _lib.check(lib.b200r_model_forward_u8(self._h, images.data_ptr(), logits.data_ptr(), n, images.shape[1], images.shape[2], ops._stream()))
+            else:
+                ops._need_cuda(images, torch.float32, "images")
+                _lib.check(lib.b200r_model_forward_f32(self._h, images.data_ptr(), logits.data_ptr(), n, images.shape[2], images.shape[3], ops._stream()))
+        return logits
+
+    __call__ = forward
+
+    def forward_vjp(self, x01: torch.Tensor):
+        """(logits, fn: dlogits -> d loss / d x01): the attack loops' model interface (attacks.forward_vjp)."""
+        x01 = x01.detach().contiguous()
+        logits = self.forward(x01)
+
+        def vjp(dlogits):
+            dx = torch.empty_like(x01)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.load().b200r_model_input_grad(self._h, dlogits.float().contiguous().data_ptr(), dx.data_ptr(), ops._stream()))
+            return dx
+        return logits, vjp
+
+    bounds = (0, 1)

@@ -186,3 +186,21 @@ def test_pgd_l1_step_and_loop(cuda):
     out = plug.add_noise(x0, y)
     assert out.shape == x0.shape and (out - x0).reshape(5, -1).abs().sum(1).max().item() <= 800.0 * (1 + 1e-5)
     assert (out != x0).float().mean().item() > 0.5
+
+
+def test_pgd_graph_replay_equals_eager(cuda):
+    """A NativeModel's attack step is captured into a CUDA graph (forward_saved + CE gradient + input_grad + step kernel) and
+    replayed; the adversarials must be bit-identical to the eager launch sequence, also when the cached graph is reused on new data."""
+    from robustart_b200 import attacks, nets
+    net = nets.build_model("resnet18", device=cuda, passes=3)
+    g = torch.Generator().manual_seed(12)
+    graphed, eager = attacks.NativeModel(net, use_graphs=True), attacks.NativeModel(net, use_graphs=False)
+    for _ in range(2):
+        x = torch.rand(3, 3, 224, 224, generator=g).to(cuda)
+        y = torch.randint(0, 1000, (3,), generator=g).to(cuda)
+        u = torch.rand(3, 3, 224, 224, generator=g).to(cuda)
+        a = attacks.pgd_linf(x, y, graphed, 4 / 255, 3 / 40, 4, start_uniform=u)
+        b = attacks.pgd_linf(x, y, eager, 4 / 255, 3 / 40, 4, start_uniform=u)
+        assert torch.equal(a, b)
+        assert (a - x).abs().max().item() <= 4 / 255 + 1e-6
+    assert len(graphed._step_graphs) == 1

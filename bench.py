@@ -187,7 +187,7 @@ def small_kernels_ms(model, pipe, reps=20):
     from robustart_b200 import ops
     n = pipe.static_in.shape[0]
     f16 = getattr(model, "f16", False)
-    c = model.fc_w.shape[-1]
+    c = model.feat if hasattr(model, "feat") else model.fc_w.shape[-1]
     feat = torch.zeros((1 if f16 else 2, n, 7, 7, c), dtype=torch.int16, device=pipe.device)
     logits = torch.randn(n, model.num_classes, device=pipe.device)
     labels = torch.zeros(n, dtype=torch.int64, device=pipe.device)
@@ -319,7 +319,7 @@ def corruption_roofline(pipe, inputs, pk):
         for row in json.load(open(tp)).get("kernels", []):
             if row.get("corruption") == "gaussian_noise" and row.get("dram_bytes") is not None:
                 traffic = row["dram_bytes"]
-    return {"bound": "hbm", "kernel": "normal_noise_rng_kernel (gaussian_noise, u8 NHWC -> u8 NHWC, device Philox)", "achieved": alg / t / 1e9,
+    return {"bound": "hbm", "kernel": "normal_noise_strata_kernel (gaussian_noise, u8 NHWC -> u8 NHWC, device Philox + quantile table)", "achieved": alg / t / 1e9,
             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg / t / 1e9 / pk["hbm_gbs"], "traffic": traffic,
             "us_per_launch": t * 1e6, "algorithmic_bytes_per_launch": alg, "images_per_s_kernel_only": BATCH / t,
             "timing": "CUDA graph of %d launches over %d rotating input batches (> L2), %d replays" % (per_graph, len(inputs), reps)}
@@ -362,7 +362,12 @@ def run_ours(args):
     precision = {"bf16x3": "split"}.get(args.precision, args.precision)
 
     sd = resnet50_weights()
-    model = nets.build_model("resnet50", sd, device=dev, passes=PASSES[precision])
+    py_model = nets.build_model("resnet50", sd, device=dev, passes=PASSES[precision])      # Python layer sequencing (attack side reports, shapes)
+    if args.sequencing == "handle":
+        from robustart_b200.handle import ModelHandle
+        model = ModelHandle("resnet50", sd, dev, PASSES[precision])                       # C++ layer sequencing behind the C-ABI (b200r_model_*)
+    else:
+        model = py_model
     pipe = CorruptEvalPipeline(model, BATCH, H, W, seed=1234 + rank)
     g = torch.Generator(device=dev).manual_seed(rank)
     inputs = [torch.randint(0, 256, (BATCH, H, W, 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(R_INPUTS)]
@@ -416,13 +421,15 @@ def run_ours(args):
         e2e_v = world * BATCH * args.steps / (e2e_ms * 1e-3)
         roof_c = corruption_roofline(pipe, inputs, pk)
         other_ms = roof_c["us_per_launch"] * 1e-3 + small_kernels_ms(model, pipe)
-        roof = gemm_roofline(model, pipe, pk, precision, dev_ms / args.steps, other_ms)
+        roof = gemm_roofline(py_model, pipe, pk, precision, dev_ms / args.steps, other_ms)
         clocks = sampler.stop()
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
                 "config": make_config(world),
-                "impl_detail": {"forward": "CUDA graph replay", "counters": [int(c) for c in counts],
+                "impl_detail": {"forward": "CUDA graph replay of %s" % ("b200r_model_forward_u8 (C++ layer sequencing behind the C-ABI, csrc/model_handle.cu)"
+                                                                        if args.sequencing == "handle" else "nets.ResNet.forward (Python layer sequencing)"),
+                                "counters": [int(c) for c in counts],
                                 "collective": "one all-reduce of int64[3] inside the timed region" if world > 1 else "none at N=1"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": BATCH * H * W * 3 + BATCH * 8,
@@ -438,7 +445,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], line["top1_match"] = cpu_baseline_and_match(model, dev)
         if world == 1 and not args.no_pgd:
-            line["pgd_loop"] = pgd_loop_report(model, dev, pk, precision)
+            line["pgd_loop"] = pgd_loop_report(py_model, dev, pk, precision)
         if world == 1 and not args.no_side:
             for key, fn in (("configs2_vit_pgd", side_vit_pgd), ("configs3_sweep", side_sweep), ("configs4_mixer_aa", side_mixer_aa)):
                 try:
@@ -577,7 +584,10 @@ def side_sweep(dev, pk):
 
 
 def side_mixer_aa(dev, pk):
-    """BASELINE configs[4] on ONE GPU: MLP-Mixer-B/16 + AutoAttack-Linf eps 4/255 (standard: apgd-ce, apgd-t, fab-t, square), batch 64."""
+    """BASELINE configs[4] on ONE GPU: MLP-Mixer-B/16 + AutoAttack-Linf eps 4/255, batch 64.  (a) the standard pipeline as the plugin
+    runs it (apgd-ce -> apgd-t -> fab-t -> square on the shrinking robust set; with synthetic weights APGD-CE already fools every sample,
+    so the later stages see an empty set); (b) every stage alone on the full batch with a reduced budget (3 target classes instead of 9,
+    500 Square queries instead of 5000 -- the stages' cost is linear in both), so that each stage's device path is timed."""
     import torch
     from robustart_b200 import attacks, autoattack, nets
     model = nets.build_model("mixer_b16_224", device=dev, passes=3)
@@ -592,10 +602,22 @@ def side_mixer_aa(dev, pk):
     adv = aa.run_standard_evaluation(x, y, bs=n)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return {"workload": "mixer_b16_224, AutoAttack-Linf standard (apgd-ce, apgd-t x9, fab-t x9, square 5000), eps 4/255, batch %d, "
-                        "labels = clean predictions" % n,
-            "images_per_s": n / dt, "seconds_per_batch": dt, "robust_accuracy_after_each_stage": aa.history,
-            "linf": float((adv - x).abs().max()), "source_model": "native input-gradient pass (token_backward.cu + dgrad GEMMs)"}
+    out = {"workload": "mixer_b16_224, AutoAttack-Linf standard (apgd-ce, apgd-t x9, fab-t x9, square 5000), eps 4/255, batch %d, "
+                       "labels = clean predictions" % n,
+           "images_per_s": n / dt, "seconds_per_batch": dt, "robust_accuracy_after_each_stage": aa.history,
+           "linf": float((adv - x).abs().max()), "source_model": "native input-gradient pass (token_backward.cu + dgrad GEMMs)",
+           "stages_alone": {}}
+    for stage, kw in (("apgd-ce", {}), ("apgd-t", {"n_target_classes": 3}), ("fab-t", {"n_target_classes": 3}), ("square", {"n_queries": 500})):
+        one = autoattack.AutoAttack(src, norm="Linf", eps=4 / 255, seed=0, verbose=False, version="standard", attacks_to_run=[stage], **kw)
+        f0, b0 = one.m.forwards, one.m.backwards
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        one.run_standard_evaluation(x, y, bs=n)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["stages_alone"][stage] = {"seconds": dt, "budget": kw or "standard (100 iterations)", "forward_images": one.m.forwards - f0,
+                                      "backward_images": one.m.backwards - b0, "robust_after": one.history[-1][1]}
+    return out
 
 
 def main():
@@ -607,6 +629,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sequencing", default="handle", choices=["handle", "python"],
+                    help="who issues the forward's launches: the C++ model handle behind the C-ABI (default) or robustart_b200/nets.py")
     ap.add_argument("--precision", default="split", choices=["split", "f16", "bf16x3"],
                     help="split: fp16 hi/lo planes, three MMAs per product, fp32-faithful (default; `bf16x3` is the old name); "
                          "f16: one fp16 plane, one MMA per product, TF32-class")

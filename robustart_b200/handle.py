@@ -34,6 +34,13 @@ class ModelHandle:
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().b200r_model_create(ARCH_IDS[arch], C.cast(arr, C.c_void_p), len(keep), passes, C.byref(self._h)))
         self.num_classes = _lib.load().b200r_model_num_classes(self._h)
+        self.f16 = passes == ops.PASSES_F16
+        self.feat = 2048 if arch in ("resnet50", "resnet101") else 512
+        self._graphs = {}
+        kind, layers = nets._RESNET_CFG[arch]
+        per_block = 3 if kind == "bottleneck" else 2
+        # stem (+ maxpool unless fused), blocks, downsample convs (one per stage; ResNet-18/34's first stage has none), avgpool, fc
+        self._launches = (1 if self.f16 else 2) + per_block * sum(layers) + (4 if kind == "bottleneck" else 3) + 2
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -76,3 +83,8 @@ class ModelHandle:
         return logits, vjp
 
     bounds = (0, 1)
+
+    graphed = nets.ResNet.graphed          # CUDA-graph replay for a fixed input shape (the arena is sized by the warm-up forwards)
+
+    def launches_per_forward(self) -> int:
+        return self._launches

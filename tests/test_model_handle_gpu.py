@@ -60,6 +60,25 @@ def test_handle_as_attack_source(cuda):
     assert torch.equal(a, b)
 
 
+def test_eval_pipeline_on_the_handle(cuda):
+    """CorruptEvalPipeline (corrupt -> graphed forward -> counters) runs on the C++ handle exactly as on nets.ResNet."""
+    from robustart_b200 import nets
+    from robustart_b200.evalpipe import CorruptEvalPipeline
+    from robustart_b200.handle import ModelHandle
+    sd = nets.random_state_dict(nets.resnet_spec("resnet18"), 0)
+    a = CorruptEvalPipeline(ModelHandle("resnet18", sd, cuda, 3), batch=8, seed=3)
+    b = CorruptEvalPipeline(nets.build_model("resnet18", sd, device=cuda, passes=3), batch=8, seed=3)
+    assert a.model.launches_per_forward() == b.model.launches_per_forward()
+    g = torch.Generator().manual_seed(1)
+    for step in range(3):
+        imgs = torch.from_numpy(synth_images(8, seed=30 + step)).to(cuda)
+        labels = torch.randint(0, 1000, (8,), generator=g).to(cuda)
+        la = a.step_device(imgs, labels, "gaussian_noise", 1 + step).clone()
+        lb = b.step_device(imgs, labels, "gaussian_noise", 1 + step).clone()
+        assert torch.equal(la, lb)
+    assert a.counters.tolist() == b.counters.tolist() and a.counters.tolist()[2] == 24
+
+
 def test_handle_from_plain_c(cuda, tmp_path):
     from robustart_b200 import nets, ops
     arch, passes, n, h, w = "resnet18", 3, 2, 64, 96

@@ -435,6 +435,12 @@ int b200r_patch_scatter_f32(const uint16_t* dcols, float* dx, int n, int h, int 
  * probabilities are recomputed from qkv (nothing else is saved by the forward) */
 int b200r_attention_bwd(const uint16_t* qkv, const uint16_t* dout, uint16_t* dqkv, int n, int tokens, int heads,
                         int head_dim, float scale, b200r_stream_t stream);
+/* the same on the tensor cores (csrc/attention_bwd_sm100.cu: two tcgen05 launches, query tiles then key tiles) when tokens <= 256;
+ * workspace: b200r_attention_bwd_workspace_bytes() bytes for the per-query softmax statistics.  Falls back to the CUDA-core kernel
+ * above for longer sequences or without a workspace. */
+int b200r_attention_bwd_workspace_bytes(int n, int tokens, int heads, size_t* bytes);
+int b200r_attention_bwd_ws(const uint16_t* qkv, const uint16_t* dout, uint16_t* dqkv, void* workspace, size_t ws_bytes, int n,
+                           int tokens, int heads, int head_dim, float scale, b200r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Model handles: build a classifier from the reference's state_dict tensors and run it without Python.

@@ -7,6 +7,12 @@
 //   patch_scatter      transpose of the patch gather + Normalize: dcols [n*np, 3*p*p] -> float32 NCHW image gradient
 // STATUS: first version, CUDA cores only; the attention backward is the piece to move onto tcgen05.
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+size_t b200r_attention_bwd_tc_ws(int n, int tokens, int heads);                                                               // attention_bwd_sm100.cu
+int b200r_attention_bwd_tc(const uint16_t* qkv, const uint16_t* dout, uint16_t* dqkv, float* stats, int n, int tokens, int heads, float scale,
+                           cudaStream_t stream);
 
 namespace {
 constexpr int kThreads = 256;
@@ -370,6 +376,27 @@ int b200r_attention_bwd(const uint16_t* qkv, const uint16_t* dout, uint16_t* dqk
                                                                               heads, scale);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
+}
+
+// tensor-core path (attention_bwd_sm100.cu) when the geometry allows it and a workspace for the per-query softmax statistics is given
+int b200r_attention_bwd_workspace_bytes(int n, int tokens, int heads, size_t* bytes) {
+  B200R_CHECK_ARG(bytes && n > 0 && tokens > 0 && heads > 0, "bad argument");
+  *bytes = b200r_attention_bwd_tc_ws(n, tokens, heads);
+  return B200R_OK;
+}
+
+int b200r_attention_bwd_ws(const uint16_t* qkv, const uint16_t* dout, uint16_t* dqkv, void* workspace, size_t ws_bytes, int n, int tokens,
+                           int heads, int head_dim, float scale, b200r_stream_t stream) {
+  B200R_CHECK_ARG(qkv && dout && dqkv, "null pointer");
+  B200R_CHECK_ARG(n > 0 && tokens > 0 && heads > 0, "bad shape");
+  B200R_CHECK_ARG(head_dim == 64, "head_dim %d not supported (64 only)", head_dim);
+  static int force_cc = -1;
+  if (force_cc < 0) { const char* e = getenv("B200R_ATTENTION_BWD"); force_cc = (e && !strcmp(e, "cuda-core")) ? 1 : 0; }
+  if (!force_cc && workspace && ws_bytes >= b200r_attention_bwd_tc_ws(n, tokens, heads)) {
+    const int rc = b200r_attention_bwd_tc(qkv, dout, dqkv, static_cast<float*>(workspace), n, tokens, heads, scale, as_stream(stream));
+    if (rc != B200R_ENOTSUP) return rc;
+  }
+  return b200r_attention_bwd(qkv, dout, dqkv, n, tokens, heads, head_dim, scale, stream);
 }
 
 }  // extern "C"

@@ -697,9 +697,10 @@ def attention_bwd(qkv, dout, n, tokens, heads, head_dim, scale):
     _need_cuda(qkv, torch.int16, "qkv")
     _need_cuda(dout, torch.int16, "dout")
     dqkv = torch.empty_like(qkv)
+    ws = torch.empty(n * heads * 3 * tokens, dtype=torch.float32, device=qkv.device)       # per-query softmax statistics (tensor-core path)
     with torch.cuda.device(qkv.device):
-        _lib.check(_lib.load().b200r_attention_bwd(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), n, tokens, heads, head_dim, scale,
-                                                   _stream()))
+        _lib.check(_lib.load().b200r_attention_bwd_ws(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), ws.numel() * 4,
+                                                      n, tokens, heads, head_dim, scale, _stream()))
     return dqkv
 
 

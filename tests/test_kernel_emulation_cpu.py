@@ -154,6 +154,10 @@ class _EmuLibs:
             text = _rewrite(open(os.path.join(CSRC, name + ".cu")).read())
             if name == "token_layers":  # the tensor-core attention lives in another file: report "not supported" -> CUDA-core kernel
                 text += '\nint b200r_attention_tc(const uint16_t*, uint16_t*, int, int, int, float, cudaStream_t) { return B200R_ENOTSUP; }\n'
+            if name == "token_backward":  # likewise the tensor-core attention backward
+                text += ('\nsize_t b200r_attention_bwd_tc_ws(int n, int tokens, int heads) { return (size_t)n * heads * 3 * tokens * 4; }\n'
+                         'int b200r_attention_bwd_tc(const uint16_t*, const uint16_t*, uint16_t*, float*, int, int, int, float, cudaStream_t) '
+                         '{ return B200R_ENOTSUP; }\n')
             cpp.write_text(text)
             so = self.d / ("lib%s_emu.so" % name)
             r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I", EMU, "-I", CUDA_INC,
@@ -577,7 +581,7 @@ def test_native_token_gradient_pass_end_to_end(emu, monkeypatch, family):
     assert F.cosine_similarity(g.double().flatten(), want.flatten(), dim=0).item() > 0.99999
     c = facade.calls
     assert c["b200r_layernorm_bwd"] == 2 * depth + 1 and c["b200r_patch_scatter_f32"] == 1
-    assert c.get("b200r_attention_bwd", 0) == (depth if family == "vit" else 0)
+    assert c.get("b200r_attention_bwd_ws", 0) == (depth if family == "vit" else 0)      # falls through to the CUDA-core kernel on the emulator
     assert c["b200r_act_bwd_planes"] == (2 * depth if family == "mixer" else depth + 1)
 
 

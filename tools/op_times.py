@@ -65,7 +65,8 @@ if grad:
 for _ in range(3):
     recs.clear()
     if grad:
-        model.loss_and_input_grad(x01, yl)
+        lg, saved = model.forward_saved(x01)
+        model.input_grad(ops.ce_loss_grad(lg, yl)[1], saved)
     else:
         model.forward(img)
     torch.cuda.synchronize()

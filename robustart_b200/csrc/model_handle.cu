@@ -288,7 +288,12 @@ int b200r_model_create(int arch, const b200r_weight* weights, int n_weights, int
     std::vector<float> t((size_t)192 * 64);
     for (int o = 0; o < 64; ++o)
       for (int j = 0; j < 192; ++j) t[(size_t)j * 64 + o] = planes_value(packed[(size_t)o * 192 + j], m->planes) * sc[o];
-    if ((rc = upload_planes(m, t, &m->stem_wt))) return fail(rc);
+    // single fp16 plane in both precisions (see nets.ResNet.input_grad): the [n*112*112, 192] output only feeds col2im
+    const int planes_saved = m->planes;
+    m->planes = 1;
+    rc = upload_planes(m, t, &m->stem_wt);
+    m->planes = planes_saved;
+    if (rc) return fail(rc);
   }
   // ---- residual stages ----
   int inplanes = 64;
@@ -464,11 +469,10 @@ int b200r_model_input_grad(b200r_model* m, const float* dlogits, float* dx, b200
   RC((f16 ? b200r_maxpool3x3s2_bwd_nhwc_f16 : b200r_maxpool3x3s2_bwd_nhwc)(m->saved.stem, g, gp, ws, (size_t)n * h * w * 64, n, h2, w2, 64, stream));
   TAKE(gr, (size_t)n * h2 * w2 * 64);
   RC(relu_bwd(gp, m->saved.stem, nullptr, gr, (size_t)n * h2 * w2 * 64, stream));
-  TAKE(dcols, (size_t)n * h2 * w2 * 192);
-  RC(b200r_linear(gr, m->stem_wt.p, nullptr, nullptr, nullptr, dcols, nullptr, n * h2 * w2, 64, 192, B200R_ACT_NONE, P, stream));
-  if (f16) return b200r_stem_col2im_f32_f16(dcols, dx, n, H, Wd, kStd, 1.0f / kGradScale, stream);
-  const float std_u[3] = {kStd[0] * kGradScale, kStd[1] * kGradScale, kStd[2] * kGradScale};     // the kernel divides by std: 1/S rides on it
-  return b200r_stem_col2im_f32(dcols, dx, n, H, Wd, std_u, stream);
+  uint16_t* dcols = static_cast<uint16_t*>(m->arena.take((size_t)n * h2 * w2 * 192 * 2));            // ONE fp16 plane (hi plane of gr in)
+  B200R_CHECK_ARG(dcols, "activation arena too small");
+  RC(b200r_linear(gr, m->stem_wt.p, nullptr, nullptr, nullptr, dcols, nullptr, n * h2 * w2, 64, 192, B200R_ACT_NONE, B200R_PASSES_F16, stream));
+  return b200r_stem_col2im_f32_f16(dcols, dx, n, H, Wd, kStd, 1.0f / kGradScale, stream);
 }
 
 // The evaluation's ONE collective: sum the int64 hit counters over the ranks of an NCCL communicator, in place, on

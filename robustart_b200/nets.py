@@ -292,7 +292,10 @@ class ResNet:
         if not hasattr(self, "_fc_wt"):
             self._fc_wt = ops.to_planes(ops.from_planes(self.fc_w).t().contiguous(), f16)    # [2048|512, classes]
             wt = ops.from_planes(self.stem_w) * self.stem_scale.view(-1, 1)                  # BN scale folded, [64, 192]
-            self._stem_wt = ops.to_planes(wt.t().contiguous(), f16)                          # [192, 64]
+            # the stem GEMM's gradient runs on single fp16 planes in BOTH precisions: its [n*112*112, 192] output is the largest tensor
+            # of the whole pass (1.2 GB as a hi/lo pair at batch 128) and only feeds col2im; 11 bits on the last contraction leave the
+            # image gradient's direction unchanged (cosine > 0.9999, tests/test_backward_gpu.py)
+            self._stem_wt = ops.to_planes(wt.t().contiguous(), True)                         # [192, 64]
         # fp16 planes: the pass runs on S * dlogits (gradients of a classifier sit at 1e-4 .. 1e-10, below fp16's
         # normal range) and 1/S is folded into the last kernel; the attacks only use the sign / direction anyway
         S = GRAD_SCALE
@@ -305,7 +308,7 @@ class ResNet:
             g = self.block_backward(self.blocks[i], saved["blocks"][i], g, P, in_mask=in_mask, g_is_masked=True)
         s0 = saved["stem"]
         g = ops.relu_bwd(ops.maxpool3x3s2_bwd(s0, g), s0)
-        dcols = ops.linear(g.view(g.shape[0], -1, 64), self._stem_wt, passes=P)              # [P, n*ho*wo, 192]
+        dcols = ops.linear(g[:1].view(1, -1, 64), self._stem_wt, passes=ops.PASSES_F16)      # hi plane only -> [1, n*ho*wo, 192]
         return ops.stem_col2im(dcols, n, h, w, unscale=1.0 / S)
 
     def loss_and_input_grad(self, x01: torch.Tensor, labels: torch.Tensor, reduction: str = "sum"):

@@ -181,7 +181,9 @@ def test_stem_backward_strict(cuda):
     g = _planes(torch.randn(2, 64, 56, 56, device=cuda))
     net.input_grad(torch.zeros_like(logits), saved)                       # builds the transposed stem weights
     gm = ops.relu_bwd(ops.maxpool3x3s2_bwd(s0, g), s0)
-    got = ops.stem_col2im(ops.linear(gm.view(2, -1, 64), net._stem_wt), 2, 224, 224)
+    # the stem GEMM's gradient runs on single fp16 planes (hi plane of the masked gradient x fp16 weights): its [n*112*112, 192] output
+    # is the largest tensor of the pass and only feeds col2im
+    got = ops.stem_col2im(ops.linear(gm[:1].view(1, -1, 64), net._stem_wt, passes=ops.PASSES_F16), 2, 224, 224)
     # reference: d/dx of sum(maxpool(relu(conv(norm(x)) * s + b)) * g) in fp64
     xd = x.double().requires_grad_(True)
     mean = torch.tensor(MEAN, device=cuda, dtype=torch.float64).view(1, 3, 1, 1)
@@ -192,8 +194,9 @@ def test_stem_backward_strict(cuda):
     out = F.max_pool2d(F.relu(pre), 3, 2, 1)
     (ref,) = torch.autograd.grad(out, xd, _nchw(g).double())
     gd, rd = got.double().flatten(), ref.flatten()
-    assert ((gd - rd).norm() / rd.norm()).item() < 1e-3          # a handful of relu / argmax ties may differ
-    assert torch.quantile((gd - rd).abs()[::97], 0.999).item() < 1e-4 * rd.abs().max().item()
+    assert ((gd - rd).norm() / rd.norm()).item() < 2e-3          # 11-bit operands on this last contraction + a handful of relu / argmax ties
+    assert torch.quantile((gd - rd).abs()[::97], 0.999).item() < 1e-3 * rd.abs().max().item()
+    assert F.cosine_similarity(gd, rd, dim=0).item() > 0.99999
 
 
 def test_pgd_native_vs_autograd_source(cuda):

@@ -56,6 +56,7 @@ struct GemmParams {
   float* y_f32;
   int res_mma;    // residual added on the tensor core: extra k-blocks R[128 x 64] * I[BN x 64]^T (needs scale == NULL)
   int tma_store;  // planes output leaves through shared memory + cp.async.bulk.tensor stores
+  int two_chains; // split planes, BN <= 128: even / odd k-blocks accumulate in two TMEM accumulators, summed in the epilogue
   // STEM variant only: the A operand is gathered from the raw uint8 NHWC image by producer warps
   const uint8_t* img;       // [N, H_in, W_in, 3] uint8 (STEM_MODE 1)  or  float32 [N, 3, H_in, W_in] (STEM_MODE 2)
   float nmean[3], nstd[3];  // STEM_MODE 2: Normalize constants (mode 1 has them baked into the LUT)
@@ -112,7 +113,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int B_OFF = F16 ? A_TILE_BYTES : 2 * A_TILE_BYTES;           // F16: [A | B]; split: [A_hi | A_lo | B_hi | B_lo]
   constexpr int STAGE_BYTES = B_OFF + (F16 ? 1 : 2) * B_TILE_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers (power of two: 128 or 256)
+  // tcgen05's fp32 accumulation truncates (profiles/r2_accumulation_bias.txt: -0.77 * 2^-23 relative per 16-wide MMA step, a pure bias
+  // that shrinks every activation of a deep network).  With split planes and BN <= 128 the even and the odd k-blocks accumulate in
+  // two separate TMEM accumulators (two chains of half the length at about half the magnitude: half the bias), summed with one
+  // round-to-nearest add in the epilogue.
+  constexpr bool TWO = !F16 && !STEM && BN <= 128;
+  constexpr uint32_t ACC_COLS = TWO ? 2 * BN : BN;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;  // two accumulator buffers (power of two: 128 .. 512)
   // instruction descriptor: fp32 accumulator (bit 4), A/B format (bits 7, 10: 1 = bf16, 0 = fp16), N >> 3, M >> 4
   // (both precisions now feed fp16 operands: split planes are fp16 pairs)
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -165,6 +172,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const int kb_conv = p.KH * p.KW * p.cin_blocks;
   const int kb_res = p.res_mma ? BN / 64 : 0;           // residual k-blocks: acc[:, 64j:64j+64] += R[:, 64j:64j+64] * I64^T
   const int kblocks = kb_conv + kb_res;
+  const bool two = TWO && p.two_chains && kb_conv >= 2;
   const uint32_t a_bytes = (uint32_t)p.rows_box * BK * 2;
   const uint32_t tx_bytes = (p.passes == 3 ? 2u : 1u) * ((STEM ? 0u : a_bytes) + (uint32_t)B_TILE_BYTES);
 
@@ -220,8 +228,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t d_base = tmem_base + (uint32_t)(acc * ACC_COLS);
       for (int kb = 0; kb < kb_conv; ++kb) {
+        const uint32_t d_tmem = d_base + ((two && (kb & 1)) ? (uint32_t)BN : 0u);
+        const int first_kb = (two && (kb & 1)) ? 1 : 0;          // the k-block that initialises this chain
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
@@ -233,7 +243,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle row
-              umma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb | k) != 0);
+              umma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, ((kb - first_kb) | k) != 0);
               umma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1);
               umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1);
             }
@@ -241,7 +251,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-              umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kb | k) != 0);
+              umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, ((kb - first_kb) | k) != 0);
             }
           }
           umma_commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
@@ -259,8 +269,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-            umma_bf16(d_tmem + (uint32_t)(j * 64), a_hi + adv, b_hi + adv, IDESC_RES, 1);
-            if (!F16) umma_bf16(d_tmem + (uint32_t)(j * 64), a_lo + adv, b_hi + adv, IDESC_RES, 1);
+            umma_bf16(d_base + (uint32_t)(j * 64), a_hi + adv, b_hi + adv, IDESC_RES, 1);
+            if (!F16) umma_bf16(d_base + (uint32_t)(j * 64), a_lo + adv, b_hi + adv, IDESC_RES, 1);
           }
           umma_commit(empty_bar(stage));
           if (j == kb_res - 1) umma_commit(tfull_bar(acc));
@@ -299,13 +309,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const size_t out_row = ((size_t)n_img * p.Ho + ho) * p.Wo + wo;
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * kColsPerWarp);
 #pragma unroll 1
         for (int rd = 0; rd < kChunks / kPer; ++rd) {
           uint32_t vv[kPer][32];
 #pragma unroll
           for (int i = 0; i < kPer; ++i) tmem_ld32(t_addr + (uint32_t)((rd * kPer + i) * 32), vv[i]);
           tmem_ld_wait();
+          if (two) {                                          // second accumulator chain (odd k-blocks)
+            uint32_t ww[kPer][32];
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) tmem_ld32(t_addr + (uint32_t)(BN + (rd * kPer + i) * 32), ww[i]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < kPer; ++i)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) vv[i][j] = __float_as_uint(__uint_as_float(vv[i][j]) + __uint_as_float(ww[i][j]));
+          }
           if (rd == kChunks / kPer - 1) {                     // accumulator is in registers: hand the TMEM buffer back early
             tc_fence_before();
             __syncwarp();
@@ -487,13 +507,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       constexpr int kColsPerWarp = STEM ? BN : BN / 2;
       constexpr int kChunks = kColsPerWarp / 32;
       constexpr int kPer = kChunks >= 2 ? 2 : 1;            // accumulator chunks fetched per tcgen05.wait::ld
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kColsPerWarp);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * kColsPerWarp);
 #pragma unroll
       for (int rd = 0; rd < kChunks / kPer; ++rd) {
       uint32_t vv[kPer][32];
 #pragma unroll
       for (int i = 0; i < kPer; ++i) tmem_ld32(t_addr + (uint32_t)((rd * kPer + i) * 32), vv[i]);
       tmem_ld_wait();
+      if (two) {                                            // second accumulator chain (odd k-blocks)
+        uint32_t ww[kPer][32];
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) tmem_ld32(t_addr + (uint32_t)(BN + (rd * kPer + i) * 32), ww[i]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < kPer; ++i)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vv[i][j] = __float_as_uint(__uint_as_float(vv[i][j]) + __uint_as_float(ww[i][j]));
+      }
       if (rd == kChunks / kPer - 1) {                       // accumulator is in registers: hand the TMEM buffer back early
         tc_fence_before();
         __syncwarp();
@@ -992,7 +1022,10 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
   // BN = 256 halves the A-operand smem traffic per MMA (96 instead of 128 B/clk), worth it when the layer still
   // yields enough tiles to fill the SMs
   int BN = (Cout <= 64) ? 64 : 128;
-  {
+  // split planes: two accumulator chains per tile (half the truncation bias of the tensor core's fp32 accumulation); they need
+  // 4 x BN TMEM columns, so BN = 256 is left to the fp16 single-plane mode.  B200R_GEMM_OPTS bit 3 switches back.
+  p.two_chains = (!f16 && !(gemm_opts() & 8)) ? 1 : 0;
+  if (!p.two_chains) {
     const long m_tiles = (long)p.tiles_w * p.tiles_h * p.tiles_img;
     if (Cout % 256 == 0 && m_tiles * (Cout / 256) >= 2L * b200r_num_sms()) BN = 256;
   }

@@ -27,14 +27,15 @@ def _sd(arch):
     return calibrated_state_dict(arch, sd, CAL)
 
 
-# Absolute bars.  1e-3 is the north-star tolerance.  Two entries are above it and say why:
-#  * resnet50: tcgen05's fp32 accumulation TRUNCATES (measured on B200, profiles/r2_accumulation_bias.txt: a K = 8192 dot product
-#    of positive numbers comes out 4.7e-5 low, linear in K, ~0.77 ulp per 16-wide MMA step), so every activation of a deep net
-#    shrinks by ~1e-6 per layer-K-step; after 53 layers the features are 4.7e-5 short, which on |W f| ~ 27 is 1.2e-3.  Operand
-#    precision is not the limit (fp16 hi/lo pairs carry 22 bits; bf16 pairs gave 1.38e-3, fp16 pairs 1.22e-3).
-#  * efficientnet_b0: the random-weight network maps all images to nearly the same feature (6 % variation), so distinct top-1
-#    classes need a head that cancels 90 % of a |s W f| ~ 100 mean: the logits are a small difference of large numbers.
-BAR = {"resnet18": 1e-3, "resnet50": 1.5e-3, "vit_b16_224": 1e-3, "mixer_b16_224": 1e-3, "mobilenet_v2": 1e-3, "efficientnet_b0": 4e-3}
+# Absolute bars.  1e-3 is the north-star tolerance; measured on a B200 (round 2): ResNet-18 2.9e-4, ResNet-50 6.5e-4, ViT-B/16 8.0e-5,
+# Mixer-B/16 9.9e-5, MobileNetV2 2.7e-4, EfficientNet-B0 1.02e-3.
+#  * What bounds the error is the tensor core, not the 22-bit operands: tcgen05's fp32 accumulation TRUNCATES
+#    (profiles/r2_accumulation_bias.txt: a K = 8192 dot product of positive numbers came out 4.7e-5 low, linear in K, ~0.77 ulp per
+#    16-wide MMA step), so every activation of a deep net shrinks a little per layer.  With ONE accumulator per tile ResNet-50 measured
+#    1.22e-3 (bf16 pairs: 1.38e-3); the GEMM now alternates k-blocks between TWO accumulators summed in the epilogue (half the bias).
+#  * efficientnet_b0 keeps a 2e-3 bar: its random-weight network maps all images to nearly the same feature (6 % variation), so distinct
+#    top-1 classes need a head that cancels 90 % of a |s W f| ~ 65 mean -- the logits are a small difference of large numbers.
+BAR = {"resnet18": 1e-3, "resnet50": 1e-3, "vit_b16_224": 1e-3, "mixer_b16_224": 1e-3, "mobilenet_v2": 1e-3, "efficientnet_b0": 2e-3}
 
 
 @pytest.mark.parametrize("arch", ["resnet18", "resnet50", "vit_b16_224", "mixer_b16_224", "mobilenet_v2", "efficientnet_b0"])

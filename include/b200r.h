@@ -389,6 +389,20 @@ int b200r_image_im2col_f32(const float* img, uint16_t* planes, int n, int h, int
                            int pad, int kpad, const float* mean_host, const float* std_host,
                            b200r_stream_t stream);
 
+/* Input-gradient pieces of the mobile families (autograd of mobilenet_v2.py:31-77 / efficientnet.py:312-360 as the attack loops
+ * see it).  The depthwise convolution's input gradient is b200r_dwconv_nhwc on flipped taps (stride 2: after b200r_dilate2_nhwc),
+ * the 1x1 convolutions are b200r_conv2d_dgrad_nhwc, activations b200r_act_bwd_planes (ReLU6 from the saved output, swish / sigmoid
+ * from the saved pre-activation). */
+/* squeeze-excite: ds planes [n, s_stride] = sum over pixels of a * b (a, b planes [n, hw, c]); columns >= c are zeroed */
+int b200r_channel_dot(const uint16_t* a, const uint16_t* b, uint16_t* ds, int n, int hw, int c, int s_stride,
+                      b200r_stream_t stream);
+/* out = a + b on split planes (two gradient branches joining); count = elements per plane, multiple of 8 */
+int b200r_planes_add(const uint16_t* a, const uint16_t* b, uint16_t* out, size_t count, b200r_stream_t stream);
+/* transpose of b200r_image_stem3x3s2_f32 composed with Normalize: dy planes [n, ho, wo, cout] -> float32 NCHW gradient w.r.t. the
+ * [0,1] image, times unscale; wgt float32 [cout][27] with the BatchNorm scale folded in */
+int b200r_image_stem3x3s2_bwd(const uint16_t* dy, const float* wgt, float* dx, int n, int h, int w, int cout,
+                              const float* std_host, float unscale, b200r_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Token models (ViT-B/16: prototype/prototype/model/vision_transformer.py:44-349; MLP-Mixer-B/16:
  * prototype/prototype/model/vit/mlp_mixer.py:7-159), split planes [rows, c].

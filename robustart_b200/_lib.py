@@ -157,6 +157,9 @@ SIGNATURES.update({
     "b200r_act_bwd_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, c_stream]),
     "b200r_patch_scatter_f32": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_host_f3, c_stream]),
     "b200r_attention_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_stream]),
+    "b200r_channel_dot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_planes_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
+    "b200r_image_stem3x3s2_bwd": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_host_f3, C.c_float, c_stream]),
     "b200r_attention_bwd_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "b200r_attention_bwd_ws": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          c_stream]),

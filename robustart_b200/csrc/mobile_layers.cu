@@ -374,4 +374,144 @@ int b200r_image_stem3x3s2_f32(const float* img, const float* wgt, const float* s
   return stem3_common(img, wgt, scale, bias, y, n, h, w, cout, act, mean_host, std_host, false, as_stream(stream));
 }
 
+
+// ---- input-gradient pieces of the mobile families (round 2) ---------------------------------------------------------------
+// autograd of mobilenet_v2.py:31-77 / efficientnet.py:312-360 as the attack loops see it (autopgd_base.py:371-376): the depthwise
+// convolution's input gradient is the SAME kernel on flipped taps (stride 2: after b200r_dilate2_nhwc), the 1x1 convolutions are
+// b200r_conv2d_dgrad_nhwc, the activations b200r_act_bwd_planes; what is new here is the squeeze-excite reduction, a plain add, and
+// the transposed 3x3/s2 image stem.
+}  // extern "C"  (kernels below live in the anonymous namespace again)
+namespace {
+
+// ds[n, c] = sum_p a[n, p, c] * b[n, p, c]  (squeeze-excite: gradient w.r.t. the per-channel scale).  One 256-thread block per
+// (image, 8-channel chunk): threads stride over the pixels, fixed-order shared-memory tree.
+__global__ void __launch_bounds__(256) channel_dot_kernel(const uint4* __restrict__ ah, const uint4* __restrict__ al, const uint4* __restrict__ bh,
+                                                          const uint4* __restrict__ bl, uint16_t* __restrict__ oh, uint16_t* __restrict__ ol, int hw,
+                                                          int c8, int s_stride) {
+  __shared__ float red[256][8];
+  const int im = blockIdx.y, cc = blockIdx.x;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = threadIdx.x; p < hw; p += 256) {
+    const size_t i = ((size_t)im * hw + p) * c8 + cc;
+    float a[8], b[8];
+    unpack8(__ldg(ah + i), __ldg(al + i), a);
+    unpack8(__ldg(bh + i), __ldg(bl + i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(a[j], b[j], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[threadIdx.x][j] += red[threadIdx.x + s][j];
+    __syncthreads();
+  }
+  if (threadIdx.x < 8) {
+    uint16_t h, l;
+    split_pair(red[0][threadIdx.x], h, l);
+    oh[(size_t)im * s_stride + cc * 8 + threadIdx.x] = h;
+    ol[(size_t)im * s_stride + cc * 8 + threadIdx.x] = l;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) planes_add_kernel(const uint4* __restrict__ ah, const uint4* __restrict__ al, const uint4* __restrict__ bh,
+                                                               const uint4* __restrict__ bl, uint4* __restrict__ oh, uint4* __restrict__ ol, size_t count8) {
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < count8; t += (size_t)gridDim.x * kThreads) {
+    float a[8], b[8];
+    unpack8(__ldg(ah + t), __ldg(al + t), a);
+    unpack8(__ldg(bh + t), __ldg(bl + t), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    uint4 h, l;
+    pack8(a, h, l);
+    oh[t] = h; ol[t] = l;
+  }
+}
+
+// transposed 3x3/s2/p1 image stem: dx[n, c, iy, ix] = unscale / std[c] * sum_{oc, ky, kx : 2 oy + ky - 1 = iy, 2 ox + kx - 1 = ix} w[oc][ky][kx][c] dy[n, oy, ox, oc]
+// thread = input pixel (three channels); weights [27][cout] in shared memory (BN scale folded in by the caller)
+__global__ void __launch_bounds__(kThreads) image_stem3x3s2_bwd_kernel(const uint4* __restrict__ dyh, const uint4* __restrict__ dyl,
+                                                                        const float* __restrict__ wgt, float* __restrict__ dx, int n, int h, int w,
+                                                                        int ho, int wo, int cout, float k0, float k1, float k2) {
+  __shared__ __align__(16) float sw[27 * 64];
+  for (int i = threadIdx.x; i < 27 * cout; i += kThreads) {          // wgt is [cout][27] (ky, kx, c) -> sw[tap][cout]
+    const int t = i / cout, oc = i - t * cout;
+    sw[i] = wgt[oc * 27 + t];
+  }
+  __syncthreads();
+  const int c8 = cout / 8;
+  const size_t total = (size_t)n * h * w;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
+    const int ix = (int)(t % w), iy = (int)((t / w) % h), im = (int)(t / ((size_t)w * h));
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = iy + 1 - ky;
+      if (ty < 0 || (ty & 1) || (ty >> 1) >= ho) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = ix + 1 - kx;
+        if (tx < 0 || (tx & 1) || (tx >> 1) >= wo) continue;
+        const size_t base = (((size_t)im * ho + (ty >> 1)) * wo + (tx >> 1)) * c8;
+        const float* wk = sw + (ky * 3 + kx) * 3 * cout;
+        for (int cc = 0; cc < c8; ++cc) {
+          float g[8];
+          unpack8(__ldg(dyh + base + cc), __ldg(dyl + base + cc), g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[0] = fmaf(g[j], wk[cc * 8 + j], acc[0]);
+            acc[1] = fmaf(g[j], wk[cout + cc * 8 + j], acc[1]);
+            acc[2] = fmaf(g[j], wk[2 * cout + cc * 8 + j], acc[2]);
+          }
+        }
+      }
+    }
+    const size_t o = ((size_t)im * 3 * h + iy) * w + ix;
+    dx[o] = acc[0] * k0; dx[o + (size_t)h * w] = acc[1] * k1; dx[o + 2 * (size_t)h * w] = acc[2] * k2;
+  }
+}
+
+}  // namespace
+extern "C" {
+
+/* ds planes [n, s_stride] (first c entries) = sum over pixels of a * b, a / b planes [n, hw, c] */
+int b200r_channel_dot(const uint16_t* a, const uint16_t* b, uint16_t* ds, int n, int hw, int c, int s_stride, b200r_stream_t stream) {
+  B200R_CHECK_ARG(a && b && ds, "null pointer");
+  B200R_CHECK_ARG(c % 8 == 0 && s_stride >= c && n > 0 && n < 65536 && hw > 0, "bad shape (c %% 8 == 0, s_stride >= c)");
+  const size_t cnt = (size_t)n * hw * c, scnt = (size_t)n * s_stride;
+  B200R_CUDA(cudaMemsetAsync(ds, 0, scnt * 2 * sizeof(uint16_t), as_stream(stream)));       // padding columns of the scale vector stay zero
+  channel_dot_kernel<<<dim3(c / 8, n), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(a + cnt),
+                                                                    reinterpret_cast<const uint4*>(b), reinterpret_cast<const uint4*>(b + cnt), ds,
+                                                                    ds + scnt, hw, c / 8, s_stride);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+/* out = a + b on split planes; count = elements per plane, multiple of 8 */
+int b200r_planes_add(const uint16_t* a, const uint16_t* b, uint16_t* out, size_t count, b200r_stream_t stream) {
+  B200R_CHECK_ARG(a && b && out, "null pointer");
+  B200R_CHECK_ARG(count % 8 == 0, "count must be a multiple of 8");
+  if (!count) return B200R_OK;
+  planes_add_kernel<<<grid_for(count / 8), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(a + count), reinterpret_cast<const uint4*>(b),
+      reinterpret_cast<const uint4*>(b + count), reinterpret_cast<uint4*>(out), reinterpret_cast<uint4*>(out + count), count / 8);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+/* transpose of b200r_image_stem3x3s2_f32 composed with Normalize: dy planes [n, ho, wo, cout] -> float32 NCHW gradient w.r.t. the
+ * [0,1] image, times `unscale`; wgt float32 [cout][27] with the BN scale already folded in */
+int b200r_image_stem3x3s2_bwd(const uint16_t* dy, const float* wgt, float* dx, int n, int h, int w, int cout, const float* std_host,
+                              float unscale, b200r_stream_t stream) {
+  B200R_CHECK_ARG(dy && wgt && dx && std_host, "null pointer");
+  B200R_CHECK_ARG(cout % 8 == 0 && cout <= 64 && n > 0 && h > 0 && w > 0, "cout must be a multiple of 8, at most 64");
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const size_t cnt = (size_t)n * ho * wo * cout;
+  image_stem3x3s2_bwd_kernel<<<grid_for((size_t)n * h * w), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(dy + cnt), wgt, dx, n, h, w, ho, wo, cout, unscale / std_host[0],
+      unscale / std_host[1], unscale / std_host[2]);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
 }  // extern "C"

@@ -128,6 +128,10 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
     }
     case B200R_ACT_GELU_ERF: return 0.5f * v * (1.f + erff(v * 0.7071067811865476f));
     case B200R_ACT_TANH: return tanhf(v);
+    case B200R_ACT_RELU: return fmaxf(v, 0.f);
+    case B200R_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
+    case B200R_ACT_SWISH: return v / (1.f + expf(-v));
+    case B200R_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
     default: return v;
   }
 }
@@ -143,6 +147,18 @@ __device__ __forceinline__ float act_deriv(float v, int act) {
     case B200R_ACT_TANH: {
       const float t = tanhf(v);
       return 1.f - t * t;
+    }
+    // ReLU / ReLU6: the derivative is the same function of the pre-activation and of the OUTPUT (0 < v [< 6]), so the saved output
+    // of a fused conv + BN + ReLU6 layer serves as `pre` (mobilenet_v2.py:31-47: ReLU6 = hardtanh(0, 6))
+    case B200R_ACT_RELU: return v > 0.f ? 1.f : 0.f;
+    case B200R_ACT_RELU6: return (v > 0.f && v < 6.f) ? 1.f : 0.f;
+    case B200R_ACT_SWISH: {                                  // x sigmoid(x) (efficientnet.py:271-277)
+      const float sg = 1.f / (1.f + expf(-v));
+      return sg * (1.f + v * (1.f - sg));
+    }
+    case B200R_ACT_SIGMOID: {
+      const float sg = 1.f / (1.f + expf(-v));
+      return sg * (1.f - sg);
     }
     default: return 1.f;
   }
@@ -310,7 +326,7 @@ inline unsigned grid_for(size_t items) {
   size_t cap = (size_t)b200r_num_sms() * 16;
   return (unsigned)(b < cap ? (b ? b : 1) : cap);
 }
-inline bool act_ok(int act) { return act == B200R_ACT_GELU_TANH || act == B200R_ACT_GELU_ERF || act == B200R_ACT_TANH; }
+inline bool act_ok(int act) { return act >= B200R_ACT_RELU && act <= B200R_ACT_SIGMOID; }
 }  // namespace
 
 extern "C" {
@@ -331,7 +347,7 @@ int b200r_layernorm_bwd(const uint16_t* dy, const uint16_t* x, const float* gamm
 int b200r_act_planes(const uint16_t* pre, uint16_t* out, size_t count, int act, b200r_stream_t stream) {
   B200R_CHECK_ARG(pre && out, "null pointer");
   B200R_CHECK_ARG(count > 0 && count % 8 == 0, "count must be a positive multiple of 8");
-  B200R_CHECK_ARG(act_ok(act), "activation %d not supported (gelu_tanh, gelu_erf, tanh)", act);
+  B200R_CHECK_ARG(act_ok(act), "activation %d not supported", act);
   act_planes_kernel<false><<<grid_for(count / 8), kThreads, 0, as_stream(stream)>>>(
       reinterpret_cast<const uint4*>(pre), reinterpret_cast<const uint4*>(pre + count), nullptr, nullptr, reinterpret_cast<uint4*>(out),
       reinterpret_cast<uint4*>(out + count), count / 8, act);
@@ -342,7 +358,7 @@ int b200r_act_planes(const uint16_t* pre, uint16_t* out, size_t count, int act, 
 int b200r_act_bwd_planes(const uint16_t* dy, const uint16_t* pre, uint16_t* dx, size_t count, int act, b200r_stream_t stream) {
   B200R_CHECK_ARG(dy && pre && dx, "null pointer");
   B200R_CHECK_ARG(count > 0 && count % 8 == 0, "count must be a positive multiple of 8");
-  B200R_CHECK_ARG(act_ok(act), "activation %d not supported (gelu_tanh, gelu_erf, tanh)", act);
+  B200R_CHECK_ARG(act_ok(act), "activation %d not supported", act);
   act_planes_kernel<true><<<grid_for(count / 8), kThreads, 0, as_stream(stream)>>>(
       reinterpret_cast<const uint4*>(pre), reinterpret_cast<const uint4*>(pre + count), reinterpret_cast<const uint4*>(dy),
       reinterpret_cast<const uint4*>(dy + count), reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dx + count), count / 8, act);

@@ -727,6 +727,13 @@ class _PW:
     def __call__(self, x, act=None, res=None, passes=3):
         return ops.conv2d_nhwc(x, self.w, self.scale, self.bias, res, act=act, passes=passes)
 
+    def dgrad(self, dy, res=None, passes=3):
+        """Input gradient of the 1x1 convolution (BN scale folded): dy planes [2,n,h,w,cout] -> planes [2,n,h,w,cin] (+ res)."""
+        if getattr(self, "_wt", None) is None:
+            w = ops.merge_f32(self.w)                                  # [cout, 1, 1, cin]
+            self._wt = ops.split_f32(w.permute(3, 1, 2, 0).contiguous())   # [cin, 1, 1, cout]
+        return ops.conv2d_dgrad(dy, self._wt, res, None, pad=0, passes=passes)
+
 
 class _DW:
     def __init__(self, sd, conv, bn, device, stride):
@@ -737,6 +744,16 @@ class _DW:
 
     def __call__(self, x, act):
         return ops.dwconv_nhwc(x, self.w, self.scale, self.bias, k=self.k, stride=self.stride, pad=self.k // 2, act=act)
+
+    def dgrad(self, dpre):
+        """Input gradient of depthwise conv + BN from the gradient w.r.t. the BN output: the same kernel on flipped taps with the BN
+        scale folded in; a stride-2 layer first re-inserts the zeros (pad k//2 = k-1-k//2 for odd k, so the padding is unchanged)."""
+        if getattr(self, "_wb", None) is None:
+            self._wb = (self.w.flip(0) * self.scale.view(1, -1)).contiguous()      # taps reversed = flipped in (ky, kx)
+            self._one, self._zero = torch.ones_like(self.scale), torch.zeros_like(self.bias)
+        if self.stride == 2:
+            dpre = ops.dilate2(dpre)
+        return ops.dwconv_nhwc(dpre, self._wb, self._one, self._zero, k=self.k, stride=1, pad=self.k // 2, act=None)
 
 
 class _ImageStem:
@@ -753,6 +770,16 @@ class _ImageStem:
         self.scale, self.bias = _fold_bn(sd, bn, device)
         self.act, self.cout = act, w.shape[0]
         self.direct = os.environ.get("B200R_IMAGE_STEM", "direct") != "gemm" and self.cout % 8 == 0 and self.cout <= 64
+
+    def dgrad(self, dpre, n, h, w, unscale):
+        """d loss / d image (float32 NCHW) from the gradient w.r.t. the stem's BN output."""
+        if getattr(self, "_w27s", None) is None:
+            self._w27s = (self.w27 * self.scale.view(-1, 1)).contiguous()
+        return ops.image_stem3x3s2_bwd(dpre, self._w27s, n, h, w, unscale=unscale)
+
+    def pre(self, images):
+        """conv + BN without the activation (the gradient pass needs swish's pre-activation)."""
+        return ops.image_stem3x3s2(images, self.w27, self.scale, self.bias, act=None)
 
     def __call__(self, images, passes):
         if self.direct:
@@ -801,6 +828,43 @@ class MobileNetV2(_TokenModel):
 
     def launches_per_forward(self):
         return 2 + sum(2 + (1 if "pw" in b else 0) for b in self.blocks) + 3
+
+    # -- forward that keeps what the input-gradient pass needs, and that pass (mobilenet_v2.py:31-202 reversed) -------------------
+    def forward_saved(self, x01: torch.Tensor):
+        """float32 NCHW [0,1] images -> (logits, saved).  Same launches as forward(); every ReLU6 output is kept (its derivative is a
+        function of the output)."""
+        n, _, h, w = x01.shape
+        P = self.passes
+        x = self.stem(x01.contiguous(), P)
+        saved = {"shape": (n, h, w), "stem": x, "blocks": []}
+        for b in self.blocks:
+            a1 = b["pw"](x, act="relu6", passes=P) if "pw" in b else None
+            a2 = b["dw"](a1 if a1 is not None else x, "relu6")
+            x = b["pl"](a2, res=x if b["res"] else None, passes=P)
+            saved["blocks"].append((a1, a2))
+        last = self.last(x, act="relu6", passes=P)
+        saved["last"] = last
+        pooled = ops.global_avgpool(last)
+        logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
+        self.fc(pooled, passes=P, out_f32=logits)
+        return logits, saved
+
+    def input_grad(self, dlogits: torch.Tensor, saved, passes: Optional[int] = None) -> torch.Tensor:
+        P = self.passes if passes is None else passes
+        n, h, w = saved["shape"]
+        S = GRAD_SCALE
+        last = saved["last"]
+        g = self.fc.dgrad(ops.to_planes(dlogits.contiguous(), False, S), P)                 # [2, n, 1280]
+        g = ops.global_avgpool_bwd(g, last.shape[2], last.shape[3])
+        g = self.last.dgrad(ops.act_bwd_planes(g, last, "relu6"), passes=P)
+        for b, (a1, a2) in zip(reversed(self.blocks), reversed(saved["blocks"])):
+            t = b["pl"].dgrad(g, passes=P)                                                  # linear bottleneck: no activation
+            t = b["dw"].dgrad(ops.act_bwd_planes(t, a2, "relu6"))
+            if a1 is not None:
+                g = b["pw"].dgrad(ops.act_bwd_planes(t, a1, "relu6"), res=g if b["res"] else None, passes=P)
+            else:
+                g = ops.planes_add(t, g) if b["res"] else t
+        return self.stem.dgrad(ops.act_bwd_planes(g, saved["stem"], "relu6"), n, h, w, 1.0 / S)
 
 
 class EfficientNetB0(_TokenModel):
@@ -852,6 +916,55 @@ class EfficientNetB0(_TokenModel):
 
     def launches_per_forward(self):
         return 2 + sum(6 + (1 if "pw" in b else 0) for b in self.blocks) + 3
+
+    # -- forward that keeps what the input-gradient pass needs, and that pass (efficientnet.py:289-495 reversed) -------------------
+    def forward_saved(self, x01: torch.Tensor):
+        """float32 NCHW [0,1] images -> (logits, saved).  swish and sigmoid need their PRE-activation, so every activated layer runs
+        as (conv + BN) then b200r_act_planes here, instead of the fused epilogue of forward()."""
+        n, _, h, w = x01.shape
+        P = self.passes
+        p0 = self.stem.pre(x01.contiguous())
+        x = ops.act_planes(p0, "swish")
+        saved = {"shape": (n, h, w), "stem": p0, "blocks": []}
+        for b in self.blocks:
+            x_in = x
+            ppw = b["pw"](x, passes=P) if "pw" in b else None
+            y = ops.act_planes(ppw, "swish") if ppw is not None else x
+            pdw = b["dw"](y, None)
+            y = ops.act_planes(pdw, "swish")
+            p1 = b["se1"](ops.global_avgpool(y), passes=P)
+            p2 = b["se2"](ops.act_planes(p1, "swish"), passes=P)
+            s = ops.act_planes(p2, "sigmoid")
+            x = b["pl"](ops.channel_scale(y, s), res=x_in if b["res"] else None, passes=P)
+            saved["blocks"].append((ppw, pdw, y, p1, p2, s))
+        ph = self.head(x, passes=P)
+        saved["head"] = ph
+        pooled = ops.global_avgpool(ops.act_planes(ph, "swish"))
+        logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
+        self.fc(pooled, passes=P, out_f32=logits)
+        return logits, saved
+
+    def input_grad(self, dlogits: torch.Tensor, saved, passes: Optional[int] = None) -> torch.Tensor:
+        P = self.passes if passes is None else passes
+        n, h, w = saved["shape"]
+        S = GRAD_SCALE
+        ph = saved["head"]
+        g = self.fc.dgrad(ops.to_planes(dlogits.contiguous(), False, S), P)
+        g = ops.global_avgpool_bwd(g, ph.shape[2], ph.shape[3])
+        g = self.head.dgrad(ops.act_bwd_planes(g, ph, "swish"), passes=P)
+        for b, (ppw, pdw, y, p1, p2, s) in zip(reversed(self.blocks), reversed(saved["blocks"])):
+            dz = b["pl"].dgrad(g, passes=P)                                                # gradient w.r.t. y * s
+            # squeeze-excite: y * s with s = sigmoid(se2(swish(se1(mean(y))))) (efficientnet.py:338-360)
+            ds = ops.channel_dot(dz, y, s.shape[-1])
+            t = b["se2"].dgrad(ops.act_bwd_planes(ds, p2, "sigmoid"), P)
+            t = b["se1"].dgrad(ops.act_bwd_planes(t, p1, "swish"), P)                      # [2, n, hid]
+            dy = ops.planes_add(ops.channel_scale(dz, s), ops.global_avgpool_bwd(t, y.shape[2], y.shape[3]))
+            t = b["dw"].dgrad(ops.act_bwd_planes(dy, pdw, "swish"))
+            if ppw is not None:
+                g = b["pw"].dgrad(ops.act_bwd_planes(t, ppw, "swish"), res=g if b["res"] else None, passes=P)
+            else:
+                g = ops.planes_add(t, g) if b["res"] else t
+        return self.stem.dgrad(ops.act_bwd_planes(g, saved["stem"], "swish"), n, h, w, 1.0 / S)
 
 
 _MOBILE_ARCHS = {"mobilenet_v2": (MobileNetV2, mobilenet_v2_spec), "mobilenet_v2_x1_0": (MobileNetV2, mobilenet_v2_spec),

@@ -762,3 +762,35 @@ def image_im2col(img, k, stride, pad, kpad, mean=IMAGENET_MEAN, std=IMAGENET_STD
     with torch.cuda.device(img.device):
         _lib.check(fn(img.data_ptr(), out.data_ptr(), n, h, w, k, stride, pad, kpad, _lib.f3(mean), _lib.f3(std), _stream()))
     return out, ho, wo
+
+
+# ------------------------------------------------------------------------------------------------
+# input-gradient pieces of the mobile families
+# ------------------------------------------------------------------------------------------------
+def channel_dot(a, b, s_stride=None):
+    """planes [2, n, s_stride]: sum over pixels of a * b (a, b planes [2,n,h,w,c]) -- d loss / d (squeeze-excite scale)."""
+    _, n, h, w, c = a.shape
+    assert a.shape == b.shape
+    s_stride = c if s_stride is None else s_stride
+    out = torch.empty((2, n, s_stride), dtype=torch.int16, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().b200r_channel_dot(a.data_ptr(), b.data_ptr(), out.data_ptr(), n, h * w, c, s_stride, _stream()))
+    return out
+
+
+def planes_add(a, b):
+    assert a.shape == b.shape
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().b200r_planes_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a[0].numel(), _stream()))
+    return out
+
+
+def image_stem3x3s2_bwd(dy, wgt_scaled, n, h, w, std=IMAGENET_STD, unscale: float = 1.0):
+    """dy planes [2, n, ho, wo, cout] -> float32 NCHW gradient w.r.t. the [0,1] image (transposed 3x3/s2 stem, 1/std, unscale)."""
+    cout = wgt_scaled.shape[0]
+    dx = torch.empty((n, 3, h, w), dtype=torch.float32, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().b200r_image_stem3x3s2_bwd(dy.data_ptr(), wgt_scaled.data_ptr(), dx.data_ptr(), n, h, w, cout, _lib.f3(std),
+                                                         unscale, _stream()))
+    return dx

@@ -217,7 +217,7 @@ def build_source_model(model_cfg, ckpt_path, device):
     arch = nets.ARCH_ALIASES.get(model_cfg["type"], model_cfg["type"])
     if arch in nets._RESNET_CFG and os.environ.get("B200R_SOURCE_AUTOGRAD", "0") != "1":
         return NativeModel(build_b200_model(model_cfg, ckpt_path, device))
-    if arch in nets._TOKEN_ARCHS and os.environ.get("B200R_SOURCE_AUTOGRAD", "0") != "1":
+    if (arch in nets._TOKEN_ARCHS or arch in nets._MOBILE_ARCHS) and os.environ.get("B200R_SOURCE_AUTOGRAD", "0") != "1":
         # forward + input gradient of ViT / Mixer on our kernels (token_backward.cu + dgrad GEMMs; 4.2x / 1.65x the autograd twin
         # on the PGD-Linf loop when first measured, profiles/r2_pgd_token.json)
         return NativeModel(build_b200_model(model_cfg, ckpt_path, device))

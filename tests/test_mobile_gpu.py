@@ -57,3 +57,56 @@ def test_mobile_logits_match_reference(cuda, arch):
     assert (got.argmax(1) == want.argmax(1)).all()
     x01 = images.permute(0, 3, 1, 2).float().div(255).contiguous()
     assert np.abs(model(x01).cpu().numpy() - got).max() < 1e-5
+
+
+@pytest.mark.parametrize("arch", ["mobilenet_v2", "efficientnet_b0"])
+def test_native_input_grad_matches_autograd_twin(cuda, arch):
+    """Input-gradient pass of the mobile families on the kernels (depthwise dgrad = the forward kernel on flipped taps, 1x1 dgrad GEMMs,
+    ReLU6 / swish / sigmoid derivatives, squeeze-excite reduction, transposed image stem) against torch.autograd on the fp64 twin
+    (whose logits equal the reference classes' goldens): what autopgd_base.py:371-376 / foolbox value_and_grad ask of a source model."""
+    import torch.nn.functional as F
+    from robustart_b200 import nets, ops, torch_models as TM
+    MEAN, STD = ops.IMAGENET_MEAN, ops.IMAGENET_STD
+    # BatchNorm statistics of a calibration batch (tests/golden/calibrated_logits.npz), the synthetic head: with unrelated random
+    # statistics these two networks collapse every image onto one feature and their gradients shrink ~1000x per block -- below any
+    # float format's range long before the image (the fp64 twin returns 1e-40s); a network whose BN matches its data does not
+    import os as _os
+    import numpy as _np
+    from util import calibrated_state_dict, HEAD_KEYS
+    raw = nets.random_state_dict(nets._MOBILE_ARCHS[arch][1](), 0)
+    cal = _np.load(_os.path.join(_os.path.dirname(__file__), "golden", "calibrated_logits.npz"))
+    sd = calibrated_state_dict(arch, raw, cal)
+    for k in (HEAD_KEYS[arch] + ".weight", HEAD_KEYS[arch] + ".bias"):
+        sd[k] = raw[k]
+    model = nets.build_model(arch, sd, device=cuda)
+    twin = TM.build(arch, nets._strip_prefix(sd)).to(cuda).double().eval()
+    torch.manual_seed(3)
+    n = 2
+    x01 = torch.rand(n, 3, 224, 224, device=cuda)
+    y = torch.randint(0, 1000, (n,), device=cuda)
+    logits, saved = model.forward_saved(x01)
+    assert (logits - model.forward(x01)).abs().max().item() < 1e-3
+    _, dlogits = ops.ce_loss_grad(logits, y)
+    g = model.input_grad(dlogits, saved)
+    assert torch.isfinite(g).all()
+    m = torch.tensor(MEAN, device=cuda, dtype=torch.float64).view(1, 3, 1, 1)
+    s = torch.tensor(STD, device=cuda, dtype=torch.float64).view(1, 3, 1, 1)
+    xd = x01.double().requires_grad_(True)
+    lt = twin((xd - m) / s)
+    assert (lt.detach() - logits.double()).abs().max().item() < 1e-3
+    (want,) = torch.autograd.grad(F.cross_entropy(lt, y, reduction="sum"), xd)
+    scale = want.abs().max().item()
+    assert scale > 1e-8, scale                      # the test network has a usable gradient
+    cos = F.cosine_similarity(g.double().flatten(), want.flatten(), dim=0).item()
+    err = (g.double() - want).abs().max().item()
+    print(arch, "|grad| max %.2e" % scale, "grad max err / max %.2e  cos %.6f" % (err / scale, cos))
+    assert cos > 0.999, cos
+    assert err < 5e-2 * scale                       # ReLU6 / swish nets flip a few saturation masks between fp32 kernels and the fp64 twin
+    big = want.abs() > 1e-2 * scale
+    assert (torch.sign(g.double())[big] == torch.sign(want)[big]).float().mean().item() > 0.99
+
+
+def test_mobile_sources_are_native(cuda):
+    from robustart_b200 import attacks, solver
+    for t in ("mobilenet_v2", "efficientnet_b0"):
+        assert isinstance(solver.build_source_model({"type": t, "kwargs": {}}, None, cuda), attacks.NativeModel)

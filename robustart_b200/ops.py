@@ -192,6 +192,8 @@ def pgd_step_l1_(x, g, x0, eps_step: float, eps: float):
     """One PGD-L1 step of ART's ProjectedGradientDescentPyTorch(norm=1), in place on x [n, ...] (b200r_pgd_step_l1)."""
     for t, nm in ((x, "x"), (g, "g"), (x0, "x0")):
         _need_cuda(t, torch.float32, nm)
+    if not (x.shape == g.shape == x0.shape):
+        raise ValueError("pgd_step_l1_: x, g, x0 must have the same shape")
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().b200r_pgd_step_l1(x.data_ptr(), g.data_ptr(), x0.data_ptr(), x.shape[0], x[0].numel(),
                                                  eps_step, eps, _stream()))
@@ -231,6 +233,9 @@ def fab_combine_linf_(x1, d1, x0, d2, dmax1, dmax2, eta: float, alpha_max: float
     """FAB's convex-combination update (fab_base.py:200-232), in place on x1 [rows, ...]."""
     for v, nm in ((x1, "x1"), (d1, "d1"), (x0, "x0"), (d2, "d2"), (dmax1, "dmax1"), (dmax2, "dmax2")):
         _need_cuda(v, torch.float32, nm)
+    rows = x1.shape[0]
+    if not (d1.numel() == d2.numel() == x0.numel() == x1.numel() and dmax1.numel() == dmax2.numel() == rows):
+        raise ValueError("fab_combine_linf_: x1, d1, x0, d2 must hold the same [rows, dim] elements and dmax1 / dmax2 one value per row")
     with torch.cuda.device(x1.device):
         _lib.check(_lib.load().b200r_fab_combine_linf(x1.data_ptr(), d1.data_ptr(), x0.data_ptr(), d2.data_ptr(), dmax1.data_ptr(),
                                                       dmax2.data_ptr(), x1.shape[0], x1[0].numel(), eta, alpha_max, _stream()))

@@ -301,17 +301,19 @@ def corruption_roofline(pipe, inputs, pk):
             for i in range(per_graph):
                 ops.corrupt_u8(inputs[i % len(inputs)], "gaussian_noise", 1 + i % 5, seed=i, out=outs[i % len(outs)])
     torch.cuda.current_stream().wait_stream(side)
-    for _ in range(3):
+    for _ in range(20):
         g.replay()
     torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    s.record()
-    for _ in range(reps):
-        g.replay()
-    e.record()
-    torch.cuda.synchronize()
-    t = s.elapsed_time(e) * 1e-3 / (reps * per_graph)
+    reps, groups, times = 10, 7, []
+    for _ in range(groups):          # median of 7 groups: a 3 ms measurement right after the long loops sees clock ramps
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        times.append(s.elapsed_time(e) * 1e-3 / (reps * per_graph))
+    t = sorted(times)[groups // 2]
     alg = 2.0 * BATCH * H * W * 3
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r2_ncu_corruptions.json")
@@ -322,7 +324,9 @@ def corruption_roofline(pipe, inputs, pk):
     return {"bound": "hbm", "kernel": "normal_noise_strata_kernel (gaussian_noise, u8 NHWC -> u8 NHWC, device Philox + quantile table)", "achieved": alg / t / 1e9,
             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg / t / 1e9 / pk["hbm_gbs"], "traffic": traffic,
             "us_per_launch": t * 1e6, "algorithmic_bytes_per_launch": alg, "images_per_s_kernel_only": BATCH / t,
-            "timing": "CUDA graph of %d launches over %d rotating input batches (> L2), %d replays" % (per_graph, len(inputs), reps)}
+            "us_per_launch_groups": [round(x * 1e6, 2) for x in times],
+            "traffic_note": "ncu dram bytes of a warm launch on ONE repeated batch (profiles/r2_ncu_corruptions.json): the 126 MB L2 holds the previous output, so less than the algorithmic bytes reach DRAM there; the timed launches rotate over 8 batches",
+            "timing": "CUDA graph of %d launches over %d rotating input batches (> L2), median of %d groups of %d replays" % (per_graph, len(inputs), groups, reps)}
 
 
 def timed_value(pipe, inputs, labels, steps, warmup, barrier):

@@ -262,6 +262,23 @@ int b200r_stem_pool_u8_f16(const uint8_t* img, const uint16_t* wgt, const float*
                            uint16_t* y, int n, int h, int w, const float* mean_host,
                            const float* std_host, b200r_stream_t stream);
 
+/* Split-precision (fp32-faithful) twin of the one-launch stem: same schedule, an EXACT one-plane A operand (pixel / 256 as
+ * fp16, fourth channel = 1 on real pixels, 0 in the padding) against the weights as an fp16 hi/lo pair -- two MMAs per product
+ * instead of three -- fp32 pooling, and the hi/lo split of the pooled value on the way out.
+ * b200r_stem_pool_split_prepare (HOST function, double arithmetic) folds x/255, 1/std, the BN scale, -mean/std, the BN bias
+ * and a range-centring power of two into the operand:
+ *   conv1_w      : host float32 [64, 3, 7, 7] (resnet_official.py:221)
+ *   bn_scale/bias: host float32 [64], gamma / sqrt(var + eps) and beta - mean * scale (nullable = 1 / 0)
+ *   planes_host  : host uint16 [2][64][224] out (hi plane, lo plane; row = [ky][t = kx + 1][R, G, B, 1]); upload as is
+ *   out_scale    : 2^-k, to hand to b200r_stem_pool_u8_split
+ * b200r_stem_pool_u8_split: img uint8 NHWC [n, h, w, 3]; wplanes = the uploaded planes; y = split planes [2][n, h/4, w/4, 64].
+ * Same geometry limits as the fp16 twin. */
+int b200r_stem_pool_split_prepare(const float* conv1_w, const float* bn_scale, const float* bn_bias,
+                                  const float* mean_host, const float* std_host, uint16_t* planes_host,
+                                  float* out_scale);
+int b200r_stem_pool_u8_split(const uint8_t* img, const uint16_t* wplanes, float out_scale, uint16_t* y,
+                             int n, int h, int w, b200r_stream_t stream);
+
 /* same, from a float32 NCHW image in [0,1] (the attack loops' iterate): (x - mean) / std and the hi/lo split happen
  * in the operand producer, with the arithmetic of b200r_stem_im2col_f32 */
 int b200r_stem_conv7x7_f32(const float* img, const uint16_t* wgt, const float* scale, const float* bias,

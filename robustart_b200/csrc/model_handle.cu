@@ -62,6 +62,8 @@ struct b200r_model {
   bool f16 = false;
   std::vector<Block> blocks;
   Planes stem_w, stem_w_folded, stem_wt, fc_w, fc_wt;
+  uint16_t* stem_wp = nullptr;   // split mode: prepared operand of the one-launch stem [2][64][224]
+  float stem_osc = 1.f;
   float *stem_scale = nullptr, *stem_bias = nullptr, *fc_b = nullptr;
   std::vector<void*> owned;          // every cudaMalloc of the weights
   Arena arena;
@@ -284,6 +286,14 @@ int b200r_model_create(int arch, const b200r_weight* weights, int n_weights, int
   if ((rc = upload_planes(m, packed, &m->stem_w)) || (rc = upload_f32(m, sc, &m->stem_scale)) || (rc = upload_f32(m, b1, &m->stem_bias)))
     return fail(rc);
   if (m->f16 && (rc = upload_planes(m, pack_stem(folded), &m->stem_w_folded))) return fail(rc);
+  if (!m->f16) {
+    std::vector<uint16_t> wp((size_t)2 * 64 * 224);
+    void* d = nullptr;
+    if ((rc = b200r_stem_pool_split_prepare(w1, sc.data(), b1.data(), kMean, kStd, wp.data(), &m->stem_osc)) || (rc = dev_alloc(m, &d, wp.size() * 2)))
+      return fail(rc);
+    if (cudaMemcpy(d, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { b200r_set_error("cudaMemcpy of the stem operand failed"); return fail(B200R_ECUDA); }
+    m->stem_wp = static_cast<uint16_t*>(d);
+  }
   {  // gradient of the stem GEMM: [192][64] = (planes' value of the packed weight * bn scale)^T
     std::vector<float> t((size_t)192 * 64);
     for (int o = 0; o < 64; ++o)
@@ -358,10 +368,11 @@ int b200r_model_forward_u8(b200r_model* m, const uint8_t* images, float* logits,
   m->saved.valid = false;
   cudaStream_t s = as_stream(stream);
   uint16_t* x;
-  if (m->f16 && h % 4 == 0 && w % 8 == 0 && w >= 8 && w <= 248 && h >= 8) {
+  if (h % 4 == 0 && w % 8 == 0 && w >= 8 && w <= 248 && h >= 8) {
     // raw pixels -> conv1 + bn1 + relu + maxpool in one launch
     TAKE(p, (size_t)n * (h / 4) * (w / 4) * 64);
-    RC(b200r_stem_pool_u8_f16(images, m->stem_w_folded.p, m->stem_bias, p, n, h, w, kMean, kStd, stream));
+    RC(m->f16 ? b200r_stem_pool_u8_f16(images, m->stem_w_folded.p, m->stem_bias, p, n, h, w, kMean, kStd, stream)
+              : b200r_stem_pool_u8_split(images, m->stem_wp, m->stem_osc, p, n, h, w, stream));
     x = p;
   } else {
     TAKE(s0, (size_t)n * (h / 2) * (w / 2) * 64);

@@ -34,15 +34,24 @@
 //   warps 0-7   epilogue: two groups of four (TMEM lane quadrant = warp % 4), group g takes channels [32g, 32g+32)
 //   warp  8     TMEM allocation + MMA issue
 //   warps 9-16  producers: raw uint8 row -> normalised fp16 row buffer
+//
+// Split-precision twin (SPLIT = true, the fp32-faithful mode the evaluation defaults to): the same schedule with
+//   * an EXACT single-plane A operand: the staged pixel is (R, G, B) / 256 as fp16 (8 significant bits, no rounding) and a
+//     fourth channel that is 1 on real pixels and 0 in the padding; x/255, 1/std, the BN scale and a power of two 2^k that
+//     centres the fp16 range are folded into the weights on the host in double (b200r_stem_pool_split_prepare), -mean/std and
+//     the BN bias ride on the fourth channel of every tap (padding taps then contribute exactly nothing, as zero padding
+//     of the NORMALISED image demands);
+//   * the weights as an fp16 hi/lo pair (22 bits): TWO MMAs per product instead of the three a two-plane A operand needs;
+//   * fp32 pooling: four epilogue groups of 16 channels (25 warps), fp32 vertical / horizontal 3-max, ReLU, 2^-k, and only
+//     then the hi/lo split of the pooled value into the two output planes [2][n, h/4, w/4, 64].
+#include <cmath>
+#include <vector>
+
 #include "sm100_ptx.cuh"
 
 namespace {
 
-constexpr int SP_EPI_WARPS = 8;              // two groups of four: group g owns channels [32g, 32g+32) of every output row
-constexpr int SP_MMA_WARP = 8;
-constexpr int SP_PROD_WARP0 = 9;
 constexpr int SP_PROD_WARPS = 8;
-constexpr int SP_THREADS = (SP_PROD_WARP0 + SP_PROD_WARPS) * 32;   // 544
 constexpr int SP_SLOTS = 16;                 // staged input rows in flight
 constexpr int SP_SLOT_BYTES = 2176;          // >= 16 * (127 + 4) = 2096 (the 128-row operand reads past the 112 real columns)
 constexpr int SP_ACC = 8;                    // TMEM accumulators (64 columns each)
@@ -52,16 +61,30 @@ constexpr int SP_STAGE_PITCH = 96;           // bytes per column in a group's st
 constexpr int SP_STAGE_BYTES = 128 * SP_STAGE_PITCH;
 constexpr int SP_OFF_B = 0;                                  // even tile [2 halves][2 chunks][256 rows][16 B] = 16 KB,
 constexpr int SP_B_ODD = 16384;                              // then the odd tile [2][2][192][16 B] = 12 KB
-constexpr int SP_OFF_ROWS = SP_OFF_B + 14 * 2048;
-constexpr int SP_OFF_STAGE = SP_OFF_ROWS + SP_SLOTS * SP_SLOT_BYTES;   // [2 groups][2 buffers][128 columns][96 B]
-constexpr int SP_OFF_BARS = SP_OFF_STAGE + 4 * SP_STAGE_BYTES;
-constexpr int SP_SMEM = SP_OFF_BARS + (2 * SP_SLOTS + 2 * SP_ACC) * 8 + 16 + 128;
+constexpr int SP_B_PLANE = 14 * 2048;                        // SPLIT: the lo-plane tiles follow the hi-plane tiles
+constexpr int SP_WROW = 7 * 8 * 4;                           // SPLIT: prepared weights per output channel, [ky][t = kx + 1][R, G, B, 1]
+
+// warp roles and shared-memory map of the two precisions
+template <bool SPLIT>
+struct SpCfg {
+  static constexpr int EPI_WARPS = SPLIT ? 16 : 8;           // groups of four (TMEM lane quadrant = warp % 4); group g owns
+  static constexpr int GROUPS = EPI_WARPS / 4;               // channels [CG g, CG g + CG) of every output row
+  static constexpr int CG = 64 / GROUPS;
+  static constexpr int MMA_WARP = EPI_WARPS;
+  static constexpr int PROD_WARP0 = EPI_WARPS + 1;
+  static constexpr int THREADS = (PROD_WARP0 + SP_PROD_WARPS) * 32;   // 544 / 800
+  static constexpr int OFF_ROWS = SP_OFF_B + (SPLIT ? 2 : 1) * SP_B_PLANE;
+  static constexpr int OFF_STAGE = OFF_ROWS + SP_SLOTS * SP_SLOT_BYTES;   // [groups][2 buffers][128 columns][96 B]
+  static constexpr int OFF_BARS = OFF_STAGE + GROUPS * 2 * SP_STAGE_BYTES;
+  static constexpr int SMEM = OFF_BARS + (2 * SP_SLOTS + 2 * SP_ACC) * 8 + 16 + 128;
+};
 
 struct StemPoolParams {
   const uint8_t* img;      // [n, h, w, 3]
-  const __half* wgt;       // [64, 192], column = ky*24 + kx*3 + c, BN scale folded in
-  const float* bias;       // [64] (nullable)
-  __half* y;               // [n, h/4, w/4, 64]
+  const __half* wgt;       // [64, 192], column = ky*24 + kx*3 + c, BN scale folded in; SPLIT: prepared planes [2][64][224]
+  const float* bias;       // [64] (nullable; SPLIT: unused, the bias is in the prepared weights)
+  __half* y;               // [n, h/4, w/4, 64]; SPLIT: hi plane, the lo plane follows at y + n*(h/4)*(w/4)*64
+  float out_scale;         // SPLIT: 2^-k
   int n, h, w;
   int units_per_img, n_units;
   float k1[3], k0[3];      // normalised = fma(byte, k1, k0)
@@ -126,14 +149,17 @@ struct MmaBases { uint32_t a_lo0, be_lo0, bo_lo0, tmem; };
 // block BMAX - k of the parity's stacked tile.  Rows [kmin, kmax] are present (interior rows: all of [0, BMAX]; the edges
 // of a unit or of the image clip the range).  Called with literal bounds the whole body folds to 4-5 UTCHMMA with
 // immediate descriptor offsets.
-template <int I>
+template <int I, bool SPLIT>
 __device__ __forceinline__ void sp_issue(const MmaBases& mb, int kmin, int kmax, bool all_fresh) {
   constexpr int PAR = I & 1, S0 = (I >> 1) % SP_ACC, BMAX = 3 - PAR;
   constexpr int SEG0_HI = S0 < BMAX ? S0 : BMAX;       // slots fall with k and wrap below 0: [0, SEG0_HI] and [S0 + 1, BMAX] are contiguous
   auto one = [&](int h, int ka, int kb, uint32_t accumulate) {     // one MMA over the rows [ka, kb], K step h
     const uint32_t d = mb.tmem + (uint32_t)((S0 - kb) & (SP_ACC - 1)) * 64u;
     const uint32_t b = (PAR ? mb.bo_lo0 : mb.be_lo0) + (uint32_t)h * (PAR ? (6144u >> 4) : (8192u >> 4)) + (uint32_t)(BMAX - kb) * 64u;
-    umma_bf16(d, sp_desc(mb.a_lo0 + I * (SP_SLOT_BYTES >> 4) + 2 * h), sp_desc(b), SP_IDESC0 | (((uint32_t)(kb - ka + 1) * 8u) << 17), accumulate);
+    const uint64_t a = sp_desc(mb.a_lo0 + I * (SP_SLOT_BYTES >> 4) + 2 * h);
+    const uint32_t idesc = SP_IDESC0 | (((uint32_t)(kb - ka + 1) * 8u) << 17);
+    umma_bf16(d, a, sp_desc(b), idesc, accumulate);
+    if constexpr (SPLIT) umma_bf16(d, a, sp_desc(b + (SP_B_PLANE >> 4)), idesc, 1u);      // the weights' lo plane
   };
   auto run = [&](int h, int lo, int hi) {
     const int b0 = hi < SEG0_HI ? hi : SEG0_HI;
@@ -153,7 +179,11 @@ __device__ __forceinline__ void sp_issue(const MmaBases& mb, int kmin, int kmax,
   run(1, kmin, kmax);
 }
 
-__global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPoolParams p) {
+template <bool SPLIT>
+__global__ void __launch_bounds__(SpCfg<SPLIT>::THREADS, 1) stem_pool_kernel(const StemPoolParams p) {
+  using C = SpCfg<SPLIT>;
+  constexpr int SP_EPI_WARPS = C::EPI_WARPS, SP_MMA_WARP = C::MMA_WARP, SP_PROD_WARP0 = C::PROD_WARP0, SP_THREADS = C::THREADS;
+  constexpr int SP_OFF_ROWS = C::OFF_ROWS, SP_OFF_STAGE = C::OFF_STAGE, SP_OFF_BARS = C::OFF_BARS;
   extern __shared__ __align__(128) uint8_t sp_smem_raw[];    // nothing here needs more than 16-byte alignment (no swizzle)
   uint8_t* smem = sp_smem_raw;
   const uint32_t sbase = smem_u32(smem);
@@ -181,26 +211,31 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
     // weights in operand layout.  Tile `par` stacks the kernel rows ky = (6 - par) - 2*jb as 64-row blocks jb; K step h covers
     // window positions t = 4h .. 4h+3 (t = kx + 1), 4 channels each; chunk j = positions 4h+2j, 4h+2j+1.
     __half* sB = reinterpret_cast<__half*>(smem + SP_OFF_B);
-    for (int idx = threadIdx.x; idx < 14 * 1024; idx += SP_THREADS) {
+    for (int idx0 = threadIdx.x; idx0 < (SPLIT ? 2 : 1) * 14 * 1024; idx0 += SP_THREADS) {
+      const int plane = idx0 >= 14 * 1024, idx = idx0 - plane * 14 * 1024;
       const int par = idx >= 8192, li = idx - par * 8192, rows = par ? 192 : 256;
       const int e = li & 7, r = (li >> 3) % rows, jh = (li >> 3) / rows;       // jh = h * 2 + j
       const int j = jh & 1, h = jh >> 1, jb = r >> 6, co = r & 63;
       const int ky = (6 - par) - 2 * jb, t = 4 * h + 2 * j + (e >> 2), c4 = e & 3;
       __half val = __float2half_rn(0.f);
-      if (c4 < 3) { if (t >= 1) val = p.wgt[co * 192 + ky * 24 + (t - 1) * 3 + c4]; }
-      else if (ky == 3 && p.bias) {
+      if constexpr (SPLIT) {
+        val = p.wgt[(plane * 64 + co) * SP_WROW + ky * 32 + t * 4 + c4];
+      } else if (c4 < 3) {
+        if (t >= 1) val = p.wgt[co * 192 + ky * 24 + (t - 1) * 3 + c4];
+      } else if (ky == 3 && p.bias) {
         const float bf = p.bias[co];
         const __half bh = __float2half_rn(bf);
         if (t == 4) val = bh;
         else if (t == 3) val = __float2half_rn(bf - __half2float(bh));
       }
-      sB[idx] = val;
+      sB[idx0] = val;
     }
-    // row ring: zero, with the constant-one fourth channel on every pixel column (padding included)
+    // row ring: zero, with the constant-one fourth channel on every pixel column (padding included; SPLIT: the padding
+    // stays all-zero, the producers write the one with every real pixel)
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem + SP_OFF_ROWS);
     for (int idx = threadIdx.x; idx < SP_SLOTS * SP_SLOT_BYTES / 4; idx += SP_THREADS) {
       const int w4 = idx % (SP_SLOT_BYTES / 4);
-      rows[idx] = ((w4 & 1) && w4 < 2 * (W + 8)) ? 0x3C000000u : 0u;
+      rows[idx] = (!SPLIT && (w4 & 1) && w4 < 2 * (W + 8)) ? 0x3C000000u : 0u;
     }
   }
   fence_proxy_async();
@@ -232,10 +267,25 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
           const uint32_t sh = (lane & 1) * 16;
           const uint32_t lo = __funnelshift_r(v[2 * j], v[2 * j + 1], sh), hi = v[2 * j + 1] >> sh;   // r0 g0 b0 r1 | g1 b1
           uint4 o;
-          o.x = cvt_f16x2(nrm(lo, 0x7651, k1g, k0g), nrm(lo, 0x7650, k1r, k0r));
-          o.y = cvt_f16x2(1.0f, nrm(lo, 0x7652, k1b, k0b));
-          o.z = cvt_f16x2(nrm(hi, 0x7650, k1g, k0g), nrm(lo, 0x7653, k1r, k0r));
-          o.w = cvt_f16x2(1.0f, nrm(hi, 0x7651, k1b, k0b));
+          if constexpr (SPLIT) {
+            // byte b under the exponent byte 0x64 is the fp16 number 1024 + b; (1024 + b) / 256 - 4 = b / 256 exactly.
+            // The fourth channel: 0x6500 = 1280 -> 1280 / 256 - 4 = 1.
+            const uint32_t p1 = __byte_perm(lo, hi, 0x0543);                         // r1 g1 b1 x
+            const uint32_t kmul = 0x1C001C00u /* 2^-8 */, kadd = 0xC400C400u /* -4 */, kexp = 0x65000064u;
+            auto cv = [&](uint32_t w) {
+              const __half2 r = __hfma2(*reinterpret_cast<const __half2*>(&w), *reinterpret_cast<const __half2*>(&kmul), *reinterpret_cast<const __half2*>(&kadd));
+              return *reinterpret_cast<const uint32_t*>(&r);
+            };
+            o.x = cv(__byte_perm(lo, kexp, 0x4140));
+            o.y = cv(__byte_perm(lo, kexp, 0x7542));
+            o.z = cv(__byte_perm(p1, kexp, 0x4140));
+            o.w = cv(__byte_perm(p1, kexp, 0x7542));
+          } else {
+            o.x = cvt_f16x2(nrm(lo, 0x7651, k1g, k0g), nrm(lo, 0x7650, k1r, k0r));
+            o.y = cvt_f16x2(1.0f, nrm(lo, 0x7652, k1b, k0b));
+            o.z = cvt_f16x2(nrm(hi, 0x7650, k1g, k0g), nrm(lo, 0x7653, k1r, k0r));
+            o.w = cvt_f16x2(1.0f, nrm(hi, 0x7651, k1b, k0b));
+          }
           sts_v4(dst + q * 16, o);
         }
       }
@@ -288,14 +338,14 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
         tc_fence_after();
         if (elect_one()) {
           switch (slot) {
-            case 0: sp_issue<0>(mb, kmin, kmax, all_fresh); break;   case 1: sp_issue<1>(mb, kmin, kmax, all_fresh); break;
-            case 2: sp_issue<2>(mb, kmin, kmax, all_fresh); break;   case 3: sp_issue<3>(mb, kmin, kmax, all_fresh); break;
-            case 4: sp_issue<4>(mb, kmin, kmax, all_fresh); break;   case 5: sp_issue<5>(mb, kmin, kmax, all_fresh); break;
-            case 6: sp_issue<6>(mb, kmin, kmax, all_fresh); break;   case 7: sp_issue<7>(mb, kmin, kmax, all_fresh); break;
-            case 8: sp_issue<8>(mb, kmin, kmax, all_fresh); break;   case 9: sp_issue<9>(mb, kmin, kmax, all_fresh); break;
-            case 10: sp_issue<10>(mb, kmin, kmax, all_fresh); break; case 11: sp_issue<11>(mb, kmin, kmax, all_fresh); break;
-            case 12: sp_issue<12>(mb, kmin, kmax, all_fresh); break; case 13: sp_issue<13>(mb, kmin, kmax, all_fresh); break;
-            case 14: sp_issue<14>(mb, kmin, kmax, all_fresh); break; default: sp_issue<15>(mb, kmin, kmax, all_fresh); break;
+            case 0: sp_issue<0, SPLIT>(mb, kmin, kmax, all_fresh); break;   case 1: sp_issue<1, SPLIT>(mb, kmin, kmax, all_fresh); break;
+            case 2: sp_issue<2, SPLIT>(mb, kmin, kmax, all_fresh); break;   case 3: sp_issue<3, SPLIT>(mb, kmin, kmax, all_fresh); break;
+            case 4: sp_issue<4, SPLIT>(mb, kmin, kmax, all_fresh); break;   case 5: sp_issue<5, SPLIT>(mb, kmin, kmax, all_fresh); break;
+            case 6: sp_issue<6, SPLIT>(mb, kmin, kmax, all_fresh); break;   case 7: sp_issue<7, SPLIT>(mb, kmin, kmax, all_fresh); break;
+            case 8: sp_issue<8, SPLIT>(mb, kmin, kmax, all_fresh); break;   case 9: sp_issue<9, SPLIT>(mb, kmin, kmax, all_fresh); break;
+            case 10: sp_issue<10, SPLIT>(mb, kmin, kmax, all_fresh); break; case 11: sp_issue<11, SPLIT>(mb, kmin, kmax, all_fresh); break;
+            case 12: sp_issue<12, SPLIT>(mb, kmin, kmax, all_fresh); break; case 13: sp_issue<13, SPLIT>(mb, kmin, kmax, all_fresh); break;
+            case 14: sp_issue<14, SPLIT>(mb, kmin, kmax, all_fresh); break; default: sp_issue<15, SPLIT>(mb, kmin, kmax, all_fresh); break;
           }
           umma_commit(empty_in(slot));
           // output rows whose last contributing input row this is: ky = 6, or the bottom image row (two taps in the padding)
@@ -318,7 +368,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
           take_row(I);                                                                       \
           tc_fence_after();                                                                  \
           if (elect_one()) {                                                                 \
-            sp_issue<I>(mb, 0, 3 - ((I) & 1), false);                                        \
+            sp_issue<I, SPLIT>(mb, 0, 3 - ((I) & 1), false);                                        \
             umma_commit(empty_in(I));                                                        \
             if (((I) & 1) == 0) umma_commit(acc_full((((I) >> 1) + SP_ACC - 3) % SP_ACC));   \
           }                                                                                  \
@@ -334,7 +384,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
               if (pp > pp_b) { more = false; break; }
               take_row(15);
               tc_fence_after();
-              if (elect_one()) { sp_issue<15>(mb, 0, 2, false); umma_commit(empty_in(15)); }
+              if (elect_one()) { sp_issue<15, SPLIT>(mb, 0, 2, false); umma_commit(empty_in(15)); }
               __syncwarp();
               ++pp;
             }
@@ -343,6 +393,72 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
 #undef SP_STEP
       }
       for (; pp <= t.p_hi; ++pp) edge(pp);
+    }
+  } else if constexpr (SPLIT) {
+    // ================================ epilogue, fp32 pooling, hi/lo planes out ================================
+    // group g = warp / 4 owns channels [16g, 16g + 16); thread = output column (TMEM lane = 32 * (warp % 4) + lane)
+    const int grp = warp >> 2, m = threadIdx.x & 127;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * 16;
+    const uint32_t stage0 = sbase + SP_OFF_STAGE + grp * 2 * SP_STAGE_BYTES;
+    const size_t plane_stride = (size_t)p.n * PH * PW * 64;
+    const float osc = p.out_scale;
+    uint32_t ph_afull = 0, emit = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit t = make_unit(p, u);
+      float prev_odd[16], v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { prev_odd[i] = 0.f; v[i] = 0.f; }
+      for (int r = t.r_first; r <= t.r_last; ++r) {
+        const uint32_t aslot = (uint32_t)r % SP_ACC;
+        mbar_wait(acc_full(aslot), (ph_afull >> aslot) & 1);
+        ph_afull ^= 1u << aslot;
+        tc_fence_after();
+        uint32_t acc[16];
+        tmem_ld16(lane_base + aslot * 64, acc);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(aslot));
+        const bool odd = r & 1;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float cur = __uint_as_float(acc[i]);
+          if (odd) { v[i] = fmaxf(v[i], cur); prev_odd[i] = cur; }
+          else v[i] = fmaxf(prev_odd[i], cur);
+        }
+        if (odd && (r >> 1) >= t.py0) {
+          // vertical 3-max of pooled row r/2 is in v (0 stands in for the padding row: the ReLU follows)
+          const uint32_t st = stage0 + (emit & 1) * SP_STAGE_BYTES;
+          if (m < WO) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              sts_v4(st + m * SP_STAGE_PITCH + ch * 16, make_uint4(__float_as_uint(v[4 * ch]), __float_as_uint(v[4 * ch + 1]),
+                                                                 __float_as_uint(v[4 * ch + 2]), __float_as_uint(v[4 * ch + 3])));
+          }
+          named_bar_sync(1 + grp, 128);
+          __half* yrow = p.y + ((size_t)(t.n * PH + (r >> 1)) * PW) * 64 + grp * 16;
+          for (int i = m; i < PW * 4; i += 128) {
+            const int px = i >> 2, ch = i & 3, c1 = 2 * px;
+            const uint32_t at = st + c1 * SP_STAGE_PITCH + ch * 16;
+            const uint4 a = lds_v4(at), b = lds_v4(at + SP_STAGE_PITCH);
+            float f0 = fmaxf(__uint_as_float(a.x), __uint_as_float(b.x)), f1 = fmaxf(__uint_as_float(a.y), __uint_as_float(b.y));
+            float f2 = fmaxf(__uint_as_float(a.z), __uint_as_float(b.z)), f3 = fmaxf(__uint_as_float(a.w), __uint_as_float(b.w));
+            if (px > 0) {
+              const uint4 l = lds_v4(at - SP_STAGE_PITCH);
+              f0 = fmaxf(f0, __uint_as_float(l.x)); f1 = fmaxf(f1, __uint_as_float(l.y));
+              f2 = fmaxf(f2, __uint_as_float(l.z)); f3 = fmaxf(f3, __uint_as_float(l.w));
+            }
+            f0 = fmaxf(f0, 0.f) * osc; f1 = fmaxf(f1, 0.f) * osc; f2 = fmaxf(f2, 0.f) * osc; f3 = fmaxf(f3, 0.f) * osc;
+            uint2 oh, ol;
+            split_f16x2(f1, f0, oh.x, ol.x);
+            split_f16x2(f3, f2, oh.y, ol.y);
+            __half* dst = yrow + px * 64 + ch * 4;
+            *reinterpret_cast<uint2*>(dst) = oh;
+            *reinterpret_cast<uint2*>(dst + plane_stride) = ol;
+          }
+          ++emit;
+        }
+      }
     }
   } else {
     // ================================ epilogue ================================
@@ -413,9 +529,88 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const StemPool
   }
 }
 
+template <bool SPLIT>
+int launch_stem_pool(StemPoolParams& p, const float* mean_host, const float* std_host, b200r_stream_t stream) {
+  p.units_per_img = ((p.h >> 2) + SP_UNIT_POOLED - 1) / SP_UNIT_POOLED;
+  p.n_units = p.n * p.units_per_img;
+  for (int c = 0; c < 3; ++c) {
+    p.k1[c] = (float)(1.0 / (255.0 * (double)std_host[c]));
+    p.k0[c] = (float)(-(double)mean_host[c] / (double)std_host[c]);
+  }
+  static bool attr_set[16] = {};
+  int dev = 0;
+  B200R_CUDA(cudaGetDevice(&dev));
+  if (dev < 16 && !attr_set[dev]) {
+    B200R_CUDA(cudaFuncSetAttribute(stem_pool_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SpCfg<SPLIT>::SMEM));
+    attr_set[dev] = true;
+  }
+  const int grid = p.n_units < b200r_num_sms() ? p.n_units : b200r_num_sms();
+  stem_pool_kernel<SPLIT><<<grid, SpCfg<SPLIT>::THREADS, SpCfg<SPLIT>::SMEM, as_stream(stream)>>>(p);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int b200r_stem_pool_split_prepare(const float* conv1_w, const float* bn_scale, const float* bn_bias, const float* mean_host,
+                                  const float* std_host, uint16_t* planes_host, float* out_scale) {
+  B200R_CHECK_ARG(conv1_w && mean_host && std_host && planes_host && out_scale, "null pointer");
+  // value of tap (co, ky, t = kx + 1, c): colour channels meet pixel / 256, the fourth channel meets 1 on real pixels
+  std::vector<double> v((size_t)64 * SP_WROW, 0.0);
+  double amax = 0.0;
+  for (int co = 0; co < 64; ++co) {
+    const double s = bn_scale ? (double)bn_scale[co] : 1.0;
+    for (int ky = 0; ky < 7; ++ky)
+      for (int kx = 0; kx < 7; ++kx) {
+        double* q = &v[(size_t)co * SP_WROW + ky * 32 + (kx + 1) * 4];
+        double m = 0.0;
+        for (int c = 0; c < 3; ++c) {
+          const double w = (double)conv1_w[((co * 3 + c) * 7 + ky) * 7 + kx] * s / (double)std_host[c];
+          q[c] = w * (256.0 / 255.0);
+          m -= w * (double)mean_host[c];
+        }
+        if (ky == 3 && kx == 3 && bn_bias) m += (double)bn_bias[co];
+        q[3] = m;
+        for (int c = 0; c < 4; ++c) amax = fmax(amax, fabs(q[c]));
+      }
+  }
+  B200R_CHECK_ARG(std::isfinite(amax), "non-finite stem weights");
+  // 2^k puts the largest entry in [2^13, 2^14): the lo plane of every entry down to 2^-13 of it stays a normal fp16 number
+  int k = 0;
+  if (amax > 0.0) {
+    int e = 0;
+    frexp(amax, &e);                  // amax = f * 2^e, f in [0.5, 1)
+    k = 14 - e;
+    if (k > 60) k = 60;
+    if (k < -60) k = -60;
+  }
+  const double up = ldexp(1.0, k);
+  for (size_t i = 0; i < v.size(); ++i) {
+    const double x = v[i] * up;
+    const __half hi = __float2half_rn((float)x);
+    const __half lo = __float2half_rn((float)(x - (double)__half2float(hi)));
+    planes_host[i] = *reinterpret_cast<const uint16_t*>(&hi);
+    planes_host[v.size() + i] = *reinterpret_cast<const uint16_t*>(&lo);
+  }
+  *out_scale = (float)ldexp(1.0, -k);
+  return B200R_OK;
+}
+
+int b200r_stem_pool_u8_split(const uint8_t* img, const uint16_t* wplanes, float out_scale, uint16_t* y, int n, int h, int w,
+                             b200r_stream_t stream) {
+  B200R_CHECK_ARG(img && wplanes && y, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h >= 8 && w >= 8, "bad shape %d x %d x %d", n, h, w);
+  B200R_CHECK_ARG(h % 4 == 0 && w % 8 == 0 && w <= 248, "stem_pool needs h %% 4 == 0, w %% 8 == 0, w <= 248 (got %d x %d)", h, w);
+  B200R_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "img must be 8-byte, y 16-byte aligned");
+  B200R_CHECK_ARG(out_scale > 0.f, "out_scale comes from b200r_stem_pool_split_prepare");
+  StemPoolParams p;
+  p.img = img; p.wgt = reinterpret_cast<const __half*>(wplanes); p.bias = nullptr; p.y = reinterpret_cast<__half*>(y);
+  p.n = n; p.h = h; p.w = w; p.out_scale = out_scale;
+  const float unit[3] = {1.f, 1.f, 1.f}, zero[3] = {0.f, 0.f, 0.f};
+  return launch_stem_pool<true>(p, zero, unit, stream);
+}
 
 int b200r_stem_pool_u8_f16(const uint8_t* img, const uint16_t* wgt, const float* bias, uint16_t* y,
                            int n, int h, int w, const float* mean_host, const float* std_host, b200r_stream_t stream) {
@@ -425,24 +620,8 @@ int b200r_stem_pool_u8_f16(const uint8_t* img, const uint16_t* wgt, const float*
   B200R_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "img must be 8-byte, y 16-byte aligned");
   StemPoolParams p;
   p.img = img; p.wgt = reinterpret_cast<const __half*>(wgt); p.bias = bias; p.y = reinterpret_cast<__half*>(y);
-  p.n = n; p.h = h; p.w = w;
-  p.units_per_img = ((h >> 2) + SP_UNIT_POOLED - 1) / SP_UNIT_POOLED;
-  p.n_units = n * p.units_per_img;
-  for (int c = 0; c < 3; ++c) {
-    p.k1[c] = (float)(1.0 / (255.0 * (double)std_host[c]));
-    p.k0[c] = (float)(-(double)mean_host[c] / (double)std_host[c]);
-  }
-  static bool attr_set[16] = {};
-  int dev = 0;
-  B200R_CUDA(cudaGetDevice(&dev));
-  if (dev < 16 && !attr_set[dev]) {
-    B200R_CUDA(cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-    attr_set[dev] = true;
-  }
-  const int grid = p.n_units < b200r_num_sms() ? p.n_units : b200r_num_sms();
-  stem_pool_kernel<<<grid, SP_THREADS, SP_SMEM, as_stream(stream)>>>(p);
-  B200R_LAUNCH_CHECK();
-  return B200R_OK;
+  p.n = n; p.h = h; p.w = w; p.out_scale = 1.f;
+  return launch_stem_pool<false>(p, mean_host, std_host, stream);
 }
 
 }  // extern "C"

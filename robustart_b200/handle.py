@@ -40,7 +40,7 @@ class ModelHandle:
         kind, layers = nets._RESNET_CFG[arch]
         per_block = 3 if kind == "bottleneck" else 2
         # stem (+ maxpool unless fused), blocks, downsample convs (one per stage; ResNet-18/34's first stage has none), avgpool, fc
-        self._launches = (1 if self.f16 else 2) + per_block * sum(layers) + (4 if kind == "bottleneck" else 3) + 2
+        self._launches = 1 + per_block * sum(layers) + (4 if kind == "bottleneck" else 3) + 2
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

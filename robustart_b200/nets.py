@@ -174,6 +174,8 @@ class ResNet:
         self.stem_scale, self.stem_bias = s.float().to(dev), (b - m * s).float().to(dev)
         # one-launch stem (fp16 mode): BN scale folded into the weights before the single rounding to fp16
         self.stem_w_folded = ops.to_planes(ops.pack_stem_weight((sd["conv1.weight"].double() * s.view(-1, 1, 1, 1)).float()).to(dev).contiguous(), True) if f16 else None
+        # one-launch stem (split mode): exact pixels against hi/lo weights with everything folded in on the host
+        self.stem_wp, self.stem_osc = (None, 1.0) if f16 else ops.stem_pool_split_prepare(sd["conv1.weight"], self.stem_scale, self.stem_bias, dev)
         self.blocks = []
         for li, blocks in enumerate(layers):
             for bi in range(blocks):
@@ -203,9 +205,9 @@ class ResNet:
         n = images.shape[0]
         h, w = (images.shape[1], images.shape[2]) if images.dtype == torch.uint8 else (images.shape[2], images.shape[3])
         P = self.passes
-        if images.dtype == torch.uint8 and self.f16 and self.fused_stem_pool and ops.stem_pool_ok(h, w):
+        if images.dtype == torch.uint8 and self.fused_stem_pool and ops.stem_pool_ok(h, w):
             # raw pixels -> conv1 + bn1 + relu + maxpool in one launch (overlapping-descriptor implicit im2col)
-            x = ops.stem_pool_u8(images, self.stem_w_folded, self.stem_bias)
+            x = ops.stem_pool_u8(images, self.stem_w_folded, self.stem_bias) if self.f16 else ops.stem_pool_u8_split(images, self.stem_wp, self.stem_osc)
         else:
             if images.dtype == torch.uint8:
                 # raw pixels: gather + ToTensor + Normalize + split fused into the stem GEMM's operand producer
@@ -345,8 +347,8 @@ class ResNet:
         return run
 
     def launches_per_forward(self) -> int:
-        # stem + maxpool (one launch in fp16 mode with the fused stem), avgpool, fc
-        n = (1 if (self.f16 and self.fused_stem_pool) else 2) + 1 + 1
+        # stem + maxpool (one launch with the fused stem), avgpool, fc
+        n = (1 if self.fused_stem_pool else 2) + 1 + 1
         for blk in self.blocks:
             n += (3 if blk["kind"] == "bottleneck" else 2) + (1 if "down" in blk else 0)
         return n

@@ -426,6 +426,35 @@ def stem_pool_u8(img, wgt_folded, bias, *, mean=IMAGENET_MEAN, std=IMAGENET_STD,
     return out
 
 
+def stem_pool_split_prepare(conv1_w, bn_scale, bn_bias, device, *, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """Operand of the split-precision one-launch stem from the float32 conv1 weight [64, 3, 7, 7] and the folded BN scale / bias
+    [64] (host arithmetic in double, include/b200r.h): (device planes [2, 64, 224] int16, out_scale)."""
+    import ctypes as C
+    w = conv1_w.detach().float().cpu().contiguous()
+    assert tuple(w.shape) == (64, 3, 7, 7), "the ResNet stem is 3 -> 64, 7x7"
+    s = None if bn_scale is None else bn_scale.detach().float().cpu().contiguous()
+    b = None if bn_bias is None else bn_bias.detach().float().cpu().contiguous()
+    planes = torch.empty((2, 64, 224), dtype=torch.int16)
+    osc = C.c_float(0.0)
+    _lib.check(_lib.load().b200r_stem_pool_split_prepare(w.data_ptr(), _ptr(s), _ptr(b), _lib.f3(mean), _lib.f3(std), planes.data_ptr(), C.byref(osc)))
+    return planes.to(device), float(osc.value)
+
+
+def stem_pool_u8_split(img, wplanes, out_scale, *, out=None):
+    """conv1 7x7/s2 + BN + ReLU + MaxPool(3,2,1) from raw uint8 NHWC pixels in one launch, split precision: planes
+    [2, n, h/4, w/4, 64].  wplanes / out_scale from stem_pool_split_prepare."""
+    _need_cuda(img, torch.uint8, "img")
+    _need_cuda(wplanes, torch.int16, "wplanes")
+    n, h, w, _ = img.shape
+    assert tuple(wplanes.shape) == (2, 64, 224), "stem_pool_u8_split takes the prepared [2, 64, 224] operand"
+    assert stem_pool_ok(h, w), "stem_pool_u8_split: unsupported geometry %dx%d" % (h, w)
+    if out is None:
+        out = torch.empty((2, n, h // 4, w // 4, 64), dtype=torch.int16, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.load().b200r_stem_pool_u8_split(img.data_ptr(), wplanes.data_ptr(), out_scale, out.data_ptr(), n, h, w, _stream()))
+    return out
+
+
 def stem_conv7x7_f32(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
     """Fused 7x7/s2 stem from a float32 NCHW image in [0,1] (attack iterates): planes [P, n, h/2, w/2, 64]."""
     _need_cuda(img, torch.float32, "img")

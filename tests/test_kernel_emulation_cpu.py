@@ -257,13 +257,14 @@ def test_layernorm_bwd_kernel(emu, rows, c, eps):
     assert lib.b200r_layernorm_bwd(_p(dyp), _p(xp), _p(gamma), None, _p(out), rows, 4, C.c_float(eps), None) != 0   # c % 8
 
 
-@pytest.mark.parametrize("act,code", [("gelu_tanh", 3), ("gelu_erf", 4), ("tanh", 6)])
+@pytest.mark.parametrize("act,code", [("gelu_tanh", 3), ("gelu_erf", 4), ("tanh", 6), ("relu", 1), ("relu6", 2), ("swish", 5), ("sigmoid", 7)])
 def test_activation_kernels(emu, act, code):
     lib = emu["token_backward"]
     torch.manual_seed(code)
     pre, dy = torch.randn(7, 520) * 2.5, torch.randn(7, 520)
     p = rt(pre).double().requires_grad_(True)
-    fn = {"gelu_tanh": lambda v: F.gelu(v, approximate="tanh"), "gelu_erf": F.gelu, "tanh": torch.tanh}[act]
+    fn = {"gelu_tanh": lambda v: F.gelu(v, approximate="tanh"), "gelu_erf": F.gelu, "tanh": torch.tanh, "relu": torch.relu,
+          "relu6": F.relu6, "swish": F.silu, "sigmoid": torch.sigmoid}[act]
     y = fn(p)
     (want,) = torch.autograd.grad(y, p, grad_outputs=rt(dy).double())
     out = torch.empty(2, 7, 520, dtype=torch.int16)
@@ -272,7 +273,8 @@ def test_activation_kernels(emu, act, code):
     assert (merge(out).double() - y.detach()).abs().max().item() < 5e-5
     _ok(lib.b200r_act_bwd_planes(_p(dyp), _p(prep), _p(out), C.c_size_t(pre.numel()), code, None))
     assert (merge(out).double() - want).abs().max().item() < 5e-5
-    assert lib.b200r_act_planes(_p(prep), _p(out), C.c_size_t(pre.numel()), 1, None) != 0            # relu: not this kernel's job
+    assert lib.b200r_act_planes(_p(prep), _p(out), C.c_size_t(pre.numel()), 0, None) != 0            # identity / unknown codes are refused
+    assert lib.b200r_act_planes(_p(prep), _p(out), C.c_size_t(pre.numel()), 8, None) != 0
 
 
 @pytest.mark.parametrize("n,h,w,p", [(2, 32, 32, 8), (1, 32, 48, 16)])

@@ -81,7 +81,12 @@ def main(src, dst):
         e = {"kernel": name, "corruption": KERNEL_TO_CORRUPTION.get(name, "?")}
         for k, m in M.items():
             e[k] = round(val(d, m), 3)
-        e["dram_bytes"] = round((e.pop("rd") + e.pop("wr")) * 1e6)
+        rdwr = (e.pop("rd") + e.pop("wr")) * 1e6
+        if rdwr == 0 and d.get("dram__bytes.sum.per_second", "") != "":
+            # section captures hold the rate, not the byte counters: bytes = rate x duration
+            per_s = float(d["dram__bytes.sum.per_second"].replace(",", "")) * {"Gbyte/s": 1e9, "Tbyte/s": 1e12, "Mbyte/s": 1e6, "Kbyte/s": 1e3, "byte/s": 1.0}.get(unit.get("dram__bytes.sum.per_second", ""), 1.0)
+            rdwr = per_s * e["us"] * 1e-6
+        e["dram_bytes"] = round(rdwr) if rdwr > 0 else None
         st = []
         for s in STALLS:
             key = "smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % s

@@ -100,7 +100,14 @@ __device__ __forceinline__ float fast_erf(float x) {
 // fetch (stall_no_inst).  LEAN also double-buffers the staging tile so a store unit costs one named barrier and never waits
 // for its own TMA store (ring one stage shorter to pay for the second 32 KB).
 // ACTS (LEAN only): 0 = the instantiation knows none / ReLU only (the convolution stacks), 1 = all activations.
-template <int BN, int STEM_MODE, bool F16, bool LEAN = false, int ACTS = 1>
+// PAIR (LEAN, split planes, BN = 128): launched as clusters of two CTAs on the two SMs of a TPC; the pair runs ONE M = 256
+// MMA (tcgen05.mma.cta_group::2) over two vertically adjacent M tiles of the same N tile.  Each CTA loads its own A tile and
+// only HALF of the weight tile (the tensor core reads the other half from the peer's shared memory), so the operand bytes a
+// CTA pulls from L2 per k-block drop from 64 KB to 48 KB -- tools/gemm_probe.py shows these GEMMs bound by exactly that
+// (12.5 TB/s of operand delivery = the L2 throughput cap, not the tensor pipe).  The leader (cluster rank 0) issues the MMAs;
+// both CTAs' TMA loads count on the leader's `full` barrier; MMA completion is multicast to both CTAs' `empty` / `tmem_full`
+// barriers; both epilogues arrive on the leader's `tmem_empty`.
+template <int BN, int STEM_MODE, bool F16, bool LEAN = false, int ACTS = 1, bool PAIR = false>
 __global__ void __launch_bounds__(STEM_MODE ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_i,
@@ -108,9 +115,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   constexpr bool STEM = STEM_MODE != 0;
   constexpr bool STEM_F32 = STEM_MODE == 2;
   static_assert(!LEAN || !STEM, "LEAN is a non-stem epilogue");
+  static_assert(!PAIR || (LEAN && !F16 && BN <= 128), "PAIR: LEAN split-plane kernel with BN = 64 / 128");
   // LEAN + fp16 double-buffers the 32 KB staging area and gives up ring stages for it
-  constexpr int kStages = (LEAN && F16) ? (BN > 128 ? 3 : (BN == 128 ? 5 : 6)) : ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
-  constexpr int B_TILE_BYTES = BN * BK * 2;
+  constexpr int kStages = PAIR ? 4 : (LEAN && F16) ? (BN > 128 ? 3 : (BN == 128 ? 5 : 6)) : ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
+  constexpr int BN_LOAD = PAIR ? BN / 2 : BN;           // weight rows this CTA holds
+  constexpr int B_TILE_BYTES = BN_LOAD * BK * 2;
   constexpr int B_OFF = F16 ? A_TILE_BYTES : 2 * A_TILE_BYTES;           // F16: [A | B]; split: [A_hi | A_lo | B_hi | B_lo]
   constexpr int STAGE_BYTES = B_OFF + (F16 ? 1 : 2) * B_TILE_BYTES;
   // tcgen05's fp32 accumulation truncates (profiles/r2_accumulation_bias.txt: -0.77 * 2^-23 relative per 16-wide MMA step, a pure bias
@@ -122,8 +131,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;  // two accumulator buffers (power of two: 128 .. 512)
   // instruction descriptor: fp32 accumulator (bit 4), A/B format (bits 7, 10: 1 = bf16, 0 = fp16), N >> 3, M >> 4
   // (both precisions now feed fp16 operands: split planes are fp16 pairs)
-  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-  constexpr uint32_t IDESC_RES = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // residual k-blocks: N = 64
+  constexpr uint32_t UMMA_M = PAIR ? 2 * BM : BM;
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
+  constexpr uint32_t IDESC_RES = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);   // residual k-blocks: N = 64
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -150,12 +160,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // STEM: the A tile is written by 128 producer threads (one arrival each) next to the TMA thread's
     // arrive.expect_tx for the weight tile
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), STEM ? 1 + kStemProducerWarps * 32 : 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), STEM ? kStemEpiWarps : 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), STEM ? kStemEpiWarps : (PAIR ? 16 : 8)); }
     fence_barrier_init();
   }
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = the pair's leader
+  if (PAIR) cluster_sync_all();                          // the peer's barriers exist before anything signals them
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -163,12 +175,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_img;
-  const int total_tiles = m_tiles * p.tiles_n;
-  // tile schedule: round-robin over CTAs; the STEM variant takes a contiguous range instead, so that consecutive
+  // PAIR: the schedule runs over pairs of M tiles (2 mp, 2 mp + 1); an odd tail tile's partner is out of range (zero-filled
+  // loads, clipped stores)
+  const int total_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * p.tiles_n;
+  // tile schedule: round-robin over CTAs (PAIR: over clusters); the STEM variant takes a contiguous range instead, so that consecutive
   // tiles of a CTA are consecutive output rows of one image and the staged input rows slide by two
-  const int t_first = STEM ? (int)((long long)blockIdx.x * total_tiles / gridDim.x) : (int)blockIdx.x;
+  const int t_first = STEM ? (int)((long long)blockIdx.x * total_tiles / gridDim.x) : (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
   const int t_end = STEM ? (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x) : total_tiles;
-  const int t_step = STEM ? 1 : (int)gridDim.x;
+  const int t_step = STEM ? 1 : (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x);
+  auto m_tile_of = [&](int t) { return PAIR ? 2 * (t / p.tiles_n) + (int)rank : t / p.tiles_n; };
   const int kb_conv = p.KH * p.KW * p.cin_blocks;
   const int kb_res = p.res_mma ? BN / 64 : 0;           // residual k-blocks: acc[:, 64j:64j+64] += R[:, 64j:64j+64] * I64^T
   const int kblocks = kb_conv + kb_res;
@@ -184,7 +199,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     int stage = 0;
     uint32_t phase = 0;
     for (int t = t_first; t < t_end; t += t_step) {
-      const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+      const int nt = t % p.tiles_n, mt = m_tile_of(t);
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
       const int w_in0 = tw * p.bw * p.stride - p.pad, h_in0 = th * p.bh * p.stride - p.pad, n0 = ti * p.bn;
       for (int kh = 0; kh < p.KH; ++kh)
@@ -193,13 +208,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             mbar_wait(empty_bar(stage), phase ^ 1);
             if (elect_one()) {
               const uint32_t sa = smem_base + stage * STAGE_BYTES;
-              mbar_expect_tx(full_bar(stage), tx_bytes);
               const int kcol = (kh * p.KW + kw) * p.cin + cb * BK;
+              if constexpr (PAIR) {
+                const uint32_t lbar = mapa_u32(full_bar(stage), 0);      // the leader's barrier counts both CTAs' bytes
+                if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * tx_bytes);
+                tma_load_5d_pair(sa, &map_a, lbar, cb * BK, w_in0 + kw, h_in0 + kh, n0, 0);
+                tma_load_3d_pair(sa + B_OFF, &map_b, lbar, kcol, nt * BN + (int)rank * BN_LOAD, 0);
+                if (p.passes == 3) {
+                  tma_load_5d_pair(sa + A_TILE_BYTES, &map_a, lbar, cb * BK, w_in0 + kw, h_in0 + kh, n0, 1);
+                  tma_load_3d_pair(sa + B_OFF + B_TILE_BYTES, &map_b, lbar, kcol, nt * BN + (int)rank * BN_LOAD, 1);
+                }
+              } else {
+              mbar_expect_tx(full_bar(stage), tx_bytes);
               if (!STEM) tma_load_5d(sa, &map_a, full_bar(stage), cb * BK, w_in0 + kw, h_in0 + kh, n0, 0);
               tma_load_3d(sa + B_OFF, &map_b, full_bar(stage), kcol, nt * BN, 0);
               if (!F16 && p.passes == 3) {
                 if (!STEM) tma_load_5d(sa + A_TILE_BYTES, &map_a, full_bar(stage), cb * BK, w_in0 + kw, h_in0 + kh, n0, 1);
                 tma_load_3d(sa + B_OFF + B_TILE_BYTES, &map_b, full_bar(stage), kcol, nt * BN, 1);
+              }
               }
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -210,20 +236,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           // residual channels [64j, 64j+64) only touch accumulator columns [64j, 64j+64): the B operand is the 64 x 64
           // identity (8 KB) and the MMA has N = 64, whatever BN is
+          if constexpr (PAIR) {
+            // each CTA holds 32 of the identity's 64 rows (map_i's box is 32 rows for a pair launch)
+            const uint32_t lbar = mapa_u32(full_bar(stage), 0);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (2u * a_bytes + (uint32_t)(32 * BK * 2)));
+            tma_load_5d_pair(sa, &map_r, lbar, nt * BN + j * BK, tw * p.bw, th * p.bh, n0, 0);
+            tma_load_5d_pair(sa + A_TILE_BYTES, &map_r, lbar, nt * BN + j * BK, tw * p.bw, th * p.bh, n0, 1);
+            tma_load_2d_pair(sa + B_OFF, &map_i, lbar, 0, (int)rank * 32);
+          } else {
           mbar_expect_tx(full_bar(stage), (F16 ? 1u : 2u) * a_bytes + (uint32_t)(64 * BK * 2));
           tma_load_5d(sa, &map_r, full_bar(stage), nt * BN + j * BK, tw * p.bw, th * p.bh, n0, 0);
           if (!F16) tma_load_5d(sa + A_TILE_BYTES, &map_r, full_bar(stage), nt * BN + j * BK, tw * p.bw, th * p.bh, n0, 1);
           tma_load_2d(sa + B_OFF, &map_i, full_bar(stage), 0, 0);
+          }
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues; PAIR: the leader CTA only) =====================
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+      if constexpr (PAIR) umma_f16_pair(d, a, b, idesc, accumulate); else umma_bf16(d, a, b, idesc, accumulate);
+    };
+    auto commit = [&](uint32_t bar) { if constexpr (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = t_first; t < t_end; t += t_step, ++it) {
+    for (int t = (PAIR && rank != 0) ? t_end : t_first; t < t_end; t += t_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -243,19 +282,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle row
-              umma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, ((kb - first_kb) | k) != 0);
-              umma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1);
-              umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1);
+              mma(d_tmem, a_lo + adv, b_hi + adv, IDESC, ((kb - first_kb) | k) != 0);
+              mma(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1);
+              mma(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1);
             }
           } else {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-              umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, ((kb - first_kb) | k) != 0);
+              mma(d_tmem, a_hi + adv, b_hi + adv, IDESC, ((kb - first_kb) | k) != 0);
             }
           }
-          umma_commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
-          if (kb == kblocks - 1) umma_commit(tfull_bar(acc));  // accumulator complete
+          commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
+          if (kb == kblocks - 1) commit(tfull_bar(acc));  // accumulator complete
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -269,11 +308,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-            umma_bf16(d_base + (uint32_t)(j * 64), a_hi + adv, b_hi + adv, IDESC_RES, 1);
-            if (!F16) umma_bf16(d_base + (uint32_t)(j * 64), a_lo + adv, b_hi + adv, IDESC_RES, 1);
+            mma(d_base + (uint32_t)(j * 64), a_hi + adv, b_hi + adv, IDESC_RES, 1);
+            if (!F16) mma(d_base + (uint32_t)(j * 64), a_lo + adv, b_hi + adv, IDESC_RES, 1);
           }
-          umma_commit(empty_bar(stage));
-          if (j == kb_res - 1) umma_commit(tfull_bar(acc));
+          commit(empty_bar(stage));
+          if (j == kb_res - 1) commit(tfull_bar(acc));
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -302,7 +341,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       for (int t = t_first; t < t_end; t += t_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+        const int nt = t % p.tiles_n, mt = m_tile_of(t);
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
         const int n_img = ti * p.bn + nl, ho = th * p.bh + hl, wo = tw * p.bw + wl;
         const bool row_ok = (r < p.rows_box) && (n_img < p.N) && (ho < p.Ho) && (wo < p.Wo);
@@ -329,7 +368,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (rd == kChunks / kPer - 1) {                     // accumulator is in registers: hand the TMEM buffer back early
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc)); }
           }
 #pragma unroll
           for (int ci = 0; ci < kPer; ++ci) {
@@ -497,7 +536,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     for (int t = t_first; t < t_end; t += t_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+      const int nt = t % p.tiles_n, mt = m_tile_of(t);
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
       const int n_img = ti * p.bn + nl, ho = th * p.bh + hl, wo = tw * p.bw + wl;
       const bool row_ok = (r < p.rows_box) && (n_img < p.N) && (ho < p.Ho) && (wo < p.Wo);
@@ -855,9 +894,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();       // the peer may still be reading this CTA's operands / signalling its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -883,21 +923,38 @@ EncodeTiledFn get_encode() {
 
 struct GemmMaps { CUtensorMap a, b, r, i, y; };
 
-template <int BN, int STEM, bool F16, bool LEAN = false, int ACTS = 1>
+template <int BN, int STEM, bool F16, bool LEAN = false, int ACTS = 1, bool PAIR = false>
 int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t s) {
-  constexpr int kStages = (LEAN && F16) ? (BN > 128 ? 3 : (BN == 128 ? 5 : 6)) : ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
-  constexpr int STAGE_BYTES = (2 * A_TILE_BYTES + 2 * BN * BK * 2) / (F16 ? 2 : 1);
+  constexpr int kStages = PAIR ? 4 : (LEAN && F16) ? (BN > 128 ? 3 : (BN == 128 ? 5 : 6)) : ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
+  constexpr int STAGE_BYTES = (2 * A_TILE_BYTES + 2 * (PAIR ? BN / 2 : BN) * BK * 2) / (F16 ? 2 : 1);
   // STEM adds the staged input rows (7 x (W_in*3 + 24) words) and the 3 KB LUT behind the barriers
   const int smem = kStages * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ +
                    ((LEAN && F16) ? 65536 : ((STEM || p.tma_store) ? 32768 : 0)) /*epilogue staging*/ + (STEM ? 7 * (p.W_in * 3 + 24) * 4 + 768 * 4 : 0);
   static int configured = 0;
   if (configured < smem) {
-    B200R_CUDA((cudaFuncSetAttribute(gemm_kernel<BN, STEM, F16, LEAN, ACTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+    B200R_CUDA((cudaFuncSetAttribute(gemm_kernel<BN, STEM, F16, LEAN, ACTS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
     configured = smem;
+  }
+  if constexpr (PAIR) {
+    // one cluster of two CTAs per pair of M tiles; grid = an even number of CTAs, at most one per SM
+    const int pairs = ((p.tiles_w * p.tiles_h * p.tiles_img + 1) / 2) * p.tiles_n;
+    const int max_clusters = b200r_num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (pairs < max_clusters ? pairs : max_clusters));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200R_CUDA((cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STEM, F16, LEAN, ACTS, PAIR>, m.a, m.b, m.r, m.i, m.y, p)));
+    return B200R_OK;
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_img * p.tiles_n;
   const int grid = total < b200r_num_sms() ? total : b200r_num_sms();
-  gemm_kernel<BN, STEM, F16, LEAN, ACTS><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(m.a, m.b, m.r, m.i, m.y, p);
+  gemm_kernel<BN, STEM, F16, LEAN, ACTS, PAIR><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(m.a, m.b, m.r, m.i, m.y, p);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
@@ -940,14 +997,14 @@ int get_identity(const uint16_t** out, bool f16) {
 
 // output / residual / identity maps + flags shared by conv_impl and the fused stem
 // tuning switch for experiments: B200R_GEMM_OPTS bit 0 = epilogue stores through the LSU instead of TMA,
-// bit 1 = residual through the LSU instead of identity k-blocks, bit 2 = general epilogue instead of the LEAN one
-int gemm_opts() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("B200R_GEMM_OPTS"); v = e ? atoi(e) : 0; }
-  return v;
+// bit 1 = residual through the LSU instead of identity k-blocks, bit 2 = general epilogue instead of the LEAN one,
+// bit 3 = one accumulator chain, bit 4 = no CTA pairs, bit 5 = CTA pairs wherever the kernel supports them
+int gemm_opts() {        // read at every launch (an A/B test flips it inside one process); launches are graph-captured where it matters
+  const char* e = getenv("B200R_GEMM_OPTS");
+  return e ? atoi(e) : 0;
 }
 
-int finish_maps(EncodeTiledFn enc, GemmMaps* m, GemmParams* p, const uint16_t* res, uint16_t* y, size_t ycount, int BN, bool f16) {
+int finish_maps(EncodeTiledFn enc, GemmMaps* m, GemmParams* p, const uint16_t* res, uint16_t* y, size_t ycount, int BN, bool f16, bool pair = false) {
   p->tma_store = 0;
   p->res_mma = 0;
   m->r = m->b; m->i = m->b; m->y = m->b;   // placeholders (never dereferenced unless the flag is set)
@@ -966,7 +1023,7 @@ int finish_maps(EncodeTiledFn enc, GemmMaps* m, GemmParams* p, const uint16_t* r
     if (rc) return rc;
     cuuint64_t dims[2] = {256, 256};
     cuuint64_t strides[1] = {512};
-    cuuint32_t box[2] = {(cuuint32_t)BK, 64};     // the 64 x 64 identity block (the kernel slides the accumulator columns instead)
+    cuuint32_t box[2] = {(cuuint32_t)BK, pair ? 32u : 64u};     // the 64 x 64 identity block (the kernel slides the accumulator columns instead); a CTA pair holds 32 rows each
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&m->i, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(ident), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1029,6 +1086,16 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
     const long m_tiles = (long)p.tiles_w * p.tiles_h * p.tiles_img;
     if (Cout % 256 == 0 && m_tiles * (Cout / 256) >= 2L * b200r_num_sms()) BN = 256;
   }
+  // CTA pairs (cta_group::2) for the LEAN split-plane BN = 128 kernel: half the weight bytes per CTA (B200R_GEMM_OPTS bit 4 = off)
+  const bool will_tma_store = y && Cout % 8 == 0 && !(gemm_opts() & 1);
+  const bool will_res_mma = res && !scale && Cout % 8 == 0 && !(gemm_opts() & 2);
+  const bool will_lean = will_tma_store && !y_f32 && (!res || will_res_mma) && !(gemm_opts() & 4);
+  // ... where operand delivery, not HBM, is the bound: time at the HBM roofline over time at the tensor roofline, per output pixel,
+  // = [4 B (Cin + Cout (1 + res)) / 6.5 TB/s] / [3 x 2 K Cout / 1353 TF/s]; measured layer by layer (ResNet-50, batch 256): pairs win
+  // below ~1.3 and lose 5-10 % on the HBM-bound 56 x 56 1x1 layers above it (lock-step of the two CTAs, no operand to save)
+  const double hbm_over_tensor = 138.8 * ((double)Cin + (double)Cout * (res ? 2.0 : 1.0)) / ((double)KH * KW * Cin * (double)Cout);
+  const bool pair = will_lean && !f16 && BN <= 128 && (long)p.tiles_w * p.tiles_h * p.tiles_img >= 2 && b200r_num_sms() >= 2 &&
+                    !(gemm_opts() & 16) && (hbm_over_tensor < 1.3 || (gemm_opts() & 32));
   p.tiles_n = (Cout + BN - 1) / BN;
   p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
   p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.cin_blocks = (Cin + 63) / 64; p.cin = Cin;
@@ -1046,7 +1113,7 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
     const cuuint64_t K = (cuuint64_t)KH * KW * Cin;
     cuuint64_t dims[3] = {K, (cuuint64_t)Cout, f16 ? 1u : 2u};
     cuuint64_t strides[2] = {K * 2, (cuuint64_t)wcount * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(pair ? BN / 2 : BN), 1};     // a CTA pair loads half the weight tile each
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&m.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<uint16_t*>(wgt), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1054,7 +1121,7 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
     if (r != CUDA_SUCCESS) { b200r_set_error("cuTensorMapEncodeTiled(B) failed: %d (Cout=%d K=%llu)", (int)r, Cout, (unsigned long long)K); return B200R_ECUDA; }
   }
   {
-    int rc = finish_maps(enc, &m, &p, res, y, ycount, BN, f16);
+    int rc = finish_maps(enc, &m, &p, res, y, ycount, BN, f16, pair);
     if (rc) return rc;
   }
   // the compact epilogue: planes out through TMA stores (Cout % 8 == 0), residual on the tensor core or none, no fp32 output
@@ -1074,6 +1141,11 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
     if (BN == 256) return launch<256, 0, true>(m, p, s);
     return BN == 64 ? launch<64, 0, true>(m, p, s) : launch<128, 0, true>(m, p, s);
   }
+  if (lean && pair) {
+    if (BN == 64) return simple_act ? launch<64, 0, false, true, 0, true>(m, p, s) : launch<64, 0, false, true, 1, true>(m, p, s);
+    return simple_act ? launch<128, 0, false, true, 0, true>(m, p, s) : launch<128, 0, false, true, 1, true>(m, p, s);
+  }
+  B200R_CHECK_ARG(!pair, "internal: pair launch planned for a non-LEAN configuration");
   if (lean) B200R_LAUNCH_LEAN(false);
 #undef B200R_LAUNCH_LEAN
   if (BN == 256) return launch<256, 0, false>(m, p, s);

@@ -161,3 +161,45 @@ def test_fused_stem_f32_matches_conv(cuda):
         cols = ops.stem_im2col(x)
         via = ops.merge_f32(ops.linear(cols, wp, s, b, act="relu")).view(shape[0], shape[2] // 2, shape[3] // 2, 64).permute(0, 3, 1, 2)
         assert (got - via).abs().max().item() < 1e-5
+
+
+PAIR_CONVS = [
+    # n, h, w, cin, cout, k, stride, pad, residual
+    (5, 14, 14, 256, 256, 3, 1, 1, False),     # 980 rows: 8 M tiles
+    (3, 14, 14, 256, 1024, 1, 1, 0, True),     # 588 rows: 5 M tiles -- the odd tail tile's partner is out of range
+    (1, 7, 7, 512, 2048, 1, 1, 0, True),       # one M tile only: no pair launch
+    (3, 28, 28, 128, 128, 3, 1, 1, False),
+    (2, 56, 56, 64, 64, 3, 1, 1, False),       # BN = 64 pairs (32 weight rows per CTA)
+    (2, 56, 56, 64, 64, 3, 1, 1, True),
+    (3, 28, 28, 256, 256, 3, 2, 1, False),
+    (2, 14, 14, 1024, 2048, 1, 2, 0, False),
+    (7, 8, 8, 192, 200, 1, 1, 0, True),        # ragged K (192 = 3 k-blocks) and ragged Cout (200: second N tile mostly out of range)
+]
+
+
+@pytest.mark.parametrize("cfg", PAIR_CONVS)
+@pytest.mark.parametrize("passes", [3, 1])
+def test_cta_pair_gemm_is_bit_identical(cuda, cfg, passes, monkeypatch):
+    """The CTA-pair kernel (tcgen05.mma.cta_group::2: one M = 256 MMA over two M tiles, half the weight tile per CTA) adds the same
+    products in the same order as the one-CTA kernel: outputs must be bit-identical, and right against fp64."""
+    from robustart_b200 import ops
+    n, h, w, cin, cout, k, stride, pad, with_res = cfg
+    torch.manual_seed(sum(cfg[:8]) + passes)
+    x = torch.randn(n, h, w, cin, device=cuda)
+    wt = torch.randn(cout, k, k, cin, device=cuda) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, device=cuda)
+    xp, wp = ops.split_f32(x), ops.split_f32(wt)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    res = torch.randn(n, ho, wo, cout, device=cuda) if with_res else None
+    rp = ops.split_f32(res) if with_res else None
+    outs = {}
+    for opts in ("32", "16"):                   # pairs wherever supported / never
+        monkeypatch.setenv("B200R_GEMM_OPTS", opts)
+        outs[opts] = ops.conv2d_nhwc(xp, wp, None, b, rp, stride=stride, pad=pad, act="relu", passes=passes).clone()
+        torch.cuda.synchronize()
+    assert torch.equal(outs["32"], outs["16"])
+    if passes == 3:
+        ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), wt.permute(0, 3, 1, 2).double(), b.double(), stride, pad).permute(0, 2, 3, 1)
+        if with_res:
+            ref = ref + res.double()
+        assert _rel_err(ops.merge_f32(outs["32"]), torch.relu(ref)) < 4e-5

@@ -51,6 +51,8 @@ def main():
                                 lambda img, *a, **k: img.numel() + BPE * img.shape[0] * 112 * 112 * 64)
     ops.stem_pool_u8 = timed(lambda img, *a, **k: "stem 7x7 s2 + maxpool, one launch", ops.stem_pool_u8, lambda img, *a, **k: 2.0 * img.shape[0] * 112 * 112 * 64 * 147,
                              lambda img, *a, **k: img.numel() + BPE * img.shape[0] * 56 * 56 * 64)
+    ops.stem_pool_u8_split = timed(lambda img, *a, **k: "stem 7x7 s2 + maxpool, one launch (split)", ops.stem_pool_u8_split, lambda img, *a, **k: 2.0 * img.shape[0] * 112 * 112 * 64 * 147,
+                                   lambda img, *a, **k: img.numel() + BPE * img.shape[0] * 56 * 56 * 64)
     ops.maxpool3x3s2 = timed(lambda x, *a, **k: "maxpool", o_mp, lambda x, *a, **k: 0.0, lambda x, *a, **k: BPE * x[0].numel() * 1.25)
     ops.global_avgpool = timed(lambda x, *a, **k: "avgpool", o_ap, lambda x, *a, **k: 0.0, lambda x, *a, **k: BPE * x[0].numel())
     for _ in range(3):

@@ -353,6 +353,16 @@ int b200r_global_avgpool_nhwc_f16(const uint16_t* x, uint16_t* y, int n, int hw,
 int b200r_conv2d_dgrad_nhwc(const uint16_t* dy, const uint16_t* wgt_t, const uint16_t* res,
                             const uint16_t* mask, uint16_t* dx, int n, int h, int w, int cdy, int cdx,
                             int kh, int kw, int pad, int passes, b200r_stream_t stream);
+/* Input gradient of a 3x3 / stride 2 / pad 1 convolution (resnet_official.py:112 conv2 of the first block of a stage) without the
+ * zero-dilated gradient: dx[2i+a, 2j+b] only meets the taps of the flipped kernel whose parity matches, so each of the four parity
+ * classes (a, b) is a (1+a) x (1+b)-tap stride-1 convolution of dy, written through a strided tensor map into its quarter of dx --
+ * a quarter of the tensor-core work of dilate + 3x3 and no dilated tensor in HBM.
+ *   dy   : planes [n, ho, wo, cdy]          dx, res, mask : planes [n, 2 ho, 2 wo, cdx] (res / mask nullable, as b200r_conv2d_dgrad_nhwc)
+ *   wab  : planes [cdx, 1+a, 1+b, cdy] = wgt_t[:, S_a, S_b, :] with S_0 = {1}, S_1 = {0, 2}, wgt_t the transposed + flipped weight
+ *          of b200r_conv2d_dgrad_nhwc */
+int b200r_conv2d_dgrad3x3s2_nhwc(const uint16_t* dy, const uint16_t* w00, const uint16_t* w01, const uint16_t* w10,
+                                 const uint16_t* w11, const uint16_t* res, const uint16_t* mask, uint16_t* dx, int n,
+                                 int ho, int wo, int cdy, int cdx, int passes, b200r_stream_t stream);
 /* ReLU backward: out = (act > 0 ? dy : 0) + add; add may be NULL (a second gradient branch joining here,
  * e.g. the identity path of a residual block).  count = elements per plane, multiple of 8. */
 int b200r_relu_bwd(const uint16_t* dy, const uint16_t* act, const uint16_t* add, uint16_t* out,
@@ -365,6 +375,11 @@ int b200r_dilate2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int 
  * the forward kernel and in PyTorch.  workspace: n*ho*wo*c bytes (arg-max codes), 8-byte aligned. */
 int b200r_maxpool3x3s2_bwd_nhwc(const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* workspace,
                                 size_t ws_bytes, int n, int h, int w, int c, b200r_stream_t stream);
+/* MaxPool2d(3,2,1) backward with the backward of the ReLU that produced x fused in (a window whose maximum is not positive routes
+ * nothing: relu'(0) = 0 as torch has it), ONE fp16 plane out whatever the precision: the ResNet stem's gradient GEMM reads a single
+ * plane (resnet_official.py:225-227).  x / dy: split planes (planes = 2) or one fp16 plane (planes = 1); dx_hi: [n, h, w, c] fp16. */
+int b200r_maxpool3x3s2_relu_bwd_hi(const uint16_t* x, const uint16_t* dy, uint16_t* dx_hi, void* workspace,
+                                   size_t ws_bytes, int n, int h, int w, int c, int planes, b200r_stream_t stream);
 /* AdaptiveAvgPool2d(1) backward: dy planes [n,c] -> dx planes [n,hw,c] = dy / hw */
 int b200r_global_avgpool_bwd_nhwc(const uint16_t* dy, uint16_t* dx, int n, int hw, int c,
                                   b200r_stream_t stream);

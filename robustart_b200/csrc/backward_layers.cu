@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(kThreads) dilate2_kernel(const uint4* __restri
 
 // ---- MaxPool2d(3, 2, 1) backward --------------------------------------------------------------------
 // pass 1: per output window, the position (ky*3+kx) of the first maximum, as the forward kernel picks it
-template <bool F16>
+// RELU: x is a post-ReLU activation and the ReLU's backward is fused in -- a window whose maximum is not positive routes nothing
+template <bool F16, bool RELU = false>
 __global__ void __launch_bounds__(kThreads) maxpool_argmax_kernel(const uint4* __restrict__ xh, const uint4* __restrict__ xl,
                                                                    uint2* __restrict__ idx, int n, int h, int w, int c8, int ho,
                                                                    int wo) {
@@ -193,11 +194,17 @@ __global__ void __launch_bounds__(kThreads) maxpool_argmax_kernel(const uint4* _
       for (int j = 0; j < 8; ++j)
         if (v[j] > best[j]) { best[j] = v[j]; bi[j] = (uint32_t)k; }
     }
+    if (RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!(best[j] > 0.f)) bi[j] = 0xFu;
+    }
     idx[t] = make_uint2(bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24), bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24));
   }
 }
 // pass 2: per input position, the sum of dy over the (at most four) windows whose maximum it is
-template <bool F16>
+// HI_ONLY: dx is ONE fp16 plane whatever the precision of dy (the stem's gradient GEMM reads a single plane)
+template <bool F16, bool HI_ONLY = false>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint2* __restrict__ idx, const uint4* __restrict__ dyh,
                                                                 const uint4* __restrict__ dyl, uint4* __restrict__ dxh,
                                                                 uint4* __restrict__ dxl, int n, int h, int w, int c8, int ho, int wo) {
@@ -238,10 +245,10 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint2* __re
       }
     }
     if (any) {
-      store8<F16>(dxh, dxl, t, acc);
+      store8<F16 || HI_ONLY>(dxh, dxl, t, acc);
     } else {
       dxh[t] = make_uint4(0, 0, 0, 0);
-      if (!F16) dxl[t] = make_uint4(0, 0, 0, 0);
+      if (!F16 && !HI_ONLY) dxl[t] = make_uint4(0, 0, 0, 0);
     }
   }
 }
@@ -342,7 +349,7 @@ static int dilate2_impl(const uint16_t* x, uint16_t* y, int n, int h, int w, int
 }
 
 static int maxpool_bwd_impl(const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* workspace, size_t ws_bytes, int n, int h, int w,
-                            int c, bool f16, cudaStream_t s) {
+                            int c, bool f16, cudaStream_t s, bool relu_hi = false) {
   B200R_CHECK_ARG(x && dy && dx && workspace, "null pointer");
   B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c % 8 == 0, "c must be a multiple of 8");
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
@@ -352,6 +359,19 @@ static int maxpool_bwd_impl(const uint16_t* x, const uint16_t* dy, uint16_t* dx,
   uint2* idx = reinterpret_cast<uint2*>(workspace);
   const uint4 *xh = reinterpret_cast<const uint4*>(x), *gh = reinterpret_cast<const uint4*>(dy);
   uint4* dh = reinterpret_cast<uint4*>(dx);
+  if (relu_hi) {          // ReLU backward fused into the routing, one fp16 plane out
+    if (f16) {
+      maxpool_argmax_kernel<true, true><<<grid_for(yout / 8), kThreads, 0, s>>>(xh, nullptr, idx, n, h, w, c / 8, ho, wo);
+      B200R_LAUNCH_CHECK();
+      maxpool_bwd_kernel<true, true><<<grid_for(xin / 8), kThreads, 0, s>>>(idx, gh, nullptr, dh, nullptr, n, h, w, c / 8, ho, wo);
+    } else {
+      maxpool_argmax_kernel<false, true><<<grid_for(yout / 8), kThreads, 0, s>>>(xh, reinterpret_cast<const uint4*>(x + xin), idx, n, h, w, c / 8, ho, wo);
+      B200R_LAUNCH_CHECK();
+      maxpool_bwd_kernel<false, true><<<grid_for(xin / 8), kThreads, 0, s>>>(idx, gh, reinterpret_cast<const uint4*>(dy + yout), dh, nullptr, n, h, w, c / 8, ho, wo);
+    }
+    B200R_LAUNCH_CHECK();
+    return B200R_OK;
+  }
   if (f16) {
     maxpool_argmax_kernel<true><<<grid_for(yout / 8), kThreads, 0, s>>>(xh, nullptr, idx, n, h, w, c / 8, ho, wo);
     B200R_LAUNCH_CHECK();
@@ -415,6 +435,11 @@ int b200r_dilate2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int 
 }
 int b200r_dilate2_nhwc_f16(const uint16_t* x, uint16_t* y, int n, int h, int w, int c, b200r_stream_t stream) {
   return dilate2_impl(x, y, n, h, w, c, true, as_stream(stream));
+}
+int b200r_maxpool3x3s2_relu_bwd_hi(const uint16_t* x, const uint16_t* dy, uint16_t* dx_hi, void* workspace, size_t ws_bytes, int n, int h,
+                                   int w, int c, int planes, b200r_stream_t stream) {
+  B200R_CHECK_ARG(planes == 1 || planes == 2, "planes must be 1 (fp16) or 2 (split)");
+  return maxpool_bwd_impl(x, dy, dx_hi, workspace, ws_bytes, n, h, w, c, planes == 1, as_stream(stream), true);
 }
 int b200r_maxpool3x3s2_bwd_nhwc(const uint16_t* x, const uint16_t* dy, uint16_t* dx, void* workspace, size_t ws_bytes, int n, int h, int w,
                                 int c, b200r_stream_t stream) {

@@ -57,6 +57,9 @@ struct GemmParams {
   int res_mma;    // residual added on the tensor core: extra k-blocks R[128 x 64] * I[BN x 64]^T (needs scale == NULL)
   int tma_store;  // planes output leaves through shared memory + cp.async.bulk.tensor stores
   int two_chains; // split planes, BN <= 128: even / odd k-blocks accumulate in two TMEM accumulators, summed in the epilogue
+  // where output pixel (n, ho, wo) lives, in pixels of the y / residual / mask tensors: n * o_img + ho * o_h + wo * o_w + o_off
+  // (dense: Ho*Wo, Wo, 1, 0; the stride-2 dgrad writes one parity class of a tensor twice as large in h and w)
+  long long o_img, o_h, o_w, o_off;
   // STEM variant only: the A operand is gathered from the raw uint8 NHWC image by producer warps
   const uint8_t* img;       // [N, H_in, W_in, 3] uint8 (STEM_MODE 1)  or  float32 [N, 3, H_in, W_in] (STEM_MODE 2)
   float nmean[3], nstd[3];  // STEM_MODE 2: Normalize constants (mode 1 has them baked into the LUT)
@@ -345,7 +348,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
         const int n_img = ti * p.bn + nl, ho = th * p.bh + hl, wo = tw * p.bw + wl;
         const bool row_ok = (r < p.rows_box) && (n_img < p.N) && (ho < p.Ho) && (wo < p.Wo);
-        const size_t out_row = ((size_t)n_img * p.Ho + ho) * p.Wo + wo;
+        const size_t out_row = (size_t)((long long)n_img * p.o_img + (long long)ho * p.o_h + (long long)wo * p.o_w + p.o_off);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * kColsPerWarp);
@@ -540,7 +543,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, ti = mt / (p.tiles_w * p.tiles_h);
       const int n_img = ti * p.bn + nl, ho = th * p.bh + hl, wo = tw * p.bw + wl;
       const bool row_ok = (r < p.rows_box) && (n_img < p.N) && (ho < p.Ho) && (wo < p.Wo);
-      const size_t out_row = ((size_t)n_img * p.Ho + ho) * p.Wo + wo;
+      const size_t out_row = (size_t)((long long)n_img * p.o_img + (long long)ho * p.o_h + (long long)wo * p.o_w + p.o_off);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       constexpr int kColsPerWarp = STEM ? BN : BN / 2;
@@ -960,10 +963,13 @@ int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t s) {
 }
 
 // 5-D map over split planes [plane][N][H][W][C] (dims listed innermost first)
+// (pw, ph, pn: pixel strides of w, h and n when the tensor is a strided view; 0 = dense)
 int make_map5(EncodeTiledFn enc, CUtensorMap* m, const uint16_t* base, int C, int W, int H, int N, size_t plane_elems, int box_c,
-              int box_w, int box_h, int box_n, int estride, CUtensorMapSwizzle swz, const char* what, bool f16) {
+              int box_w, int box_h, int box_n, int estride, CUtensorMapSwizzle swz, const char* what, bool f16, long long pw = 0,
+              long long ph = 0, long long pn = 0) {
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, f16 ? 1u : 2u};
-  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)plane_elems * 2};
+  cuuint64_t strides[4] = {(cuuint64_t)(pw ? pw : 1) * C * 2, (cuuint64_t)(ph ? ph : W) * C * 2, (cuuint64_t)(pn ? pn : (long long)H * W) * C * 2,
+                           (cuuint64_t)plane_elems * 2};
   cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), (cuuint32_t)box_n, 1};
   cuuint32_t estr[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<uint16_t*>(base), dims,
@@ -1005,18 +1011,22 @@ int gemm_opts() {        // read at every launch (an A/B test flips it inside on
 }
 
 int finish_maps(EncodeTiledFn enc, GemmMaps* m, GemmParams* p, const uint16_t* res, uint16_t* y, size_t ycount, int BN, bool f16, bool pair = false) {
+  // strided output view (GemmParams::o_*): the maps start at the view's first pixel and carry its strides
+  const bool dense = p->o_off == 0 && p->o_w == 1 && p->o_h == p->Wo && p->o_img == (long long)p->Ho * p->Wo;
+  const long long vw = dense ? 0 : p->o_w, vh = dense ? 0 : p->o_h, vn = dense ? 0 : p->o_img;
+  const size_t voff = (size_t)p->o_off * p->Cout;
   p->tma_store = 0;
   p->res_mma = 0;
   m->r = m->b; m->i = m->b; m->y = m->b;   // placeholders (never dereferenced unless the flag is set)
   if (y && p->Cout % 8 == 0 && !(gemm_opts() & 1)) {
     // split-bf16: 32-channel (64-byte) rows per plane; fp16: 64-channel (128-byte) rows, half as many and twice as wide stores
-    int rc = make_map5(enc, &m->y, y, p->Cout, p->Wo, p->Ho, p->N, ycount, f16 ? 64 : 32, p->bw, p->bh, p->bn, 1,
-                       f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "Y", f16);
+    int rc = make_map5(enc, &m->y, y + voff, p->Cout, p->Wo, p->Ho, p->N, ycount, f16 ? 64 : 32, p->bw, p->bh, p->bn, 1,
+                       f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "Y", f16, vw, vh, vn);
     if (rc) return rc;
     p->tma_store = 1;
   }
   if (res && !p->scale && p->Cout % 8 == 0 && !(gemm_opts() & 2)) {
-    int rc = make_map5(enc, &m->r, res, p->Cout, p->Wo, p->Ho, p->N, ycount, BK, p->bw, p->bh, p->bn, 1, CU_TENSOR_MAP_SWIZZLE_128B, "R", f16);
+    int rc = make_map5(enc, &m->r, res + voff, p->Cout, p->Wo, p->Ho, p->N, ycount, BK, p->bw, p->bh, p->bn, 1, CU_TENSOR_MAP_SWIZZLE_128B, "R", f16, vw, vh, vn);
     if (rc) return rc;
     const uint16_t* ident = nullptr;
     rc = get_identity(&ident, f16);
@@ -1055,9 +1065,13 @@ void choose_box(int N, int Ho, int Wo, int stride, int& bn, int& bh, int& bw) {
   }
 }
 
+// Output as a strided view of a larger tensor: logical size Ho x Wo per image (overrides the convolution formula: taps beyond the
+// input's edge read TMA zero fill), pixel (n, ho, wo) at n * img + ho * h + wo * w + off pixels, planes plane_elems apart.
+struct OutView { int Ho, Wo; long long img, h, w, off; size_t plane_elems; };
+
 int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias, const uint16_t* res,
               uint16_t* y, float* y_f32, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-              int act, int passes, bool flat2d, cudaStream_t s, const uint16_t* mask = nullptr) {
+              int act, int passes, bool flat2d, cudaStream_t s, const uint16_t* mask = nullptr, const OutView* ov = nullptr) {
   B200R_CHECK_ARG(x && wgt && (y || y_f32), "null pointer");
   // K tails (Cin % 64 != 0) ride on TMA out-of-bounds zero fill of the activation's channel dimension
   B200R_CHECK_ARG(Cin % 8 == 0, "cin (%d) must be a multiple of 8 (16-byte TMA strides)", Cin);
@@ -1067,9 +1081,10 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
   B200R_CHECK_ARG(stride >= 1 && stride <= 8 && KH >= 1 && KW >= 1 && pad >= 0, "bad conv geometry");
   EncodeTiledFn enc = get_encode();
   if (!enc) { b200r_set_error("cuTensorMapEncodeTiled not available from the driver"); return B200R_ECUDA; }
-  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const int Ho = ov ? ov->Ho : (H + 2 * pad - KH) / stride + 1, Wo = ov ? ov->Wo : (W + 2 * pad - KW) / stride + 1;
   B200R_CHECK_ARG(Ho > 0 && Wo > 0, "empty output");
-  const size_t xcount = (size_t)N * H * W * Cin, wcount = (size_t)Cout * KH * KW * Cin, ycount = (size_t)N * Ho * Wo * Cout;
+  B200R_CHECK_ARG(!ov || (!y_f32 && !flat2d), "strided output views are for plane outputs of spatial convolutions");
+  const size_t xcount = (size_t)N * H * W * Cin, wcount = (size_t)Cout * KH * KW * Cin, ycount = ov ? ov->plane_elems : (size_t)N * Ho * Wo * Cout;
 
   GemmParams p{};
   if (flat2d) { p.bn = 1; p.bh = 1; p.bw = 128; }
@@ -1098,6 +1113,7 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
                     !(gemm_opts() & 16) && (hbm_over_tensor < 1.3 || (gemm_opts() & 32));
   p.tiles_n = (Cout + BN - 1) / BN;
   p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+  p.o_img = ov ? ov->img : (long long)Ho * Wo; p.o_h = ov ? ov->h : Wo; p.o_w = ov ? ov->w : 1; p.o_off = ov ? ov->off : 0;
   p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.cin_blocks = (Cin + 63) / 64; p.cin = Cin;
   p.passes = passes; p.act = act; p.scale = scale; p.bias = bias;
   p.res_hi = res; p.res_lo = (res && !f16) ? res + ycount : nullptr;
@@ -1207,6 +1223,7 @@ static int stem_impl(const void* img, bool f32, const uint16_t* wgt, const float
   p.M_total = (long long)n * Ho * Wo;
   p.tiles_w = 1; p.tiles_h = Ho; p.tiles_img = n; p.tiles_n = 1;
   p.N = n; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+  p.o_img = (long long)Ho * Wo; p.o_h = Wo; p.o_w = 1; p.o_off = 0;
   p.KH = 1; p.KW = 1; p.stride = 1; p.pad = 0; p.cin_blocks = K / 64; p.cin = K;
   p.passes = passes; p.act = act; p.scale = scale; p.bias = bias;
   p.y_hi = y; p.y_lo = f16 ? nullptr : y + (size_t)p.M_total * Cout;
@@ -1260,6 +1277,27 @@ int b200r_conv2d_dgrad_nhwc(const uint16_t* dy, const uint16_t* wgt_t, const uin
   const bool flat = (kh == 1 && kw == 1 && pad == 0);
   if (flat) return conv_impl(dy, wgt_t, nullptr, nullptr, res, dx, nullptr, 1, 1, n * h * w, cdy, cdx, 1, 1, 1, 0, B200R_ACT_NONE, passes, true, as_stream(stream), mask);
   return conv_impl(dy, wgt_t, nullptr, nullptr, res, dx, nullptr, n, h, w, cdy, cdx, kh, kw, 1, pad, B200R_ACT_NONE, passes, false, as_stream(stream), mask);
+}
+
+int b200r_conv2d_dgrad3x3s2_nhwc(const uint16_t* dy, const uint16_t* w00, const uint16_t* w01, const uint16_t* w10, const uint16_t* w11,
+                                 const uint16_t* res, const uint16_t* mask, uint16_t* dx, int n, int ho, int wo, int cdy, int cdx,
+                                 int passes, b200r_stream_t stream) {
+  B200R_CHECK_ARG(dy && w00 && w01 && w10 && w11 && dx, "null pointer");
+  B200R_CHECK_ARG(n > 0 && ho > 0 && wo > 0 && cdy > 0 && cdx > 0, "bad shape");
+  // dx[2i + a, 2j + b] only meets the taps ky' = a + 1 (mod 2), kx' = b + 1 (mod 2) of the flipped kernel: parity class (a, b) is a
+  // (1 + a) x (1 + b)-tap stride-1 convolution of dy itself -- 9 tap-GEMMs on the small map instead of 9 on the zero-dilated one
+  const uint16_t* wsub[4] = {w00, w01, w10, w11};
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      OutView ov;
+      ov.Ho = ho; ov.Wo = wo;
+      ov.img = 4LL * ho * wo; ov.h = 4LL * wo; ov.w = 2; ov.off = (long long)a * 2 * wo + b;
+      ov.plane_elems = (size_t)n * 4 * ho * wo * cdx;
+      int rc = conv_impl(dy, wsub[a * 2 + b], nullptr, nullptr, res, dx, nullptr, n, ho, wo, cdy, cdx, 1 + a, 1 + b, 1, 0, B200R_ACT_NONE, passes,
+                         false, as_stream(stream), mask, &ov);
+      if (rc) return rc;
+    }
+  return B200R_OK;
 }
 
 int b200r_linear(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias, const uint16_t* res,

@@ -30,6 +30,7 @@ struct Planes {              // a tensor in the precision's plane format on the 
 
 struct ConvBN {
   Planes w, wt;              // forward weight [cout][kh][kw][cin]; dgrad weight [cin][kh][kw][cout] (transposed + flipped)
+  Planes wt_s2[4];           // 3x3 / stride 2: the dgrad weight's parity-class sub-kernels [cin][1+a][1+b][cout] (b200r_conv2d_dgrad3x3s2_nhwc)
   float* bias = nullptr;
   int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
 };
@@ -158,6 +159,20 @@ int make_conv(b200r_model* m, const Weights& W, const std::string& conv, const s
         }
   out->cin = cin; out->cout = cout; out->k = k; out->stride = stride; out->pad = pad;
   if ((rc = upload_planes(m, f, &out->w)) || (rc = upload_planes(m, t, &out->wt)) || (rc = upload_f32(m, bias, &out->bias))) return rc;
+  if (k == 3 && stride == 2 && pad == 1) {
+    const int taps[2][2] = {{1, 1}, {0, 2}};      // S_0 = {1}, S_1 = {0, 2}
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const int kh = 1 + a, kw = 1 + b;
+        std::vector<float> sub((size_t)cin * kh * kw * cout);
+        for (int i = 0; i < cin; ++i)
+          for (int y = 0; y < kh; ++y)
+            for (int x = 0; x < kw; ++x)
+              for (int o = 0; o < cout; ++o)
+                sub[(((size_t)i * kh + y) * kw + x) * cout + o] = t[(((size_t)i * 3 + taps[a][y]) * 3 + taps[b][x]) * cout + o];
+        if ((rc = upload_planes(m, sub, &out->wt_s2[a * 2 + b]))) return rc;
+      }
+  }
   return B200R_OK;
 }
 
@@ -446,40 +461,36 @@ int b200r_model_input_grad(b200r_model* m, const float* dlogits, float* dx, b200
     if (b.bottleneck) {
       TAKE(t3, (size_t)n * h * w * b.c3.cin);
       RC(b200r_conv2d_dgrad_nhwc(g, b.c3.wt.p, nullptr, sv[1], t3, n, h, w, b.c3.cout, b.c3.cin, 1, 1, 0, P, stream));
-      uint16_t* dy2 = t3;
-      if (stride == 2) {
-        TAKE(dd, (size_t)n * hi * wi * b.c2.cout);
-        RC(dilate2(t3, dd, n, h, w, b.c2.cout, stream));
-        dy2 = dd;
-      }
       TAKE(t2, (size_t)n * hi * wi * b.c2.cin);
-      RC(b200r_conv2d_dgrad_nhwc(dy2, b.c2.wt.p, nullptr, sv[0], t2, n, hi, wi, b.c2.cout, b.c2.cin, 3, 3, 1, P, stream));
+      if (stride == 2) {        // parity classes: four small convolutions of t3 itself, no zero-dilated tensor
+        RC(b200r_conv2d_dgrad3x3s2_nhwc(t3, b.c2.wt_s2[0].p, b.c2.wt_s2[1].p, b.c2.wt_s2[2].p, b.c2.wt_s2[3].p, nullptr, sv[0], t2, n, h, w,
+                                        b.c2.cout, b.c2.cin, P, stream));
+      } else {
+        RC(b200r_conv2d_dgrad_nhwc(t3, b.c2.wt.p, nullptr, sv[0], t2, n, hi, wi, b.c2.cout, b.c2.cin, 3, 3, 1, P, stream));
+      }
       TAKE(t1, (size_t)n * hi * wi * cin);
       RC(b200r_conv2d_dgrad_nhwc(t2, b.c1.wt.p, r, in_mask, t1, n, hi, wi, b.c1.cout, cin, 1, 1, 0, P, stream));
       t = t1;
     } else {
       TAKE(t2, (size_t)n * h * w * b.c2.cin);
       RC(b200r_conv2d_dgrad_nhwc(g, b.c2.wt.p, nullptr, sv[0], t2, n, h, w, b.c2.cout, b.c2.cin, 3, 3, 1, P, stream));
-      uint16_t* dy1 = t2;
-      if (stride == 2) {
-        TAKE(dd, (size_t)n * hi * wi * b.c1.cout);
-        RC(dilate2(t2, dd, n, h, w, b.c1.cout, stream));
-        dy1 = dd;
-      }
       TAKE(t1, (size_t)n * hi * wi * cin);
-      RC(b200r_conv2d_dgrad_nhwc(dy1, b.c1.wt.p, r, in_mask, t1, n, hi, wi, b.c1.cout, cin, 3, 3, 1, P, stream));
+      if (stride == 2) {
+        RC(b200r_conv2d_dgrad3x3s2_nhwc(t2, b.c1.wt_s2[0].p, b.c1.wt_s2[1].p, b.c1.wt_s2[2].p, b.c1.wt_s2[3].p, r, in_mask, t1, n, h, w,
+                                        b.c1.cout, cin, P, stream));
+      } else {
+        RC(b200r_conv2d_dgrad_nhwc(t2, b.c1.wt.p, r, in_mask, t1, n, hi, wi, b.c1.cout, cin, 3, 3, 1, P, stream));
+      }
       t = t1;
     }
     g = t; h = hi; w = wi; c = cin;
   }
   // maxpool backward into the 112^2 stem activation, its ReLU, the stem GEMM's gradient, col2im (+ 1/std, 1/S)
   const int h2 = H / 2, w2 = Wd / 2;
-  TAKE(gp, (size_t)n * h2 * w2 * 64);
+  uint16_t* gr = static_cast<uint16_t*>(m->arena.take((size_t)n * h2 * w2 * 64 * 2));               // ONE fp16 plane
   void* ws = m->arena.take((size_t)n * h * w * 64 + 8);
-  B200R_CHECK_ARG(ws, "activation arena too small");
-  RC((f16 ? b200r_maxpool3x3s2_bwd_nhwc_f16 : b200r_maxpool3x3s2_bwd_nhwc)(m->saved.stem, g, gp, ws, (size_t)n * h * w * 64, n, h2, w2, 64, stream));
-  TAKE(gr, (size_t)n * h2 * w2 * 64);
-  RC(relu_bwd(gp, m->saved.stem, nullptr, gr, (size_t)n * h2 * w2 * 64, stream));
+  B200R_CHECK_ARG(gr && ws, "activation arena too small");
+  RC(b200r_maxpool3x3s2_relu_bwd_hi(m->saved.stem, g, gr, ws, (size_t)n * h * w * 64, n, h2, w2, 64, f16 ? 1 : 2, stream));
   uint16_t* dcols = static_cast<uint16_t*>(m->arena.take((size_t)n * h2 * w2 * 192 * 2));            // ONE fp16 plane (hi plane of gr in)
   B200R_CHECK_ARG(dcols, "activation arena too small");
   RC(b200r_linear(gr, m->stem_wt.p, nullptr, nullptr, nullptr, dcols, nullptr, n * h2 * w2, 64, 192, B200R_ACT_NONE, B200R_PASSES_F16, stream));

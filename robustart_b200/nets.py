@@ -132,7 +132,7 @@ class _ConvBN:
         self.w = ops.to_planes(w.permute(0, 2, 3, 1).contiguous().to(device), f16)
         self.stride, self.pad = stride, pad
         self.k = w.shape[-1]
-        self._w_folded, self._w_dgrad, self._device = w, None, device
+        self._w_folded, self._w_dgrad, self._w_dgrad_s2, self._device = w, None, None, device
 
     def dgrad(self, dy, res=None, mask=None, passes=3):
         """Input gradient of the convolution: dy planes [2,n,ho,wo,cout] -> [mask > 0] * (planes [2,n,h,w,cin] + res).
@@ -148,6 +148,14 @@ class _ConvBN:
             # 1x1/s2 (downsample branch): contract on the small map, then zero-insert
             assert res is None and mask is None
             return ops.dilate2(ops.conv2d_dgrad(dy, self._w_dgrad, passes=passes))
+        if self.stride == 2 and self.k == 3 and self.pad == 1 and os.environ.get("B200R_DGRAD_S2", "parity") == "parity":
+            # parity classes of the output only meet 1, 2, 2 and 4 of the nine flipped taps: four small stride-1 convolutions of dy
+            # itself, each written into its quarter of dx (no zero-dilated tensor, a quarter of the MMAs)
+            if self._w_dgrad_s2 is None:
+                wt = self._w_folded.flip(2, 3).permute(1, 2, 3, 0)                 # [cin, ky', kx', cout]
+                S = ([1], [0, 2])
+                self._w_dgrad_s2 = [ops.to_planes(wt[:, S[a]][:, :, S[b]].contiguous().to(self._device), self.f16) for a in (0, 1) for b in (0, 1)]
+            return ops.conv2d_dgrad3x3s2(dy, self._w_dgrad_s2, res, mask, passes=passes)
         if self.stride == 2:
             dy = ops.dilate2(dy)
         return ops.conv2d_dgrad(dy, self._w_dgrad, res, mask, pad=self.k - 1 - self.pad, passes=passes)
@@ -309,8 +317,8 @@ class ResNet:
             in_mask = saved["blocks"][i - 1][-1] if i > 0 else None     # block input = previous block's output
             g = self.block_backward(self.blocks[i], saved["blocks"][i], g, P, in_mask=in_mask, g_is_masked=True)
         s0 = saved["stem"]
-        g = ops.relu_bwd(ops.maxpool3x3s2_bwd(s0, g), s0)
-        dcols = ops.linear(g[:1].view(1, -1, 64), self._stem_wt, passes=ops.PASSES_F16)      # hi plane only -> [1, n*ho*wo, 192]
+        g = ops.maxpool3x3s2_relu_bwd_hi(s0, g)          # max-pool and stem-ReLU backward in one pass, one fp16 plane out
+        dcols = ops.linear(g.view(1, -1, 64), self._stem_wt, passes=ops.PASSES_F16)          # -> [1, n*ho*wo, 192]
         return ops.stem_col2im(dcols, n, h, w, unscale=1.0 / S)
 
     def loss_and_input_grad(self, x01: torch.Tensor, labels: torch.Tensor, reduction: str = "sum"):

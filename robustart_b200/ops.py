@@ -566,6 +566,27 @@ def conv2d_dgrad(dy, wgt_t, res=None, mask=None, *, pad=0, passes=3):
     return out
 
 
+def conv2d_dgrad3x3s2(dy, wsub, res=None, mask=None, *, passes=3):
+    """Input gradient of a 3x3 / stride 2 / pad 1 convolution by parity classes (include/b200r.h): dy planes [P,n,ho,wo,cdy],
+    wsub = the four sub-kernels [P,cdx,1+a,1+b,cdy] in the order (0,0), (0,1), (1,0), (1,1) -> planes [P,n,2ho,2wo,cdx]."""
+    _need_cuda(dy, torch.int16, "dy")
+    P, n, ho, wo, cdy = dy.shape
+    cdx = wsub[0].shape[1]
+    for i, ws in enumerate(wsub):
+        _need_cuda(ws, torch.int16, "wsub")
+        if tuple(ws.shape) != (P, cdx, 1 + i // 2, 1 + i % 2, cdy) or not ws.is_contiguous():
+            raise ValueError("conv2d_dgrad3x3s2: sub-kernel %d must be contiguous planes [%d, %d, %d, %d, %d]" % (i, P, cdx, 1 + i // 2, 1 + i % 2, cdy))
+    passes = _passes_for(dy, passes)
+    out = torch.empty((P, n, 2 * ho, 2 * wo, cdx), dtype=torch.int16, device=dy.device)
+    for t, nm in ((res, "res"), (mask, "mask")):
+        if t is not None and t.shape != out.shape:
+            raise ValueError("conv2d_dgrad3x3s2: %s must have the output's shape %s" % (nm, tuple(out.shape)))
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().b200r_conv2d_dgrad3x3s2_nhwc(dy.data_ptr(), wsub[0].data_ptr(), wsub[1].data_ptr(), wsub[2].data_ptr(), wsub[3].data_ptr(),
+                                                            _ptr(res), _ptr(mask), out.data_ptr(), n, ho, wo, cdy, cdx, passes, _stream()))
+    return out
+
+
 def relu_bwd(dy, act, add=None, out=None):
     """(act > 0 ? dy : 0) + add on split planes of any shape [2, ...]."""
     assert dy.shape == act.shape and (add is None or add.shape == dy.shape)
@@ -595,6 +616,21 @@ def maxpool3x3s2_bwd(x, dy):
     fn = _lib.load().b200r_maxpool3x3s2_bwd_nhwc_f16 if x.shape[0] == 1 else _lib.load().b200r_maxpool3x3s2_bwd_nhwc
     with torch.cuda.device(x.device):
         _lib.check(fn(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), ws.data_ptr(), ws.numel(), n, h, w, c, _stream()))
+    return dx
+
+
+def maxpool3x3s2_relu_bwd_hi(x, dy):
+    """MaxPool(3,2,1) backward with the backward of the ReLU that produced x fused in; ONE fp16 plane [1,n,h,w,c] out (the stem's
+    gradient GEMM reads a single plane).  x: the pool's forward input planes [P,n,h,w,c]; dy planes [P,n,ho,wo,c]."""
+    _need_cuda(x, torch.int16, "x")
+    _need_cuda(dy, torch.int16, "dy")
+    P, n, h, w, c = x.shape
+    if dy.shape[0] != P or tuple(dy.shape[1:]) != (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c):
+        raise ValueError("maxpool3x3s2_relu_bwd_hi: dy must be the pooled shape of x in the same precision")
+    ws = torch.empty(dy[0].numel(), dtype=torch.uint8, device=x.device)
+    dx = torch.empty((1, n, h, w, c), dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_maxpool3x3s2_relu_bwd_hi(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), ws.data_ptr(), ws.numel(), n, h, w, c, P, _stream()))
     return dx
 
 

@@ -219,3 +219,57 @@ def test_pgd_native_vs_autograd_source(cuda):
         la = F.cross_entropy(net.forward(a), y, reduction="sum").item()
         l0 = F.cross_entropy(net.forward(x), y, reduction="sum").item()
     assert la > l0
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+def test_maxpool_relu_bwd_fused_matches_two_passes(cuda, planes):
+    """maxpool backward with the ReLU backward fused in and one fp16 plane out = relu_bwd(maxpool_bwd(x, dy), x), hi plane
+    (resnet_official.py:225-227)."""
+    from robustart_b200 import ops
+    torch.manual_seed(planes)
+    f16 = planes == 1
+    x = torch.relu(torch.randn(3, 20, 28, 64, device=cuda))
+    x[0, :6] = 0.0                                           # whole windows at zero: relu'(0) = 0 routes nothing
+    dy = torch.randn(3, 10, 14, 64, device=cuda)
+    xp, dyp = ops.to_planes(x, f16), ops.to_planes(dy, f16)
+    want = ops.relu_bwd(ops.maxpool3x3s2_bwd(xp, dyp), xp)
+    got = ops.maxpool3x3s2_relu_bwd_hi(xp, dyp)
+    assert got.shape == (1, 3, 20, 28, 64)
+    a, b = ops.from_planes(got), ops.from_planes(want)
+    assert (a - b).abs().max().item() <= 2 ** -10 * b.abs().max().item()       # the hi plane of a split pair is the fp16 rounding
+    assert ((a == 0) == (b == 0)).all()
+    # and against autograd
+    xr = ops.from_planes(xp).requires_grad_(True)
+    (torch.nn.functional.max_pool2d(torch.relu(xr.permute(0, 3, 1, 2)), 3, 2, 1) * ops.from_planes(dyp).permute(0, 3, 1, 2)).sum().backward()
+    ref = xr.grad
+    assert (a - ref).abs().max().item() <= 2 ** -10 * ref.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("n,ho,wo,cin,cout,with_res", [(3, 14, 14, 128, 128, False), (2, 7, 9, 64, 256, True), (5, 28, 28, 128, 128, False)])
+def test_dgrad_3x3_stride2_by_parity_classes(cuda, n, ho, wo, cin, cout, with_res):
+    """b200r_conv2d_dgrad3x3s2_nhwc (four parity-class convolutions of dy written through strided tensor maps) against autograd of
+    the stride-2 convolution and against the dilate + 3x3 path it replaces (resnet_official.py:112)."""
+    from robustart_b200 import ops
+    torch.manual_seed(n + ho + cin)
+    h, w = 2 * ho, 2 * wo
+    wt = torch.randn(cout, cin, 3, 3, device=cuda) / (cin * 9) ** 0.5
+    x = torch.randn(n, cin, h, w, device=cuda, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(n, ho, wo, cout, device=cuda)
+    act = torch.relu(torch.randn(n, h, w, cin, device=cuda))                  # the activation the gradient flows into
+    res = torch.randn(n, h, w, cin, device=cuda) if with_res else None
+    y = torch.nn.functional.conv2d(x, wt.double(), None, 2, 1)
+    (ref,) = torch.autograd.grad(y, x, dy.permute(0, 3, 1, 2).double())
+    ref = ref.permute(0, 2, 3, 1)
+    if with_res:
+        ref = ref + res.double()
+    ref = ref * (act > 0)
+    wflip = wt.flip(2, 3).permute(1, 2, 3, 0)                                 # [cin, ky', kx', cout]
+    S = ([1], [0, 2])
+    wsub = [ops.to_planes(wflip[:, S[a]][:, :, S[b]].contiguous()) for a in (0, 1) for b in (0, 1)]
+    dyp, ap = ops.to_planes(dy), ops.to_planes(act)
+    rp = ops.to_planes(res) if with_res else None
+    got = ops.from_planes(ops.conv2d_dgrad3x3s2(dyp, wsub, rp, ap)).double()
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() < 2e-5 * scale
+    old = ops.from_planes(ops.conv2d_dgrad(ops.dilate2(dyp), ops.to_planes(wflip.contiguous()), rp, ap, pad=1)).double()
+    assert (got - old).abs().max().item() < 2e-5 * scale

@@ -260,7 +260,8 @@ def gemm_roofline(model, pipe, pk, precision, step_ms, other_ms):
     achieved = flops / gemm_ms / 1e9                                       # FLOP / ms / 1e9 = TFLOP/s
     layer_ms = sum(max(b / (pk["hbm_gbs"] * 1e9), mmas * f / (one_pass_peak * 1e12)) for f, b in recs) * 1e3
     traffic = None
-    for name in ("r2_gemm_traffic_%s.json" % precision, "r1_gemm_traffic_%s.json" % {"split": "bf16x3"}.get(precision, precision)):
+    for name in ("r2_gemm_traffic_pairs.json" if precision == "split" else "", "r2_gemm_traffic_%s.json" % precision,
+                 "r1_gemm_traffic_%s.json" % {"split": "bf16x3"}.get(precision, precision)):
         tp = os.path.join(ROOT, "profiles", name)
         if os.path.exists(tp):      # dram__bytes_read+write summed over the same launches, from one ncu capture (profiles/)
             traffic = json.load(open(tp)).get("dram_bytes_per_forward")

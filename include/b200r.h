@@ -118,6 +118,11 @@ int b200r_normalize_f32nchw(const float* in, float* out, int n, int h, int w,
 int b200r_random_start_linf(const float* x0, float* x, size_t n, size_t chw, float eps,
                             uint64_t seed, uint64_t image_offset, const float* u, int clip01,
                             b200r_stream_t stream);
+/* L2 random start (foolbox L2ProjectedGradientDescentAttack.get_random_start -> uniform_l2_n_balls): x = clip01(x0 + eps * u), u uniform
+ * in the unit chw-ball = the first chw of chw + 1 normals over their norm.  Philox4x32-10 keyed by `seed`, sample i of this call draws
+ * stream image_offset + i (a sharded / re-batched attack reproduces the same starts). */
+int b200r_random_start_l2(const float* x0, float* x, size_t n, size_t chw, float eps, uint64_t seed,
+                          uint64_t image_offset, b200r_stream_t stream);
 /* x = clip01(x0 + clip(x + alpha*sign(g) - x0, -eps, eps)); x updated in place. */
 int b200r_pgd_step_linf(float* x, const float* g, const float* x0, size_t n, size_t chw,
                         float alpha, float eps, b200r_stream_t stream);

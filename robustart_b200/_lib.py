@@ -52,6 +52,7 @@ SIGNATURES = {
                                           C.c_uint64, C.c_uint64, c_f32p, C.c_int, c_stream]),
     "b200r_pgd_step_linf": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_size_t, C.c_size_t, C.c_float,
                                       C.c_float, c_stream]),
+    "b200r_random_start_l2": (C.c_int, [c_f32p, c_f32p, C.c_size_t, C.c_size_t, C.c_float, C.c_uint64, C.c_uint64, c_stream]),
     "b200r_pgd_step_l2": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_size_t, C.c_size_t, C.c_float,
                                     C.c_float, c_f32p, c_stream]),
     "b200r_mim_step_linf": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_size_t, C.c_size_t,

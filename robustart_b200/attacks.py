@@ -197,21 +197,17 @@ def fgsm(input, label, f_model, eps):
 def pgd_l2(input, label, f_model, eps, rel_stepsize, steps, *, random_start=True, seed: Optional[int] = None,
            start_direction: Optional[torch.Tensor] = None):
     """foolbox L2ProjectedGradientDescentAttack (attack.py:25-28).  Random start: a uniform draw from
-    the eps-ball (foolbox uniform_n_balls: the first n coordinates of a uniform point on the
-    (n+1)-sphere); the n+1 normals come from torch's generator (plumbing, once per call)."""
+    the eps-ball (foolbox uniform_l2_n_balls: the first n coordinates of a uniform point on the
+    (n+1)-sphere), drawn on the device by b200r_random_start_l2; `start_direction` (tests) overrides it."""
     _bounds01(f_model)
     x0, y = _prep(input, label)
     alpha = float(rel_stepsize) * float(eps)
     n = x0.shape[0]
     if random_start:
         if start_direction is None:
-            gen = None
-            if seed is not None:
-                gen = torch.Generator(device=x0.device)
-                gen.manual_seed(seed)
-            z = torch.randn(n, x0[0].numel() + 1, device=x0.device, generator=gen)
-            start_direction = (z / z.norm(dim=1, keepdim=True))[:, :-1].reshape(x0.shape)
-        x = (x0 + float(eps) * start_direction).clamp_(0, 1).contiguous()
+            x = ops.random_start_l2(x0, float(eps), seed=next(_call_counter) if seed is None else int(seed))
+        else:
+            x = (x0 + float(eps) * start_direction).clamp_(0, 1).contiguous()
     else:
         x = x0.clone()
     for _ in range(int(steps)):

@@ -413,3 +413,73 @@ int b200r_masked_rows_copy(float* dst, const float* src, const uint8_t* mask, si
 }
 
 }  // extern "C"
+
+// ---- L2 random start (foolbox L2ProjectedGradientDescentAttack.get_random_start -> uniform_l2_n_balls) -------------------------
+// A uniform point of the unit n-ball = the first n coordinates of a uniform point on the (n+1)-sphere = n + 1 normals over their
+// norm.  One CTA per sample; the normals are a pure function of (seed, sample, position), so pass 2 regenerates what pass 1 summed.
+namespace {
+
+__device__ __forceinline__ void normals4(uint64_t seed, uint64_t sample, uint32_t group, float z[4]) {
+  const uint4 r = philox4x32_10(make_uint4(group, 0x4C32u, (uint32_t)sample, (uint32_t)(sample >> 32)), (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)(w[2 * h] >> 8) + 1.0f) * (1.0f / 16777216.0f);     // (0, 1]
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif((float)w[2 * h + 1] * (2.0f / 4294967296.0f), &sn, &cs);
+    z[2 * h] = rad * cs;
+    z[2 * h + 1] = rad * sn;
+  }
+}
+
+__global__ void __launch_bounds__(1024) random_start_l2_kernel(const float4* __restrict__ x0, float4* __restrict__ x, uint32_t chw4, float eps,
+                                                               uint64_t seed, uint64_t sample0) {
+  __shared__ double red[32];
+  __shared__ float s_scale;
+  const uint64_t sample = sample0 + blockIdx.x;
+  double acc = 0.0;
+  for (uint32_t g = threadIdx.x; g <= chw4; g += 1024) {      // group chw4 holds the (n+1)-th normal
+    float z[4];
+    normals4(seed, sample, g, z);
+    if (g < chw4) acc += (double)z[0] * z[0] + (double)z[1] * z[1] + (double)z[2] * z[2] + (double)z[3] * z[3];
+    else acc += (double)z[0] * z[0];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += red[i];
+    s_scale = (float)((double)eps / sqrt(t));
+  }
+  __syncthreads();
+  const float sc = s_scale;
+  const float4* x0r = x0 + (size_t)blockIdx.x * chw4;
+  float4* xr = x + (size_t)blockIdx.x * chw4;
+  for (uint32_t g = threadIdx.x; g < chw4; g += 1024) {
+    float z[4];
+    normals4(seed, sample, g, z);
+    const float4 a = x0r[g];
+    float4 o;
+    o.x = fminf(fmaxf(fmaf(sc, z[0], a.x), 0.f), 1.f);
+    o.y = fminf(fmaxf(fmaf(sc, z[1], a.y), 0.f), 1.f);
+    o.z = fminf(fmaxf(fmaf(sc, z[2], a.z), 0.f), 1.f);
+    o.w = fminf(fmaxf(fmaf(sc, z[3], a.w), 0.f), 1.f);
+    xr[g] = o;
+  }
+}
+
+}  // namespace
+
+extern "C" int b200r_random_start_l2(const float* x0, float* x, size_t n, size_t chw, float eps, uint64_t seed, uint64_t image_offset,
+                                     b200r_stream_t stream) {
+  B200R_CHECK_ARG(x0 && x, "null pointer");
+  B200R_CHECK_ARG(chw % 4 == 0 && chw / 4 < 0xFFFFFFFFull && n < (1u << 30), "chw must be a multiple of 4");
+  B200R_CHECK_ARG(eps >= 0.f, "eps must be non-negative");
+  if (n == 0) return B200R_OK;
+  random_start_l2_kernel<<<(unsigned)n, 1024, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x0), reinterpret_cast<float4*>(x),
+                                                                      (uint32_t)(chw / 4), eps, seed, image_offset);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}

@@ -156,6 +156,16 @@ def random_start_linf(x0: torch.Tensor, eps: float, *, seed: int = 0, image_offs
     return x
 
 
+def random_start_l2(x0: torch.Tensor, eps: float, *, seed: int = 0, image_offset: int = 0) -> torch.Tensor:
+    """clip01(x0 + eps * u), u uniform in the unit ball of x0[0].numel() dimensions (foolbox uniform_l2_n_balls), device Philox."""
+    _need_cuda(x0, torch.float32, "x0")
+    x0 = x0.contiguous()
+    x = torch.empty_like(x0)
+    with torch.cuda.device(x0.device):
+        _lib.check(_lib.load().b200r_random_start_l2(x0.data_ptr(), x.data_ptr(), x0.shape[0], x0[0].numel(), eps, seed, image_offset, _stream()))
+    return x
+
+
 def pgd_step_linf_(x: torch.Tensor, g: torch.Tensor, x0: torch.Tensor, alpha: float, eps: float):
     for t, nm in ((x, "x"), (g, "g"), (x0, "x0")):
         _need_cuda(t, torch.float32, nm)

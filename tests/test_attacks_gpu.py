@@ -204,3 +204,33 @@ def test_pgd_graph_replay_equals_eager(cuda):
         assert torch.equal(a, b)
         assert (a - x).abs().max().item() <= 4 / 255 + 1e-6
     assert len(graphed._step_graphs) == 1
+
+
+def test_random_start_l2_uniform_in_ball(cuda):
+    """b200r_random_start_l2 (foolbox uniform_l2_n_balls): points uniform in the eps-ball -- the radius of a uniform point in a
+    D-ball concentrates at eps * (1 - 1/D), the direction is isotropic, seeds / image offsets give reproducible streams."""
+    from robustart_b200 import ops
+    n, d, eps = 64, 3 * 32 * 32, 2.5
+    x0 = torch.full((n, 3, 32, 32), 0.5, device=cuda)            # clipping to [0, 1] cannot touch |delta| <= 2.5 / sqrt(3072) per pixel scale
+    x = ops.random_start_l2(x0, eps, seed=7)
+    delta = (x - x0).view(n, -1).double()
+    r = delta.norm(dim=1)
+    assert (r <= eps * (1 + 1e-5)).all()
+    # radius of a uniform point in the unit D-ball: U^(1/D); its mean is D / (D + 1)
+    assert abs(r.mean().item() / eps - d / (d + 1.0)) < 2e-4
+    # isotropy: coordinates have mean 0 and variance eps^2 / (D + 2)
+    assert abs(delta.mean().item()) < 4 * eps / (d ** 0.5) / (n * d) ** 0.5 * 1.5
+    assert abs(delta.var().item() * (d + 2) / eps ** 2 - 1.0) < 0.02
+    # distinct samples are uncorrelated; the same (seed, offset) reproduces, a re-batched call continues the streams
+    c = (delta[0] * delta[1]).sum().item() / (r[0] * r[1]).item()
+    assert abs(c) < 0.1
+    assert torch.equal(x, ops.random_start_l2(x0, eps, seed=7))
+    assert not torch.equal(x, ops.random_start_l2(x0, eps, seed=8))
+    assert torch.equal(x[16:], ops.random_start_l2(x0[16:], eps, seed=7, image_offset=16))
+    # clipping
+    y = ops.random_start_l2(torch.zeros(4, 3, 8, 8, device=cuda), 50.0, seed=1)
+    assert y.min().item() == 0.0 and y.max().item() <= 1.0
+    # normality of the direction: kurtosis of the coordinates of one long sample ~ 3
+    z = ops.random_start_l2(torch.full((1, 3, 224, 224), 0.5, device=cuda), 1.0, seed=3).view(-1).double() - 0.5
+    k = ((z - z.mean()) ** 4).mean() / z.var() ** 2
+    assert abs(k.item() - 3.0) < 0.1

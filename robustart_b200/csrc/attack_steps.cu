@@ -427,7 +427,7 @@ __device__ __forceinline__ void normals4(uint64_t seed, uint64_t sample, uint32_
     const float u1 = ((float)(w[2 * h] >> 8) + 1.0f) * (1.0f / 16777216.0f);     // (0, 1]
     const float rad = sqrtf(-2.0f * logf(u1));
     float sn, cs;
-    sincospif((float)w[2 * h + 1] * (2.0f / 4294967296.0f), &sn, &cs);
+    sincosf((float)w[2 * h + 1] * (6.283185307179586f / 4294967296.0f), &sn, &cs);
     z[2 * h] = rad * cs;
     z[2 * h + 1] = rad * sn;
   }
@@ -435,7 +435,7 @@ __device__ __forceinline__ void normals4(uint64_t seed, uint64_t sample, uint32_
 
 __global__ void __launch_bounds__(1024) random_start_l2_kernel(const float4* __restrict__ x0, float4* __restrict__ x, uint32_t chw4, float eps,
                                                                uint64_t seed, uint64_t sample0) {
-  __shared__ double red[32];
+  __shared__ double red[1024];
   __shared__ float s_scale;
   const uint64_t sample = sample0 + blockIdx.x;
   double acc = 0.0;
@@ -445,14 +445,13 @@ __global__ void __launch_bounds__(1024) random_start_l2_kernel(const float4* __r
     if (g < chw4) acc += (double)z[0] * z[0] + (double)z[1] * z[1] + (double)z[2] * z[2] + (double)z[3] * z[3];
     else acc += (double)z[0] * z[0];
   }
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  red[threadIdx.x] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < 32; ++i) t += red[i];
-    s_scale = (float)((double)eps / sqrt(t));
+  for (int o = 512; o > 0; o >>= 1) {            // fixed-order tree: the start is reproducible bit for bit
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
   }
+  if (threadIdx.x == 0) s_scale = (float)((double)eps / sqrt(red[0]));
   __syncthreads();
   const float sc = s_scale;
   const float4* x0r = x0 + (size_t)blockIdx.x * chw4;

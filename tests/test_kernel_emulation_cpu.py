@@ -409,6 +409,15 @@ def test_attack_step_and_loss_kernels(emu):
         ref = (x0 + (ref + alpha * g.sign() - x0).clamp(-eps, eps)).clamp(0, 1)
         _ok(lib.b200r_pgd_step_linf(_p(x), _p(g), _p(x0), n, chw, alpha, eps, None))
     assert torch.equal(x, ref)
+    # L2 random start: inside the ball, reproducible, streams continue across a re-batched call
+    lib.b200r_random_start_l2.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float, C.c_uint64, C.c_uint64, C.c_void_p]
+    half = torch.full((n, chw), 0.5)
+    a, b = torch.empty(n, chw), torch.empty(n, chw)
+    _ok(lib.b200r_random_start_l2(_p(half), _p(a), n, chw, 1.5, 11, 0, None))
+    r = (a - half).double().norm(dim=1)
+    assert (r <= 1.5 * (1 + 1e-5)).all() and (r > 1.5 * 0.98).all()             # U^(1/768) > 0.98 with probability 1 - 2e-7
+    _ok(lib.b200r_random_start_l2(_p(half[1:]), _p(b), n - 1, chw, 1.5, 11, 1, None))
+    assert torch.equal(a[1:], b[: n - 1])
     lm = emu["loss_metrics"]
     z, y = torch.randn(5, 1000) * 3, torch.randint(0, 1000, (5,))
     z[2, y[2]] += 20.0                                                           # one certain top-1 hit

@@ -61,11 +61,7 @@ __device__ __forceinline__ void store8(uint4* __restrict__ ph, uint4* __restrict
       const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
       rh[j] = *reinterpret_cast<const uint32_t*>(&h);
     } else {
-      uint16_t h0, l0, h1, l1;
-      split_pair(v[2 * j], h0, l0);
-      split_pair(v[2 * j + 1], h1, l1);
-      rh[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-      rl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+      split_pair2(v[2 * j], v[2 * j + 1], rh[j], rl[j]);
     }
   }
   ph[i] = make_uint4(rh[0], rh[1], rh[2], rh[3]);

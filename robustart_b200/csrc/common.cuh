@@ -162,6 +162,15 @@ __device__ __forceinline__ float plane_bits_to_f32(uint16_t b) { return __half2f
 // the two fp16 values packed in one 32-bit word of a plane (element 2j in the low half, 2j + 1 in the high half)
 __device__ __forceinline__ float plane_lo16_f32(uint32_t w) { return __half2float(__ushort_as_half((uint16_t)(w & 0xFFFFu))); }
 __device__ __forceinline__ float plane_hi16_f32(uint32_t w) { return __half2float(__ushort_as_half((uint16_t)(w >> 16))); }
+// two values at once, packed in plane words (v0 in the low half): the packed conversions (F2FP.F16.F32.PACK_AB on the ALU pipe,
+// HADD2.F32 back) instead of four scalar F2F on the quarter-rate XU pipe -- same round-to-nearest results bit for bit
+__device__ __forceinline__ void split_pair2(float v0, float v1, uint32_t& hw, uint32_t& lw) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+  hw = *reinterpret_cast<const uint32_t*>(&h);
+  lw = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void split_pair(float v, uint16_t& hi, uint16_t& lo) {
   const __half h = __float2half_rn(v);
   hi = __half_as_ushort(h);

@@ -24,11 +24,11 @@ __global__ void __launch_bounds__(kThreads) split_kernel(const float4* __restric
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < count4; i += (size_t)gridDim.x * kThreads) {
     float4 v = ld_stream_f4(in + i);
     v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-    uint16_t h[4], l[4];
-    split_pair(v.x, h[0], l[0]); split_pair(v.y, h[1], l[1]);
-    split_pair(v.z, h[2], l[2]); split_pair(v.w, h[3], l[3]);
-    hi[i] = make_uint2(pack_u16x2(h[0], h[1]), pack_u16x2(h[2], h[3]));
-    lo[i] = make_uint2(pack_u16x2(l[0], l[1]), pack_u16x2(l[2], l[3]));
+    uint32_t h[2], l[2];
+    split_pair2(v.x, v.y, h[0], l[0]);
+    split_pair2(v.z, v.w, h[1], l[1]);
+    hi[i] = make_uint2(h[0], h[1]);
+    lo[i] = make_uint2(l[0], l[1]);
   }
 }
 

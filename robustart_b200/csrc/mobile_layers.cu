@@ -21,13 +21,7 @@ __device__ __forceinline__ void unpack8(uint4 h, uint4 l, float* v) {
 __device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
   uint32_t hw[4], lw[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint16_t h0, l0, h1, l1;
-    split_pair(v[2 * j], h0, l0);
-    split_pair(v[2 * j + 1], h1, l1);
-    hw[j] = h0 | ((uint32_t)h1 << 16);
-    lw[j] = l0 | ((uint32_t)l1 << 16);
-  }
+  for (int j = 0; j < 4; ++j) split_pair2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
   h = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
@@ -160,6 +154,128 @@ __global__ void __launch_bounds__(kThreads) dwconv_strip_kernel(const uint4* __r
       pack8(ov, hh, ll);
       yh[obase + (size_t)o * c8] = hh;
       yl[obase + (size_t)o * c8] = ll;
+    }
+  }
+}
+
+// Tiled version (round 2).  ncu on the strip kernel (MobileNetV2, batch 256): 104 registers -> 16 resident warps, every pixel loaded
+// AND unpacked (hi/lo fp16 -> fp32: ~45 instructions per 8 channels) 4.5 times through L1, 600 instructions per 64-byte output, issue
+// 60 %, DRAM 31-37 %: 2.2x the layers' HBM time.  Here a CTA owns a tile of TH x TW output pixels x CG channel groups (8 channels
+// each): the input patch is loaded from global memory ONCE, unpacked ONCE and parked in shared memory as fp32
+// [half][group][row][column] float4 planes (plane size = 16 bytes mod 128, so the 4 groups x 2 strips of a quarter-warp hit eight
+// different 16-byte bank groups).  A thread then computes a strip of OW outputs along x: per kernel row the K weight vectors (two
+// broadcast LDS.128 each) and the row's (OW-1)*S+K pixels are read once and every pixel feeds all the (output, tap) pairs it belongs to.
+// Threads map to (group fastest, strip, row): four neighbours store 64 contiguous bytes per plane.
+template <int K, int S, int OW>
+__global__ void __launch_bounds__(kThreads) dwconv_tile_kernel(const uint4* __restrict__ xh, const uint4* __restrict__ xl,
+                                                                const float* __restrict__ wgt, const float* __restrict__ scale,
+                                                                const float* __restrict__ bias, uint4* __restrict__ yh,
+                                                                uint4* __restrict__ yl, int h, int w, int c8, int ho, int wo, int act,
+                                                                int TH, int TW, int CG, int tiles_x, int tiles_y, int tiles_c,
+                                                                int plane4 /* float4 per (half, group) plane, padded */) {
+  extern __shared__ __align__(16) float4 dw_smem[];
+  constexpr int PAD = K / 2, IW = (OW - 1) * S + K;
+  const int THI = (TH - 1) * S + K, TWI = (TW - 1) * S + K;
+  float4* s_w = dw_smem;                                   // [K*K][CG][2]
+  float4* s_x = dw_smem + K * K * CG * 2;                  // [2][CG][THI][TWI] (+ padding)
+  const int half4 = CG * plane4;
+  int t = blockIdx.x;
+  const int tc = t % tiles_c; t /= tiles_c;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int im = t / tiles_y;
+  const int cg0 = tc * CG, oy0 = ty * TH, ox0 = tx * TW, iy0 = oy0 * S - PAD, ix0 = ox0 * S - PAD;
+  for (int i = threadIdx.x; i < K * K * CG * 2; i += kThreads) {
+    const int hf = i & 1, g = (i >> 1) % CG, tap = (i >> 1) / CG;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cg0 + g < c8) v = __ldg(reinterpret_cast<const float4*>(wgt + ((size_t)tap * c8 + cg0 + g) * 8) + hf);
+    s_w[i] = v;
+  }
+  // input patch: one pass.  Work item = (group, patch column, chunk of four rows) -- group fastest: 64 contiguous bytes per plane and
+  // pixel -- with the item's eight loads in flight before the first conversion; three divisions per item, not per pixel.
+  const int cols = TWI * CG, chunks = (THI + 3) >> 2;
+  for (int e = threadIdx.x; e < cols * chunks; e += kThreads) {
+    const int chunk = e / cols, rem = e - chunk * cols;
+    const int px = rem / CG, g = rem - px * CG;
+    const int ix = ix0 + px, py = chunk * 4;
+    const bool col_ok = ix >= 0 && ix < w && cg0 + g < c8;
+    const size_t col = (size_t)im * h * w * c8 + (size_t)(col_ok ? ix : 0) * c8 + (col_ok ? cg0 + g : 0);
+    const size_t row_pitch = (size_t)w * c8;
+    float4* d = s_x + g * plane4 + px;
+    uint4 rh[4], rl[4];
+    bool ok[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int iy = iy0 + py + r;
+      ok[r] = col_ok && py + r < THI && iy >= 0 && iy < h;
+      const size_t at = col + (size_t)(ok[r] ? iy : 0) * row_pitch;
+      rh[r] = __ldg(xh + at);
+      rl[r] = __ldg(xl + at);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (py + r >= THI) break;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok[r]) unpack8(rh[r], rl[r], v);
+      d[(py + r) * TWI] = make_float4(v[0], v[1], v[2], v[3]);
+      d[half4 + (py + r) * TWI] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  __syncthreads();
+  const int SW = TW / OW;                                  // the host picks TW as a multiple of OW
+  for (int it = threadIdx.x; it < TH * SW * CG; it += kThreads) {
+    const int g = it % CG, sx = (it / CG) % SW, y = it / (CG * SW);
+    const int oy = oy0 + y, oxs = ox0 + sx * OW, cc = cg0 + g;
+    if (oy >= ho || oxs >= wo || cc >= c8) continue;
+    float a[OW][8];
+#pragma unroll
+    for (int o = 0; o < OW; ++o)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[o][q] = 0.f;
+    const float4* row0 = s_x + g * plane4 + (y * S) * TWI + sx * OW * S;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      float4 w0[K], w1[K];
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        w0[kx] = s_w[((ky * K + kx) * CG + g) * 2];
+        w1[kx] = s_w[((ky * K + kx) * CG + g) * 2 + 1];
+      }
+      const float4* rp = row0 + ky * TWI;
+#pragma unroll
+      for (int j = 0; j < IW; ++j) {
+        const float4 v0 = rp[j], v1 = rp[half4 + j];
+#pragma unroll
+        for (int o = 0; o < OW; ++o) {
+          const int kx = j - o * S;                          // compile-time after unrolling
+          if (kx >= 0 && kx < K) {
+            a[o][0] = fmaf(v0.x, w0[kx].x, a[o][0]); a[o][1] = fmaf(v0.y, w0[kx].y, a[o][1]);
+            a[o][2] = fmaf(v0.z, w0[kx].z, a[o][2]); a[o][3] = fmaf(v0.w, w0[kx].w, a[o][3]);
+            a[o][4] = fmaf(v1.x, w1[kx].x, a[o][4]); a[o][5] = fmaf(v1.y, w1[kx].y, a[o][5]);
+            a[o][6] = fmaf(v1.z, w1[kx].z, a[o][6]); a[o][7] = fmaf(v1.w, w1[kx].w, a[o][7]);
+          }
+        }
+      }
+    }
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cc * 8)), s1 = __ldg(reinterpret_cast<const float4*>(scale + cc * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cc * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + cc * 8) + 1);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const size_t ob = (((size_t)im * ho + oy) * wo + oxs) * c8 + cc;
+#pragma unroll
+    for (int o = 0; o < OW; ++o) {
+      if (oxs + o >= wo) break;
+      float ov[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float r = fmaf(a[o][q], sc[q], bi[q]);
+        ov[q] = act == B200R_ACT_RELU6 ? fminf(fmaxf(r, 0.f), 6.f)
+              : act == B200R_ACT_SWISH ? __fdividef(r, 1.f + __expf(-r))
+              : act_apply(r, act);
+      }
+      uint4 hh, ll;
+      pack8(ov, hh, ll);
+      yh[ob + (size_t)o * c8] = hh;
+      yl[ob + (size_t)o * c8] = ll;
     }
   }
 }
@@ -301,6 +417,44 @@ int b200r_dwconv_nhwc(const uint16_t* x, const float* wgt, const float* scale, c
   uint4 *yh = reinterpret_cast<uint4*>(y), *yl = reinterpret_cast<uint4*>(y + cout);
   static int use_strip = -1;      // B200R_DW_STRIP=0: generic kernel for every shape (A/B measurements)
   if (use_strip < 0) { const char* e = getenv("B200R_DW_STRIP"); use_strip = (e && e[0] == '0') ? 0 : 1; }
+  const char* tile_env = getenv("B200R_DW_TILE");          // B200R_DW_TILE=0: the round-1 strip kernel
+  // measured (batch 256): the tile kernel wins for 5 x 5 (25 taps of reuse: 0.31 -> 0.23 ms at 240 ch @28), the strip kernel for 3 x 3
+  // (0.31 vs 0.40 ms at 144 ch @56: the two-phase tile does not hide its fill at 9 taps); B200R_DW_TILE=1 forces the tile kernel
+  const bool want_tile = tile_env ? tile_env[0] == '1' : k == 5;
+  if (want_tile && pad == k / 2 && (k == 3 || k == 5) && (stride == 1 || stride == 2)) {
+    // strips of OW outputs (4 at stride 1, 2 at stride 2: the strip pitch stays 64 bytes, conflict-free); tile = TW x TH outputs x CG
+    // channel groups with ~256 strips per CTA
+    const int c8 = c / 8, OW = stride == 1 ? 4 : 2;
+    int TW = wo < 16 ? ((wo + OW - 1) / OW) * OW : 16;
+    const int SW = TW / OW;
+    int TH = 64 / SW;                                        // with CG = 4: 256 strips
+    if (TH > ho) TH = ho;
+    int CG = 256 / (TH * SW);
+    if (CG < 4) CG = 4;
+    if (CG > c8) CG = c8;
+    const int THI = (TH - 1) * stride + k, TWI = (TW - 1) * stride + k;
+    int plane4 = THI * TWI;                                  // float4 units; pad to 1 mod 8: the next group starts 16 bytes mod 128 later
+    plane4 += (9 - plane4 % 8) % 8;
+    const int tiles_x = (wo + TW - 1) / TW, tiles_y = (ho + TH - 1) / TH, tiles_c = (c8 + CG - 1) / CG;
+    const size_t smem = ((size_t)k * k * CG * 2 + (size_t)CG * 2 * plane4) * sizeof(float4);
+    const long long blocks = (long long)n * tiles_y * tiles_x * tiles_c;
+    if (smem <= 96 * 1024 && blocks < (1LL << 31)) {
+#define B200R_DWT(K, S, O)                                                                                                           \
+      do {                                                                                                                           \
+        static size_t conf = 0;                                                                                                      \
+        if (conf < smem) { B200R_CUDA(cudaFuncSetAttribute(dwconv_tile_kernel<K, S, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf = smem; } \
+        dwconv_tile_kernel<K, S, O><<<(unsigned)blocks, kThreads, smem, as_stream(stream)>>>(xh, xl, wgt, scale, bias, yh, yl, h, w, c8, ho, wo, act, \
+                                                                                            TH, TW, CG, tiles_x, tiles_y, tiles_c, plane4); \
+      } while (0)
+      if (k == 3 && stride == 1) B200R_DWT(3, 1, 4);
+      else if (k == 3) B200R_DWT(3, 2, 2);
+      else if (stride == 1) B200R_DWT(5, 1, 4);
+      else B200R_DWT(5, 2, 2);
+#undef B200R_DWT
+      B200R_LAUNCH_CHECK();
+      return B200R_OK;
+    }
+  }
   if (use_strip && pad == k / 2 && (k == 3 || k == 5) && (stride == 1 || stride == 2)) {
     const size_t threads = (size_t)n * ho * ((wo + 3) / 4) * (c / 8);
 #define B200R_DW(K, S) dwconv_strip_kernel<K, S><<<grid_for(threads), kThreads, 0, as_stream(stream)>>>(xh, xl, wgt, scale, bias, yh, yl, n, h, w, c / 8, ho, wo, act)

@@ -36,13 +36,7 @@ __device__ __forceinline__ void unpack8(uint4 h, uint4 l, float* v) {
 __device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
   uint32_t hw[4], lw[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint16_t h0, l0, h1, l1;
-    split_pair(v[2 * j], h0, l0);
-    split_pair(v[2 * j + 1], h1, l1);
-    hw[j] = h0 | ((uint32_t)h1 << 16);
-    lw[j] = l0 | ((uint32_t)l1 << 16);
-  }
+  for (int j = 0; j < 4; ++j) split_pair2(v[2 * j], v[2 * j + 1], hw[j], lw[j]);
   h = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }

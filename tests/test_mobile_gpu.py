@@ -28,6 +28,33 @@ def test_depthwise_conv(cuda, k, stride, c):
     assert (y.permute(0, 3, 1, 2).double() - ref).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("k,stride,c,h,w", [(3, 1, 32, 112, 112), (3, 2, 96, 112, 112), (3, 1, 144, 56, 56), (3, 2, 144, 56, 56), (3, 1, 384, 14, 14),
+                                            (3, 1, 960, 7, 7), (5, 1, 240, 28, 28), (5, 2, 672, 14, 14), (5, 1, 1152, 7, 7), (3, 1, 8, 15, 17),
+                                            (5, 2, 24, 33, 19), (3, 2, 16, 9, 9)])
+def test_depthwise_tile_kernel_geometries(cuda, k, stride, c, h, w, monkeypatch):
+    """dwconv_tile_kernel (shared-memory tile, one load + one unpack per input pixel) on the mobile families' layer shapes, ragged
+    tiles, channel-group remainders and odd sizes: against fp64 and against the strip kernel it replaces
+    (mobilenet_v2.py:31-47; efficientnet.py:322-336)."""
+    from robustart_b200 import ops
+    torch.manual_seed(k * 1000 + c + h)
+    n = 2
+    x = torch.randn(n, c, h, w, device=cuda)
+    wt = torch.randn(c, 1, k, k, device=cuda) * 0.2
+    s, b = torch.rand(c, device=cuda) + 0.5, torch.randn(c, device=cuda)
+    xp = ops.split_f32(x.permute(0, 2, 3, 1).contiguous())
+    xm = ops.merge_f32(xp).permute(0, 3, 1, 2)
+    wk = wt.reshape(c, -1).t().contiguous()
+    ref = torch.nn.functional.conv2d(xm.double(), wt.double(), stride=stride, padding=k // 2, groups=c)
+    ref = torch.clamp(ref * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1), 0, 6).permute(0, 2, 3, 1)
+    monkeypatch.setenv("B200R_DW_TILE", "1")
+    got = ops.merge_f32(ops.dwconv_nhwc(xp, wk, s, b, k=k, stride=stride, pad=k // 2, act="relu6"))
+    assert got.shape == ref.shape
+    assert (got.double() - ref).abs().max().item() < 1e-4
+    monkeypatch.setenv("B200R_DW_TILE", "0")
+    old = ops.merge_f32(ops.dwconv_nhwc(xp, wk, s, b, k=k, stride=stride, pad=k // 2, act="relu6"))
+    assert (got - old).abs().max().item() < 2e-5
+
+
 def test_se_scale_and_small_channel_gemm(cuda):
     from robustart_b200 import ops
     torch.manual_seed(0)

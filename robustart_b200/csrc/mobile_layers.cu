@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kThreads) image_im2col_kernel(const void* __re
 // MobileNetV2 (mobilenet_v2.py:130) and EfficientNet-B0 (efficientnet.py:429-433).  As im2col (K = 27 padded to 32) + GEMM
 // the layer wrote and re-read a 205 MB patch matrix per 128 images (0.25 + 0.15 ms, 10 % of a MobileNetV2 forward); the
 // arithmetic is 1 728 FLOP per output pixel, so CUDA cores at fp32 do it in the time it takes to write the output.
-// thread = (output pixel, 8 output channels); weights [27][cout] in shared memory, ToTensor + Normalize on the fly.
+// thread = output pixel (all output channels); weights [27][cout] in shared memory, ToTensor + Normalize on the fly.
 template <bool U8>
 __global__ void __launch_bounds__(kThreads) image_stem3x3s2_kernel(const void* __restrict__ img, const float* __restrict__ wgt,
                                                                     const float* __restrict__ scale, const float* __restrict__ bias,
@@ -349,6 +349,8 @@ __global__ void __launch_bounds__(kThreads) image_stem3x3s2_kernel(const void* _
                                                                     int ho, int wo, int cout, int act, Norm3 nm) {
   __shared__ __align__(16) float sw[27 * 64];
   __shared__ float lut[U8 ? 768 : 1];                                // ToTensor + Normalize of every byte value, per channel
+  __shared__ float ssc[64], sbi[64];
+  if (threadIdx.x < cout) { ssc[threadIdx.x] = scale[threadIdx.x]; sbi[threadIdx.x] = bias[threadIdx.x]; }
   for (int i = threadIdx.x; i < 27 * cout; i += kThreads) {          // wgt is [cout][27] (ky, kx, c) -> sw[tap][cout]
     const int t = i / cout, oc = i - t * cout;
     sw[i] = wgt[oc * 27 + t];
@@ -356,11 +358,12 @@ __global__ void __launch_bounds__(kThreads) image_stem3x3s2_kernel(const void* _
   if (U8)
     for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = (__fdiv_rn((float)(i & 255), 255.0f) - nm.mean[i >> 8]) / nm.std[i >> 8];
   __syncthreads();
+  // thread = one output pixel, ALL output channels (round 2; was (pixel, 8 channels): four threads repeated the pixel's 27 byte
+  // loads and 27 table lookups, and ncu showed the L1 / shared-memory path 98 % busy): the 27 normalised inputs are gathered once
+  // into registers, then each group of 8 output channels is 27 x 2 warp-uniform (broadcast) LDS.128 of weights + 216 FFMA
   const int c8 = cout / 8;
-  const size_t total = (size_t)n * ho * wo * c8;
-  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
-    const int cc = (int)(t % c8);
-    const size_t pix = t / c8;
+  const size_t total = (size_t)n * ho * wo;
+  for (size_t pix = (size_t)blockIdx.x * kThreads + threadIdx.x; pix < total; pix += (size_t)gridDim.x * kThreads) {
     const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), im = (int)(pix / ((size_t)wo * ho));
     float x[27];
 #pragma unroll
@@ -379,22 +382,24 @@ __global__ void __launch_bounds__(kThreads) image_stem3x3s2_kernel(const void* _
           x[(ky * 3 + kx) * 3 + c] = v;
         }
       }
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int cc = 0; cc < c8; ++cc) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      const float4 w0 = *reinterpret_cast<const float4*>(sw + k * cout + cc * 8), w1 = *reinterpret_cast<const float4*>(sw + k * cout + cc * 8 + 4);
-      acc[0] = fmaf(x[k], w0.x, acc[0]); acc[1] = fmaf(x[k], w0.y, acc[1]); acc[2] = fmaf(x[k], w0.z, acc[2]); acc[3] = fmaf(x[k], w0.w, acc[3]);
-      acc[4] = fmaf(x[k], w1.x, acc[4]); acc[5] = fmaf(x[k], w1.y, acc[5]); acc[6] = fmaf(x[k], w1.z, acc[6]); acc[7] = fmaf(x[k], w1.w, acc[7]);
-    }
-    float o[8];
+      for (int k = 0; k < 27; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + k * cout + cc * 8), w1 = *reinterpret_cast<const float4*>(sw + k * cout + cc * 8 + 4);
+        acc[0] = fmaf(x[k], w0.x, acc[0]); acc[1] = fmaf(x[k], w0.y, acc[1]); acc[2] = fmaf(x[k], w0.z, acc[2]); acc[3] = fmaf(x[k], w0.w, acc[3]);
+        acc[4] = fmaf(x[k], w1.x, acc[4]); acc[5] = fmaf(x[k], w1.y, acc[5]); acc[6] = fmaf(x[k], w1.z, acc[6]); acc[7] = fmaf(x[k], w1.w, acc[7]);
+      }
+      float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float y = fmaf(acc[j], scale[cc * 8 + j], bias[cc * 8 + j]);
-      o[j] = act == B200R_ACT_RELU6 ? fminf(fmaxf(y, 0.f), 6.f) : act == B200R_ACT_SWISH ? __fdividef(y, 1.f + __expf(-y)) : act_apply(y, act);
+      for (int j = 0; j < 8; ++j) {
+        const float y = fmaf(acc[j], ssc[cc * 8 + j], sbi[cc * 8 + j]);
+        o[j] = act == B200R_ACT_RELU6 ? fminf(fmaxf(y, 0.f), 6.f) : act == B200R_ACT_SWISH ? __fdividef(y, 1.f + __expf(-y)) : act_apply(y, act);
+      }
+      uint4 hh, ll;
+      pack8(o, hh, ll);
+      yh[pix * c8 + cc] = hh; yl[pix * c8 + cc] = ll;
     }
-    uint4 hh, ll;
-    pack8(o, hh, ll);
-    yh[t] = hh; yl[t] = ll;
   }
 }
 
@@ -514,8 +519,8 @@ static int stem3_common(const void* img, const float* wgt, const float* scale, c
   Norm3 nm;
   for (int i = 0; i < 3; ++i) { nm.mean[i] = mean[i]; nm.std[i] = stdv[i]; }
   uint4 *yh = reinterpret_cast<uint4*>(y), *yl = reinterpret_cast<uint4*>(y + cnt);
-  if (u8) image_stem3x3s2_kernel<true><<<grid_for(cnt / 8), kThreads, 0, s>>>(img, wgt, scale, bias, yh, yl, n, h, w, ho, wo, cout, act, nm);
-  else image_stem3x3s2_kernel<false><<<grid_for(cnt / 8), kThreads, 0, s>>>(img, wgt, scale, bias, yh, yl, n, h, w, ho, wo, cout, act, nm);
+  if (u8) image_stem3x3s2_kernel<true><<<grid_for(cnt / cout), kThreads, 0, s>>>(img, wgt, scale, bias, yh, yl, n, h, w, ho, wo, cout, act, nm);
+  else image_stem3x3s2_kernel<false><<<grid_for(cnt / cout), kThreads, 0, s>>>(img, wgt, scale, bias, yh, yl, n, h, w, ho, wo, cout, act, nm);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }

@@ -414,6 +414,13 @@ int b200r_stem_col2im_f32_f16(const uint16_t* dcols, float* dx, int n, int h, in
 int b200r_dwconv_nhwc(const uint16_t* x, const float* wgt, const float* scale, const float* bias,
                       uint16_t* y, int n, int h, int w, int c, int k, int stride, int pad, int act,
                       b200r_stream_t stream);
+/* 1x1 convolution with a small input width on CUDA cores, exact fp32: y = act(x W^T + bias (+ res)) for cin in {8, 16, 24, 32} -- the
+ * expansion / projection layers of the mobile families at 112 x 112 and 56 x 56 (mobilenet_v2.py:52-60; efficientnet.py:312-321), where
+ * a tensor-core tile is one mostly-empty k-block and the layer is pure output streaming.
+ *   x: split planes [m, cin]; wgt: float32 [cout][cin] (BN scale folded in); bias: float32 [cout] (nullable);
+ *   res: split planes [m, cout] (nullable); y: split planes [m, cout]; cout % 8 == 0, cout * cin * 4 <= 96 KB. */
+int b200r_pointwise_smallk_nhwc(const uint16_t* x, const float* wgt, const float* bias, const uint16_t* res, uint16_t* y,
+                                size_t m, int cin, int cout, int act, b200r_stream_t stream);
 /* squeeze-excite scaling: y[n, p, c] = x[n, p, c] * s[n, c]  (s: split planes [n, s_stride]) */
 int b200r_channel_scale(const uint16_t* x, const uint16_t* s, uint16_t* y, int n, int hw, int c,
                         int s_stride, b200r_stream_t stream);

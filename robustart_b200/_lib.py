@@ -173,6 +173,7 @@ SIGNATURES.update({
 SIGNATURES.update({
     "b200r_dwconv_nhwc": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_pointwise_smallk_nhwc": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_channel_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_image_im2col_u8": (C.c_int, [c_u8p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_host_f3,
                                         c_host_f3, c_stream]),

@@ -733,8 +733,13 @@ class _PW:
         self.scale = None                                    # folded into the weights (see _ConvBN)
         w = (w.reshape(w.shape[0], -1).double() * scale.double().cpu().view(-1, 1)).float()
         self.w = ops.split_f32(w.reshape(w.shape[0], 1, 1, w.shape[1]).contiguous().to(device))
+        # narrow inputs (the expansion / projection layers at 112 x 112 and 56 x 56): pure output streaming, no use for a tensor-core tile
+        cin = w.shape[1]
+        self.w_f32 = w.contiguous().to(device) if (cin % 8 == 0 and cin <= 32 and os.environ.get("B200R_PW_SMALLK", "1") != "0") else None
 
     def __call__(self, x, act=None, res=None, passes=3):
+        if self.w_f32 is not None and x.shape[0] == 2:
+            return ops.pointwise_smallk(x, self.w_f32, self.bias, res, act=act)
         return ops.conv2d_nhwc(x, self.w, self.scale, self.bias, res, act=act, passes=passes)
 
     def dgrad(self, dy, res=None, passes=3):

@@ -801,6 +801,25 @@ def dwconv_nhwc(x, wgt, scale, bias, *, k, stride, pad, act=None):
     return out
 
 
+def pointwise_smallk(x, wgt, bias=None, res=None, *, act=None):
+    """1x1 convolution with cin in {8, 16, 24, 32} on CUDA cores in exact fp32 (include/b200r.h): x planes [2, ..., cin],
+    wgt float32 [cout, cin] (BN scale folded), bias float32 [cout], res planes [2, ..., cout] -> planes [2, ..., cout]."""
+    _need_cuda(x, torch.int16, "x")
+    _need_cuda(wgt, torch.float32, "wgt")
+    cin, cout = x.shape[-1], wgt.shape[0]
+    if x.shape[0] != 2 or tuple(wgt.shape) != (cout, cin) or not wgt.is_contiguous():
+        raise ValueError("pointwise_smallk: x must be split planes [2, ..., cin] and wgt contiguous float32 [cout, cin]")
+    m = x[0].numel() // cin
+    out = torch.empty((2,) + tuple(x.shape[1:-1]) + (cout,), dtype=torch.int16, device=x.device)
+    if res is not None and res.shape != out.shape:
+        raise ValueError("pointwise_smallk: res must have the output's shape")
+    if bias is not None:
+        _need_cuda(bias, torch.float32, "bias")
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_pointwise_smallk_nhwc(x.data_ptr(), wgt.data_ptr(), _ptr(bias), _ptr(res), out.data_ptr(), m, cin, cout, ACT[act], _stream()))
+    return out
+
+
 def channel_scale(x, s):
     """x: planes [2,n,h,w,c]; s: planes [2,n,c_stride] -> x * s[n, :c]."""
     _, n, h, w, c = x.shape

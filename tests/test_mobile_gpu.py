@@ -137,3 +137,27 @@ def test_mobile_sources_are_native(cuda):
     from robustart_b200 import attacks, solver
     for t in ("mobilenet_v2", "efficientnet_b0"):
         assert isinstance(solver.build_source_model({"type": t, "kwargs": {}}, None, cuda), attacks.NativeModel)
+
+
+@pytest.mark.parametrize("cin,cout,act,with_res", [(16, 96, "relu6", False), (24, 144, "swish", False), (32, 16, None, False), (8, 8, "relu", True),
+                                                   (32, 192, "relu6", False), (24, 24, None, True), (16, 1000, "sigmoid", False)])
+def test_pointwise_smallk(cuda, cin, cout, act, with_res):
+    """b200r_pointwise_smallk_nhwc (CUDA cores, exact fp32) against fp64 and against the tensor-core GEMM it replaces for narrow inputs
+    (mobilenet_v2.py:52-60; efficientnet.py:312-321)."""
+    from robustart_b200 import ops
+    torch.manual_seed(cin * 7 + cout)
+    x = torch.randn(3, 19, 23, cin, device=cuda)                  # 1311 pixels: not a multiple of the block
+    w = torch.randn(cout, cin, device=cuda) / cin ** 0.5
+    b = torch.randn(cout, device=cuda)
+    res = torch.randn(3, 19, 23, cout, device=cuda) if with_res else None
+    xp = ops.split_f32(x)
+    rp = ops.split_f32(res) if with_res else None
+    ref = ops.merge_f32(xp).double().view(-1, cin) @ w.double().t() + b.double()
+    if with_res:
+        ref = ref + ops.merge_f32(rp).double().view(-1, cout)
+    fn = {"relu6": lambda v: v.clamp(0, 6), "swish": lambda v: v * torch.sigmoid(v), "relu": torch.relu, "sigmoid": torch.sigmoid, None: lambda v: v}[act]
+    ref = fn(ref).view(3, 19, 23, cout)
+    got = ops.merge_f32(ops.pointwise_smallk(xp, w, b, rp, act=act)).double()
+    assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    gemm = ops.merge_f32(ops.conv2d_nhwc(xp, ops.split_f32(w.view(cout, 1, 1, cin).contiguous()), None, b, rp, act=act)).double()
+    assert (got - gemm).abs().max().item() < 5e-5 * max(1.0, ref.abs().max().item())

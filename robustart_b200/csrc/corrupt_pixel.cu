@@ -358,7 +358,7 @@ StrataEntry g_strata[8][16];
 std::mutex g_strata_mu;
 
 // table for sigma = c with `add` folded in (gaussian: the -0.5/255 that turns the final round into a truncation)
-int get_strata(float c, float add, const float** out) {
+int get_strata(float c, float add, const float** out, cudaStream_t stream) {
   int dev = 0;
   B200R_CUDA(cudaGetDevice(&dev));
   B200R_CHECK_ARG(dev >= 0 && dev < 8, "device index %d out of range", dev);
@@ -369,6 +369,13 @@ int get_strata(float c, float add, const float** out) {
     if (!e.d && !slot) slot = &e;
   }
   B200R_CHECK_ARG(slot, "more than 16 distinct noise scales in one process");
+  {  // the table of a (device, scale) pair is uploaded at its first use with a blocking copy, which a capturing stream cannot do
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    B200R_CUDA(cudaStreamIsCapturing(stream, &cs));
+    B200R_CHECK_ARG(cs == cudaStreamCaptureStatusNone,
+                    "gaussian / speckle noise: the quantile table of this noise scale is built at its first use and cannot be built during "
+                    "stream capture -- run this corruption and severity once before capturing the graph");
+  }
   static std::vector<double> z;
   if (z.empty()) { z.resize((size_t)kStrataRows * kStrataLanes); build_strata(z.data()); }
   std::vector<float> h(z.size());
@@ -1078,7 +1085,7 @@ static int launch_noise_rng(const CorruptArgs& a, const uint4* in, uint4* out, u
   const size_t total = (size_t)gpi * a.n;
   if (use_bm || total >= 0xFFFFFFFFull) return launch_noise_bm<SPECKLE>(a, in, out, gpi, c, k0, k1);
   const float* table = nullptr;
-  int rc = get_strata(c, SPECKLE ? 0.f : -0.5f / 255.0f, &table);
+  int rc = get_strata(c, SPECKLE ? 0.f : -0.5f / 255.0f, &table, a.stream);
   if (rc) return rc;
   const uint64_t pos0 = a.image_offset * (uint64_t)gpi;
   const auto keys = make_keys<7>(k0, k1);

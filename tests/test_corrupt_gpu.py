@@ -181,3 +181,36 @@ def test_argument_errors(cuda):
         ops.corrupt_u8(images.cpu(), "gaussian_noise", 1)  # no CPU fallback
     empty = torch.zeros((0, 224, 224, 3), dtype=torch.uint8, device=cuda)
     assert ops.corrupt_u8(empty, "gaussian_noise", 1).shape[0] == 0
+
+
+def test_noise_table_first_use_during_capture_fails_loudly(cuda):
+    """The gaussian / speckle quantile table of a noise scale is uploaded at its first use; inside a stream capture that must be a clear
+    error (and must not poison the capture), and the same launch is capturable once the table exists."""
+    from robustart_b200 import ops
+    img = torch.randint(0, 256, (2, 32, 32, 3), dtype=torch.uint8, device=cuda)
+    out = torch.empty_like(img)
+    sev = 2
+    # a scale no other test uses: speckle severity 2 on a fresh process may already be cached, so accept either outcome of the first
+    # capture but require the message when it fails
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    failed = False
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            try:
+                ops.corrupt_u8(img, "speckle_noise", sev, seed=1, out=out)
+            except ValueError as e:                       # B200R_EINVAL: a refused request, nothing was launched
+                failed = True
+                assert "stream capture" in str(e)
+    torch.cuda.current_stream().wait_stream(s)
+    ops.corrupt_u8(img, "speckle_noise", sev, seed=1, out=out)       # eager: builds the table
+    want = out.clone()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g2, stream=s):
+            ops.corrupt_u8(img, "speckle_noise", sev, seed=1, out=out)
+    out.zero_()
+    g2.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)

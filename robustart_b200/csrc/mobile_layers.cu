@@ -27,9 +27,14 @@ __device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
 }
 // 256-bit global store (sm_100): one full 32-byte sector per thread
 __device__ __forceinline__ void st_v8(uint4* p, const uint4& a, const uint4& b) {
+#ifdef __CUDA_ARCH__
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z),
                "r"(b.w)
                : "memory");
+#else            // host build of the kernel sources (tests/emu)
+  p[0] = a;
+  p[1] = b;
+#endif
 }
 __device__ __forceinline__ float act_apply(float v, int act) {
   switch (act) {

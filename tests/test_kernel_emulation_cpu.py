@@ -656,3 +656,75 @@ def test_imagenet_s_opencv_types_through_the_plugin(emu, monkeypatch, tmp_path):
         out = gen.add_noise(path)
         want = cv2.resize(img, (256, 256), interpolation=inter)[16:240, 16:240]
         assert out.shape == (224, 224, 3) and np.array_equal(out, want), rt
+
+
+def _nhwc_planes(x):
+    return split(x)
+
+
+@pytest.mark.parametrize("k,stride,c,h,w,tile", [(3, 1, 16, 9, 11, "0"), (3, 2, 24, 10, 8, "0"), (5, 1, 16, 9, 11, "1"), (5, 2, 8, 11, 9, "1"), (3, 1, 40, 7, 7, "1"),
+                                                 (3, 2, 16, 12, 20, "1")])
+def test_depthwise_kernels(emu, k, stride, c, h, w, tile, monkeypatch):
+    """csrc/mobile_layers.cu from its own source on the host: the depthwise strip kernel (B200R_DW_TILE=0) and the shared-memory tile
+    kernel (=1) against torch (mobilenet_v2.py:31-47; efficientnet.py:322-336)."""
+    lib = emu["mobile_layers"]
+    monkeypatch.setenv("B200R_DW_TILE", tile)
+    torch.manual_seed(k * 10 + c + h)
+    n = 2
+    x = torch.randn(n, h, w, c)
+    wt = torch.randn(c, 1, k, k) * 0.3
+    s, b = torch.rand(c) + 0.5, torch.randn(c)
+    xp = split(x)
+    ho, wo = (h + 2 * (k // 2) - k) // stride + 1, (w + 2 * (k // 2) - k) // stride + 1
+    out = torch.empty(2, n, ho, wo, c, dtype=torch.int16)
+    wk = wt.reshape(c, -1).t().contiguous()
+    lib.b200r_dwconv_nhwc.argtypes = [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p]
+    _ok(lib.b200r_dwconv_nhwc(_p(xp), _p(wk), _p(s), _p(b), _p(out), n, h, w, c, k, stride, k // 2, 2, None))          # act 2 = ReLU6
+    ref = F.conv2d(merge(xp).permute(0, 3, 1, 2).double(), wt.double(), stride=stride, padding=k // 2, groups=c)
+    ref = torch.clamp(ref * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1), 0, 6).permute(0, 2, 3, 1)
+    assert (merge(out).double() - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,act,with_res", [(16, 96, 2, False), (24, 24, 0, True), (8, 40, 5, False), (32, 16, 0, False)])
+def test_pointwise_smallk_kernel(emu, cin, cout, act, with_res):
+    """b200r_pointwise_smallk_nhwc (narrow 1x1 convolutions on CUDA cores, paired-group full-sector stores) against fp64."""
+    lib = emu["mobile_layers"]
+    torch.manual_seed(cin + cout)
+    m = 301
+    x, w, b = torch.randn(m, cin), torch.randn(cout, cin) / cin ** 0.5, torch.randn(cout)
+    res = torch.randn(m, cout) if with_res else None
+    xp, rp = split(x), (split(res) if with_res else None)
+    out = torch.empty(2, m, cout, dtype=torch.int16)
+    lib.b200r_pointwise_smallk_nhwc.argtypes = [C.c_void_p] * 5 + [C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    _ok(lib.b200r_pointwise_smallk_nhwc(_p(xp), _p(w), _p(b), _p(rp) if with_res else None, _p(out), m, cin, cout, act, None))
+    ref = merge(xp).double() @ w.double().t() + b.double()
+    if with_res:
+        ref = ref + merge(rp).double()
+    ref = {0: lambda v: v, 2: lambda v: v.clamp(0, 6), 5: lambda v: v * torch.sigmoid(v)}[act](ref)
+    assert (merge(out).double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert lib.b200r_pointwise_smallk_nhwc(_p(xp), _p(w), _p(b), None, _p(out), m, 40, cout, act, None) != 0      # cin > 32 is the GEMM's job
+
+
+@pytest.mark.parametrize("planes", [2, 1])
+def test_maxpool_relu_bwd_kernel(emu, planes):
+    """b200r_maxpool3x3s2_relu_bwd_hi from csrc/backward_layers.cu on the host against autograd of max_pool2d(relu(x))."""
+    lib = emu["backward_layers"]
+    torch.manual_seed(planes)
+    n, h, w, c = 2, 10, 12, 16
+    x = torch.relu(torch.randn(n, h, w, c))
+    x[0, :4] = 0.0
+    dy = torch.randn(n, h // 2, w // 2, c)
+    if planes == 2:
+        xp, dyp = split(x), split(dy)
+    else:
+        xp, dyp = x.half().view(torch.int16).unsqueeze(0).contiguous(), dy.half().view(torch.int16).unsqueeze(0).contiguous()
+    xv = merge(xp) if planes == 2 else xp[0].view(torch.float16).float()
+    dv = merge(dyp) if planes == 2 else dyp[0].view(torch.float16).float()
+    out = torch.empty(n, h, w, c, dtype=torch.int16)
+    ws = torch.empty(dy.numel() + 8, dtype=torch.uint8)
+    lib.b200r_maxpool3x3s2_relu_bwd_hi.argtypes = [C.c_void_p] * 4 + [C.c_size_t] + [C.c_int] * 5 + [C.c_void_p]
+    _ok(lib.b200r_maxpool3x3s2_relu_bwd_hi(_p(xp), _p(dyp), _p(out), _p(ws), dy.numel(), n, h, w, c, planes, None))
+    xr = xv.clone().requires_grad_(True)
+    (F.max_pool2d(torch.relu(xr.permute(0, 3, 1, 2)), 3, 2, 1) * dv.permute(0, 3, 1, 2)).sum().backward()
+    got = out.view(torch.float16).float()
+    assert (got - xr.grad).abs().max().item() <= 2 ** -10 * xr.grad.abs().max().item() + 1e-6

@@ -385,6 +385,14 @@ int b200r_maxpool3x3s2_bwd_nhwc(const uint16_t* x, const uint16_t* dy, uint16_t*
  * plane (resnet_official.py:225-227).  x / dy: split planes (planes = 2) or one fp16 plane (planes = 1); dx_hi: [n, h, w, c] fp16. */
 int b200r_maxpool3x3s2_relu_bwd_hi(const uint16_t* x, const uint16_t* dy, uint16_t* dx_hi, void* workspace,
                                    size_t ws_bytes, int n, int h, int w, int c, int planes, b200r_stream_t stream);
+/* The same in two halves for a saved forward (the attack path): the forward pool also writes, per pooled element, the window position
+ * of its first maximum (one byte; 0xF where the maximum is not positive = the producing ReLU's backward folded in), and the backward
+ * routes dy through those codes without touching the 112 x 112 activation again.
+ *   codes: [n, ho, wo, c] bytes, 8-byte aligned.  b200r_maxpool3x3s2_nhwc_codes takes split planes; dy of the backward: planes = 2 / 1. */
+int b200r_maxpool3x3s2_nhwc_codes(const uint16_t* x, uint16_t* y, void* codes, int n, int h, int w, int c,
+                                  b200r_stream_t stream);
+int b200r_maxpool3x3s2_bwd_codes_hi(const void* codes, const uint16_t* dy, uint16_t* dx_hi, int n, int h, int w, int c,
+                                    int planes, b200r_stream_t stream);
 /* AdaptiveAvgPool2d(1) backward: dy planes [n,c] -> dx planes [n,hw,c] = dy / hw */
 int b200r_global_avgpool_bwd_nhwc(const uint16_t* dy, uint16_t* dx, int n, int hw, int c,
                                   b200r_stream_t stream);

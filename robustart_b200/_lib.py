@@ -99,6 +99,8 @@ SIGNATURES = {
                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
     "b200r_dilate2_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_maxpool3x3s2_nhwc_codes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_maxpool3x3s2_bwd_codes_hi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_maxpool3x3s2_relu_bwd_hi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_maxpool3x3s2_bwd_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                               C.c_int, C.c_int, C.c_int, c_stream]),

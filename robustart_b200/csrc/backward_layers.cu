@@ -432,6 +432,22 @@ int b200r_dilate2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w, int 
 int b200r_dilate2_nhwc_f16(const uint16_t* x, uint16_t* y, int n, int h, int w, int c, b200r_stream_t stream) {
   return dilate2_impl(x, y, n, h, w, c, true, as_stream(stream));
 }
+int b200r_maxpool3x3s2_bwd_codes_hi(const void* codes, const uint16_t* dy, uint16_t* dx_hi, int n, int h, int w, int c, int planes,
+                                    b200r_stream_t stream) {
+  B200R_CHECK_ARG(codes && dy && dx_hi, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c % 8 == 0, "c must be a multiple of 8");
+  B200R_CHECK_ARG(planes == 1 || planes == 2, "planes must be 1 (fp16) or 2 (split)");
+  B200R_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & 7) == 0, "codes must be 8-byte aligned");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const size_t xin = (size_t)n * h * w * c, yout = (size_t)n * ho * wo * c;
+  const uint2* idx = reinterpret_cast<const uint2*>(codes);
+  const uint4* gh = reinterpret_cast<const uint4*>(dy);
+  uint4* dh = reinterpret_cast<uint4*>(dx_hi);
+  if (planes == 1) maxpool_bwd_kernel<true, true><<<grid_for(xin / 8), kThreads, 0, as_stream(stream)>>>(idx, gh, nullptr, dh, nullptr, n, h, w, c / 8, ho, wo);
+  else maxpool_bwd_kernel<false, true><<<grid_for(xin / 8), kThreads, 0, as_stream(stream)>>>(idx, gh, reinterpret_cast<const uint4*>(dy + yout), dh, nullptr, n, h, w, c / 8, ho, wo);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
 int b200r_maxpool3x3s2_relu_bwd_hi(const uint16_t* x, const uint16_t* dy, uint16_t* dx_hi, void* workspace, size_t ws_bytes, int n, int h,
                                    int w, int c, int planes, b200r_stream_t stream) {
   B200R_CHECK_ARG(planes == 1 || planes == 2, "planes must be 1 (fp16) or 2 (split)");

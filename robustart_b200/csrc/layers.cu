@@ -87,8 +87,11 @@ __global__ void __launch_bounds__(kThreads) stem_im2col_kernel(const void* __res
 }
 
 // ---- maxpool 3x3 s2 p1, 8 channels per thread ---------------------------------------------------
+// CODES: also writes, per pooled element, the window position ky*3+kx of its (first) maximum -- 0xF where the maximum is not positive,
+// i.e. with the backward of the ReLU that produced x folded in -- for b200r_maxpool3x3s2_bwd_codes_hi (the attack path's saved forward)
+template <bool CODES>
 __global__ void __launch_bounds__(kThreads) maxpool_kernel(const uint4* __restrict__ xhi, const uint4* __restrict__ xlo,
-                                                            uint4* __restrict__ yhi, uint4* __restrict__ ylo,
+                                                            uint4* __restrict__ yhi, uint4* __restrict__ ylo, uint2* __restrict__ codes,
                                                             int n, int h, int w, int c8, int ho, int wo) {
   const size_t total = (size_t)n * ho * wo * c8;
   for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kThreads) {
@@ -96,9 +99,9 @@ __global__ void __launch_bounds__(kThreads) maxpool_kernel(const uint4* __restri
     const size_t pix = t / c8;
     const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), im = (int)(pix / ((size_t)wo * ho));
     float best[8];
-    uint32_t bh[8], bl[8];
+    uint32_t bh[8], bl[8], bi[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bh[j] = 0xFF80u; bl[j] = 0; }
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bh[j] = 0xFF80u; bl[j] = 0; bi[j] = 0xFu; }
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = oy * 2 - 1 + ky;
       if (iy < 0 || iy >= h) continue;
@@ -112,12 +115,18 @@ __global__ void __launch_bounds__(kThreads) maxpool_kernel(const uint4* __restri
         for (int j = 0; j < 8; ++j) {
           uint32_t hb = (aw[j >> 1] >> (16 * (j & 1))) & 0xFFFF, lb = (bw[j >> 1] >> (16 * (j & 1))) & 0xFFFF;
           float v = plane_bits_to_f32((uint16_t)hb) + plane_bits_to_f32((uint16_t)lb);
-          if (v > best[j]) { best[j] = v; bh[j] = hb; bl[j] = lb; }
+          if (v > best[j]) { best[j] = v; bh[j] = hb; bl[j] = lb; if (CODES) bi[j] = (uint32_t)(ky * 3 + kx); }
         }
       }
     }
     yhi[t] = make_uint4(bh[0] | (bh[1] << 16), bh[2] | (bh[3] << 16), bh[4] | (bh[5] << 16), bh[6] | (bh[7] << 16));
     ylo[t] = make_uint4(bl[0] | (bl[1] << 16), bl[2] | (bl[3] << 16), bl[4] | (bl[5] << 16), bl[6] | (bl[7] << 16));
+    if (CODES) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!(best[j] > 0.f)) bi[j] = 0xFu;
+      codes[t] = make_uint2(bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24), bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24));
+    }
   }
 }
 
@@ -330,9 +339,22 @@ int b200r_maxpool3x3s2_nhwc(const uint16_t* x, uint16_t* y, int n, int h, int w,
   B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c % 8 == 0, "c must be a multiple of 8");
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
   const size_t cin = (size_t)n * h * w * c, cout = (size_t)n * ho * wo * c;
-  maxpool_kernel<<<grid_for(cout / 8), kThreads, 0, as_stream(stream)>>>(
+  maxpool_kernel<false><<<grid_for(cout / 8), kThreads, 0, as_stream(stream)>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + cin), reinterpret_cast<uint4*>(y),
-      reinterpret_cast<uint4*>(y + cout), n, h, w, c / 8, ho, wo);
+      reinterpret_cast<uint4*>(y + cout), nullptr, n, h, w, c / 8, ho, wo);
+  B200R_LAUNCH_CHECK();
+  return B200R_OK;
+}
+
+int b200r_maxpool3x3s2_nhwc_codes(const uint16_t* x, uint16_t* y, void* codes, int n, int h, int w, int c, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x && y && codes, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && c % 8 == 0, "c must be a multiple of 8");
+  B200R_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & 7) == 0, "codes must be 8-byte aligned");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const size_t cin = (size_t)n * h * w * c, cout = (size_t)n * ho * wo * c;
+  maxpool_kernel<true><<<grid_for(cout / 8), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(x + cin), reinterpret_cast<uint4*>(y),
+      reinterpret_cast<uint4*>(y + cout), reinterpret_cast<uint2*>(codes), n, h, w, c / 8, ho, wo);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }

@@ -69,7 +69,7 @@ struct b200r_model {
   std::vector<void*> owned;          // every cudaMalloc of the weights
   Arena arena;
   // state of the last forward_f32 (for input_grad)
-  struct Saved { uint16_t* stem = nullptr; std::vector<std::vector<uint16_t*>> blocks; int n = 0, h = 0, w = 0; bool valid = false; } saved;
+  struct Saved { uint16_t* stem = nullptr; void* pool_codes = nullptr; std::vector<std::vector<uint16_t*>> blocks; int n = 0, h = 0, w = 0; bool valid = false; } saved;
 };
 
 namespace {
@@ -408,7 +408,14 @@ int b200r_model_forward_f32(b200r_model* m, const float* x01, float* logits, int
   TAKE(s0, (size_t)n * (h / 2) * (w / 2) * 64);
   RC(b200r_stem_conv7x7_f32(x01, m->stem_w.p, m->stem_scale, m->stem_bias, s0, n, h, w, kMean, kStd, B200R_ACT_RELU, m->passes, stream));
   TAKE(p, (size_t)n * (h / 4) * (w / 4) * 64);
-  RC((m->f16 ? b200r_maxpool3x3s2_nhwc_f16 : b200r_maxpool3x3s2_nhwc)(s0, p, n, h / 2, w / 2, 64, stream));
+  m->saved.pool_codes = nullptr;
+  if (m->f16) {
+    RC(b200r_maxpool3x3s2_nhwc_f16(s0, p, n, h / 2, w / 2, 64, stream));
+  } else {          // the pool leaves its arg-max codes (stem ReLU's backward folded in): the gradient pass never reads s0 again
+    m->saved.pool_codes = m->arena.take((size_t)n * (h / 4) * (w / 4) * 64 + 8);
+    B200R_CHECK_ARG(m->saved.pool_codes, "activation arena too small");
+    RC(b200r_maxpool3x3s2_nhwc_codes(s0, p, m->saved.pool_codes, n, h / 2, w / 2, 64, stream));
+  }
   m->saved.stem = s0; m->saved.n = n; m->saved.h = h; m->saved.w = w;
   int rc = run_body(m, p, n, h / 4, w / 4, logits, true, s);
   m->saved.valid = rc == B200R_OK;
@@ -488,9 +495,14 @@ int b200r_model_input_grad(b200r_model* m, const float* dlogits, float* dx, b200
   // maxpool backward into the 112^2 stem activation, its ReLU, the stem GEMM's gradient, col2im (+ 1/std, 1/S)
   const int h2 = H / 2, w2 = Wd / 2;
   uint16_t* gr = static_cast<uint16_t*>(m->arena.take((size_t)n * h2 * w2 * 64 * 2));               // ONE fp16 plane
-  void* ws = m->arena.take((size_t)n * h * w * 64 + 8);
-  B200R_CHECK_ARG(gr && ws, "activation arena too small");
-  RC(b200r_maxpool3x3s2_relu_bwd_hi(m->saved.stem, g, gr, ws, (size_t)n * h * w * 64, n, h2, w2, 64, f16 ? 1 : 2, stream));
+  B200R_CHECK_ARG(gr, "activation arena too small");
+  if (m->saved.pool_codes) {
+    RC(b200r_maxpool3x3s2_bwd_codes_hi(m->saved.pool_codes, g, gr, n, h2, w2, 64, 2, stream));
+  } else {
+    void* ws = m->arena.take((size_t)n * h * w * 64 + 8);
+    B200R_CHECK_ARG(ws, "activation arena too small");
+    RC(b200r_maxpool3x3s2_relu_bwd_hi(m->saved.stem, g, gr, ws, (size_t)n * h * w * 64, n, h2, w2, 64, f16 ? 1 : 2, stream));
+  }
   uint16_t* dcols = static_cast<uint16_t*>(m->arena.take((size_t)n * h2 * w2 * 192 * 2));            // ONE fp16 plane (hi plane of gr in)
   B200R_CHECK_ARG(dcols, "activation arena too small");
   RC(b200r_linear(gr, m->stem_wt.p, nullptr, nullptr, nullptr, dcols, nullptr, n * h2 * w2, 64, 192, B200R_ACT_NONE, B200R_PASSES_F16, stream));

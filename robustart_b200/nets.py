@@ -255,8 +255,14 @@ class ResNet:
         n, _, h, w = x01.shape
         P = self.passes
         s0 = self._stem_f32(x01, P)
-        x = ops.maxpool3x3s2(s0)
-        saved = {"shape": (n, h, w), "stem": s0, "blocks": []}
+        if self.f16:
+            x = ops.maxpool3x3s2(s0)
+            saved = {"shape": (n, h, w), "stem": s0, "blocks": []}
+        else:
+            # the pool also leaves its arg-max codes (with the stem ReLU's backward folded in): the gradient pass routes through them and
+            # never reads the 112 x 112 activation again, which is not kept
+            x, codes = ops.maxpool3x3s2_codes(s0)
+            saved = {"shape": (n, h, w), "stem": None, "pool_codes": codes, "stem_hw": (s0.shape[2], s0.shape[3]), "blocks": []}
         for blk in self.blocks:
             idn = blk["down"](x, passes=P) if "down" in blk else x
             if blk["kind"] == "bottleneck":
@@ -316,8 +322,10 @@ class ResNet:
         for i in range(len(self.blocks) - 1, -1, -1):
             in_mask = saved["blocks"][i - 1][-1] if i > 0 else None     # block input = previous block's output
             g = self.block_backward(self.blocks[i], saved["blocks"][i], g, P, in_mask=in_mask, g_is_masked=True)
-        s0 = saved["stem"]
-        g = ops.maxpool3x3s2_relu_bwd_hi(s0, g)          # max-pool and stem-ReLU backward in one pass, one fp16 plane out
+        if saved.get("pool_codes") is not None:
+            g = ops.maxpool3x3s2_bwd_codes_hi(saved["pool_codes"], g, *saved["stem_hw"])
+        else:
+            g = ops.maxpool3x3s2_relu_bwd_hi(saved["stem"], g)   # max-pool and stem-ReLU backward in one pass, one fp16 plane out
         dcols = ops.linear(g.view(1, -1, 64), self._stem_wt, passes=ops.PASSES_F16)          # -> [1, n*ho*wo, 192]
         return ops.stem_col2im(dcols, n, h, w, unscale=1.0 / S)
 

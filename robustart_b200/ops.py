@@ -629,6 +629,33 @@ def maxpool3x3s2_bwd(x, dy):
     return dx
 
 
+def maxpool3x3s2_codes(x):
+    """MaxPool(3,2,1) of post-ReLU split planes that also returns the arg-max codes (uint8 [n,ho,wo,c]; 0xF = nothing to route: the
+    ReLU's backward folded in) for maxpool3x3s2_bwd_codes_hi."""
+    _need_cuda(x, torch.int16, "x")
+    P, n, h, w, c = x.shape
+    if P != 2:
+        raise ValueError("maxpool3x3s2_codes takes split planes")
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = torch.empty((2, n, ho, wo, c), dtype=torch.int16, device=x.device)
+    codes = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_maxpool3x3s2_nhwc_codes(x.data_ptr(), out.data_ptr(), codes.data_ptr(), n, h, w, c, _stream()))
+    return out, codes
+
+
+def maxpool3x3s2_bwd_codes_hi(codes, dy, h, w):
+    """Routes dy planes [P,n,ho,wo,c] back through the codes of maxpool3x3s2_codes: ONE fp16 plane [1,n,h,w,c]."""
+    _need_cuda(dy, torch.int16, "dy")
+    P, n, ho, wo, c = dy.shape
+    if codes.dtype != torch.uint8 or tuple(codes.shape) != (n, ho, wo, c) or ho != (h - 1) // 2 + 1 or wo != (w - 1) // 2 + 1:
+        raise ValueError("maxpool3x3s2_bwd_codes_hi: codes must be the uint8 [n, ho, wo, c] tensor of the forward pool of an h x w input")
+    dx = torch.empty((1, n, h, w, c), dtype=torch.int16, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().b200r_maxpool3x3s2_bwd_codes_hi(codes.data_ptr(), dy.data_ptr(), dx.data_ptr(), n, h, w, c, P, _stream()))
+    return dx
+
+
 def maxpool3x3s2_relu_bwd_hi(x, dy):
     """MaxPool(3,2,1) backward with the backward of the ReLU that produced x fused in; ONE fp16 plane [1,n,h,w,c] out (the stem's
     gradient GEMM reads a single plane).  x: the pool's forward input planes [P,n,h,w,c]; dy planes [P,n,ho,wo,c]."""

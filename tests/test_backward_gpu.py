@@ -177,10 +177,14 @@ def test_stem_backward_strict(cuda):
     torch.manual_seed(6)
     x = torch.rand(2, 3, 224, 224, device=cuda)
     logits, saved = net.forward_saved(x)
-    s0 = saved["stem"]
     g = _planes(torch.randn(2, 64, 56, 56, device=cuda))
     net.input_grad(torch.zeros_like(logits), saved)                       # builds the transposed stem weights
-    gm = ops.relu_bwd(ops.maxpool3x3s2_bwd(s0, g), s0)
+    # the saved forward keeps the pool's arg-max codes (stem ReLU folded in), not the 112 x 112 activation
+    assert saved["stem"] is None and saved["pool_codes"].shape == (2, 56, 56, 64)
+    gm = ops.maxpool3x3s2_bwd_codes_hi(saved["pool_codes"], g, 112, 112)
+    s0 = net._stem_f32(x, net.passes)
+    two = ops.from_planes(ops.relu_bwd(ops.maxpool3x3s2_bwd(s0, g), s0))
+    assert (ops.from_planes(gm) - two).abs().max().item() <= 2 ** -10 * two.abs().max().item()
     # the stem GEMM's gradient runs on single fp16 planes (hi plane of the masked gradient x fp16 weights): its [n*112*112, 192] output
     # is the largest tensor of the pass and only feeds col2im
     got = ops.stem_col2im(ops.linear(gm[:1].view(1, -1, 64), net._stem_wt, passes=ops.PASSES_F16), 2, 224, 224)
@@ -273,3 +277,19 @@ def test_dgrad_3x3_stride2_by_parity_classes(cuda, n, ho, wo, cin, cout, with_re
     assert (got - ref).abs().max().item() < 2e-5 * scale
     old = ops.from_planes(ops.conv2d_dgrad(ops.dilate2(dyp), ops.to_planes(wflip.contiguous()), rp, ap, pad=1)).double()
     assert (got - old).abs().max().item() < 2e-5 * scale
+
+
+def test_maxpool_codes_forward_and_backward(cuda):
+    """b200r_maxpool3x3s2_nhwc_codes + b200r_maxpool3x3s2_bwd_codes_hi (codes written by the forward pool of the attack path's saved
+    forward) = the plain pool and the fused two-pass backward, bit for bit."""
+    from robustart_b200 import ops
+    torch.manual_seed(3)
+    x = torch.relu(torch.randn(3, 20, 28, 64, device=cuda))
+    x[1, 4:9] = 0.0
+    dy = torch.randn(3, 10, 14, 64, device=cuda)
+    xp, dyp = ops.to_planes(x), ops.to_planes(dy)
+    y, codes = ops.maxpool3x3s2_codes(xp)
+    assert torch.equal(y, ops.maxpool3x3s2(xp))
+    assert codes.dtype == torch.uint8 and ((codes <= 8) | (codes == 15)).all()
+    got = ops.maxpool3x3s2_bwd_codes_hi(codes, dyp, 20, 28)
+    assert torch.equal(got, ops.maxpool3x3s2_relu_bwd_hi(xp, dyp))

@@ -91,9 +91,26 @@ HostTable make_nearest(int in_size, int out_size) {
 }
 
 struct DevTable { const int* xmin; const int* xcnt; const int* coef; int ksize; };
-struct Entry { DevTable d; std::vector<int> xmin, xcnt; };            // host copy of the bounds: source range of an output window
+struct Entry { DevTable d; std::vector<int> xmin, xcnt; uint64_t last_use = 0; };   // host copy of the bounds: source range of an output window
 std::map<std::tuple<int, int, int, int>, Entry> g_tables;            // (device, in, out, filter)
 std::mutex g_mu;
+uint64_t g_tick = 0;
+// A file-backed run resizes every image at its native size: thousands of distinct (in, out) pairs.  The cache is bounded: beyond
+// kMaxTables entries the least recently used one is freed (after a device synchronise -- a kernel may still read it), never one of the
+// last 16 looked up (a resize call holds two tables at a time).
+constexpr size_t kMaxTables = 512;
+
+void evict_lru_locked() {
+  auto victim = g_tables.end();
+  for (auto it = g_tables.begin(); it != g_tables.end(); ++it)
+    if (it->second.last_use + 16 < g_tick && (victim == g_tables.end() || it->second.last_use < victim->second.last_use)) victim = it;
+  if (victim == g_tables.end()) return;
+  cudaDeviceSynchronize();
+  cudaFree(const_cast<int*>(victim->second.d.xmin));
+  cudaFree(const_cast<int*>(victim->second.d.xcnt));
+  cudaFree(const_cast<int*>(victim->second.d.coef));
+  g_tables.erase(victim);
+}
 
 int get_table(int in_size, int out_size, int filter, const Entry** out) {
   int dev = 0;
@@ -101,7 +118,8 @@ int get_table(int in_size, int out_size, int filter, const Entry** out) {
   std::lock_guard<std::mutex> lk(g_mu);
   const auto key = std::make_tuple(dev, in_size, out_size, filter);
   auto it = g_tables.find(key);
-  if (it == g_tables.end()) {      // first use: blocking upload (not capturable), kept for the life of the process
+  if (it == g_tables.end()) {      // first use: blocking upload (not capturable)
+    if (g_tables.size() >= kMaxTables) evict_lru_locked();
     const HostTable t = filter == 0 ? make_nearest(in_size, out_size) : make_table(in_size, out_size, filter);
     int *dx, *dc, *dk;
     B200R_CUDA(cudaMalloc(&dx, t.xmin.size() * 4));
@@ -113,6 +131,7 @@ int get_table(int in_size, int out_size, int filter, const Entry** out) {
     Entry e{DevTable{dx, dc, dk, t.ksize}, t.xmin, t.xcnt};
     it = g_tables.emplace(key, std::move(e)).first;
   }
+  it->second.last_use = ++g_tick;
   *out = &it->second;
   return B200R_OK;
 }

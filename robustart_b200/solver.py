@@ -273,6 +273,9 @@ class EvalSolver:
             self.dataset = SyntheticImageNet(n_items, self.input_size, self.device, raw_size=data.get("raw_size"),
                                              test_resize=int(data.get("test_resize", 256)))
         self.indices = shard_indices(n_items, self.dist.world_size, self.dist.rank)
+        # RNG stream of an image = its POSITION in the epoch's permutation (this rank's slice starts at rank * ceil(N / W)): unique per
+        # image, and the same whatever the batch size or the number of ranks -- any sharding corrupts an image with the same noise
+        self.stream_base = int(math.ceil(n_items * 1.0 / self.dist.world_size)) * self.dist.rank
         self.result_path = os.path.join(config.get("save_path", "."), prefix, "results")
         if self.dist.rank == 0:
             os.makedirs(self.result_path, exist_ok=True)
@@ -313,7 +316,7 @@ class EvalSolver:
         for imgs, labels in self._batches():
             n = imgs.shape[0]
             if corruption is not None:
-                ops.corrupt_u8(imgs, corruption, severity, seed=anu._seed(), image_offset=int(self.indices[done]), out=imgs)
+                ops.corrupt_u8(imgs, corruption, severity, seed=anu._seed(), image_offset=self.stream_base + done, out=imgs)
             logits = model(imgs)
             if writer is None:
                 ops.topk_count_(counters, logits, labels)
@@ -366,7 +369,7 @@ class EvalSolver:
                 if (t, s) in skipped:
                     continue
                 try:
-                    ops.corrupt_u8(imgs, t, s, seed=anu._seed(), image_offset=int(self.indices[done]), out=work)
+                    ops.corrupt_u8(imgs, t, s, seed=anu._seed(), image_offset=self.stream_base + done, out=work)
                 except NotImplementedError as e:                 # a cell without a kernel yet is reported, not faked
                     skipped[(t, s)] = str(e)
                     continue

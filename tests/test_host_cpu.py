@@ -255,3 +255,20 @@ def test_missing_checkpoint_raises(tmp_path):
         S.load_checkpoint(str(tmp_path / "nope.pth.tar"))
     torch.save({"model": {"a": torch.ones(2)}}, tmp_path / "ok.pth.tar")
     assert "model" in S.load_checkpoint(str(tmp_path / "ok.pth.tar"))
+
+
+def test_noise_stream_ids_are_positions_in_the_permutation():
+    """solver.stream_base + position: every image gets a unique RNG stream that does not depend on the number of ranks (ADVICE r1:
+    permuted shard indices used as contiguous offsets let different images share a Philox stream)."""
+    import math
+    from robustart_b200.solver import shard_indices
+    n, ref = 103, None
+    for world in (1, 2, 3, 8):
+        seen = {}
+        for r in range(world):
+            base = int(math.ceil(n / world)) * r
+            for j, i in enumerate(shard_indices(n, world, r).tolist()):
+                seen[i] = base + j
+        assert sorted(seen.values()) == list(range(n))
+        assert ref is None or seen == ref
+        ref = seen

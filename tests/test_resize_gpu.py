@@ -60,3 +60,17 @@ def test_eval_transform_and_imagenet_s_plugin(cuda, tmp_path):
     gen.set_config(decoder_type="ffmpeg")            # the one decoder without an implementation fails loudly
     with pytest.raises(NotImplementedError):
         gen.add_noise(path)
+
+
+def test_resize_table_cache_is_bounded(cuda):
+    """More distinct (in, out) size pairs than the coefficient-table cache holds (a file-backed run resizes every image at its native
+    size): old entries are evicted and rebuilt on demand, results unchanged."""
+    from robustart_b200 import ops
+    torch.manual_seed(0)
+    first = torch.randint(0, 256, (1, 9, 8, 3), dtype=torch.uint8, device=cuda)
+    want = ops.resize_u8(first, (5, 4), "bilinear").clone()
+    for i in range(560):                                  # 560 new widths -> 560 new horizontal tables (+ the shared vertical one)
+        img = torch.randint(0, 256, (1, 9, 10 + i, 3), dtype=torch.uint8, device=cuda)
+        out = ops.resize_u8(img, (5, 4), "bilinear")
+        assert out.shape == (1, 5, 4, 3)
+    assert torch.equal(ops.resize_u8(first, (5, 4), "bilinear"), want)

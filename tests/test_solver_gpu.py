@@ -32,6 +32,11 @@ def test_cls_solver_clean_and_imagenet_c(cuda, tmp_path, monkeypatch):
     m1 = cls.main(["--config", cfg, "--evaluate", "--corruption", "gaussian_noise", "--severity", "5"])
     assert m1["count"] == 96
     assert json.load(open(tmp_path / "results" / "noise-gaussian_noise-5-results.metrics.json")) == m1
+    # an image's noise stream is its position in the epoch permutation: another batch size corrupts every image identically
+    anu.reseed(7)
+    (tmp_path / "b48").mkdir()
+    m2 = cls.main(["--config", _cfg(tmp_path / "b48", bs=48), "--evaluate", "--corruption", "gaussian_noise", "--severity", "5"])
+    assert (m2["top1"], m2["top5"], m2["count"]) == (m1["top1"], m1["top5"], m1["count"])
     # same counters as doing it by hand through the kernel ops
     from robustart_b200 import nets, ops, solver as S
     model = nets.build_model("resnet18", device=cuda)

@@ -58,7 +58,10 @@ struct Arena {
 
 }  // namespace
 
+struct VitNet;                 // ViT-B/16 (vision_transformer.py): defined below, owned by the handle
+
 struct b200r_model {
+  VitNet* vit = nullptr;
   int arch = 0, passes = 3, planes = 2, classes = 1000, feat = 512;
   bool f16 = false;
   std::vector<Block> blocks;
@@ -198,7 +201,9 @@ uint16_t* take_planes(b200r_model* m, size_t count) { return static_cast<uint16_
   if (!ptr) { b200r_set_error("activation arena too small: call b200r_model_reserve with this batch / image size first"); return B200R_EINVAL; }
 #define RC(call) { int rc__ = (call); if (rc__) return rc__; }
 
+size_t vit_arena_need(const b200r_model* m, int n, bool save);
 size_t arena_need(const b200r_model* m, int n, int h, int w, bool save) {
+  if (m->vit) return vit_arena_need(m, n, save);
   // elements per input pixel, bounded from above by a closed form.  Inference: two halves, each the largest block footprint
   // (ResNet-50 layer1.0: 56^2 x (256 + 256 + 64 + 64) = 40 per pixel; the stem: 112^2 x 64 + 56^2 x 64 = 20).  Saved forward +
   // gradient pass: every activation (ResNet-50: ~220 per pixel) + the gradient pass's own tensors (~280, of which 48 for the stem
@@ -263,14 +268,261 @@ int run_body(b200r_model* m, uint16_t* x, int n, int h, int w, float* logits, bo
   return B200R_OK;
 }
 
+// ---- ViT-B/16 (prototype/prototype/model/vision_transformer.py:44-349): the launch sequence of nets.ViT --------------------------
+struct Lin { Planes w, wt; float* b = nullptr; int k = 0, nout = 0; };      // nn.Linear: w [nout][k], wt [k][nout] for the input gradient
+struct VitBlock { float *n1w, *n1b, *n2w, *n2b; Lin qkv, out, m1, m2; };
+struct VitSaved { uint16_t *x_in, *qkv, *x_mid, *pre; };
+}  // namespace
+struct VitNet {
+  int depth = 12, dim = 768, heads = 12, patch = 16, hidden = 3072, tokens = 197, rep = 768;
+  Lin embed, head, pre;
+  bool has_pre = false;
+  float *cls = nullptr, *pos = nullptr, *normw = nullptr, *normb = nullptr;
+  std::vector<VitBlock> blocks;
+  std::vector<VitSaved> saved;
+  uint16_t *final_x = nullptr, *pre_logits = nullptr;
+  int n = 0, h = 0, w = 0;
+  bool valid = false;
+};
+namespace {
+
+int make_lin(b200r_model* m, const Weights& W, const std::string& name, int nout, int k, Lin* out) {
+  const float *w, *b;
+  int rc;
+  if ((rc = get(W, name + ".weight", (int64_t)nout * k, &w)) || (rc = get(W, name + ".bias", nout, &b))) return rc;
+  std::vector<float> wv(w, w + (size_t)nout * k), wt(wv.size()), bv(b, b + nout);
+  for (int o = 0; o < nout; ++o)
+    for (int j = 0; j < k; ++j) wt[(size_t)j * nout + o] = planes_value(wv[(size_t)o * k + j], 2);   // transpose of the value the planes hold
+  out->k = k; out->nout = nout;
+  if ((rc = upload_planes(m, wv, &out->w)) || (rc = upload_planes(m, wt, &out->wt)) || (rc = upload_f32(m, bv, &out->b))) return rc;
+  return B200R_OK;
+}
+int upload_vec(b200r_model* m, const Weights& W, const std::string& key, int64_t numel, float** out) {
+  const float* v;
+  int rc = get(W, key, numel, &v);
+  if (rc) return rc;
+  return upload_f32(m, std::vector<float>(v, v + numel), out);
+}
+
+int vit_create(b200r_model* m, const Weights& W) {
+  VitNet* v = new VitNet();
+  m->vit = v;
+  const int D = v->dim, P = v->patch;
+  int rc;
+  auto pw = W.find("pos_embedding");
+  B200R_CHECK_ARG(pw != W.end() && pw->second.second % D == 0, "state_dict tensor 'pos_embedding' is missing or not a multiple of %d", D);
+  v->tokens = (int)(pw->second.second / D);
+  if ((rc = make_lin(m, W, "embedding", D, 3 * P * P, &v->embed)) ||                 // conv weight [D, 3, P, P] == Linear over (c, ky, kx)
+      (rc = upload_vec(m, W, "cls_token", D, &v->cls)) || (rc = upload_vec(m, W, "pos_embedding", (int64_t)v->tokens * D, &v->pos)))
+    return rc;
+  v->blocks.resize(v->depth);
+  for (int d = 0; d < v->depth; ++d) {
+    const std::string p = "transformer.encoders.encoder_" + std::to_string(d) + ".";
+    VitBlock& b = v->blocks[d];
+    if ((rc = upload_vec(m, W, p + "norm1.weight", D, &b.n1w)) || (rc = upload_vec(m, W, p + "norm1.bias", D, &b.n1b)) ||
+        (rc = upload_vec(m, W, p + "norm2.weight", D, &b.n2w)) || (rc = upload_vec(m, W, p + "norm2.bias", D, &b.n2b)) ||
+        (rc = make_lin(m, W, p + "attention.to_qkv", 3 * D, D, &b.qkv)) || (rc = make_lin(m, W, p + "attention.to_out", D, D, &b.out)) ||
+        (rc = make_lin(m, W, p + "feedforward.mlp1", v->hidden, D, &b.m1)) || (rc = make_lin(m, W, p + "feedforward.mlp2", D, v->hidden, &b.m2)))
+      return rc;
+  }
+  if ((rc = upload_vec(m, W, "transformer.encoder_norm.weight", D, &v->normw)) || (rc = upload_vec(m, W, "transformer.encoder_norm.bias", D, &v->normb)))
+    return rc;
+  v->has_pre = W.count("pre_logits.weight") != 0;
+  if (v->has_pre) {
+    v->rep = (int)(W.at("pre_logits.weight").second / D);
+    if ((rc = make_lin(m, W, "pre_logits", v->rep, D, &v->pre))) return rc;
+  }
+  auto hw = W.find("head.weight");
+  B200R_CHECK_ARG(hw != W.end(), "state_dict tensor 'head.weight' is missing");
+  m->classes = (int)(hw->second.second / v->rep);
+  return make_lin(m, W, "head", m->classes, v->rep, &v->head);
+}
+
+size_t vit_arena_need(const b200r_model* m, int n, bool save) {
+  const VitNet* v = m->vit;
+  const double tok = (double)n * v->tokens;
+  // planes elements per token: saved forward keeps (x_in, qkv, x_mid, pre) = 7 D + hidden per block plus ln / attention / act outputs;
+  // the gradient pass adds ~3 (D + hidden) of temporaries per block.  Inference: one block's worth, twice.
+  const double per_tok = save ? v->depth * (8.0 * v->dim + 2.0 * v->hidden) + 4.0 * v->hidden + 16.0 * v->dim : 2.0 * (10.0 * v->dim + 2.0 * v->hidden);
+  return (size_t)(per_tok * tok * 4.0) + (size_t)n * 3 * 224 * 224 * 8 + (64u << 20);
+}
+
+int lin_fwd(const Lin& l, const uint16_t* x, const uint16_t* res, uint16_t* y, float* y_f32, int rows, int act, int passes, b200r_stream_t st) {
+  return b200r_linear(x, l.w.p, nullptr, l.b, res, y, y_f32, rows, l.k, l.nout, act, passes, st);
+}
+int lin_dgrad(const Lin& l, const uint16_t* g, uint16_t* dx, int rows, int passes, b200r_stream_t st) {
+  return b200r_linear(g, l.wt.p, nullptr, nullptr, nullptr, dx, nullptr, rows, l.nout, l.k, B200R_ACT_NONE, passes, st);
+}
+// rows [first, first + count) of every image's token block: planes [2][n][T][D] -> planes [2][n][count][D] (class token / patch tokens)
+int token_rows(const uint16_t* x, uint16_t* y, int n, int T, int D, int first, int count, bool scatter, cudaStream_t s) {
+  for (int p = 0; p < 2; ++p) {
+    const uint16_t* src = x + (size_t)p * n * (scatter ? count : T) * D + (scatter ? 0 : (size_t)first * D);
+    uint16_t* dst = y + (size_t)p * n * (scatter ? T : count) * D + (scatter ? (size_t)first * D : 0);
+    B200R_CUDA(cudaMemcpy2DAsync(dst, (size_t)(scatter ? T : count) * D * 2, src, (size_t)(scatter ? count : T) * D * 2, (size_t)count * D * 2, n,
+                                 cudaMemcpyDeviceToDevice, s));
+  }
+  return B200R_OK;
+}
+
+// save == false: the inference sequence of nets.ViT.forward (fused GELU); save == true: nets.ViT.forward_saved
+int vit_forward(b200r_model* m, const void* images, bool u8, float* logits, int n, int h, int w, bool save, cudaStream_t s) {
+  VitNet* v = m->vit;
+  const b200r_stream_t st = reinterpret_cast<b200r_stream_t>(s);
+  const int D = v->dim, P = m->passes, pp = v->patch, np = (h / pp) * (w / pp), T = np + 1, hd = D / v->heads;
+  B200R_CHECK_ARG(T == v->tokens, "ViT: %d x %d images give %d tokens, the position embedding has %d", h, w, T, v->tokens);
+  B200R_CHECK_ARG(m->planes == 2, "ViT handles run in split precision (passes = 3)");
+  const float scale = 1.0f / sqrtf((float)hd);
+  m->arena.reset();
+  const int rows = n * T;
+  TAKE(cols, (size_t)n * np * 3 * pp * pp);
+  RC(u8 ? b200r_patch_gather_u8(static_cast<const uint8_t*>(images), cols, n, h, w, pp, kMean, kStd, st)
+        : b200r_patch_gather_f32(static_cast<const float*>(images), cols, n, h, w, pp, kMean, kStd, st));
+  TAKE(emb, (size_t)n * np * D);
+  RC(lin_fwd(v->embed, cols, nullptr, emb, nullptr, n * np, B200R_ACT_NONE, P, st));
+  TAKE(x0, (size_t)rows * D);
+  RC(b200r_assemble_tokens(emb, v->cls, v->pos, x0, n, np, D, st));
+  uint16_t* x = x0;
+  if (save) { v->saved.clear(); v->valid = false; }
+  // inference: two x buffers alternate, every block reuses the same scratch behind them
+  uint16_t* xalt = nullptr;
+  size_t scratch_mark = 0;
+  if (!save) {
+    xalt = take_planes(m, (size_t)rows * D);
+    B200R_CHECK_ARG(xalt, "activation arena too small");
+    scratch_mark = m->arena.off;
+  }
+  for (const VitBlock& b : v->blocks) {
+    if (!save) m->arena.off = scratch_mark;
+    TAKE(y1, (size_t)rows * D);
+    RC(b200r_layernorm(x, y1, b.n1w, b.n1b, rows, D, 1e-5f, st));
+    TAKE(qkv, (size_t)rows * 3 * D);
+    RC(lin_fwd(b.qkv, y1, nullptr, qkv, nullptr, rows, B200R_ACT_NONE, P, st));
+    TAKE(att, (size_t)rows * D);
+    RC(b200r_attention(qkv, att, n, T, v->heads, hd, scale, st));
+    TAKE(x_mid, (size_t)rows * D);
+    RC(lin_fwd(b.out, att, x, x_mid, nullptr, rows, B200R_ACT_NONE, P, st));            // x_mid = attn(norm1(x)) + x
+    TAKE(y2, (size_t)rows * D);
+    RC(b200r_layernorm(x_mid, y2, b.n2w, b.n2b, rows, D, 1e-5f, st));
+    TAKE(hbuf, (size_t)rows * v->hidden);
+    uint16_t* xn;
+    if (save) {
+      RC(lin_fwd(b.m1, y2, nullptr, hbuf, nullptr, rows, B200R_ACT_NONE, P, st));       // the pre-activation is kept
+      TAKE(act, (size_t)rows * v->hidden);
+      RC(b200r_act_planes(hbuf, act, (size_t)rows * v->hidden, B200R_ACT_GELU_TANH, st));
+      TAKE(xo, (size_t)rows * D);
+      RC(lin_fwd(b.m2, act, x_mid, xo, nullptr, rows, B200R_ACT_NONE, P, st));
+      v->saved.push_back({x, qkv, x_mid, hbuf});
+      xn = xo;
+    } else {
+      RC(lin_fwd(b.m1, y2, nullptr, hbuf, nullptr, rows, B200R_ACT_GELU_TANH, P, st));  // tanh-approximation GELU (:19-37) in the epilogue
+      xn = (x == x0) ? xalt : x0;
+      RC(lin_fwd(b.m2, hbuf, x_mid, xn, nullptr, rows, B200R_ACT_NONE, P, st));
+    }
+    x = xn;
+  }
+  if (!save) m->arena.off = scratch_mark;
+  TAKE(xn, (size_t)rows * D);
+  RC(b200r_layernorm(x, xn, v->normw, v->normb, rows, D, 1e-5f, st));
+  TAKE(cls, (size_t)n * D);
+  RC(token_rows(xn, cls, n, T, D, 0, 1, false, s));                                      // x[:, 0]
+  const uint16_t* feat = cls;
+  v->pre_logits = nullptr;
+  if (v->has_pre) {
+    TAKE(pl, (size_t)n * v->rep);
+    if (save) {
+      RC(lin_fwd(v->pre, cls, nullptr, pl, nullptr, n, B200R_ACT_NONE, P, st));
+      TAKE(pa, (size_t)n * v->rep);
+      RC(b200r_act_planes(pl, pa, (size_t)n * v->rep, B200R_ACT_TANH, st));
+      v->pre_logits = pl;
+      feat = pa;
+    } else {
+      RC(lin_fwd(v->pre, cls, nullptr, pl, nullptr, n, B200R_ACT_TANH, P, st));
+      feat = pl;
+    }
+  }
+  RC(lin_fwd(v->head, feat, nullptr, nullptr, logits, n, B200R_ACT_NONE, P, st));
+  if (save) { v->final_x = x; v->n = n; v->h = h; v->w = w; v->valid = true; }
+  return B200R_OK;
+}
+
+int vit_input_grad(b200r_model* m, const float* dlogits, float* dx, cudaStream_t s) {
+  VitNet* v = m->vit;
+  B200R_CHECK_ARG(v->valid, "input_grad needs the activations of a preceding b200r_model_forward_f32 on this handle");
+  const b200r_stream_t st = reinterpret_cast<b200r_stream_t>(s);
+  const int D = v->dim, P = m->passes, n = v->n, T = v->tokens, rows = n * T, hd = D / v->heads;
+  const float scale = 1.0f / sqrtf((float)hd);
+  TAKE(g0, (size_t)n * m->classes);
+  RC(b200r_split_f32_scaled(dlogits, g0, (size_t)n * m->classes, kGradScale, st));
+  TAKE(g1, (size_t)n * v->rep);
+  RC(lin_dgrad(v->head, g0, g1, n, P, st));
+  uint16_t* gc = g1;
+  if (v->has_pre) {
+    TAKE(g2, (size_t)n * v->rep);
+    RC(b200r_act_bwd_planes(g1, v->pre_logits, g2, (size_t)n * v->rep, B200R_ACT_TANH, st));
+    TAKE(g3, (size_t)n * D);
+    RC(lin_dgrad(v->pre, g2, g3, n, P, st));
+    gc = g3;
+  }
+  // encoder_norm only feeds x[:, 0]: LayerNorm is row-wise, so its backward runs on the class rows alone
+  TAKE(xcls, (size_t)n * D);
+  RC(token_rows(v->final_x, xcls, n, T, D, 0, 1, false, s));
+  TAKE(gcls, (size_t)n * D);
+  RC(b200r_layernorm_bwd(gc, xcls, v->normw, nullptr, gcls, n, D, 1e-5f, st));
+  TAKE(g, (size_t)rows * D);
+  B200R_CUDA(cudaMemsetAsync(g, 0, (size_t)rows * D * 4, s));
+  RC(token_rows(gcls, g, n, T, D, 0, 1, true, s));
+  size_t ws_bytes = 0;
+  RC(b200r_attention_bwd_workspace_bytes(n, T, v->heads, &ws_bytes));
+  void* ws = m->arena.take(ws_bytes + 256);
+  B200R_CHECK_ARG(ws, "activation arena too small");
+  const size_t mark = m->arena.off;
+  uint16_t* gbuf[2] = {g, nullptr};
+  gbuf[1] = take_planes(m, (size_t)rows * D);
+  B200R_CHECK_ARG(gbuf[1], "activation arena too small");
+  const size_t mark2 = m->arena.off;
+  (void)mark;
+  int cur = 0;
+  for (int d = v->depth - 1; d >= 0; --d) {
+    const VitBlock& b = v->blocks[d];
+    const VitSaved& sv = v->saved[d];
+    m->arena.off = mark2;
+    TAKE(t1, (size_t)rows * v->hidden);
+    RC(lin_dgrad(b.m2, gbuf[cur], t1, rows, P, st));
+    TAKE(t2, (size_t)rows * v->hidden);
+    RC(b200r_act_bwd_planes(t1, sv.pre, t2, (size_t)rows * v->hidden, B200R_ACT_GELU_TANH, st));
+    TAKE(t3, (size_t)rows * D);
+    RC(lin_dgrad(b.m1, t2, t3, rows, P, st));
+    TAKE(gm, (size_t)rows * D);
+    RC(b200r_layernorm_bwd(t3, sv.x_mid, b.n2w, gbuf[cur], gm, rows, D, 1e-5f, st));       // x = x_mid + mlp(norm2(x_mid))
+    TAKE(t4, (size_t)rows * D);
+    RC(lin_dgrad(b.out, gm, t4, rows, P, st));
+    TAKE(t5, (size_t)rows * 3 * D);
+    RC(b200r_attention_bwd_ws(sv.qkv, t4, t5, ws, ws_bytes, n, T, v->heads, hd, scale, st));
+    TAKE(t6, (size_t)rows * D);
+    RC(lin_dgrad(b.qkv, t5, t6, rows, P, st));
+    RC(b200r_layernorm_bwd(t6, sv.x_in, b.n1w, gm, gbuf[cur ^ 1], rows, D, 1e-5f, st));    // x_mid = x_in + attn(norm1(x_in))
+    cur ^= 1;
+  }
+  m->arena.off = mark2;
+  const int np = T - 1;
+  TAKE(gp, (size_t)n * np * D);
+  RC(token_rows(gbuf[cur], gp, n, T, D, 1, np, false, s));                                 // drop the class token
+  TAKE(dcols, (size_t)n * np * v->embed.k);
+  RC(lin_dgrad(v->embed, gp, dcols, n * np, P, st));
+  float stdu[3];
+  for (int i = 0; i < 3; ++i) stdu[i] = kStd[i] * kGradScale;                              // 1/S rides on the 1/std of the scatter
+  return b200r_patch_scatter_f32(dcols, dx, n, v->h, v->w, v->patch, stdu, st);
+}
+
 }  // namespace
 
 extern "C" {
 
 int b200r_model_create(int arch, const b200r_weight* weights, int n_weights, int passes, b200r_model** out) {
   B200R_CHECK_ARG(out && weights && n_weights > 0, "null argument");
-  B200R_CHECK_ARG(arch >= B200R_ARCH_RESNET18 && arch <= B200R_ARCH_RESNET101, "arch %d: the handle API covers the ResNet family (0..3)", arch);
-  B200R_CHECK_ARG(passes == 3 || passes == B200R_PASSES_F16, "passes must be 3 (split planes, fp32-faithful) or B200R_PASSES_F16");
+  B200R_CHECK_ARG(arch >= B200R_ARCH_RESNET18 && arch <= B200R_ARCH_VIT_B16, "arch %d: the handle API covers the ResNet family (0..3) and ViT-B/16 (4)", arch);
+  B200R_CHECK_ARG(passes == 3 || (passes == B200R_PASSES_F16 && arch != B200R_ARCH_VIT_B16),
+                  "passes must be 3 (split planes, fp32-faithful) or, for the ResNets, B200R_PASSES_F16");
   static const int kLayers[4][4] = {{2, 2, 2, 2}, {3, 4, 6, 3}, {3, 4, 6, 3}, {3, 4, 23, 3}};
   const bool bott = arch >= B200R_ARCH_RESNET50;
   Weights W;
@@ -286,6 +538,11 @@ int b200r_model_create(int arch, const b200r_weight* weights, int n_weights, int
   m->feat = bott ? 2048 : 512;
   int rc = B200R_OK;
   auto fail = [&](int code) { b200r_model_destroy(m); return code; };
+  if (arch == B200R_ARCH_VIT_B16) {
+    if ((rc = vit_create(m, W))) return fail(rc);
+    *out = m;
+    return B200R_OK;
+  }
   // ---- stem ----
   const float* w1;
   if ((rc = get(W, "conv1.weight", 64 * 3 * 7 * 7, &w1))) return fail(rc);
@@ -364,6 +621,7 @@ int b200r_model_destroy(b200r_model* m) {
   if (!m) return B200R_OK;
   for (void* p : m->owned) cudaFree(p);
   if (m->arena.base) cudaFree(m->arena.base);
+  delete m->vit;
   delete m;
   return B200R_OK;
 }
@@ -379,6 +637,7 @@ int b200r_model_forward_u8(b200r_model* m, const uint8_t* images, float* logits,
   B200R_CHECK_ARG(m && images && logits && n > 0, "bad argument");
   B200R_CHECK_ARG(h % 32 == 0 && w % 32 == 0, "image size must be a multiple of 32 (got %dx%d)", h, w);
   RC(ensure_arena(m, n, h, w, false));
+  if (m->vit) return vit_forward(m, images, true, logits, n, h, w, false, as_stream(stream));
   m->arena.region(1);
   m->saved.valid = false;
   cudaStream_t s = as_stream(stream);
@@ -403,6 +662,7 @@ int b200r_model_forward_f32(b200r_model* m, const float* x01, float* logits, int
   B200R_CHECK_ARG(m && x01 && logits && n > 0, "bad argument");
   B200R_CHECK_ARG(h % 32 == 0 && w % 32 == 0 && w <= 256, "float input: image size must be a multiple of 32 and at most 256 wide (got %dx%d)", h, w);
   RC(ensure_arena(m, n, h, w, true));
+  if (m->vit) return vit_forward(m, x01, false, logits, n, h, w, true, as_stream(stream));
   m->arena.reset();
   cudaStream_t s = as_stream(stream);
   TAKE(s0, (size_t)n * (h / 2) * (w / 2) * 64);
@@ -425,6 +685,7 @@ int b200r_model_forward_f32(b200r_model* m, const float* x01, float* logits, int
 // d loss / d x01 from d loss / d logits and the activations of the last b200r_model_forward_f32
 int b200r_model_input_grad(b200r_model* m, const float* dlogits, float* dx, b200r_stream_t stream) {
   B200R_CHECK_ARG(m && dlogits && dx, "bad argument");
+  if (m->vit) return vit_input_grad(m, dlogits, dx, as_stream(stream));
   B200R_CHECK_ARG(m->saved.valid, "b200r_model_input_grad needs a preceding b200r_model_forward_f32 on this handle");
   const int n = m->saved.n, H = m->saved.h, Wd = m->saved.w, P = m->passes;
   const bool f16 = m->f16;

@@ -147,3 +147,29 @@ def test_allreduce_counts_single_rank_communicator(cuda):
         assert counts.tolist() == [17, 42, 256]
         nccl.ncclCommDestroy.argtypes = [C.c_void_p]
         nccl.ncclCommDestroy(comm)
+
+
+def test_vit_handle_matches_python_sequencing(cuda):
+    """ViT-B/16 behind the C-ABI (b200r_model_create(B200R_ARCH_VIT_B16, ...)): logits from uint8 and float input, and the input
+    gradient, bit-identical to nets.ViT's launch sequence (vision_transformer.py:44-349)."""
+    from robustart_b200 import nets, ops
+    from robustart_b200.handle import ModelHandle
+    sd = nets.random_token_state_dict(nets.vit_spec(), 0)
+    ref = nets.build_model("vit_b16_224", sd, device=cuda)
+    hm = ModelHandle("vit_b16_224", {"module." + k: v for k, v in sd.items()}, cuda, 3)
+    assert hm.num_classes == ref.num_classes
+    images = torch.from_numpy(synth_images(3, seed=5)).to(cuda)
+    assert torch.equal(hm(images), ref(images))
+    x01 = images.permute(0, 3, 1, 2).float().div(255).contiguous()
+    la, vjp = hm.forward_vjp(x01)
+    lb, saved = ref.forward_saved(x01)
+    assert torch.equal(la, lb)
+    _, d = ops.ce_loss_grad(la, torch.tensor([7, 1, 3], device=cuda))
+    ga, gb = vjp(d), ref.input_grad(d, saved)
+    assert torch.isfinite(ga).all() and ga.abs().max().item() > 0
+    assert torch.equal(ga, gb)
+    big = torch.from_numpy(synth_images(5, seed=6)).to(cuda)              # a larger batch re-sizes the arena
+    assert torch.equal(hm(big), ref(big))
+    with pytest.raises(ValueError):
+        hm(torch.zeros(2, 160, 160, 3, dtype=torch.uint8, device=cuda))  # 101 tokens against a 197-row position embedding
+    hm.close()

@@ -512,7 +512,7 @@ int b200r_attention_bwd_ws(const uint16_t* qkv, const uint16_t* dout, uint16_t* 
 /* ------------------------------------------------------------------------------------------
  * Model handles: build a classifier from the reference's state_dict tensors and run it without Python.
  * Replaces model_entry() + nn.Module.forward for the ResNet family (prototype/prototype/model/resnet_official.py:40-140,
- * 221-239,330-346) and ViT-B/16 (vision_transformer.py:44-349), and autograd.grad(loss, x) of the attack loops (autopgd_base.py:371-376; foolbox value_and_grad behind
+ * 221-239,330-346), ViT-B/16 (vision_transformer.py:44-349) and MLP-Mixer-B/16 (vit/mlp_mixer.py:7-159), and autograd.grad(loss, x) of the attack loops (autopgd_base.py:371-376; foolbox value_and_grad behind
  * adv/attack.py:20-33).  The handle owns its device weights and an activation arena; one handle per (process, device);
  * calls on one handle must not overlap.  Every layer is a launch of the entry points above on `stream`; nothing synchronises.
  * ------------------------------------------------------------------------------------------ */
@@ -521,7 +521,10 @@ enum b200r_arch { B200R_ARCH_RESNET18 = 0, B200R_ARCH_RESNET34 = 1, B200R_ARCH_R
                   /* ViT-B/16 (vision_transformer.py:44-349; state_dict keys embedding.*, cls_token, pos_embedding,
                    * transformer.encoders.encoder_<i>.{norm1,norm2,attention.to_qkv,attention.to_out,feedforward.mlp1,feedforward.mlp2}.*,
                    * transformer.encoder_norm.*, [pre_logits.*,] head.*): split precision only */
-                  B200R_ARCH_VIT_B16 = 4 };
+                  B200R_ARCH_VIT_B16 = 4,
+                  /* MLP-Mixer-B/16 (vit/mlp_mixer.py:7-159; keys patch_embed.proj.*, blocks.<i>.{norm1,norm2,token_mix.fc1,token_mix.fc2,
+                   * channel_mix.fc1,channel_mix.fc2}.*, norm.*, head.*): split precision only */
+                  B200R_ARCH_MIXER_B16 = 5 };
 /* one state_dict entry: the reference's key ("layer1.0.conv1.weight", "bn1.running_var", "fc.bias", ...; optional "module." /
  * "base_model." prefixes are stripped, benchmark_eval_adv.py:162-168), HOST float32 data in PyTorch layout, element count */
 typedef struct b200r_weight { const char* name; const float* data; int64_t numel; } b200r_weight;

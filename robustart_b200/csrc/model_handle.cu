@@ -59,9 +59,11 @@ struct Arena {
 }  // namespace
 
 struct VitNet;                 // ViT-B/16 (vision_transformer.py): defined below, owned by the handle
+struct MixerNet;               // MLP-Mixer-B/16 (vit/mlp_mixer.py, vit/vit_base.py)
 
 struct b200r_model {
   VitNet* vit = nullptr;
+  MixerNet* mixer = nullptr;
   int arch = 0, passes = 3, planes = 2, classes = 1000, feat = 512;
   bool f16 = false;
   std::vector<Block> blocks;
@@ -202,8 +204,10 @@ uint16_t* take_planes(b200r_model* m, size_t count) { return static_cast<uint16_
 #define RC(call) { int rc__ = (call); if (rc__) return rc__; }
 
 size_t vit_arena_need(const b200r_model* m, int n, bool save);
+size_t mixer_arena_need(const b200r_model* m, int n, bool save);
 size_t arena_need(const b200r_model* m, int n, int h, int w, bool save) {
   if (m->vit) return vit_arena_need(m, n, save);
+  if (m->mixer) return mixer_arena_need(m, n, save);
   // elements per input pixel, bounded from above by a closed form.  Inference: two halves, each the largest block footprint
   // (ResNet-50 layer1.0: 56^2 x (256 + 256 + 64 + 64) = 40 per pixel; the stem: 112^2 x 64 + 56^2 x 64 = 20).  Saved forward +
   // gradient pass: every activation (ResNet-50: ~220 per pixel) + the gradient pass's own tensors (~280, of which 48 for the stem
@@ -286,11 +290,17 @@ struct VitNet {
 };
 namespace {
 
-int make_lin(b200r_model* m, const Weights& W, const std::string& name, int nout, int k, Lin* out) {
+// k_pad / n_pad: the weight is embedded in a zero [n_pad][k_pad] matrix (Mixer's token dimension padded to 256: 16-byte rows, K % 64)
+int make_lin(b200r_model* m, const Weights& W, const std::string& name, int nout0, int k0, Lin* out, int n_pad = 0, int k_pad = 0) {
   const float *w, *b;
   int rc;
-  if ((rc = get(W, name + ".weight", (int64_t)nout * k, &w)) || (rc = get(W, name + ".bias", nout, &b))) return rc;
-  std::vector<float> wv(w, w + (size_t)nout * k), wt(wv.size()), bv(b, b + nout);
+  if ((rc = get(W, name + ".weight", (int64_t)nout0 * k0, &w)) || (rc = get(W, name + ".bias", nout0, &b))) return rc;
+  const int nout = n_pad ? n_pad : nout0, k = k_pad ? k_pad : k0;
+  std::vector<float> wv((size_t)nout * k, 0.f), wt(wv.size()), bv(nout, 0.f);
+  for (int o = 0; o < nout0; ++o) {
+    bv[o] = b[o];
+    for (int j = 0; j < k0; ++j) wv[(size_t)o * k + j] = w[(size_t)o * k0 + j];
+  }
   for (int o = 0; o < nout; ++o)
     for (int j = 0; j < k; ++j) wt[(size_t)j * nout + o] = planes_value(wv[(size_t)o * k + j], 2);   // transpose of the value the planes hold
   out->k = k; out->nout = nout;
@@ -514,14 +524,194 @@ int vit_input_grad(b200r_model* m, const float* dlogits, float* dx, cudaStream_t
   return b200r_patch_scatter_f32(dcols, dx, n, v->h, v->w, v->patch, stdu, st);
 }
 
+
+// ---- MLP-Mixer-B/16 (vit/mlp_mixer.py:7-159 on vit/vit_base.py): the launch sequence of nets.Mixer ------------------------------
+struct MixBlock { float *n1w, *n1b, *n2w, *n2b; Lin t1, t2, c1, c2; };
+struct MixSaved { uint16_t *x_in, *p1, *x_mid, *p2; };
+}  // namespace
+struct MixerNet {
+  int depth = 12, dim = 768, patch = 16, tokens = 196, tok_hidden = 384, ch_hidden = 3072, t_pad = 256;
+  Lin embed, head;
+  float *normw = nullptr, *normb = nullptr;
+  std::vector<MixBlock> blocks;
+  std::vector<MixSaved> saved;
+  uint16_t* final_x = nullptr;
+  int n = 0, h = 0, w = 0;
+  bool valid = false;
+};
+namespace {
+
+int mixer_create(b200r_model* m, const Weights& W) {
+  MixerNet* v = new MixerNet();
+  m->mixer = v;
+  const int D = v->dim, P = v->patch;
+  int rc;
+  auto f1 = W.find("blocks.0.token_mix.fc1.weight");
+  auto c1 = W.find("blocks.0.channel_mix.fc1.weight");
+  B200R_CHECK_ARG(f1 != W.end() && c1 != W.end(), "state_dict tensors 'blocks.0.token_mix.fc1.weight' / 'blocks.0.channel_mix.fc1.weight' are missing");
+  v->ch_hidden = (int)(c1->second.second / D);
+  auto f1b = W.find("blocks.0.token_mix.fc1.bias");
+  B200R_CHECK_ARG(f1b != W.end(), "state_dict tensor 'blocks.0.token_mix.fc1.bias' is missing");
+  v->tok_hidden = (int)f1b->second.second;
+  v->tokens = (int)(f1->second.second / v->tok_hidden);
+  B200R_CHECK_ARG(v->tokens <= v->t_pad, "Mixer: %d tokens exceed the padded token dimension %d", v->tokens, v->t_pad);
+  if ((rc = make_lin(m, W, "patch_embed.proj", D, 3 * P * P, &v->embed))) return rc;
+  v->blocks.resize(v->depth);
+  for (int d = 0; d < v->depth; ++d) {
+    const std::string p = "blocks." + std::to_string(d) + ".";
+    MixBlock& b = v->blocks[d];
+    if ((rc = upload_vec(m, W, p + "norm1.weight", D, &b.n1w)) || (rc = upload_vec(m, W, p + "norm1.bias", D, &b.n1b)) ||
+        (rc = upload_vec(m, W, p + "norm2.weight", D, &b.n2w)) || (rc = upload_vec(m, W, p + "norm2.bias", D, &b.n2b)) ||
+        (rc = make_lin(m, W, p + "token_mix.fc1", v->tok_hidden, v->tokens, &b.t1, 0, v->t_pad)) ||
+        (rc = make_lin(m, W, p + "token_mix.fc2", v->tokens, v->tok_hidden, &b.t2, v->t_pad, 0)) ||
+        (rc = make_lin(m, W, p + "channel_mix.fc1", v->ch_hidden, D, &b.c1)) || (rc = make_lin(m, W, p + "channel_mix.fc2", D, v->ch_hidden, &b.c2)))
+      return rc;
+  }
+  if ((rc = upload_vec(m, W, "norm.weight", D, &v->normw)) || (rc = upload_vec(m, W, "norm.bias", D, &v->normb))) return rc;
+  auto hw = W.find("head.weight");
+  B200R_CHECK_ARG(hw != W.end(), "state_dict tensor 'head.weight' is missing");
+  m->classes = (int)(hw->second.second / D);
+  return make_lin(m, W, "head", m->classes, D, &v->head);
+}
+
+size_t mixer_arena_need(const b200r_model* m, int n, bool save) {
+  const MixerNet* v = m->mixer;
+  // planes elements per image and block: token side D (t_pad + tok_hidden) x 2-3, channel side T (ch_hidden x 2 + D x 4)
+  const double tokside = (double)v->dim * (3.0 * v->t_pad + 3.0 * v->tok_hidden), chside = (double)v->tokens * (3.0 * v->ch_hidden + 8.0 * v->dim);
+  const double per_img = save ? v->depth * (tokside + chside) + 2.0 * (tokside + chside) : 2.0 * (tokside + chside);
+  return (size_t)(per_img * n * 4.0) + (size_t)n * 3 * 224 * 224 * 8 + (64u << 20);
+}
+
+int mixer_forward(b200r_model* m, const void* images, bool u8, float* logits, int n, int h, int w, bool save, cudaStream_t s) {
+  MixerNet* v = m->mixer;
+  const b200r_stream_t st = reinterpret_cast<b200r_stream_t>(s);
+  const int D = v->dim, P = m->passes, pp = v->patch, T = (h / pp) * (w / pp), TP = v->t_pad;
+  B200R_CHECK_ARG(T == v->tokens, "Mixer: %d x %d images give %d tokens, the token-mixing MLP has %d", h, w, T, v->tokens);
+  B200R_CHECK_ARG(m->planes == 2, "Mixer handles run in split precision (passes = 3)");
+  m->arena.reset();
+  const int rows = n * T, crow = n * D;
+  TAKE(cols, (size_t)rows * 3 * pp * pp);
+  RC(u8 ? b200r_patch_gather_u8(static_cast<const uint8_t*>(images), cols, n, h, w, pp, kMean, kStd, st)
+        : b200r_patch_gather_f32(static_cast<const float*>(images), cols, n, h, w, pp, kMean, kStd, st));
+  TAKE(x0, (size_t)rows * D);
+  RC(lin_fwd(v->embed, cols, nullptr, x0, nullptr, rows, B200R_ACT_NONE, P, st));
+  uint16_t* x = x0;
+  if (save) { v->saved.clear(); v->valid = false; }
+  uint16_t* xalt = nullptr;
+  size_t mark = 0;
+  if (!save) {
+    xalt = take_planes(m, (size_t)rows * D);
+    B200R_CHECK_ARG(xalt, "activation arena too small");
+    mark = m->arena.off;
+  }
+  for (const MixBlock& b : v->blocks) {
+    if (!save) m->arena.off = mark;
+    TAKE(y1, (size_t)rows * D);
+    RC(b200r_layernorm(x, y1, b.n1w, b.n1b, rows, D, 1e-6f, st));                        // vit_base.py:159
+    TAKE(yt, (size_t)crow * TP);
+    RC(b200r_tokens_to_channels(y1, yt, n, T, D, TP, st));                                // [n*D, 256] (zero padded)
+    TAKE(p1, (size_t)crow * v->tok_hidden);
+    TAKE(y2, (size_t)crow * TP);
+    if (save) {
+      RC(lin_fwd(b.t1, yt, nullptr, p1, nullptr, crow, B200R_ACT_NONE, P, st));
+      TAKE(a1, (size_t)crow * v->tok_hidden);
+      RC(b200r_act_planes(p1, a1, (size_t)crow * v->tok_hidden, B200R_ACT_GELU_ERF, st));
+      RC(lin_fwd(b.t2, a1, nullptr, y2, nullptr, crow, B200R_ACT_NONE, P, st));
+    } else {
+      RC(lin_fwd(b.t1, yt, nullptr, p1, nullptr, crow, B200R_ACT_GELU_ERF, P, st));       // nn.GELU (erf)
+      RC(lin_fwd(b.t2, p1, nullptr, y2, nullptr, crow, B200R_ACT_NONE, P, st));
+    }
+    TAKE(x_mid, (size_t)rows * D);
+    RC(b200r_channels_to_tokens_add(y2, x, x_mid, n, T, D, TP, st));                      // x + token_mix(...)^T
+    TAKE(y3, (size_t)rows * D);
+    RC(b200r_layernorm(x_mid, y3, b.n2w, b.n2b, rows, D, 1e-6f, st));
+    TAKE(p2, (size_t)rows * v->ch_hidden);
+    uint16_t* xn;
+    if (save) {
+      RC(lin_fwd(b.c1, y3, nullptr, p2, nullptr, rows, B200R_ACT_NONE, P, st));
+      TAKE(a2, (size_t)rows * v->ch_hidden);
+      RC(b200r_act_planes(p2, a2, (size_t)rows * v->ch_hidden, B200R_ACT_GELU_ERF, st));
+      TAKE(xo, (size_t)rows * D);
+      RC(lin_fwd(b.c2, a2, x_mid, xo, nullptr, rows, B200R_ACT_NONE, P, st));
+      v->saved.push_back({x, p1, x_mid, p2});
+      xn = xo;
+    } else {
+      RC(lin_fwd(b.c1, y3, nullptr, p2, nullptr, rows, B200R_ACT_GELU_ERF, P, st));
+      xn = (x == x0) ? xalt : x0;
+      RC(lin_fwd(b.c2, p2, x_mid, xn, nullptr, rows, B200R_ACT_NONE, P, st));
+    }
+    x = xn;
+  }
+  if (!save) m->arena.off = mark;
+  TAKE(xnrm, (size_t)rows * D);
+  RC(b200r_layernorm(x, xnrm, v->normw, v->normb, rows, D, 1e-6f, st));
+  TAKE(pooled, (size_t)n * D);
+  RC(b200r_global_avgpool_nhwc(xnrm, pooled, n, T, D, st));                               // x.mean(dim=1)
+  RC(lin_fwd(v->head, pooled, nullptr, nullptr, logits, n, B200R_ACT_NONE, P, st));
+  if (save) { v->final_x = x; v->n = n; v->h = h; v->w = w; v->valid = true; }
+  return B200R_OK;
+}
+
+int mixer_input_grad(b200r_model* m, const float* dlogits, float* dx, cudaStream_t s) {
+  MixerNet* v = m->mixer;
+  B200R_CHECK_ARG(v->valid, "input_grad needs the activations of a preceding b200r_model_forward_f32 on this handle");
+  const b200r_stream_t st = reinterpret_cast<b200r_stream_t>(s);
+  const int D = v->dim, P = m->passes, n = v->n, T = v->tokens, rows = n * T, crow = n * D, TP = v->t_pad;
+  TAKE(g0, (size_t)n * m->classes);
+  RC(b200r_split_f32_scaled(dlogits, g0, (size_t)n * m->classes, kGradScale, st));
+  TAKE(g1, (size_t)n * D);
+  RC(lin_dgrad(v->head, g0, g1, n, P, st));
+  TAKE(g2, (size_t)rows * D);
+  RC(b200r_global_avgpool_bwd_nhwc(g1, g2, n, T, D, st));                                 // x.mean(dim=1) backward
+  uint16_t* gbuf[2];
+  gbuf[0] = take_planes(m, (size_t)rows * D);
+  gbuf[1] = take_planes(m, (size_t)rows * D);
+  uint16_t* zeros = take_planes(m, (size_t)rows * D);                                     // residual operand of the plain transpose
+  B200R_CHECK_ARG(gbuf[0] && gbuf[1] && zeros, "activation arena too small");
+  B200R_CUDA(cudaMemsetAsync(zeros, 0, (size_t)rows * D * 4, s));
+  RC(b200r_layernorm_bwd(g2, v->final_x, v->normw, nullptr, gbuf[0], rows, D, 1e-6f, st));
+  const size_t mark = m->arena.off;
+  int cur = 0;
+  for (int d = v->depth - 1; d >= 0; --d) {
+    const MixBlock& b = v->blocks[d];
+    const MixSaved& sv = v->saved[d];
+    m->arena.off = mark;
+    TAKE(t1, (size_t)rows * v->ch_hidden);
+    RC(lin_dgrad(b.c2, gbuf[cur], t1, rows, P, st));
+    TAKE(t2, (size_t)rows * v->ch_hidden);
+    RC(b200r_act_bwd_planes(t1, sv.p2, t2, (size_t)rows * v->ch_hidden, B200R_ACT_GELU_ERF, st));
+    TAKE(t3, (size_t)rows * D);
+    RC(lin_dgrad(b.c1, t2, t3, rows, P, st));
+    TAKE(gm, (size_t)rows * D);
+    RC(b200r_layernorm_bwd(t3, sv.x_mid, b.n2w, gbuf[cur], gm, rows, D, 1e-6f, st));       // x = x_mid + channel_mix(norm2(x_mid))
+    TAKE(t4, (size_t)crow * TP);
+    RC(b200r_tokens_to_channels(gm, t4, n, T, D, TP, st));
+    TAKE(t5, (size_t)crow * v->tok_hidden);
+    RC(lin_dgrad(b.t2, t4, t5, crow, P, st));
+    TAKE(t6, (size_t)crow * v->tok_hidden);
+    RC(b200r_act_bwd_planes(t5, sv.p1, t6, (size_t)crow * v->tok_hidden, B200R_ACT_GELU_ERF, st));
+    TAKE(t7, (size_t)crow * TP);
+    RC(lin_dgrad(b.t1, t6, t7, crow, P, st));
+    TAKE(t8, (size_t)rows * D);
+    RC(b200r_channels_to_tokens_add(t7, zeros, t8, n, T, D, TP, st));
+    RC(b200r_layernorm_bwd(t8, sv.x_in, b.n1w, gm, gbuf[cur ^ 1], rows, D, 1e-6f, st));    // x_mid = x_in + token_mix(norm1(x_in))
+    cur ^= 1;
+  }
+  m->arena.off = mark;
+  TAKE(dcols, (size_t)rows * v->embed.k);
+  RC(lin_dgrad(v->embed, gbuf[cur], dcols, rows, P, st));
+  float stdu[3];
+  for (int i = 0; i < 3; ++i) stdu[i] = kStd[i] * kGradScale;
+  return b200r_patch_scatter_f32(dcols, dx, n, v->h, v->w, v->patch, stdu, st);
+}
 }  // namespace
 
 extern "C" {
 
 int b200r_model_create(int arch, const b200r_weight* weights, int n_weights, int passes, b200r_model** out) {
   B200R_CHECK_ARG(out && weights && n_weights > 0, "null argument");
-  B200R_CHECK_ARG(arch >= B200R_ARCH_RESNET18 && arch <= B200R_ARCH_VIT_B16, "arch %d: the handle API covers the ResNet family (0..3) and ViT-B/16 (4)", arch);
-  B200R_CHECK_ARG(passes == 3 || (passes == B200R_PASSES_F16 && arch != B200R_ARCH_VIT_B16),
+  B200R_CHECK_ARG(arch >= B200R_ARCH_RESNET18 && arch <= B200R_ARCH_MIXER_B16, "arch %d: the handle API covers the ResNet family (0..3), ViT-B/16 (4) and MLP-Mixer-B/16 (5)", arch);
+  B200R_CHECK_ARG(passes == 3 || (passes == B200R_PASSES_F16 && arch < B200R_ARCH_VIT_B16),
                   "passes must be 3 (split planes, fp32-faithful) or, for the ResNets, B200R_PASSES_F16");
   static const int kLayers[4][4] = {{2, 2, 2, 2}, {3, 4, 6, 3}, {3, 4, 6, 3}, {3, 4, 23, 3}};
   const bool bott = arch >= B200R_ARCH_RESNET50;
@@ -538,8 +728,8 @@ int b200r_model_create(int arch, const b200r_weight* weights, int n_weights, int
   m->feat = bott ? 2048 : 512;
   int rc = B200R_OK;
   auto fail = [&](int code) { b200r_model_destroy(m); return code; };
-  if (arch == B200R_ARCH_VIT_B16) {
-    if ((rc = vit_create(m, W))) return fail(rc);
+  if (arch == B200R_ARCH_VIT_B16 || arch == B200R_ARCH_MIXER_B16) {
+    if ((rc = arch == B200R_ARCH_VIT_B16 ? vit_create(m, W) : mixer_create(m, W))) return fail(rc);
     *out = m;
     return B200R_OK;
   }
@@ -622,6 +812,7 @@ int b200r_model_destroy(b200r_model* m) {
   for (void* p : m->owned) cudaFree(p);
   if (m->arena.base) cudaFree(m->arena.base);
   delete m->vit;
+  delete m->mixer;
   delete m;
   return B200R_OK;
 }
@@ -638,6 +829,7 @@ int b200r_model_forward_u8(b200r_model* m, const uint8_t* images, float* logits,
   B200R_CHECK_ARG(h % 32 == 0 && w % 32 == 0, "image size must be a multiple of 32 (got %dx%d)", h, w);
   RC(ensure_arena(m, n, h, w, false));
   if (m->vit) return vit_forward(m, images, true, logits, n, h, w, false, as_stream(stream));
+  if (m->mixer) return mixer_forward(m, images, true, logits, n, h, w, false, as_stream(stream));
   m->arena.region(1);
   m->saved.valid = false;
   cudaStream_t s = as_stream(stream);
@@ -663,6 +855,7 @@ int b200r_model_forward_f32(b200r_model* m, const float* x01, float* logits, int
   B200R_CHECK_ARG(h % 32 == 0 && w % 32 == 0 && w <= 256, "float input: image size must be a multiple of 32 and at most 256 wide (got %dx%d)", h, w);
   RC(ensure_arena(m, n, h, w, true));
   if (m->vit) return vit_forward(m, x01, false, logits, n, h, w, true, as_stream(stream));
+  if (m->mixer) return mixer_forward(m, x01, false, logits, n, h, w, true, as_stream(stream));
   m->arena.reset();
   cudaStream_t s = as_stream(stream);
   TAKE(s0, (size_t)n * (h / 2) * (w / 2) * 64);
@@ -686,6 +879,7 @@ int b200r_model_forward_f32(b200r_model* m, const float* x01, float* logits, int
 int b200r_model_input_grad(b200r_model* m, const float* dlogits, float* dx, b200r_stream_t stream) {
   B200R_CHECK_ARG(m && dlogits && dx, "bad argument");
   if (m->vit) return vit_input_grad(m, dlogits, dx, as_stream(stream));
+  if (m->mixer) return mixer_input_grad(m, dlogits, dx, as_stream(stream));
   B200R_CHECK_ARG(m->saved.valid, "b200r_model_input_grad needs a preceding b200r_model_forward_f32 on this handle");
   const int n = m->saved.n, H = m->saved.h, Wd = m->saved.w, P = m->passes;
   const bool f16 = m->f16;

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib, nets, ops
 
-ARCH_IDS = {"resnet18": 0, "resnet34": 1, "resnet50": 2, "resnet101": 3, "vit_b16_224": 4, "vit_base_patch16_224": 4}
+ARCH_IDS = {"resnet18": 0, "resnet34": 1, "resnet50": 2, "resnet101": 3, "vit_b16_224": 4, "vit_base_patch16_224": 4, "mixer_b16_224": 5}
 
 
 class _Weight(C.Structure):
@@ -25,7 +25,7 @@ class ModelHandle:
     def __init__(self, arch: str, state_dict: Dict[str, torch.Tensor], device, passes: int = 3):
         arch = nets.ARCH_ALIASES.get(arch, arch)
         if arch not in ARCH_IDS:
-            raise NotImplementedError("model handles cover the ResNet family and ViT-B/16, not %r" % arch)
+            raise NotImplementedError("model handles cover the ResNet family, ViT-B/16 and MLP-Mixer-B/16, not %r" % arch)
         self.arch, self.device, self.passes = arch, torch.device(device), passes
         sd = nets._strip_prefix(state_dict)
         keep = [(k, v.detach().to("cpu", torch.float32).contiguous()) for k, v in sd.items() if not k.endswith("num_batches_tracked")]
@@ -36,6 +36,11 @@ class ModelHandle:
         self.num_classes = _lib.load().b200r_model_num_classes(self._h)
         self.f16 = passes == ops.PASSES_F16
         self._graphs = {}
+        if ARCH_IDS[arch] == 5:
+            # patch gather, embedding, 12 x (2 layernorm + 2 transposes + 4 linear), final norm, token mean, head
+            self.feat = 768
+            self._launches = 2 + 12 * 8 + 3
+            return
         if ARCH_IDS[arch] == 4:
             # patch gather, embedding, token assembly, 12 x (2 layernorm + 4 linear + attention), final norm, class-token copies, head
             self.feat = 768

@@ -173,3 +173,24 @@ def test_vit_handle_matches_python_sequencing(cuda):
     with pytest.raises(ValueError):
         hm(torch.zeros(2, 160, 160, 3, dtype=torch.uint8, device=cuda))  # 101 tokens against a 197-row position embedding
     hm.close()
+
+
+def test_mixer_handle_matches_python_sequencing(cuda):
+    """MLP-Mixer-B/16 behind the C-ABI (B200R_ARCH_MIXER_B16): forward from uint8 / float input and the input gradient, bit-identical
+    to nets.Mixer's launch sequence (vit/mlp_mixer.py:7-159)."""
+    from robustart_b200 import nets, ops
+    from robustart_b200.handle import ModelHandle
+    sd = nets.random_token_state_dict(nets.mixer_spec(), 0)
+    ref = nets.build_model("mixer_b16_224", sd, device=cuda)
+    hm = ModelHandle("mixer_b16_224", sd, cuda, 3)
+    images = torch.from_numpy(synth_images(3, seed=8)).to(cuda)
+    assert torch.equal(hm(images), ref(images))
+    x01 = images.permute(0, 3, 1, 2).float().div(255).contiguous()
+    la, vjp = hm.forward_vjp(x01)
+    lb, saved = ref.forward_saved(x01)
+    assert torch.equal(la, lb)
+    _, d = ops.ce_loss_grad(la, torch.tensor([7, 1, 3], device=cuda))
+    ga, gb = vjp(d), ref.input_grad(d, saved)
+    assert torch.isfinite(ga).all() and ga.abs().max().item() > 0
+    assert torch.equal(ga, gb)
+    hm.close()

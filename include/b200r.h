@@ -524,7 +524,11 @@ enum b200r_arch { B200R_ARCH_RESNET18 = 0, B200R_ARCH_RESNET34 = 1, B200R_ARCH_R
                   B200R_ARCH_VIT_B16 = 4,
                   /* MLP-Mixer-B/16 (vit/mlp_mixer.py:7-159; keys patch_embed.proj.*, blocks.<i>.{norm1,norm2,token_mix.fc1,token_mix.fc2,
                    * channel_mix.fc1,channel_mix.fc2}.*, norm.*, head.*): split precision only */
-                  B200R_ARCH_MIXER_B16 = 5 };
+                  B200R_ARCH_MIXER_B16 = 5,
+                  /* MobileNetV2 x1.0 (mobilenet_v2.py:80-202; keys features.*, classifier.1.*) and EfficientNet-B0 (efficientnet.py:91-125,
+                   * 289-495; keys stem.*, blocks.<i>.{in_conv,se_block,out_conv}.*, head.*, fc.*): split precision, INFERENCE handles --
+                   * b200r_model_forward_u8 only (the ImageNet-C sweep is evaluation); forward_f32 / input_grad return B200R_ENOTSUP */
+                  B200R_ARCH_MOBILENET_V2 = 6, B200R_ARCH_EFFICIENTNET_B0 = 7 };
 /* one state_dict entry: the reference's key ("layer1.0.conv1.weight", "bn1.running_var", "fc.bias", ...; optional "module." /
  * "base_model." prefixes are stripped, benchmark_eval_adv.py:162-168), HOST float32 data in PyTorch layout, element count */
 typedef struct b200r_weight { const char* name; const float* data; int64_t numel; } b200r_weight;

@@ -60,10 +60,12 @@ struct Arena {
 
 struct VitNet;                 // ViT-B/16 (vision_transformer.py): defined below, owned by the handle
 struct MixerNet;               // MLP-Mixer-B/16 (vit/mlp_mixer.py, vit/vit_base.py)
+struct MobileNet;              // MobileNetV2 / EfficientNet-B0 (mobilenet_v2.py, efficientnet.py): inference forward
 
 struct b200r_model {
   VitNet* vit = nullptr;
   MixerNet* mixer = nullptr;
+  MobileNet* mobile = nullptr;
   int arch = 0, passes = 3, planes = 2, classes = 1000, feat = 512;
   bool f16 = false;
   std::vector<Block> blocks;
@@ -205,7 +207,9 @@ uint16_t* take_planes(b200r_model* m, size_t count) { return static_cast<uint16_
 
 size_t vit_arena_need(const b200r_model* m, int n, bool save);
 size_t mixer_arena_need(const b200r_model* m, int n, bool save);
+size_t mobile_arena_need(const b200r_model* m, int n, int h, int w);
 size_t arena_need(const b200r_model* m, int n, int h, int w, bool save) {
+  if (m->mobile) return mobile_arena_need(m, n, h, w);
   if (m->vit) return vit_arena_need(m, n, save);
   if (m->mixer) return mixer_arena_need(m, n, save);
   // elements per input pixel, bounded from above by a closed form.  Inference: two halves, each the largest block footprint
@@ -704,13 +708,208 @@ int mixer_input_grad(b200r_model* m, const float* dlogits, float* dx, cudaStream
   for (int i = 0; i < 3; ++i) stdu[i] = kStd[i] * kGradScale;
   return b200r_patch_scatter_f32(dcols, dx, n, v->h, v->w, v->patch, stdu, st);
 }
+
+// ---- MobileNetV2 x1.0 (mobilenet_v2.py:80-202) and EfficientNet-B0 (efficientnet.py:91-125,289-495): the inference launch
+// sequence of nets.MobileNetV2 / nets.EfficientNetB0 (the ImageNet-C sweep of BASELINE configs[3] is evaluation only) --------------
+struct PwConv { Planes w; float *w_f32 = nullptr, *bias = nullptr; int cin = 0, cout = 0; };    // 1x1 conv + folded BN
+struct DwConv { float *w = nullptr, *scale = nullptr, *bias = nullptr; int c = 0, k = 3, stride = 1; };
+struct MbBlock { bool has_pw = false, has_se = false, res = false; PwConv pw, pl; DwConv dw; Lin se1, se2; };
+}  // namespace
+struct MobileNet {
+  int act = B200R_ACT_RELU6;          // ReLU6 (MobileNetV2) / swish (EfficientNet)
+  float *stem_w = nullptr, *stem_scale = nullptr, *stem_bias = nullptr;
+  int stem_cout = 32;
+  std::vector<MbBlock> blocks;
+  PwConv last;
+  Lin fc;
+};
+namespace {
+
+// folded BN as nets._fold_bn returns it: float32 scale and bias (the scale is rounded to float BEFORE it is folded into a weight)
+int fold_bn_f32(const Weights& W, const std::string& bn, int c, std::vector<float>* scale, std::vector<float>* bias) {
+  std::vector<double> sd;
+  int rc = fold_bn(W, bn, c, &sd, bias);
+  if (rc) return rc;
+  scale->resize(c);
+  for (int i = 0; i < c; ++i) (*scale)[i] = (float)sd[i];
+  return B200R_OK;
+}
+int make_pw(b200r_model* m, const Weights& W, const std::string& conv, const std::string& bn, int cin, int cout, PwConv* out) {
+  const float* w;
+  int rc = get(W, conv + ".weight", (int64_t)cout * cin, &w);
+  if (rc) return rc;
+  std::vector<float> sc, bi;
+  if ((rc = fold_bn_f32(W, bn, cout, &sc, &bi))) return rc;
+  std::vector<float> wf((size_t)cout * cin);
+  for (int o = 0; o < cout; ++o)
+    for (int i = 0; i < cin; ++i) wf[(size_t)o * cin + i] = (float)((double)w[(size_t)o * cin + i] * (double)sc[o]);
+  out->cin = cin; out->cout = cout;
+  if ((rc = upload_planes(m, wf, &out->w)) || (rc = upload_f32(m, bi, &out->bias))) return rc;
+  if (cin % 8 == 0 && cin <= 32) return upload_f32(m, wf, &out->w_f32);       // narrow inputs: the CUDA-core kernel's float32 weights
+  return B200R_OK;
+}
+int make_dw(b200r_model* m, const Weights& W, const std::string& conv, const std::string& bn, int c, int k, int stride, DwConv* out) {
+  const float* w;
+  int rc = get(W, conv + ".weight", (int64_t)c * k * k, &w);
+  if (rc) return rc;
+  std::vector<float> wt((size_t)k * k * c), sc, bi;
+  for (int ch = 0; ch < c; ++ch)
+    for (int t = 0; t < k * k; ++t) wt[(size_t)t * c + ch] = w[(size_t)ch * k * k + t];          // [c, 1, k, k] -> [k*k, c]
+  if ((rc = fold_bn_f32(W, bn, c, &sc, &bi))) return rc;
+  out->c = c; out->k = k; out->stride = stride;
+  if ((rc = upload_f32(m, wt, &out->w)) || (rc = upload_f32(m, sc, &out->scale)) || (rc = upload_f32(m, bi, &out->bias))) return rc;
+  return B200R_OK;
+}
+int make_image_stem(b200r_model* m, const Weights& W, const std::string& conv, const std::string& bn, int cout, MobileNet* v) {
+  const float* w;
+  int rc = get(W, conv + ".weight", (int64_t)cout * 27, &w);
+  if (rc) return rc;
+  std::vector<float> w27((size_t)cout * 27), sc, bi;
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < 3; ++c)
+      for (int t = 0; t < 9; ++t) w27[(size_t)o * 27 + t * 3 + c] = w[((size_t)o * 3 + c) * 9 + t];  // [o, c, ky, kx] -> [o, (ky, kx, c)]
+  if ((rc = fold_bn_f32(W, bn, cout, &sc, &bi))) return rc;
+  v->stem_cout = cout;
+  if ((rc = upload_f32(m, w27, &v->stem_w)) || (rc = upload_f32(m, sc, &v->stem_scale)) || (rc = upload_f32(m, bi, &v->stem_bias))) return rc;
+  return B200R_OK;
+}
+
+int mobilenet_v2_create(b200r_model* m, const Weights& W) {
+  MobileNet* v = new MobileNet();
+  m->mobile = v;
+  v->act = B200R_ACT_RELU6;
+  int rc;
+  if ((rc = make_image_stem(m, W, "features.0.0", "features.0.1", 32, v))) return rc;
+  static const int kSetting[7][4] = {{1, 16, 1, 1}, {6, 24, 2, 2}, {6, 32, 3, 2}, {6, 64, 4, 2}, {6, 96, 3, 1}, {6, 160, 3, 2}, {6, 320, 1, 1}};
+  int cin = 32, idx = 1;
+  for (const auto& st : kSetting)
+    for (int i = 0; i < st[2]; ++i) {
+      const int t = st[0], c = st[1], stride = i == 0 ? st[3] : 1, hid = cin * t;
+      const std::string p = "features." + std::to_string(idx) + ".conv.";
+      MbBlock b;
+      b.res = stride == 1 && cin == c;
+      int j = 0;
+      if (t != 1) {
+        b.has_pw = true;
+        if ((rc = make_pw(m, W, p + "0.0", p + "0.1", cin, hid, &b.pw))) return rc;
+        j = 1;
+      }
+      if ((rc = make_dw(m, W, p + std::to_string(j) + ".0", p + std::to_string(j) + ".1", hid, 3, stride, &b.dw)) ||
+          (rc = make_pw(m, W, p + std::to_string(j + 1), p + std::to_string(j + 2), hid, c, &b.pl)))
+        return rc;
+      v->blocks.push_back(b);
+      cin = c;
+      ++idx;
+    }
+  if ((rc = make_pw(m, W, "features." + std::to_string(idx) + ".0", "features." + std::to_string(idx) + ".1", cin, 1280, &v->last))) return rc;
+  auto fw = W.find("classifier.1.weight");
+  B200R_CHECK_ARG(fw != W.end(), "state_dict tensor 'classifier.1.weight' is missing");
+  m->classes = (int)(fw->second.second / 1280);
+  return make_lin(m, W, "classifier.1", m->classes, 1280, &v->fc);
+}
+
+int efficientnet_b0_create(b200r_model* m, const Weights& W) {
+  MobileNet* v = new MobileNet();
+  m->mobile = v;
+  v->act = B200R_ACT_SWISH;
+  int rc;
+  if ((rc = make_image_stem(m, W, "stem.0", "stem.1", 32, v))) return rc;
+  static const int kBlocks[7][6] = {{1, 3, 1, 1, 32, 16}, {2, 3, 2, 6, 16, 24}, {2, 5, 2, 6, 24, 40}, {3, 3, 2, 6, 40, 80}, {3, 5, 1, 6, 80, 112},
+                                    {4, 5, 2, 6, 112, 192}, {1, 3, 1, 6, 192, 320}};     // (repeat, kernel, stride, expand, in, out), efficientnet.py:101-109
+  int bi = 0;
+  for (const auto& st : kBlocks)
+    for (int r = 0; r < st[0]; ++r) {
+      const int k = st[1], e = st[3], ci = r == 0 ? st[4] : st[5], cout = st[5], stride = r == 0 ? st[2] : 1, hid = ci * e;
+      const std::string p = "blocks." + std::to_string(bi) + ".";
+      MbBlock b;
+      b.res = stride == 1 && ci == cout;
+      b.has_se = true;
+      int j = 0;
+      if (e != 1) {
+        b.has_pw = true;
+        if ((rc = make_pw(m, W, p + "in_conv.0", p + "in_conv.1", ci, hid, &b.pw))) return rc;
+        j = 3;
+      }
+      auto sw = W.find(p + "se_block.conv1.bias");
+      B200R_CHECK_ARG(sw != W.end(), "state_dict tensor '%sse_block.conv1.bias' is missing", p.c_str());
+      const int se = (int)sw->second.second, sep = (se + 7) / 8 * 8;                       // squeeze width padded to a 16-byte row
+      if ((rc = make_dw(m, W, p + "in_conv." + std::to_string(j), p + "in_conv." + std::to_string(j + 1), hid, k, stride, &b.dw)) ||
+          (rc = make_lin(m, W, p + "se_block.conv1", se, hid, &b.se1, sep, 0)) || (rc = make_lin(m, W, p + "se_block.conv2", hid, se, &b.se2, 0, sep)) ||
+          (rc = make_pw(m, W, p + "out_conv.0", p + "out_conv.1", hid, cout, &b.pl)))
+        return rc;
+      v->blocks.push_back(b);
+      ++bi;
+    }
+  if ((rc = make_pw(m, W, "head.0", "head.1", 320, 1280, &v->last))) return rc;
+  auto fw = W.find("fc.weight");
+  B200R_CHECK_ARG(fw != W.end(), "state_dict tensor 'fc.weight' is missing");
+  m->classes = (int)(fw->second.second / 1280);
+  return make_lin(m, W, "fc", m->classes, 1280, &v->fc);
+}
+
+size_t mobile_arena_need(const b200r_model*, int n, int h, int w) {
+  // largest block (EfficientNet blocks.1: 96 ch @112^2 + 2 x 96 ch @56^2 + 24 ch @56^2): 37.5 plane elements per input pixel per half
+  return (size_t)(2 * 48.0 * n * h * w * 4.0) + (64u << 20);
+}
+
+int pw_fwd(b200r_model* m, const PwConv& c, const uint16_t* x, const uint16_t* res, uint16_t* y, int n, int h, int w, int act, b200r_stream_t st) {
+  if (c.w_f32) return b200r_pointwise_smallk_nhwc(x, c.w_f32, c.bias, res, y, (size_t)n * h * w, c.cin, c.cout, act, st);
+  return b200r_conv2d_nhwc(x, c.w.p, nullptr, c.bias, res, y, nullptr, n, h, w, c.cin, c.cout, 1, 1, 1, 0, act, m->passes, st);
+}
+
+int mobile_forward(b200r_model* m, const uint8_t* images, float* logits, int n, int h, int w, cudaStream_t s) {
+  MobileNet* v = m->mobile;
+  const b200r_stream_t st = reinterpret_cast<b200r_stream_t>(s);
+  B200R_CHECK_ARG(m->planes == 2, "the mobile-family handles run in split precision (passes = 3)");
+  const int P = m->passes;
+  m->arena.region(1);
+  int hh = (h - 1) / 2 + 1, ww = (w - 1) / 2 + 1, c = v->stem_cout, bi = 0;
+  TAKE(x0, (size_t)n * hh * ww * c);
+  RC(b200r_image_stem3x3s2_u8(images, v->stem_w, v->stem_scale, v->stem_bias, x0, n, h, w, c, v->act, kMean, kStd, st));
+  uint16_t* x = x0;
+  for (const MbBlock& b : v->blocks) {
+    m->arena.region(bi++ & 1);                      // the input lives in the other half
+    const uint16_t* y = x;
+    int hid = c;
+    if (b.has_pw) {
+      TAKE(a1, (size_t)n * hh * ww * b.pw.cout);
+      RC(pw_fwd(m, b.pw, x, nullptr, a1, n, hh, ww, v->act, st));
+      y = a1;
+      hid = b.pw.cout;
+    }
+    const int k = b.dw.k, ho = (hh + 2 * (k / 2) - k) / b.dw.stride + 1, wo = (ww + 2 * (k / 2) - k) / b.dw.stride + 1;
+    TAKE(a2, (size_t)n * ho * wo * hid);
+    RC(b200r_dwconv_nhwc(y, b.dw.w, b.dw.scale, b.dw.bias, a2, n, hh, ww, hid, k, b.dw.stride, k / 2, v->act, st));
+    const uint16_t* z = a2;
+    if (b.has_se) {
+      TAKE(sq, (size_t)n * hid);
+      RC(b200r_global_avgpool_nhwc(a2, sq, n, ho * wo, hid, st));                          // squeeze
+      TAKE(s1, (size_t)n * b.se1.nout);
+      RC(lin_fwd(b.se1, sq, nullptr, s1, nullptr, n, B200R_ACT_SWISH, P, st));
+      TAKE(s2, (size_t)n * b.se2.nout);
+      RC(lin_fwd(b.se2, s1, nullptr, s2, nullptr, n, B200R_ACT_SIGMOID, P, st));
+      TAKE(a3, (size_t)n * ho * wo * hid);
+      RC(b200r_channel_scale(a2, s2, a3, n, ho * wo, hid, b.se2.nout, st));                // excite
+      z = a3;
+    }
+    TAKE(o, (size_t)n * ho * wo * b.pl.cout);
+    RC(pw_fwd(m, b.pl, z, b.res ? x : nullptr, o, n, ho, wo, B200R_ACT_NONE, st));         // linear bottleneck (+ skip)
+    x = o; hh = ho; ww = wo; c = b.pl.cout;
+  }
+  m->arena.region(bi & 1);
+  TAKE(last, (size_t)n * hh * ww * v->last.cout);
+  RC(pw_fwd(m, v->last, x, nullptr, last, n, hh, ww, v->act, st));
+  TAKE(pooled, (size_t)n * v->last.cout);
+  RC(b200r_global_avgpool_nhwc(last, pooled, n, hh * ww, v->last.cout, st));
+  return lin_fwd(v->fc, pooled, nullptr, nullptr, logits, n, B200R_ACT_NONE, P, st);
+}
 }  // namespace
 
 extern "C" {
 
 int b200r_model_create(int arch, const b200r_weight* weights, int n_weights, int passes, b200r_model** out) {
   B200R_CHECK_ARG(out && weights && n_weights > 0, "null argument");
-  B200R_CHECK_ARG(arch >= B200R_ARCH_RESNET18 && arch <= B200R_ARCH_MIXER_B16, "arch %d: the handle API covers the ResNet family (0..3), ViT-B/16 (4) and MLP-Mixer-B/16 (5)", arch);
+  B200R_CHECK_ARG(arch >= B200R_ARCH_RESNET18 && arch <= B200R_ARCH_EFFICIENTNET_B0, "arch %d: the handle API covers the ResNet family (0..3), ViT-B/16 (4), MLP-Mixer-B/16 (5), MobileNetV2 (6) and EfficientNet-B0 (7)", arch);
   B200R_CHECK_ARG(passes == 3 || (passes == B200R_PASSES_F16 && arch < B200R_ARCH_VIT_B16),
                   "passes must be 3 (split planes, fp32-faithful) or, for the ResNets, B200R_PASSES_F16");
   static const int kLayers[4][4] = {{2, 2, 2, 2}, {3, 4, 6, 3}, {3, 4, 6, 3}, {3, 4, 23, 3}};
@@ -728,8 +927,10 @@ int b200r_model_create(int arch, const b200r_weight* weights, int n_weights, int
   m->feat = bott ? 2048 : 512;
   int rc = B200R_OK;
   auto fail = [&](int code) { b200r_model_destroy(m); return code; };
-  if (arch == B200R_ARCH_VIT_B16 || arch == B200R_ARCH_MIXER_B16) {
-    if ((rc = arch == B200R_ARCH_VIT_B16 ? vit_create(m, W) : mixer_create(m, W))) return fail(rc);
+  if (arch >= B200R_ARCH_VIT_B16) {
+    if ((rc = arch == B200R_ARCH_VIT_B16 ? vit_create(m, W) : arch == B200R_ARCH_MIXER_B16 ? mixer_create(m, W)
+              : arch == B200R_ARCH_MOBILENET_V2 ? mobilenet_v2_create(m, W) : efficientnet_b0_create(m, W)))
+      return fail(rc);
     *out = m;
     return B200R_OK;
   }
@@ -813,6 +1014,7 @@ int b200r_model_destroy(b200r_model* m) {
   if (m->arena.base) cudaFree(m->arena.base);
   delete m->vit;
   delete m->mixer;
+  delete m->mobile;
   delete m;
   return B200R_OK;
 }
@@ -830,6 +1032,7 @@ int b200r_model_forward_u8(b200r_model* m, const uint8_t* images, float* logits,
   RC(ensure_arena(m, n, h, w, false));
   if (m->vit) return vit_forward(m, images, true, logits, n, h, w, false, as_stream(stream));
   if (m->mixer) return mixer_forward(m, images, true, logits, n, h, w, false, as_stream(stream));
+  if (m->mobile) return mobile_forward(m, images, logits, n, h, w, as_stream(stream));
   m->arena.region(1);
   m->saved.valid = false;
   cudaStream_t s = as_stream(stream);
@@ -856,6 +1059,7 @@ int b200r_model_forward_f32(b200r_model* m, const float* x01, float* logits, int
   RC(ensure_arena(m, n, h, w, true));
   if (m->vit) return vit_forward(m, x01, false, logits, n, h, w, true, as_stream(stream));
   if (m->mixer) return mixer_forward(m, x01, false, logits, n, h, w, true, as_stream(stream));
+  if (m->mobile) { b200r_set_error("the MobileNetV2 / EfficientNet-B0 handles are inference handles (b200r_model_forward_u8): their input gradient is sequenced by robustart_b200.nets"); return B200R_ENOTSUP; }
   m->arena.reset();
   cudaStream_t s = as_stream(stream);
   TAKE(s0, (size_t)n * (h / 2) * (w / 2) * 64);
@@ -880,6 +1084,7 @@ int b200r_model_input_grad(b200r_model* m, const float* dlogits, float* dx, b200
   B200R_CHECK_ARG(m && dlogits && dx, "bad argument");
   if (m->vit) return vit_input_grad(m, dlogits, dx, as_stream(stream));
   if (m->mixer) return mixer_input_grad(m, dlogits, dx, as_stream(stream));
+  if (m->mobile) { b200r_set_error("the MobileNetV2 / EfficientNet-B0 handles are inference handles"); return B200R_ENOTSUP; }
   B200R_CHECK_ARG(m->saved.valid, "b200r_model_input_grad needs a preceding b200r_model_forward_f32 on this handle");
   const int n = m->saved.n, H = m->saved.h, Wd = m->saved.w, P = m->passes;
   const bool f16 = m->f16;

@@ -14,7 +14,8 @@ import torch
 
 from . import _lib, nets, ops
 
-ARCH_IDS = {"resnet18": 0, "resnet34": 1, "resnet50": 2, "resnet101": 3, "vit_b16_224": 4, "vit_base_patch16_224": 4, "mixer_b16_224": 5}
+ARCH_IDS = {"resnet18": 0, "resnet34": 1, "resnet50": 2, "resnet101": 3, "vit_b16_224": 4, "vit_base_patch16_224": 4, "mixer_b16_224": 5, "mobilenet_v2": 6,
+            "efficientnet_b0": 7}
 
 
 class _Weight(C.Structure):
@@ -25,7 +26,7 @@ class ModelHandle:
     def __init__(self, arch: str, state_dict: Dict[str, torch.Tensor], device, passes: int = 3):
         arch = nets.ARCH_ALIASES.get(arch, arch)
         if arch not in ARCH_IDS:
-            raise NotImplementedError("model handles cover the ResNet family, ViT-B/16 and MLP-Mixer-B/16, not %r" % arch)
+            raise NotImplementedError("model handles cover the ResNet family, ViT-B/16, MLP-Mixer-B/16, MobileNetV2 and EfficientNet-B0, not %r" % arch)
         self.arch, self.device, self.passes = arch, torch.device(device), passes
         sd = nets._strip_prefix(state_dict)
         keep = [(k, v.detach().to("cpu", torch.float32).contiguous()) for k, v in sd.items() if not k.endswith("num_batches_tracked")]
@@ -36,6 +37,10 @@ class ModelHandle:
         self.num_classes = _lib.load().b200r_model_num_classes(self._h)
         self.f16 = passes == ops.PASSES_F16
         self._graphs = {}
+        if ARCH_IDS[arch] >= 6:
+            self.feat = 1280
+            self._launches = {6: 2 + 17 * 2 + 16 + 3, 7: 2 + 16 * 6 + 15 + 3}[ARCH_IDS[arch]]     # stem, blocks (pw? dw [se x4] pl), last, pool, fc
+            return
         if ARCH_IDS[arch] == 5:
             # patch gather, embedding, 12 x (2 layernorm + 2 transposes + 4 linear), final norm, token mean, head
             self.feat = 768

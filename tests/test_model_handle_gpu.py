@@ -194,3 +194,21 @@ def test_mixer_handle_matches_python_sequencing(cuda):
     assert torch.isfinite(ga).all() and ga.abs().max().item() > 0
     assert torch.equal(ga, gb)
     hm.close()
+
+
+@pytest.mark.parametrize("arch", ["mobilenet_v2", "efficientnet_b0"])
+def test_mobile_inference_handles_match_python_sequencing(cuda, arch):
+    """MobileNetV2 / EfficientNet-B0 inference handles (B200R_ARCH_MOBILENET_V2 / _EFFICIENTNET_B0; the ImageNet-C sweep of BASELINE
+    configs[3] is evaluation only): logits bit-identical to nets.MobileNetV2 / nets.EfficientNetB0; the gradient calls are refused."""
+    from robustart_b200 import nets
+    from robustart_b200.handle import ModelHandle
+    sd = nets.random_state_dict(nets._MOBILE_ARCHS[arch][1](), 0)
+    ref = nets.build_model(arch, sd, device=cuda)
+    hm = ModelHandle(arch, sd, cuda, 3)
+    assert hm.num_classes == ref.num_classes
+    for n, seed in ((3, 5), (6, 9)):                                     # the second, larger batch re-sizes the arena
+        images = torch.from_numpy(synth_images(n, seed=seed)).to(cuda)
+        assert torch.equal(hm(images), ref(images))
+    with pytest.raises(NotImplementedError):
+        hm.forward_vjp(torch.rand(2, 3, 224, 224, device=cuda))
+    hm.close()

@@ -18,7 +18,9 @@ EXACT = {"shot_noise", "impulse_noise"}
 # brightness / saturate: the HSV round trip often lands EXACTLY on an integer in real arithmetic
 # (e.g. saturate c=2: p*255 = 2*min - max), so fp64 rounding noise alone decides k vs k-1 in the
 # reference; fp32 decides differently on a large share of such pixels.  Still <= 1 LSB.
-MISMATCH_FRAC = {"default": 0.02, "brightness": 0.5, "saturate": 0.5, "fog": 0.05, "frost": 0.05}
+# Limits = ~1.5x the largest fraction measured on a B200 over the five severities of these seeds (round 2: brightness 0.094,
+# saturate 0.149, frost 0.028, everything else < 1e-4)
+MISMATCH_FRAC = {"default": 0.002, "brightness": 0.15, "saturate": 0.22, "fog": 0.002, "frost": 0.05}
 PIXEL_FAMILY = ["gaussian_noise", "shot_noise", "impulse_noise", "speckle_noise", "brightness", "saturate",
                 "contrast", "frost", "fog"]
 
@@ -60,8 +62,10 @@ STENCIL_FAMILY = ["gaussian_blur", "glass_blur", "defocus_blur", "zoom_blur", "m
 # kernels with a hard threshold / rounding step inside (snow: layer < c3 -> 0; motion: Q16 round half up;
 # elastic: OpenCV's 1/32-pixel coordinate quantisation and a displacement field scaled by up to 488 px):
 # an fp32-vs-fp64 tie flips a whole quantisation step at isolated pixels, bounded by OUTLIER_FRAC.
-OUTLIER_FRAC = {"snow": 2e-3, "motion_blur": 1e-3, "glass_blur": 2e-3, "elastic_transform": 5e-3}
-STENCIL_MISMATCH = {"elastic_transform": 0.25}
+# measured (round 2, these seeds): no pixel of snow / motion_blur / glass_blur off by more than 1 LSB; elastic 1.5e-4 (max 5 LSB);
+# pixels off by exactly 1 LSB: defocus 0.028 (severity 1), snow 1e-3, elastic 8e-4, the rest <= 5e-4
+OUTLIER_FRAC = {"snow": 2e-4, "motion_blur": 2e-4, "glass_blur": 2e-4, "elastic_transform": 5e-4}
+STENCIL_MISMATCH = {"elastic_transform": 0.003, "defocus_blur": 0.045, "snow": 0.003}
 
 
 @pytest.mark.parametrize("name", STENCIL_FAMILY)
@@ -74,7 +78,7 @@ def test_stencil_family_matches_oracle(cuda, name, sev):
     outl = (diff > 1).mean()
     assert outl <= OUTLIER_FRAC.get(name, 0.0), f"{name} s{sev}: {outl:.2e} of pixels differ by more than 1 LSB (max {diff.max()})"
     frac = np.count_nonzero(diff) / diff.size
-    assert frac <= STENCIL_MISMATCH.get(name, 0.03), f"{name} s{sev}: {frac:.4f} of pixels differ"
+    assert frac <= STENCIL_MISMATCH.get(name, 0.002), f"{name} s{sev}: {frac:.4f} of pixels differ"
     # in-place call gives the same bytes
     from robustart_b200 import ops
     d = torch.from_numpy(images).to(cuda)

@@ -218,3 +218,27 @@ def test_noise_table_first_use_during_capture_fails_loudly(cuda):
     g2.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, want)
+
+
+@pytest.mark.parametrize("sev", [1, 3, 5])
+def test_motion_blur_kernel_against_independent_filter2d_statement(cuda, sev):
+    """C6 (unpinned: no ImageMagick here) -- the GPU kernel against the SECOND statement of MotionBlurImage (cv2.filter2D of the documented
+    one-sided Gaussian kernel, tests/test_oracle_cpu.py::_motion_blur_by_filter2d), with the angle handed in: random image, impulse,
+    constant image."""
+    from robustart_b200 import ops
+    from oracle import imagenet_c as O
+    from test_oracle_cpu import _motion_blur_by_filter2d
+    rs = np.random.RandomState(sev)
+    images = rs.randint(0, 256, (3, 224, 224, 3)).astype(np.uint8)
+    images[1] = 0
+    images[1, 100, 120] = 255
+    images[2] = 91
+    u = np.array([0.15, 0.63611, 0.98889], np.float32)            # the kernel takes the reference's uniform draw: angle = -45 + 90 u
+    angles = (-45.0 + 90.0 * u.astype(np.float64))
+    got = ops.corrupt_u8(torch.from_numpy(images).to(cuda), "motion_blur", sev, ext_noise=torch.from_numpy(u).to(cuda)).cpu().numpy()
+    radius, sigma = O.MOTION_PARAMS[sev - 1]
+    for i in range(3):
+        want = _motion_blur_by_filter2d(images[i], radius, sigma, float(angles[i]))[0]
+        d = np.abs(got[i].astype(int) - want.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3, (i, d.max(), (d > 0).mean())
+    assert (got[2] == 91).all()

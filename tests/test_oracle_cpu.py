@@ -328,3 +328,56 @@ def test_l1_projection_restatement_matches_reference_code():
         assert np.abs(d - g["d%d" % k]).max() <= 1e-7, k
         z = y.numpy() + d
         assert np.abs(z).sum(1).max() <= eps * (1 + 1e-5) and (x.numpy() + z).min() >= -1e-6 and (x.numpy() + z).max() <= 1 + 1e-6
+
+
+def _motion_blur_by_filter2d(img_u8, radius, sigma, angle_deg):
+    """A second, independent evaluation of ImageMagick's MotionBlurImage for the unpinned C6 / C8 rows (Wand is absent here): the
+    one-sided Gaussian kernel of the documented definition (effect.c GetMotionBlurKernel: k[i] ~ exp(-i^2 / 2 sigma^2), i = 0..width-1,
+    width = 2 ceil(radius) + 1; offsets ceil(i cos(a) - 0.5), ceil(i sin(a) - 0.5) along the angle) rasterised into a dense 2-D kernel
+    and applied by OpenCV's filter2D with a replicated border, on the Q16 values; then ImageMagick's quantum rounding."""
+    import math
+    import cv2
+    width = int(2 * math.ceil(radius) + 1)
+    i = np.arange(width, dtype=np.float64)
+    k = np.exp(-i * i / (2 * sigma * sigma))
+    k /= k.sum()
+    a = math.radians(angle_deg)
+    ox = np.ceil(i * math.cos(a) - 0.5).astype(int)
+    oy = np.ceil(i * math.sin(a) - 0.5).astype(int)
+    R = width
+    dense = np.zeros((2 * R + 1, 2 * R + 1), np.float64)
+    for w, dx, dy in zip(k, ox, oy):
+        dense[R + dy, R + dx] += w                       # filter2D correlates: out(y, x) = sum K[j, i] * src(y + j - R, x + i - R)
+    q = cv2.filter2D(img_u8.astype(np.float64) * 257.0, cv2.CV_64F, dense, borderType=cv2.BORDER_REPLICATE)
+    q = np.floor(np.clip(q, 0, 65535.0) + 0.5)
+    return np.floor((q + 128.0) / 257.0).astype(np.uint8), k, ox, oy
+
+
+def test_motion_blur_second_independent_statement():
+    """VERDICT r1 missing #8: motion_blur / snow are unpinned (no ImageMagick here).  The oracle's restatement is cross-checked against
+    an independent evaluation through cv2.filter2D and against the documented properties of the kernel."""
+    from oracle import imagenet_c as O
+    rs = np.random.RandomState(3)
+    img = rs.randint(0, 256, (64, 80, 3)).astype(np.uint8)
+    for (radius, sigma) in O.MOTION_PARAMS:
+        for angle in (-45.0, -17.3, 0.0, 8.9, 44.9, 135.0, -120.0):
+            want = O.magick_motion_blur_u8(img, radius, sigma, angle)
+            got, k, ox, oy = _motion_blur_by_filter2d(img, radius, sigma, angle)
+            d = np.abs(got.astype(int) - want.astype(int))
+            assert d.max() <= 1 and (d > 0).mean() < 1e-3, (radius, sigma, angle, d.max(), (d > 0).mean())   # fp64 summation order only
+            # documented properties: normalised, one-sided (starts at the pixel itself), monotonically decreasing, width 2 ceil(r) + 1
+            assert abs(k.sum() - 1) < 1e-12 and len(k) == 2 * int(np.ceil(radius)) + 1 and (np.diff(k) < 0).all()
+            assert ox[0] == 0 and oy[0] == 0
+            # the smear runs along the angle: the farthest tap sits at distance ~ width - 1 in direction (cos a, sin a)
+            far = np.array([ox[-1], oy[-1]], float)
+            dirv = np.array([np.cos(np.radians(angle)), np.sin(np.radians(angle))])
+            assert abs(np.linalg.norm(far) - (len(k) - 1)) <= 1.0 and far @ dirv > 0.98 * np.linalg.norm(far)
+    # a constant image is a fixed point; an impulse spreads into exactly the kernel's taps
+    const = np.full((32, 32, 3), 137, np.uint8)
+    assert (O.magick_motion_blur_u8(const, 15, 8, 30.0) == 137).all()
+    imp = np.zeros((64, 64, 3), np.uint8)
+    imp[32, 32] = 255
+    out = O.magick_motion_blur_u8(imp, 10, 3, 20.0)
+    kk, ox, oy = O.motion_blur_kernel(10, 3, 20.0)
+    ys, xs = np.nonzero(out[..., 0])
+    assert set(zip(ys.tolist(), xs.tolist())) <= {(32 - int(b), 32 - int(a)) for a, b in zip(ox, oy)}       # the tap reads src(x + ox): the impulse lands at x - ox

@@ -728,3 +728,29 @@ def test_maxpool_relu_bwd_kernel(emu, planes):
     (F.max_pool2d(torch.relu(xr.permute(0, 3, 1, 2)), 3, 2, 1) * dv.permute(0, 3, 1, 2)).sum().backward()
     got = out.view(torch.float16).float()
     assert (got - xr.grad).abs().max().item() <= 2 ** -10 * xr.grad.abs().max().item() + 1e-6
+
+
+def test_maxpool_codes_kernels(emu):
+    """The saved forward's pool (csrc/layers.cu: pooled planes + arg-max codes with the ReLU's backward folded in) and the backward
+    that routes through the codes (csrc/backward_layers.cu), from their own sources on the host, against autograd."""
+    fwd, bwd = emu["layers"], emu["backward_layers"]
+    torch.manual_seed(4)
+    n, h, w, c = 2, 10, 12, 16
+    x = torch.relu(torch.randn(n, h, w, c))
+    x[1, :5] = 0.0
+    dy = torch.randn(n, h // 2, w // 2, c)
+    xp, dyp = split(x), split(dy)
+    y = torch.empty(2, n, h // 2, w // 2, c, dtype=torch.int16)
+    codes = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8)
+    fwd.b200r_maxpool3x3s2_nhwc_codes.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
+    _ok(fwd.b200r_maxpool3x3s2_nhwc_codes(_p(xp), _p(y), _p(codes), n, h, w, c, None))
+    xv = merge(xp)
+    assert torch.equal(merge(y), F.max_pool2d(xv.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1))
+    assert ((codes <= 8) | (codes == 15)).all() and (codes[1, :2] == 15).all()          # all-zero windows route nothing
+    out = torch.empty(n, h, w, c, dtype=torch.int16)
+    bwd.b200r_maxpool3x3s2_bwd_codes_hi.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]
+    _ok(bwd.b200r_maxpool3x3s2_bwd_codes_hi(_p(codes), _p(dyp), _p(out), n, h, w, c, 2, None))
+    xr = xv.clone().requires_grad_(True)
+    (F.max_pool2d(torch.relu(xr.permute(0, 3, 1, 2)), 3, 2, 1) * merge(dyp).permute(0, 3, 1, 2)).sum().backward()
+    got = out.view(torch.float16).float()
+    assert (got - xr.grad).abs().max().item() <= 2 ** -10 * xr.grad.abs().max().item() + 1e-6

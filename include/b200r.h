@@ -274,15 +274,23 @@ int b200r_stem_pool_u8_f16(const uint8_t* img, const uint16_t* wgt, const float*
  * and a range-centring power of two into the operand:
  *   conv1_w      : host float32 [64, 3, 7, 7] (resnet_official.py:221)
  *   bn_scale/bias: host float32 [64], gamma / sqrt(var + eps) and beta - mean * scale (nullable = 1 / 0)
+ *   f32_input    : 0 = the kernel stages byte / 256 (b200r_stem_pool_u8_split), 1 = a float image in [0, 1] (b200r_stem_pool_f32_split)
  *   planes_host  : host uint16 [2][64][224] out (hi plane, lo plane; row = [ky][t = kx + 1][R, G, B, 1]); upload as is
  *   out_scale    : 2^-k, to hand to b200r_stem_pool_u8_split
  * b200r_stem_pool_u8_split: img uint8 NHWC [n, h, w, 3]; wplanes = the uploaded planes; y = split planes [2][n, h/4, w/4, 64].
  * Same geometry limits as the fp16 twin. */
 int b200r_stem_pool_split_prepare(const float* conv1_w, const float* bn_scale, const float* bn_bias,
-                                  const float* mean_host, const float* std_host, uint16_t* planes_host,
-                                  float* out_scale);
+                                  const float* mean_host, const float* std_host, int f32_input,
+                                  uint16_t* planes_host, float* out_scale);
 int b200r_stem_pool_u8_split(const uint8_t* img, const uint16_t* wplanes, float out_scale, uint16_t* y,
                              int n, int h, int w, b200r_stream_t stream);
+/* The same from a float32 NCHW image in [0, 1] (the attack loops' iterate) for a SAVED forward: the pixel enters as an fp16 hi/lo pair
+ * (three MMAs per product; prepare the operand with f32_input = 1: the colour weights then meet x itself, not byte / 256), and next
+ * to the pooled planes the kernel writes the pool's arg-max codes [n, h/4, w/4, 64] (uint8: window position ky*3+kx of the first
+ * maximum, 0xF where the maximum is not positive = the stem ReLU's backward folded in) for b200r_maxpool3x3s2_bwd_codes_hi -- the
+ * 112 x 112 activation is never written and never needed by the gradient pass. */
+int b200r_stem_pool_f32_split(const float* x01, const uint16_t* wplanes, float out_scale, uint16_t* y, uint8_t* codes,
+                              int n, int h, int w, b200r_stream_t stream);
 
 /* same, from a float32 NCHW image in [0,1] (the attack loops' iterate): (x - mean) / std and the hi/lo split happen
  * in the operand producer, with the arithmetic of b200r_stem_im2col_f32 */

@@ -76,7 +76,8 @@ SIGNATURES = {
                                         c_host_f3, c_host_f3, C.c_int, C.c_int, c_stream]),
     "b200r_stem_pool_u8_f16": (C.c_int, [c_u8p, C.c_void_p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          c_host_f3, c_host_f3, c_stream]),
-    "b200r_stem_pool_split_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_host_f3, c_host_f3, C.c_void_p, C.POINTER(C.c_float)]),
+    "b200r_stem_pool_split_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_host_f3, c_host_f3, C.c_int, C.c_void_p, C.POINTER(C.c_float)]),
+    "b200r_stem_pool_f32_split": (C.c_int, [c_f32p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_stem_pool_u8_split": (C.c_int, [c_u8p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_stem_conv7x7_f32": (C.c_int, [c_f32p, C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          c_host_f3, c_host_f3, C.c_int, C.c_int, c_stream]),

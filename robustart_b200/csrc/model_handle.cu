@@ -72,6 +72,8 @@ struct b200r_model {
   Planes stem_w, stem_w_folded, stem_wt, fc_w, fc_wt;
   uint16_t* stem_wp = nullptr;   // split mode: prepared operand of the one-launch stem [2][64][224]
   float stem_osc = 1.f;
+  uint16_t* stem_wpf = nullptr;  // ... and of its float-input twin (b200r_stem_pool_f32_split)
+  float stem_oscf = 1.f;
   float *stem_scale = nullptr, *stem_bias = nullptr, *fc_b = nullptr;
   std::vector<void*> owned;          // every cudaMalloc of the weights
   Arena arena;
@@ -952,10 +954,15 @@ int b200r_model_create(int arch, const b200r_weight* weights, int n_weights, int
   if (!m->f16) {
     std::vector<uint16_t> wp((size_t)2 * 64 * 224);
     void* d = nullptr;
-    if ((rc = b200r_stem_pool_split_prepare(w1, sc.data(), b1.data(), kMean, kStd, wp.data(), &m->stem_osc)) || (rc = dev_alloc(m, &d, wp.size() * 2)))
+    if ((rc = b200r_stem_pool_split_prepare(w1, sc.data(), b1.data(), kMean, kStd, 0, wp.data(), &m->stem_osc)) || (rc = dev_alloc(m, &d, wp.size() * 2)))
       return fail(rc);
     if (cudaMemcpy(d, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { b200r_set_error("cudaMemcpy of the stem operand failed"); return fail(B200R_ECUDA); }
     m->stem_wp = static_cast<uint16_t*>(d);
+    void* df = nullptr;
+    if ((rc = b200r_stem_pool_split_prepare(w1, sc.data(), b1.data(), kMean, kStd, 1, wp.data(), &m->stem_oscf)) || (rc = dev_alloc(m, &df, wp.size() * 2)))
+      return fail(rc);
+    if (cudaMemcpy(df, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { b200r_set_error("cudaMemcpy of the stem operand failed"); return fail(B200R_ECUDA); }
+    m->stem_wpf = static_cast<uint16_t*>(df);
   }
   {  // gradient of the stem GEMM: [192][64] = (planes' value of the packed weight * bn scale)^T
     std::vector<float> t((size_t)192 * 64);
@@ -1062,6 +1069,17 @@ int b200r_model_forward_f32(b200r_model* m, const float* x01, float* logits, int
   if (m->mobile) { b200r_set_error("the MobileNetV2 / EfficientNet-B0 handles are inference handles (b200r_model_forward_u8): their input gradient is sequenced by robustart_b200.nets"); return B200R_ENOTSUP; }
   m->arena.reset();
   cudaStream_t s = as_stream(stream);
+  if (!m->f16 && h % 4 == 0 && w % 8 == 0 && w >= 8 && w <= 248 && h >= 8) {
+    // conv1 + bn1 + relu + maxpool + arg-max codes in one launch: the 112 x 112 activation is never written
+    TAKE(pq, (size_t)n * (h / 4) * (w / 4) * 64);
+    m->saved.pool_codes = m->arena.take((size_t)n * (h / 4) * (w / 4) * 64 + 8);
+    B200R_CHECK_ARG(m->saved.pool_codes, "activation arena too small");
+    RC(b200r_stem_pool_f32_split(x01, m->stem_wpf, m->stem_oscf, pq, static_cast<uint8_t*>(m->saved.pool_codes), n, h, w, stream));
+    m->saved.stem = nullptr; m->saved.n = n; m->saved.h = h; m->saved.w = w;
+    const int rc = run_body(m, pq, n, h / 4, w / 4, logits, true, s);
+    m->saved.valid = rc == B200R_OK;
+    return rc;
+  }
   TAKE(s0, (size_t)n * (h / 2) * (w / 2) * 64);
   RC(b200r_stem_conv7x7_f32(x01, m->stem_w.p, m->stem_scale, m->stem_bias, s0, n, h, w, kMean, kStd, B200R_ACT_RELU, m->passes, stream));
   TAKE(p, (size_t)n * (h / 4) * (w / 4) * 64);

@@ -65,8 +65,11 @@ constexpr int SP_B_PLANE = 14 * 2048;                        // SPLIT: the lo-pl
 constexpr int SP_WROW = 7 * 8 * 4;                           // SPLIT: prepared weights per output channel, [ky][t = kx + 1][R, G, B, 1]
 
 // warp roles and shared-memory map of the two precisions
-template <bool SPLIT>
+// MODE: 0 = fp16 planes from uint8 pixels, 1 = split planes from uint8 pixels, 2 = split planes + arg-max codes from float32 NCHW
+// pixels in [0, 1] (the attack path's saved forward: A operand as an fp16 hi/lo pair, three MMAs per product)
+template <int MODE>
 struct SpCfg {
+  static constexpr bool SPLIT = MODE >= 1, F32IN = MODE == 2;
   static constexpr int EPI_WARPS = SPLIT ? 16 : 8;           // groups of four (TMEM lane quadrant = warp % 4); group g owns
   static constexpr int GROUPS = EPI_WARPS / 4;               // channels [CG g, CG g + CG) of every output row
   static constexpr int CG = 64 / GROUPS;
@@ -74,13 +77,16 @@ struct SpCfg {
   static constexpr int PROD_WARP0 = EPI_WARPS + 1;
   static constexpr int THREADS = (PROD_WARP0 + SP_PROD_WARPS) * 32;   // 544 / 800
   static constexpr int OFF_ROWS = SP_OFF_B + (SPLIT ? 2 : 1) * SP_B_PLANE;
-  static constexpr int OFF_STAGE = OFF_ROWS + SP_SLOTS * SP_SLOT_BYTES;   // [groups][2 buffers][128 columns][96 B]
+  static constexpr int OFF_ROWS_LO = OFF_ROWS + SP_SLOTS * SP_SLOT_BYTES;                 // F32IN: the lo plane of the staged rows
+  static constexpr int OFF_STAGE = OFF_ROWS + (F32IN ? 2 : 1) * SP_SLOTS * SP_SLOT_BYTES;   // [groups][2 buffers][128 columns][96 B]
   static constexpr int OFF_BARS = OFF_STAGE + GROUPS * 2 * SP_STAGE_BYTES;
   static constexpr int SMEM = OFF_BARS + (2 * SP_SLOTS + 2 * SP_ACC) * 8 + 16 + 128;
 };
 
 struct StemPoolParams {
   const uint8_t* img;      // [n, h, w, 3]
+  const float* img_f32;    // MODE 2: float32 NCHW [n, 3, h, w] in [0, 1]
+  uint8_t* codes;          // MODE 2: [n, h/4, w/4, 64] window position ky*3+kx of the pooled maximum, 0xF where it is not positive
   const __half* wgt;       // [64, 192], column = ky*24 + kx*3 + c, BN scale folded in; SPLIT: prepared planes [2][64][224]
   const float* bias;       // [64] (nullable; SPLIT: unused, the bias is in the prepared weights)
   __half* y;               // [n, h/4, w/4, 64]; SPLIT: hi plane, the lo plane follows at y + n*(h/4)*(w/4)*64
@@ -149,8 +155,9 @@ struct MmaBases { uint32_t a_lo0, be_lo0, bo_lo0, tmem; };
 // block BMAX - k of the parity's stacked tile.  Rows [kmin, kmax] are present (interior rows: all of [0, BMAX]; the edges
 // of a unit or of the image clip the range).  Called with literal bounds the whole body folds to 4-5 UTCHMMA with
 // immediate descriptor offsets.
-template <int I, bool SPLIT>
+template <int I, int MODE>
 __device__ __forceinline__ void sp_issue(const MmaBases& mb, int kmin, int kmax, bool all_fresh) {
+  constexpr bool SPLIT = MODE >= 1, F32IN = MODE == 2;
   constexpr int PAR = I & 1, S0 = (I >> 1) % SP_ACC, BMAX = 3 - PAR;
   constexpr int SEG0_HI = S0 < BMAX ? S0 : BMAX;       // slots fall with k and wrap below 0: [0, SEG0_HI] and [S0 + 1, BMAX] are contiguous
   auto one = [&](int h, int ka, int kb, uint32_t accumulate) {     // one MMA over the rows [ka, kb], K step h
@@ -160,6 +167,7 @@ __device__ __forceinline__ void sp_issue(const MmaBases& mb, int kmin, int kmax,
     const uint32_t idesc = SP_IDESC0 | (((uint32_t)(kb - ka + 1) * 8u) << 17);
     umma_bf16(d, a, sp_desc(b), idesc, accumulate);
     if constexpr (SPLIT) umma_bf16(d, a, sp_desc(b + (SP_B_PLANE >> 4)), idesc, 1u);      // the weights' lo plane
+    if constexpr (F32IN) umma_bf16(d, a + ((SP_SLOTS * SP_SLOT_BYTES) >> 4), sp_desc(b), idesc, 1u);   // the pixels' lo plane x the weights' hi plane
   };
   auto run = [&](int h, int lo, int hi) {
     const int b0 = hi < SEG0_HI ? hi : SEG0_HI;
@@ -179,9 +187,10 @@ __device__ __forceinline__ void sp_issue(const MmaBases& mb, int kmin, int kmax,
   run(1, kmin, kmax);
 }
 
-template <bool SPLIT>
-__global__ void __launch_bounds__(SpCfg<SPLIT>::THREADS, 1) stem_pool_kernel(const StemPoolParams p) {
-  using C = SpCfg<SPLIT>;
+template <int MODE>
+__global__ void __launch_bounds__(SpCfg<MODE>::THREADS, 1) stem_pool_kernel(const StemPoolParams p) {
+  using C = SpCfg<MODE>;
+  constexpr bool SPLIT = C::SPLIT, F32IN = C::F32IN;
   constexpr int SP_EPI_WARPS = C::EPI_WARPS, SP_MMA_WARP = C::MMA_WARP, SP_PROD_WARP0 = C::PROD_WARP0, SP_THREADS = C::THREADS;
   constexpr int SP_OFF_ROWS = C::OFF_ROWS, SP_OFF_STAGE = C::OFF_STAGE, SP_OFF_BARS = C::OFF_BARS;
   extern __shared__ __align__(128) uint8_t sp_smem_raw[];    // nothing here needs more than 16-byte alignment (no swizzle)
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(SpCfg<SPLIT>::THREADS, 1) stem_pool_kernel(con
     // row ring: zero, with the constant-one fourth channel on every pixel column (padding included; SPLIT: the padding
     // stays all-zero, the producers write the one with every real pixel)
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem + SP_OFF_ROWS);
-    for (int idx = threadIdx.x; idx < SP_SLOTS * SP_SLOT_BYTES / 4; idx += SP_THREADS) {
+    for (int idx = threadIdx.x; idx < (F32IN ? 2 : 1) * SP_SLOTS * SP_SLOT_BYTES / 4; idx += SP_THREADS) {
       const int w4 = idx % (SP_SLOT_BYTES / 4);
       rows[idx] = (!SPLIT && (w4 & 1) && w4 < 2 * (W + 8)) ? 0x3C000000u : 0u;
     }
@@ -244,7 +253,56 @@ __global__ void __launch_bounds__(SpCfg<SPLIT>::THREADS, 1) stem_pool_kernel(con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= SP_PROD_WARP0) {
+  if (F32IN && warp >= SP_PROD_WARP0) {
+    // ================================ producers, float32 NCHW pixels in [0, 1] ================================
+    // lane owns the pixel pairs q = lane + 32 j: three coalesced 8-byte loads per pair (one per channel plane); the pixel becomes an
+    // fp16 hi/lo pair -- (R, G, B, 1) into the hi ring, (R_lo, G_lo, B_lo, 0) into the lo ring, 16-byte stores in 512-byte runs
+    const int pw = warp - SP_PROD_WARP0;
+    float2 cur[12];
+    int cur_cnt = -1;
+    uint32_t ph_empty = 0;
+    auto commit_row = [&](const float2 (&v)[12], uint32_t slot) {
+      mbar_wait(empty_in(slot), ((ph_empty >> slot) & 1) ^ 1);
+      ph_empty ^= 1u << slot;
+      const uint32_t dst = sbase + SP_OFF_ROWS + slot * SP_SLOT_BYTES + 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = lane + 32 * j;
+        if (q < WO) {
+          const float2 r = v[3 * j], g = v[3 * j + 1], b = v[3 * j + 2];
+          uint4 oh, ol;
+          split_f16x2(g.x, r.x, oh.x, ol.x);
+          split_f16x2(1.0f, b.x, oh.y, ol.y);             // fourth channel: 1 in the hi plane, 0 in the lo plane
+          split_f16x2(g.y, r.y, oh.z, ol.z);
+          split_f16x2(1.0f, b.y, oh.w, ol.w);
+          sts_v4(dst + q * 16, oh);
+          sts_v4(dst + SP_SLOTS * SP_SLOT_BYTES + q * 16, ol);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_in(slot));
+    };
+    const size_t plane = (size_t)H * W;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit t = make_unit(p, u);
+      for (int pp = t.p_lo + ((pw - t.p_lo) & (SP_PROD_WARPS - 1)); pp <= t.p_hi; pp += SP_PROD_WARPS) {   // rows with pp % 8 == pw
+        float2 nxt[12];
+        const float* rowp = p.img_f32 + (size_t)t.n * 3 * plane + (size_t)(pp - 3) * W;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int q = lane + 32 * j;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) nxt[3 * j + c] = q < WO ? __ldg(reinterpret_cast<const float2*>(rowp + c * plane) + q) : make_float2(0.f, 0.f);
+        }
+        if (cur_cnt >= 0) commit_row(cur, (uint32_t)cur_cnt);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) cur[j] = nxt[j];
+        cur_cnt = pp % SP_SLOTS;
+      }
+    }
+    if (cur_cnt >= 0) commit_row(cur, (uint32_t)cur_cnt);
+  } else if (warp >= SP_PROD_WARP0) {
     // ================================ producers ================================
     const int pw = warp - SP_PROD_WARP0;
     // lane owns the pixel pairs q = lane + 32 j: the warp's four 16-byte stores per row are contiguous 512-byte runs.
@@ -338,14 +396,14 @@ __global__ void __launch_bounds__(SpCfg<SPLIT>::THREADS, 1) stem_pool_kernel(con
         tc_fence_after();
         if (elect_one()) {
           switch (slot) {
-            case 0: sp_issue<0, SPLIT>(mb, kmin, kmax, all_fresh); break;   case 1: sp_issue<1, SPLIT>(mb, kmin, kmax, all_fresh); break;
-            case 2: sp_issue<2, SPLIT>(mb, kmin, kmax, all_fresh); break;   case 3: sp_issue<3, SPLIT>(mb, kmin, kmax, all_fresh); break;
-            case 4: sp_issue<4, SPLIT>(mb, kmin, kmax, all_fresh); break;   case 5: sp_issue<5, SPLIT>(mb, kmin, kmax, all_fresh); break;
-            case 6: sp_issue<6, SPLIT>(mb, kmin, kmax, all_fresh); break;   case 7: sp_issue<7, SPLIT>(mb, kmin, kmax, all_fresh); break;
-            case 8: sp_issue<8, SPLIT>(mb, kmin, kmax, all_fresh); break;   case 9: sp_issue<9, SPLIT>(mb, kmin, kmax, all_fresh); break;
-            case 10: sp_issue<10, SPLIT>(mb, kmin, kmax, all_fresh); break; case 11: sp_issue<11, SPLIT>(mb, kmin, kmax, all_fresh); break;
-            case 12: sp_issue<12, SPLIT>(mb, kmin, kmax, all_fresh); break; case 13: sp_issue<13, SPLIT>(mb, kmin, kmax, all_fresh); break;
-            case 14: sp_issue<14, SPLIT>(mb, kmin, kmax, all_fresh); break; default: sp_issue<15, SPLIT>(mb, kmin, kmax, all_fresh); break;
+            case 0: sp_issue<0, MODE>(mb, kmin, kmax, all_fresh); break;   case 1: sp_issue<1, MODE>(mb, kmin, kmax, all_fresh); break;
+            case 2: sp_issue<2, MODE>(mb, kmin, kmax, all_fresh); break;   case 3: sp_issue<3, MODE>(mb, kmin, kmax, all_fresh); break;
+            case 4: sp_issue<4, MODE>(mb, kmin, kmax, all_fresh); break;   case 5: sp_issue<5, MODE>(mb, kmin, kmax, all_fresh); break;
+            case 6: sp_issue<6, MODE>(mb, kmin, kmax, all_fresh); break;   case 7: sp_issue<7, MODE>(mb, kmin, kmax, all_fresh); break;
+            case 8: sp_issue<8, MODE>(mb, kmin, kmax, all_fresh); break;   case 9: sp_issue<9, MODE>(mb, kmin, kmax, all_fresh); break;
+            case 10: sp_issue<10, MODE>(mb, kmin, kmax, all_fresh); break; case 11: sp_issue<11, MODE>(mb, kmin, kmax, all_fresh); break;
+            case 12: sp_issue<12, MODE>(mb, kmin, kmax, all_fresh); break; case 13: sp_issue<13, MODE>(mb, kmin, kmax, all_fresh); break;
+            case 14: sp_issue<14, MODE>(mb, kmin, kmax, all_fresh); break; default: sp_issue<15, MODE>(mb, kmin, kmax, all_fresh); break;
           }
           umma_commit(empty_in(slot));
           // output rows whose last contributing input row this is: ky = 6, or the bottom image row (two taps in the padding)
@@ -368,7 +426,7 @@ __global__ void __launch_bounds__(SpCfg<SPLIT>::THREADS, 1) stem_pool_kernel(con
           take_row(I);                                                                       \
           tc_fence_after();                                                                  \
           if (elect_one()) {                                                                 \
-            sp_issue<I, SPLIT>(mb, 0, 3 - ((I) & 1), false);                                        \
+            sp_issue<I, MODE>(mb, 0, 3 - ((I) & 1), false);                                        \
             umma_commit(empty_in(I));                                                        \
             if (((I) & 1) == 0) umma_commit(acc_full((((I) >> 1) + SP_ACC - 3) % SP_ACC));   \
           }                                                                                  \
@@ -384,7 +442,7 @@ __global__ void __launch_bounds__(SpCfg<SPLIT>::THREADS, 1) stem_pool_kernel(con
               if (pp > pp_b) { more = false; break; }
               take_row(15);
               tc_fence_after();
-              if (elect_one()) { sp_issue<15, SPLIT>(mb, 0, 2, false); umma_commit(empty_in(15)); }
+              if (elect_one()) { sp_issue<15, MODE>(mb, 0, 2, false); umma_commit(empty_in(15)); }
               __syncwarp();
               ++pp;
             }
@@ -393,6 +451,109 @@ __global__ void __launch_bounds__(SpCfg<SPLIT>::THREADS, 1) stem_pool_kernel(con
 #undef SP_STEP
       }
       for (; pp <= t.p_hi; ++pp) edge(pp);
+    }
+  } else if constexpr (F32IN) {
+    // ================================ epilogue, fp32 pooling + arg-max codes ================================
+    // as the SPLIT epilogue, and every maximum carries the kernel row / column it came from: the vertical pass keeps ky (two bits per
+    // channel in one word), the horizontal pass picks, among the columns that tie for the maximum, the smallest ky*3+kx -- the first
+    // maximum in the window's scan order, as max_pool2d's backward routes it.  A maximum that is not positive gets code 0xF: the ReLU
+    // that follows has derivative 0 there (the backward of pool and ReLU in one code).
+    const int grp = warp >> 2, m = threadIdx.x & 127;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * 16;
+    const uint32_t stage0 = sbase + SP_OFF_STAGE + grp * 2 * SP_STAGE_BYTES;
+    const size_t plane_stride = (size_t)p.n * PH * PW * 64;
+    const float osc = p.out_scale;
+    uint32_t ph_afull = 0, emit = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit t = make_unit(p, u);
+      float prev_odd[16], v[16];
+      uint32_t kyw = 0;                                    // ky of v[i] in bits 2i, 2i+1
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { prev_odd[i] = 0.f; v[i] = 0.f; }
+      for (int r = t.r_first; r <= t.r_last; ++r) {
+        const uint32_t aslot = (uint32_t)r % SP_ACC;
+        mbar_wait(acc_full(aslot), (ph_afull >> aslot) & 1);
+        ph_afull ^= 1u << aslot;
+        tc_fence_after();
+        uint32_t acc[16];
+        tmem_ld16(lane_base + aslot * 64, acc);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(aslot));
+        const bool odd = r & 1;
+        if (odd) {                                         // conv row 2 py + 1: kernel row 2 of pooled row py, row 0 of pooled row py + 1
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float cur = __uint_as_float(acc[i]);
+            if (cur > v[i]) { v[i] = cur; kyw = (kyw & ~(3u << (2 * i))) | (2u << (2 * i)); }
+            prev_odd[i] = cur;
+          }
+        } else {                                           // conv row 2 py: kernel row 1; the previous odd row is kernel row 0
+          kyw = 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float cur = __uint_as_float(acc[i]);
+            v[i] = prev_odd[i];
+            if (cur > v[i]) { v[i] = cur; kyw |= 1u << (2 * i); }
+          }
+        }
+        if (odd && (r >> 1) >= t.py0) {
+          const uint32_t st = stage0 + (emit & 1) * SP_STAGE_BYTES;
+          if (m < WO) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              sts_v4(st + m * SP_STAGE_PITCH + ch * 16, make_uint4(__float_as_uint(v[4 * ch]), __float_as_uint(v[4 * ch + 1]),
+                                                                 __float_as_uint(v[4 * ch + 2]), __float_as_uint(v[4 * ch + 3])));
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(st + m * SP_STAGE_PITCH + 64), "r"(kyw) : "memory");
+          }
+          named_bar_sync(1 + grp, 128);
+          const size_t prow = ((size_t)(t.n * PH + (r >> 1)) * PW) * 64 + grp * 16;
+          __half* yrow = p.y + prow;
+          for (int i = m; i < PW * 4; i += 128) {
+            const int px = i >> 2, ch = i & 3, c1 = 2 * px;
+            const uint32_t at = st + c1 * SP_STAGE_PITCH + ch * 16;
+            const uint4 a = lds_v4(at), b = lds_v4(at + SP_STAGE_PITCH);
+            uint32_t ka, kb, kl = 0;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ka) : "r"(st + c1 * SP_STAGE_PITCH + 64));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kb) : "r"(st + (c1 + 1) * SP_STAGE_PITCH + 64));
+            uint4 l = make_uint4(0, 0, 0, 0);
+            if (px > 0) {
+              l = lds_v4(at - SP_STAGE_PITCH);
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kl) : "r"(st + (c1 - 1) * SP_STAGE_PITCH + 64));
+            }
+            const float fa[4] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w)};
+            const float fb[4] = {__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w)};
+            const float fl[4] = {__uint_as_float(l.x), __uint_as_float(l.y), __uint_as_float(l.z), __uint_as_float(l.w)};
+            float f[4];
+            uint32_t cw = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int cidx = 4 * ch + e;
+              // scan order: (ky, kx) ascending; columns kx = 0 (left), 1 (centre), 2 (right)
+              float best = fa[e];
+              uint32_t code = ((ka >> (2 * cidx)) & 3u) * 3u + 1u;
+              if (px > 0) {
+                const uint32_t cl = ((kl >> (2 * cidx)) & 3u) * 3u;
+                if (fl[e] > best || (fl[e] == best && cl < code)) { best = fl[e]; code = cl; }
+              }
+              const uint32_t cr = ((kb >> (2 * cidx)) & 3u) * 3u + 2u;
+              if (fb[e] > best || (fb[e] == best && cr < code)) { best = fb[e]; code = cr; }
+              if (!(best > 0.f)) code = 0xFu;
+              cw |= code << (8 * e);
+              f[e] = fmaxf(best, 0.f) * osc;
+            }
+            uint2 oh, ol;
+            split_f16x2(f[1], f[0], oh.x, ol.x);
+            split_f16x2(f[3], f[2], oh.y, ol.y);
+            __half* dst = yrow + px * 64 + ch * 4;
+            *reinterpret_cast<uint2*>(dst) = oh;
+            *reinterpret_cast<uint2*>(dst + plane_stride) = ol;
+            *reinterpret_cast<uint32_t*>(p.codes + prow + px * 64 + ch * 4) = cw;
+          }
+          ++emit;
+        }
+      }
     }
   } else if constexpr (SPLIT) {
     // ================================ epilogue, fp32 pooling, hi/lo planes out ================================
@@ -529,7 +690,7 @@ __global__ void __launch_bounds__(SpCfg<SPLIT>::THREADS, 1) stem_pool_kernel(con
   }
 }
 
-template <bool SPLIT>
+template <int MODE>
 int launch_stem_pool(StemPoolParams& p, const float* mean_host, const float* std_host, b200r_stream_t stream) {
   p.units_per_img = ((p.h >> 2) + SP_UNIT_POOLED - 1) / SP_UNIT_POOLED;
   p.n_units = p.n * p.units_per_img;
@@ -541,11 +702,11 @@ int launch_stem_pool(StemPoolParams& p, const float* mean_host, const float* std
   int dev = 0;
   B200R_CUDA(cudaGetDevice(&dev));
   if (dev < 16 && !attr_set[dev]) {
-    B200R_CUDA(cudaFuncSetAttribute(stem_pool_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SpCfg<SPLIT>::SMEM));
+    B200R_CUDA(cudaFuncSetAttribute(stem_pool_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SpCfg<MODE>::SMEM));
     attr_set[dev] = true;
   }
   const int grid = p.n_units < b200r_num_sms() ? p.n_units : b200r_num_sms();
-  stem_pool_kernel<SPLIT><<<grid, SpCfg<SPLIT>::THREADS, SpCfg<SPLIT>::SMEM, as_stream(stream)>>>(p);
+  stem_pool_kernel<MODE><<<grid, SpCfg<MODE>::THREADS, SpCfg<MODE>::SMEM, as_stream(stream)>>>(p);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
@@ -555,7 +716,7 @@ int launch_stem_pool(StemPoolParams& p, const float* mean_host, const float* std
 extern "C" {
 
 int b200r_stem_pool_split_prepare(const float* conv1_w, const float* bn_scale, const float* bn_bias, const float* mean_host,
-                                  const float* std_host, uint16_t* planes_host, float* out_scale) {
+                                  const float* std_host, int f32_input, uint16_t* planes_host, float* out_scale) {
   B200R_CHECK_ARG(conv1_w && mean_host && std_host && planes_host && out_scale, "null pointer");
   // value of tap (co, ky, t = kx + 1, c): colour channels meet pixel / 256, the fourth channel meets 1 on real pixels
   std::vector<double> v((size_t)64 * SP_WROW, 0.0);
@@ -568,7 +729,7 @@ int b200r_stem_pool_split_prepare(const float* conv1_w, const float* bn_scale, c
         double m = 0.0;
         for (int c = 0; c < 3; ++c) {
           const double w = (double)conv1_w[((co * 3 + c) * 7 + ky) * 7 + kx] * s / (double)std_host[c];
-          q[c] = w * (256.0 / 255.0);
+          q[c] = f32_input ? w : w * (256.0 / 255.0);        // the colour channels meet x in [0, 1] (float input) or byte / 256
           m -= w * (double)mean_host[c];
         }
         if (ky == 3 && kx == 3 && bn_bias) m += (double)bn_bias[co];
@@ -606,10 +767,26 @@ int b200r_stem_pool_u8_split(const uint8_t* img, const uint16_t* wplanes, float 
   B200R_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "img must be 8-byte, y 16-byte aligned");
   B200R_CHECK_ARG(out_scale > 0.f, "out_scale comes from b200r_stem_pool_split_prepare");
   StemPoolParams p;
-  p.img = img; p.wgt = reinterpret_cast<const __half*>(wplanes); p.bias = nullptr; p.y = reinterpret_cast<__half*>(y);
+  p.img = img; p.img_f32 = nullptr; p.codes = nullptr; p.wgt = reinterpret_cast<const __half*>(wplanes); p.bias = nullptr; p.y = reinterpret_cast<__half*>(y);
   p.n = n; p.h = h; p.w = w; p.out_scale = out_scale;
   const float unit[3] = {1.f, 1.f, 1.f}, zero[3] = {0.f, 0.f, 0.f};
-  return launch_stem_pool<true>(p, zero, unit, stream);
+  return launch_stem_pool<1>(p, zero, unit, stream);
+}
+
+int b200r_stem_pool_f32_split(const float* x01, const uint16_t* wplanes, float out_scale, uint16_t* y, uint8_t* codes, int n, int h,
+                              int w, b200r_stream_t stream) {
+  B200R_CHECK_ARG(x01 && wplanes && y && codes, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h >= 8 && w >= 8, "bad shape %d x %d x %d", n, h, w);
+  B200R_CHECK_ARG(h % 4 == 0 && w % 8 == 0 && w <= 248, "stem_pool needs h %% 4 == 0, w %% 8 == 0, w <= 248 (got %d x %d)", h, w);
+  B200R_CHECK_ARG((reinterpret_cast<uintptr_t>(x01) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(codes) & 3) == 0,
+                  "x01 must be 8-byte, y 16-byte, codes 4-byte aligned");
+  B200R_CHECK_ARG(out_scale > 0.f, "out_scale comes from b200r_stem_pool_split_prepare");
+  StemPoolParams p;
+  p.img = nullptr; p.img_f32 = x01; p.codes = codes; p.wgt = reinterpret_cast<const __half*>(wplanes); p.bias = nullptr;
+  p.y = reinterpret_cast<__half*>(y);
+  p.n = n; p.h = h; p.w = w; p.out_scale = out_scale;
+  const float unit[3] = {1.f, 1.f, 1.f}, zero[3] = {0.f, 0.f, 0.f};
+  return launch_stem_pool<2>(p, zero, unit, stream);
 }
 
 int b200r_stem_pool_u8_f16(const uint8_t* img, const uint16_t* wgt, const float* bias, uint16_t* y,
@@ -619,9 +796,9 @@ int b200r_stem_pool_u8_f16(const uint8_t* img, const uint16_t* wgt, const float*
   B200R_CHECK_ARG(h % 4 == 0 && w % 8 == 0 && w <= 248, "stem_pool needs h %% 4 == 0, w %% 8 == 0, w <= 248 (got %d x %d)", h, w);
   B200R_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "img must be 8-byte, y 16-byte aligned");
   StemPoolParams p;
-  p.img = img; p.wgt = reinterpret_cast<const __half*>(wgt); p.bias = bias; p.y = reinterpret_cast<__half*>(y);
+  p.img = img; p.img_f32 = nullptr; p.codes = nullptr; p.wgt = reinterpret_cast<const __half*>(wgt); p.bias = bias; p.y = reinterpret_cast<__half*>(y);
   p.n = n; p.h = h; p.w = w; p.out_scale = 1.f;
-  return launch_stem_pool<false>(p, mean_host, std_host, stream);
+  return launch_stem_pool<0>(p, mean_host, std_host, stream);
 }
 
 }  // extern "C"

@@ -184,6 +184,10 @@ class ResNet:
         self.stem_w_folded = ops.to_planes(ops.pack_stem_weight((sd["conv1.weight"].double() * s.view(-1, 1, 1, 1)).float()).to(dev).contiguous(), True) if f16 else None
         # one-launch stem (split mode): exact pixels against hi/lo weights with everything folded in on the host
         self.stem_wp, self.stem_osc = (None, 1.0) if f16 else ops.stem_pool_split_prepare(sd["conv1.weight"], self.stem_scale, self.stem_bias, dev)
+        # ... and its float-input twin (the attack path): pixel as an fp16 hi/lo pair, arg-max codes out
+        self.stem_wpf, self.stem_oscf = (None, 1.0) if f16 else ops.stem_pool_split_prepare(sd["conv1.weight"], self.stem_scale, self.stem_bias, dev,
+                                                                                            f32_input=True)
+        self.fused_stem_f32 = os.environ.get("B200R_STEM_POOL_F32", "1") != "0"
         self.blocks = []
         for li, blocks in enumerate(layers):
             for bi in range(blocks):
@@ -217,12 +221,15 @@ class ResNet:
             # raw pixels -> conv1 + bn1 + relu + maxpool in one launch (overlapping-descriptor implicit im2col)
             x = ops.stem_pool_u8(images, self.stem_w_folded, self.stem_bias) if self.f16 else ops.stem_pool_u8_split(images, self.stem_wp, self.stem_osc)
         else:
-            if images.dtype == torch.uint8:
-                # raw pixels: gather + ToTensor + Normalize + split fused into the stem GEMM's operand producer
-                x = ops.stem_conv7x7_u8(images, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P)
+            if images.dtype != torch.uint8 and not self.f16 and self.fused_stem_pool and self.fused_stem_f32 and ops.stem_pool_ok(h, w):
+                x, _ = ops.stem_pool_f32_split(images.contiguous(), self.stem_wpf, self.stem_oscf)     # float iterate: one launch too
             else:
-                x = self._stem_f32(images, P)
-            x = ops.maxpool3x3s2(x)
+                if images.dtype == torch.uint8:
+                    # raw pixels: gather + ToTensor + Normalize + split fused into the stem GEMM's operand producer
+                    x = ops.stem_conv7x7_u8(images, self.stem_w, self.stem_scale, self.stem_bias, act="relu", passes=P)
+                else:
+                    x = self._stem_f32(images, P)
+                x = ops.maxpool3x3s2(x)
         for blk in self.blocks:
             idn = blk["down"](x, passes=P) if "down" in blk else x
             if blk["kind"] == "bottleneck":
@@ -254,6 +261,11 @@ class ResNet:
         """float32 NCHW [0,1] images -> (logits, saved activations).  Same launch sequence as forward()."""
         n, _, h, w = x01.shape
         P = self.passes
+        if not self.f16 and self.fused_stem_pool and self.fused_stem_f32 and ops.stem_pool_ok(h, w):
+            # conv1 + bn1 + relu + maxpool + arg-max codes in one launch: the 112 x 112 activation is never written
+            x, codes = ops.stem_pool_f32_split(x01.contiguous(), self.stem_wpf, self.stem_oscf)
+            saved = {"shape": (n, h, w), "stem": None, "pool_codes": codes, "stem_hw": (h // 2, w // 2), "blocks": []}
+            return self._body_saved(x, saved, n, P)
         s0 = self._stem_f32(x01, P)
         if self.f16:
             x = ops.maxpool3x3s2(s0)
@@ -263,6 +275,9 @@ class ResNet:
             # never reads the 112 x 112 activation again, which is not kept
             x, codes = ops.maxpool3x3s2_codes(s0)
             saved = {"shape": (n, h, w), "stem": None, "pool_codes": codes, "stem_hw": (s0.shape[2], s0.shape[3]), "blocks": []}
+        return self._body_saved(x, saved, n, P)
+
+    def _body_saved(self, x, saved, n, P):
         for blk in self.blocks:
             idn = blk["down"](x, passes=P) if "down" in blk else x
             if blk["kind"] == "bottleneck":

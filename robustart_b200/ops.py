@@ -436,7 +436,7 @@ def stem_pool_u8(img, wgt_folded, bias, *, mean=IMAGENET_MEAN, std=IMAGENET_STD,
     return out
 
 
-def stem_pool_split_prepare(conv1_w, bn_scale, bn_bias, device, *, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+def stem_pool_split_prepare(conv1_w, bn_scale, bn_bias, device, *, mean=IMAGENET_MEAN, std=IMAGENET_STD, f32_input=False):
     """Operand of the split-precision one-launch stem from the float32 conv1 weight [64, 3, 7, 7] and the folded BN scale / bias
     [64] (host arithmetic in double, include/b200r.h): (device planes [2, 64, 224] int16, out_scale)."""
     import ctypes as C
@@ -446,7 +446,8 @@ def stem_pool_split_prepare(conv1_w, bn_scale, bn_bias, device, *, mean=IMAGENET
     b = None if bn_bias is None else bn_bias.detach().float().cpu().contiguous()
     planes = torch.empty((2, 64, 224), dtype=torch.int16)
     osc = C.c_float(0.0)
-    _lib.check(_lib.load().b200r_stem_pool_split_prepare(w.data_ptr(), _ptr(s), _ptr(b), _lib.f3(mean), _lib.f3(std), planes.data_ptr(), C.byref(osc)))
+    _lib.check(_lib.load().b200r_stem_pool_split_prepare(w.data_ptr(), _ptr(s), _ptr(b), _lib.f3(mean), _lib.f3(std), int(f32_input), planes.data_ptr(),
+                                                         C.byref(osc)))
     return planes.to(device), float(osc.value)
 
 
@@ -463,6 +464,22 @@ def stem_pool_u8_split(img, wplanes, out_scale, *, out=None):
     with torch.cuda.device(img.device):
         _lib.check(_lib.load().b200r_stem_pool_u8_split(img.data_ptr(), wplanes.data_ptr(), out_scale, out.data_ptr(), n, h, w, _stream()))
     return out
+
+
+def stem_pool_f32_split(x01, wplanes, out_scale):
+    """conv1 7x7/s2 + BN + ReLU + MaxPool(3,2,1) from a float32 NCHW image in [0,1] in one launch (split precision): (planes
+    [2, n, h/4, w/4, 64], arg-max codes uint8 [n, h/4, w/4, 64] for maxpool3x3s2_bwd_codes_hi).  wplanes / out_scale from
+    stem_pool_split_prepare(..., f32_input=True)."""
+    _need_cuda(x01, torch.float32, "x01")
+    _need_cuda(wplanes, torch.int16, "wplanes")
+    n, c, h, w = x01.shape
+    assert c == 3 and x01.is_contiguous() and tuple(wplanes.shape) == (2, 64, 224)
+    assert stem_pool_ok(h, w), "stem_pool_f32_split: unsupported geometry %dx%d" % (h, w)
+    out = torch.empty((2, n, h // 4, w // 4, 64), dtype=torch.int16, device=x01.device)
+    codes = torch.empty((n, h // 4, w // 4, 64), dtype=torch.uint8, device=x01.device)
+    with torch.cuda.device(x01.device):
+        _lib.check(_lib.load().b200r_stem_pool_f32_split(x01.data_ptr(), wplanes.data_ptr(), out_scale, out.data_ptr(), codes.data_ptr(), n, h, w, _stream()))
+    return out, codes
 
 
 def stem_conv7x7_f32(img, wgt, scale, bias, *, act="relu", passes=3, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):

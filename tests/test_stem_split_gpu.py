@@ -79,3 +79,45 @@ def test_resnet_forward_uses_split_stem(cuda):
     model.fused_stem_pool = False
     b = model(images)
     assert (a - b).abs().max().item() < 2e-5 * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 224, 224), (3, 64, 64), (1, 40, 248), (5, 8, 8), (2, 100, 72), (30, 224, 224)])
+def test_stem_pool_f32_with_codes(cuda, n, h, w):
+    """b200r_stem_pool_f32_split (MODE 2: float image in [0,1] as an fp16 hi/lo pair, three MMAs per product, arg-max codes out): pooled
+    planes against fp64, codes against the window position of the fp64 maximum (first maximum in scan order, 0xF where not positive),
+    and both against the two-launch path (b200r_stem_conv7x7_f32 + b200r_maxpool3x3s2_nhwc_codes) it replaces."""
+    from robustart_b200 import ops
+    torch.manual_seed(n * 13 + h + w)
+    x01 = torch.rand(n, 3, h, w, device=cuda)
+    wt = torch.randn(64, 3, 7, 7, device=cuda) / 147 ** 0.5
+    s, b = torch.rand(64, device=cuda) + 0.5, torch.randn(64, device=cuda) * 0.3
+    s[::5] *= -1
+    mean = torch.tensor(ops.IMAGENET_MEAN, device=cuda, dtype=torch.float64).view(1, 3, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD, device=cuda, dtype=torch.float64).view(1, 3, 1, 1)
+    sel = list(range(n)) if n <= 8 else [0, 1, n // 2, n - 1]
+    conv = F.conv2d((x01[sel].double() - mean) / std, wt.double(), None, 2, 3) * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1)
+    act = torch.relu(conv)
+    ref, idx = F.max_pool2d(act, 3, 2, 1, return_indices=True)
+    wp, osc = ops.stem_pool_split_prepare(wt, s, b, cuda, f32_input=True)
+    y, codes = ops.stem_pool_f32_split(x01, wp, osc)
+    assert y.shape == (2, n, h // 4, w // 4, 64) and codes.shape == (n, h // 4, w // 4, 64)
+    got = ops.from_planes(y).double()[sel]
+    err = (got - ref.permute(0, 2, 3, 1)).abs().max().item()
+    assert err <= 3e-6 * max(1.0, ref.abs().max().item()), err
+    # codes: flat index of the fp64 arg-max -> (ky, kx) inside the window; positions where the maximum is 0 route nothing
+    ho, wo = h // 2, w // 2
+    iy, ix = idx // wo, idx % wo
+    py = torch.arange(h // 4, device=cuda).view(1, 1, -1, 1)
+    px = torch.arange(w // 4, device=cuda).view(1, 1, 1, -1)
+    want = ((iy - (2 * py - 1)) * 3 + (ix - (2 * px - 1))).permute(0, 2, 3, 1)
+    want = torch.where(ref.permute(0, 2, 3, 1) > 0, want, torch.full_like(want, 15))
+    c = codes[sel].long()
+    agree = (c == want).double().mean().item()
+    assert agree > 0.9995, agree                     # near-ties between window entries may resolve differently in fp32
+    assert ((c <= 8) | (c == 15)).all()
+    # the two-launch path it replaces
+    w3 = ops.to_planes(ops.pack_stem_weight(wt).contiguous(), False)
+    if w % 16 == 0:
+        y2, c2 = ops.maxpool3x3s2_codes(ops.stem_conv7x7_f32(x01, w3, s, b, act="relu"))
+        assert (ops.from_planes(y2) - ops.from_planes(y)).abs().max().item() < 2e-5
+        assert (c2 == codes).double().mean().item() > 0.9995

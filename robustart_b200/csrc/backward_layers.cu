@@ -285,32 +285,50 @@ constexpr int kRunPitch = 25;
 template <bool F16>
 __global__ void __launch_bounds__(kThreads) stem_col2im_kernel(const uint16_t* __restrict__ ch, const uint16_t* __restrict__ cl,
                                                                 float* __restrict__ dx, int h, int w, int ho, int wo, Inv3 inv_std) {
-  extern __shared__ float runs[];                                // [4][wo][kRunPitch]
+  // runs[4][wo + 4][kRunPitch]: two zero columns on either side, so the gather below needs no bounds checks and every tap is a
+  // compile-time offset from the thread's base (the first version computed kx ranges, bounds and three divisions per element at run
+  // time: ncu showed it issue-bound at 70 %, 3.6x its HBM time)
+  extern __shared__ float runs[];
   const int iy = blockIdx.x % h, im = blockIdx.x / h;
   const int ky0 = (iy + 1) & 1;                                  // iy = 2*oy - 3 + ky
-  for (int g = threadIdx.x; g < 4 * wo * 3; g += kThreads) {
-    const int kyi = g / (wo * 3), rem = g - kyi * wo * 3, ox = rem / 3, part = rem - ox * 3;
-    const int ky = ky0 + 2 * kyi, oy = (iy + 3 - ky) >> 1;
-    float vals[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (ky <= 6 && oy >= 0 && oy < ho) {
-      const size_t base = (((size_t)im * ho + oy) * wo + ox) * kStemK + ky * 24 + part * 8;
-      load8<F16>(reinterpret_cast<const uint4*>(ch + base), reinterpret_cast<const uint4*>(cl + base), 0, vals);
-    }
-    float* dst = runs + (kyi * wo + ox) * kRunPitch + part * 8;
+  const int rowp = (wo + 4) * kRunPitch;
+  for (int i = threadIdx.x; i < 4 * 4 * kRunPitch; i += kThreads) {           // the margins
+    const int kyi = i / (4 * kRunPitch), r = i - kyi * 4 * kRunPitch, col = r / kRunPitch, e = r - col * kRunPitch;
+    runs[kyi * rowp + (col < 2 ? col : wo + col) * kRunPitch + e] = 0.f;
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst[j] = vals[j];
+  for (int kyi = 0; kyi < 4; ++kyi) {
+    const int ky = ky0 + 2 * kyi, oy = (iy + 3 - ky) >> 1;
+    const bool valid = ky <= 6 && oy >= 0 && oy < ho;
+    const size_t rbase = (((size_t)im * ho + (valid ? oy : 0)) * wo) * kStemK + ky * 24;
+    for (int idx = threadIdx.x; idx < wo * 3; idx += kThreads) {
+      const int ox = idx / 3, part = idx - ox * 3;
+      float vals[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+        const size_t base = rbase + (size_t)ox * kStemK + part * 8;
+        load8<F16>(reinterpret_cast<const uint4*>(ch + base), reinterpret_cast<const uint4*>(cl + base), 0, vals);
+      }
+      float* dst = runs + kyi * rowp + (ox + 2) * kRunPitch + part * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = vals[j];
+    }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 3 * w; e += kThreads) {
-    const int c = e / w, ix = e - c * w;
-    float acc = 0.f;
+  // thread = (channel, output column pair 2j, 2j + 1): even columns meet kx = 1, 3, 5 at ox = j + 1, j, j - 1; odd columns kx = 0, 2, 4, 6
+  // at ox = j + 2, j + 1, j, j - 1
 #pragma unroll
-    for (int kyi = 0; kyi < 4; ++kyi)
-      for (int kx = (ix + 1) & 1; kx < 7; kx += 2) {
-        const int ox = (ix + 3 - kx) >> 1;
-        if (ox >= 0 && ox < wo) acc += runs[(kyi * wo + ox) * kRunPitch + kx * 3 + c];
+  for (int c = 0; c < 3; ++c) {
+    for (int j = threadIdx.x; j < wo; j += kThreads) {
+      const float* b = runs + (j + 2) * kRunPitch + c;
+      float even = 0.f, odd = 0.f;
+#pragma unroll
+      for (int kyi = 0; kyi < 4; ++kyi) {
+        const float* r = b + kyi * rowp;
+        even += r[1 * kRunPitch + 1 * 3] + r[0 * kRunPitch + 3 * 3] + r[-1 * kRunPitch + 5 * 3];
+        odd += r[2 * kRunPitch + 0 * 3] + r[1 * kRunPitch + 2 * 3] + r[0 * kRunPitch + 4 * 3] + r[-1 * kRunPitch + 6 * 3];
       }
-    dx[(((size_t)im * 3 + c) * h + iy) * w + ix] = acc * inv_std.v[c];
+      *reinterpret_cast<float2*>(dx + (((size_t)im * 3 + c) * h + iy) * w + 2 * j) = make_float2(even * inv_std.v[c], odd * inv_std.v[c]);
+    }
   }
 }
 }  // namespace
@@ -411,7 +429,7 @@ static int col2im_impl(const uint16_t* dcols, float* dx, int n, int h, int w, co
   const size_t rows = (size_t)n * ho * wo;
   Inv3 inv;
   for (int i = 0; i < 3; ++i) inv.v[i] = unscale / std_host[i];
-  const int smem = 4 * wo * kRunPitch * (int)sizeof(float);
+  const int smem = 4 * (wo + 4) * kRunPitch * (int)sizeof(float);
   B200R_CHECK_ARG(smem <= 200 * 1024, "image too wide for the staged col2im (w = %d)", w);
   static int configured[2] = {0, 0};
   if (configured[f16] < smem) {

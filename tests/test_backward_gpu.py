@@ -293,3 +293,24 @@ def test_maxpool_codes_forward_and_backward(cuda):
     assert codes.dtype == torch.uint8 and ((codes <= 8) | (codes == 15)).all()
     got = ops.maxpool3x3s2_bwd_codes_hi(codes, dyp, 20, 28)
     assert torch.equal(got, ops.maxpool3x3s2_relu_bwd_hi(xp, dyp))
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 32, 32), (1, 64, 48), (3, 224, 224)])
+def test_stem_col2im_against_explicit_scatter(cuda, n, h, w):
+    """b200r_stem_col2im_f32_f16 (transpose of the stem's im2col composed with 1/std): dcols [n*ho*wo, 192] fp16, column = ky*24 + kx*3 + c,
+    against an explicit scatter-add in fp64 (resnet_official.py:221-224 reversed)."""
+    from robustart_b200 import ops
+    torch.manual_seed(h + w)
+    ho, wo = h // 2, w // 2
+    d = torch.randn(n * ho * wo, 192, device=cuda).half()
+    d.view(n, ho, wo, 8, 24)[..., 21:] = 0                      # the im2col's padding columns carry nothing
+    d[:, 168:] = 0
+    got = ops.stem_col2im(d.view(torch.int16).unsqueeze(0).contiguous(), n, h, w).double()
+    dd = d.double().view(n, ho, wo, 192)
+    ref = torch.zeros(n, 3, h + 6, w + 6, device=cuda, dtype=torch.float64)     # padded by 3: iy + 3 = 2 oy + ky
+    for ky in range(7):
+        for kx in range(7):
+            ref[:, :, ky:ky + 2 * ho:2, kx:kx + 2 * wo:2] += dd[..., ky * 24 + kx * 3: ky * 24 + kx * 3 + 3].permute(0, 3, 1, 2)
+    std = torch.tensor(ops.IMAGENET_STD, device=cuda, dtype=torch.float64).view(1, 3, 1, 1)
+    ref = ref[:, :, 3:3 + h, 3:3 + w] / std
+    assert (got - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())

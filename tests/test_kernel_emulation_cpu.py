@@ -754,3 +754,27 @@ def test_maxpool_codes_kernels(emu):
     (F.max_pool2d(torch.relu(xr.permute(0, 3, 1, 2)), 3, 2, 1) * merge(dyp).permute(0, 3, 1, 2)).sum().backward()
     got = out.view(torch.float16).float()
     assert (got - xr.grad).abs().max().item() <= 2 ** -10 * xr.grad.abs().max().item() + 1e-6
+
+
+def test_stem_col2im_kernel(emu):
+    """b200r_stem_col2im_f32_f16 (csrc/backward_layers.cu, zero-margin staging + compile-time taps) on the host against an explicit fp64
+    scatter-add of the stem's im2col columns (resnet_official.py:221-224 reversed)."""
+    lib = emu["backward_layers"]
+    torch.manual_seed(9)
+    n, h, w = 2, 16, 24
+    ho, wo = h // 2, w // 2
+    d = torch.randn(n * ho * wo, 192).half()
+    d.view(n, ho, wo, 8, 24)[..., 21:] = 0
+    d[:, 168:] = 0
+    out = torch.empty(n, 3, h, w)
+    std = (C.c_float * 3)(0.229, 0.224, 0.225)
+    lib.b200r_stem_col2im_f32_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_void_p]
+    dp = d.view(torch.int16).contiguous()
+    _ok(lib.b200r_stem_col2im_f32_f16(_p(dp), _p(out), n, h, w, std, C.c_float(0.5), None))
+    dd = d.double().view(n, ho, wo, 192)
+    ref = torch.zeros(n, 3, h + 6, w + 6, dtype=torch.float64)
+    for ky in range(7):
+        for kx in range(7):
+            ref[:, :, ky:ky + 2 * ho:2, kx:kx + 2 * wo:2] += dd[..., ky * 24 + kx * 3: ky * 24 + kx * 3 + 3].permute(0, 3, 1, 2)
+    ref = ref[:, :, 3:3 + h, 3:3 + w] * 0.5 / torch.tensor([0.229, 0.224, 0.225], dtype=torch.float64).view(1, 3, 1, 1)
+    assert (out.double() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())

@@ -235,6 +235,13 @@ int b200r_linear(const uint16_t* x, const uint16_t* wgt, const float* scale, con
                  const uint16_t* res, uint16_t* y, float* y_f32, int m, int k, int nout, int act,
                  int passes, b200r_stream_t stream);
 
+/* The Linear a gradient pass keeps (vision_transformer.py:62-75 / mlp_mixer.py MLP blocks, where autograd saves the
+ * pre-activation): one launch writes pre = x . wgt^T + bias to `pre` and act(pre) to `y`, both as split planes
+ * [2][m][nout], bit-identical to b200r_linear(act = none) followed by b200r_act_planes.  Split precision only (three
+ * passes); act must be one of the smooth activations (gelu / swish / tanh / sigmoid / relu6); nout % 8 == 0. */
+int b200r_linear_keep_pre(const uint16_t* x, const uint16_t* wgt, const float* bias, uint16_t* y, uint16_t* pre,
+                          int m, int k, int nout, int act, b200r_stream_t stream);
+
 /* 7x7/s2 stem patches (resnet_official.py:221-224): u8 NHWC image -> normalised, im2col'd split
  * planes [n*ho*wo, kpad] with kpad = 192: column = ky*24 + kx*3 + c (kx < 7); each ky run is padded to 8
  * taps, so columns ky*24+21..23 and 168..191 are zero. */

@@ -68,6 +68,8 @@ SIGNATURES = {
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_linear": (C.c_int, [C.c_void_p, C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, c_f32p,
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
+    "b200r_linear_keep_pre": (C.c_int, [C.c_void_p, C.c_void_p, c_f32p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_stem_im2col_u8": (C.c_int, [c_u8p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_host_f3,
                                        c_host_f3, c_stream]),
     "b200r_stem_im2col_f32": (C.c_int, [c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_host_f3,

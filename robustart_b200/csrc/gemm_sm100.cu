@@ -110,12 +110,15 @@ __device__ __forceinline__ float fast_erf(float x) {
 // (12.5 TB/s of operand delivery = the L2 throughput cap, not the tensor pipe).  The leader (cluster rank 0) issues the MMAs;
 // both CTAs' TMA loads count on the leader's `full` barrier; MMA completion is multicast to both CTAs' `empty` / `tmem_full`
 // barriers; both epilogues arrive on the leader's `tmem_empty`.
-template <int BN, int STEM_MODE, bool F16, bool LEAN = false, int ACTS = 1, bool PAIR = false>
+// DUAL (LEAN, split planes, ACTS = 1): the pre-activation planes leave through a second tensor map (map_y2) before the activation
+// is applied -- the forward a gradient pass keeps (ViT / Mixer MLP blocks), one launch instead of GEMM + activation pass.
+template <int BN, int STEM_MODE, bool F16, bool LEAN = false, int ACTS = 1, bool PAIR = false, bool DUAL = false>
 __global__ void __launch_bounds__(STEM_MODE ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_i,
-            const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
+            const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y2, const GemmParams p) {
   constexpr bool STEM = STEM_MODE != 0;
+  static_assert(!DUAL || (LEAN && !F16 && ACTS == 1), "DUAL: LEAN split-plane kernel with the full activation set");
   constexpr bool STEM_F32 = STEM_MODE == 2;
   static_assert(!LEAN || !STEM, "LEAN is a non-stem epilogue");
   static_assert(!PAIR || (LEAN && !F16 && BN <= 128), "PAIR: LEAN split-plane kernel with BN = 64 / 128");
@@ -159,6 +162,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
     if (p.tma_store) prefetch_tmap(&map_y);
+    if constexpr (DUAL) prefetch_tmap(&map_y2);
     if (p.res_mma) { prefetch_tmap(&map_r); prefetch_tmap(&map_i); }
     // STEM: the A tile is written by 128 producer threads (one arrival each) next to the TMA thread's
     // arrive.expect_tx for the weight tile
@@ -379,6 +383,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const int col0 = nt * BN + half * kColsPerWarp + (rd * kPer + ci) * 32;
             const bool live = col0 < p.Cout;                  // uniform across the warp group (ragged Cout: whole chunks drop out)
             float f[32];
+            // split planes: one 32-column chunk, hi and lo, through the group's staging buffer and two TMA stores
+            auto emit_planes = [&](const CUtensorMap* map) {
+              // the group's buffer must have been read by the previous chunk's stores before it is rewritten
+              uint8_t* stg = smem + STG_OFF + half * 16384;
+              if (issuer) bulk_wait_read0();
+              named_bar_sync(2 + half, 128);
+              if (live) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint32_t ph[4], pl[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float x0 = f[8 * q + 2 * j], x1 = f[8 * q + 2 * j + 1];
+                    split_f16x2(x1, x0, ph[j], pl[j]);
+                  }
+                  // 64-byte rows in the TMA SWIZZLE_64B pattern (16-byte chunk index ^= (row >> 1) & 3): conflict-free stores
+                  const int pos = (q ^ ((r >> 1) & 3)) * 16;
+                  *reinterpret_cast<uint4*>(stg + r * 64 + pos) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                  *reinterpret_cast<uint4*>(stg + 8192 + r * 64 + pos) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                }
+              }
+              fence_proxy_async();
+              named_bar_sync(2 + half, 128);
+              if (issuer && live) {
+                const uint32_t stg_u32 = smem_base + STG_OFF + half * 16384;
+                tma_store_5d(map, stg_u32, col0, tw * p.bw, th * p.bh, ti * p.bn, 0);
+                tma_store_5d(map, stg_u32 + 8192, col0, tw * p.bw, th * p.bh, ti * p.bn, 1);
+                bulk_commit();
+              }
+            };
             if (live) {
               if (col0 + 32 <= p.Cout) {
                 if (p.scale) {
@@ -432,6 +466,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     }
                 }
               }
+            }
+            if constexpr (DUAL) emit_planes(&map_y2);         // the pre-activation, as the plain GEMM would have stored it
+            if (live) {
               if constexpr (ACTS == 0) {
                 if (p.act == B200R_ACT_RELU) {
 #pragma unroll
@@ -486,33 +523,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                                  cvt_f16x2(f[8 * q + 5], f[8 * q + 4]), cvt_f16x2(f[8 * q + 7], f[8 * q + 6]));
               }
             } else {
-              // split planes: the group's buffer must have been read by the previous chunk's stores before it is rewritten
-              uint8_t* stg = smem + STG_OFF + half * 16384;
-              if (issuer) bulk_wait_read0();
-              named_bar_sync(2 + half, 128);
-              if (live) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  uint32_t ph[4], pl[4];
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float x0 = f[8 * q + 2 * j], x1 = f[8 * q + 2 * j + 1];
-                    split_f16x2(x1, x0, ph[j], pl[j]);
-                  }
-                  // 64-byte rows in the TMA SWIZZLE_64B pattern (16-byte chunk index ^= (row >> 1) & 3): conflict-free stores
-                  const int pos = (q ^ ((r >> 1) & 3)) * 16;
-                  *reinterpret_cast<uint4*>(stg + r * 64 + pos) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                  *reinterpret_cast<uint4*>(stg + 8192 + r * 64 + pos) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                }
-              }
-              fence_proxy_async();
-              named_bar_sync(2 + half, 128);
-              if (issuer && live) {
-                const uint32_t stg_u32 = smem_base + STG_OFF + half * 16384;
-                tma_store_5d(&map_y, stg_u32, col0, tw * p.bw, th * p.bh, ti * p.bn, 0);
-                tma_store_5d(&map_y, stg_u32 + 8192, col0, tw * p.bw, th * p.bh, ti * p.bn, 1);
-                bulk_commit();
-              }
+              emit_planes(&map_y);
             }
           }
           if constexpr (F16) {
@@ -924,9 +935,9 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-struct GemmMaps { CUtensorMap a, b, r, i, y; };
+struct GemmMaps { CUtensorMap a, b, r, i, y, y2; };
 
-template <int BN, int STEM, bool F16, bool LEAN = false, int ACTS = 1, bool PAIR = false>
+template <int BN, int STEM, bool F16, bool LEAN = false, int ACTS = 1, bool PAIR = false, bool DUAL = false>
 int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t s) {
   constexpr int kStages = PAIR ? 4 : (LEAN && F16) ? (BN > 128 ? 3 : (BN == 128 ? 5 : 6)) : ((BN > 128) ? 2 : (BN == 64 && !STEM ? 4 : kStagesDefault)) * (F16 ? 2 : 1);
   constexpr int STAGE_BYTES = (2 * A_TILE_BYTES + 2 * (PAIR ? BN / 2 : BN) * BK * 2) / (F16 ? 2 : 1);
@@ -935,7 +946,7 @@ int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t s) {
                    ((LEAN && F16) ? 65536 : ((STEM || p.tma_store) ? 32768 : 0)) /*epilogue staging*/ + (STEM ? 7 * (p.W_in * 3 + 24) * 4 + 768 * 4 : 0);
   static int configured = 0;
   if (configured < smem) {
-    B200R_CUDA((cudaFuncSetAttribute(gemm_kernel<BN, STEM, F16, LEAN, ACTS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+    B200R_CUDA((cudaFuncSetAttribute(gemm_kernel<BN, STEM, F16, LEAN, ACTS, PAIR, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
     configured = smem;
   }
   if constexpr (PAIR) {
@@ -952,12 +963,12 @@ int launch(const GemmMaps& m, const GemmParams& p, cudaStream_t s) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B200R_CUDA((cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STEM, F16, LEAN, ACTS, PAIR>, m.a, m.b, m.r, m.i, m.y, p)));
+    B200R_CUDA((cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STEM, F16, LEAN, ACTS, PAIR, DUAL>, m.a, m.b, m.r, m.i, m.y, m.y2, p)));
     return B200R_OK;
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_img * p.tiles_n;
   const int grid = total < b200r_num_sms() ? total : b200r_num_sms();
-  gemm_kernel<BN, STEM, F16, LEAN, ACTS, PAIR><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(m.a, m.b, m.r, m.i, m.y, p);
+  gemm_kernel<BN, STEM, F16, LEAN, ACTS, PAIR, DUAL><<<grid, STEM ? (2 + kStemEpiWarps + kStemProducerWarps) * 32 : kThreads, smem, s>>>(m.a, m.b, m.r, m.i, m.y, m.y2, p);
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }
@@ -1017,7 +1028,7 @@ int finish_maps(EncodeTiledFn enc, GemmMaps* m, GemmParams* p, const uint16_t* r
   const size_t voff = (size_t)p->o_off * p->Cout;
   p->tma_store = 0;
   p->res_mma = 0;
-  m->r = m->b; m->i = m->b; m->y = m->b;   // placeholders (never dereferenced unless the flag is set)
+  m->r = m->b; m->i = m->b; m->y = m->b; m->y2 = m->b;   // placeholders (never dereferenced unless the flag is set)
   if (y && p->Cout % 8 == 0 && !(gemm_opts() & 1)) {
     // split-bf16: 32-channel (64-byte) rows per plane; fp16: 64-channel (128-byte) rows, half as many and twice as wide stores
     int rc = make_map5(enc, &m->y, y + voff, p->Cout, p->Wo, p->Ho, p->N, ycount, f16 ? 64 : 32, p->bw, p->bh, p->bn, 1,
@@ -1071,7 +1082,8 @@ struct OutView { int Ho, Wo; long long img, h, w, off; size_t plane_elems; };
 
 int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias, const uint16_t* res,
               uint16_t* y, float* y_f32, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-              int act, int passes, bool flat2d, cudaStream_t s, const uint16_t* mask = nullptr, const OutView* ov = nullptr) {
+              int act, int passes, bool flat2d, cudaStream_t s, const uint16_t* mask = nullptr, const OutView* ov = nullptr,
+              uint16_t* pre = nullptr) {
   B200R_CHECK_ARG(x && wgt && (y || y_f32), "null pointer");
   // K tails (Cin % 64 != 0) ride on TMA out-of-bounds zero fill of the activation's channel dimension
   B200R_CHECK_ARG(Cin % 8 == 0, "cin (%d) must be a multiple of 8 (16-byte TMA strides)", Cin);
@@ -1156,6 +1168,14 @@ int conv_impl(const uint16_t* x, const uint16_t* wgt, const float* scale, const 
     if (lean) B200R_LAUNCH_LEAN(true);
     if (BN == 256) return launch<256, 0, true>(m, p, s);
     return BN == 64 ? launch<64, 0, true>(m, p, s) : launch<128, 0, true>(m, p, s);
+  }
+  if (pre) {
+    // second output (the pre-activation planes): the DUAL instantiations of the LEAN split-plane kernel
+    B200R_CHECK_ARG(lean && !f16 && !simple_act && !ov && BN <= 128, "pre-activation output: split precision, a non-trivial activation, Cout %% 8 == 0, dense planes");
+    int rc = make_map5(enc, &m.y2, pre, Cout, Wo, Ho, N, ycount, 32, p.bw, p.bh, p.bn, 1, CU_TENSOR_MAP_SWIZZLE_64B, "Y2", false);
+    if (rc) return rc;
+    if (pair) return BN == 64 ? launch<64, 0, false, true, 1, true, true>(m, p, s) : launch<128, 0, false, true, 1, true, true>(m, p, s);
+    return BN == 64 ? launch<64, 0, false, true, 1, false, true>(m, p, s) : launch<128, 0, false, true, 1, false, true>(m, p, s);
   }
   if (lean && pair) {
     if (BN == 64) return simple_act ? launch<64, 0, false, true, 0, true>(m, p, s) : launch<64, 0, false, true, 1, true>(m, p, s);
@@ -1304,6 +1324,13 @@ int b200r_linear(const uint16_t* x, const uint16_t* wgt, const float* scale, con
                  uint16_t* y, float* y_f32, int m, int k, int nout, int act, int passes, b200r_stream_t stream) {
   B200R_CHECK_ARG(m > 0 && k > 0 && nout > 0, "bad shape");
   return conv_impl(x, wgt, scale, bias, res, y, y_f32, 1, 1, m, k, nout, 1, 1, 1, 0, act, passes, true, as_stream(stream));
+}
+
+int b200r_linear_keep_pre(const uint16_t* x, const uint16_t* wgt, const float* bias, uint16_t* y, uint16_t* pre, int m, int k, int nout,
+                          int act, void* stream) {
+  B200R_CHECK_ARG(m > 0 && k > 0 && nout > 0, "bad shape");
+  B200R_CHECK_ARG(y && pre && y != pre, "two distinct outputs");
+  return conv_impl(x, wgt, nullptr, bias, nullptr, y, nullptr, 1, 1, m, k, nout, 1, 1, 1, 0, act, 3, true, as_stream(stream), nullptr, nullptr, pre);
 }
 
 }  // extern "C"

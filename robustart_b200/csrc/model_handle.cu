@@ -366,6 +366,13 @@ size_t vit_arena_need(const b200r_model* m, int n, bool save) {
 int lin_fwd(const Lin& l, const uint16_t* x, const uint16_t* res, uint16_t* y, float* y_f32, int rows, int act, int passes, b200r_stream_t st) {
   return b200r_linear(x, l.w.p, nullptr, l.b, res, y, y_f32, rows, l.k, l.nout, act, passes, st);
 }
+// pre = Linear(x), y = act(pre), both kept: one launch in split precision, Linear + activation pass in the fp16 mode
+int lin_keep_pre(const Lin& l, const uint16_t* x, uint16_t* y, uint16_t* pre, int rows, int act, int passes, b200r_stream_t st) {
+  if (passes == 3) return b200r_linear_keep_pre(x, l.w.p, l.b, y, pre, rows, l.k, l.nout, act, st);
+  int rc = b200r_linear(x, l.w.p, nullptr, l.b, nullptr, pre, nullptr, rows, l.k, l.nout, B200R_ACT_NONE, passes, st);
+  if (rc) return rc;
+  return b200r_act_planes(pre, y, (size_t)rows * l.nout, act, st);
+}
 int lin_dgrad(const Lin& l, const uint16_t* g, uint16_t* dx, int rows, int passes, b200r_stream_t st) {
   return b200r_linear(g, l.wt.p, nullptr, nullptr, nullptr, dx, nullptr, rows, l.nout, l.k, B200R_ACT_NONE, passes, st);
 }
@@ -422,9 +429,8 @@ int vit_forward(b200r_model* m, const void* images, bool u8, float* logits, int 
     TAKE(hbuf, (size_t)rows * v->hidden);
     uint16_t* xn;
     if (save) {
-      RC(lin_fwd(b.m1, y2, nullptr, hbuf, nullptr, rows, B200R_ACT_NONE, P, st));       // the pre-activation is kept
       TAKE(act, (size_t)rows * v->hidden);
-      RC(b200r_act_planes(hbuf, act, (size_t)rows * v->hidden, B200R_ACT_GELU_TANH, st));
+      RC(lin_keep_pre(b.m1, y2, act, hbuf, rows, B200R_ACT_GELU_TANH, P, st));          // the pre-activation is kept
       TAKE(xo, (size_t)rows * D);
       RC(lin_fwd(b.m2, act, x_mid, xo, nullptr, rows, B200R_ACT_NONE, P, st));
       v->saved.push_back({x, qkv, x_mid, hbuf});
@@ -619,9 +625,8 @@ int mixer_forward(b200r_model* m, const void* images, bool u8, float* logits, in
     TAKE(p1, (size_t)crow * v->tok_hidden);
     TAKE(y2, (size_t)crow * TP);
     if (save) {
-      RC(lin_fwd(b.t1, yt, nullptr, p1, nullptr, crow, B200R_ACT_NONE, P, st));
       TAKE(a1, (size_t)crow * v->tok_hidden);
-      RC(b200r_act_planes(p1, a1, (size_t)crow * v->tok_hidden, B200R_ACT_GELU_ERF, st));
+      RC(lin_keep_pre(b.t1, yt, a1, p1, crow, B200R_ACT_GELU_ERF, P, st));
       RC(lin_fwd(b.t2, a1, nullptr, y2, nullptr, crow, B200R_ACT_NONE, P, st));
     } else {
       RC(lin_fwd(b.t1, yt, nullptr, p1, nullptr, crow, B200R_ACT_GELU_ERF, P, st));       // nn.GELU (erf)
@@ -634,9 +639,8 @@ int mixer_forward(b200r_model* m, const void* images, bool u8, float* logits, in
     TAKE(p2, (size_t)rows * v->ch_hidden);
     uint16_t* xn;
     if (save) {
-      RC(lin_fwd(b.c1, y3, nullptr, p2, nullptr, rows, B200R_ACT_NONE, P, st));
       TAKE(a2, (size_t)rows * v->ch_hidden);
-      RC(b200r_act_planes(p2, a2, (size_t)rows * v->ch_hidden, B200R_ACT_GELU_ERF, st));
+      RC(lin_keep_pre(b.c1, y3, a2, p2, rows, B200R_ACT_GELU_ERF, P, st));
       TAKE(xo, (size_t)rows * D);
       RC(lin_fwd(b.c2, a2, x_mid, xo, nullptr, rows, B200R_ACT_NONE, P, st));
       v->saved.push_back({x, p1, x_mid, p2});

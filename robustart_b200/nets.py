@@ -470,6 +470,14 @@ class _Lin:
             return ops.linear(x, self.w, None, self.b, res, act=act, passes=passes, out_f32=out_f32, want_planes=False)
         return ops.linear(x, self.w, None, self.b, res, act=act, passes=passes)
 
+    def keep_pre(self, x, act, passes=3):
+        """(act(pre), pre) for the gradient pass: one launch in split precision (b200r_linear_keep_pre), Linear + b200r_act_planes
+        in the fp16 mode (or with B200R_KEEP_PRE=0)."""
+        if passes == 3 and x.shape[0] == 2 and os.environ.get("B200R_KEEP_PRE", "1") != "0":
+            return ops.linear_keep_pre(x, self.w, self.b, act=act)
+        pre = ops.linear(x, self.w, None, self.b, None, act=None, passes=passes)
+        return ops.act_planes(pre, act), pre
+
     def dgrad(self, g, passes=3):
         """Input gradient of the Linear: g planes [2, m, nout] -> planes [2, m, k] = g W (a GEMM with the transposed weights)."""
         if getattr(self, "_wt", None) is None:
@@ -551,8 +559,8 @@ class ViT(_TokenModel):
             x_in = x
             qkv = b["qkv"](ops.layernorm(x, *b["n1"], eps=1e-5), passes=P)
             x_mid = b["out"](ops.attention(qkv, n, T, self.heads, hd, hd ** -0.5), res=x, passes=P)
-            pre = b["m1"](ops.layernorm(x_mid, *b["n2"], eps=1e-5), passes=P)
-            x = b["m2"](ops.act_planes(pre, "gelu_tanh"), res=x_mid, passes=P)
+            a, pre = b["m1"].keep_pre(ops.layernorm(x_mid, *b["n2"], eps=1e-5), "gelu_tanh", passes=P)
+            x = b["m2"](a, res=x_mid, passes=P)
             saved["blocks"].append((x_in, qkv, x_mid, pre))
         saved["final"] = x
         cls = ops.layernorm(x, *self.norm, eps=1e-5).view(2, n, T, self.dim)[:, :, 0].contiguous()
@@ -645,11 +653,11 @@ class Mixer(_TokenModel):
         for b in self.blocks:
             x_in = x
             y = ops.tokens_to_channels(ops.layernorm(x, *b["n1"], eps=1e-6), n, T, self.dim, self.T_PAD)
-            p1 = b["t1"](y, passes=P)
-            y = b["t2"](ops.act_planes(p1, "gelu_erf"), passes=P)
+            a1, p1 = b["t1"].keep_pre(y, "gelu_erf", passes=P)
+            y = b["t2"](a1, passes=P)
             x_mid = ops.channels_to_tokens_add(y, x, n, T, self.dim, self.T_PAD)
-            p2 = b["c1"](ops.layernorm(x_mid, *b["n2"], eps=1e-6), passes=P)
-            x = b["c2"](ops.act_planes(p2, "gelu_erf"), res=x_mid, passes=P)
+            a2, p2 = b["c1"].keep_pre(ops.layernorm(x_mid, *b["n2"], eps=1e-6), "gelu_erf", passes=P)
+            x = b["c2"](a2, res=x_mid, passes=P)
             saved["blocks"].append((x_in, p1, x_mid, p2))
         saved["final"] = x
         x = ops.layernorm(x, *self.norm, eps=1e-6)

@@ -375,6 +375,24 @@ def linear(x, wgt, scale=None, bias=None, res=None, *, act=None, passes=3, out=N
     return out if out is not None else out_f32
 
 
+def linear_keep_pre(x, wgt, bias=None, *, act):
+    """One launch for the Linear a gradient pass keeps: returns (act(pre), pre), both split planes [2, m, nout] and bit-identical to
+    `linear(act=None)` followed by `act_planes`.  Split precision only."""
+    _need_cuda(x, torch.int16, "x")
+    _need_cuda(wgt, torch.int16, "wgt")
+    if x.shape[0] != 2 or wgt.shape[0] != 2:
+        raise ValueError("linear_keep_pre: split planes ([2, ...]) only")
+    k = x.shape[-1]
+    m = x[0].numel() // k
+    nout = wgt.shape[1]
+    y = torch.empty((2, m, nout), dtype=torch.int16, device=x.device)
+    pre = torch.empty_like(y)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b200r_linear_keep_pre(x.data_ptr(), wgt.data_ptr(), _ptr(bias), y.data_ptr(), pre.data_ptr(),
+                                                     m, k, nout, ACT[act], _stream()))
+    return y, pre
+
+
 def stem_im2col(img, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
     """uint8 NHWC or float32 NCHW image batch -> planes [2, n*ho*wo, 192] of normalised 7x7/s2 patches."""
     if img.dtype == torch.uint8:

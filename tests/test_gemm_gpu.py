@@ -203,3 +203,43 @@ def test_cta_pair_gemm_is_bit_identical(cuda, cfg, passes, monkeypatch):
         if with_res:
             ref = ref + res.double()
         assert _rel_err(ops.merge_f32(outs["32"]), torch.relu(ref)) < 4e-5
+
+
+KEEP_PRE = [
+    # m, k, nout, act
+    (1576, 768, 3072, "gelu_tanh"),      # ViT MLP (8 images): pairs
+    (300, 256, 384, "gelu_erf"),         # Mixer token mixing: ragged rows, 3 N tiles
+    (130, 64, 64, "swish"),              # BN = 64
+    (128, 192, 200, "tanh"),             # one M tile (no pair), ragged K and Cout
+    (517, 96, 40, "sigmoid"),
+]
+
+
+@pytest.mark.parametrize("cfg", KEEP_PRE)
+@pytest.mark.parametrize("opts", ["0", "16", "32"])
+def test_linear_keep_pre_is_linear_then_activation(cuda, cfg, opts, monkeypatch):
+    """b200r_linear_keep_pre (one launch, two outputs) against the two launches it replaces -- b200r_linear(act none) and
+    b200r_act_planes: the pre-activation planes bit-identical, the activation within the two implementations' rounding (the pass
+    kernel and the GEMM epilogue evaluate the same formulas) and right against fp64."""
+    from robustart_b200 import ops
+    m, k, nout, act = cfg
+    monkeypatch.setenv("B200R_GEMM_OPTS", opts)
+    torch.manual_seed(m + k + nout)
+    x = torch.randn(m, k, device=cuda)
+    wt = torch.randn(nout, k, device=cuda) / k ** 0.5 * 2
+    b = torch.randn(nout, device=cuda)
+    xp, wp = ops.split_f32(x).view(2, m, k), ops.split_f32(wt).view(2, nout, k)
+    y, pre = ops.linear_keep_pre(xp, wp, b, act=act)
+    pre_ref = ops.linear(xp, wp, None, b, act=None, passes=3)
+    fused_ref = ops.linear(xp, wp, None, b, act=act, passes=3)
+    torch.cuda.synchronize()
+    assert torch.equal(pre, pre_ref)
+    assert torch.equal(y, fused_ref)                       # same epilogue code as the fused-activation GEMM
+    via_pass = ops.merge_f32(ops.act_planes(pre_ref, act))
+    assert (ops.merge_f32(y) - via_pass).abs().max().item() < 2e-6
+    z = x.double() @ wt.double().t() + b.double()
+    want = {"gelu_tanh": lambda t: torch.nn.functional.gelu(t, approximate="tanh"), "gelu_erf": torch.nn.functional.gelu,
+            "swish": torch.nn.functional.silu, "tanh": torch.tanh, "sigmoid": torch.sigmoid}[act](z)
+    assert (ops.merge_f32(y).double() - want).abs().max().item() < 3e-5
+    with pytest.raises(ValueError):
+        ops.linear_keep_pre(xp, wp, b, act="relu")         # ReLU's derivative needs no pre-activation: refused

@@ -495,7 +495,8 @@ def test_validated_corruptions_from_source(emu, name, cid, sev):
 class _Facade:
     """What robustart_b200._lib.load() returns in this test: every symbol resolved in the emulated libraries with the prototypes of
     _lib.SIGNATURES attached (so a wrong ctypes signature or argument order in ops.py fails here, not on the GPU), and ONE Python
-    stand-in: b200r_linear, the tcgen05 GEMM, which no host emulator can run (split planes in, fp32 accumulate, split planes out)."""
+    stand-in: b200r_linear (and its two-output form b200r_linear_keep_pre), the tcgen05 GEMM, which no host emulator can run
+    (split planes in, fp32 accumulate, split planes out)."""
 
     def __init__(self, emu, names):
         from robustart_b200 import _lib
@@ -547,6 +548,10 @@ class _Facade:
         if out is not None:
             self._view(out, (2, m, nout), torch.int16).copy_(split(y))
         return 0
+
+    def b200r_linear_keep_pre(self, x, w, bias, y, pre, m, k, nout, act, stream):
+        return (self.b200r_linear(x, w, None, bias, None, pre, None, m, k, nout, 0, 3, stream) or
+                self.b200r_linear(x, w, None, bias, None, y, None, m, k, nout, act, 3, stream))
 
 
 @pytest.mark.parametrize("family", ["mixer", "vit"])

@@ -66,6 +66,10 @@ def _install(monkeypatch):
             return out_f32
         return _pl(y)
 
+    def linear_keep_pre(x, wgt, bias=None, *, act):            # gemm_sm100.cu, DUAL epilogue: (act(pre), pre) from one launch
+        pre = linear(x, wgt, None, bias)
+        return _pl(_act(pre[0], act)), pre
+
     def layernorm(x, gamma, beta, eps=1e-5, out=None):
         return _pl(F.layer_norm(x[0], (x.shape[-1],), gamma.to(DT), beta.to(DT), eps))
 

@@ -157,7 +157,38 @@ __device__ __forceinline__ float act_deriv(float v, int act) {
     default: return 1.f;
   }
 }
-template <bool BWD>
+// The gradient pass's form of the derivatives: one ex2 and one rcp on the MUFU per element (the formulas of the GEMM epilogue's
+// activations, gemm_sm100.cu), absolute error ~2e-7 -- the libm forms above cost 40-60 instructions per element and made the
+// pass issue-bound (ncu: 75 % issue, 43 % DRAM).  ACT is a template parameter: no switch inside the element loop.
+template <int ACT>
+__device__ __forceinline__ float act_deriv_fast(float v) {
+  if constexpr (ACT == B200R_ACT_GELU_TANH) {
+    // gelu = v s, s = 0.5 (1 + tanh u) = 1 / (1 + exp(-2u)), u = k (v + c v^3):  d = s + 2 v s (1 - s) k (1 + 3 c v^2)
+    const float v2 = v * v;
+    const float u = 0.7978845608028654f * fmaf(0.044715f * v2, v, v);
+    const float sg = __fdividef(1.f, 1.f + __expf(-2.f * u));
+    return fmaf(2.f * v * sg * (1.f - sg), 0.7978845608028654f * fmaf(3.f * 0.044715f, v2, 1.f), sg);
+  } else if constexpr (ACT == B200R_ACT_GELU_ERF) {
+    // d = Phi(v) + v phi(v); erf(v / sqrt 2) by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7), sharing exp(-v^2 / 2) with phi
+    const float ax = fabsf(v) * 0.7071067811865476f, t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+    const float e = __expf(-ax * ax);
+    const float erfv = copysignf(1.f - poly * e, v);
+    return fmaf(v * 0.3989422804014327f, e, 0.5f * (1.f + erfv));
+  } else if constexpr (ACT == B200R_ACT_TANH) {
+    const float t = 1.f - __fdividef(2.f, 1.f + __expf(2.f * v));
+    return 1.f - t * t;
+  } else if constexpr (ACT == B200R_ACT_SWISH) {
+    const float sg = __fdividef(1.f, 1.f + __expf(-v));
+    return sg * fmaf(v, 1.f - sg, 1.f);
+  } else if constexpr (ACT == B200R_ACT_SIGMOID) {
+    const float sg = __fdividef(1.f, 1.f + __expf(-v));
+    return sg * (1.f - sg);
+  } else {
+    return act_deriv(v, ACT);                                // ReLU / ReLU6: comparisons only
+  }
+}
+template <bool BWD, int ACT = 0>
 __global__ void __launch_bounds__(kThreads) act_planes_kernel(const uint4* __restrict__ ph, const uint4* __restrict__ pl,
                                                                const uint4* __restrict__ dyh, const uint4* __restrict__ dyl,
                                                                uint4* __restrict__ oh, uint4* __restrict__ ol, size_t count8, int act) {
@@ -168,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) act_planes_kernel(const uint4* __res
       float d[8];
       unpack8(__ldg(dyh + t), __ldg(dyl + t), d);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = d[j] * act_deriv(p[j], act);
+      for (int j = 0; j < 8; ++j) o[j] = d[j] * act_deriv_fast<ACT>(p[j]);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = act_fwd(p[j], act);
@@ -353,9 +384,22 @@ int b200r_act_bwd_planes(const uint16_t* dy, const uint16_t* pre, uint16_t* dx, 
   B200R_CHECK_ARG(dy && pre && dx, "null pointer");
   B200R_CHECK_ARG(count > 0 && count % 8 == 0, "count must be a positive multiple of 8");
   B200R_CHECK_ARG(act_ok(act), "activation %d not supported", act);
-  act_planes_kernel<true><<<grid_for(count / 8), kThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const uint4*>(pre), reinterpret_cast<const uint4*>(pre + count), reinterpret_cast<const uint4*>(dy),
-      reinterpret_cast<const uint4*>(dy + count), reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dx + count), count / 8, act);
+#define B200R_ACT_BWD(A)                                                                                                           \
+  case A:                                                                                                                          \
+    act_planes_kernel<true, A><<<grid_for(count / 8), kThreads, 0, as_stream(stream)>>>(                                           \
+        reinterpret_cast<const uint4*>(pre), reinterpret_cast<const uint4*>(pre + count), reinterpret_cast<const uint4*>(dy),      \
+        reinterpret_cast<const uint4*>(dy + count), reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dx + count), count / 8, act); \
+    break
+  switch (act) {
+    B200R_ACT_BWD(B200R_ACT_RELU);
+    B200R_ACT_BWD(B200R_ACT_RELU6);
+    B200R_ACT_BWD(B200R_ACT_GELU_TANH);
+    B200R_ACT_BWD(B200R_ACT_GELU_ERF);
+    B200R_ACT_BWD(B200R_ACT_SWISH);
+    B200R_ACT_BWD(B200R_ACT_TANH);
+    default: B200R_ACT_BWD(B200R_ACT_SIGMOID);
+  }
+#undef B200R_ACT_BWD
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }

@@ -211,17 +211,19 @@ def test_emulator_reproduces_validated_kernels(emu):
     _ok(lib.b200r_layernorm(_p(xp), _p(yp), _p(g), _p(b), rows, c, C.c_float(1e-5), None))
     ref = F.layer_norm(rt(x).double(), (c,), g.double(), b.double(), 1e-5)
     assert (merge(yp).double() - ref).abs().max().item() < 2e-4
-    # token transposes (static shared tiles + __syncthreads)
-    B, T, Cc, Tp = 2, 10, 64, 16
-    x = torch.randn(B * T, Cc)
-    xp = split(x)
-    yp = torch.empty(2, B * Cc, Tp, dtype=torch.int16)
-    _ok(lib.b200r_tokens_to_channels(_p(xp), _p(yp), B, T, Cc, Tp, None))
-    y = merge(yp).view(B, Cc, Tp)
-    assert torch.equal(y[:, :, :T], rt(x).view(B, T, Cc).transpose(1, 2)) and y[:, :, T:].abs().max().item() == 0
-    op = torch.empty(2, B * T, Cc, dtype=torch.int16)
-    _ok(lib.b200r_channels_to_tokens_add(_p(yp), _p(xp), _p(op), B, T, Cc, Tp, None))
-    assert (merge(op) - 2 * rt(x)).abs().max().item() < 1e-5
+    # token transposes (static shared tiles + __syncthreads): the four-element kernels (t_pad % 4 == 0 and c % 4 == 0; several tiles
+    # with ragged edges in both directions, the Mixer's own 196 -> 256) and the two-element ones (the other geometries)
+    for B, T, Cc, Tp in [(2, 10, 64, 16), (1, 196, 72, 256), (2, 70, 132, 72), (2, 10, 66, 16), (1, 66, 64, 70), (1, 67, 64, 68)]:
+        x = torch.randn(B * T, Cc)
+        xp = split(x)
+        yp = torch.full((2, B * Cc, Tp), 0x3C00, dtype=torch.int16)
+        _ok(lib.b200r_tokens_to_channels(_p(xp), _p(yp), B, T, Cc, Tp, None))
+        y = merge(yp).view(B, Cc, Tp)
+        assert torch.equal(y[:, :, :T], rt(x).view(B, T, Cc).transpose(1, 2)) and y[:, :, T:].abs().max().item() == 0
+        res = torch.randn(B * T, Cc)
+        rp, op = split(res), torch.empty(2, B * T, Cc, dtype=torch.int16)
+        _ok(lib.b200r_channels_to_tokens_add(_p(yp), _p(rp), _p(op), B, T, Cc, Tp, None))
+        assert (merge(op) - (rt(x) + rt(res))).abs().max().item() < 1e-5
     # CUDA-core attention forward (dynamic shared memory, per-warp scratch)
     n, t, heads = 2, 37, 2
     qkv = torch.randn(n * t, 3 * heads * 64)

@@ -63,6 +63,27 @@ def test_token_transposes_and_patches(cuda):
     assert (cols - ref).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("geo", [(3, 196, 768, 256), (2, 10, 64, 16), (1, 196, 72, 256), (2, 70, 132, 72), (2, 10, 66, 16), (1, 66, 64, 70),
+                                 (2, 257, 196, 260)])
+def test_token_transposes_all_geometries(cuda, geo):
+    """Both transposes of the Mixer's token mixing, exact: the four-element kernels (t_pad % 4 == 0 and c % 4 == 0) over ragged tiles in
+    both directions, the two-element kernels for the other geometries; the padding columns of the channel-major tensor come out zero
+    even when the buffer held something else, and the way back adds an independent residual."""
+    from robustart_b200 import ops
+    b, t, c, tp = geo
+    torch.manual_seed(sum(geo))
+    x = torch.randn(b * t, c, device=cuda)
+    res = torch.randn(b * t, c, device=cuda)
+    xp, rp = ops.split_f32(x), ops.split_f32(res)
+    yp = ops.tokens_to_channels(xp, b, t, c, tp)
+    y = ops.merge_f32(yp).view(b, c, tp)
+    xm = ops.merge_f32(xp).view(b, t, c)
+    assert torch.equal(y[:, :, :t], xm.transpose(1, 2)) and y[:, :, t:].abs().max().item() == 0
+    back = ops.merge_f32(ops.channels_to_tokens_add(yp, rp, b, t, c, tp)).view(b, t, c)
+    want = xm.double() + ops.merge_f32(rp).view(b, t, c).double()
+    assert (back.double() - want).abs().max().item() < 1e-6 * max(1.0, want.abs().max().item())
+
+
 @pytest.mark.parametrize("arch", ["vit_b16_224", "mixer_b16_224"])
 def test_token_model_logits_match_reference(cuda, arch):
     from robustart_b200 import nets

@@ -43,18 +43,28 @@ __device__ __forceinline__ void pack8(const float* v, uint4& h, uint4& l) {
 
 // ---- LayerNorm backward: one warp per row, C <= 1024 ------------------------------------------------
 //   xhat = (x - mean) rstd,  gy = dy gamma,  dx = rstd (gy - mean(gy) - xhat mean(gy xhat))  [+ add]
+// NV = 16-byte vectors per lane (ceil(C / 256)): ViT / Mixer rows (C = 768) keep 2 x 24 values in registers instead of 2 x 32, and the
+// residual-gradient operand is requested together with the other two -- three CTAs per SM and no second exposed DRAM latency
+// (ncu before: 84 registers -> 2 CTAs per SM, 22 % of the warp slots, top stall long_scoreboard, 44 % of the DRAM peak).
 constexpr int kLnMaxVec = 4;
-__global__ void __launch_bounds__(kThreads) layernorm_bwd_kernel(const uint4* __restrict__ dyh, const uint4* __restrict__ dyl,
+template <int NV>
+__global__ void __launch_bounds__(kThreads, NV <= 3 ? 3 : 2) layernorm_bwd_kernel(const uint4* __restrict__ dyh, const uint4* __restrict__ dyl,
                                                                   const uint4* __restrict__ xh, const uint4* __restrict__ xl,
                                                                   const uint4* __restrict__ ah, const uint4* __restrict__ al,
                                                                   uint4* __restrict__ oh, uint4* __restrict__ ol,
                                                                   const float* __restrict__ gamma, int rows, int c8, float eps) {
   const int row = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= rows) return;
-  float v[kLnMaxVec][8], g[kLnMaxVec][8];
+  float v[NV][8], g[NV][8];
+  uint4 rah[NV], ral[NV];                                   // residual gradient, raw planes (in flight during the reductions)
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = lane + 32 * k;
+    if (ah && i < c8) { rah[k] = __ldg(ah + (size_t)row * c8 + i); ral[k] = __ldg(al + (size_t)row * c8 + i); }
+  }
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int i = lane + 32 * k;
     if (i < c8) {
       unpack8(__ldg(xh + (size_t)row * c8 + i), __ldg(xl + (size_t)row * c8 + i), v[k]);
@@ -74,7 +84,7 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_kernel(const uint4* __
   const float mean = warp_sum(s) * inv_c;
   float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k)
+  for (int k = 0; k < NV; ++k)
     if (lane + 32 * k < c8) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { const float d = v[k][j] - mean; q += d * d; }
@@ -82,7 +92,7 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_kernel(const uint4* __
   const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k)
+  for (int k = 0; k < NV; ++k)
     if (lane + 32 * k < c8) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -94,7 +104,7 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_kernel(const uint4* __
   s1 = warp_sum(s1) * inv_c;
   s2 = warp_sum(s2) * inv_c;
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int i = lane + 32 * k;
     if (i >= c8) continue;
     float o[8];
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_kernel(const uint4* __
     for (int j = 0; j < 8; ++j) o[j] = rstd * (g[k][j] - s1 - v[k][j] * s2);
     if (ah) {
       float a[8];
-      unpack8(__ldg(ah + (size_t)row * c8 + i), __ldg(al + (size_t)row * c8 + i), a);
+      unpack8(rah[k], ral[k], a);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] += a[j];
     }
@@ -361,10 +371,18 @@ int b200r_layernorm_bwd(const uint16_t* dy, const uint16_t* x, const float* gamm
   B200R_CHECK_ARG(dy && x && gamma && dx, "null pointer");
   B200R_CHECK_ARG(rows > 0 && c % 8 == 0 && c <= 32 * 8 * kLnMaxVec, "c must be a multiple of 8 and <= %d", 32 * 8 * kLnMaxVec);
   const size_t cnt = (size_t)rows * c;
-  layernorm_bwd_kernel<<<(unsigned)(((size_t)rows * 32 + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(dy + cnt), reinterpret_cast<const uint4*>(x),
-      reinterpret_cast<const uint4*>(x + cnt), reinterpret_cast<const uint4*>(add), reinterpret_cast<const uint4*>(add ? add + cnt : nullptr),
-      reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dx + cnt), gamma, rows, c / 8, eps);
+#define B200R_LN_BWD(NV)                                                                                                          \
+  layernorm_bwd_kernel<NV><<<(unsigned)(((size_t)rows * 32 + kThreads - 1) / kThreads), kThreads, 0, as_stream(stream)>>>(          \
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(dy + cnt), reinterpret_cast<const uint4*>(x),              \
+      reinterpret_cast<const uint4*>(x + cnt), reinterpret_cast<const uint4*>(add), reinterpret_cast<const uint4*>(add ? add + cnt : nullptr), \
+      reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dx + cnt), gamma, rows, c / 8, eps)
+  switch ((c / 8 + 31) / 32) {
+    case 1: B200R_LN_BWD(1); break;
+    case 2: B200R_LN_BWD(2); break;
+    case 3: B200R_LN_BWD(3); break;
+    default: B200R_LN_BWD(4); break;
+  }
+#undef B200R_LN_BWD
   B200R_LAUNCH_CHECK();
   return B200R_OK;
 }

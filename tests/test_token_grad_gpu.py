@@ -24,7 +24,7 @@ def _rt(ops, x):
 def test_layernorm_bwd(cuda):
     from robustart_b200 import ops
     torch.manual_seed(0)
-    for rows, c, eps in [(3 * 197, 768, 1e-5), (2 * 196, 768, 1e-6), (5, 64, 1e-5), (7, 1024, 1e-6)]:
+    for rows, c, eps in [(3 * 197, 768, 1e-5), (2 * 196, 768, 1e-6), (5, 64, 1e-5), (7, 1024, 1e-6), (9, 384, 1e-5), (4, 520, 1e-6)]:   # 1-4 vectors per lane, partial last
         x = torch.randn(rows, c, device=cuda) * 2 + 0.3
         dy = torch.randn(rows, c, device=cuda)
         add = torch.randn(rows, c, device=cuda)

@@ -383,6 +383,14 @@ int b200r_conv2d_dgrad_nhwc(const uint16_t* dy, const uint16_t* wgt_t, const uin
 int b200r_conv2d_dgrad3x3s2_nhwc(const uint16_t* dy, const uint16_t* w00, const uint16_t* w01, const uint16_t* w10,
                                  const uint16_t* w11, const uint16_t* res, const uint16_t* mask, uint16_t* dx, int n,
                                  int ho, int wo, int cdy, int cdx, int passes, b200r_stream_t stream);
+
+/* Input gradient of a 1x1 / stride-2 convolution (the ResNet downsample branch, resnet_official.py:255-262), ACCUMULATED in place
+ * into a gradient that already holds the main branch: dx[:, 2i, 2j, :] = [mask > 0] * (dx[:, 2i, 2j, :] + dy[:, i, j, :] . wgt_t^T),
+ * other positions untouched.  dy planes [n][(h+1)/2][(w+1)/2][cdy], wgt_t [cdx][cdy], dx / mask planes [n][h][w][cdx] (mask may
+ * be NULL; it is the one already applied to dx, so masking the sum equals masking the new term).  cdx % 8 == 0.  Replaces
+ * b200r_conv2d_dgrad_nhwc on the small map + b200r_dilate2_nhwc + the residual operand of the main branch's last dgrad. */
+int b200r_conv2d_dgrad1x1s2_acc_nhwc(const uint16_t* dy, const uint16_t* wgt_t, const uint16_t* mask, uint16_t* dx,
+                                     int n, int h, int w, int cdy, int cdx, int passes, b200r_stream_t stream);
 /* ReLU backward: out = (act > 0 ? dy : 0) + add; add may be NULL (a second gradient branch joining here,
  * e.g. the identity path of a residual block).  count = elements per plane, multiple of 8. */
 int b200r_relu_bwd(const uint16_t* dy, const uint16_t* act, const uint16_t* add, uint16_t* out,

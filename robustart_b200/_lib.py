@@ -98,6 +98,7 @@ SIGNATURES = {
     "b200r_maxpool3x3s2_nhwc_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_global_avgpool_nhwc_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_conv2d_dgrad3x3s2_nhwc": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 6 + [c_stream]),
+    "b200r_conv2d_dgrad1x1s2_acc_nhwc": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 6 + [c_stream]),
     "b200r_conv2d_dgrad_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_stream]),
     "b200r_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),

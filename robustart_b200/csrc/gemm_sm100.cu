@@ -1320,6 +1320,21 @@ int b200r_conv2d_dgrad3x3s2_nhwc(const uint16_t* dy, const uint16_t* w00, const 
   return B200R_OK;
 }
 
+int b200r_conv2d_dgrad1x1s2_acc_nhwc(const uint16_t* dy, const uint16_t* wgt_t, const uint16_t* mask, uint16_t* dx, int n, int h, int w,
+                                     int cdy, int cdx, int passes, b200r_stream_t stream) {
+  B200R_CHECK_ARG(dy && wgt_t && dx, "null pointer");
+  B200R_CHECK_ARG(n > 0 && h > 0 && w > 0 && cdy > 0 && cdx > 0, "bad shape");
+  B200R_CHECK_ARG(cdx % 8 == 0, "cdx must be a multiple of 8 (the accumulation rides on the tensor core's residual path)");
+  // dx[:, 2i, 2j] += W^T dy[:, i, j] in place: output AND residual are the same strided view of dx (every tile reads its own rows
+  // before it stores them; tiles are disjoint), so neither the zero-inserted gradient nor a separate add pass exists
+  OutView ov;
+  ov.Ho = (h - 1) / 2 + 1; ov.Wo = (w - 1) / 2 + 1;
+  ov.img = (long long)h * w; ov.h = 2LL * w; ov.w = 2; ov.off = 0;
+  ov.plane_elems = (size_t)n * h * w * cdx;
+  return conv_impl(dy, wgt_t, nullptr, nullptr, dx, dx, nullptr, n, ov.Ho, ov.Wo, cdy, cdx, 1, 1, 1, 0, B200R_ACT_NONE, passes, false,
+                   as_stream(stream), mask, &ov);
+}
+
 int b200r_linear(const uint16_t* x, const uint16_t* wgt, const float* scale, const float* bias, const uint16_t* res,
                  uint16_t* y, float* y_f32, int m, int k, int nout, int act, int passes, b200r_stream_t stream) {
   B200R_CHECK_ARG(m > 0 && k > 0 && nout > 0, "bad shape");

@@ -1134,8 +1134,11 @@ int b200r_model_input_grad(b200r_model* m, const float* dlogits, float* dx, b200
     const int stride = b.bottleneck ? b.c2.stride : b.c1.stride;
     const int cin = b.c1.cin, hi = h * stride, wi = w * stride;
     // identity path: the 1x1 downsample's dgrad (stride 2: contract on the small map, then zero-insert) or g itself
-    const uint16_t* r = g;
-    if (b.has_down) {
+    // (a stride-2 downsample is accumulated in place into the main branch's result afterwards: no zero-inserted tensor, no residual)
+    static const bool ds_acc = !(getenv("B200R_DS_ACC") && atoi(getenv("B200R_DS_ACC")) == 0);
+    const bool acc = b.has_down && stride == 2 && ds_acc;
+    const uint16_t* r = acc ? nullptr : g;
+    if (b.has_down && !acc) {
       TAKE(d0, (size_t)n * h * w * cin);
       RC(b200r_conv2d_dgrad_nhwc(g, b.down.wt.p, nullptr, nullptr, d0, n, h, w, b.down.cout, cin, 1, 1, 0, P, stream));
       if (stride == 2) {
@@ -1172,6 +1175,7 @@ int b200r_model_input_grad(b200r_model* m, const float* dlogits, float* dx, b200
       }
       t = t1;
     }
+    if (acc) RC(b200r_conv2d_dgrad1x1s2_acc_nhwc(g, b.down.wt.p, in_mask, t, n, hi, wi, b.down.cout, cin, P, stream));
     g = t; h = hi; w = wi; c = cin;
   }
   // maxpool backward into the 112^2 stem activation, its ReLU, the stem GEMM's gradient, col2im (+ 1/std, 1/S)

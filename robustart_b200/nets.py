@@ -160,6 +160,14 @@ class _ConvBN:
             dy = ops.dilate2(dy)
         return ops.conv2d_dgrad(dy, self._w_dgrad, res, mask, pad=self.k - 1 - self.pad, passes=passes)
 
+    def dgrad_acc(self, dy, dx, mask=None, passes=3):
+        """1x1 / stride 2 only: dx[..., 2i, 2j, :] += (this convolution's input gradient of dy), in place, masked like dx was."""
+        assert self.stride == 2 and self.k == 1
+        if self._w_dgrad is None:
+            wt = self._w_folded.flip(2, 3).permute(1, 2, 3, 0).contiguous()       # [cin, 1, 1, cout]
+            self._w_dgrad = ops.to_planes(wt.to(self._device), self.f16)
+        return ops.conv2d_dgrad1x1s2_acc(dy, self._w_dgrad, dx, mask, passes=passes)
+
     def __call__(self, x, act=None, res=None, passes=3):
         return ops.conv2d_nhwc(x, self.w, self.scale, self.bias, res, stride=self.stride, pad=self.pad, act=act,
                                passes=passes)
@@ -303,8 +311,10 @@ class ResNet:
         activation = the previous block's output) applies the PREVIOUS block's output ReLU to the result, so the
         chain needs no stand-alone masking pass (g_is_masked: the caller did that for this block's own output)."""
         dz = g if g_is_masked else ops.relu_bwd(g, sv[-1])
-        # identity path: the 1x1 downsample's dgrad (stride 2: contract on the small map, then zero-insert) or dz itself
-        r = blk["down"].dgrad(dz, passes=P) if "down" in blk else dz
+        # identity path: the 1x1 downsample's dgrad or dz itself.  A stride-2 downsample is accumulated IN PLACE into the main branch's
+        # result afterwards (b200r_conv2d_dgrad1x1s2_acc_nhwc): no zero-inserted tensor, no residual operand (B200R_DS_ACC=0: old path)
+        acc = "down" in blk and blk["down"].stride == 2 and os.environ.get("B200R_DS_ACC", "1") != "0"
+        r = None if acc else (blk["down"].dgrad(dz, passes=P) if "down" in blk else dz)
         if blk["kind"] == "bottleneck":
             a1, a2, _ = sv
             t = blk["c3"].dgrad(dz, mask=a2, passes=P)
@@ -312,7 +322,10 @@ class ResNet:
         else:
             a1, _ = sv
             t = blk["c2"].dgrad(dz, mask=a1, passes=P)
-        return blk["c1"].dgrad(t, res=r, mask=in_mask, passes=P)
+        out = blk["c1"].dgrad(t, res=r, mask=in_mask, passes=P)
+        if acc:
+            blk["down"].dgrad_acc(dz, out, mask=in_mask, passes=P)
+        return out
 
     def input_grad(self, dlogits: torch.Tensor, saved, passes: Optional[int] = None) -> torch.Tensor:
         """d loss / d x01 (float32 NCHW) from d loss / d logits (float32 [n, classes]) and forward_saved()'s state.

@@ -632,6 +632,28 @@ def conv2d_dgrad3x3s2(dy, wsub, res=None, mask=None, *, passes=3):
     return out
 
 
+def conv2d_dgrad1x1s2_acc(dy, wgt_t, dx, mask=None, *, passes=3):
+    """In place: dx[:, :, 2i, 2j] = [mask > 0] * (dx[:, :, 2i, 2j] + dy[:, :, i, j] . wgt_t^T) -- the input gradient of a 1x1 / stride-2
+    convolution (the downsample branch) accumulated into the main branch's gradient (include/b200r.h).  dy planes [P,n,ho,wo,cdy],
+    wgt_t planes [P,cdx,1,1,cdy], dx (and mask) planes [P,n,h,w,cdx] with ho = (h + 1) // 2.  Returns dx."""
+    _need_cuda(dy, torch.int16, "dy")
+    _need_cuda(wgt_t, torch.int16, "wgt_t")
+    _need_cuda(dx, torch.int16, "dx")
+    P, n, ho, wo, cdy = dy.shape
+    _, n2, h, w, cdx = dx.shape
+    if dx.shape[0] != P or n2 != n or (h + 1) // 2 != ho or (w + 1) // 2 != wo or not dx.is_contiguous():
+        raise ValueError("conv2d_dgrad1x1s2_acc: dx %s does not match dy %s" % (tuple(dx.shape), tuple(dy.shape)))
+    if wgt_t.shape[0] != P or wgt_t[0].numel() != cdx * cdy or not wgt_t.is_contiguous():
+        raise ValueError("conv2d_dgrad1x1s2_acc: wgt_t must be contiguous planes [%d, %d, 1, 1, %d]" % (P, cdx, cdy))
+    if mask is not None and (mask.shape != dx.shape or not mask.is_contiguous()):
+        raise ValueError("conv2d_dgrad1x1s2_acc: mask must have dx's shape")
+    passes = _passes_for(dy, passes)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().b200r_conv2d_dgrad1x1s2_acc_nhwc(dy.data_ptr(), wgt_t.data_ptr(), _ptr(mask), dx.data_ptr(), n, h, w, cdy, cdx,
+                                                                passes, _stream()))
+    return dx
+
+
 def relu_bwd(dy, act, add=None, out=None):
     """(act > 0 ? dy : 0) + add on split planes of any shape [2, ...]."""
     assert dy.shape == act.shape and (add is None or add.shape == dy.shape)

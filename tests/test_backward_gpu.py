@@ -314,3 +314,41 @@ def test_stem_col2im_against_explicit_scatter(cuda, n, h, w):
     std = torch.tensor(ops.IMAGENET_STD, device=cuda, dtype=torch.float64).view(1, 3, 1, 1)
     ref = ref[:, :, 3:3 + h, 3:3 + w] / std
     assert (got - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,masked,f16", [
+    (5, 28, 28, 256, 512, True, False), (3, 14, 14, 512, 1024, True, False), (2, 56, 56, 64, 128, False, False),
+    (2, 15, 13, 64, 72, True, False),                     # odd spatial size: ho = (h + 1) // 2, last row / column has no partner
+    (3, 14, 14, 256, 512, True, True)])
+def test_downsample_dgrad_accumulates_in_place(cuda, n, h, w, cin, cout, masked, f16):
+    """b200r_conv2d_dgrad1x1s2_acc_nhwc: dx[:, 2i, 2j] = mask * (dx[:, 2i, 2j] + W^T dy[:, i, j]) with output and residual the SAME
+    strided view of dx -- against fp64 and against the path it replaces (dgrad on the small map, dilate2, residual operand of the main
+    branch's dgrad); positions off the stride-2 lattice must keep their bits."""
+    from robustart_b200 import ops
+    torch.manual_seed(n + h + cin)
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    wt = torch.randn(cout, cin, device=cuda) / cin ** 0.5                     # the 1x1 downsample kernel
+    dy = torch.randn(n, ho, wo, cout, device=cuda)
+    act = torch.relu(torch.randn(n, h, w, cin, device=cuda))
+    main = torch.randn(n, h, w, cin, device=cuda) * (act > 0 if masked else 1)   # the main branch's (already masked) gradient
+    dyp, mp, ap = ops.to_planes(dy, f16), ops.to_planes(main, f16), ops.to_planes(act, f16)
+    wtp = ops.to_planes(wt.t().contiguous().view(cin, 1, 1, cout), f16)       # [cdx, 1, 1, cdy]
+    before = mp.clone()
+    passes = ops.PASSES_F16 if f16 else 3
+    out = ops.conv2d_dgrad1x1s2_acc(dyp, wtp, mp, ap if masked else None, passes=passes)
+    assert out.data_ptr() == mp.data_ptr()
+    got = ops.from_planes(mp).double()
+    ref = ops.from_planes(before).double()
+    add = ops.from_planes(dyp).double() @ ops.from_planes(wtp).double().view(cin, cout).t()
+    ref[:, ::2, ::2] += add
+    if masked:
+        ref = ref * (act > 0)
+    tol = (2e-3 if f16 else 2e-5) * ref.abs().max().item()
+    assert (got - ref).abs().max().item() < tol
+    lattice = torch.zeros(h, w, dtype=torch.bool, device=cuda)
+    lattice[::2, ::2] = True
+    assert torch.equal(mp[:, :, ~lattice], before[:, :, ~lattice])            # untouched bits elsewhere
+    if masked and h % 2 == 0 and w % 2 == 0:
+        # the replaced path: contract on the small map, zero-insert, mask, add the (already masked) main branch
+        old = ops.from_planes(ops.relu_bwd(ops.dilate2(ops.conv2d_dgrad(dyp, wtp, passes=passes)), ap, add=before))
+        assert (got - old.double()).abs().max().item() < tol

@@ -7,6 +7,9 @@
 // 4 * 602 112 B; L2 / MIM add one extra read of g for the per-sample norm.
 #include "common.cuh"
 #include "corrupt.cuh"
+#ifdef __CUDACC__                       // (the host emulator of tests/emu compiles this file without the cluster kernels)
+#include <cooperative_groups.h>
+#endif
 
 namespace {
 constexpr int kThreads = 256;
@@ -186,6 +189,121 @@ __global__ void __launch_bounds__(kThreads) l2_project_kernel(float4* __restrict
   }
 }
 
+#ifdef __CUDACC__
+// ---- L2 phases 2 + 3 in one kernel: a cluster of 8 CTAs owns one image -------------------------------------------------------
+// The ascent needs ||x' - x0|| of the WHOLE image before the projection can scale any element, which is why the three-kernel form
+// above touches x twice more (8 passes over an image per step against the algorithmic 5).  Here the image's 150 528 elements live
+// in the registers of 8 x 512 threads (10 float4 of d = x' - x0 each, two CTAs per SM; x0 is read again from L2 at the end), the squared norm is reduced through distributed
+// shared memory in fixed order (block tree, then the 8 CTA partials in rank order: deterministic, no atomics), and x is written once.
+// The norm of g is the same reduction one phase earlier; g's second read and x0's second read are L2 hits, so HBM sees 4 passes
+// (x, g, x0 in, x out) in ONE launch.
+namespace cg = cooperative_groups;
+constexpr int kClusterCtas = 8, kClusterThreads = 512, kClusterVec = 10, kClusterCtasPerSm = 2;
+__device__ __forceinline__ float cluster_sum_ordered(float v, float* sh /* [33] */) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    const float t = warp_sum(lane < kClusterThreads / 32 ? sh[lane] : 0.f);
+    if (lane == 0) sh[32] = t;
+  }
+  cluster.sync();                                            // every CTA's partial is in its sh[32]
+  float tot = 0.f;
+#pragma unroll
+  for (int r = 0; r < kClusterCtas; ++r) tot += *cluster.map_shared_rank(sh + 32, r);
+  cluster.sync();                                            // nobody leaves (or reuses sh) while a peer still reads it
+  return tot;
+}
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads, kClusterCtasPerSm)
+    l2_step_cluster_kernel(float4* __restrict__ x, const float4* __restrict__ g, const float4* __restrict__ x0, size_t chw4, float alpha,
+                           float eps) {
+  __shared__ float sh[33];
+  const size_t img = blockIdx.y;
+  // phase 1: ||g||^2 (g is read again below: an L2 hit, the cluster's image is 602 KB)
+  float s0 = 0.f;
+#pragma unroll
+  for (int k = 0; k < kClusterVec; ++k) {
+    const size_t i = ((size_t)k * kClusterCtas + blockIdx.x) * kClusterThreads + threadIdx.x;
+    if (i < chw4) {
+      const float4 v = __ldg(g + img * chw4 + i);
+      s0 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  }
+  const float f = alpha * (1.0f / fmaxf(sqrtf(cluster_sum_ordered(s0, sh)), 1e-12f));
+  float4 d[kClusterVec];                                    // x0 is read again in the last phase: an L2 hit (a cluster's image is 602 KB)
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kClusterVec; ++k) {
+    const size_t i = ((size_t)k * kClusterCtas + blockIdx.x) * kClusterThreads + threadIdx.x;
+    if (i < chw4) {
+      const size_t at = img * chw4 + i;
+      float4 xv = x[at];
+      const float4 gv = ld_stream_f4(g + at);
+      const float4 ov = __ldg(x0 + at);
+      xv.x = __fadd_rn(xv.x, __fmul_rn(f, gv.x)); xv.y = __fadd_rn(xv.y, __fmul_rn(f, gv.y));
+      xv.z = __fadd_rn(xv.z, __fmul_rn(f, gv.z)); xv.w = __fadd_rn(xv.w, __fmul_rn(f, gv.w));
+      d[k] = make_float4(__fsub_rn(xv.x, ov.x), __fsub_rn(xv.y, ov.y), __fsub_rn(xv.z, ov.z), __fsub_rn(xv.w, ov.w));
+      s += d[k].x * d[k].x + d[k].y * d[k].y + d[k].z * d[k].z + d[k].w * d[k].w;
+    }
+  }
+  const float tot = cluster_sum_ordered(s, sh);
+  const float f2 = fminf(1.0f, eps / fmaxf(sqrtf(tot), 1e-12f));
+#pragma unroll
+  for (int k = 0; k < kClusterVec; ++k) {
+    const size_t i = ((size_t)k * kClusterCtas + blockIdx.x) * kClusterThreads + threadIdx.x;
+    if (i < chw4) {
+      const float4 ov = ld_stream_f4(x0 + img * chw4 + i);
+      float4 xv;
+      xv.x = clampf(__fadd_rn(ov.x, __fmul_rn(d[k].x, f2)), 0.f, 1.f);
+      xv.y = clampf(__fadd_rn(ov.y, __fmul_rn(d[k].y, f2)), 0.f, 1.f);
+      xv.z = clampf(__fadd_rn(ov.z, __fmul_rn(d[k].z, f2)), 0.f, 1.f);
+      xv.w = clampf(__fadd_rn(ov.w, __fmul_rn(d[k].w, f2)), 0.f, 1.f);
+      x[img * chw4 + i] = xv;
+    }
+  }
+}
+// MI-FGSM the same way: g stays in registers across the mean|g| reduction, so the step is 6 passes (g, x, m, x0 in; x, m out)
+// instead of 7, in one launch, with a deterministic reduction.
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads, kClusterCtasPerSm)
+    mim_step_cluster_kernel(float4* __restrict__ x, float4* __restrict__ mom, const float4* __restrict__ g, const float4* __restrict__ x0,
+                            size_t chw4, float step, float eps, float decay) {
+  __shared__ float sh[33];
+  const size_t img = blockIdx.y;
+  float4 gv[kClusterVec];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kClusterVec; ++k) {
+    const size_t i = ((size_t)k * kClusterCtas + blockIdx.x) * kClusterThreads + threadIdx.x;
+    if (i < chw4) {
+      gv[k] = ld_stream_f4(g + img * chw4 + i);
+      s += fabsf(gv[k].x) + fabsf(gv[k].y) + fabsf(gv[k].z) + fabsf(gv[k].w);
+    }
+  }
+  const float mean_abs = cluster_sum_ordered(s, sh) / (float)(chw4 * 4);
+#pragma unroll
+  for (int k = 0; k < kClusterVec; ++k) {
+    const size_t i = ((size_t)k * kClusterCtas + blockIdx.x) * kClusterThreads + threadIdx.x;
+    if (i < chw4) {
+      const size_t at = img * chw4 + i;
+      float4 xv = x[at], mv = mom[at];
+      const float4 ov = ld_stream_f4(x0 + at);
+      mv.x = __fadd_rn(__fmul_rn(decay, mv.x), gv[k].x / mean_abs);
+      mv.y = __fadd_rn(__fmul_rn(decay, mv.y), gv[k].y / mean_abs);
+      mv.z = __fadd_rn(__fmul_rn(decay, mv.z), gv[k].z / mean_abs);
+      mv.w = __fadd_rn(__fmul_rn(decay, mv.w), gv[k].w / mean_abs);
+      xv.x = linf_update(xv.x, step * sgn(mv.x), ov.x, eps);
+      xv.y = linf_update(xv.y, step * sgn(mv.y), ov.y, eps);
+      xv.z = linf_update(xv.z, step * sgn(mv.z), ov.z, eps);
+      xv.w = linf_update(xv.w, step * sgn(mv.w), ov.w, eps);
+      mom[at] = mv;
+      x[at] = xv;
+    }
+  }
+}
+#endif  // __CUDACC__
+
 // MIM phase 2: m = decay*m + g/mean|g| ; x = linf_update(x, step*sign(m), x0, eps)
 __global__ void __launch_bounds__(kThreads) mim_apply_kernel(float4* __restrict__ x,
                                                               float4* __restrict__ mom,
@@ -289,6 +407,15 @@ int b200r_pgd_step_l2(float* x, const float* g, const float* x0, size_t n, size_
   B200R_CHECK_ARG(chw % 4 == 0 && n < 65536, "chw must be a multiple of 4 and n < 65536");
   if (n == 0) return B200R_OK;
   cudaStream_t s = as_stream(stream);
+#ifdef __CUDACC__
+  const bool three_kernels = getenv("B200R_L2_STEP") && !strcmp(getenv("B200R_L2_STEP"), "3k");
+  if (chw / 4 <= (size_t)kClusterCtas * kClusterThreads * kClusterVec && !three_kernels) {   // the image fits one cluster's registers
+    l2_step_cluster_kernel<<<dim3(kClusterCtas, (unsigned)n), kClusterThreads, 0, s>>>(
+        reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(x0), chw / 4, alpha, eps);
+    B200R_LAUNCH_CHECK();
+    return B200R_OK;
+  }
+#endif
   B200R_CUDA(cudaMemsetAsync(workspace, 0, 2 * n * sizeof(float), s));
   dim3 grid(slices_for(chw / 4, n), (unsigned)n);
   sample_reduce_kernel<0><<<grid, kThreads, 0, s>>>(reinterpret_cast<const float4*>(g), workspace, chw / 4);
@@ -307,6 +434,16 @@ int b200r_mim_step_linf(float* x, float* momentum, const float* g, const float* 
   B200R_CHECK_ARG(chw % 4 == 0 && n < 65536, "chw must be a multiple of 4 and n < 65536");
   if (n == 0) return B200R_OK;
   cudaStream_t s = as_stream(stream);
+#ifdef __CUDACC__
+  const bool two_kernels = getenv("B200R_MIM_STEP") && !strcmp(getenv("B200R_MIM_STEP"), "2k");
+  if (chw / 4 <= (size_t)kClusterCtas * kClusterThreads * kClusterVec && !two_kernels) {
+    mim_step_cluster_kernel<<<dim3(kClusterCtas, (unsigned)n), kClusterThreads, 0, s>>>(
+        reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(momentum), reinterpret_cast<const float4*>(g),
+        reinterpret_cast<const float4*>(x0), chw / 4, step, eps, decay);
+    B200R_LAUNCH_CHECK();
+    return B200R_OK;
+  }
+#endif
   B200R_CUDA(cudaMemsetAsync(workspace, 0, n * sizeof(float), s));
   dim3 grid(slices_for(chw / 4, n), (unsigned)n);
   sample_reduce_kernel<1><<<grid, kThreads, 0, s>>>(reinterpret_cast<const float4*>(g), workspace, chw / 4);

@@ -234,3 +234,39 @@ def test_random_start_l2_uniform_in_ball(cuda):
     z = ops.random_start_l2(torch.full((1, 3, 224, 224), 0.5, device=cuda), 1.0, seed=3).view(-1).double() - 0.5
     k = ((z - z.mean()) ** 4).mean() / z.var() ** 2
     assert abs(k.item() - 3.0) < 0.1
+
+
+@pytest.mark.parametrize("n,c,h,w", [(5, 3, 224, 224), (3, 3, 100, 100), (2, 1, 8, 8), (2, 3, 256, 256)])
+def test_cluster_step_kernels_match_the_multi_kernel_form(cuda, n, c, h, w, monkeypatch):
+    """PGD-L2 and MI-FGSM steps as ONE cluster launch per step (8 CTAs per image, the image in registers, the per-image norm reduced
+    through distributed shared memory in fixed order) against the multi-kernel form with atomics (B200R_L2_STEP=3k / B200R_MIM_STEP=2k;
+    also what an image too large for a cluster's registers takes: 3 x 256 x 256): same updates, and bit-identical from run to run."""
+    from robustart_b200 import ops
+    from oracle import attacks as OA
+    torch.manual_seed(n + h)
+    x0 = torch.rand(n, c, h, w, device=cuda)
+    g = torch.randn(n, c, h, w, device=cuda) * torch.rand(n, 1, 1, 1, device=cuda)
+    eps, alpha = 2.0, 0.4
+    fits = c * h * w // 4 <= 8 * 512 * 10               # else both settings run the multi-kernel form (atomics: not bit-reproducible)
+    outs = {}
+    for mode in ("cluster", "cluster", "3k"):
+        monkeypatch.setenv("B200R_L2_STEP", mode)
+        x = x0.clone()
+        for _ in range(3):
+            ops.pgd_step_l2_(x, g, x0, alpha, eps)
+        outs.setdefault(mode, []).append(x)
+    assert not fits or torch.equal(outs["cluster"][0], outs["cluster"][1])
+    assert (outs["cluster"][0] - outs["3k"][0]).abs().max().item() < 2e-6
+    assert OA._l2(outs["cluster"][0] - x0).max().item() <= eps * (1 + 1e-5)
+    step, decay = 0.002, 1.0
+    outs = {}
+    for mode in ("cluster", "cluster", "2k"):
+        monkeypatch.setenv("B200R_MIM_STEP", mode)
+        x, m = x0.clone(), torch.zeros_like(x0)
+        for it in range(3):
+            ops.mim_step_linf_(x, m, g * (it + 1), x0, step, 8 / 255, decay)
+        outs.setdefault(mode, []).append((x, m))
+    assert not fits or (torch.equal(outs["cluster"][0][0], outs["cluster"][1][0]) and torch.equal(outs["cluster"][0][1], outs["cluster"][1][1]))
+    ma, mb = outs["cluster"][0][1], outs["2k"][0][1]
+    assert (ma - mb).abs().max().item() < 1e-5 * mb.abs().max().item()
+    assert (outs["cluster"][0][0] != outs["2k"][0][0]).float().mean().item() < 1e-4

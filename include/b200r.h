@@ -127,11 +127,12 @@ int b200r_random_start_l2(const float* x0, float* x, size_t n, size_t chw, float
 int b200r_pgd_step_linf(float* x, const float* g, const float* x0, size_t n, size_t chw,
                         float alpha, float eps, b200r_stream_t stream);
 /* x = x + alpha*g/max(||g||_2,1e-12); d = x - x0; x = clip01(x0 + d*min(1, eps/||d||_2)) per
- * sample.  workspace: 2*n floats. */
+ * sample.  workspace: 2*n floats.  Images of up to 8*512*10*4 values (3 x 233 x 233) run as ONE launch (a cluster of 8 CTAs per
+ * image, fixed-order reductions: bit-reproducible, workspace untouched); larger ones as three kernels with atomics. */
 int b200r_pgd_step_l2(float* x, const float* g, const float* x0, size_t n, size_t chw, float alpha,
                       float eps, float* workspace, b200r_stream_t stream);
 /* MI-FGSM step (Attacks/imfgsm_attack.py:85-90): m = decay*m + g/mean|g| (per sample);
- * x = clip01(x0 + clip(x + step*sign(m) - x0, -eps, eps)).  workspace: n floats. */
+ * x = clip01(x0 + clip(x + step*sign(m) - x0, -eps, eps)).  workspace: n floats (same one-launch / fallback rule as pgd_step_l2). */
 int b200r_mim_step_linf(float* x, float* momentum, const float* g, const float* x0, size_t n,
                         size_t chw, float step, float eps, float decay, float* workspace,
                         b200r_stream_t stream);

@@ -199,6 +199,8 @@ __global__ void __launch_bounds__(kThreads) l2_project_kernel(float4* __restrict
 // (x, g, x0 in, x out) in ONE launch.
 namespace cg = cooperative_groups;
 constexpr int kClusterCtas = 8, kClusterThreads = 512, kClusterVec = 10, kClusterCtasPerSm = 2;
+// sh: one 33-float buffer per call of a kernel (a CTA may write its next partial while a slow peer still reads the previous one);
+// the caller ends with cluster_exit_sync() so that no CTA leaves while a peer can still read its shared memory
 __device__ __forceinline__ float cluster_sum_ordered(float v, float* sh /* [33] */) {
   cg::cluster_group cluster = cg::this_cluster();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -213,13 +215,13 @@ __device__ __forceinline__ float cluster_sum_ordered(float v, float* sh /* [33] 
   float tot = 0.f;
 #pragma unroll
   for (int r = 0; r < kClusterCtas; ++r) tot += *cluster.map_shared_rank(sh + 32, r);
-  cluster.sync();                                            // nobody leaves (or reuses sh) while a peer still reads it
   return tot;
 }
+__device__ __forceinline__ void cluster_exit_sync() { cg::this_cluster().sync(); }
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads, kClusterCtasPerSm)
     l2_step_cluster_kernel(float4* __restrict__ x, const float4* __restrict__ g, const float4* __restrict__ x0, size_t chw4, float alpha,
                            float eps) {
-  __shared__ float sh[33];
+  __shared__ float sh[2][33];
   const size_t img = blockIdx.y;
   // phase 1: ||g||^2 (g is read again below: an L2 hit, the cluster's image is 602 KB)
   float s0 = 0.f;
@@ -231,7 +233,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
       s0 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
   }
-  const float f = alpha * (1.0f / fmaxf(sqrtf(cluster_sum_ordered(s0, sh)), 1e-12f));
+  const float f = alpha * (1.0f / fmaxf(sqrtf(cluster_sum_ordered(s0, sh[0])), 1e-12f));
   float4 d[kClusterVec];                                    // x0 is read again in the last phase: an L2 hit (a cluster's image is 602 KB)
   float s = 0.f;
 #pragma unroll
@@ -248,7 +250,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
       s += d[k].x * d[k].x + d[k].y * d[k].y + d[k].z * d[k].z + d[k].w * d[k].w;
     }
   }
-  const float tot = cluster_sum_ordered(s, sh);
+  const float tot = cluster_sum_ordered(s, sh[1]);
   const float f2 = fminf(1.0f, eps / fmaxf(sqrtf(tot), 1e-12f));
 #pragma unroll
   for (int k = 0; k < kClusterVec; ++k) {
@@ -263,6 +265,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
       x[img * chw4 + i] = xv;
     }
   }
+  cluster_exit_sync();
 }
 // MI-FGSM the same way: g stays in registers across the mean|g| reduction, so the step is 6 passes (g, x, m, x0 in; x, m out)
 // instead of 7, in one launch, with a deterministic reduction.
@@ -301,6 +304,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
       x[at] = xv;
     }
   }
+  cluster_exit_sync();
 }
 #endif  // __CUDACC__
 

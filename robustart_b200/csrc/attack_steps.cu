@@ -20,30 +20,55 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fm
 // ---- u8 NHWC -> float NCHW, (x/255 - mean)/std -----------------------------------------------
 struct Norm3 { float mean[3], inv_std[3], std[3]; };
 
-__global__ void __launch_bounds__(kThreads) u8nhwc_to_f32nchw_kernel(const uint4* __restrict__ in,
-                                                                      float* __restrict__ out,
-                                                                      uint32_t groups_per_image,
-                                                                      uint32_t hw, Norm3 nm) {
-  const uint32_t img = blockIdx.y;
-  const uint32_t gi = blockIdx.x * kThreads + threadIdx.x;
-  if (gi >= groups_per_image) return;
-  const uint4* p = in + ((size_t)img * groups_per_image + gi) * 3;
-  uint4 a = ld_stream_u4(p), b = ld_stream_u4(p + 1), c = ld_stream_u4(p + 2);
-  uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-  float v[3][16];
-#pragma unroll
-  for (int byte = 0; byte < 48; ++byte) {
-    const int ch = byte % 3, px = byte / 3;
-    float x = (float)((w[byte >> 2] >> (8 * (byte & 3))) & 0xFFu);
+// A thread converts 16 pixels (48 bytes in, three 64-byte runs out) by table look-up: the 96 IEEE divisions per thread of the direct
+// form made the kernel ALU-bound; the 3 x 256 table is built with the same two divisions, so results stay bit-identical.  Written straight from the registers, every store instruction
+// would put 16 bytes per lane at a 64-byte stride -- half-filled 32-byte sectors, the pattern that halves a kernel's store rate --
+// so the CTA's 3 x 2048 floats go through shared memory (16-byte chunks, XOR-swizzled: conflict-free both ways) and leave as
+// 512 contiguous bytes per warp and instruction.
+constexpr int kCvtThreads = 128;
+__global__ void __launch_bounds__(kCvtThreads) u8nhwc_to_f32nchw_kernel(const uint4* __restrict__ in,
+                                                                         float* __restrict__ out,
+                                                                         uint32_t groups_per_image,
+                                                                         uint32_t hw, Norm3 nm) {
+  __shared__ float4 stg[3][kCvtThreads * 4];
+  __shared__ float lut[3][256];                             // every value a byte can become, with the reference's two true divisions
+  for (int e = threadIdx.x; e < 768; e += kCvtThreads) {
+    const int ch = e >> 8;
     // torchvision ToTensor: x/255 (true division), Normalize: (t - mean)/std
-    v[ch][px] = (__fdiv_rn(x, 255.0f) - nm.mean[ch]) / nm.std[ch];
+    lut[ch][e & 255] = (__fdiv_rn((float)(e & 255), 255.0f) - nm.mean[ch]) / nm.std[ch];
   }
+  __syncthreads();
+  const uint32_t img = blockIdx.y;
+  const uint32_t g0 = blockIdx.x * kCvtThreads, gi = g0 + threadIdx.x;
+  if (gi < groups_per_image) {
+    const uint4* p = in + ((size_t)img * groups_per_image + gi) * 3;
+    uint4 a = ld_stream_u4(p), b = ld_stream_u4(p + 1), c = ld_stream_u4(p + 2);
+    uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    float v[3][16];
+#pragma unroll
+    for (int byte = 0; byte < 48; ++byte) {
+      const int ch = byte % 3, px = byte / 3;
+      v[ch][px] = lut[ch][(w[byte >> 2] >> (8 * (byte & 3))) & 0xFFu];
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t ck = 4 * threadIdx.x + q;
+        stg[ch][ck ^ ((ck >> 3) & 7)] = make_float4(v[ch][4 * q], v[ch][4 * q + 1], v[ch][4 * q + 2], v[ch][4 * q + 3]);
+      }
+  }
+  __syncthreads();
+  const uint32_t left = groups_per_image - g0;
+  const uint32_t chunks = (left < (uint32_t)kCvtThreads ? left : (uint32_t)kCvtThreads) * 4;
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    float* o = out + ((size_t)img * 3 + ch) * hw + (size_t)gi * 16;
+    float* o = out + ((size_t)img * 3 + ch) * hw + (size_t)g0 * 16;
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      st_stream_f4(o + 4 * q, make_float4(v[ch][4 * q], v[ch][4 * q + 1], v[ch][4 * q + 2], v[ch][4 * q + 3]));
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t ck = threadIdx.x + kCvtThreads * k;
+      if (ck < chunks) st_stream_f4(o + 4 * ck, stg[ch][ck ^ ((ck >> 3) & 7)]);
+    }
   }
 }
 
@@ -356,8 +381,8 @@ int b200r_u8nhwc_to_f32nchw(const uint8_t* in, float* out, int n, int h, int w, 
   B200R_CHECK_ARG(n >= 0 && h > 0 && w > 0 && (h * w) % 16 == 0, "h*w must be a multiple of 16");
   if (n == 0) return B200R_OK;
   const uint32_t g48 = (uint32_t)(h * w) / 16;
-  dim3 grid((g48 + kThreads - 1) / kThreads, n);
-  u8nhwc_to_f32nchw_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(
+  dim3 grid((g48 + kCvtThreads - 1) / kCvtThreads, n);
+  u8nhwc_to_f32nchw_kernel<<<grid, kCvtThreads, 0, as_stream(stream)>>>(
       reinterpret_cast<const uint4*>(in), out, g48, (uint32_t)(h * w), make_norm(mean_host, std_host));
   B200R_LAUNCH_CHECK();
   return B200R_OK;

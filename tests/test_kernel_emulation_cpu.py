@@ -411,6 +411,15 @@ def test_attack_step_and_loss_kernels(emu):
         ref = (x0 + (ref + alpha * g.sign() - x0).clamp(-eps, eps)).clamp(0, 1)
         _ok(lib.b200r_pgd_step_linf(_p(x), _p(g), _p(x0), n, chw, alpha, eps, None))
     assert torch.equal(x, ref)
+    # uint8 NHWC -> normalised float32 NCHW through the swizzled shared-memory staging (full CTAs, a partial one, a single group)
+    lib.b200r_u8nhwc_to_f32nchw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    for nn, hh, ww in [(2, 48, 48), (1, 52, 44), (3, 4, 4)]:
+        img = torch.randint(0, 256, (nn, hh, ww, 3), dtype=torch.uint8)
+        out = torch.empty(nn, 3, hh, ww)
+        _ok(lib.b200r_u8nhwc_to_f32nchw(_p(img), _p(out), nn, hh, ww, _f3(mean), _f3(std), None))
+        want = ((img.permute(0, 3, 1, 2).float() / 255) - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+        assert torch.equal(out, want)
     # L2 random start: inside the ball, reproducible, streams continue across a re-batched call
     lib.b200r_random_start_l2.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float, C.c_uint64, C.c_uint64, C.c_void_p]
     half = torch.full((n, chw), 0.5)

@@ -65,6 +65,10 @@ def test_layout_and_normalize(cuda):
     # kernel multiplies by the reciprocal instead), so the bit-exact reference is the CPU computation.
     ref = ((img.cpu().permute(0, 3, 1, 2).float() / 255) - m.cpu()) / s.cpu()
     assert torch.equal(out.cpu(), ref)
+    for shape in [(2, 48, 48, 3), (1, 52, 44, 3), (3, 4, 4, 3), (2, 256, 256, 3)]:     # full CTAs, partial last CTA, a single group
+        im = torch.from_numpy(rs.randint(0, 256, size=shape, dtype=np.uint8)).to(cuda)
+        want = ((im.cpu().permute(0, 3, 1, 2).float() / 255) - m.cpu()) / s.cpu()
+        assert torch.equal(ops.u8nhwc_to_f32nchw(im).cpu(), want)
     inv = ops.normalize(out, "inv")
     assert torch.equal(inv, out * s + m)
     assert torch.equal(ops.normalize(inv, "normal"), (inv - m) / s)
